@@ -1,0 +1,79 @@
+/* prisma_b200 -- C ABI of the B200-native per-frame inference engine for PRISMA's band pipeline.
+ *
+ * The reference (patriciogonzalezvivo/prisma @ e00192dd) is pure Python and has no FFI; each entry point
+ * below replaces the body of one reference function, cited as file:line relative to the reference root.
+ * Conventions: 0 = OK, negative = error (text via prisma_last_error(), thread-local);
+ * nothing throws or exits across the ABI; the caller owns every host buffer, the engine owns device memory,
+ * streams and weights; one engine handle is not re-entrant, different handles are independent.
+ * All pointers are plain host pointers (pinned or pageable); no torch / numpy types appear here.
+ */
+#ifndef PRISMA_B200_H
+#define PRISMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct prisma_engine prisma_engine;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+const char* prisma_last_error(void);
+int prisma_device_count(void);          /* number of visible CUDA devices, or negative on error            */
+const char* prisma_version(void);
+
+/* ---- Depth-Anything band: replaces bands/depth_anything.py:init_model (:48-76) + infer (:100-143)
+ *      + the per-frame encode of process_video (:215-221)                                                  */
+/* encoder: "vits" | "vitb" | "vitl" (bands/depth_anything.py:263)                                          */
+int prisma_depth_create(const char* encoder, int device, prisma_engine** out);
+/* Weight converter input: one call per tensor of the reference state_dict of DPT_DINOv2
+ * (bands/d_anything/dpt.py:139-153; names as in SURVEY.md Appendix B), fp32, row-major, host memory.       */
+int prisma_depth_load_tensor(prisma_engine* e, const char* name, const float* data, const int64_t* shape, int ndim);
+/* Packs the tensors into kernel layouts (fp16 operands, padded K, folded q-scale) and uploads them.        */
+int prisma_depth_finalize(prisma_engine* e);
+/* One frame.  rgb: h*w*3 u8 RGB.  depth_out (h*w f32, may be NULL) = infer(img) of the reference;
+ * rgb_out (h*w*3 u8, may be NULL) = (heat_to_rgb(1 - normalised depth) * 255).astype(u8) (:215-220);
+ * min_out / max_out = the per-frame scalars written to <band>_min.csv / _max.csv (:221,231-238).
+ * Includes the H2D copy of the frame and the D2H copies of the requested outputs.                          */
+int prisma_depth_infer(prisma_engine* e, const uint8_t* rgb, int h, int w, float* depth_out, uint8_t* rgb_out,
+                       float* min_out, float* max_out);
+/* Same computation with the frame already resident in device memory and outputs left on the device
+ * (bench.py's kernel-only leg); timing of the last call in ms via CUDA events on the engine stream.        */
+int prisma_depth_infer_resident(prisma_engine* e, int h, int w, int iters, float* ms_per_iter);
+/* Encoder-only entry used by the parity tests: encode a given h*w f32 prediction (:215-220).               */
+int prisma_depth_encode(prisma_engine* e, const float* prediction, int h, int w, int flip, uint8_t* rgb_out,
+                        float* min_out, float* max_out);
+/* Intermediate tensors of the last prisma_depth_infer call as dense fp32 (tests only):
+ * "net_input" [3][hn][wn], "tokens" [T][D], "feat0".."feat3" [T][D], "net_depth" [hn][wn], ...
+ * returns the number of floats written, or negative.                                                       */
+long long prisma_depth_read_tap(prisma_engine* e, const char* name, float* out, long long capacity);
+/* Per-kernel-group CUDA-event timings of one frame (ms), for bench.py's roofline block:
+ * out[0]=pre, out[1]=encoder linear GEMMs, out[2]=attention, out[3]=layernorm, out[4]=head convs,
+ * out[5]=resamplers, out[6]=post, out[7]=total.                                                             */
+int prisma_depth_profile(prisma_engine* e, int h, int w, float* out8);
+/* Algorithmic work of one frame at (h,w): out[0]=encoder-linear FLOP, out[1]=attention FLOP, out[2]=head FLOP,
+ * out[3]=kernel launches per frame.                                                                         */
+int prisma_depth_work(prisma_engine* e, int h, int w, double* out4);
+
+int prisma_engine_destroy(prisma_engine* e);
+
+/* ---- kernel-level entry points (parity tests and micro-benchmarks call the kernels through the C ABI) ---- */
+/* D = A[M,K] * W[N,K]^T (+bias) with fp16 operands / fp32 accumulate on the tcgen05 core; A, W, D host fp32.
+ * act: 0 none, 1 gelu, 2 relu.  force_bn: 0 = auto, else 32/64/128/256.  ms_out (may be NULL): kernel time.   */
+int prisma_debug_gemm(int device, const float* A, const float* W, const float* bias, float* D, int M, int N, int K,
+                      int act, int force_bn, int iters, float* ms_out);
+/* 3x3 (kh x kw) stride-1 'same' convolution, NHWC fp32 host in/out, through the shifted-row GEMM.           */
+int prisma_debug_conv(int device, const float* x_nhwc, const float* w_oihw, const float* bias, float* y_nhwc, int H,
+                      int W, int Cin, int Cout, int kh, int kw, int relu, float* ms_out);
+/* softmax(q k^T) v per head (head_dim 64); qkv host fp32 [T][3*D] (q NOT pre-scaled; scaled inside), out [T][D] */
+int prisma_debug_attention(int device, const float* qkv, float* out, int T, int heads, int iters, float* ms_out);
+int prisma_debug_layernorm(int device, const float* x, const float* g, const float* b, float* y, int rows, int D);
+/* OpenCV-exact cubic resize + normalise (K1): rgb u8 h*w*3 -> f32 [3][hn][wn]                                */
+int prisma_debug_da_preprocess(int device, const uint8_t* rgb, int h, int w, float* out, int hn, int wn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRISMA_B200_H */

@@ -1,0 +1,128 @@
+"""Pin the oracle against the reference and write the golden fixtures (TEST INFRASTRUCTURE).
+
+Runs ONLY in the authoring container (needs /root/reference).  It
+  1. imports the reference modules read-only (PYTHONPATH=/root/reference/bands, cwd
+     /root/reference because d_anything/dpt.py:147 uses a relative torch.hub path),
+  2. loads oracle.weights' seeded state_dict into them (strict=True -> names/shapes pinned),
+  3. checks every oracle stage against the reference module's output on seeded inputs,
+  4. writes small fixtures to tests/golden/*.npz (inputs + reference outputs) that the
+     `-m "not gpu"` tests replay against the oracle and the `-m gpu` tests against CUDA.
+
+    python oracle/tools/make_golden.py            # from /root/repo
+"""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = "/root/reference"
+sys.dont_write_bytecode = True
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REF, "bands"))
+os.chdir(REF)
+
+import numpy as np
+import torch
+
+from oracle import da as oda
+from oracle.weights import make_da_weights, DA_CONFIGS
+from oracle.frames import synthetic_frame
+
+GOLD = os.path.join(REPO, "tests", "golden")
+os.makedirs(GOLD, exist_ok=True)
+torch.set_grad_enabled(False)
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def golden_da(encoder, H, W, tag):
+    from d_anything.dpt import DPT_DINOv2
+    from d_anything.util.transform import Resize, NormalizeImage, PrepareForNet
+    from torchvision.transforms import Compose
+    import cv2
+    import common.encode as renc
+
+    c = DA_CONFIGS[encoder]
+    sd = make_da_weights(encoder, seed=0)
+    ref = DPT_DINOv2(encoder, c["features"], c["out_channels"]).eval()
+    missing = ref.load_state_dict(sd, strict=True)
+    print(f"[{tag}] load_state_dict strict ok: {missing}")
+
+    img = synthetic_frame(H, W, 0)
+    # --- reference pipeline, exactly depth_anything.py:63-75,122-133,215-220
+    transform = Compose([
+        Resize(width=518, height=518, resize_target=False, keep_aspect_ratio=True, ensure_multiple_of=14,
+               resize_method='lower_bound', image_interpolation_method=cv2.INTER_CUBIC),
+        NormalizeImage(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225]),
+        PrepareForNet(),
+    ])
+    image = img / 255.0
+    x_ref = transform({'image': image})['image']
+    x_t = torch.from_numpy(x_ref).unsqueeze(0)
+    feats_ref = ref.pretrained.get_intermediate_layers(x_t, 4, return_class_token=True)
+    depth_ref = ref(x_t)
+    pred_ref = torch.nn.functional.interpolate(depth_ref[None], (H, W), mode='bilinear', align_corners=False)[0, 0].numpy()
+    dmin, dmax = pred_ref.min(), pred_ref.max()
+    dn = 1.0 - (pred_ref - dmin) / (dmax - dmin)
+    rgb_ref = (renc.heat_to_rgb(dn.astype(np.float64)) * 255).astype(np.uint8)
+
+    # --- oracle
+    x_or = oda.da_preprocess(img)
+    assert x_or.shape == x_ref.shape, (x_or.shape, x_ref.shape)
+    print(f"[{tag}] preprocess max abs diff {np.abs(x_or - x_ref).max():.3e}")
+    assert np.array_equal(x_or, x_ref)
+    taps = {}
+    depth_or = oda.da_model(sd, torch.from_numpy(x_or).unsqueeze(0), encoder, taps=taps)
+    for i in range(4):
+        e = rel(taps["feats"][i].numpy(), feats_ref[i][0].numpy())
+        print(f"[{tag}] feats[{i}] rel err {e:.3e}")
+        assert e < 1e-5
+    e = rel(depth_or.numpy(), depth_ref.numpy())
+    print(f"[{tag}] depth rel err {e:.3e}  range [{depth_ref.min():.4f},{depth_ref.max():.4f}]")
+    assert e < 1e-5
+    pred_or = oda.da_upsample(depth_or, H, W)
+    rgb_or, omin, omax = oda.da_encode(pred_or)
+    print(f"[{tag}] pred rel err {rel(pred_or, pred_ref):.3e}; rgb max diff "
+          f"{np.abs(rgb_or.astype(int) - rgb_ref.astype(int)).max()}")
+    # encode pinned on the *reference* prediction so it is independent of model rounding
+    rgb_or2, _, _ = oda.da_encode(pred_ref)
+    assert np.array_equal(rgb_or2, rgb_ref)
+
+    np.savez_compressed(
+        os.path.join(GOLD, f"da_{tag}.npz"),
+        encoder=encoder, seed=0, frame_hw=np.array([H, W]), frame_index=0,
+        net_input_s4=x_ref[:, ::4, ::4].astype(np.float32),         # every 4th pixel of the net input
+        feat3_s7=feats_ref[3][0].numpy()[0, ::7].astype(np.float32),  # every 7th token of the last tap
+        depth_s2=depth_ref.numpy()[0, ::2, ::2].astype(np.float32),  # every 2nd pixel of the net depth
+        prediction=pred_ref.astype(np.float32),
+        rgb=rgb_ref, dmin=np.float32(dmin), dmax=np.float32(dmax),
+    )
+    print(f"[{tag}] wrote fixture")
+
+
+def golden_sizes():
+    from d_anything.util.transform import Resize
+    import cv2
+    r = Resize(width=518, height=518, resize_target=False, keep_aspect_ratio=True, ensure_multiple_of=14,
+               resize_method='lower_bound', image_interpolation_method=cv2.INTER_CUBIC)
+    rows = []
+    for (w, h) in [(1920, 1080), (1280, 720), (640, 480), (934, 440), (518, 518), (500, 300), (300, 500),
+                   (1000, 1000), (4096, 2160), (321, 123)]:
+        rw, rh = r.get_size(w, h)
+        assert (int(rw), int(rh)) == oda.da_get_size(w, h), (w, h)
+        rows.append((w, h, int(rw), int(rh)))
+    np.savez(os.path.join(GOLD, "da_sizes.npz"), rows=np.array(rows))
+    print("sizes ok", rows)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["sizes", "da_small", "da_vits"]
+    if "sizes" in which:
+        golden_sizes()
+    if "da_small" in which:
+        golden_da("vits", 160, 208, "vits_160x208")   # net input 518x672 (lower_bound up-scales small frames)
+    if "da_vits" in which:
+        golden_da("vits", 480, 640, "vits_480x640")   # BASELINE config 1 stand-in

@@ -1,0 +1,251 @@
+// prisma_b200 -- ViT self-attention on tcgen05 (sm_100a): softmax(q k^T) v, non-causal, head_dim 64
+// (dinov2/layers/attention.py:49-62; the 1/sqrt(64) scale is folded into the q rows of the qkv weights, exactly).
+//
+// One CTA per (128-query tile, head, image); 2 CTAs co-reside per SM so one CTA's softmax overlaps the other's MMAs.
+//   warp 0   : TMA producer  (Q once; K/V 128x64 fp16 tiles in a 2-stage ring, 128B swizzle, straight out of the
+//                             [tokens][3*D] qkv matrix -- no head split/transposes ever materialise)
+//   warp 1   : MMA issuer    (S = Q K^T  -> TMEM cols [0,128);  O_j = P V_j -> TMEM cols [128,192), V as MN-major B)
+//   warps 2-5: softmax       (thread = query row: tcgen05.ld S, online max/sum in fp32, P -> fp16 -> swizzled smem
+//                             as the A operand of the PV MMA; O accumulated in registers with the usual rescale)
+#include "attention.cuh"
+
+namespace prisma {
+
+constexpr int ATT_BQ = 128, ATT_BKV = 128, ATT_HD = 64;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
+constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 + 2 + 2) + 1024 + 128;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ AttnArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;      // 2 stages
+  uint8_t* sV = smem + 3 * ATT_TILE_BYTES;  // 2 stages
+  uint8_t* sP = smem + 5 * ATT_TILE_BYTES;  // 2 K-slabs of [128][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint64_t* o_free = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = args.tokens, D = args.D;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int head = blockIdx.y;
+  const int row_base = blockIdx.z * T;  // first row of this image in the qkv matrix
+  const int n_kv = (T + ATT_BKV - 1) / ATT_BKV;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_2d(sQ, &tmQKV, q_full, head * ATT_HD, row_base + q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
+        tma_load_2d(sK + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], D + head * ATT_HD, row_base + j * ATT_BKV);
+        tma_load_2d(sV + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], 2 * D + head * ATT_HD, row_base + j * ATT_BKV);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);  // B (= V) is MN-major
+      const uint64_t qdesc = make_sdesc_sw128(smem_u32(sQ));
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      {
+        const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(p_full, j & 1);                 // P(j) in smem, S(j) fully read
+        if (j > 0) mbar_wait(o_free, (j - 1) & 1);  // O_tile(j-1) consumed
+        tc_fence_after();
+        const uint32_t vbase = smem_u32(sV + st * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t pdesc = make_sdesc_sw128(smem_u32(sP + (k >> 2) * ATT_TILE_BYTES)) + 2 * (k & 3);
+          const uint64_t vdesc = make_sdesc_sw128(vbase + k * 2048);
+          umma_f16(tmem_O, pdesc, vdesc, idesc_o, k != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+        if (j + 1 < n_kv) {
+          const int st1 = (j + 1) & 1;
+          mbar_wait(&kv_full[st1], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK + st1 * ATT_TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(s_full);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    float m_run = -INFINITY, l_run = 0.f;
+    float O[ATT_HD];
+#pragma unroll
+    for (int d = 0; d < ATT_HD; ++d) O[d] = 0.f;
+    uint8_t* prow = sP + r * 128;
+    const int rsw = r & 7;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int valid = min(ATT_BKV, T - j * ATT_BKV);  // >= 1
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // ---- pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < ATT_BKV; c0 += 32) {
+        if (c0 >= valid) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_sel + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 <= valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (c0 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = ex2_approx((m_run - m_new) * LOG2E);
+      const float mscaled = m_new * LOG2E;
+      // ---- pass 2: p = exp(s - m), row sum, P -> fp16 -> swizzled smem (A operand of the PV MMA)
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < ATT_BKV; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_sel + c0, v);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = ex2_approx(fmaf(__uint_as_float(v[i]), LOG2E, -mscaled));
+          p[i] = (c0 + i < valid) ? e : 0.f;
+          sum += p[i];
+        }
+        uint8_t* slab = prow + (c0 >> 6) * ATT_TILE_BYTES;
+        const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_half2(p[g * 8 + 0], p[g * 8 + 1]);
+          o.y = pack_half2(p[g * 8 + 2], p[g * 8 + 3]);
+          o.z = pack_half2(p[g * 8 + 4], p[g * 8 + 5]);
+          o.w = pack_half2(p[g * 8 + 6], p[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(slab + (((chunk0 + g) ^ rsw) << 4)) = o;
+        }
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // ---- O = O * alpha + P V_j
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld32(tmem_O + lane_sel + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) O[h * 32 + i] = fmaf(O[h * 32 + i], alpha, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+    }
+    // ---- normalise and store: out[row][head*64 + d]
+    const int q = q0 + r;
+    if (q < T) {
+      const float inv = 1.0f / l_run;
+      __half* dst = args.out + (size_t)(row_base + q) * args.out_ld + head * ATT_HD;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 o;
+        o.x = pack_half2(O[g * 8 + 0] * inv, O[g * 8 + 1] * inv);
+        o.y = pack_half2(O[g * 8 + 2] * inv, O[g * 8 + 3] * inv);
+        o.z = pack_half2(O[g * 8 + 4] * inv, O[g * 8 + 5] * inv);
+        o.w = pack_half2(O[g * 8 + 6] * inv, O[g * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + g * 8) = o;
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int attention_prepare(AttnLaunch* out, const __half* qkv, __half* o, int batch, int tokens, int heads, int D) {
+  PRISMA_CHECK(D == heads * ATT_HD, "attention: head_dim must be 64");
+  out->args.tokens = tokens;
+  out->args.heads = heads;
+  out->args.D = D;
+  out->args.batch = batch;
+  out->args.out = o;
+  out->args.out_ld = D;
+  PRISMA_TRY(make_tmap_2d_f16(&out->tm, qkv, (uint64_t)3 * D, (uint64_t)batch * tokens, (uint64_t)3 * D, 64, 128));
+  out->grid = dim3(ceil_div(tokens, ATT_BQ), heads, batch);
+  out->flops = 4.0 * batch * heads * (double)tokens * tokens * ATT_HD;
+  return 0;
+}
+
+int attention_run(const AttnLaunch& a, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PRISMA_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    attr_set = true;
+  }
+  attention_kernel<<<a.grid, ATT_THREADS, ATT_SMEM, s>>>(a.tm, a.args);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace prisma

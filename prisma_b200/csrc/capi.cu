@@ -1,0 +1,323 @@
+// prisma_b200 -- the C ABI (include/prisma_b200.h).  Nothing throws across it.
+#include "../../include/prisma_b200.h"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "engine_da.cuh"
+
+using namespace prisma;
+
+struct prisma_engine {
+  int kind;  // 1 = depth
+  DepthEngine* depth;
+};
+
+#define API_GUARD_BEGIN try {
+#define API_GUARD_END                                                   \
+  }                                                                     \
+  catch (const std::exception& ex) {                                    \
+    set_last_error(std::string("exception: ") + ex.what());             \
+    return -3;                                                          \
+  }                                                                     \
+  catch (...) {                                                         \
+    set_last_error("unknown exception");                                \
+    return -3;                                                          \
+  }
+
+// ------------------------------------------------------------------------------------------------ debug / kernel-level
+namespace {
+struct Scratch {
+  std::vector<void*> p;
+  ~Scratch() { for (void* q : p) cudaFree(q); }
+  template <typename T>
+  T* alloc(size_t n) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 256)) != cudaSuccess) return nullptr;
+    cudaMemset(q, 0, std::max<size_t>(n * sizeof(T), 256));
+    p.push_back(q);
+    return reinterpret_cast<T*>(q);
+  }
+};
+int device_sms(int device, int* sms) {
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PRISMA_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  PRISMA_CHECK(prop.major == 10, "prisma_b200 kernels are sm_100a only; there is no fallback path");
+  *sms = prop.multiProcessorCount;
+  return 0;
+}
+std::vector<__half> to_half_padded(const float* src, int rows, int cols, int rows_pad, int cols_pad) {
+  std::vector<__half> h((size_t)rows_pad * cols_pad, __float2half_rn(0.f));
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) h[(size_t)r * cols_pad + c] = __float2half_rn(src[(size_t)r * cols + c]);
+  return h;
+}
+int timed(cudaStream_t s, int iters, float* ms_out, const std::function<int()>& fn) {
+  cudaEvent_t a, b;
+  PRISMA_CUDA_OK(cudaEventCreate(&a));
+  PRISMA_CUDA_OK(cudaEventCreate(&b));
+  PRISMA_TRY(fn());  // warm
+  PRISMA_CUDA_OK(cudaEventRecord(a, s));
+  for (int i = 0; i < iters; ++i) PRISMA_TRY(fn());
+  PRISMA_CUDA_OK(cudaEventRecord(b, s));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(s));
+  float ms = 0;
+  PRISMA_CUDA_OK(cudaEventElapsedTime(&ms, a, b));
+  if (ms_out) *ms_out = ms / std::max(iters, 1);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* prisma_last_error(void) { return get_last_error(); }
+const char* prisma_version(void) { return "prisma_b200 0.1 (sm_100a)"; }
+
+int prisma_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_last_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return -2;
+  }
+  return n;
+}
+
+int prisma_depth_create(const char* encoder, int device, prisma_engine** out) {
+  API_GUARD_BEGIN
+  PRISMA_CHECK(encoder != nullptr && out != nullptr, "null argument");
+  DepthEngine* d = new DepthEngine();
+  int r = d->init(encoder, device);
+  if (r != 0) { delete d; return r; }
+  prisma_engine* e = new prisma_engine{1, d};
+  *out = e;
+  return 0;
+  API_GUARD_END
+}
+
+static DepthEngine* as_depth(prisma_engine* e) {
+  if (!e || e->kind != 1 || !e->depth) { set_last_error("not a depth engine handle"); return nullptr; }
+  return e->depth;
+}
+
+int prisma_depth_load_tensor(prisma_engine* e, const char* name, const float* data, const int64_t* shape, int ndim) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  if (!d) return -1;
+  PRISMA_CHECK(name && data && shape && ndim >= 1 && ndim <= 4, "bad tensor");
+  return d->load_tensor(name, data, shape, ndim);
+  API_GUARD_END
+}
+int prisma_depth_finalize(prisma_engine* e) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  return d ? d->finalize() : -1;
+  API_GUARD_END
+}
+int prisma_depth_infer(prisma_engine* e, const uint8_t* rgb, int h, int w, float* depth_out, uint8_t* rgb_out,
+                       float* min_out, float* max_out) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  return d ? d->infer(rgb, h, w, depth_out, rgb_out, min_out, max_out) : -1;
+  API_GUARD_END
+}
+int prisma_depth_infer_resident(prisma_engine* e, int h, int w, int iters, float* ms_per_iter) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  return d ? d->infer_resident(h, w, iters, ms_per_iter) : -1;
+  API_GUARD_END
+}
+int prisma_depth_encode(prisma_engine* e, const float* prediction, int h, int w, int flip, uint8_t* rgb_out,
+                        float* min_out, float* max_out) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  PRISMA_CHECK(prediction && rgb_out, "null argument");
+  return d ? d->encode(prediction, h, w, flip, rgb_out, min_out, max_out) : -1;
+  API_GUARD_END
+}
+long long prisma_depth_read_tap(prisma_engine* e, const char* name, float* out, long long capacity) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  return d ? d->read_tap(name, out, capacity) : -1;
+  API_GUARD_END
+}
+int prisma_depth_profile(prisma_engine* e, int h, int w, float* out8) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  return d ? d->profile(h, w, out8) : -1;
+  API_GUARD_END
+}
+int prisma_depth_work(prisma_engine* e, int h, int w, double* out4) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  if (!d) return -1;
+  PRISMA_TRY(d->build_plan(h, w));
+  out4[0] = d->work_linear;
+  out4[1] = d->work_attn;
+  out4[2] = d->work_head;
+  out4[3] = (double)d->steps.size();
+  return 0;
+  API_GUARD_END
+}
+int prisma_engine_destroy(prisma_engine* e) {
+  API_GUARD_BEGIN
+  if (!e) return 0;
+  delete e->depth;
+  delete e;
+  return 0;
+  API_GUARD_END
+}
+
+
+int prisma_debug_gemm(int device, const float* A, const float* W, const float* bias, float* Dout, int M, int N, int K,
+                      int act, int force_bn, int iters, float* ms_out) {
+  API_GUARD_BEGIN
+  int sms = 0;
+  PRISMA_TRY(device_sms(device, &sms));
+  Scratch sc;
+  const int Kp = round_up(K, 8);  // row pitch must be a multiple of 16 bytes
+  const int Kw = round_up(K, 64), Nw = round_up(N, 256);
+  auto hA = to_half_padded(A, M, K, M, Kp);
+  auto hW = to_half_padded(W, N, K, Nw, Kw);
+  __half* dA = sc.alloc<__half>(hA.size());
+  __half* dW = sc.alloc<__half>(hW.size());
+  float* dB = sc.alloc<float>(round_up(N, 8));
+  float* dD = sc.alloc<float>((size_t)M * N);
+  PRISMA_CHECK(dA && dW && dB && dD, "cudaMalloc failed");
+  PRISMA_CUDA_OK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  PRISMA_CUDA_OK(cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice));
+  if (bias) PRISMA_CUDA_OK(cudaMemcpy(dB, bias, N * 4, cudaMemcpyHostToDevice));
+  GemmEpilogue ep;
+  ep.bias = bias ? dB : nullptr;
+  ep.act = act;
+  ep.out_f32 = dD;
+  ep.out_f32_ld = N;
+  GemmLaunch g;
+  const int off[1] = {0};
+  PRISMA_TRY(gemm_prepare(&g, dA, M, K, Kp, dW, Nw, M, N, 1, off, ep, sms, force_bn));
+  PRISMA_TRY(timed(0, iters > 0 ? iters : 1, ms_out, [&]() { return gemm_run(g, 0); }));
+  PRISMA_CUDA_OK(cudaMemcpy(Dout, dD, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+  return 0;
+  API_GUARD_END
+}
+
+int prisma_debug_conv(int device, const float* x, const float* w_oihw, const float* bias, float* y, int H, int W,
+                      int Cin, int Cout, int kh, int kw, int relu, float* ms_out) {
+  API_GUARD_BEGIN
+  int sms = 0;
+  PRISMA_TRY(device_sms(device, &sms));
+  PRISMA_CHECK(Cin % 8 == 0 && Cout % 8 == 0, "conv: channels must be multiples of 8");
+  PRISMA_CHECK(kh * kw <= GEMM_MAX_TAPS && (kh & 1) && (kw & 1), "conv: odd kernel up to 7x7");
+  Scratch sc;
+  const int ph = kh / 2, pw = kw / 2;  // 'same' padding; the border must be at least that wide
+  const int Hp = H + 2 * ph, Wp = W + 2 * pw;
+  std::vector<__half> hx((size_t)Hp * Wp * Cin, __float2half_rn(0.f));
+  for (int yy = 0; yy < H; ++yy)
+    for (int xx = 0; xx < W; ++xx)
+      for (int c = 0; c < Cin; ++c)
+        hx[((size_t)(yy + ph) * Wp + xx + pw) * Cin + c] = __float2half_rn(x[((size_t)yy * W + xx) * Cin + c]);
+  const int kc = ceil_div(Cin, 64), taps = kh * kw, Kw = taps * kc * 64, Nw = round_up(Cout, 256);
+  std::vector<__half> hw((size_t)Nw * Kw, __float2half_rn(0.f));
+  for (int n = 0; n < Cout; ++n)
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < Cin; ++c)
+        hw[(size_t)n * Kw + (size_t)t * kc * 64 + c] = __float2half_rn(w_oihw[((size_t)n * Cin + c) * taps + t]);
+  __half* dx = sc.alloc<__half>(hx.size());
+  __half* dw = sc.alloc<__half>(hw.size());
+  float* db = sc.alloc<float>(round_up(Cout, 8));
+  float* dy = sc.alloc<float>((size_t)Hp * Wp * Cout);
+  PRISMA_CHECK(dx && dw && db && dy, "cudaMalloc failed");
+  PRISMA_CUDA_OK(cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
+  PRISMA_CUDA_OK(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  if (bias) PRISMA_CUDA_OK(cudaMemcpy(db, bias, Cout * 4, cudaMemcpyHostToDevice));
+  int off[GEMM_MAX_TAPS];
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) off[ky * kw + kx] = (ky - ph) * Wp + (kx - pw);
+  GemmEpilogue ep;
+  ep.bias = bias ? db : nullptr;
+  ep.act = relu ? 2 : 0;
+  ep.out_f32 = dy;
+  ep.out_f32_ld = Cout;
+  // generic border width: use LINEAR mapping and crop on the host (the engine's 3x3 path uses ROW_PADDED)
+  GemmLaunch g;
+  PRISMA_TRY(gemm_prepare(&g, dx, (long long)Hp * Wp, Cin, Cin, dw, Nw, Hp * Wp, Cout, taps, off, ep, sms, 0));
+  PRISMA_TRY(timed(0, 1, ms_out, [&]() { return gemm_run(g, 0); }));
+  std::vector<float> hy((size_t)Hp * Wp * Cout);
+  PRISMA_CUDA_OK(cudaMemcpy(hy.data(), dy, hy.size() * 4, cudaMemcpyDeviceToHost));
+  for (int yy = 0; yy < H; ++yy)
+    for (int xx = 0; xx < W; ++xx)
+      memcpy(y + ((size_t)yy * W + xx) * Cout, hy.data() + ((size_t)(yy + ph) * Wp + xx + pw) * Cout, Cout * 4);
+  return 0;
+  API_GUARD_END
+}
+
+int prisma_debug_attention(int device, const float* qkv, float* out, int T, int heads, int iters, float* ms_out) {
+  API_GUARD_BEGIN
+  int sms = 0;
+  PRISMA_TRY(device_sms(device, &sms));
+  const int D = heads * 64;
+  Scratch sc;
+  std::vector<__half> h((size_t)T * 3 * D);
+  for (int t = 0; t < T; ++t)
+    for (int c = 0; c < 3 * D; ++c)
+      h[(size_t)t * 3 * D + c] = __float2half_rn(qkv[(size_t)t * 3 * D + c] * (c < D ? 0.125f : 1.f));
+  __half* dq = sc.alloc<__half>(h.size());
+  __half* dO = sc.alloc<__half>((size_t)T * D);
+  PRISMA_CHECK(dq && dO, "cudaMalloc failed");
+  PRISMA_CUDA_OK(cudaMemcpy(dq, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  AttnLaunch a;
+  PRISMA_TRY(attention_prepare(&a, dq, dO, 1, T, heads, D));
+  PRISMA_TRY(timed(0, iters > 0 ? iters : 1, ms_out, [&]() { return attention_run(a, 0); }));
+  std::vector<__half> ho((size_t)T * D);
+  PRISMA_CUDA_OK(cudaMemcpy(ho.data(), dO, ho.size() * 2, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < ho.size(); ++i) out[i] = __half2float(ho[i]);
+  return 0;
+  API_GUARD_END
+}
+
+int prisma_debug_layernorm(int device, const float* x, const float* g, const float* b, float* y, int rows, int D) {
+  API_GUARD_BEGIN
+  int sms = 0;
+  PRISMA_TRY(device_sms(device, &sms));
+  Scratch sc;
+  float* dx = sc.alloc<float>((size_t)rows * D);
+  float* dg = sc.alloc<float>(D);
+  float* db = sc.alloc<float>(D);
+  __half* dy = sc.alloc<__half>((size_t)rows * D);
+  PRISMA_CHECK(dx && dg && db && dy, "cudaMalloc failed");
+  PRISMA_CUDA_OK(cudaMemcpy(dx, x, (size_t)rows * D * 4, cudaMemcpyHostToDevice));
+  PRISMA_CUDA_OK(cudaMemcpy(dg, g, D * 4, cudaMemcpyHostToDevice));
+  PRISMA_CUDA_OK(cudaMemcpy(db, b, D * 4, cudaMemcpyHostToDevice));
+  PRISMA_TRY(layernorm_f16(dx, dg, db, dy, rows, D, 1e-6f, 0));
+  std::vector<__half> hy((size_t)rows * D);
+  PRISMA_CUDA_OK(cudaMemcpy(hy.data(), dy, hy.size() * 2, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < hy.size(); ++i) y[i] = __half2float(hy[i]);
+  return 0;
+  API_GUARD_END
+}
+
+int prisma_debug_da_preprocess(int device, const uint8_t* rgb, int h, int w, float* out, int hn, int wn) {
+  API_GUARD_BEGIN
+  int sms = 0;
+  PRISMA_TRY(device_sms(device, &sms));
+  int ewn, ehn;
+  da_net_size(w, h, &ewn, &ehn);
+  PRISMA_CHECK(ewn == wn && ehn == hn, "net size mismatch: expected " + std::to_string(ewn) + "x" + std::to_string(ehn));
+  Scratch sc;
+  uint8_t* di = sc.alloc<uint8_t>((size_t)h * w * 3);
+  float* dout = sc.alloc<float>((size_t)3 * hn * wn);
+  PRISMA_CHECK(di && dout, "cudaMalloc failed");
+  PRISMA_CUDA_OK(cudaMemcpy(di, rgb, (size_t)h * w * 3, cudaMemcpyHostToDevice));
+  PRISMA_TRY(da_preprocess(di, h, w, dout, hn, wn, 0));
+  PRISMA_CUDA_OK(cudaMemcpy(out, dout, (size_t)3 * hn * wn * 4, cudaMemcpyDeviceToHost));
+  return 0;
+  API_GUARD_END
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

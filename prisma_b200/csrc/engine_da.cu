@@ -1,0 +1,609 @@
+// prisma_b200 -- Depth-Anything engine: weights -> kernel layouts, per-resolution launch plan, per-frame run.
+//
+// Replaces DPT_DINOv2.forward (bands/d_anything/dpt.py:155-166) and the pre/post-processing around it in
+// bands/depth_anything.py:100-143,215-221 with the sm_100a kernels of this directory.  Data layout in HBM:
+//   * residual stream x            fp32 [T][D]            (T = 1 + ph*pw tokens)
+//   * every GEMM operand           fp16, K contiguous     (LayerNorm output, qkv, attention output, MLP hidden)
+//   * DPT feature maps             fp16 NHWC with a one-pixel zero border, pixels flattened to rows, so a 3x3
+//                                  conv is nine row-shifted GEMM slabs of the same 2-D TMA descriptor
+//   * weights                      fp16 [N_pad][taps * ceil64(Cin)], biases / LayerScale / LayerNorm fp32
+#include "engine_da.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+#include <cstring>
+
+namespace prisma {
+
+// ------------------------------------------------------------------------------------------------ helpers
+struct DaCfg { int D, depth, heads, F, oc[4]; };
+static bool da_cfg(const std::string& enc, DaCfg* c) {
+  if (enc == "vits") { *c = {384, 12, 6, 64, {48, 96, 192, 384}}; return true; }
+  if (enc == "vitb") { *c = {768, 12, 12, 128, {96, 192, 384, 768}}; return true; }
+  if (enc == "vitl") { *c = {1024, 24, 16, 256, {256, 512, 1024, 1024}}; return true; }
+  return false;
+}
+
+// Resize.get_size, lower_bound / keep_aspect_ratio / multiple of 14 (d_anything/util/transform.py:111-166).
+// np.round is round-half-even == nearbyint in the default rounding mode.
+void da_net_size(int W, int H, int* wn, int* hn) {
+  double sh = 518.0 / H, sw = 518.0 / W;
+  if (sw > sh) sh = sw; else sw = sh;
+  auto constrain = [](double x) {
+    int y = (int)(nearbyint(x / 14.0) * 14.0);
+    if (y < 518) y = (int)(ceil(x / 14.0) * 14.0);
+    return y;
+  };
+  *hn = constrain(sh * H);
+  *wn = constrain(sw * W);
+}
+
+DepthEngine::~DepthEngine() {
+  cudaSetDevice(device);
+  for (void* p : allocs) cudaFree(p);
+  for (void* p : plan_allocs) cudaFree(p);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+template <typename T>
+static int dev_alloc(std::vector<void*>& pool, T** out, size_t n, bool zero = true) {
+  void* p = nullptr;
+  PRISMA_CUDA_OK(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 256)));
+  if (zero) PRISMA_CUDA_OK(cudaMemset(p, 0, std::max<size_t>(n * sizeof(T), 256)));
+  pool.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+
+int DepthEngine::init(const std::string& enc, int dev) {
+  DaCfg c;
+  PRISMA_CHECK(da_cfg(enc, &c), "unknown encoder '" + enc + "' (vits|vitb|vitl)");
+  encoder = enc;
+  D = c.D; depth = c.depth; heads = c.heads; F = c.F;
+  for (int i = 0; i < 4; ++i) oc[i] = c.oc[i];
+  device = dev;
+  int n = 0;
+  PRISMA_CUDA_OK(cudaGetDeviceCount(&n));
+  PRISMA_CHECK(dev >= 0 && dev < n, "bad device ordinal");
+  PRISMA_CUDA_OK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  PRISMA_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  PRISMA_CHECK(prop.major == 10, "prisma_b200 kernels are sm_100a only (found sm_" + std::to_string(prop.major) +
+                                     std::to_string(prop.minor) + "); there is no fallback path");
+  num_sms = prop.multiProcessorCount;
+  PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  PRISMA_CUDA_OK(cudaEventCreate(&ev0));
+  PRISMA_CUDA_OK(cudaEventCreate(&ev1));
+  return 0;
+}
+
+int DepthEngine::load_tensor(const std::string& name, const float* data, const int64_t* shape, int ndim) {
+  PRISMA_CHECK(!finalized, "load_tensor after finalize");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(data, data + n);
+  host[name] = std::move(t);
+  return 0;
+}
+
+const HostTensor* DepthEngine::get(const std::string& name, std::initializer_list<int64_t> shape) {
+  auto it = host.find(name);
+  if (it == host.end()) { set_last_error("missing weight tensor '" + name + "'"); return nullptr; }
+  if (shape.size()) {
+    std::vector<int64_t> s(shape);
+    if (s != it->second.shape) { set_last_error("weight tensor '" + name + "' has an unexpected shape"); return nullptr; }
+  }
+  return &it->second;
+}
+
+int DepthEngine::up_f32(const std::string& name, std::initializer_list<int64_t> shape, float** out, float scale_first_rows,
+                        int n_scaled) {
+  const HostTensor* t = get(name, shape);
+  if (!t) return -1;
+  std::vector<float> tmp(t->data);
+  for (int i = 0; i < n_scaled && i < (int)tmp.size(); ++i) tmp[i] *= scale_first_rows;
+  // pad to a multiple of 8 floats so vectorised epilogue loads never run off the end
+  tmp.resize(round_up((int)tmp.size(), 8), 0.f);
+  PRISMA_TRY(dev_alloc(allocs, out, tmp.size(), false));
+  PRISMA_CUDA_OK(cudaMemcpy(*out, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// fp16 [round_up(N,256)][Kpad] from a host fp32 functor w(n, k)
+template <typename Fn>
+static int up_matrix(std::vector<void*>& pool, __half** out, int N, int Kpad, Fn fn) {
+  const int rows = round_up(N, 256);
+  std::vector<__half> h((size_t)rows * Kpad, __float2half_rn(0.f));
+  for (int n = 0; n < N; ++n) fn(n, h.data() + (size_t)n * Kpad);
+  PRISMA_TRY(dev_alloc(pool, out, h.size(), false));
+  PRISMA_CUDA_OK(cudaMemcpy(*out, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int DepthEngine::up_linear(const std::string& name, int N, int K, __half** out, float scale, int n_scaled) {
+  const HostTensor* t = get(name, {N, K});
+  if (!t) return -1;
+  const int Kpad = round_up(K, 64);
+  return up_matrix(allocs, out, N, Kpad, [&](int n, __half* row) {
+    const float s = n < n_scaled ? scale : 1.f;
+    for (int k = 0; k < K; ++k) row[k] = __float2half_rn(t->data[(size_t)n * K + k] * s);
+  });
+}
+
+int DepthEngine::up_conv(const std::string& name, int Cout, int Cin, int kh, int kw, __half** out) {
+  const HostTensor* t = get(name, {Cout, Cin, kh, kw});
+  if (!t) return -1;
+  const int kc = ceil_div(Cin, 64), taps = kh * kw;
+  return up_matrix(allocs, out, Cout, taps * kc * 64, [&](int n, __half* row) {
+    for (int tp = 0; tp < taps; ++tp)
+      for (int c = 0; c < Cin; ++c)
+        row[(size_t)tp * kc * 64 + c] = __float2half_rn(t->data[((size_t)n * Cin + c) * taps + tp]);
+  });
+}
+
+// ConvTranspose2d weight [Cin][Cout][s][s], kernel == stride: B[(dy*s+dx)*Cout + co][ci]
+int DepthEngine::up_convT(const std::string& name, int Cin, int Cout, int s, __half** out, float** bias_out) {
+  const HostTensor* t = get(name + ".weight", {Cin, Cout, s, s});
+  const HostTensor* b = get(name + ".bias", {Cout});
+  if (!t || !b) return -1;
+  const int N = s * s * Cout, Kpad = round_up(Cin, 64);
+  PRISMA_TRY(up_matrix(allocs, out, N, Kpad, [&](int n, __half* row) {
+    const int q = n / Cout, co = n % Cout, dy = q / s, dx = q % s;
+    for (int ci = 0; ci < Cin; ++ci)
+      row[ci] = __float2half_rn(t->data[(((size_t)ci * Cout + co) * s + dy) * s + dx]);
+  }));
+  std::vector<float> be(round_up(N, 8), 0.f);
+  for (int n = 0; n < N; ++n) be[n] = b->data[n % Cout];
+  PRISMA_TRY(dev_alloc(allocs, bias_out, be.size(), false));
+  PRISMA_CUDA_OK(cudaMemcpy(*bias_out, be.data(), be.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int DepthEngine::finalize() {
+  PRISMA_CHECK(!finalized, "finalize called twice");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  const std::string p = "pretrained.";
+  PRISMA_TRY(up_f32(p + "cls_token", {1, 1, D}, &w.cls));
+  PRISMA_TRY(up_f32(p + "pos_embed", {1, 1370, D}, &w.pos));
+  {
+    const HostTensor* t = get(p + "patch_embed.proj.weight", {D, 3, 14, 14});
+    if (!t) return -1;
+    PRISMA_TRY(up_matrix(allocs, &w.patch_w, D, 640, [&](int n, __half* row) {
+      for (int k = 0; k < 588; ++k) row[k] = __float2half_rn(t->data[(size_t)n * 588 + k]);
+    }));
+    PRISMA_TRY(up_f32(p + "patch_embed.proj.bias", {D}, &w.patch_b));
+  }
+  w.blk.resize(depth);
+  const float qscale = 0.125f;  // head_dim^-0.5, head_dim == 64 for every DINOv2 variant (attention.py:41-42)
+  for (int i = 0; i < depth; ++i) {
+    const std::string b = p + "blocks." + std::to_string(i) + ".";
+    BlockW& k = w.blk[i];
+    PRISMA_TRY(up_f32(b + "norm1.weight", {D}, &k.n1w));
+    PRISMA_TRY(up_f32(b + "norm1.bias", {D}, &k.n1b));
+    PRISMA_TRY(up_linear(b + "attn.qkv.weight", 3 * D, D, &k.qkv_w, qscale, D));
+    PRISMA_TRY(up_f32(b + "attn.qkv.bias", {3 * D}, &k.qkv_b, qscale, D));
+    PRISMA_TRY(up_linear(b + "attn.proj.weight", D, D, &k.proj_w));
+    PRISMA_TRY(up_f32(b + "attn.proj.bias", {D}, &k.proj_b));
+    PRISMA_TRY(up_f32(b + "ls1.gamma", {D}, &k.g1));
+    PRISMA_TRY(up_f32(b + "norm2.weight", {D}, &k.n2w));
+    PRISMA_TRY(up_f32(b + "norm2.bias", {D}, &k.n2b));
+    PRISMA_TRY(up_linear(b + "mlp.fc1.weight", 4 * D, D, &k.fc1_w));
+    PRISMA_TRY(up_f32(b + "mlp.fc1.bias", {4 * D}, &k.fc1_b));
+    PRISMA_TRY(up_linear(b + "mlp.fc2.weight", D, 4 * D, &k.fc2_w));
+    PRISMA_TRY(up_f32(b + "mlp.fc2.bias", {D}, &k.fc2_b));
+    PRISMA_TRY(up_f32(b + "ls2.gamma", {D}, &k.g2));
+  }
+  PRISMA_TRY(up_f32(p + "norm.weight", {D}, &w.nw));
+  PRISMA_TRY(up_f32(p + "norm.bias", {D}, &w.nb));
+
+  const std::string h = "depth_head.";
+  for (int i = 0; i < 4; ++i) {
+    const std::string n = h + "projects." + std::to_string(i);
+    const HostTensor* t = get(n + ".weight", {oc[i], D, 1, 1});
+    if (!t) return -1;
+    const int K = D, N = oc[i];
+    PRISMA_TRY(up_matrix(allocs, &w.proj_w[i], N, round_up(K, 64), [&](int r, __half* row) {
+      for (int k = 0; k < K; ++k) row[k] = __float2half_rn(t->data[(size_t)r * K + k]);
+    }));
+    PRISMA_TRY(up_f32(n + ".bias", {oc[i]}, &w.proj_b[i]));
+  }
+  PRISMA_TRY(up_convT(h + "resize_layers.0", oc[0], oc[0], 4, &w.rs0_w, &w.rs0_b));
+  PRISMA_TRY(up_convT(h + "resize_layers.1", oc[1], oc[1], 2, &w.rs1_w, &w.rs1_b));
+  PRISMA_TRY(up_conv(h + "resize_layers.3.weight", oc[3], oc[3], 3, 3, &w.rs3_w));
+  PRISMA_TRY(up_f32(h + "resize_layers.3.bias", {oc[3]}, &w.rs3_b));
+  const std::string s = h + "scratch.";
+  for (int i = 0; i < 4; ++i)
+    PRISMA_TRY(up_conv(s + "layer" + std::to_string(i + 1) + "_rn.weight", F, oc[i], 3, 3, &w.rn_w[i]));
+  for (int i = 0; i < 4; ++i) {
+    const std::string r = s + "refinenet" + std::to_string(i + 1) + ".";
+    RefineW& k = w.ref[i];
+    {
+      const HostTensor* t = get(r + "out_conv.weight", {F, F, 1, 1});
+      if (!t) return -1;
+      PRISMA_TRY(up_matrix(allocs, &k.out_w, F, round_up(F, 64), [&](int n, __half* row) {
+        for (int c = 0; c < F; ++c) row[c] = __float2half_rn(t->data[(size_t)n * F + c]);
+      }));
+      PRISMA_TRY(up_f32(r + "out_conv.bias", {F}, &k.out_b));
+    }
+    for (int u = 0; u < 2; ++u) {
+      if (i == 3 && u == 0) continue;  // refinenet4.resConfUnit1 exists but is never used (dpt.py:127)
+      const std::string ru = r + "resConfUnit" + std::to_string(u + 1) + ".";
+      PRISMA_TRY(up_conv(ru + "conv1.weight", F, F, 3, 3, &k.c1_w[u]));
+      PRISMA_TRY(up_f32(ru + "conv1.bias", {F}, &k.c1_b[u]));
+      PRISMA_TRY(up_conv(ru + "conv2.weight", F, F, 3, 3, &k.c2_w[u]));
+      PRISMA_TRY(up_f32(ru + "conv2.bias", {F}, &k.c2_b[u]));
+    }
+  }
+  PRISMA_TRY(up_conv(s + "output_conv1.weight", F / 2, F, 3, 3, &w.oc1_w));
+  PRISMA_TRY(up_f32(s + "output_conv1.bias", {F / 2}, &w.oc1_b));
+  PRISMA_TRY(up_conv(s + "output_conv2.0.weight", 32, F / 2, 3, 3, &w.oc2_w));
+  PRISMA_TRY(up_f32(s + "output_conv2.0.bias", {32}, &w.oc2_b));
+  PRISMA_TRY(up_f32(s + "output_conv2.2.weight", {1, 32, 1, 1}, &w.oc3_w));
+  {
+    const HostTensor* t = get(s + "output_conv2.2.bias", {1});
+    if (!t) return -1;
+    w.oc3_b = t->data[0];
+  }
+  host.clear();
+  finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+struct PMap {  // zero-bordered NHWC fp16 feature map
+  __half* p = nullptr;
+  int H = 0, W = 0, C = 0;
+  int Hp() const { return H + 2; }
+  int Wp() const { return W + 2; }
+  long long rows() const { return (long long)Hp() * Wp(); }
+};
+
+int DepthEngine::new_map(PMap* m, int H, int W, int C) {
+  m->H = H; m->W = W; m->C = C;
+  // +GEMM_BM rows of slack: TMA boxes never need it (OOB reads are zero-filled) but debug reads may
+  return dev_alloc(plan_allocs, &m->p, (size_t)m->rows() * C, true);
+}
+
+void DepthEngine::add(int group, const char* name, std::function<int(cudaStream_t)> fn) {
+  steps.push_back({group, name, std::move(fn)});
+}
+
+int DepthEngine::add_gemm(int group, const char* name, const __half* A, long long a_rows, int a_cols, int a_pitch,
+                          const __half* W, int M, int N, int taps, const int* tap_off, const GemmEpilogue& ep,
+                          double flops) {
+  GemmLaunch g;
+  PRISMA_TRY(gemm_prepare(&g, A, a_rows, a_cols, a_pitch, W, round_up(N, 256), M, N, taps, tap_off, ep, num_sms));
+  if (group == G_LINEAR) work_linear += flops; else work_head += flops;
+  add(group, name, [g](cudaStream_t s) { return gemm_run(g, s); });
+  return 0;
+}
+
+// 3x3 stride-1 'same' conv on a padded map, output in the same padded geometry (or subsampled by `sub`)
+int DepthEngine::add_conv3x3(const char* name, const PMap& in, const __half* W, int Cout, GemmEpilogue ep, int sub,
+                             const PMap* out_geom) {
+  int off[9];
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky - 1) * in.Wp() + (kx - 1);
+  ep.row_map = ROW_PADDED;
+  ep.in_w = in.Wp();
+  ep.in_h = in.Hp();
+  ep.sub = sub;
+  if (sub > 1) { ep.out_wp = out_geom->Wp(); ep.out_img_rows = (int)out_geom->rows(); }
+  const double flops = 2.0 * (double)(in.H / sub + (in.H % sub ? 1 : 0)) * (in.W / sub + (in.W % sub ? 1 : 0)) * 9.0 * in.C * Cout;
+  return add_gemm(G_HEAD, name, in.p, in.rows(), in.C, in.C, W, (int)in.rows(), Cout, 9, off, ep, flops);
+}
+
+int DepthEngine::build_plan(int H, int W) {
+  PRISMA_CHECK(finalized, "weights not finalized");
+  if (plan_H == H && plan_W == W) return 0;
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  for (void* q : plan_allocs) cudaFree(q);
+  plan_allocs.clear();
+  steps.clear();
+  taps.clear();
+  work_linear = work_attn = work_head = 0;
+  plan_H = plan_W = 0;
+
+  da_net_size(W, H, &wn, &hn);
+  ph = hn / 14; pw = wn / 14;
+  const int P = ph * pw;
+  T = P + 1;
+  const int zero_off[1] = {0};
+
+  // ---- frame-level buffers
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.img, (size_t)H * W * 3));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.net_in, (size_t)3 * hn * wn));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.patches, (size_t)P * 640));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.pos, (size_t)T * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.x, (size_t)T * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.tokens_tap, (size_t)T * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.ln, (size_t)T * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.qkv, (size_t)T * 3 * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.attn, (size_t)T * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.hid, (size_t)T * 4 * D));
+  for (int i = 0; i < 4; ++i) PRISMA_TRY(dev_alloc(plan_allocs, &b.feat[i], (size_t)T * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.depth, (size_t)hn * wn));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.pred, (size_t)H * W));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.rgb, (size_t)H * W * 3));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.mm, 2));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.minmax, 2));
+
+  // pos-embed for this resolution (constant per resolution): computed once, here
+  PRISMA_TRY(da_pos_embed(w.pos, w.cls, 37, D, ph, pw, b.pos, stream));
+
+  // ---- pre-process + patch embed
+  {
+    const uint8_t* img = b.img; float* net = b.net_in; __half* pat = b.patches;
+    const int hn_ = hn, wn_ = wn;
+    add(G_PRE, "da_preprocess", [=](cudaStream_t s) { return da_preprocess(img, H, W, net, hn_, wn_, s); });
+    add(G_PRE, "patchify", [=](cudaStream_t s) { return da_patchify(net, hn_, wn_, pat, 640, s); });
+    GemmEpilogue ep;
+    ep.bias = w.patch_b;
+    ep.res_f32 = b.pos + D; ep.res_f32_ld = D;   // + pos-embed of patch tokens
+    ep.out_f32 = b.x + D; ep.out_f32_ld = D;      // token rows 1..P
+    PRISMA_TRY(add_gemm(G_LINEAR, "patch_embed", b.patches, P, 640, 640, w.patch_w, P, D, 1, zero_off, ep,
+                        2.0 * P * D * 588.0));
+    float* x = b.x; const float* pos = b.pos; const int D_ = D;
+    add(G_PRE, "cls_row", [=](cudaStream_t s) {
+      PRISMA_CUDA_OK(cudaMemcpyAsync(x, pos, D_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      return 0;
+    });
+    if (debug_taps) {
+      float* tap = b.tokens_tap; const size_t n = (size_t)T * D;
+      add(G_PRE, "tap_tokens", [=](cudaStream_t s) {
+        PRISMA_CUDA_OK(cudaMemcpyAsync(tap, x, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        return 0;
+      });
+    }
+  }
+  // ---- transformer blocks
+  AttnLaunch att;
+  PRISMA_TRY(attention_prepare(&att, b.qkv, b.attn, 1, T, heads, D));
+  for (int i = 0; i < depth; ++i) {
+    const BlockW& k = w.blk[i];
+    const float* x = b.x; __half* ln = b.ln; const int T_ = T, D_ = D;
+    add(G_LN, "ln1", [=](cudaStream_t s) { return layernorm_f16(x, k.n1w, k.n1b, ln, T_, D_, 1e-6f, s); });
+    { GemmEpilogue ep; ep.bias = k.qkv_b; ep.out_f16 = b.qkv; ep.out_f16_ld = 3 * D;
+      PRISMA_TRY(add_gemm(G_LINEAR, "qkv", b.ln, T, D, D, k.qkv_w, T, 3 * D, 1, zero_off, ep, 2.0 * T * 3.0 * D * D)); }
+    work_attn += att.flops;
+    add(G_ATTN, "attention", [att](cudaStream_t s) { return attention_run(att, s); });
+    { GemmEpilogue ep; ep.bias = k.proj_b; ep.gamma = k.g1; ep.res_f32 = b.x; ep.res_f32_ld = D; ep.out_f32 = b.x; ep.out_f32_ld = D;
+      PRISMA_TRY(add_gemm(G_LINEAR, "proj", b.attn, T, D, D, k.proj_w, T, D, 1, zero_off, ep, 2.0 * T * (double)D * D)); }
+    add(G_LN, "ln2", [=](cudaStream_t s) { return layernorm_f16(x, k.n2w, k.n2b, ln, T_, D_, 1e-6f, s); });
+    { GemmEpilogue ep; ep.bias = k.fc1_b; ep.act = 1; ep.out_f16 = b.hid; ep.out_f16_ld = 4 * D;
+      PRISMA_TRY(add_gemm(G_LINEAR, "fc1", b.ln, T, D, D, k.fc1_w, T, 4 * D, 1, zero_off, ep, 2.0 * T * 4.0 * D * D)); }
+    { GemmEpilogue ep; ep.bias = k.fc2_b; ep.gamma = k.g2; ep.res_f32 = b.x; ep.res_f32_ld = D; ep.out_f32 = b.x; ep.out_f32_ld = D;
+      PRISMA_TRY(add_gemm(G_LINEAR, "fc2", b.hid, T, 4 * D, 4 * D, k.fc2_w, T, D, 1, zero_off, ep, 2.0 * T * 4.0 * D * D)); }
+    if (i >= depth - 4) {
+      __half* f = b.feat[i - (depth - 4)];
+      const float* nw = w.nw; const float* nb = w.nb;
+      add(G_LN, "ln_out", [=](cudaStream_t s) { return layernorm_f16(x, nw, nb, f, T_, D_, 1e-6f, s); });
+    }
+  }
+
+  // ---- DPT head (dpt.py:103-136), all maps zero-bordered NHWC fp16
+  PMap L[4], R[4], Rr[4];
+  const int h4 = (ph - 1) / 2 + 1, w4 = (pw - 1) / 2 + 1;
+  PRISMA_TRY(new_map(&L[0], 4 * ph, 4 * pw, oc[0]));
+  PRISMA_TRY(new_map(&L[1], 2 * ph, 2 * pw, oc[1]));
+  PRISMA_TRY(new_map(&L[2], ph, pw, oc[2]));
+  PRISMA_TRY(new_map(&L[3], h4, w4, oc[3]));
+  PMap L3pre;
+  PRISMA_TRY(new_map(&L3pre, ph, pw, oc[3]));
+  for (int i = 0; i < 4; ++i) {
+    PRISMA_TRY(new_map(&R[i], L[i].H, L[i].W, F));
+    PRISMA_TRY(new_map(&Rr[i], L[i].H, L[i].W, F));
+  }
+  // projects (1x1 conv on tokens = GEMM over the patch tokens, cls dropped) + resize layers
+  for (int i = 0; i < 4; ++i) {
+    const __half* A = b.feat[i] + D;  // skip the cls row (use_clstoken=False, dpt.py:110-111)
+    if (i < 2) {
+      __half* dense = nullptr;
+      PRISMA_TRY(dev_alloc(plan_allocs, &dense, (size_t)P * oc[i]));
+      { GemmEpilogue ep; ep.bias = w.proj_b[i]; ep.out_f16 = dense; ep.out_f16_ld = oc[i];
+        PRISMA_TRY(add_gemm(G_HEAD, "project", A, P, D, D, w.proj_w[i], P, oc[i], 1, zero_off, ep, 2.0 * P * (double)D * oc[i])); }
+      const int s = i == 0 ? 4 : 2;
+      GemmEpilogue ep;
+      ep.bias = i == 0 ? w.rs0_b : w.rs1_b;
+      ep.out_f16 = L[i].p; ep.out_f16_ld = oc[i];
+      ep.row_map = ROW_SHUFFLE; ep.in_w = pw; ep.in_h = ph; ep.out_wp = L[i].Wp(); ep.out_img_rows = (int)L[i].rows();
+      ep.shuf_s = s; ep.shuf_cout = oc[i];
+      PRISMA_TRY(add_gemm(G_HEAD, "resize_convT", dense, P, oc[i], oc[i], i == 0 ? w.rs0_w : w.rs1_w, P, s * s * oc[i], 1,
+                          zero_off, ep, 2.0 * P * (double)oc[i] * s * s * oc[i]));
+    } else {
+      const PMap& dst = i == 2 ? L[2] : L3pre;
+      GemmEpilogue ep; ep.bias = w.proj_b[i]; ep.out_f16 = dst.p; ep.out_f16_ld = oc[i];
+      ep.row_map = ROW_TOK2PAD; ep.in_w = pw; ep.in_h = ph; ep.out_wp = dst.Wp(); ep.out_img_rows = (int)dst.rows();
+      PRISMA_TRY(add_gemm(G_HEAD, "project", A, P, D, D, w.proj_w[i], P, oc[i], 1, zero_off, ep, 2.0 * P * (double)D * oc[i]));
+    }
+  }
+  { GemmEpilogue ep; ep.bias = w.rs3_b; ep.out_f16 = L[3].p; ep.out_f16_ld = oc[3];
+    PRISMA_TRY(add_conv3x3("resize_conv_s2", L3pre, w.rs3_w, oc[3], ep, 2, &L[3])); }
+  // layerN_rn: 3x3, no bias; write x and relu(x) (the RCUs take relu(x) as operand and x as skip)
+  for (int i = 0; i < 4; ++i) {
+    GemmEpilogue ep; ep.out_f16 = R[i].p; ep.out_f16_ld = F; ep.out_f16_relu = Rr[i].p; ep.out_f16_relu_ld = F;
+    PRISMA_TRY(add_conv3x3("layer_rn", L[i], w.rn_w[i], F, ep, 1, nullptr));
+  }
+  // refinenet4..1 (blocks.py:126-153).  The 1x1 out_conv commutes with the bilinear resize (both linear, the
+  // interpolation weights sum to 1), so it runs before the resize on 4x fewer pixels.
+  PMap path;  // output of the previous fusion block (already resized to this level)
+  for (int lvl = 3; lvl >= 0; --lvl) {
+    const RefineW& k = w.ref[lvl];
+    PMap t1, S, Sr, U, V;
+    PRISMA_TRY(new_map(&t1, R[lvl].H, R[lvl].W, F));
+    PRISMA_TRY(new_map(&U, R[lvl].H, R[lvl].W, F));
+    PRISMA_TRY(new_map(&V, R[lvl].H, R[lvl].W, F));
+    const PMap* in = &R[lvl];
+    const PMap* in_relu = &Rr[lvl];
+    if (lvl != 3) {
+      // output = path + RCU1(R) ; RCU1(R) = conv2(relu(conv1(relu(R)))) + R
+      PRISMA_TRY(new_map(&S, R[lvl].H, R[lvl].W, F));
+      PRISMA_TRY(new_map(&Sr, R[lvl].H, R[lvl].W, F));
+      { GemmEpilogue ep; ep.bias = k.c1_b[0]; ep.act = 2; ep.out_f16 = t1.p; ep.out_f16_ld = F;
+        PRISMA_TRY(add_conv3x3("rcu1_conv1", Rr[lvl], k.c1_w[0], F, ep, 1, nullptr)); }
+      { GemmEpilogue ep; ep.bias = k.c2_b[0]; ep.res_a = R[lvl].p; ep.res_a_ld = F; ep.res_b = path.p; ep.res_b_ld = F;
+        ep.out_f16 = S.p; ep.out_f16_ld = F; ep.out_f16_relu = Sr.p; ep.out_f16_relu_ld = F;
+        PRISMA_TRY(add_conv3x3("rcu1_conv2", t1, k.c2_w[0], F, ep, 1, nullptr)); }
+      in = &S; in_relu = &Sr;
+    }
+    { GemmEpilogue ep; ep.bias = k.c1_b[1]; ep.act = 2; ep.out_f16 = t1.p; ep.out_f16_ld = F;
+      PRISMA_TRY(add_conv3x3("rcu2_conv1", *in_relu, k.c1_w[1], F, ep, 1, nullptr)); }
+    { GemmEpilogue ep; ep.bias = k.c2_b[1]; ep.res_a = in->p; ep.res_a_ld = F; ep.out_f16 = U.p; ep.out_f16_ld = F;
+      PRISMA_TRY(add_conv3x3("rcu2_conv2", t1, k.c2_w[1], F, ep, 1, nullptr)); }
+    { GemmEpilogue ep; ep.bias = k.out_b; ep.out_f16 = V.p; ep.out_f16_ld = F;
+      ep.row_map = ROW_PADDED; ep.in_w = U.Wp(); ep.in_h = U.Hp();
+      PRISMA_TRY(add_gemm(G_HEAD, "out_conv1x1", U.p, U.rows(), F, F, k.out_w, (int)U.rows(), F, 1, zero_off, ep,
+                          2.0 * U.H * (double)U.W * F * F)); }
+    const int oh = lvl > 0 ? R[lvl - 1].H : 2 * R[0].H, ow = lvl > 0 ? R[lvl - 1].W : 2 * R[0].W;
+    PMap nxt;
+    PRISMA_TRY(new_map(&nxt, oh, ow, F));
+    { const __half* src = V.p; __half* dst = nxt.p; const int ih = V.H, iw = V.W, C = F;
+      add(G_RESAMPLE, "upsample_ac", [=](cudaStream_t s) { return upsample_ac_f16(src, ih, iw, C, dst, oh, ow, nullptr, s); }); }
+    path = nxt;
+    if (lvl == 0) taps["path1"] = {path.p, path.H, path.W, path.C, 1};
+  }
+  // output_conv1 (3x3 F -> F/2) ; bilinear(align_corners=True) to (14ph,14pw) ; output_conv2 (3x3 -> 32, ReLU, 1x1 -> 1, ReLU)
+  PMap O1, O1u;
+  PRISMA_TRY(new_map(&O1, path.H, path.W, F / 2));
+  PRISMA_TRY(new_map(&O1u, hn, wn, F / 2));
+  { GemmEpilogue ep; ep.bias = w.oc1_b; ep.out_f16 = O1.p; ep.out_f16_ld = F / 2;
+    PRISMA_TRY(add_conv3x3("output_conv1", path, w.oc1_w, F / 2, ep, 1, nullptr)); }
+  { const __half* src = O1.p; __half* dst = O1u.p; const int ih = O1.H, iw = O1.W, C = F / 2, oh = hn, ow = wn;
+    add(G_RESAMPLE, "upsample_ac", [=](cudaStream_t s) { return upsample_ac_f16(src, ih, iw, C, dst, oh, ow, nullptr, s); }); }
+  { GemmEpilogue ep; ep.bias = w.oc2_b; ep.act = 2; ep.head_w = w.oc3_w; ep.head_b = w.oc3_b; ep.head_out = b.depth;
+    PRISMA_TRY(add_conv3x3("output_conv2_fused", O1u, w.oc2_w, 32, ep, 1, nullptr)); }
+  // (dpt.py:163-164: the final F.interpolate to (h,w) is the identity at equal size and the ReLU is idempotent)
+
+  // ---- post-process (K10)
+  {
+    const float* d = b.depth; float* pred = b.pred; uint8_t* rgb = b.rgb; uint32_t* mm = b.mm; float* mmo = b.minmax;
+    const int hn_ = hn, wn_ = wn, sms = num_sms;
+    add(G_POST, "depth_postprocess", [=](cudaStream_t s) { return depth_postprocess(d, hn_, wn_, H, W, 1, pred, rgb, mm, mmo, sms, s); });
+  }
+  taps["net_input"] = {b.net_in, 3, hn * wn, 1, 0};
+  taps["tokens"] = {b.tokens_tap, T, D, 1, 0};
+  for (int i = 0; i < 4; ++i) taps["feat" + std::to_string(i)] = {b.feat[i], T, D, 1, 2};
+  taps["net_depth"] = {b.depth, hn, wn, 1, 0};
+  taps["x_final"] = {b.x, T, D, 1, 0};
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  plan_H = H; plan_W = W;
+  return 0;
+}
+
+int DepthEngine::run_steps(cudaStream_t s) {
+  for (auto& st : steps) PRISMA_TRY(st.fn(s));
+  return 0;
+}
+
+int DepthEngine::infer(const uint8_t* rgb, int H, int W, float* depth_out, uint8_t* rgb_out, float* min_out,
+                       float* max_out) {
+  PRISMA_CHECK(rgb != nullptr && H > 0 && W > 0, "bad frame");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_TRY(build_plan(H, W));
+  PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, rgb, (size_t)H * W * 3, cudaMemcpyHostToDevice, stream));
+  PRISMA_TRY(run_steps(stream));
+  float mm[2];
+  if (depth_out) PRISMA_CUDA_OK(cudaMemcpyAsync(depth_out, b.pred, (size_t)H * W * 4, cudaMemcpyDeviceToHost, stream));
+  if (rgb_out) PRISMA_CUDA_OK(cudaMemcpyAsync(rgb_out, b.rgb, (size_t)H * W * 3, cudaMemcpyDeviceToHost, stream));
+  PRISMA_CUDA_OK(cudaMemcpyAsync(mm, b.minmax, 8, cudaMemcpyDeviceToHost, stream));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  if (min_out) *min_out = mm[0];
+  if (max_out) *max_out = mm[1];
+  return 0;
+}
+
+int DepthEngine::infer_resident(int H, int W, int iters, float* ms_per_iter) {
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_TRY(build_plan(H, W));
+  PRISMA_CUDA_OK(cudaEventRecord(ev0, stream));
+  for (int i = 0; i < iters; ++i) PRISMA_TRY(run_steps(stream));
+  PRISMA_CUDA_OK(cudaEventRecord(ev1, stream));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  float ms = 0;
+  PRISMA_CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));
+  if (ms_per_iter) *ms_per_iter = ms / std::max(iters, 1);
+  return 0;
+}
+
+int DepthEngine::encode(const float* pred, int H, int W, int flip, uint8_t* rgb_out, float* min_out, float* max_out) {
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  float* d_pred = nullptr; uint8_t* d_rgb = nullptr; uint32_t* d_mm = nullptr; float* d_out = nullptr;
+  std::vector<void*> tmp;
+  auto cleanup = [&]() { for (void* q : tmp) cudaFree(q); };
+  int r = 0;
+  if ((r = dev_alloc(tmp, &d_pred, (size_t)H * W, false)) || (r = dev_alloc(tmp, &d_rgb, (size_t)H * W * 3, false)) ||
+      (r = dev_alloc(tmp, &d_mm, 2)) || (r = dev_alloc(tmp, &d_out, 2))) { cleanup(); return r; }
+  cudaMemcpyAsync(d_pred, pred, (size_t)H * W * 4, cudaMemcpyHostToDevice, stream);
+  r = depth_encode_only(d_pred, H, W, flip, d_rgb, d_mm, d_out, num_sms, stream);
+  float mm[2] = {0, 0};
+  if (r == 0) {
+    cudaMemcpyAsync(rgb_out, d_rgb, (size_t)H * W * 3, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(mm, d_out, 8, cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_last_error(std::string("encode: ") + cudaGetErrorString(e)); r = -2; }
+  }
+  cleanup();
+  if (min_out) *min_out = mm[0];
+  if (max_out) *max_out = mm[1];
+  return r;
+}
+
+long long DepthEngine::read_tap(const std::string& name, float* out, long long capacity) {
+  auto it = taps.find(name);
+  if (it == taps.end()) { set_last_error("unknown tap '" + name + "'"); return -1; }
+  cudaSetDevice(device);
+  const Tap& t = it->second;
+  if (t.kind == 0 || t.kind == 2) {  // dense f32 / f16 [a][b]
+    const long long n = (long long)t.a * t.b;
+    if (n > capacity) { set_last_error("tap buffer too small"); return -1; }
+    if (t.kind == 0) {
+      if (cudaMemcpy(out, t.p, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+    } else {
+      std::vector<__half> h(n);
+      if (cudaMemcpy(h.data(), t.p, n * 2, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+      for (long long i = 0; i < n; ++i) out[i] = __half2float(h[i]);
+    }
+    return n;
+  }
+  // kind 1: zero-bordered NHWC fp16 map (a=H, b=W, c=C) -> dense [H][W][C] f32
+  const long long n = (long long)t.a * t.b * t.c;
+  if (n > capacity) { set_last_error("tap buffer too small"); return -1; }
+  const size_t tot = (size_t)(t.a + 2) * (t.b + 2) * t.c;
+  std::vector<__half> h(tot);
+  if (cudaMemcpy(h.data(), t.p, tot * 2, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+  for (int y = 0; y < t.a; ++y)
+    for (int x = 0; x < t.b; ++x)
+      for (int c = 0; c < t.c; ++c)
+        out[((size_t)y * t.b + x) * t.c + c] = __half2float(h[((size_t)(y + 1) * (t.b + 2) + x + 1) * t.c + c]);
+  return n;
+}
+
+int DepthEngine::profile(int H, int W, float* out8) {
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_TRY(build_plan(H, W));
+  PRISMA_TRY(run_steps(stream));  // warm
+  std::vector<cudaEvent_t> ev(steps.size() + 1);
+  for (auto& e : ev) PRISMA_CUDA_OK(cudaEventCreate(&e));
+  PRISMA_CUDA_OK(cudaEventRecord(ev[0], stream));
+  for (size_t i = 0; i < steps.size(); ++i) {
+    PRISMA_TRY(steps[i].fn(stream));
+    PRISMA_CUDA_OK(cudaEventRecord(ev[i + 1], stream));
+  }
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  for (int i = 0; i < 8; ++i) out8[i] = 0.f;
+  for (size_t i = 0; i < steps.size(); ++i) {
+    float ms = 0;
+    PRISMA_CUDA_OK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    out8[steps[i].group] += ms;
+    out8[7] += ms;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+}  // namespace prisma

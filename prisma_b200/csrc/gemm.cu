@@ -1,0 +1,117 @@
+// prisma_b200 -- host side of the tcgen05 shifted-row GEMM: TMA descriptor encode, tile-shape choice, launch.
+#include "gemm_tc.cuh"
+
+#include <mutex>
+
+namespace prisma {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* get_last_error() { return g_last_error.c_str(); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
+                     uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  PRISMA_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  PRISMA_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  PRISMA_CHECK((pitch_elems * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  PRISMA_CHECK(box_cols * 2 == 128 && box_rows >= 1 && box_rows <= 256, "TMA box must be 64 fp16 wide, <=256 rows");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PRISMA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  return 0;
+}
+
+// Tile-N choice: minimise waves x per-tile MMA time.  Per-tile time model (cycles per 16-wide K step, one SM,
+// cta_group::1, M = 128): max(tensor floor 128*N/256, smem operand reads (4096 + 32*N) B / 128 B/clk).
+int gemm_pick_bn(int M, int N, int num_sms) {
+  const int cands[4] = {256, 128, 64, 32};
+  int best = 128;
+  double best_cost = 1e30;
+  const int tiles_m = ceil_div(M, GEMM_BM);
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (bn > 32 && bn >= 2 * round_up(N, 32)) continue;  // mostly padding
+    const int tiles = tiles_m * ceil_div(N, bn);
+    const int waves = ceil_div(tiles, num_sms);
+    const double t_tensor = 128.0 * bn / 256.0;
+    const double t_smem = (4096.0 + 32.0 * bn) / 128.0;
+    const double cost = waves * (t_tensor > t_smem ? t_tensor : t_smem) + 0.02 * waves;  // tie -> fewer waves
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols, int a_pitch, const __half* W,
+                 int w_rows, int M, int N, int taps, const int* tap_off, const GemmEpilogue& ep, int num_sms,
+                 int force_bn) {
+  PRISMA_CHECK(taps >= 1 && taps <= GEMM_MAX_TAPS, "gemm: bad tap count");
+  PRISMA_CHECK(N % 8 == 0, "gemm: N must be a multiple of 8");
+  PRISMA_CHECK(M >= 1 && a_cols >= 1, "gemm: empty problem");
+  const int bn = force_bn ? force_bn : gemm_pick_bn(M, N, num_sms);
+  PRISMA_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: unsupported BLOCK_N");
+  PRISMA_CHECK(w_rows >= round_up(N, bn), "gemm: weight rows must be padded to a multiple of BLOCK_N");
+  const int kchunks = ceil_div(a_cols, GEMM_BK);
+  out->bn = bn;
+  out->args.M = M;
+  out->args.N = N;
+  out->args.taps = taps;
+  out->args.kchunks = kchunks;
+  for (int t = 0; t < GEMM_MAX_TAPS; ++t) out->args.tap_off[t] = t < taps ? tap_off[t] : 0;
+  out->args.ep = ep;
+  PRISMA_TRY(make_tmap_2d_f16(&out->tmA, A, (uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)a_pitch, 64, GEMM_BM));
+  PRISMA_TRY(make_tmap_2d_f16(&out->tmB, W, (uint64_t)taps * kchunks * 64, (uint64_t)w_rows,
+                              (uint64_t)taps * kchunks * 64, 64, bn));
+  const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, bn);
+  out->grid = tiles < num_sms ? tiles : num_sms;
+  out->flops = 2.0 * M * (double)N * taps * a_cols;
+  return 0;
+}
+
+template <int BN>
+static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
+  static bool attr_set = false;  // per-process, per-instantiation
+  if (!attr_set) {
+    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        GemmCfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_tc_kernel<BN><<<g.grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(g.tmA, g.tmB, g.args);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gemm_run(const GemmLaunch& g, cudaStream_t stream) {
+  switch (g.bn) {
+    case 256: return launch_bn<256>(g, stream);
+    case 128: return launch_bn<128>(g, stream);
+    case 64: return launch_bn<64>(g, stream);
+    case 32: return launch_bn<32>(g, stream);
+  }
+  set_last_error("gemm_run: unsupported BLOCK_N");
+  return -1;
+}
+
+}  // namespace prisma

@@ -1,0 +1,120 @@
+"""Host-side mirror of the reference Depth-Anything band interface on top of the C ABI.
+
+Mirrors bands/depth_anything.py: `init_model()` (:48-76) -> `DepthAnythingEngine(...)`,
+`infer(img, normalize=False)` (:100-143) -> `engine.infer(img)`, and the per-frame video encode
+(:215-221) -> `engine.infer_encoded(img)`.  All arithmetic happens in libprisma_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import PrismaError, check, fptr, lib, u8ptr, c_i64_p
+
+
+def da_net_size(width, height):
+    """Resize.get_size with the band's settings (d_anything/util/transform.py:111-166), host logic only."""
+    sh, sw = 518.0 / height, 518.0 / width
+    if sw > sh:
+        sh = sw
+    else:
+        sw = sh
+
+    def constrain(x):
+        y = int(np.round(x / 14) * 14)
+        if y < 518:
+            y = int(np.ceil(x / 14) * 14)
+        return y
+
+    return constrain(sw * width), constrain(sh * height)
+
+
+class DepthAnythingEngine:
+    """One engine per (GPU, band).  Not re-entrant; owns device memory, stream and weights."""
+
+    def __init__(self, encoder="vitl", state_dict=None, device=0):
+        self._h = C.c_void_p()
+        self.encoder = encoder
+        self.device = device
+        check(lib().prisma_depth_create(encoder.encode(), device, C.byref(self._h)))
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    def load_state_dict(self, state_dict):
+        """Weight converter: accepts the reference DPT_DINOv2 state_dict (torch tensors or numpy arrays)."""
+        l = lib()
+        for name, t in state_dict.items():
+            a = t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+            if a.dtype.kind != "f":
+                continue  # e.g. num_batches_tracked
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            shape = (C.c_int64 * max(a.ndim, 1))(*(a.shape if a.ndim else (1,)))
+            check(l.prisma_depth_load_tensor(self._h, name.encode(), fptr(a), C.cast(shape, c_i64_p), max(a.ndim, 1)))
+        check(l.prisma_depth_finalize(self._h))
+
+    def infer(self, img, normalize=False):
+        """HxWx3 u8 RGB -> HxW f32 depth == bands/depth_anything.py:infer(img, normalize) (--metric none)."""
+        pred, _, _, _ = self._run(img, want_depth=True, want_rgb=False)
+        if normalize:
+            dmin, dmax = pred.min(), pred.max()
+            if dmax - dmin > np.finfo("float").eps:
+                pred = (pred - dmin) / (dmax - dmin)
+        return pred
+
+    def infer_encoded(self, img, want_depth=False):
+        """One video frame: (rgb u8 HxWx3, min, max[, depth]) == process_video's loop body (:206-221)."""
+        pred, rgb, dmin, dmax = self._run(img, want_depth=want_depth, want_rgb=True)
+        return (rgb, dmin, dmax, pred) if want_depth else (rgb, dmin, dmax)
+
+    def _run(self, img, want_depth, want_rgb):
+        img = np.ascontiguousarray(img)
+        if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+            raise PrismaError("expected an HxWx3 uint8 RGB frame")
+        h, w = img.shape[:2]
+        pred = np.empty((h, w), np.float32) if want_depth else None
+        rgb = np.empty((h, w, 3), np.uint8) if want_rgb else None
+        dmin, dmax = C.c_float(), C.c_float()
+        check(lib().prisma_depth_infer(self._h, u8ptr(img), h, w, fptr(pred) if want_depth else None,
+                                       u8ptr(rgb) if want_rgb else None, C.byref(dmin), C.byref(dmax)))
+        return pred, rgb, dmin.value, dmax.value
+
+    def encode(self, prediction, flip=True):
+        """(heat_to_rgb(1 - normalised) * 255).astype(u8) of a given HxW f32 prediction (:215-220)."""
+        p = np.ascontiguousarray(prediction, dtype=np.float32)
+        h, w = p.shape
+        rgb = np.empty((h, w, 3), np.uint8)
+        dmin, dmax = C.c_float(), C.c_float()
+        check(lib().prisma_depth_encode(self._h, fptr(p), h, w, int(flip), u8ptr(rgb), C.byref(dmin), C.byref(dmax)))
+        return rgb, dmin.value, dmax.value
+
+    def read_tap(self, name, shape):
+        out = np.empty(int(np.prod(shape)), np.float32)
+        n = check(lib().prisma_depth_read_tap(self._h, name.encode(), fptr(out), out.size))
+        assert n == out.size, (name, n, out.size)
+        return out.reshape(shape)
+
+    def time_resident(self, h, w, iters):
+        ms = C.c_float()
+        check(lib().prisma_depth_infer_resident(self._h, h, w, iters, C.byref(ms)))
+        return ms.value
+
+    def profile(self, h, w):
+        out = (C.c_float * 8)()
+        check(lib().prisma_depth_profile(self._h, h, w, out))
+        keys = ["pre", "linear", "attention", "layernorm", "head", "resample", "post", "total"]
+        return dict(zip(keys, [float(v) for v in out]))
+
+    def work(self, h, w):
+        out = (C.c_double * 4)()
+        check(lib().prisma_depth_work(self._h, h, w, out))
+        return dict(linear_flop=out[0], attention_flop=out[1], head_flop=out[2], launches=int(out[3]))
+
+    def close(self):
+        if self._h:
+            lib().prisma_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

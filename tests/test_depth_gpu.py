@@ -1,0 +1,67 @@
+"""GPU: the whole Depth-Anything band path (prisma_depth_infer through the C ABI) vs the reference fixtures and the
+CPU oracle.  Tolerance (north_star): depth floats within 1e-3 relative -- asserted as max|d| <= 1e-3 * max|ref| and
+relative L2 <= 1e-3; the u8 frame may differ by the propagated float error only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import da as oda
+from oracle.frames import synthetic_frame
+from oracle.weights import make_da_weights
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max()), float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.fixture(scope="module")
+def vits_engine():
+    from prisma_b200.depth import DepthAnythingEngine
+    eng = DepthAnythingEngine("vits", make_da_weights("vits", 0))
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("tag", ["vits_160x208", "vits_480x640"])
+def test_depth_band_matches_reference_fixture(golden_dir, vits_engine, tag):
+    g = np.load(os.path.join(golden_dir, f"da_{tag}.npz"))
+    H, W = [int(v) for v in g["frame_hw"]]
+    img = synthetic_frame(H, W, int(g["frame_index"]))
+    rgb, dmin, dmax, pred = vits_engine.infer_encoded(img, want_depth=True)
+    wn, hn = oda.da_get_size(W, H)
+    T, D = 1 + (hn // 14) * (wn // 14), 384
+    report = {}
+    net = vits_engine.read_tap("net_input", (3, hn, wn))
+    report["net_input"] = float(np.abs(net[:, ::4, ::4] - g["net_input_s4"]).max())
+    feat3 = vits_engine.read_tap("feat3", (T, D))[1:]
+    report["feat3"] = _rel(feat3[::7], g["feat3_s7"])
+    depth = vits_engine.read_tap("net_depth", (hn, wn))
+    report["net_depth"] = _rel(depth[::2, ::2], g["depth_s2"])
+    report["prediction"] = _rel(pred, g["prediction"])
+    report["minmax"] = (abs(dmin - float(g["dmin"])) / float(g["dmax"]), abs(dmax - float(g["dmax"])) / float(g["dmax"]))
+    report["rgb_max_lsb"] = int(np.abs(rgb.astype(int) - g["rgb"].astype(int)).max())
+    report["rgb_mean_lsb"] = float(np.abs(rgb.astype(int) - g["rgb"].astype(int)).mean())
+    print(tag, report)
+    assert report["net_input"] <= 5e-7 * 3
+    assert report["feat3"][0] <= 5e-3 and report["feat3"][1] <= 2e-3   # intermediate tokens (fp16 operands)
+    assert report["net_depth"][0] <= TOL and report["net_depth"][1] <= TOL
+    assert report["prediction"][0] <= TOL and report["prediction"][1] <= TOL
+    assert max(report["minmax"]) <= TOL
+
+
+def test_depth_band_matches_oracle_720p(vits_engine):
+    """BASELINE config-2 frame size (720p) with the ViT-S weights: CUDA vs the CPU oracle on the same frame."""
+    img = synthetic_frame(720, 1280, 5)
+    pred = vits_engine.infer(img)
+    sd = make_da_weights("vits", 0)
+    ref = oda.da_infer(sd, img, "vits")
+    m, l2 = _rel(pred, ref)
+    print("720p vits: max-rel %.3e  rel-L2 %.3e" % (m, l2))
+    assert m <= TOL and l2 <= TOL
+    # determinism / idempotence: the same frame twice gives identical bits
+    assert np.array_equal(pred, vits_engine.infer(img))

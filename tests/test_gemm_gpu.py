@@ -1,0 +1,75 @@
+"""GPU: the tcgen05 shifted-row GEMM core through the C ABI vs a plain fp32 reference on fp16-rounded operands."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from prisma_b200._lib import check, fptr, lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _h(a):  # fp16 operand rounding (the kernels' operand type); accumulation is fp32
+    return a.astype(np.float16).astype(np.float32)
+
+
+def _gemm(A, W, bias, act, bn):
+    M, K = A.shape
+    N = W.shape[0]
+    D = np.empty((M, N), np.float32)
+    ms = C.c_float()
+    check(lib().prisma_debug_gemm(0, fptr(A), fptr(W), fptr(bias) if bias is not None else None, fptr(D), M, N, K, act, bn, 1, C.byref(ms)))
+    return D
+
+
+@pytest.mark.parametrize("M,N,K,act,bn", [
+    (128, 128, 64, 0, 128),      # one tile, one k-block
+    (256, 256, 256, 0, 128),     # accumulate over k-blocks, several tiles
+    (300, 384, 200, 0, 0),       # ragged M, K tail (zero-filled by TMA), auto tile
+    (2443, 1152, 384, 0, 0),     # ViT-S qkv
+    (2443, 1024, 1024, 2, 256),  # BN=256, relu
+    (1813, 1536, 384, 1, 64),    # BN=64, gelu
+    (500, 48, 384, 0, 0),        # narrow N (ViT-S head), BN=32/64
+    (333, 32, 1152, 2, 32),      # BN=32
+    (40000, 256, 128, 0, 0),     # many tiles per CTA (persistent loop, TMEM double buffering)
+    (64, 64, 64, 0, 0),          # smaller than a tile
+])
+def test_gemm_matches_fp32_reference(M, N, K, act, bn):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((M, K), dtype=np.float32)
+    W = rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)
+    bias = rng.standard_normal(N, dtype=np.float32)
+    got = _gemm(A, W, bias, act, bn)
+    ref = torch.from_numpy(_h(A)) @ torch.from_numpy(_h(W)).T + torch.from_numpy(bias)
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    ref = ref.numpy()
+    err = np.abs(got - ref).max()
+    assert err <= 2e-4 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout,k,relu", [
+    (37, 66, 64, 64, 3, 1),
+    (19, 33, 384, 64, 3, 0),
+    (40, 50, 48, 64, 3, 0),      # Cin < 64: TMA box wider than the tensor
+    (24, 31, 128, 32, 1, 0),
+    (30, 44, 64, 128, 5, 0),
+])
+def test_conv_matches_torch(H, W, Cin, Cout, k, relu):
+    rng = np.random.default_rng(H * W + Cin)
+    x = rng.standard_normal((H, W, Cin), dtype=np.float32)
+    w = rng.standard_normal((Cout, Cin, k, k), dtype=np.float32) / np.sqrt(Cin * k * k)
+    b = rng.standard_normal(Cout, dtype=np.float32)
+    y = np.empty((H, W, Cout), np.float32)
+    ms = C.c_float()
+    check(lib().prisma_debug_conv(0, fptr(x), fptr(w), fptr(b), fptr(y), H, W, Cin, Cout, k, k, relu, C.byref(ms)))
+    xt = torch.from_numpy(_h(x)).permute(2, 0, 1)[None]
+    ref = torch.nn.functional.conv2d(xt, torch.from_numpy(_h(w)), torch.from_numpy(b), padding=k // 2)
+    if relu:
+        ref = torch.relu(ref)
+    ref = ref[0].permute(1, 2, 0).numpy()
+    err = np.abs(y - ref).max()
+    assert err <= 2e-4 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
