@@ -107,3 +107,68 @@ def make_da_weights(encoder="vits", seed=0):
     # degenerate and measures cancellation noise rather than the kernels.
     sd[h + "scratch.output_conv2.2.bias"] = torch.full((1,), 0.25)
     return sd
+
+
+def make_raft_weights(seed=0):
+    """state_dict of RAFT(args) (bands/raft/raft.py:24-57), seeded.
+
+    Convs: kaiming_normal(fan_out, relu) as BasicEncoder's own init loop (raft/extractor.py:148-150) for the
+    encoders, torch-default kaiming-uniform for the update block (which has no init loop); biases torch-default
+    uniform.  cnet BatchNorm gets non-trivial affine + running statistics so that the eval-mode fold is tested.
+    """
+    sd = {}
+
+    def conv(name, out_c, in_c, kh, kw, mode):
+        fan_in = in_c * kh * kw
+        if mode == "kaiming_out":
+            std = (2.0 / (out_c * kh * kw)) ** 0.5
+            sd[name + ".weight"] = _normal(name + ".weight", seed, (out_c, in_c, kh, kw), std)
+        else:
+            b = (1.0 / fan_in) ** 0.5
+            sd[name + ".weight"] = _uniform(name + ".weight", seed, (out_c, in_c, kh, kw), -b, b)
+        b = (1.0 / fan_in) ** 0.5
+        sd[name + ".bias"] = _uniform(name + ".bias", seed, (out_c,), -b, b)
+
+    def bn(name, c):
+        sd[name + ".weight"] = _normal(name + ".weight", seed, (c,), 0.1, 1.0)
+        sd[name + ".bias"] = _normal(name + ".bias", seed, (c,), 0.05)
+        sd[name + ".running_mean"] = _normal(name + ".running_mean", seed, (c,), 0.1)
+        sd[name + ".running_var"] = _uniform(name + ".running_var", seed, (c,), 0.5, 1.5)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    for net, out_dim, has_bn in (("fnet", 256, False), ("cnet", 256, True)):
+        p = net + "."
+        conv(p + "conv1", 64, 3, 7, 7, "kaiming_out")
+        if has_bn:
+            bn(p + "norm1", 64)
+        cin = 64
+        for li, dim, stride in ((1, 64, 1), (2, 96, 2), (3, 128, 2)):
+            for bi in (0, 1):
+                q = f"{p}layer{li}.{bi}."
+                conv(q + "conv1", dim, cin if bi == 0 else dim, 3, 3, "kaiming_out")
+                conv(q + "conv2", dim, dim, 3, 3, "kaiming_out")
+                if has_bn:
+                    bn(q + "norm1", dim)
+                    bn(q + "norm2", dim)
+                if bi == 0 and stride != 1:
+                    conv(q + "downsample.0", dim, cin, 1, 1, "kaiming_out")
+                    if has_bn:
+                        bn(q + "norm3", dim)
+                        for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+                            sd[q + "downsample.1." + k] = sd[q + "norm3." + k]   # same module, two names
+            cin = dim
+        conv(p + "conv2", out_dim, 128, 1, 1, "kaiming_out")
+    u = "update_block."
+    conv(u + "encoder.convc1", 256, 324, 1, 1, "default")
+    conv(u + "encoder.convc2", 192, 256, 3, 3, "default")
+    conv(u + "encoder.convf1", 128, 2, 7, 7, "default")
+    conv(u + "encoder.convf2", 64, 128, 3, 3, "default")
+    conv(u + "encoder.conv", 126, 256, 3, 3, "default")
+    for g in ("z", "r", "q"):
+        conv(u + f"gru.conv{g}1", 128, 384, 1, 5, "default")
+        conv(u + f"gru.conv{g}2", 128, 384, 5, 1, "default")
+    conv(u + "flow_head.conv1", 256, 128, 3, 3, "default")
+    conv(u + "flow_head.conv2", 2, 256, 3, 3, "default")
+    conv(u + "mask.0", 256, 128, 3, 3, "default")
+    conv(u + "mask.2", 576, 256, 1, 1, "default")
+    return sd

@@ -67,8 +67,17 @@ def check(rc):
 
 
 def fptr(a):
+    """float32 C-contiguous numpy array -> float* (None passes NULL)."""
+    if a is None:
+        return None
+    if a.dtype.name != "float32" or not a.flags["C_CONTIGUOUS"]:
+        raise PrismaError(f"expected a C-contiguous float32 array, got {a.dtype} (contiguous={a.flags['C_CONTIGUOUS']})")
     return a.ctypes.data_as(c_float_p)
 
 
 def u8ptr(a):
+    if a is None:
+        return None
+    if a.dtype.name != "uint8" or not a.flags["C_CONTIGUOUS"]:
+        raise PrismaError(f"expected a C-contiguous uint8 array, got {a.dtype}")
     return a.ctypes.data_as(c_u8_p)

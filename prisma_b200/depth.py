@@ -73,8 +73,8 @@ class DepthAnythingEngine:
         pred = np.empty((h, w), np.float32) if want_depth else None
         rgb = np.empty((h, w, 3), np.uint8) if want_rgb else None
         dmin, dmax = C.c_float(), C.c_float()
-        check(lib().prisma_depth_infer(self._h, u8ptr(img), h, w, fptr(pred) if want_depth else None,
-                                       u8ptr(rgb) if want_rgb else None, C.byref(dmin), C.byref(dmax)))
+        check(lib().prisma_depth_infer(self._h, u8ptr(img), h, w, fptr(pred),
+                                       u8ptr(rgb), C.byref(dmin), C.byref(dmax)))
         return pred, rgb, dmin.value, dmax.value
 
     def encode(self, prediction, flip=True):

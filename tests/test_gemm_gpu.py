@@ -38,7 +38,7 @@ def _gemm(A, W, bias, act, bn):
 def test_gemm_matches_fp32_reference(M, N, K, act, bn):
     rng = np.random.default_rng(M * 7 + N * 3 + K)
     A = rng.standard_normal((M, K), dtype=np.float32)
-    W = rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)
+    W = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
     bias = rng.standard_normal(N, dtype=np.float32)
     got = _gemm(A, W, bias, act, bn)
     ref = torch.from_numpy(_h(A)) @ torch.from_numpy(_h(W)).T + torch.from_numpy(bias)
@@ -61,7 +61,7 @@ def test_gemm_matches_fp32_reference(M, N, K, act, bn):
 def test_conv_matches_torch(H, W, Cin, Cout, k, relu):
     rng = np.random.default_rng(H * W + Cin)
     x = rng.standard_normal((H, W, Cin), dtype=np.float32)
-    w = rng.standard_normal((Cout, Cin, k, k), dtype=np.float32) / np.sqrt(Cin * k * k)
+    w = (rng.standard_normal((Cout, Cin, k, k), dtype=np.float32) / np.sqrt(Cin * k * k)).astype(np.float32)
     b = rng.standard_normal(Cout, dtype=np.float32)
     y = np.empty((H, W, Cout), np.float32)
     ms = C.c_float()
