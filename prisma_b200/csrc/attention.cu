@@ -6,7 +6,10 @@
 //                             [tokens][3*D] qkv matrix -- no head split/transposes ever materialise)
 //   warp 1   : MMA issuer    (S = Q K^T  -> TMEM cols [0,128);  O_j = P V_j -> TMEM cols [128,192), V as MN-major B)
 //   warps 2-5: softmax       (thread = query row: tcgen05.ld S, online max/sum in fp32, P -> fp16 -> swizzled smem
-//                             as the A operand of the PV MMA; O accumulated in registers with the usual rescale)
+//                             as the A operand of the PV MMA).  O accumulates in TMEM across all KV tiles; the
+//                             running-max rescale is lazy: O (and l) are only rescaled -- tcgen05.ld/st of this
+//                             warp's 32 lanes -- when a row's max grew by more than 2^8, so P stays <= 256 in fp16
+//                             and the common path has no per-tile accumulator traffic at all.
 #include "attention.cuh"
 
 namespace prisma {
@@ -14,18 +17,23 @@ namespace prisma {
 constexpr int ATT_BQ = 128, ATT_BKV = 128, ATT_HD = 64;
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
-constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 + 2 + 2) + 1024 + 128;
+// 7 tiles + barriers = 114,816 B: two CTAs (+1 KB reserved each) fit the 228 KB of an SM; no alignment slack, the
+// dynamic smem base is declared 1024-aligned (128B-swizzle atoms are 1 KB) and checked at kernel entry.
+constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 + 2 + 2) + 128;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ AttnArgs args) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("prisma: attention smem base not 1024-aligned\n");
+    __trap();
+  }
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE_BYTES;      // 2 stages
   uint8_t* sV = smem + 3 * ATT_TILE_BYTES;  // 2 stages
@@ -36,8 +44,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* kv_empty = bars + 3;  // [2]
   uint64_t* s_full = bars + 5;
   uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint64_t* o_free = bars + 8;
+  uint64_t* pv_done = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -53,8 +60,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
     mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
-    mbar_init(o_free, 4);
+    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
@@ -93,17 +99,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       }
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
-        mbar_wait(p_full, j & 1);                 // P(j) in smem, S(j) fully read
-        if (j > 0) mbar_wait(o_free, (j - 1) & 1);  // O_tile(j-1) consumed
+        mbar_wait(p_full, j & 1);  // P(j) in smem, S(j) fully read, any lazy rescale of O done
         tc_fence_after();
         const uint32_t vbase = smem_u32(sV + st * ATT_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t pdesc = make_sdesc_sw128(smem_u32(sP + (k >> 2) * ATT_TILE_BYTES)) + 2 * (k & 3);
           const uint64_t vdesc = make_sdesc_sw128(vbase + k * 2048);
-          umma_f16(tmem_O, pdesc, vdesc, idesc_o, k != 0);
+          umma_f16(tmem_O, pdesc, vdesc, idesc_o, (j | k) != 0);  // O accumulates over all KV tiles
         }
-        umma_commit(o_full);
+        umma_commit(pv_done);
         umma_commit(&kv_empty[st]);
         if (j + 1 < n_kv) {
           const int st1 = (j + 1) & 1;
@@ -121,16 +126,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f;
-    float O[ATT_HD];
-#pragma unroll
-    for (int d = 0; d < ATT_HD; ++d) O[d] = 0.f;
+    float m_used = -INFINITY, l_run = 0.f;  // m_used: the max P / O are currently scaled by
     uint8_t* prow = sP + r * 128;
     const int rsw = r & 7;
 
     for (int j = 0; j < n_kv; ++j) {
       const int valid = min(ATT_BKV, T - j * ATT_BKV);  // >= 1
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, j & 1);  // S(j) ready; MMAs retire in order, so PV(j-1) has also finished reading P(j-1)
       tc_fence_after();
       // ---- pass 1: row max
       float mx = -INFINITY;
@@ -148,10 +150,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           for (int i = 0; i < 32; ++i) if (c0 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2_approx((m_run - m_new) * LOG2E);
-      const float mscaled = m_new * LOG2E;
-      // ---- pass 2: p = exp(s - m), row sum, P -> fp16 -> swizzled smem (A operand of the PV MMA)
+      // ---- lazy rescale (warp-uniform decision; each warp owns its 32 TMEM lanes)
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = (mx - m_used) * LOG2E > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? mx : m_used;
+          const float alpha = ex2_approx((m_used - m_new) * LOG2E);  // 1 for rows that keep their max
+          mbar_wait(pv_done, (j - 1) & 1);                            // no PV may be in flight on O
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(tmem_O + lane_sel + h * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tmem_O + lane_sel + h * 32, v);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_used = m_new;
+        }
+      }
+      const float mscaled = m_used * LOG2E;
+      // ---- pass 2: p = exp(s - m_used), row sum, P -> fp16 -> swizzled smem (A operand of the PV MMA)
       float sum = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < ATT_BKV; c0 += 32) {
@@ -177,26 +201,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           *reinterpret_cast<uint4*>(slab + (((chunk0 + g) ^ rsw) << 4)) = o;
         }
       }
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
+      l_run += sum;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      // ---- O = O * alpha + P V_j
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
+    }
+    // ---- O is complete once the last PV retires
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    float O[ATT_HD];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld32(tmem_O + lane_sel + h * 32, v);
-        tmem_ld_wait();
+    for (int h = 0; h < 2; ++h) {
+      uint32_t v[32];
+      tmem_ld32(tmem_O + lane_sel + h * 32, v);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) O[h * 32 + i] = fmaf(O[h * 32 + i], alpha, __uint_as_float(v[i]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
+      for (int i = 0; i < 32; ++i) O[h * 32 + i] = __uint_as_float(v[i]);
     }
     // ---- normalise and store: out[row][head*64 + d]
     const int q = q0 + r;

@@ -194,9 +194,16 @@ int prisma_debug_gemm(int device, const float* A, const float* W, const float* b
   if (bias) PRISMA_CUDA_OK(cudaMemcpy(dB, bias, N * 4, cudaMemcpyHostToDevice));
   GemmEpilogue ep;
   ep.bias = bias ? dB : nullptr;
-  ep.act = act;
-  ep.out_f32 = dD;
+  ep.act = act < 0 ? 0 : act;
+  ep.out_f32 = act == -1 ? nullptr : dD;  // act == -1: mainloop only (no stores), act == -2: fp16 output
   ep.out_f32_ld = N;
+  __half* dH = nullptr;
+  if (act == -2) {
+    dH = sc.alloc<__half>((size_t)M * N);
+    ep.out_f32 = nullptr;
+    ep.out_f16 = dH;
+    ep.out_f16_ld = N;
+  }
   GemmLaunch g;
   const int off[1] = {0};
   PRISMA_TRY(gemm_prepare(&g, dA, M, K, Kp, dW, Nw, M, N, 1, off, ep, sms, force_bn));

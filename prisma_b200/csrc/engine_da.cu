@@ -43,6 +43,7 @@ DepthEngine::~DepthEngine() {
   cudaSetDevice(device);
   for (void* p : allocs) cudaFree(p);
   for (void* p : plan_allocs) cudaFree(p);
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);
@@ -77,6 +78,8 @@ int DepthEngine::init(const std::string& enc, int dev) {
   PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   PRISMA_CUDA_OK(cudaEventCreate(&ev0));
   PRISMA_CUDA_OK(cudaEventCreate(&ev1));
+  const char* ng = getenv("PRISMA_NO_GRAPH");
+  use_graph = !(ng && ng[0] == '1');
   return 0;
 }
 
@@ -492,12 +495,34 @@ int DepthEngine::build_plan(int H, int W) {
   taps["x_final"] = {b.x, T, D, 1, 0};
   PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
   plan_H = H; plan_W = W;
+  // ---- one CUDA graph per resolution: ~200 launches per frame replayed with a single cudaGraphLaunch
+  if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  if (use_graph) {
+    PRISMA_TRY(run_steps_direct(stream));  // warm: sets per-kernel attributes outside the capture
+    PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+    cudaGraph_t graph = nullptr;
+    PRISMA_CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    int r = run_steps_direct(stream);
+    cudaError_t e = cudaStreamEndCapture(stream, &graph);
+    if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+    PRISMA_CUDA_OK(e);
+    PRISMA_CUDA_OK(cudaGraphInstantiate(&graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  return 0;
+}
+
+int DepthEngine::run_steps_direct(cudaStream_t s) {
+  for (auto& st : steps) PRISMA_TRY(st.fn(s));
   return 0;
 }
 
 int DepthEngine::run_steps(cudaStream_t s) {
-  for (auto& st : steps) PRISMA_TRY(st.fn(s));
-  return 0;
+  if (graph_exec) {
+    PRISMA_CUDA_OK(cudaGraphLaunch(graph_exec, s));
+    return 0;
+  }
+  return run_steps_direct(s);
 }
 
 int DepthEngine::infer(const uint8_t* rgb, int H, int W, float* depth_out, uint8_t* rgb_out, float* min_out,
@@ -586,7 +611,7 @@ long long DepthEngine::read_tap(const std::string& name, float* out, long long c
 int DepthEngine::profile(int H, int W, float* out8) {
   PRISMA_CUDA_OK(cudaSetDevice(device));
   PRISMA_TRY(build_plan(H, W));
-  PRISMA_TRY(run_steps(stream));  // warm
+  PRISMA_TRY(run_steps_direct(stream));  // warm
   std::vector<cudaEvent_t> ev(steps.size() + 1);
   for (auto& e : ev) PRISMA_CUDA_OK(cudaEventCreate(&e));
   PRISMA_CUDA_OK(cudaEventRecord(ev[0], stream));

@@ -70,12 +70,15 @@ class DepthEngine {
   int add_conv3x3(const char* name, const PMap& in, const __half* W, int Cout, GemmEpilogue ep, int sub,
                   const PMap* out_geom);
   int run_steps(cudaStream_t s);
+  int run_steps_direct(cudaStream_t s);
 
   std::string encoder;
   int D = 0, depth = 0, heads = 0, F = 0, oc[4] = {0, 0, 0, 0};
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool use_graph = true;
   bool finalized = false;
   std::map<std::string, HostTensor> host;
   std::vector<void*> allocs, plan_allocs;

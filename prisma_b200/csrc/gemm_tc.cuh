@@ -12,8 +12,10 @@
 //   warp 0   : TMA producer  (A 128x64 and W BNx64 fp16 tiles, 128B swizzle, STAGES-deep mbarrier ring)
 //   warp 1   : MMA issuer    (one lane: tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16; fp32 accum in TMEM,
 //                             two accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1)
-//   warps 2-5: epilogue      (tcgen05.ld 32x32b -> registers -> bias / GELU / ReLU / LayerScale / residuals ->
-//                             fp32 and/or fp16 stores with the row mapping of the consumer's layout)
+//   warps 2-9: epilogue      (tcgen05.ld 32x32b -> registers -> smem transpose -> bias / GELU / ReLU / LayerScale /
+//                             residuals -> coalesced fp32 and/or fp16 stores with the row mapping of the consumer's
+//                             layout; two warps per TMEM lane quarter take alternate 32-column chunks; every
+//                             global access of a chunk is issued as a batch of 8 independent requests per lane)
 #pragma once
 #include "common.cuh"
 
@@ -21,7 +23,8 @@ namespace prisma {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                          // two per TMEM lane quarter
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;      // + TMA producer warp + MMA warp
 constexpr int GEMM_MAX_TAPS = 49;
 
 enum RowMap : int {
@@ -77,71 +80,88 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 7);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 32 * 4;  // epilogue transpose staging: 32x32 fp32 per warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-// One 8-column group of one accumulator row -> epilogue math -> stores.
-__device__ __forceinline__ void epilogue_store8(const GemmEpilogue& ep, float* v, long long drow, int n) {
-  if (ep.bias) {
-    const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + n);
-    const float4 b1 = *reinterpret_cast<const float4*>(ep.bias + n + 4);
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void add_h4(float4& v, const uint2& r) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+}
+
+// Coalesced phase of the epilogue for one 32-column chunk: this lane owns 4 consecutive columns (col..col+3) of the
+// 8 rows dr[0..7] (8 lanes cover a row's 32 columns, so a warp instruction touches 4 rows x 128 B fp32 / 64 B fp16).
+// All loads of a kind are issued before any is consumed (8 independent requests in flight per lane).
+__device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&v)[8], const int (&dr)[8], uint32_t okm,
+                                               const float4& bias, const float4& gamma, int col) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { v[i].x += bias.x; v[i].y += bias.y; v[i].z += bias.z; v[i].w += bias.w; }
   if (ep.act == 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+    for (int i = 0; i < 8; ++i) { v[i].x = gelu_erf(v[i].x); v[i].y = gelu_erf(v[i].y); v[i].z = gelu_erf(v[i].z); v[i].w = gelu_erf(v[i].w); }
   } else if (ep.act == 2) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+    for (int i = 0; i < 8; ++i) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
   }
-  if (ep.gamma) {
-    const float4 g0 = *reinterpret_cast<const float4*>(ep.gamma + n);
-    const float4 g1 = *reinterpret_cast<const float4*>(ep.gamma + n + 4);
-    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-    v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
-  }
-  int col = n;
-  if (ep.row_map == ROW_SHUFFLE) col = n % ep.shuf_cout;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { v[i].x *= gamma.x; v[i].y *= gamma.y; v[i].z *= gamma.z; v[i].w *= gamma.w; }
   if (ep.res_f32) {
-    const float* p = ep.res_f32 + drow * ep.res_f32_ld + col;
-    const float4 r0 = *reinterpret_cast<const float4*>(p);
-    const float4 r1 = *reinterpret_cast<const float4*>(p + 4);
-    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    float4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      t[i] = (okm >> i) & 1 ? *reinterpret_cast<const float4*>(ep.res_f32 + (size_t)dr[i] * ep.res_f32_ld + col)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i].x += t[i].x; v[i].y += t[i].y; v[i].z += t[i].z; v[i].w += t[i].w; }
   }
   if (ep.res_a) {
-    const uint4 r = *reinterpret_cast<const uint4*>(ep.res_a + drow * ep.res_a_ld + col);
-    const __half2* h = reinterpret_cast<const __half2*>(&r);
+    uint2 t[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+    for (int i = 0; i < 8; ++i)
+      t[i] = (okm >> i) & 1 ? *reinterpret_cast<const uint2*>(ep.res_a + (size_t)dr[i] * ep.res_a_ld + col) : make_uint2(0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) add_h4(v[i], t[i]);
   }
   if (ep.res_b) {
-    const uint4 r = *reinterpret_cast<const uint4*>(ep.res_b + drow * ep.res_b_ld + col);
-    const __half2* h = reinterpret_cast<const __half2*>(&r);
+    uint2 t[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+    for (int i = 0; i < 8; ++i)
+      t[i] = (okm >> i) & 1 ? *reinterpret_cast<const uint2*>(ep.res_b + (size_t)dr[i] * ep.res_b_ld + col) : make_uint2(0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) add_h4(v[i], t[i]);
   }
   if (ep.out_f32) {
-    float* p = ep.out_f32 + drow * ep.out_f32_ld + col;
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((okm >> i) & 1) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)dr[i] * ep.out_f32_ld + col) = v[i];
   }
   if (ep.out_f16) {
-    uint4 o;
-    o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]); o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(ep.out_f16 + drow * ep.out_f16_ld + col) = o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((okm >> i) & 1)
+        *reinterpret_cast<uint2*>(ep.out_f16 + (size_t)dr[i] * ep.out_f16_ld + col) =
+            make_uint2(pack_half2(v[i].x, v[i].y), pack_half2(v[i].z, v[i].w));
   }
   if (ep.out_f16_relu) {
-    uint4 o;
-    o.x = pack_half2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f)); o.y = pack_half2(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
-    o.z = pack_half2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f)); o.w = pack_half2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
-    *reinterpret_cast<uint4*>(ep.out_f16_relu + drow * ep.out_f16_relu_ld + col) = o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((okm >> i) & 1)
+        *reinterpret_cast<uint2*>(ep.out_f16_relu + (size_t)dr[i] * ep.out_f16_relu_ld + col) =
+            make_uint2(pack_half2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f)), pack_half2(fmaxf(v[i].z, 0.f), fmaxf(v[i].w, 0.f)));
   }
 }
 
@@ -151,11 +171,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("prisma: gemm smem base not 1024-aligned\n");
+    __trap();
+  }
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -173,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], GEMM_EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -229,9 +253,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (2..5)
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue warps (2..9)
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int chunk_par = (warp - 2) >> 2;  // the two warps of a quarter take even / odd 32-column chunks
     const GemmEpilogue& ep = args.ep;
+    const uint32_t stg = smem_u32(stg_all) + (warp - 2) * 4096;
+    const int cg = lane & 7;     // coalesced phase: which 4-column group of the 32-column chunk
+    const int rsub = lane >> 3;  // coalesced phase: row offset inside a 4-row step
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -239,11 +267,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (tile % tiles_m) * GEMM_BM;
       const int n0 = (tile / tiles_m) * BN;
       const int m = m0 + quarter * 32 + lane;
-      // ---- row mapping
-      bool valid = m < args.M;
-      long long drow = m;
-      int ty = 0, tx = 0;  // token coordinates for ROW_SHUFFLE
-      long long img_base = 0;
+      // ---- row mapping of "my" accumulator row (lane == row inside this warp's 32-row slab)
+      int valid = m < args.M;
+      int drow = m;
+      int ty = 0, tx = 0, img_base = 0;  // token coordinates / image base row for ROW_SHUFFLE
       if (ep.row_map == ROW_PADDED) {
         int img = 0, r = m;
         if (ep.img_rows > 0) { img = m / ep.img_rows; r = m - img * ep.img_rows; }
@@ -251,48 +278,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         valid = valid && y >= 1 && y <= ep.in_h - 2 && x >= 1 && x <= ep.in_w - 2;
         if (ep.sub > 1) {
           valid = valid && ((y - 1) % ep.sub == 0) && ((x - 1) % ep.sub == 0);
-          drow = (long long)img * ep.out_img_rows + (long long)((y - 1) / ep.sub + 1) * ep.out_wp + (x - 1) / ep.sub + 1;
+          drow = img * ep.out_img_rows + ((y - 1) / ep.sub + 1) * ep.out_wp + (x - 1) / ep.sub + 1;
         }
       } else if (ep.row_map == ROW_TOK2PAD || ep.row_map == ROW_SHUFFLE) {
         const int per = ep.in_w * ep.in_h;
         const int img = m / per, r = m - img * per;
         ty = r / ep.in_w; tx = r - ty * ep.in_w;
-        img_base = (long long)img * ep.out_img_rows;
-        drow = img_base + (long long)(ty + 1) * ep.out_wp + tx + 1;
+        img_base = img * ep.out_img_rows;
+        drow = img_base + (ty + 1) * ep.out_wp + tx + 1;
+      }
+      // row mapping of the 8 rows this lane stores in the coalesced phase (constant over the tile's chunks)
+      int dr8[8], ty8[8], tx8[8], ib8[8];
+      uint32_t okrows = 0;
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) {
+        const int row = rr * 4 + rsub;
+        okrows |= (__shfl_sync(0xffffffffu, valid, row) ? 1u : 0u) << rr;
+        dr8[rr] = __shfl_sync(0xffffffffu, drow, row);
+        if (ep.row_map == ROW_SHUFFLE) {
+          ty8[rr] = __shfl_sync(0xffffffffu, ty, row);
+          tx8[rr] = __shfl_sync(0xffffffffu, tx, row);
+          ib8[rr] = __shfl_sync(0xffffffffu, img_base, row);
+        }
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chunk_par * 32; c0 < BN; c0 += 64) {
         if (n0 + c0 >= args.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
-        if (valid && ep.head_w != nullptr) {
-          float acc = ep.head_b;
+        if (ep.head_w != nullptr) {
+          if (valid) {
+            float acc = ep.head_b;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            acc = fmaf(fmaxf(__uint_as_float(r[j]) + __ldg(ep.bias + j), 0.f), __ldg(ep.head_w + j), acc);
-          const int y = m / ep.in_w, x = m - y * ep.in_w;
-          ep.head_out[(size_t)(y - 1) * (ep.in_w - 2) + (x - 1)] = fmaxf(acc, 0.f);
-        } else if (valid) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + c0 + g * 8;
-            if (n < args.N) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              long long dr = drow;
-              if (ep.row_map == ROW_SHUFFLE) {
-                const int q = n / ep.shuf_cout;
-                const int dy = q / ep.shuf_s, dx = q - dy * ep.shuf_s;
-                dr = img_base + (long long)(ty * ep.shuf_s + dy + 1) * ep.out_wp + tx * ep.shuf_s + dx + 1;
-              }
-              epilogue_store8(ep, v, dr, n);
-            }
+            for (int j = 0; j < 32; ++j)
+              acc = fmaf(fmaxf(__uint_as_float(r[j]) + __ldg(ep.bias + j), 0.f), __ldg(ep.head_w + j), acc);
+            const int y = m / ep.in_w, x = m - y * ep.in_w;
+            ep.head_out[(size_t)(y - 1) * (ep.in_w - 2) + (x - 1)] = fmaxf(acc, 0.f);
           }
+          continue;
+        }
+        // ---- phase 1: row-per-lane registers -> swizzled smem (conflict-free 16 B slots)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(stg + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        // ---- phase 2: 8 lanes x 4 columns cover one row's 32 columns; 4 rows per step -> coalesced global access
+        const int n = n0 + c0 + cg * 4;
+        const bool ncol_ok = n < args.N;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), gamma4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (ncol_ok && ep.bias) bias4 = *reinterpret_cast<const float4*>(ep.bias + n);
+        if (ncol_ok && ep.gamma) gamma4 = *reinterpret_cast<const float4*>(ep.gamma + n);
+        float4 v[8];
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int row = rr * 4 + rsub;
+          v[rr] = lds128(stg + row * 128 + ((cg ^ (row & 7)) << 4));
+        }
+        __syncwarp();  // staging may be overwritten by the next chunk from here on
+        int col = n;
+        if (ep.row_map == ROW_SHUFFLE) {
+          const int q = n / ep.shuf_cout;
+          col = n - q * ep.shuf_cout;
+          const int sdy = q / ep.shuf_s, sdx = q - sdy * ep.shuf_s;
+          int drs[8];
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr)
+            drs[rr] = ib8[rr] + (ty8[rr] * ep.shuf_s + sdy + 1) * ep.out_wp + tx8[rr] * ep.shuf_s + sdx + 1;
+          epilogue_rows8(ep, v, drs, ncol_ok ? okrows : 0u, bias4, gamma4, col);
+        } else {
+          epilogue_rows8(ep, v, dr8, ncol_ok ? okrows : 0u, bias4, gamma4, col);
         }
       }
       tc_fence_before();

@@ -1,0 +1,21 @@
+"""A few launches of the two tensor-core kernels at ViT-L shapes, for ncu (run under `ncu ... python tools/prof_kernels.py`)."""
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from prisma_b200._lib import fptr, lib
+l = lib()
+rng = np.random.default_rng(0)
+which = sys.argv[1] if len(sys.argv) > 1 else "both"
+if which in ("gemm", "both"):
+    for (M, N, K, bn) in [(2443, 3072, 1024, 256), (2443, 1024, 4096, 128)]:
+        A = rng.standard_normal((M, K), dtype=np.float32)
+        W = (rng.standard_normal((N, K), dtype=np.float32) / 32).astype(np.float32)
+        b = np.zeros(N, np.float32); D = np.empty((M, N), np.float32); ms = C.c_float()
+        assert l.prisma_debug_gemm(0, fptr(A), fptr(W), fptr(b), fptr(D), M, N, K, 0, bn, 3, C.byref(ms)) == 0
+        print("gemm", M, N, K, bn, "ms", ms.value, "TF", 2.0 * M * N * K / ms.value / 1e9)
+if which in ("attn", "both"):
+    T, heads = 2443, 16
+    qkv = rng.standard_normal((T, 3 * heads * 64), dtype=np.float32)
+    out = np.empty((T, heads * 64), np.float32); ms = C.c_float()
+    assert l.prisma_debug_attention(0, fptr(qkv), fptr(out), T, heads, 3, C.byref(ms)) == 0
+    print("attn ms", ms.value, "TF", 4.0 * heads * T * T * 64 / ms.value / 1e9)
