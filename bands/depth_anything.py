@@ -1,0 +1,134 @@
+#!/usr/bin/env python3
+"""depth_anything band on the B200 engine -- drop-in for the reference's bands/depth_anything.py.
+
+Same plugin surface: module constants/globals, init_model(), infer(img, normalize),
+process_image(args), process_video(args), the CLI flags of bands/depth_anything.py:255-265, the outputs
+(<band>.mp4|png, <band>_min.csv, <band>_max.csv, optional <sub>/%05d.npy) and the metadata.json keys
+(:155-166,241-251).  The model call and the numpy encode are replaced by libprisma_b200.so; there is no CPU path.
+
+Additions: --weights (a DPT_DINOv2 state_dict: torch .pth/.pt or .npz), --seeded-weights (offline test weights),
+--device, --batch.  `--metric indoor|outdoor` (ZoeDepth head) is a SURVEY section 8f "next" row and raises here.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bands.common.meta import get_target, get_url, is_video, load_metadata, write_metadata  # noqa: E402
+from bands.common.media import VideoReader, VideoWriter, create_folder, open_rgb, write_rgb  # noqa: E402
+
+BAND = "depth_anything"
+DEVICE = 0
+WEIGHTS = "models/depth_anything_{}14.pth"
+
+model = None
+data = None
+args = None
+
+
+def _load_state_dict(a):
+    if a.seeded_weights:
+        # seeded random weights (no checkpoint is reachable offline)
+        from prisma_b200.seeded_weights import make_da_weights
+        return make_da_weights(a.encoder, 0)
+    path = a.weights or WEIGHTS.format(a.encoder)
+    if path.endswith(".npz"):
+        return dict(np.load(path))
+    import torch
+    sd = torch.load(path, map_location="cpu")
+    return sd.get("state_dict", sd)
+
+
+def init_model():
+    """reference :48-76 (relative-depth branch): build the engine and upload the converted weights."""
+    global model
+    from prisma_b200.depth import DepthAnythingEngine
+    model = DepthAnythingEngine(args.encoder, _load_state_dict(args), device=args.device)
+    return model
+
+
+def infer(img, normalize=False):
+    """HxWx3 u8 RGB -> HxW f32 (reference :100-143)."""
+    if model is None:
+        init_model()
+    return model.infer(img, normalize=normalize)
+
+
+def process_image(a):
+    img = open_rgb(a.input)
+    rgb, dmin, dmax, pred = model.infer_encoded(img, want_depth=True)
+    if a.npy:
+        np.save(os.path.splitext(a.output)[0] + ".npy", pred)
+    write_rgb(a.output, rgb)
+    if data:
+        data["bands"][BAND]["values"] = {"min": {"type": "float", "value": dmin}, "max": {"type": "float", "value": dmax}}
+
+
+def process_video(a):
+    reader = VideoReader(a.input)
+    out = VideoWriter(reader.width, reader.height, reader.get_avg_fps(), a.output)
+    folder = os.path.dirname(a.output)
+    sub = ""
+    if a.subpath != "":
+        if data:
+            data["bands"][BAND]["folder"] = a.subpath
+        sub = os.path.join(folder, a.subpath)
+        create_folder(sub)
+    mins, maxs = [], []
+    for i, frame in enumerate(reader):
+        rgb, dmin, dmax, pred = model.infer_encoded(frame, want_depth=bool(a.npy))
+        if a.npy:
+            np.save(os.path.join(sub or folder, "{:05d}.npy".format(i)), pred)
+        out.write(rgb)
+        mins.append(dmin)
+        maxs.append(dmax)
+    out.close()
+    with open(os.path.join(folder, BAND + "_min.csv"), "w") as f:
+        f.writelines("{}\n".format(v) for v in mins)
+    with open(os.path.join(folder, BAND + "_max.csv"), "w") as f:
+        f.writelines("{}\n".format(v) for v in maxs)
+    if data:
+        data["bands"][BAND]["values"] = {"min": {"type": "float", "url": BAND + "_min.csv"},
+                                         "max": {"type": "float", "url": BAND + "_max.csv"}}
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--input", "-i", help="Input image/video", type=str, required=True)
+    p.add_argument("--output", "-o", help="Output image/video", type=str, default="")
+    p.add_argument("--npy", "-n", help="Save numpy data", action="store_true")
+    p.add_argument("--ply", "-p", help="Create point cloud PLY", action="store_true")
+    p.add_argument("--subpath", "-d", help="subpath to frames", type=str, default="")
+    p.add_argument("--encoder", type=str, default="vitl", choices=["vits", "vitb", "vitl"])
+    p.add_argument("--metric", help="Use a metric model", type=str, default="none", choices=["none", "indoor", "outdoor"])
+    p.add_argument("--weights", type=str, default="", help="DPT_DINOv2 state_dict (.pth/.npz)")
+    p.add_argument("--seeded-weights", action="store_true", help="seeded random weights (offline testing)")
+    p.add_argument("--device", type=int, default=DEVICE)
+    return p
+
+
+def main(argv=None):
+    global args, data
+    args = build_parser().parse_args(argv)
+    if args.metric != "none":
+        raise NotImplementedError("--metric indoor|outdoor (ZoeDepth head) is not built yet (SURVEY.md section 8f row 1)")
+    if args.ply:
+        print("--ply is outside the engine's scope (optional export, SURVEY.md section 2); ignored")
+    data = load_metadata(args.input)
+    if data:
+        args.input = get_url(args.input, data, "rgba")
+        args.output = get_target(args.input, data, band=BAND, target=args.output, force_extension="png")
+    elif args.output == "":
+        args.output = os.path.join(os.path.dirname(args.input), BAND + os.path.splitext(args.input)[1])
+    init_model()
+    if is_video(args.output):
+        process_video(args)
+    else:
+        process_image(args)
+    write_metadata(args.input, data)
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,28 @@ int prisma_depth_work(prisma_engine* e, int h, int w, double* out4);
 
 int prisma_engine_destroy(prisma_engine* e);
 
+/* ---- RAFT band, HBM-bound stages (replaces parts of bands/flow_raft.py + bands/raft/corr.py; the conv encoders and
+ *      the ConvGRU update block are the next rows of SURVEY.md section 8)                                        */
+/* K11: cv2.resize(frame, fx=fy=scale, INTER_CUBIC) + load_image + InputPadder('sintel').pad + 2*(x/255)-1
+ * (flow_raft.py:100-101, common/flow.py:13-16,46-56, raft/raft.py:90-91).  rgb u8 h*w*3 -> resized u8 hs*ws*3
+ * (may be NULL) and chw_padded f32 [3][hp][wp]; hs=round(h*scale), hp/wp = hs/ws rounded up to a multiple of 8.  */
+int prisma_flow_preprocess(int device, const uint8_t* rgb, int h, int w, float scale, uint8_t* resized,
+                           float* chw_padded);
+/* K20: process_flow (common/encode.py:113-126): flow f32 h*w*2 -> rgb u8 h*w*3 + max displacement.            */
+int prisma_flow_encode(int device, const float* flow, int h, int w, uint8_t* rgb_out, float* max_disp_out);
+/* K13-K15: CorrBlock (raft/corr.py:12-60) for `batch` image pairs at 1/8 resolution, 256 channels.             */
+int prisma_flowcorr_create(int device, int batch, int h8, int w8, prisma_engine** out);
+/* fmap1/fmap2: host f32 [batch][256][h8][w8] (NCHW, as BasicEncoder returns them)                              */
+int prisma_flowcorr_set_fmaps(prisma_engine* e, const float* fmap1, const float* fmap2);
+/* builds the 4-level fp32 correlation pyramid; ms_out = CUDA-event time per build over `iters` builds          */
+int prisma_flowcorr_build(prisma_engine* e, int iters, float* ms_out);
+/* CorrBlock.__call__: coords host f32 [batch][2][h8][w8] -> out f32 [batch][324][h8][w8] (may be NULL)          */
+int prisma_flowcorr_lookup(prisma_engine* e, const float* coords, float* out, int iters, float* ms_out);
+/* rows [row0,row0+nrows) of pyramid level `level` of image `b`: out f32 [nrows][(h8>>level)*(w8>>level)]        */
+int prisma_flowcorr_read_level(prisma_engine* e, int level, int b, int row0, int nrows, float* out);
+/* algorithmic work of one build: out[0] = FLOP, out[1] = bytes (fp32 pyramid written + fp16 features read)      */
+int prisma_flowcorr_work(prisma_engine* e, double* out2);
+
 /* ---- kernel-level entry points (parity tests and micro-benchmarks call the kernels through the C ABI) ---- */
 /* D = A[M,K] * W[N,K]^T (+bias) with fp16 operands / fp32 accumulate on the tcgen05 core; A, W, D host fp32.
  * act: 0 none, 1 gelu, 2 relu.  force_bn: 0 = auto, else 32/64/128/256.  ms_out (may be NULL): kernel time.   */

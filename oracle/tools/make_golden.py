@@ -118,11 +118,68 @@ def golden_sizes():
     print("sizes ok", rows)
 
 
+def golden_raft():
+    """RAFT: reference model vs oracle on a 240x320 pair (fwd+bwd), fixtures for the correlation / lookup / encode stages."""
+    import argparse
+    from raft.raft import RAFT
+    from common import encode as renc
+    from common.flow import InputPadder
+    from oracle import raft as oraft
+    from oracle.weights import make_raft_weights
+    sd = make_raft_weights(0)
+    m = RAFT(argparse.Namespace(small=False, mixed_precision=False, alternate_corr=False)).eval()
+    print("[raft] load_state_dict:", m.load_state_dict(sd, strict=True))
+    f0, f1 = synthetic_frame(240, 320, 0), synthetic_frame(240, 320, 1)
+    import cv2
+    a = torch.from_numpy(np.array(cv2.resize(f0, None, fx=0.75, fy=0.75, interpolation=cv2.INTER_CUBIC))).permute(2, 0, 1).float()[None]
+    b = torch.from_numpy(np.array(cv2.resize(f1, None, fx=0.75, fy=0.75, interpolation=cv2.INTER_CUBIC))).permute(2, 0, 1).float()[None]
+    assert torch.equal(a[0], oraft.raft_preprocess(f0)) and torch.equal(b[0], oraft.raft_preprocess(f1))
+    i1, i2 = torch.cat([a, b]), torch.cat([b, a])
+    padder = InputPadder(i1.shape)
+    assert padder._pad == oraft.input_pad(*i1.shape[-2:])
+    p1, p2 = padder.pad(i1, i2)
+    lo_r, up_r = m(p1, p2, iters=12, test_mode=True)
+    taps = {}
+    lo_o, up_o = oraft.raft_forward(sd, p1, p2, 12, taps=taps)
+    print("[raft] flow_low err %.3e flow_up err %.3e" % (float((lo_r - lo_o).abs().max()), float((up_r - up_o).abs().max())))
+    assert torch.equal(lo_r, lo_o) and torch.equal(up_r, up_o)
+    fwd_r = padder.unpad(up_r[0]).permute(1, 2, 0).numpy()
+    fwd_o, bwd_o = oraft.raft_infer(sd, i1, i2, 12)
+    assert np.array_equal(fwd_r, fwd_o)
+    rgb_r, md_r = renc.process_flow(fwd_r)
+    rgb_o, md_o = oraft.process_flow(fwd_o)
+    assert np.array_equal(rgb_r, rgb_o) and md_r == md_o
+    # reference CorrBlock on the oracle's feature maps: pins corr_pyramid / corr_lookup separately
+    from raft.corr import CorrBlock
+    cb = CorrBlock(taps["fmap1"], taps["fmap2"], radius=4)
+    for l in range(4):
+        assert torch.equal(cb.corr_pyramid[l], oraft.corr_pyramid(taps["fmap1"], taps["fmap2"])[l])
+    g = torch.Generator().manual_seed(0)
+    coords = oraft.coords_grid(2, 23, 30) + 6 * torch.randn(2, 2, 23, 30, generator=g)
+    lk_r = cb(coords)
+    lk_o = oraft.corr_lookup(oraft.corr_pyramid(taps["fmap1"], taps["fmap2"]), coords)
+    assert torch.equal(lk_r, lk_o)
+    np.savez_compressed(
+        os.path.join(GOLD, "raft_240x320.npz"),
+        seed=0, iters=12, frame_hw=np.array([240, 320]), scale=0.75, pad=np.array(padder._pad),
+        resized0=a[0].permute(1, 2, 0).numpy().astype(np.uint8),
+        fmap1=taps["fmap1"].numpy().astype(np.float16), fmap2=taps["fmap2"].numpy().astype(np.float16),
+        corr_l0_rows=cb.corr_pyramid[0][:64, 0].numpy().astype(np.float32),        # first 64 rows of image 0
+        corr_l3_rows=cb.corr_pyramid[3][:64, 0].numpy().astype(np.float32),
+        coords=coords.numpy().astype(np.float32), lookup=lk_r.numpy().astype(np.float16),
+        flow_fwd=fwd_r.astype(np.float32), flow_rgb=rgb_r, flow_max=np.float32(md_r),
+    )
+    print("[raft] wrote fixture; max|flow| %.2f" % float(np.abs(fwd_r).max()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sizes", "da_small", "da_vits"]
+    which = sys.argv[1:] or ["sizes", "da_small", "da_vits", "raft"]
     if "sizes" in which:
         golden_sizes()
     if "da_small" in which:
         golden_da("vits", 160, 208, "vits_160x208")   # net input 518x672 (lower_bound up-scales small frames)
     if "da_vits" in which:
         golden_da("vits", 480, 640, "vits_480x640")   # BASELINE config 1 stand-in (SURVEY.md §8c)
+    if "raft" in which:
+        golden_raft()
+

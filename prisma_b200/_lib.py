@@ -30,6 +30,14 @@ SIGNATURES = {
     "prisma_depth_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "prisma_depth_work": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
     "prisma_engine_destroy": (C.c_int, [C.c_void_p]),
+    "prisma_flow_preprocess": (C.c_int, [C.c_int, c_u8_p, C.c_int, C.c_int, C.c_float, c_u8_p, c_float_p]),
+    "prisma_flow_encode": (C.c_int, [C.c_int, c_float_p, C.c_int, C.c_int, c_u8_p, c_float_p]),
+    "prisma_flowcorr_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "prisma_flowcorr_set_fmaps": (C.c_int, [C.c_void_p, c_float_p, c_float_p]),
+    "prisma_flowcorr_build": (C.c_int, [C.c_void_p, C.c_int, c_float_p]),
+    "prisma_flowcorr_lookup": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int, c_float_p]),
+    "prisma_flowcorr_read_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p]),
+    "prisma_flowcorr_work": (C.c_int, [C.c_void_p, c_double_p]),
     "prisma_debug_gemm": (C.c_int, [C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, c_float_p]),
     "prisma_debug_conv": (C.c_int, [C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,

@@ -6,12 +6,14 @@
 #include <vector>
 
 #include "engine_da.cuh"
+#include "flow.cuh"
 
 using namespace prisma;
 
 struct prisma_engine {
-  int kind;  // 1 = depth
+  int kind;  // 1 = depth, 2 = flow correlation
   DepthEngine* depth;
+  FlowCorr* corr;
 };
 
 #define API_GUARD_BEGIN try {
@@ -94,7 +96,7 @@ int prisma_depth_create(const char* encoder, int device, prisma_engine** out) {
   DepthEngine* d = new DepthEngine();
   int r = d->init(encoder, device);
   if (r != 0) { delete d; return r; }
-  prisma_engine* e = new prisma_engine{1, d};
+  prisma_engine* e = new prisma_engine{1, d, nullptr};
   *out = e;
   return 0;
   API_GUARD_END
@@ -168,6 +170,7 @@ int prisma_engine_destroy(prisma_engine* e) {
   API_GUARD_BEGIN
   if (!e) return 0;
   delete e->depth;
+  delete e->corr;
   delete e;
   return 0;
   API_GUARD_END
@@ -322,6 +325,101 @@ int prisma_debug_da_preprocess(int device, const uint8_t* rgb, int h, int w, flo
   PRISMA_CUDA_OK(cudaMemcpy(di, rgb, (size_t)h * w * 3, cudaMemcpyHostToDevice));
   PRISMA_TRY(da_preprocess(di, h, w, dout, hn, wn, 0));
   PRISMA_CUDA_OK(cudaMemcpy(out, dout, (size_t)3 * hn * wn * 4, cudaMemcpyDeviceToHost));
+  return 0;
+  API_GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------------ RAFT band (HBM-bound stages)
+static FlowCorr* as_corr(prisma_engine* e) {
+  if (!e || e->kind != 2 || !e->corr) { set_last_error("not a flow-correlation handle"); return nullptr; }
+  return e->corr;
+}
+
+int prisma_flow_preprocess(int device, const uint8_t* rgb, int h, int w, float scale, uint8_t* resized, float* chw) {
+  API_GUARD_BEGIN
+  int sms = 0;
+  PRISMA_TRY(device_sms(device, &sms));
+  PRISMA_CHECK(rgb && chw && h > 0 && w > 0 && scale > 0.f, "bad argument");
+  const int hs = (int)nearbyint((double)h * scale), ws = (int)nearbyint((double)w * scale);
+  const int pad_h = (((hs / 8) + 1) * 8 - hs) % 8, pad_w = (((ws / 8) + 1) * 8 - ws) % 8;  // common/flow.py:46-53
+  const int pad[4] = {pad_w / 2, pad_w - pad_w / 2, pad_h / 2, pad_h - pad_h / 2};
+  const int hp = hs + pad_h, wp = ws + pad_w;
+  Scratch sc;
+  uint8_t* di = sc.alloc<uint8_t>((size_t)h * w * 3);
+  uint8_t* dr = sc.alloc<uint8_t>((size_t)hs * ws * 3);
+  float* dc = sc.alloc<float>((size_t)3 * hp * wp);
+  PRISMA_CHECK(di && dr && dc, "cudaMalloc failed");
+  PRISMA_CUDA_OK(cudaMemcpy(di, rgb, (size_t)h * w * 3, cudaMemcpyHostToDevice));
+  PRISMA_TRY(raft_preprocess(di, h, w, hs, ws, pad, dr, dc, 0));
+  if (resized) PRISMA_CUDA_OK(cudaMemcpy(resized, dr, (size_t)hs * ws * 3, cudaMemcpyDeviceToHost));
+  PRISMA_CUDA_OK(cudaMemcpy(chw, dc, (size_t)3 * hp * wp * 4, cudaMemcpyDeviceToHost));
+  return 0;
+  API_GUARD_END
+}
+
+int prisma_flow_encode(int device, const float* flow, int h, int w, uint8_t* rgb_out, float* max_disp_out) {
+  API_GUARD_BEGIN
+  int sms = 0;
+  PRISMA_TRY(device_sms(device, &sms));
+  PRISMA_CHECK(flow && rgb_out, "null argument");
+  Scratch sc;
+  float* df = sc.alloc<float>((size_t)h * w * 2);
+  uint8_t* dr = sc.alloc<uint8_t>((size_t)h * w * 3);
+  uint32_t* dm = sc.alloc<uint32_t>(2);
+  float* dmax = sc.alloc<float>(2);
+  PRISMA_CHECK(df && dr && dm && dmax, "cudaMalloc failed");
+  PRISMA_CUDA_OK(cudaMemcpy(df, flow, (size_t)h * w * 8, cudaMemcpyHostToDevice));
+  PRISMA_TRY(flow_encode(df, h, w, dr, dm, dmax, sms, 0));
+  PRISMA_CUDA_OK(cudaMemcpy(rgb_out, dr, (size_t)h * w * 3, cudaMemcpyDeviceToHost));
+  float m = 0;
+  PRISMA_CUDA_OK(cudaMemcpy(&m, dmax, 4, cudaMemcpyDeviceToHost));
+  if (max_disp_out) *max_disp_out = m;
+  return 0;
+  API_GUARD_END
+}
+
+int prisma_flowcorr_create(int device, int batch, int h8, int w8, prisma_engine** out) {
+  API_GUARD_BEGIN
+  PRISMA_CHECK(out != nullptr, "null argument");
+  FlowCorr* c = new FlowCorr();
+  int r = c->init(device, batch, h8, w8);
+  if (r != 0) { delete c; return r; }
+  *out = new prisma_engine{2, nullptr, c};
+  return 0;
+  API_GUARD_END
+}
+int prisma_flowcorr_set_fmaps(prisma_engine* e, const float* fmap1, const float* fmap2) {
+  API_GUARD_BEGIN
+  FlowCorr* c = as_corr(e);
+  PRISMA_CHECK(fmap1 && fmap2, "null argument");
+  return c ? c->set_fmaps(fmap1, fmap2) : -1;
+  API_GUARD_END
+}
+int prisma_flowcorr_build(prisma_engine* e, int iters, float* ms_out) {
+  API_GUARD_BEGIN
+  FlowCorr* c = as_corr(e);
+  return c ? c->time_build(iters > 0 ? iters : 1, ms_out) : -1;
+  API_GUARD_END
+}
+int prisma_flowcorr_lookup(prisma_engine* e, const float* coords, float* out, int iters, float* ms_out) {
+  API_GUARD_BEGIN
+  FlowCorr* c = as_corr(e);
+  PRISMA_CHECK(coords != nullptr, "null argument");
+  return c ? c->lookup_host(coords, out, iters > 0 ? iters : 1, ms_out) : -1;
+  API_GUARD_END
+}
+int prisma_flowcorr_read_level(prisma_engine* e, int level, int b, int row0, int nrows, float* out) {
+  API_GUARD_BEGIN
+  FlowCorr* c = as_corr(e);
+  return c ? c->read_level(level, b, row0, nrows, out) : -1;
+  API_GUARD_END
+}
+int prisma_flowcorr_work(prisma_engine* e, double* out2) {
+  API_GUARD_BEGIN
+  FlowCorr* c = as_corr(e);
+  if (!c) return -1;
+  out2[0] = c->flops_build;
+  out2[1] = c->bytes_build;
   return 0;
   API_GUARD_END
 }

@@ -1,0 +1,357 @@
+// prisma_b200 -- RAFT band kernels that are HBM / gather bound.
+#include "flow.cuh"
+
+#include <algorithm>
+#include <functional>
+
+#include "pointwise.cuh"
+
+namespace prisma {
+
+// ------------------------------------------------------------------------------------------------
+// K11: cv2.resize(frame_u8, fx=fy=scale, INTER_CUBIC) -> load_image -> InputPadder('sintel') replicate pad ->
+// 2*(x/255)-1 (bands/flow_raft.py:100-101, common/flow.py:13-16,46-56, raft/raft.py:90-91).
+// OpenCV's 8-bit cubic path: tap weights (float, A=-0.75, 4th = 1-sum) scaled by 2048 and truncated to short,
+// horizontal pass in int32, vertical pass in fp32 (taps * 2^-22), round-to-nearest-even, saturate.  (The weight
+// truncation and the float vertical pass were established empirically against cv2 4.13: <0.1% of the pixels differ,
+// by 1 LSB -- OpenCV's SIMD rounding is build-dependent, see tests/test_flow_gpu.py.)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cv_cubic_coeffs_i(float x, int* c) {
+  const float A = -0.75f;
+  const float x1 = __fadd_rn(x, 1.f);
+  float f[4];
+  f[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), __fmul_rn(5.f, A)), x1), __fmul_rn(8.f, A)), x1), __fmul_rn(4.f, A));
+  f[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.f), x), __fadd_rn(A, 3.f)), x), x), 1.f);
+  const float y = __fsub_rn(1.f, x);
+  f[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.f), y), __fadd_rn(A, 3.f)), y), y), 1.f);
+  f[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, f[0]), f[1]), f[2]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c[k] = (int)__fmul_rn(f[k], 2048.f);  // truncation toward zero
+}
+
+__global__ void k_raft_resize(const uint8_t* __restrict__ img, int H, int W, uint8_t* __restrict__ out, int h, int w,
+                              double scale) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  if (ox >= w) return;
+  float fx = (float)__dsub_rn(__dmul_rn((double)ox + 0.5, scale), 0.5);
+  int sx = (int)floorf(fx);
+  fx = __fsub_rn(fx, (float)sx);
+  float fy = (float)__dsub_rn(__dmul_rn((double)oy + 0.5, scale), 0.5);
+  int sy = (int)floorf(fy);
+  fy = __fsub_rn(fy, (float)sy);
+  int cx[4], cy[4];
+  cv_cubic_coeffs_i(fx, cx);
+  cv_cubic_coeffs_i(fy, cy);
+  const float vscale = 1.0f / (2048.f * 2048.f);
+  float acc[3];
+#pragma unroll
+  for (int j = 3; j >= 0; --j) {  // OpenCV's vertical SIMD pass nests from the last tap outwards
+    const int yy = min(max(sy - 1 + j, 0), H - 1);
+    const uint8_t* row = img + (size_t)yy * W * 3;
+    const float b = __fmul_rn((float)cy[j], vscale);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int hs = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hs += (int)row[min(max(sx - 1 + k, 0), W - 1) * 3 + c] * cx[k];
+      const float t = __fmul_rn((float)hs, b);
+      acc[c] = (j == 3) ? t : __fadd_rn(t, acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[((size_t)oy * w + ox) * 3 + c] = (uint8_t)min(max(__float2int_rn(acc[c]), 0), 255);
+}
+
+__global__ void k_raft_pad_norm(const uint8_t* __restrict__ rs, int h, int w, float* __restrict__ chw, int hp, int wp,
+                                int pad_l, int pad_t) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= wp) return;
+  const int sx = min(max(x - pad_l, 0), w - 1), sy = min(max(y - pad_t, 0), h - 1);  // replicate
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = (float)rs[((size_t)sy * w + sx) * 3 + c];
+    chw[((size_t)c * hp + y) * wp + x] = __fsub_rn(__fmul_rn(2.f, __fdiv_rn(v, 255.f)), 1.f);
+  }
+}
+
+int raft_preprocess(const uint8_t* img, int H, int W, int h, int w, const int pad[4], uint8_t* resized, float* chw,
+                    cudaStream_t s) {
+  const double scale = 1.0 / ((double)w / (double)W);  // the band passes fx=fy; cv2 derives dsize = round(src*fx)
+  dim3 block(128), grid(ceil_div(w, 128), h);
+  k_raft_resize<<<grid, block, 0, s>>>(img, H, W, resized, h, w, scale);
+  const int hp = h + pad[2] + pad[3], wp = w + pad[0] + pad[1];
+  dim3 grid2(ceil_div(wp, 128), hp);
+  k_raft_pad_norm<<<grid2, block, 0, s>>>(resized, h, w, chw, hp, wp, pad[0], pad[2]);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K20: process_flow (common/encode.py:113-126): max |flow|, polar HSV encode, truncating u8 cast.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord_pos(float f) { return __float_as_uint(f); }  // distances are >= 0
+
+__global__ void k_flow_max(const float2* __restrict__ flow, long long n, uint32_t* __restrict__ mx) {
+  float hi = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float2 f = flow[i];
+    hi = fmaxf(hi, __fsqrt_rn(__fadd_rn(__fmul_rn(f.x, f.x), __fmul_rn(f.y, f.y))));
+  }
+  hi = warp_max(hi);
+  if ((threadIdx.x & 31) == 0) atomicMax(mx, f2ord_pos(hi));
+}
+__global__ void k_zero_u32(uint32_t* p) { *p = 0u; }
+
+__device__ __forceinline__ uint8_t polar_channel_u8(float h6f, double off, double rad, double one_minus_rad) {
+  double v = fmod(__dadd_rn((double)h6f, off) , 6.0);
+  // note: the reference adds the channel offset in f32 (hue*6.0 + 4.0 on an f32 array) before the f64 mod
+  v = __dsub_rn(fabs(__dsub_rn(v, 3.0)), 1.0);
+  v = fmin(fmax(v, 0.0), 1.0);
+  v = __dadd_rn(__dmul_rn(v, rad), one_minus_rad);
+  return (uint8_t)(int)__dmul_rn(v, 255.0);
+}
+
+__global__ void k_flow_encode(const float2* __restrict__ flow, long long n, const uint32_t* __restrict__ mx,
+                              uint8_t* __restrict__ rgb, float* __restrict__ max_out) {
+  const float maxd = __uint_as_float(*mx);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && max_out) *max_out = maxd;
+  const float PI_F = 3.14159274101257324f;  // float32(np.pi)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint8_t* o = rgb + i * 3;
+    if (!(maxd > 0.f)) { o[0] = o[1] = o[2] = 0; continue; }  // reference: 0/0 -> NaN -> astype(u8) == 0 on x86
+    const float2 f = flow[i];
+    const float dX = __fdiv_rn(f.x, maxd), dY = __fdiv_rn(f.y, maxd);
+    const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(dX, dX), __fmul_rn(dY, dY)));
+    const float ang = (float)atan2((double)dY, (double)dX);  // correctly rounded f32 arctan2
+    const float a = __fmul_rn(__fadd_rn(__fdiv_rn(ang, PI_F), 1.0f), 0.5f);
+    const float h6 = __fmul_rn(a, 6.0f);
+    const float h6g = __fadd_rn(h6, 4.0f), h6b = __fadd_rn(h6, 2.0f);  // f32 adds, as numpy does on the f32 array
+    const double radd = (double)rad, omr = (double)__fsub_rn(1.0f, rad);
+    o[0] = polar_channel_u8(h6, 0.0, radd, omr);
+    o[1] = polar_channel_u8(h6g, 0.0, radd, omr);
+    o[2] = polar_channel_u8(h6b, 0.0, radd, omr);
+  }
+}
+
+int flow_encode(const float* flow, int H, int W, uint8_t* rgb, uint32_t* mm_scratch, float* max_out, int num_sms,
+                cudaStream_t s) {
+  const long long n = (long long)H * W;
+  k_zero_u32<<<1, 1, 0, s>>>(mm_scratch);
+  k_flow_max<<<num_sms * 4, 256, 0, s>>>(reinterpret_cast<const float2*>(flow), n, mm_scratch);
+  k_flow_encode<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float2*>(flow), n, mm_scratch, rgb, max_out);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K14 (by linearity): avg_pool2d of the correlation volume over its last two dims == correlation with the
+// average-pooled fmap2.  Pool fmap2 (fp16 [P][C]) into the three coarser levels (floor sizes, corr.py:24-27).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pool_fmap(const __half* __restrict__ f, int H8, int W8, int C, __half* __restrict__ out, int lh, int lw,
+                            int win) {
+  const int cell = blockIdx.x;  // y * lw + x
+  const int y = cell / lw, x = cell - y * lw;
+  const float inv = 1.0f / (float)(win * win);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int dy = 0; dy < win; ++dy)
+      for (int dx = 0; dx < win; ++dx) acc += __half2float(f[((size_t)(y * win + dy) * W8 + x * win + dx) * C + c]);
+    out[(size_t)cell * C + c] = __float2half_rn(acc * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K15: CorrBlock.__call__ (raft/corr.py:29-50) + bilinear_sampler (raft/utils/utils.py:58-72).
+// One warp per (image, position).  For pyramid level l the 9x9 window of integer offsets around coords/2^l shares
+// one fractional part, so a 10x10 neighbourhood is fetched once: lanes 10g..10g+9 (g = level group) hold one column
+// each (10 rows in registers), the right-hand column comes from lane+1 by shuffle.  Channel = l*81 + i*9 + j with
+// i moving x and j moving y (the reference's meshgrid quirk), zero outside the volume.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_corr_lookup(const float* __restrict__ v0, const float* __restrict__ v1, const float* __restrict__ v2,
+                              const float* __restrict__ v3, int B, int P, int H8, int W8, int lh0, int lw0, int lp0,
+                              int lh1, int lw1, int lp1, int lh2, int lw2, int lp2, int lh3, int lw3, int lp3,
+                              const float* __restrict__ coords, __half* __restrict__ out, int out_ld) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= B * P) return;
+  const int b = wid / P, i = wid - b * P;
+  const float cx = coords[((size_t)b * 2 + 0) * P + i], cy = coords[((size_t)b * 2 + 1) * P + i];
+  const int grp = lane / 10, col = lane - grp * 10;  // lanes 30,31 idle
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int lvl = pass == 0 ? grp : 3;
+    const bool active = pass == 0 ? (grp < 3) : (grp == 0);
+    const float* vol = lvl == 0 ? v0 : (lvl == 1 ? v1 : (lvl == 2 ? v2 : v3));
+    const int lh = lvl == 0 ? lh0 : (lvl == 1 ? lh1 : (lvl == 2 ? lh2 : lh3));
+    const int lw = lvl == 0 ? lw0 : (lvl == 1 ? lw1 : (lvl == 2 ? lw2 : lw3));
+    const int lp = lvl == 0 ? lp0 : (lvl == 1 ? lp1 : (lvl == 2 ? lp2 : lp3));
+    const float inv = lvl == 0 ? 1.f : (lvl == 1 ? 0.5f : (lvl == 2 ? 0.25f : 0.125f));
+    const float x = cx * inv, y = cy * inv;  // division by 2^l is exact
+    const float xf = floorf(x), yf = floorf(y);
+    const float wx1 = x - xf, wy1 = y - yf, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    const int x0 = (int)xf - 4 + col, y0 = (int)yf - 4;
+    const float* row = vol + (size_t)wid * lp;
+    float v[10];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const int yy = y0 + r;
+      v[r] = (active && x0 >= 0 && x0 < lw && yy >= 0 && yy < lh) ? __ldg(row + (size_t)yy * lw + x0) : 0.f;
+    }
+    float vn[10];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) vn[r] = __shfl_down_sync(0xffffffffu, v[r], 1);
+    if (active && col < 9) {
+      __half* o = out + (size_t)wid * out_ld + lvl * 81 + col * 9;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const float s = wy0 * (wx0 * v[j] + wx1 * vn[j]) + wy1 * (wx0 * v[j + 1] + wx1 * vn[j + 1]);
+        o[j] = __float2half_rn(s);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ FlowCorr
+template <typename T>
+static int fc_alloc(std::vector<void*>& pool, T** out, size_t n) {
+  void* p = nullptr;
+  PRISMA_CUDA_OK(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 256)));
+  PRISMA_CUDA_OK(cudaMemset(p, 0, std::max<size_t>(n * sizeof(T), 256)));
+  pool.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+
+FlowCorr::~FlowCorr() {
+  cudaSetDevice(device);
+  for (void* p : allocs) cudaFree(p);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int FlowCorr::init(int dev, int batch, int h8, int w8) {
+  device = dev; B = batch; H8 = h8; W8 = w8; P = h8 * w8;
+  PRISMA_CHECK(batch >= 1 && h8 >= 8 && w8 >= 8, "flowcorr: bad geometry");
+  PRISMA_CUDA_OK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  PRISMA_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  PRISMA_CHECK(prop.major == 10, "prisma_b200 kernels are sm_100a only; there is no fallback path");
+  num_sms = prop.multiProcessorCount;
+  PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  rows_pad = round_up(P, 256);
+  PRISMA_TRY(fc_alloc(allocs, &fmap1, (size_t)B * rows_pad * C));
+  for (int l = 0; l < 4; ++l) {
+    lh[l] = H8 >> l; lw[l] = W8 >> l; ln[l] = lh[l] * lw[l];
+    lpitch[l] = round_up(ln[l], 4);
+    lrows_pad[l] = round_up(lpitch[l], 256);
+    PRISMA_TRY(fc_alloc(allocs, &fmap2[l], (size_t)B * lrows_pad[l] * C));
+    PRISMA_TRY(fc_alloc(allocs, &vol[l], (size_t)B * P * lpitch[l]));
+  }
+  PRISMA_TRY(fc_alloc(allocs, &coords, (size_t)B * 2 * P));
+  PRISMA_TRY(fc_alloc(allocs, &lookup_out, (size_t)B * P * 384));
+  // one GEMM per (image, level): vol_l[b] = fmap1[b] . fmap2_l[b]^T / sqrt(C)      (corr.py:53-60)
+  const int off[1] = {0};
+  bytes_build = flops_build = 0;
+  for (int b = 0; b < B; ++b)
+    for (int l = 0; l < 4; ++l) {
+      GemmEpilogue ep;
+      ep.alpha = 1.0f / sqrtf((float)C);
+      ep.out_f32 = vol[l] + (size_t)b * P * lpitch[l];
+      ep.out_f32_ld = lpitch[l];
+      GemmLaunch g;
+      PRISMA_TRY(gemm_prepare(&g, fmap1 + (size_t)b * rows_pad * C, P, C, C, fmap2[l] + (size_t)b * lrows_pad[l] * C,
+                              lrows_pad[l], P, lpitch[l], 1, off, ep, num_sms));
+      gemms.push_back(g);
+      flops_build += 2.0 * P * (double)ln[l] * C;
+      bytes_build += 4.0 * P * (double)ln[l];
+    }
+  bytes_build += 2.0 * B * P * (double)C * 2.0;  // the two fp16 feature maps, read once
+  return 0;
+}
+
+int FlowCorr::set_fmaps(const float* f1, const float* f2) {
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  std::vector<__half> h((size_t)B * rows_pad * C, __float2half_rn(0.f));
+  for (int which = 0; which < 2; ++which) {
+    const float* src = which == 0 ? f1 : f2;
+    std::fill(h.begin(), h.end(), __float2half_rn(0.f));
+    for (int b = 0; b < B; ++b)
+      for (int c = 0; c < C; ++c)
+        for (int p = 0; p < P; ++p)
+          h[((size_t)b * rows_pad + p) * C + c] = __float2half_rn(src[((size_t)b * C + c) * P + p]);
+    if (which == 0) {
+      PRISMA_CUDA_OK(cudaMemcpy(fmap1, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    } else {
+      // level 0 buffer has lrows_pad[0] == rows_pad rows per image
+      PRISMA_CUDA_OK(cudaMemcpy(fmap2[0], h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    }
+  }
+  return 0;
+}
+
+int FlowCorr::build(cudaStream_t s) {
+  for (int b = 0; b < B; ++b)
+    for (int l = 1; l < 4; ++l)
+      k_pool_fmap<<<ln[l], 128, 0, s>>>(fmap2[0] + (size_t)b * lrows_pad[0] * C, H8, W8, C,
+                                        fmap2[l] + (size_t)b * lrows_pad[l] * C, lh[l], lw[l], 1 << l);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  for (auto& g : gemms) PRISMA_TRY(gemm_run(g, s));
+  return 0;
+}
+
+int FlowCorr::lookup(const float* d_coords, cudaStream_t s) {
+  const int warps = B * P;
+  k_corr_lookup<<<ceil_div(warps * 32, 256), 256, 0, s>>>(vol[0], vol[1], vol[2], vol[3], B, P, H8, W8, lh[0], lw[0],
+                                                          lpitch[0], lh[1], lw[1], lpitch[1], lh[2], lw[2], lpitch[2],
+                                                          lh[3], lw[3], lpitch[3], d_coords, lookup_out, 384);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int timed_loop(cudaStream_t s, int iters, float* ms, const std::function<int()>& fn) {
+  cudaEvent_t a, b;
+  PRISMA_CUDA_OK(cudaEventCreate(&a));
+  PRISMA_CUDA_OK(cudaEventCreate(&b));
+  PRISMA_TRY(fn());
+  PRISMA_CUDA_OK(cudaEventRecord(a, s));
+  for (int i = 0; i < iters; ++i) PRISMA_TRY(fn());
+  PRISMA_CUDA_OK(cudaEventRecord(b, s));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(s));
+  float t = 0;
+  PRISMA_CUDA_OK(cudaEventElapsedTime(&t, a, b));
+  if (ms) *ms = t / std::max(iters, 1);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return 0;
+}
+
+int FlowCorr::time_build(int iters, float* ms) {
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  return timed_loop(stream, iters, ms, [&]() { return build(stream); });
+}
+
+int FlowCorr::lookup_host(const float* c, float* out_nchw, int iters, float* ms) {
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_CUDA_OK(cudaMemcpy(coords, c, (size_t)B * 2 * P * 4, cudaMemcpyHostToDevice));
+  PRISMA_TRY(timed_loop(stream, iters, ms, [&]() { return lookup(coords, stream); }));
+  if (out_nchw) {
+    std::vector<__half> h((size_t)B * P * 384);
+    PRISMA_CUDA_OK(cudaMemcpy(h.data(), lookup_out, h.size() * 2, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b)
+      for (int k = 0; k < 324; ++k)
+        for (int p = 0; p < P; ++p)
+          out_nchw[((size_t)b * 324 + k) * P + p] = __half2float(h[((size_t)b * P + p) * 384 + k]);
+  }
+  return 0;
+}
+
+int FlowCorr::read_level(int level, int b, int row0, int nrows, float* out) {
+  PRISMA_CHECK(level >= 0 && level < 4 && b >= 0 && b < B && row0 >= 0 && row0 + nrows <= P, "flowcorr: bad range");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_CUDA_OK(cudaMemcpy2D(out, (size_t)ln[level] * 4, vol[level] + ((size_t)b * P + row0) * lpitch[level],
+                              (size_t)lpitch[level] * 4, (size_t)ln[level] * 4, nrows, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // namespace prisma

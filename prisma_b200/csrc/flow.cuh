@@ -1,0 +1,41 @@
+// prisma_b200 -- RAFT band, HBM-bound part: pre-process (K11), all-pairs correlation pyramid (K13+K14, on the tcgen05
+// GEMM core), correlation lookup (K15) and HSV flow encode (K20).  See flow.cu.
+#pragma once
+#include <vector>
+
+#include "gemm_tc.cuh"
+
+namespace prisma {
+
+int raft_preprocess(const uint8_t* img, int H, int W, int h, int w, const int pad[4], uint8_t* resized, float* chw,
+                    cudaStream_t s);
+int flow_encode(const float* flow, int H, int W, uint8_t* rgb, uint32_t* mm_scratch, float* max_out, int num_sms,
+                cudaStream_t s);
+
+// All-pairs correlation pyramid + lookup for `batch` image pairs at 1/8 resolution (h8 x w8, C = 256 channels).
+class FlowCorr {
+ public:
+  ~FlowCorr();
+  int init(int device, int batch, int h8, int w8);
+  int set_fmaps(const float* fmap1_nchw, const float* fmap2_nchw);  // host fp32 [B][256][h8][w8]
+  int build(cudaStream_t s);                                        // K13 + K14
+  int lookup(const float* d_coords, cudaStream_t s);                // K15: coords device fp32 [B][2][h8][w8]
+  int lookup_host(const float* coords, float* out_nchw, int iters, float* ms);
+  int time_build(int iters, float* ms);
+  int read_level(int level, int b, int row0, int nrows, float* out);
+
+  int device = 0, B = 0, H8 = 0, W8 = 0, P = 0, C = 256, num_sms = 148;
+  int lh[4], lw[4], ln[4], lpitch[4];  // level sizes, element counts, row pitch (multiple of 4) of the fp32 volumes
+  __half* fmap1 = nullptr;             // [B][P][C]   (rows padded to the next multiple of 256)
+  __half* fmap2[4] = {nullptr, nullptr, nullptr, nullptr};  // per level [B][ln_pad][C]: level l = 2^l x 2^l mean of fmap2
+  float* vol[4] = {nullptr, nullptr, nullptr, nullptr};     // per level fp32 [B*P][lpitch]
+  float* coords = nullptr;
+  __half* lookup_out = nullptr;  // [B*P][384] fp16 (324 used), the A operand of the motion encoder's convc1
+  int rows_pad = 0, lrows_pad[4];
+  std::vector<GemmLaunch> gemms;
+  std::vector<void*> allocs;
+  cudaStream_t stream = nullptr;
+  double bytes_build = 0, flops_build = 0;
+};
+
+}  // namespace prisma

@@ -35,6 +35,7 @@ enum RowMap : int {
 };
 
 struct GemmEpilogue {
+  float alpha = 1.0f;            // accumulator scale (e.g. 1/sqrt(C) of the RAFT correlation), applied first
   const float* bias = nullptr;   // [N]
   const float* gamma = nullptr;  // [N]  LayerScale
   int act = 0;                   // 0 none, 1 exact-erf GELU, 2 ReLU
@@ -109,7 +110,10 @@ __device__ __forceinline__ void add_h4(float4& v, const uint2& r) {
 __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&v)[8], const int (&dr)[8], uint32_t okm,
                                                const float4& bias, const float4& gamma, int col) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { v[i].x += bias.x; v[i].y += bias.y; v[i].z += bias.z; v[i].w += bias.w; }
+  for (int i = 0; i < 8; ++i) {
+    v[i].x = fmaf(v[i].x, ep.alpha, bias.x); v[i].y = fmaf(v[i].y, ep.alpha, bias.y);
+    v[i].z = fmaf(v[i].z, ep.alpha, bias.z); v[i].w = fmaf(v[i].w, ep.alpha, bias.w);
+  }
   if (ep.act == 1) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i].x = gelu_erf(v[i].x); v[i].y = gelu_erf(v[i].y); v[i].z = gelu_erf(v[i].z); v[i].w = gelu_erf(v[i].w); }

@@ -1,0 +1,174 @@
+"""Deterministic seeded weights for offline runs, the tests and the oracle (no arithmetic of the hot path here).
+
+No checkpoint is reachable offline (weights come from
+download_models.sh / HF hub), so parity is asserted on seeded random weights.
+Tensor *names and shapes* are exactly the reference ``state_dict`` ones
+(verified by ``oracle/tools/make_golden.py`` which
+``load_state_dict(strict=True)``s them into the reference modules), so the
+product's converter accepts real checkpoints unchanged.
+
+Distributions follow the reference modules' own initialisers (trunc-normal
+0.02 ViT linears, torch-default kaiming-uniform convs) but, unlike them, biases, LayerNorm
+affine and LayerScale are non-trivial, so a swapped bias or a dropped gamma shows up in parity.  Values depend only on (seed, tensor name) through a CPU
+``torch.Generator`` -> identical in the authoring container and on the GPU box.
+"""
+import zlib
+
+import torch
+
+DA_CONFIGS = {
+    # dim, depth, heads: bands/d_anything/torchhub/.../vision_transformer.py:339-378
+    # features/out_channels: ViT-L from patchfusion/.../base_models/depth_anything.py:339,
+    # ViT-S/B from the upstream HF config.json (not in tree)
+    "vits": dict(dim=384, depth=12, heads=6, features=64, out_channels=[48, 96, 192, 384]),
+    "vitb": dict(dim=768, depth=12, heads=12, features=128, out_channels=[96, 192, 384, 768]),
+    "vitl": dict(dim=1024, depth=24, heads=16, features=256, out_channels=[256, 512, 1024, 1024]),
+}
+
+
+def _gen(name, seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+    return g
+
+
+def _normal(name, seed, shape, std, mean=0.0):
+    return torch.randn(shape, generator=_gen(name, seed), dtype=torch.float32) * std + mean
+
+
+def _uniform(name, seed, shape, lo, hi):
+    return torch.rand(shape, generator=_gen(name, seed), dtype=torch.float32) * (hi - lo) + lo
+
+
+def make_da_weights(encoder="vits", seed=0):
+    """state_dict of DPT_DINOv2(encoder) (bands/d_anything/dpt.py:139-153) with seeded values."""
+    c = DA_CONFIGS[encoder]
+    D, depth, F, oc = c["dim"], c["depth"], c["features"], c["out_channels"]
+    sd = {}
+
+    def lin(name, out_f, in_f, bias=True, std=None):
+        std = std if std is not None else 0.02
+        sd[name + ".weight"] = _normal(name + ".weight", seed, (out_f, in_f), std)
+        if bias:
+            sd[name + ".bias"] = _normal(name + ".bias", seed, (out_f,), 0.01)
+
+    def conv(name, out_c, in_c, kh, kw, bias=True, transpose=False):
+        # torch's default conv initialiser (what the reference modules get): kaiming_uniform(a=sqrt(5))
+        # -> U(-b, b), b = 1/sqrt(fan_in); fan_in of a ConvTranspose2d weight [in,out,kh,kw] is out*kh*kw
+        fan_in = (out_c if transpose else in_c) * kh * kw
+        b = (1.0 / fan_in) ** 0.5
+        shape = (in_c, out_c, kh, kw) if transpose else (out_c, in_c, kh, kw)
+        sd[name + ".weight"] = _uniform(name + ".weight", seed, shape, -b, b)
+        if bias:
+            sd[name + ".bias"] = _uniform(name + ".bias", seed, (out_c,), -b, b)
+
+    def ln(name, dim):
+        sd[name + ".weight"] = _normal(name + ".weight", seed, (dim,), 0.1, 1.0)
+        sd[name + ".bias"] = _normal(name + ".bias", seed, (dim,), 0.05)
+
+    p = "pretrained."
+    sd[p + "cls_token"] = _normal(p + "cls_token", seed, (1, 1, D), 0.02)
+    sd[p + "pos_embed"] = _normal(p + "pos_embed", seed, (1, 1370, D), 0.02)
+    sd[p + "mask_token"] = torch.zeros(1, D)
+    sd[p + "patch_embed.proj.weight"] = _normal(p + "patch_embed.proj.weight", seed, (D, 3, 14, 14), 0.02)
+    sd[p + "patch_embed.proj.bias"] = _normal(p + "patch_embed.proj.bias", seed, (D,), 0.02)
+    for i in range(depth):
+        b = f"{p}blocks.{i}."
+        ln(b + "norm1", D)
+        lin(b + "attn.qkv", 3 * D, D, std=0.04)  # larger than 0.02 so attention is not uniform
+        lin(b + "attn.proj", D, D)
+        sd[b + "ls1.gamma"] = _uniform(b + "ls1.gamma", seed, (D,), 0.3, 1.0)
+        ln(b + "norm2", D)
+        lin(b + "mlp.fc1", 4 * D, D)
+        lin(b + "mlp.fc2", D, 4 * D)
+        sd[b + "ls2.gamma"] = _uniform(b + "ls2.gamma", seed, (D,), 0.3, 1.0)
+    ln(p + "norm", D)
+
+    h = "depth_head."
+    for i, c_out in enumerate(oc):
+        conv(f"{h}projects.{i}", c_out, D, 1, 1)
+    conv(h + "resize_layers.0", oc[0], oc[0], 4, 4, transpose=True)
+    conv(h + "resize_layers.1", oc[1], oc[1], 2, 2, transpose=True)
+    conv(h + "resize_layers.3", oc[3], oc[3], 3, 3)
+    for i in range(4):
+        conv(f"{h}scratch.layer{i + 1}_rn", F, oc[i], 3, 3, bias=False)
+    for i in range(1, 5):
+        r = f"{h}scratch.refinenet{i}."
+        conv(r + "out_conv", F, F, 1, 1)
+        for u in (1, 2):
+            conv(f"{r}resConfUnit{u}.conv1", F, F, 3, 3)
+            conv(f"{r}resConfUnit{u}.conv2", F, F, 3, 3)
+    conv(h + "scratch.output_conv1", F // 2, F, 3, 3)
+    conv(h + "scratch.output_conv2.0", 32, F // 2, 3, 3)
+    conv(h + "scratch.output_conv2.2", 1, 32, 1, 1)
+    # Final bias: positive, so that (as for the trained model and for the reference's default
+    # init) the depth map is strictly positive instead of being half
+    # clamped to 0 by the last ReLU -- a clamped map makes the band's min/max normalisation
+    # degenerate and measures cancellation noise rather than the kernels.
+    sd[h + "scratch.output_conv2.2.bias"] = torch.full((1,), 0.25)
+    return sd
+
+
+def make_raft_weights(seed=0):
+    """state_dict of RAFT(args) (bands/raft/raft.py:24-57), seeded.
+
+    Convs: kaiming_normal(fan_out, relu) as BasicEncoder's own init loop (raft/extractor.py:148-150) for the
+    encoders, torch-default kaiming-uniform for the update block (which has no init loop); biases torch-default
+    uniform.  cnet BatchNorm gets non-trivial affine + running statistics so that the eval-mode fold is tested.
+    """
+    sd = {}
+
+    def conv(name, out_c, in_c, kh, kw, mode):
+        fan_in = in_c * kh * kw
+        if mode == "kaiming_out":
+            std = (2.0 / (out_c * kh * kw)) ** 0.5
+            sd[name + ".weight"] = _normal(name + ".weight", seed, (out_c, in_c, kh, kw), std)
+        else:
+            b = (1.0 / fan_in) ** 0.5
+            sd[name + ".weight"] = _uniform(name + ".weight", seed, (out_c, in_c, kh, kw), -b, b)
+        b = (1.0 / fan_in) ** 0.5
+        sd[name + ".bias"] = _uniform(name + ".bias", seed, (out_c,), -b, b)
+
+    def bn(name, c):
+        sd[name + ".weight"] = _normal(name + ".weight", seed, (c,), 0.1, 1.0)
+        sd[name + ".bias"] = _normal(name + ".bias", seed, (c,), 0.05)
+        sd[name + ".running_mean"] = _normal(name + ".running_mean", seed, (c,), 0.1)
+        sd[name + ".running_var"] = _uniform(name + ".running_var", seed, (c,), 0.5, 1.5)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    for net, out_dim, has_bn in (("fnet", 256, False), ("cnet", 256, True)):
+        p = net + "."
+        conv(p + "conv1", 64, 3, 7, 7, "kaiming_out")
+        if has_bn:
+            bn(p + "norm1", 64)
+        cin = 64
+        for li, dim, stride in ((1, 64, 1), (2, 96, 2), (3, 128, 2)):
+            for bi in (0, 1):
+                q = f"{p}layer{li}.{bi}."
+                conv(q + "conv1", dim, cin if bi == 0 else dim, 3, 3, "kaiming_out")
+                conv(q + "conv2", dim, dim, 3, 3, "kaiming_out")
+                if has_bn:
+                    bn(q + "norm1", dim)
+                    bn(q + "norm2", dim)
+                if bi == 0 and stride != 1:
+                    conv(q + "downsample.0", dim, cin, 1, 1, "kaiming_out")
+                    if has_bn:
+                        bn(q + "norm3", dim)
+                        for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+                            sd[q + "downsample.1." + k] = sd[q + "norm3." + k]   # same module, two names
+            cin = dim
+        conv(p + "conv2", out_dim, 128, 1, 1, "kaiming_out")
+    u = "update_block."
+    conv(u + "encoder.convc1", 256, 324, 1, 1, "default")
+    conv(u + "encoder.convc2", 192, 256, 3, 3, "default")
+    conv(u + "encoder.convf1", 128, 2, 7, 7, "default")
+    conv(u + "encoder.convf2", 64, 128, 3, 3, "default")
+    conv(u + "encoder.conv", 126, 256, 3, 3, "default")
+    for g in ("z", "r", "q"):
+        conv(u + f"gru.conv{g}1", 128, 384, 1, 5, "default")
+        conv(u + f"gru.conv{g}2", 128, 384, 5, 1, "default")
+    conv(u + "flow_head.conv1", 256, 128, 3, 3, "default")
+    conv(u + "flow_head.conv2", 2, 256, 3, 3, "default")
+    conv(u + "mask.0", 256, 128, 3, 3, "default")
+    conv(u + "mask.2", 576, 256, 1, 1, "default")
+    return sd

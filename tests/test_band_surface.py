@@ -1,0 +1,55 @@
+"""Plugin surface: metadata contract (CPU) and the depth_anything band end to end into a temp PRISMA folder (GPU)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_metadata_contract(tmp_path):
+    from bands.common import meta
+    folder = str(tmp_path / "clip")
+    data = meta.create_metadata(folder)
+    assert data == {"bands": {}}
+    meta.add_band(data, "rgba", url="rgba.mp4")
+    meta.write_metadata(folder, data)
+    assert meta.get_url(folder, meta.load_metadata(folder), "rgba") == os.path.join(folder, "rgba.mp4")
+    tgt = meta.get_target(os.path.join(folder, "rgba.mp4"), data, band="depth_anything", force_extension="png")
+    assert tgt == os.path.join(folder, "depth_anything.mp4") and data["bands"]["depth_anything"]["url"] == "depth_anything.mp4"
+    tgt = meta.get_target(os.path.join(folder, "rgba.png"), data, band="depth_anything", force_extension="png")
+    assert tgt.endswith("depth_anything.png")
+    assert meta.is_video("a.mp4") and not meta.is_video("a.png")
+
+
+def test_band_cli_matches_reference_flags():
+    sys.path.insert(0, ROOT)
+    from bands import depth_anything as band
+    a = band.build_parser().parse_args(["-i", "x.mp4", "-o", "y.mp4", "-n", "-d", "frames", "--encoder", "vits", "--metric", "none"])
+    assert (a.input, a.output, a.npy, a.subpath, a.encoder, a.metric) == ("x.mp4", "y.mp4", True, "frames", "vits", "none")
+    assert band.BAND == "depth_anything"
+
+
+@pytest.mark.gpu
+def test_process_runs_band_into_prisma_folder(tmp_path):
+    import cv2
+    from oracle.frames import synthetic_frame
+    src = str(tmp_path / "clip.mp4")
+    w = cv2.VideoWriter(src, cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
+    for t in range(3):
+        w.write(synthetic_frame(240, 320, t)[..., ::-1].copy())
+    w.release()
+    rc = subprocess.call([sys.executable, os.path.join(ROOT, "process.py"), "-i", src, "--encoder", "vits", "--seeded-weights"])
+    assert rc == 0
+    folder = str(tmp_path / "clip")
+    meta = json.load(open(os.path.join(folder, "metadata.json")))
+    band = meta["bands"]["depth_anything"]
+    assert band["url"] == "depth_anything.mp4" and os.path.exists(os.path.join(folder, band["url"]))
+    assert band["values"]["min"] == {"type": "float", "url": "depth_anything_min.csv"}
+    mins = [float(l) for l in open(os.path.join(folder, "depth_anything_min.csv"))]
+    maxs = [float(l) for l in open(os.path.join(folder, "depth_anything_max.csv"))]
+    assert len(mins) == 3 and all(b > a for a, b in zip(mins, maxs))
+    assert meta["bands"]["depth"] == band and meta["width"] == 320 and meta["frames"] == 3
