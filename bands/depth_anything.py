@@ -78,7 +78,7 @@ def process_video(a):
         create_folder(sub)
     mins, maxs = [], []
     for i, frame in enumerate(reader):
-        rgb, dmin, dmax, pred = model.infer_encoded(frame, want_depth=bool(a.npy))
+        rgb, dmin, dmax, pred = model.infer_encoded(frame, want_depth=True)
         if a.npy:
             np.save(os.path.join(sub or folder, "{:05d}.npy".format(i)), pred)
         out.write(rgb)

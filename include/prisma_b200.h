@@ -39,9 +39,14 @@ int prisma_depth_finalize(prisma_engine* e);
  * Includes the H2D copy of the frame and the D2H copies of the requested outputs.                          */
 int prisma_depth_infer(prisma_engine* e, const uint8_t* rgb, int h, int w, float* depth_out, uint8_t* rgb_out,
                        float* min_out, float* max_out);
-/* Same computation with the frame already resident in device memory and outputs left on the device
- * (bench.py's kernel-only leg); timing of the last call in ms via CUDA events on the engine stream.        */
-int prisma_depth_infer_resident(prisma_engine* e, int h, int w, int iters, float* ms_per_iter);
+/* n frames of one size in one pass (rgb: n*h*w*3; outputs n-major; min_out/max_out: n floats each).  Frames are
+ * independent (bands/depth_anything.py:203-221 carries no state across iterations); batching only raises the
+ * tile count of every launch.  Results are identical to n calls of prisma_depth_infer.                     */
+int prisma_depth_infer_batch(prisma_engine* e, const uint8_t* rgb, int n, int h, int w, float* depth_out,
+                             uint8_t* rgb_out, float* min_out, float* max_out);
+/* Same computation with the n frames already resident in device memory and outputs left on the device
+ * (bench.py's kernel-only leg): ms per pass (CUDA events on the engine stream) over `iters` passes.       */
+int prisma_depth_infer_resident(prisma_engine* e, int h, int w, int n, int iters, float* ms_per_iter);
 /* Encoder-only entry used by the parity tests: encode a given h*w f32 prediction (:215-220).               */
 int prisma_depth_encode(prisma_engine* e, const float* prediction, int h, int w, int flip, uint8_t* rgb_out,
                         float* min_out, float* max_out);
@@ -49,13 +54,13 @@ int prisma_depth_encode(prisma_engine* e, const float* prediction, int h, int w,
  * "net_input" [3][hn][wn], "tokens" [T][D], "feat0".."feat3" [T][D], "net_depth" [hn][wn], ...
  * returns the number of floats written, or negative.                                                       */
 long long prisma_depth_read_tap(prisma_engine* e, const char* name, float* out, long long capacity);
-/* Per-kernel-group CUDA-event timings of one frame (ms), for bench.py's roofline block:
+/* Per-kernel-group CUDA-event timings of one pass over n frames (ms), for bench.py's roofline block:
  * out[0]=pre, out[1]=encoder linear GEMMs, out[2]=attention, out[3]=layernorm, out[4]=head convs,
  * out[5]=resamplers, out[6]=post, out[7]=total.                                                             */
-int prisma_depth_profile(prisma_engine* e, int h, int w, float* out8);
-/* Algorithmic work of one frame at (h,w): out[0]=encoder-linear FLOP, out[1]=attention FLOP, out[2]=head FLOP,
- * out[3]=kernel launches per frame.                                                                         */
-int prisma_depth_work(prisma_engine* e, int h, int w, double* out4);
+int prisma_depth_profile(prisma_engine* e, int h, int w, int n, float* out8);
+/* Algorithmic work of one pass over n frames at (h,w): out[0]=encoder-linear FLOP, out[1]=attention FLOP,
+ * out[2]=head FLOP, out[3]=kernel launches per pass.                                                       */
+int prisma_depth_work(prisma_engine* e, int h, int w, int n, double* out4);
 
 int prisma_engine_destroy(prisma_engine* e);
 

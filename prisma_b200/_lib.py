@@ -24,11 +24,12 @@ SIGNATURES = {
     "prisma_depth_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, c_float_p, c_i64_p, C.c_int]),
     "prisma_depth_finalize": (C.c_int, [C.c_void_p]),
     "prisma_depth_infer": (C.c_int, [C.c_void_p, c_u8_p, C.c_int, C.c_int, c_float_p, c_u8_p, c_float_p, c_float_p]),
-    "prisma_depth_infer_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p]),
+    "prisma_depth_infer_batch": (C.c_int, [C.c_void_p, c_u8_p, C.c_int, C.c_int, C.c_int, c_float_p, c_u8_p, c_float_p, c_float_p]),
+    "prisma_depth_infer_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p]),
     "prisma_depth_encode": (C.c_int, [C.c_void_p, c_float_p, C.c_int, C.c_int, C.c_int, c_u8_p, c_float_p, c_float_p]),
     "prisma_depth_read_tap": (C.c_longlong, [C.c_void_p, C.c_char_p, c_float_p, C.c_longlong]),
-    "prisma_depth_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
-    "prisma_depth_work": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
+    "prisma_depth_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p]),
+    "prisma_depth_work": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "prisma_engine_destroy": (C.c_int, [C.c_void_p]),
     "prisma_flow_preprocess": (C.c_int, [C.c_int, c_u8_p, C.c_int, C.c_int, C.c_float, c_u8_p, c_float_p]),
     "prisma_flow_encode": (C.c_int, [C.c_int, c_float_p, C.c_int, C.c_int, c_u8_p, c_float_p]),

@@ -125,13 +125,20 @@ int prisma_depth_infer(prisma_engine* e, const uint8_t* rgb, int h, int w, float
                        float* min_out, float* max_out) {
   API_GUARD_BEGIN
   DepthEngine* d = as_depth(e);
-  return d ? d->infer(rgb, h, w, depth_out, rgb_out, min_out, max_out) : -1;
+  return d ? d->infer(rgb, 1, h, w, depth_out, rgb_out, min_out, max_out) : -1;
   API_GUARD_END
 }
-int prisma_depth_infer_resident(prisma_engine* e, int h, int w, int iters, float* ms_per_iter) {
+int prisma_depth_infer_batch(prisma_engine* e, const uint8_t* rgb, int n, int h, int w, float* depth_out,
+                             uint8_t* rgb_out, float* min_out, float* max_out) {
   API_GUARD_BEGIN
   DepthEngine* d = as_depth(e);
-  return d ? d->infer_resident(h, w, iters, ms_per_iter) : -1;
+  return d ? d->infer(rgb, n, h, w, depth_out, rgb_out, min_out, max_out) : -1;
+  API_GUARD_END
+}
+int prisma_depth_infer_resident(prisma_engine* e, int h, int w, int n, int iters, float* ms_per_iter) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  return d ? d->infer_resident(h, w, n, iters, ms_per_iter) : -1;
   API_GUARD_END
 }
 int prisma_depth_encode(prisma_engine* e, const float* prediction, int h, int w, int flip, uint8_t* rgb_out,
@@ -148,17 +155,17 @@ long long prisma_depth_read_tap(prisma_engine* e, const char* name, float* out, 
   return d ? d->read_tap(name, out, capacity) : -1;
   API_GUARD_END
 }
-int prisma_depth_profile(prisma_engine* e, int h, int w, float* out8) {
+int prisma_depth_profile(prisma_engine* e, int h, int w, int n, float* out8) {
   API_GUARD_BEGIN
   DepthEngine* d = as_depth(e);
-  return d ? d->profile(h, w, out8) : -1;
+  return d ? d->profile(h, w, n, out8) : -1;
   API_GUARD_END
 }
-int prisma_depth_work(prisma_engine* e, int h, int w, double* out4) {
+int prisma_depth_work(prisma_engine* e, int h, int w, int n, double* out4) {
   API_GUARD_BEGIN
   DepthEngine* d = as_depth(e);
   if (!d) return -1;
-  PRISMA_TRY(d->build_plan(h, w));
+  PRISMA_TRY(d->build_plan(h, w, n));
   out4[0] = d->work_linear;
   out4[1] = d->work_attn;
   out4[2] = d->work_head;

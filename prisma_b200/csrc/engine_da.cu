@@ -257,16 +257,17 @@ int DepthEngine::finalize() {
 }
 
 // ------------------------------------------------------------------------------------------------ plan
-struct PMap {  // zero-bordered NHWC fp16 feature map
+struct PMap {  // B zero-bordered NHWC fp16 feature maps, stacked image-major
   __half* p = nullptr;
-  int H = 0, W = 0, C = 0;
+  int B = 1, H = 0, W = 0, C = 0;
   int Hp() const { return H + 2; }
   int Wp() const { return W + 2; }
-  long long rows() const { return (long long)Hp() * Wp(); }
+  long long img_rows() const { return (long long)Hp() * Wp(); }
+  long long rows() const { return B * img_rows(); }
 };
 
-int DepthEngine::new_map(PMap* m, int H, int W, int C) {
-  m->H = H; m->W = W; m->C = C;
+int DepthEngine::new_map(PMap* m, int H, int W, int C) {  // `batch` images
+  m->B = batch; m->H = H; m->W = W; m->C = C;
   // +GEMM_BM rows of slack: TMA boxes never need it (OOB reads are zero-filled) but debug reads may
   return dev_alloc(plan_allocs, &m->p, (size_t)m->rows() * C, true);
 }
@@ -294,15 +295,18 @@ int DepthEngine::add_conv3x3(const char* name, const PMap& in, const __half* W, 
   ep.row_map = ROW_PADDED;
   ep.in_w = in.Wp();
   ep.in_h = in.Hp();
+  ep.img_rows = (int)in.img_rows();
   ep.sub = sub;
-  if (sub > 1) { ep.out_wp = out_geom->Wp(); ep.out_img_rows = (int)out_geom->rows(); }
-  const double flops = 2.0 * (double)(in.H / sub + (in.H % sub ? 1 : 0)) * (in.W / sub + (in.W % sub ? 1 : 0)) * 9.0 * in.C * Cout;
+  if (sub > 1) { ep.out_wp = out_geom->Wp(); ep.out_img_rows = (int)out_geom->img_rows(); }
+  const double flops = 2.0 * in.B * (double)(in.H / sub + (in.H % sub ? 1 : 0)) * (in.W / sub + (in.W % sub ? 1 : 0)) * 9.0 * in.C * Cout;
   return add_gemm(G_HEAD, name, in.p, in.rows(), in.C, in.C, W, (int)in.rows(), Cout, 9, off, ep, flops);
 }
 
-int DepthEngine::build_plan(int H, int W) {
+int DepthEngine::build_plan(int H, int W, int Bt) {
   PRISMA_CHECK(finalized, "weights not finalized");
-  if (plan_H == H && plan_W == W) return 0;
+  PRISMA_CHECK(Bt >= 1 && Bt <= 64, "batch must be in [1,64]");
+  if (plan_H == H && plan_W == W && batch == Bt) return 0;
+  batch = Bt;
   PRISMA_CUDA_OK(cudaSetDevice(device));
   PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
   for (void* q : plan_allocs) cudaFree(q);
@@ -316,48 +320,57 @@ int DepthEngine::build_plan(int H, int W) {
   ph = hn / 14; pw = wn / 14;
   const int P = ph * pw;
   T = P + 1;
+  const int BP = Bt * P, BT = Bt * T;
   const int zero_off[1] = {0};
 
   // ---- frame-level buffers
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.img, (size_t)H * W * 3));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.net_in, (size_t)3 * hn * wn));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.patches, (size_t)P * 640));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.pos, (size_t)T * D));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.x, (size_t)T * D));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.tokens_tap, (size_t)T * D));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.ln, (size_t)T * D));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.qkv, (size_t)T * 3 * D));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.attn, (size_t)T * D));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.hid, (size_t)T * 4 * D));
-  for (int i = 0; i < 4; ++i) PRISMA_TRY(dev_alloc(plan_allocs, &b.feat[i], (size_t)T * D));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.depth, (size_t)hn * wn));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.pred, (size_t)H * W));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.rgb, (size_t)H * W * 3));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.mm, 2));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.minmax, 2));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.img, (size_t)Bt * H * W * 3));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.net_in, (size_t)Bt * 3 * hn * wn));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.patches, (size_t)BP * 640));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.pos, (size_t)BT * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.x, (size_t)BT * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.tokens_tap, (size_t)BT * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.ln, (size_t)BT * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.qkv, (size_t)BT * 3 * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.attn, (size_t)BT * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.hid, (size_t)BT * 4 * D));
+  for (int i = 0; i < 4; ++i) PRISMA_TRY(dev_alloc(plan_allocs, &b.feat[i], (size_t)BP * D));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.depth, (size_t)Bt * hn * wn));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.pred, (size_t)Bt * H * W));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.rgb, (size_t)Bt * H * W * 3));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.mm, 2 * Bt));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.minmax, 2 * Bt));
 
   // pos-embed for this resolution (constant per resolution): computed once, here
   PRISMA_TRY(da_pos_embed(w.pos, w.cls, 37, D, ph, pw, b.pos, stream));
+  for (int i = 1; i < Bt; ++i)  // one copy per image so that residual rows and destination rows coincide
+    PRISMA_CUDA_OK(cudaMemcpyAsync(b.pos + (size_t)i * T * D, b.pos, (size_t)T * D * sizeof(float), cudaMemcpyDeviceToDevice, stream));
 
   // ---- pre-process + patch embed
   {
     const uint8_t* img = b.img; float* net = b.net_in; __half* pat = b.patches;
     const int hn_ = hn, wn_ = wn;
-    add(G_PRE, "da_preprocess", [=](cudaStream_t s) { return da_preprocess(img, H, W, net, hn_, wn_, s); });
-    add(G_PRE, "patchify", [=](cudaStream_t s) { return da_patchify(net, hn_, wn_, pat, 640, s); });
+    add(G_PRE, "da_preprocess", [=](cudaStream_t s) {
+      for (int i = 0; i < Bt; ++i)
+        PRISMA_TRY(da_preprocess(img + (size_t)i * H * W * 3, H, W, net + (size_t)i * 3 * hn_ * wn_, hn_, wn_, s));
+      return 0;
+    });
+    add(G_PRE, "patchify", [=](cudaStream_t s) { return da_patchify(net, Bt, hn_, wn_, pat, 640, s); });
     GemmEpilogue ep;
     ep.bias = w.patch_b;
-    ep.res_f32 = b.pos + D; ep.res_f32_ld = D;   // + pos-embed of patch tokens
-    ep.out_f32 = b.x + D; ep.out_f32_ld = D;      // token rows 1..P
-    PRISMA_TRY(add_gemm(G_LINEAR, "patch_embed", b.patches, P, 640, 640, w.patch_w, P, D, 1, zero_off, ep,
-                        2.0 * P * D * 588.0));
-    float* x = b.x; const float* pos = b.pos; const int D_ = D;
-    add(G_PRE, "cls_row", [=](cudaStream_t s) {
-      PRISMA_CUDA_OK(cudaMemcpyAsync(x, pos, D_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    ep.row_map = ROW_TOKSKIP; ep.in_w = P;       // patch rows b*P+p -> token rows b*T+1+p
+    ep.res_f32 = b.pos; ep.res_f32_ld = D;       // + pos-embed of the same token row
+    ep.out_f32 = b.x; ep.out_f32_ld = D;
+    PRISMA_TRY(add_gemm(G_LINEAR, "patch_embed", b.patches, BP, 640, 640, w.patch_w, BP, D, 1, zero_off, ep,
+                        2.0 * BP * D * 588.0));
+    float* x = b.x; const float* pos = b.pos; const int D_ = D, T_ = T;
+    add(G_PRE, "cls_rows", [=](cudaStream_t s) {  // token 0 of every image = cls + pos[0]
+      PRISMA_CUDA_OK(cudaMemcpy2DAsync(x, (size_t)T_ * D_ * sizeof(float), pos, (size_t)T_ * D_ * sizeof(float),
+                                       D_ * sizeof(float), Bt, cudaMemcpyDeviceToDevice, s));
       return 0;
     });
     if (debug_taps) {
-      float* tap = b.tokens_tap; const size_t n = (size_t)T * D;
+      float* tap = b.tokens_tap; const size_t n = (size_t)BT * D;
       add(G_PRE, "tap_tokens", [=](cudaStream_t s) {
         PRISMA_CUDA_OK(cudaMemcpyAsync(tap, x, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
         return 0;
@@ -366,26 +379,27 @@ int DepthEngine::build_plan(int H, int W) {
   }
   // ---- transformer blocks
   AttnLaunch att;
-  PRISMA_TRY(attention_prepare(&att, b.qkv, b.attn, 1, T, heads, D));
+  PRISMA_TRY(attention_prepare(&att, b.qkv, b.attn, Bt, T, heads, D));
   for (int i = 0; i < depth; ++i) {
     const BlockW& k = w.blk[i];
-    const float* x = b.x; __half* ln = b.ln; const int T_ = T, D_ = D;
+    const float* x = b.x; __half* ln = b.ln; const int T_ = BT, D_ = D;
     add(G_LN, "ln1", [=](cudaStream_t s) { return layernorm_f16(x, k.n1w, k.n1b, ln, T_, D_, 1e-6f, s); });
     { GemmEpilogue ep; ep.bias = k.qkv_b; ep.out_f16 = b.qkv; ep.out_f16_ld = 3 * D;
-      PRISMA_TRY(add_gemm(G_LINEAR, "qkv", b.ln, T, D, D, k.qkv_w, T, 3 * D, 1, zero_off, ep, 2.0 * T * 3.0 * D * D)); }
+      PRISMA_TRY(add_gemm(G_LINEAR, "qkv", b.ln, BT, D, D, k.qkv_w, BT, 3 * D, 1, zero_off, ep, 2.0 * BT * 3.0 * D * D)); }
     work_attn += att.flops;
     add(G_ATTN, "attention", [att](cudaStream_t s) { return attention_run(att, s); });
     { GemmEpilogue ep; ep.bias = k.proj_b; ep.gamma = k.g1; ep.res_f32 = b.x; ep.res_f32_ld = D; ep.out_f32 = b.x; ep.out_f32_ld = D;
-      PRISMA_TRY(add_gemm(G_LINEAR, "proj", b.attn, T, D, D, k.proj_w, T, D, 1, zero_off, ep, 2.0 * T * (double)D * D)); }
+      PRISMA_TRY(add_gemm(G_LINEAR, "proj", b.attn, BT, D, D, k.proj_w, BT, D, 1, zero_off, ep, 2.0 * BT * (double)D * D)); }
     add(G_LN, "ln2", [=](cudaStream_t s) { return layernorm_f16(x, k.n2w, k.n2b, ln, T_, D_, 1e-6f, s); });
     { GemmEpilogue ep; ep.bias = k.fc1_b; ep.act = 1; ep.out_f16 = b.hid; ep.out_f16_ld = 4 * D;
-      PRISMA_TRY(add_gemm(G_LINEAR, "fc1", b.ln, T, D, D, k.fc1_w, T, 4 * D, 1, zero_off, ep, 2.0 * T * 4.0 * D * D)); }
+      PRISMA_TRY(add_gemm(G_LINEAR, "fc1", b.ln, BT, D, D, k.fc1_w, BT, 4 * D, 1, zero_off, ep, 2.0 * BT * 4.0 * D * D)); }
     { GemmEpilogue ep; ep.bias = k.fc2_b; ep.gamma = k.g2; ep.res_f32 = b.x; ep.res_f32_ld = D; ep.out_f32 = b.x; ep.out_f32_ld = D;
-      PRISMA_TRY(add_gemm(G_LINEAR, "fc2", b.hid, T, 4 * D, 4 * D, k.fc2_w, T, D, 1, zero_off, ep, 2.0 * T * 4.0 * D * D)); }
+      PRISMA_TRY(add_gemm(G_LINEAR, "fc2", b.hid, BT, 4 * D, 4 * D, k.fc2_w, BT, D, 1, zero_off, ep, 2.0 * BT * 4.0 * D * D)); }
     if (i >= depth - 4) {
       __half* f = b.feat[i - (depth - 4)];
       const float* nw = w.nw; const float* nb = w.nb;
-      add(G_LN, "ln_out", [=](cudaStream_t s) { return layernorm_f16(x, nw, nb, f, T_, D_, 1e-6f, s); });
+      // final norm of the tapped block, patch tokens only (use_clstoken=False, dpt.py:110-111): dense [B*P][D]
+      add(G_LN, "ln_out", [=](cudaStream_t s) { return layernorm_f16(x, nw, nb, f, BP, D_, 1e-6f, s, P); });
     }
   }
 
@@ -404,25 +418,25 @@ int DepthEngine::build_plan(int H, int W) {
   }
   // projects (1x1 conv on tokens = GEMM over the patch tokens, cls dropped) + resize layers
   for (int i = 0; i < 4; ++i) {
-    const __half* A = b.feat[i] + D;  // skip the cls row (use_clstoken=False, dpt.py:110-111)
+    const __half* A = b.feat[i];  // patch tokens of all images, cls rows already dropped
     if (i < 2) {
       __half* dense = nullptr;
-      PRISMA_TRY(dev_alloc(plan_allocs, &dense, (size_t)P * oc[i]));
+      PRISMA_TRY(dev_alloc(plan_allocs, &dense, (size_t)BP * oc[i]));
       { GemmEpilogue ep; ep.bias = w.proj_b[i]; ep.out_f16 = dense; ep.out_f16_ld = oc[i];
-        PRISMA_TRY(add_gemm(G_HEAD, "project", A, P, D, D, w.proj_w[i], P, oc[i], 1, zero_off, ep, 2.0 * P * (double)D * oc[i])); }
+        PRISMA_TRY(add_gemm(G_HEAD, "project", A, BP, D, D, w.proj_w[i], BP, oc[i], 1, zero_off, ep, 2.0 * BP * (double)D * oc[i])); }
       const int s = i == 0 ? 4 : 2;
       GemmEpilogue ep;
       ep.bias = i == 0 ? w.rs0_b : w.rs1_b;
       ep.out_f16 = L[i].p; ep.out_f16_ld = oc[i];
-      ep.row_map = ROW_SHUFFLE; ep.in_w = pw; ep.in_h = ph; ep.out_wp = L[i].Wp(); ep.out_img_rows = (int)L[i].rows();
+      ep.row_map = ROW_SHUFFLE; ep.in_w = pw; ep.in_h = ph; ep.out_wp = L[i].Wp(); ep.out_img_rows = (int)L[i].img_rows();
       ep.shuf_s = s; ep.shuf_cout = oc[i];
-      PRISMA_TRY(add_gemm(G_HEAD, "resize_convT", dense, P, oc[i], oc[i], i == 0 ? w.rs0_w : w.rs1_w, P, s * s * oc[i], 1,
-                          zero_off, ep, 2.0 * P * (double)oc[i] * s * s * oc[i]));
+      PRISMA_TRY(add_gemm(G_HEAD, "resize_convT", dense, BP, oc[i], oc[i], i == 0 ? w.rs0_w : w.rs1_w, BP, s * s * oc[i], 1,
+                          zero_off, ep, 2.0 * BP * (double)oc[i] * s * s * oc[i]));
     } else {
       const PMap& dst = i == 2 ? L[2] : L3pre;
       GemmEpilogue ep; ep.bias = w.proj_b[i]; ep.out_f16 = dst.p; ep.out_f16_ld = oc[i];
-      ep.row_map = ROW_TOK2PAD; ep.in_w = pw; ep.in_h = ph; ep.out_wp = dst.Wp(); ep.out_img_rows = (int)dst.rows();
-      PRISMA_TRY(add_gemm(G_HEAD, "project", A, P, D, D, w.proj_w[i], P, oc[i], 1, zero_off, ep, 2.0 * P * (double)D * oc[i]));
+      ep.row_map = ROW_TOK2PAD; ep.in_w = pw; ep.in_h = ph; ep.out_wp = dst.Wp(); ep.out_img_rows = (int)dst.img_rows();
+      PRISMA_TRY(add_gemm(G_HEAD, "project", A, BP, D, D, w.proj_w[i], BP, oc[i], 1, zero_off, ep, 2.0 * BP * (double)D * oc[i]));
     }
   }
   { GemmEpilogue ep; ep.bias = w.rs3_b; ep.out_f16 = L[3].p; ep.out_f16_ld = oc[3];
@@ -459,14 +473,14 @@ int DepthEngine::build_plan(int H, int W) {
     { GemmEpilogue ep; ep.bias = k.c2_b[1]; ep.res_a = in->p; ep.res_a_ld = F; ep.out_f16 = U.p; ep.out_f16_ld = F;
       PRISMA_TRY(add_conv3x3("rcu2_conv2", t1, k.c2_w[1], F, ep, 1, nullptr)); }
     { GemmEpilogue ep; ep.bias = k.out_b; ep.out_f16 = V.p; ep.out_f16_ld = F;
-      ep.row_map = ROW_PADDED; ep.in_w = U.Wp(); ep.in_h = U.Hp();
+      ep.row_map = ROW_PADDED; ep.in_w = U.Wp(); ep.in_h = U.Hp(); ep.img_rows = (int)U.img_rows();
       PRISMA_TRY(add_gemm(G_HEAD, "out_conv1x1", U.p, U.rows(), F, F, k.out_w, (int)U.rows(), F, 1, zero_off, ep,
-                          2.0 * U.H * (double)U.W * F * F)); }
+                          2.0 * Bt * U.H * (double)U.W * F * F)); }
     const int oh = lvl > 0 ? R[lvl - 1].H : 2 * R[0].H, ow = lvl > 0 ? R[lvl - 1].W : 2 * R[0].W;
     PMap nxt;
     PRISMA_TRY(new_map(&nxt, oh, ow, F));
     { const __half* src = V.p; __half* dst = nxt.p; const int ih = V.H, iw = V.W, C = F;
-      add(G_RESAMPLE, "upsample_ac", [=](cudaStream_t s) { return upsample_ac_f16(src, ih, iw, C, dst, oh, ow, nullptr, s); }); }
+      add(G_RESAMPLE, "upsample_ac", [=](cudaStream_t s) { return upsample_ac_f16(src, Bt, ih, iw, C, dst, oh, ow, nullptr, s); }); }
     path = nxt;
     if (lvl == 0) taps["path1"] = {path.p, path.H, path.W, path.C, 1};
   }
@@ -477,7 +491,7 @@ int DepthEngine::build_plan(int H, int W) {
   { GemmEpilogue ep; ep.bias = w.oc1_b; ep.out_f16 = O1.p; ep.out_f16_ld = F / 2;
     PRISMA_TRY(add_conv3x3("output_conv1", path, w.oc1_w, F / 2, ep, 1, nullptr)); }
   { const __half* src = O1.p; __half* dst = O1u.p; const int ih = O1.H, iw = O1.W, C = F / 2, oh = hn, ow = wn;
-    add(G_RESAMPLE, "upsample_ac", [=](cudaStream_t s) { return upsample_ac_f16(src, ih, iw, C, dst, oh, ow, nullptr, s); }); }
+    add(G_RESAMPLE, "upsample_ac", [=](cudaStream_t s) { return upsample_ac_f16(src, Bt, ih, iw, C, dst, oh, ow, nullptr, s); }); }
   { GemmEpilogue ep; ep.bias = w.oc2_b; ep.act = 2; ep.head_w = w.oc3_w; ep.head_b = w.oc3_b; ep.head_out = b.depth;
     PRISMA_TRY(add_conv3x3("output_conv2_fused", O1u, w.oc2_w, 32, ep, 1, nullptr)); }
   // (dpt.py:163-164: the final F.interpolate to (h,w) is the identity at equal size and the ReLU is idempotent)
@@ -486,13 +500,18 @@ int DepthEngine::build_plan(int H, int W) {
   {
     const float* d = b.depth; float* pred = b.pred; uint8_t* rgb = b.rgb; uint32_t* mm = b.mm; float* mmo = b.minmax;
     const int hn_ = hn, wn_ = wn, sms = num_sms;
-    add(G_POST, "depth_postprocess", [=](cudaStream_t s) { return depth_postprocess(d, hn_, wn_, H, W, 1, pred, rgb, mm, mmo, sms, s); });
+    add(G_POST, "depth_postprocess", [=](cudaStream_t s) {
+      for (int i = 0; i < Bt; ++i)
+        PRISMA_TRY(depth_postprocess(d + (size_t)i * hn_ * wn_, hn_, wn_, H, W, 1, pred + (size_t)i * H * W,
+                                     rgb + (size_t)i * H * W * 3, mm + 2 * i, mmo + 2 * i, sms, s));
+      return 0;
+    });
   }
-  taps["net_input"] = {b.net_in, 3, hn * wn, 1, 0};
-  taps["tokens"] = {b.tokens_tap, T, D, 1, 0};
-  for (int i = 0; i < 4; ++i) taps["feat" + std::to_string(i)] = {b.feat[i], T, D, 1, 2};
-  taps["net_depth"] = {b.depth, hn, wn, 1, 0};
-  taps["x_final"] = {b.x, T, D, 1, 0};
+  taps["net_input"] = {b.net_in, Bt * 3, hn * wn, 1, 0};
+  taps["tokens"] = {b.tokens_tap, BT, D, 1, 0};
+  for (int i = 0; i < 4; ++i) taps["feat" + std::to_string(i)] = {b.feat[i], BP, D, 1, 2};  // patch tokens only
+  taps["net_depth"] = {b.depth, Bt * hn, wn, 1, 0};
+  taps["x_final"] = {b.x, BT, D, 1, 0};
   PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
   plan_H = H; plan_W = W;
   // ---- one CUDA graph per resolution: ~200 launches per frame replayed with a single cudaGraphLaunch
@@ -525,26 +544,28 @@ int DepthEngine::run_steps(cudaStream_t s) {
   return run_steps_direct(s);
 }
 
-int DepthEngine::infer(const uint8_t* rgb, int H, int W, float* depth_out, uint8_t* rgb_out, float* min_out,
+int DepthEngine::infer(const uint8_t* rgb, int n, int H, int W, float* depth_out, uint8_t* rgb_out, float* min_out,
                        float* max_out) {
-  PRISMA_CHECK(rgb != nullptr && H > 0 && W > 0, "bad frame");
+  PRISMA_CHECK(rgb != nullptr && H > 0 && W > 0 && n >= 1, "bad frame batch");
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  PRISMA_TRY(build_plan(H, W));
-  PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, rgb, (size_t)H * W * 3, cudaMemcpyHostToDevice, stream));
+  PRISMA_TRY(build_plan(H, W, n));
+  PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, rgb, (size_t)n * H * W * 3, cudaMemcpyHostToDevice, stream));
   PRISMA_TRY(run_steps(stream));
-  float mm[2];
-  if (depth_out) PRISMA_CUDA_OK(cudaMemcpyAsync(depth_out, b.pred, (size_t)H * W * 4, cudaMemcpyDeviceToHost, stream));
-  if (rgb_out) PRISMA_CUDA_OK(cudaMemcpyAsync(rgb_out, b.rgb, (size_t)H * W * 3, cudaMemcpyDeviceToHost, stream));
-  PRISMA_CUDA_OK(cudaMemcpyAsync(mm, b.minmax, 8, cudaMemcpyDeviceToHost, stream));
+  std::vector<float> mm(2 * n);
+  if (depth_out) PRISMA_CUDA_OK(cudaMemcpyAsync(depth_out, b.pred, (size_t)n * H * W * 4, cudaMemcpyDeviceToHost, stream));
+  if (rgb_out) PRISMA_CUDA_OK(cudaMemcpyAsync(rgb_out, b.rgb, (size_t)n * H * W * 3, cudaMemcpyDeviceToHost, stream));
+  PRISMA_CUDA_OK(cudaMemcpyAsync(mm.data(), b.minmax, 8 * n, cudaMemcpyDeviceToHost, stream));
   PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
-  if (min_out) *min_out = mm[0];
-  if (max_out) *max_out = mm[1];
+  for (int i = 0; i < n; ++i) {
+    if (min_out) min_out[i] = mm[2 * i];
+    if (max_out) max_out[i] = mm[2 * i + 1];
+  }
   return 0;
 }
 
-int DepthEngine::infer_resident(int H, int W, int iters, float* ms_per_iter) {
+int DepthEngine::infer_resident(int H, int W, int n, int iters, float* ms_per_iter) {
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  PRISMA_TRY(build_plan(H, W));
+  PRISMA_TRY(build_plan(H, W, n));
   PRISMA_CUDA_OK(cudaEventRecord(ev0, stream));
   for (int i = 0; i < iters; ++i) PRISMA_TRY(run_steps(stream));
   PRISMA_CUDA_OK(cudaEventRecord(ev1, stream));
@@ -608,9 +629,9 @@ long long DepthEngine::read_tap(const std::string& name, float* out, long long c
   return n;
 }
 
-int DepthEngine::profile(int H, int W, float* out8) {
+int DepthEngine::profile(int H, int W, int n, float* out8) {
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  PRISMA_TRY(build_plan(H, W));
+  PRISMA_TRY(build_plan(H, W, n));
   PRISMA_TRY(run_steps_direct(stream));  // warm
   std::vector<cudaEvent_t> ev(steps.size() + 1);
   for (auto& e : ev) PRISMA_CUDA_OK(cudaEventCreate(&e));

@@ -45,12 +45,12 @@ class DepthEngine {
   int init(const std::string& encoder, int device);
   int load_tensor(const std::string& name, const float* data, const int64_t* shape, int ndim);
   int finalize();
-  int infer(const uint8_t* rgb, int H, int W, float* depth_out, uint8_t* rgb_out, float* min_out, float* max_out);
-  int infer_resident(int H, int W, int iters, float* ms_per_iter);
+  int infer(const uint8_t* rgb, int n, int H, int W, float* depth_out, uint8_t* rgb_out, float* min_out, float* max_out);
+  int infer_resident(int H, int W, int n, int iters, float* ms_per_iter);
   int encode(const float* pred, int H, int W, int flip, uint8_t* rgb_out, float* min_out, float* max_out);
   long long read_tap(const std::string& name, float* out, long long capacity);
-  int profile(int H, int W, float* out8);
-  int build_plan(int H, int W);
+  int profile(int H, int W, int n, float* out8);
+  int build_plan(int H, int W, int batch);
 
   bool debug_taps = true;
   double work_linear = 0, work_attn = 0, work_head = 0;
@@ -85,7 +85,7 @@ class DepthEngine {
   DaWeights w;
   DaBuffers b;
   std::map<std::string, Tap> taps;
-  int plan_H = 0, plan_W = 0, hn = 0, wn = 0, ph = 0, pw = 0, T = 0;
+  int plan_H = 0, plan_W = 0, batch = 0, hn = 0, wn = 0, ph = 0, pw = 0, T = 0;
 };
 
 }  // namespace prisma

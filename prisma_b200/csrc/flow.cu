@@ -149,6 +149,8 @@ int flow_encode(const float* flow, int H, int W, uint8_t* rgb, uint32_t* mm_scra
 // K14 (by linearity): avg_pool2d of the correlation volume over its last two dims == correlation with the
 // average-pooled fmap2.  Pool fmap2 (fp16 [P][C]) into the three coarser levels (floor sizes, corr.py:24-27).
 // ------------------------------------------------------------------------------------------------
+// The pooled features are kept as an fp16 hi/lo pair ([hi(C) | lo(C)] per row, consumed as two K-slabs of the same
+// GEMM) so the coarse levels carry no extra rounding beyond the fp16 feature maps themselves.
 __global__ void k_pool_fmap(const __half* __restrict__ f, int H8, int W8, int C, __half* __restrict__ out, int lh, int lw,
                             int win) {
   const int cell = blockIdx.x;  // y * lw + x
@@ -158,7 +160,10 @@ __global__ void k_pool_fmap(const __half* __restrict__ f, int H8, int W8, int C,
     float acc = 0.f;
     for (int dy = 0; dy < win; ++dy)
       for (int dx = 0; dx < win; ++dx) acc += __half2float(f[((size_t)(y * win + dy) * W8 + x * win + dx) * C + c]);
-    out[(size_t)cell * C + c] = __float2half_rn(acc * inv);
+    const float m = acc * inv;
+    const __half hi = __float2half_rn(m);
+    out[(size_t)cell * 2 * C + c] = hi;
+    out[(size_t)cell * 2 * C + C + c] = __float2half_rn(m - __half2float(hi));
   }
 }
 
@@ -245,13 +250,13 @@ int FlowCorr::init(int dev, int batch, int h8, int w8) {
     lh[l] = H8 >> l; lw[l] = W8 >> l; ln[l] = lh[l] * lw[l];
     lpitch[l] = round_up(ln[l], 4);
     lrows_pad[l] = round_up(lpitch[l], 256);
-    PRISMA_TRY(fc_alloc(allocs, &fmap2[l], (size_t)B * lrows_pad[l] * C));
+    PRISMA_TRY(fc_alloc(allocs, &fmap2[l], (size_t)B * lrows_pad[l] * C * (l == 0 ? 1 : 2)));
     PRISMA_TRY(fc_alloc(allocs, &vol[l], (size_t)B * P * lpitch[l]));
   }
   PRISMA_TRY(fc_alloc(allocs, &coords, (size_t)B * 2 * P));
   PRISMA_TRY(fc_alloc(allocs, &lookup_out, (size_t)B * P * 384));
   // one GEMM per (image, level): vol_l[b] = fmap1[b] . fmap2_l[b]^T / sqrt(C)      (corr.py:53-60)
-  const int off[1] = {0};
+  const int off[2] = {0, 0};
   bytes_build = flops_build = 0;
   for (int b = 0; b < B; ++b)
     for (int l = 0; l < 4; ++l) {
@@ -260,8 +265,9 @@ int FlowCorr::init(int dev, int batch, int h8, int w8) {
       ep.out_f32 = vol[l] + (size_t)b * P * lpitch[l];
       ep.out_f32_ld = lpitch[l];
       GemmLaunch g;
-      PRISMA_TRY(gemm_prepare(&g, fmap1 + (size_t)b * rows_pad * C, P, C, C, fmap2[l] + (size_t)b * lrows_pad[l] * C,
-                              lrows_pad[l], P, lpitch[l], 1, off, ep, num_sms));
+      const int wk = l == 0 ? 1 : 2;  // coarse levels: fmap1 against [hi | lo] pooled features = two K-slabs
+      PRISMA_TRY(gemm_prepare(&g, fmap1 + (size_t)b * rows_pad * C, P, C, C, fmap2[l] + (size_t)b * lrows_pad[l] * C * wk,
+                              lrows_pad[l], P, lpitch[l], wk, off, ep, num_sms));
       gemms.push_back(g);
       flops_build += 2.0 * P * (double)ln[l] * C;
       bytes_build += 4.0 * P * (double)ln[l];
@@ -294,7 +300,7 @@ int FlowCorr::build(cudaStream_t s) {
   for (int b = 0; b < B; ++b)
     for (int l = 1; l < 4; ++l)
       k_pool_fmap<<<ln[l], 128, 0, s>>>(fmap2[0] + (size_t)b * lrows_pad[0] * C, H8, W8, C,
-                                        fmap2[l] + (size_t)b * lrows_pad[l] * C, lh[l], lw[l], 1 << l);
+                                        fmap2[l] + (size_t)b * lrows_pad[l] * C * 2, lh[l], lw[l], 1 << l);
   PRISMA_CUDA_OK(cudaGetLastError());
   for (auto& g : gemms) PRISMA_TRY(gemm_run(g, s));
   return 0;

@@ -68,7 +68,7 @@ int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols,
                  int w_rows, int M, int N, int taps, const int* tap_off, const GemmEpilogue& ep, int num_sms,
                  int force_bn) {
   PRISMA_CHECK(taps >= 1 && taps <= GEMM_MAX_TAPS, "gemm: bad tap count");
-  PRISMA_CHECK(N % 8 == 0, "gemm: N must be a multiple of 8");
+  PRISMA_CHECK(N % 4 == 0, "gemm: N must be a multiple of 4");
   PRISMA_CHECK(M >= 1 && a_cols >= 1, "gemm: empty problem");
   const int bn = force_bn ? force_bn : gemm_pick_bn(M, N, num_sms);
   PRISMA_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: unsupported BLOCK_N");

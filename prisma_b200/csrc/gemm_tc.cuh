@@ -31,6 +31,7 @@ enum RowMap : int {
   ROW_LINEAR = 0,   // dst row = m                                   (valid: m < M)
   ROW_PADDED = 1,   // m indexes a zero-bordered [Hp][Wp] image; only interior pixels are stored (borders stay zero)
   ROW_TOK2PAD = 2,  // m = y*W + x (dense tokens)  -> dst row (y+1)*out_wp + x+1
+  ROW_TOKSKIP = 4,  // m = b*P + p (patch tokens of image b) -> dst row b*(P+1) + 1 + p  (skips the cls rows; in_w = P)
   ROW_SHUFFLE = 3,  // ConvTranspose k == s: m = y*W + x, n = (dy*s+dx)*cout + co -> dst row (y*s+dy+1)*out_wp + x*s+dx+1
 };
 
@@ -284,6 +285,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           valid = valid && ((y - 1) % ep.sub == 0) && ((x - 1) % ep.sub == 0);
           drow = img * ep.out_img_rows + ((y - 1) / ep.sub + 1) * ep.out_wp + (x - 1) / ep.sub + 1;
         }
+      } else if (ep.row_map == ROW_TOKSKIP) {
+        drow = m + m / ep.in_w + 1;
       } else if (ep.row_map == ROW_TOK2PAD || ep.row_map == ROW_SHUFFLE) {
         const int per = ep.in_w * ep.in_h;
         const int img = m / per, r = m - img * per;
@@ -320,8 +323,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               acc = fmaf(fmaxf(__uint_as_float(r[j]) + __ldg(ep.bias + j), 0.f), __ldg(ep.head_w + j), acc);
-            const int y = m / ep.in_w, x = m - y * ep.in_w;
-            ep.head_out[(size_t)(y - 1) * (ep.in_w - 2) + (x - 1)] = fmaxf(acc, 0.f);
+            int img = 0, rpix = m;
+            if (ep.img_rows > 0) { img = m / ep.img_rows; rpix = m - img * ep.img_rows; }
+            const int y = rpix / ep.in_w, x = rpix - y * ep.in_w;
+            ep.head_out[((size_t)img * (ep.in_h - 2) + (y - 1)) * (ep.in_w - 2) + (x - 1)] = fmaxf(acc, 0.f);
           }
           continue;
         }

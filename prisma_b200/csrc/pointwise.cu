@@ -82,9 +82,13 @@ int da_preprocess(const uint8_t* img, int H, int W, float* out, int h, int w, cu
 // K2a: patchify  f32 CHW [3][h][w] -> fp16 [P][kpad]  (k = c*196 + ky*14 + kx, zero padded to kpad)
 // = im2col of the 14x14/stride-14 patch-embed conv (dinov2/layers/patch_embed.py:66,76-78).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_patchify(const float* __restrict__ x, int h, int w, __half* __restrict__ out, int pw, int kpad) {
-  const int p = blockIdx.x;
-  const int py = p / pw, px = p - py * pw;
+__global__ void k_patchify(const float* __restrict__ x_all, int h, int w, __half* __restrict__ out, int pw, int kpad,
+                           int per_img) {
+  const int img = blockIdx.x / per_img;
+  const int p = blockIdx.x;             // output row (image-major)
+  const int pl = p - img * per_img;     // patch index inside the image
+  const float* x = x_all + (size_t)img * 3 * h * w;
+  const int py = pl / pw, px = pl - py * pw;
   for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
     float v = 0.f;
     if (k < 588) {
@@ -94,9 +98,9 @@ __global__ void k_patchify(const float* __restrict__ x, int h, int w, __half* __
     out[(size_t)p * kpad + k] = __float2half_rn(v);
   }
 }
-int da_patchify(const float* x, int h, int w, __half* out, int kpad, cudaStream_t s) {
+int da_patchify(const float* x, int batch, int h, int w, __half* out, int kpad, cudaStream_t s) {
   const int ph = h / 14, pw = w / 14;
-  k_patchify<<<ph * pw, 160, 0, s>>>(x, h, w, out, pw, kpad);
+  k_patchify<<<batch * ph * pw, 160, 0, s>>>(x, h, w, out, pw, kpad, ph * pw);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -154,12 +158,14 @@ int da_pos_embed(const float* pos, const float* cls, int S, int D, int ph, int p
 // ------------------------------------------------------------------------------------------------
 template <int V4>  // float4 per lane: D = 128 * V4
 __global__ void k_layernorm(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
-                            __half* __restrict__ y, int rows, float eps) {
+                            __half* __restrict__ y, int rows, float eps, int skip_per) {
   constexpr int D = 128 * V4;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  // skip_per > 0: output row r = b*skip_per + p reads input row b*(skip_per+1) + 1 + p (drops each image's cls token)
+  const int src = skip_per > 0 ? row + row / skip_per + 1 : row;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)src * D);
   float4 v[V4];
   float s = 0.f;
 #pragma unroll
@@ -187,13 +193,13 @@ __global__ void k_layernorm(const float* __restrict__ x, const float* __restrict
   }
 }
 int layernorm_f16(const float* x, const float* g, const float* b, __half* y, int rows, int D, float eps,
-                  cudaStream_t s) {
+                  cudaStream_t s, int skip_per) {
   const int wpb = 8;
   dim3 grid(ceil_div(rows, wpb)), block(32 * wpb);
   switch (D) {
-    case 384: k_layernorm<3><<<grid, block, 0, s>>>(x, g, b, y, rows, eps); break;
-    case 768: k_layernorm<6><<<grid, block, 0, s>>>(x, g, b, y, rows, eps); break;
-    case 1024: k_layernorm<8><<<grid, block, 0, s>>>(x, g, b, y, rows, eps); break;
+    case 384: k_layernorm<3><<<grid, block, 0, s>>>(x, g, b, y, rows, eps, skip_per); break;
+    case 768: k_layernorm<6><<<grid, block, 0, s>>>(x, g, b, y, rows, eps, skip_per); break;
+    case 1024: k_layernorm<8><<<grid, block, 0, s>>>(x, g, b, y, rows, eps, skip_per); break;
     default: set_last_error("layernorm: unsupported D"); return -1;
   }
   PRISMA_CUDA_OK(cudaGetLastError());
@@ -206,8 +212,11 @@ int layernorm_f16(const float* x, const float* g, const float* b, __half* y, int
 // torch: scale=(in-1)/(out-1) (float), src=scale*dst, i0=(int)src, i1=i0+(i0<in-1), l1=src-i0, l0=1-l1.
 // 8 channels (16 B) per thread.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_upsample_ac(const __half* __restrict__ in, int ih, int iw, int C, __half* __restrict__ out, int oh,
-                              int ow, float sy, float sx, int relu_copy, __half* __restrict__ out_relu) {
+__global__ void k_upsample_ac(const __half* __restrict__ in_all, int ih, int iw, int C, __half* __restrict__ out_all,
+                              int oh, int ow, float sy, float sx, int relu_copy, __half* __restrict__ out_relu_all) {
+  const __half* in = in_all + (size_t)blockIdx.y * (ih + 2) * (iw + 2) * C;
+  __half* out = out_all + (size_t)blockIdx.y * (oh + 2) * (ow + 2) * C;
+  __half* out_relu = relu_copy ? out_relu_all + (size_t)blockIdx.y * (oh + 2) * (ow + 2) * C : nullptr;
   const int c8 = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)oh * ow * c8;
@@ -242,13 +251,13 @@ __global__ void k_upsample_ac(const __half* __restrict__ in, int ih, int iw, int
   *reinterpret_cast<uint4*>(out + off) = make_uint4(o[0], o[1], o[2], o[3]);
   if (relu_copy) *reinterpret_cast<uint4*>(out_relu + off) = make_uint4(orl[0], orl[1], orl[2], orl[3]);
 }
-int upsample_ac_f16(const __half* in, int ih, int iw, int C, __half* out, int oh, int ow, __half* out_relu,
+int upsample_ac_f16(const __half* in, int batch, int ih, int iw, int C, __half* out, int oh, int ow, __half* out_relu,
                     cudaStream_t s) {
   PRISMA_CHECK(C % 8 == 0, "upsample: C must be a multiple of 8");
   const float sy = oh > 1 ? (float)(ih - 1) / (float)(oh - 1) : 0.f;
   const float sx = ow > 1 ? (float)(iw - 1) / (float)(ow - 1) : 0.f;
   const long long total = (long long)oh * ow * (C / 8);
-  k_upsample_ac<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+  k_upsample_ac<<<dim3((unsigned)((total + 255) / 256), batch), 256, 0, s>>>(
       in, ih, iw, C, out, oh, ow, sy, sx, out_relu != nullptr, out_relu);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;

@@ -77,6 +77,20 @@ class DepthAnythingEngine:
                                        u8ptr(rgb), C.byref(dmin), C.byref(dmax)))
         return pred, rgb, dmin.value, dmax.value
 
+    def infer_batch(self, frames, want_depth=False, want_rgb=True):
+        """n frames of one size in one pass: (rgb [n,H,W,3] u8 | None, mins [n], maxs [n], depth [n,H,W] f32 | None).
+        Identical results to n infer_encoded() calls; the video loop of the band uses this to fill the GPU."""
+        x = np.ascontiguousarray(np.stack(frames) if not isinstance(frames, np.ndarray) else frames)
+        if x.dtype != np.uint8 or x.ndim != 4 or x.shape[3] != 3:
+            raise PrismaError("expected n HxWx3 uint8 RGB frames")
+        n, h, w = x.shape[:3]
+        pred = np.empty((n, h, w), np.float32) if want_depth else None
+        rgb = np.empty((n, h, w, 3), np.uint8) if want_rgb else None
+        mins = np.empty(n, np.float32)
+        maxs = np.empty(n, np.float32)
+        check(lib().prisma_depth_infer_batch(self._h, u8ptr(x), n, h, w, fptr(pred), u8ptr(rgb), fptr(mins), fptr(maxs)))
+        return rgb, mins, maxs, pred
+
     def encode(self, prediction, flip=True):
         """(heat_to_rgb(1 - normalised) * 255).astype(u8) of a given HxW f32 prediction (:215-220)."""
         p = np.ascontiguousarray(prediction, dtype=np.float32)
@@ -92,20 +106,21 @@ class DepthAnythingEngine:
         assert n == out.size, (name, n, out.size)
         return out.reshape(shape)
 
-    def time_resident(self, h, w, iters):
+    def time_resident(self, h, w, iters, batch=1):
+        """ms per pass over `batch` resident frames."""
         ms = C.c_float()
-        check(lib().prisma_depth_infer_resident(self._h, h, w, iters, C.byref(ms)))
+        check(lib().prisma_depth_infer_resident(self._h, h, w, batch, iters, C.byref(ms)))
         return ms.value
 
-    def profile(self, h, w):
+    def profile(self, h, w, batch=1):
         out = (C.c_float * 8)()
-        check(lib().prisma_depth_profile(self._h, h, w, out))
+        check(lib().prisma_depth_profile(self._h, h, w, batch, out))
         keys = ["pre", "linear", "attention", "layernorm", "head", "resample", "post", "total"]
         return dict(zip(keys, [float(v) for v in out]))
 
-    def work(self, h, w):
+    def work(self, h, w, batch=1):
         out = (C.c_double * 4)()
-        check(lib().prisma_depth_work(self._h, h, w, out))
+        check(lib().prisma_depth_work(self._h, h, w, batch, out))
         return dict(linear_flop=out[0], attention_flop=out[1], head_flop=out[2], launches=int(out[3]))
 
     def close(self):
