@@ -100,7 +100,8 @@ def test_corr_pyramid_and_lookup_match_reference(golden_dir):
     out = np.empty((B, 324, h8, w8), np.float32)
     check(l.prisma_flowcorr_lookup(h, fptr(coords), fptr(out), 1, C.byref(ms)))
     ref = g["lookup"].astype(np.float32)
-    assert np.abs(out - ref).max() <= 2e-3 * scale
+    # both the engine's lookup output (the fp16 A operand of convc1) and the fixture are fp16: 2 x 2^-11 relative
+    assert np.abs(out - ref).max() <= 1.5e-3 * np.abs(ref).max()
     # far outside the volume everything is zero (zeros padding)
     far = coords + 1000.0
     check(l.prisma_flowcorr_lookup(h, fptr(np.ascontiguousarray(far)), fptr(out), 1, C.byref(ms)))

@@ -19,3 +19,12 @@ if which in ("attn", "both"):
     out = np.empty((T, heads * 64), np.float32); ms = C.c_float()
     assert l.prisma_debug_attention(0, fptr(qkv), fptr(out), T, heads, 3, C.byref(ms)) == 0
     print("attn ms", ms.value, "TF", 4.0 * heads * T * T * 64 / ms.value / 1e9)
+if which in ("corr",):
+    h8, w8 = 102, 180
+    fm1 = rng.standard_normal((2, 256, h8, w8), dtype=np.float32); fm2 = rng.standard_normal((2, 256, h8, w8), dtype=np.float32)
+    h = C.c_void_p(); ms = C.c_float()
+    assert l.prisma_flowcorr_create(0, 2, h8, w8, C.byref(h)) == 0, l.prisma_last_error()
+    assert l.prisma_flowcorr_set_fmaps(h, fptr(fm1), fptr(fm2)) == 0
+    assert l.prisma_flowcorr_build(h, 2, C.byref(ms)) == 0
+    work = (C.c_double * 2)(); l.prisma_flowcorr_work(h, work)
+    print("corr build ms", ms.value, "GB/s", work[1] / ms.value / 1e6, "TF", work[0] / ms.value / 1e9)
