@@ -33,13 +33,14 @@ def build(verbose=False, force=False):
     hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
     newest_hdr = max(os.path.getmtime(h) for h in hdrs)
     nvcc = _nvcc()
+    extra = os.environ.get("PRISMA_NVCC_EXTRA", "").split()  # e.g. -DPRISMA_ATTN_PROFILE for the cycle counters
     jobs = []
     objs = []
     for s in srcs:
         o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), newest_hdr):
-            jobs.append([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o])
+            jobs.append([nvcc] + NVCC_FLAGS + extra + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

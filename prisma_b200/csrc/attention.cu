@@ -45,6 +45,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* s_full = bars + 5;
   uint64_t* p_full = bars + 6;
   uint64_t* pv_done = bars + 7;
+  uint64_t* s_free = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -61,6 +62,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     mbar_init(s_full, 1);
     mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
+    mbar_init(s_free, 4);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
@@ -99,7 +101,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       }
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
-        mbar_wait(p_full, j & 1);  // P(j) in smem, S(j) fully read, any lazy rescale of O done
+        if (j + 1 < n_kv) {
+          // S(j+1) as soon as the softmax warps hold S(j) in registers: it overlaps the whole softmax of tile j
+          const int st1 = (j + 1) & 1;
+          mbar_wait(s_free, j & 1);
+          mbar_wait(&kv_full[st1], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK + st1 * ATT_TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(s_full);
+        }
+        mbar_wait(p_full, j & 1);  // P(j) in smem, any lazy rescale of O done
         tc_fence_after();
         const uint32_t vbase = smem_u32(sV + st * ATT_TILE_BYTES);
 #pragma unroll
@@ -110,15 +123,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         }
         umma_commit(pv_done);
         umma_commit(&kv_empty[st]);
-        if (j + 1 < n_kv) {
-          const int st1 = (j + 1) & 1;
-          mbar_wait(&kv_full[st1], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK + st1 * ATT_TILE_BYTES));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
-        }
       }
     }
   } else {
@@ -127,28 +131,39 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
     float m_used = -INFINITY, l_run = 0.f;  // m_used: the max P / O are currently scaled by
+#ifdef PRISMA_ATTN_PROFILE
+    long long t_wait = 0, t_p1 = 0, t_p2 = 0, t_tot = clock64();
+    const bool prof = args.dbg != nullptr && threadIdx.x == 64 && blockIdx.x == 1 && blockIdx.y == 1;
+#define ATT_CLK(x) long long x = clock64()
+#else
+#define ATT_CLK(x)
+#endif
     uint8_t* prow = sP + r * 128;
     const int rsw = r & 7;
 
     for (int j = 0; j < n_kv; ++j) {
       const int valid = min(ATT_BKV, T - j * ATT_BKV);  // >= 1
-      mbar_wait(s_full, j & 1);  // S(j) ready; MMAs retire in order, so PV(j-1) has also finished reading P(j-1)
+      ATT_CLK(c0_);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // ---- pass 1: row max
+      ATT_CLK(c1_);
+      // ---- the whole S row (128 fp32) into registers with one wait; the TMEM buffer is then free for S(j+1)
+      uint32_t v[128];
+      tmem_ld32(tmem_S + lane_sel + 0, v);
+      tmem_ld32(tmem_S + lane_sel + 32, v + 32);
+      tmem_ld32(tmem_S + lane_sel + 64, v + 64);
+      tmem_ld32(tmem_S + lane_sel + 96, v + 96);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < ATT_BKV; c0 += 32) {
-        if (c0 >= valid) break;
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_sel + c0, v);
-        tmem_ld_wait();
-        if (c0 + 32 <= valid) {
+      if (valid == ATT_BKV) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (c0 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
+        for (int i = 0; i < 128; ++i) if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
       // ---- lazy rescale (warp-uniform decision; each warp owns its 32 TMEM lanes)
       if (j == 0) {
@@ -162,12 +177,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           tc_fence_after();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld32(tmem_O + lane_sel + h * 32, v);
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_sel + h * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st32(tmem_O + lane_sel + h * 32, v);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_sel + h * 32, o);
           }
           tmem_st_wait();
           l_run *= alpha;
@@ -175,38 +190,50 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         }
       }
       const float mscaled = m_used * LOG2E;
-      // ---- pass 2: p = exp(s - m_used), row sum, P -> fp16 -> swizzled smem (A operand of the PV MMA)
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < ATT_BKV; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_sel + c0, v);
-        tmem_ld_wait();
-        float p[32];
+      ATT_CLK(c2_);
+      // ---- P(j-1) must have been consumed by PV(j-1) before the buffer is rewritten (issued a whole softmax ago)
+      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
+      // ---- p = exp(s - m_used), row sum (4 independent partial sums), P -> fp16 -> swizzled smem chunk by chunk
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      if (valid == ATT_BKV) {  // every tile but the last: no masking instructions at all
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = ex2_approx(fmaf(__uint_as_float(v[i]), LOG2E, -mscaled));
-          p[i] = (c0 + i < valid) ? e : 0.f;
-          sum += p[i];
-        }
-        uint8_t* slab = prow + (c0 >> 6) * ATT_TILE_BYTES;
-        const int chunk0 = (c0 & 63) >> 3;
+        for (int c = 0; c < 16; ++c) {  // 16-byte chunks: 8 columns each
+          float e[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[c * 8 + i]), LOG2E, -mscaled));
+          sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
           uint4 o;
-          o.x = pack_half2(p[g * 8 + 0], p[g * 8 + 1]);
-          o.y = pack_half2(p[g * 8 + 2], p[g * 8 + 3]);
-          o.z = pack_half2(p[g * 8 + 4], p[g * 8 + 5]);
-          o.w = pack_half2(p[g * 8 + 6], p[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(slab + (((chunk0 + g) ^ rsw) << 4)) = o;
+          o.x = pack_half2(e[0], e[1]); o.y = pack_half2(e[2], e[3]); o.z = pack_half2(e[4], e[5]); o.w = pack_half2(e[6], e[7]);
+          *reinterpret_cast<uint4*>(prow + (c >> 3) * ATT_TILE_BYTES + (((c & 7) ^ rsw) << 4)) = o;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {  // last KV tile only; fully unrolled so v[] stays in registers
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x = ex2_approx(fmaf(__uint_as_float(v[c * 8 + i]), LOG2E, -mscaled));
+            e[i] = (c * 8 + i < valid) ? x : 0.f;
+          }
+          sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
+          uint4 o;
+          o.x = pack_half2(e[0], e[1]); o.y = pack_half2(e[2], e[3]); o.z = pack_half2(e[4], e[5]); o.w = pack_half2(e[6], e[7]);
+          *reinterpret_cast<uint4*>(prow + (c >> 3) * ATT_TILE_BYTES + (((c & 7) ^ rsw) << 4)) = o;
         }
       }
-      l_run += sum;
+      l_run += (sum0 + sum1) + (sum2 + sum3);
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+#ifdef PRISMA_ATTN_PROFILE
+      long long c3_ = clock64();
+      t_wait += c1_ - c0_; t_p1 += c2_ - c1_; t_p2 += c3_ - c2_;
+#endif
     }
+#ifdef PRISMA_ATTN_PROFILE
+    if (prof) { args.dbg[0] = t_wait; args.dbg[1] = t_p1; args.dbg[2] = t_p2; args.dbg[3] = clock64() - t_tot; args.dbg[4] = n_kv; }
+#endif
     // ---- O is complete once the last PV retires
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
@@ -252,6 +279,7 @@ int attention_prepare(AttnLaunch* out, const __half* qkv, __half* o, int batch, 
   out->args.batch = batch;
   out->args.out = o;
   out->args.out_ld = D;
+  out->args.dbg = nullptr;
   PRISMA_TRY(make_tmap_2d_f16(&out->tm, qkv, (uint64_t)3 * D, (uint64_t)batch * tokens, (uint64_t)3 * D, 64, 128));
   out->grid = dim3(ceil_div(tokens, ATT_BQ), heads, batch);
   out->flops = 4.0 * batch * heads * (double)tokens * tokens * ATT_HD;
