@@ -86,6 +86,24 @@ int prisma_flowcorr_read_level(prisma_engine* e, int level, int b, int row0, int
 /* algorithmic work of one build: out[0] = FLOP, out[1] = bytes (fp32 pyramid written + fp16 features read)      */
 int prisma_flowcorr_work(prisma_engine* e, double* out2);
 
+/* ---- RAFT band, whole model: replaces init_model (bands/flow_raft.py:38-48) + infer (:51-66) + the resize of
+ *      process_video (:100-101) + process_flow (common/encode.py:113-126) for one frame pair, forward and backward   */
+int prisma_flow_create(int device, prisma_engine** out);
+/* one call per tensor of the RAFT state_dict (bands/raft/raft.py:24-57; a leading "module." is stripped)           */
+int prisma_flow_load_tensor(prisma_engine* e, const char* name, const float* data, const int64_t* shape, int ndim);
+int prisma_flow_finalize(prisma_engine* e);
+/* prev / curr: h*w*3 u8 RGB frames.  scale = args.scale (0.75), iters = args.iterations.  Outputs (each may be NULL):
+ * fwd / bwd: hs*ws*2 f32 flows (hs = round(h*scale)), fwd_rgb / bwd_rgb: hs*ws*3 u8 HSV encodings, max_*: the
+ * per-frame max displacement written to <band>.csv.  ms_out: device time of the pass (CUDA events), may be NULL.    */
+int prisma_flow_infer(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, float scale, int iters,
+                      float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd,
+                      float* ms_out);
+/* intermediate tensors of the last pass (tests): "fmap" [2][P][256], "cnet_out" [2P][256], "coords1_iter0",
+ * "h_iter0", "coords1"; returns the number of floats written                                                       */
+long long prisma_flow_read_tap(prisma_engine* e, const char* name, float* out, long long capacity);
+/* out[0] = algorithmic FLOP of one pass, out[1] = kernel launches per pass, out[2] = hs, out[3] = ws               */
+int prisma_flow_work(prisma_engine* e, int h, int w, float scale, int iters, double* out4);
+
 /* ---- kernel-level entry points (parity tests and micro-benchmarks call the kernels through the C ABI) ---- */
 /* D = A[M,K] * W[N,K]^T (+bias) with fp16 operands / fp32 accumulate on the tcgen05 core; A, W, D host fp32.
  * act: 0 none, 1 gelu, 2 relu.  force_bn: 0 = auto, else 32/64/128/256.  ms_out (may be NULL): kernel time.   */

@@ -6,14 +6,16 @@
 #include <vector>
 
 #include "engine_da.cuh"
+#include "engine_raft.cuh"
 #include "flow.cuh"
 
 using namespace prisma;
 
 struct prisma_engine {
-  int kind;  // 1 = depth, 2 = flow correlation
+  int kind;  // 1 = depth, 2 = flow correlation, 3 = RAFT
   DepthEngine* depth;
   FlowCorr* corr;
+  RaftEngine* raft = nullptr;
 };
 
 #define API_GUARD_BEGIN try {
@@ -178,6 +180,7 @@ int prisma_engine_destroy(prisma_engine* e) {
   if (!e) return 0;
   delete e->depth;
   delete e->corr;
+  delete e->raft;
   delete e;
   return 0;
   API_GUARD_END
@@ -434,6 +437,61 @@ int prisma_flowcorr_work(prisma_engine* e, double* out2) {
   if (!c) return -1;
   out2[0] = c->flops_build;
   out2[1] = c->bytes_build;
+  return 0;
+  API_GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------------ RAFT engine
+static RaftEngine* as_raft(prisma_engine* e) {
+  if (!e || e->kind != 3 || !e->raft) { set_last_error("not a RAFT engine handle"); return nullptr; }
+  return e->raft;
+}
+int prisma_flow_create(int device, prisma_engine** out) {
+  API_GUARD_BEGIN
+  PRISMA_CHECK(out != nullptr, "null argument");
+  RaftEngine* r = new RaftEngine();
+  int rc = r->init(device);
+  if (rc != 0) { delete r; return rc; }
+  prisma_engine* e = new prisma_engine{3, nullptr, nullptr};
+  e->raft = r;
+  *out = e;
+  return 0;
+  API_GUARD_END
+}
+int prisma_flow_load_tensor(prisma_engine* e, const char* name, const float* data, const int64_t* shape, int ndim) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  if (!r) return -1;
+  PRISMA_CHECK(name && data && shape && ndim >= 1 && ndim <= 4, "bad tensor");
+  return r->load_tensor(name, data, shape, ndim);
+  API_GUARD_END
+}
+int prisma_flow_finalize(prisma_engine* e) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  return r ? r->finalize() : -1;
+  API_GUARD_END
+}
+int prisma_flow_infer(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, float scale, int iters,
+                      float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd,
+                      float* ms_out) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  return r ? r->infer(prev, curr, h, w, scale, iters, fwd, bwd, fwd_rgb, bwd_rgb, max_fwd, max_bwd, ms_out) : -1;
+  API_GUARD_END
+}
+long long prisma_flow_read_tap(prisma_engine* e, const char* name, float* out, long long capacity) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  return r ? r->read_tap(name, out, capacity) : -1;
+  API_GUARD_END
+}
+int prisma_flow_work(prisma_engine* e, int h, int w, float scale, int iters, double* out4) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  if (!r) return -1;
+  PRISMA_TRY(r->build_plan(h, w, scale, iters));
+  out4[0] = r->flops; out4[1] = (double)r->steps.size(); out4[2] = r->Hs; out4[3] = r->Ws;
   return 0;
   API_GUARD_END
 }

@@ -1,0 +1,549 @@
+// prisma_b200 -- RAFT optical-flow engine: flow_raft.infer (bands/flow_raft.py:51-66) for one frame pair, forward
+// and backward flow in one pass (batch 2 = [prev,curr] / [curr,prev], flow_raft.py:105-106).
+//
+// Reference model: bands/raft/raft.py:87-146 (test_mode), extractor.py (BasicEncoder), corr.py (CorrBlock),
+// update.py (BasicUpdateBlock).  What differs structurally from the reference, with identical results:
+//   * fnet runs on the two distinct frames once (the reference runs it on the 4-image concatenation of two identical
+//     pairs; InstanceNorm statistics are per image so the outputs are the same) and cnet likewise;
+//   * only the last iteration's up-sampling mask / convex up-sampling is computed (test_mode consumes only that one);
+//   * BatchNorm (eval) of cnet is folded into the conv weights; InstanceNorm of fnet is a two-stage reduction +
+//     normalise kernel between convs; every conv is the tcgen05 shifted-row GEMM on zero-bordered NHWC fp16 maps.
+#include "engine_raft.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+
+namespace prisma {
+
+struct RMap {  // B zero-bordered NHWC fp16 maps
+  __half* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0, pad = 1;
+  int Hp() const { return H + 2 * pad; }
+  int Wp() const { return W + 2 * pad; }
+  long long img_rows() const { return (long long)Hp() * Wp(); }
+  long long rows() const { return B * img_rows(); }
+};
+
+template <typename T>
+static int r_alloc(std::vector<void*>& pool, T** out, size_t n) {
+  void* p = nullptr;
+  PRISMA_CUDA_OK(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 256)));
+  PRISMA_CUDA_OK(cudaMemset(p, 0, std::max<size_t>(n * sizeof(T), 256)));
+  pool.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+
+RaftEngine::~RaftEngine() {
+  cudaSetDevice(device);
+  for (void* p : allocs) cudaFree(p);
+  for (void* p : plan_allocs) cudaFree(p);
+  delete corr;
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int RaftEngine::init(int dev) {
+  device = dev;
+  int n = 0;
+  PRISMA_CUDA_OK(cudaGetDeviceCount(&n));
+  PRISMA_CHECK(dev >= 0 && dev < n, "bad device ordinal");
+  PRISMA_CUDA_OK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  PRISMA_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  PRISMA_CHECK(prop.major == 10, "prisma_b200 kernels are sm_100a only; there is no fallback path");
+  num_sms = prop.multiProcessorCount;
+  PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const char* ng = getenv("PRISMA_NO_GRAPH");
+  use_graph = !(ng && ng[0] == '1');
+  return 0;
+}
+
+int RaftEngine::load_tensor(const std::string& name, const float* data, const int64_t* shape, int ndim) {
+  PRISMA_CHECK(!finalized, "load_tensor after finalize");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(data, data + n);
+  std::string key = name;
+  if (key.rfind("module.", 0) == 0) key = key.substr(7);  // DataParallel checkpoints (flow_raft.py:42-44)
+  host[key] = std::move(t);
+  return 0;
+}
+
+const HostTensor* RaftEngine::get(const std::string& name) {
+  auto it = host.find(name);
+  if (it == host.end()) { set_last_error("missing RAFT weight tensor '" + name + "'"); return nullptr; }
+  return &it->second;
+}
+
+// conv weight [Cout][Cin][kh][kw] (+bias) -> fp16 [round_up(Npad,256)][taps*kc*64], fp32 bias [Npad]; optional eval-mode
+// BatchNorm folding (y = (conv(x) - mean) * gamma / sqrt(var + eps) + beta, eps = 1e-5) and output scale.
+int RaftEngine::up_conv(const std::string& name, const std::string& bn, int Cout, int Cin, int kh, int kw, int Npad,
+                        float out_scale, ConvW* out) {
+  const HostTensor* w = get(name + ".weight");
+  const HostTensor* b = get(name + ".bias");
+  if (!w || !b) return -1;
+  PRISMA_CHECK((long long)w->data.size() == (long long)Cout * Cin * kh * kw, "RAFT weight '" + name + "' has an unexpected size");
+  std::vector<float> sc(Cout, out_scale), sh(Cout, 0.f);
+  for (int n = 0; n < Cout; ++n) sh[n] = b->data[n] * out_scale;
+  if (!bn.empty()) {
+    const HostTensor *g = get(bn + ".weight"), *be = get(bn + ".bias"), *mu = get(bn + ".running_mean"), *var = get(bn + ".running_var");
+    if (!g || !be || !mu || !var) return -1;
+    for (int n = 0; n < Cout; ++n) {
+      const float k = g->data[n] / sqrtf(var->data[n] + 1e-5f);
+      sc[n] = k;
+      sh[n] = (b->data[n] - mu->data[n]) * k + be->data[n];
+    }
+  }
+  const int taps = kh * kw, kc = ceil_div(Cin, 64), K = taps * kc * 64, rows = round_up(Npad, 256);
+  std::vector<__half> h((size_t)rows * K, __float2half_rn(0.f));
+  for (int n = 0; n < Cout; ++n)
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < Cin; ++c)
+        h[(size_t)n * K + (size_t)t * kc * 64 + c] = __float2half_rn(w->data[((size_t)n * Cin + c) * taps + t] * sc[n]);
+  PRISMA_TRY(r_alloc(allocs, &out->w, h.size()));
+  PRISMA_CUDA_OK(cudaMemcpy(out->w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> bias(round_up(Npad, 8), 0.f);
+  for (int n = 0; n < Cout; ++n) bias[n] = sh[n];
+  PRISMA_TRY(r_alloc(allocs, &out->b, bias.size()));
+  PRISMA_CUDA_OK(cudaMemcpy(out->b, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  out->cout = Npad; out->cin = Cin; out->kh = kh; out->kw = kw;
+  return 0;
+}
+
+int RaftEngine::up_encoder(const std::string& p, bool bn, EncW* e) {
+  auto B = [&](const std::string& n) { return bn ? p + n : std::string(); };
+  {  // stem: im2col K = 147 -> 192; weight [64][3][7][7] flattens to k = c*49 + ky*7 + kx, i.e. a "1x1 conv" with Cin 147
+    const HostTensor* w = get(p + "conv1.weight");
+    if (!w) return -1;
+    HostTensor flat = *w;
+    host[p + "conv1_flat.weight"] = flat;
+    host[p + "conv1_flat.bias"] = *get(p + "conv1.bias");
+    PRISMA_TRY(up_conv(p + "conv1_flat", B("norm1"), 64, 147, 1, 1, 64, 1.f, &e->stem));
+  }
+  const int dims[3] = {64, 96, 128};
+  int cin = 64;
+  for (int li = 0; li < 3; ++li) {
+    for (int bi = 0; bi < 2; ++bi) {
+      const std::string q = p + "layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".";
+      ResW& r = e->blk[li][bi];
+      PRISMA_TRY(up_conv(q + "conv1", B(("layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".norm1")), dims[li], bi == 0 ? cin : dims[li], 3, 3, dims[li], 1.f, &r.c1));
+      PRISMA_TRY(up_conv(q + "conv2", B(("layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".norm2")), dims[li], dims[li], 3, 3, dims[li], 1.f, &r.c2));
+      r.has_ds = (bi == 0 && li > 0);
+      if (r.has_ds)
+        PRISMA_TRY(up_conv(q + "downsample.0", B(("layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".downsample.1")), dims[li], cin, 1, 1, dims[li], 1.f, &r.ds));
+    }
+    cin = dims[li];
+  }
+  PRISMA_TRY(up_conv(p + "conv2", "", 256, 128, 1, 1, 256, 1.f, &e->out));
+  return 0;
+}
+
+int RaftEngine::finalize() {
+  PRISMA_CHECK(!finalized, "finalize called twice");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_TRY(up_encoder("fnet.", false, &w.fnet));
+  PRISMA_TRY(up_encoder("cnet.", true, &w.cnet));
+  const std::string u = "update_block.";
+  PRISMA_TRY(up_conv(u + "encoder.convc1", "", 256, 324, 1, 1, 256, 1.f, &w.convc1));
+  PRISMA_TRY(up_conv(u + "encoder.convc2", "", 192, 256, 3, 3, 192, 1.f, &w.convc2));
+  PRISMA_TRY(up_conv(u + "encoder.convf2", "", 64, 128, 3, 3, 64, 1.f, &w.convf2));
+  PRISMA_TRY(up_conv(u + "encoder.conv", "", 126, 256, 3, 3, 128, 1.f, &w.conv));  // 126 -> 128 (two zero channels)
+  {  // convf1 7x7 on the 2-channel flow: direct kernel, fp32 weights
+    const HostTensor* wt = get(u + "encoder.convf1.weight");
+    const HostTensor* bs = get(u + "encoder.convf1.bias");
+    if (!wt || !bs) return -1;
+    PRISMA_TRY(r_alloc(allocs, &w.convf1_w, wt->data.size()));
+    PRISMA_TRY(r_alloc(allocs, &w.convf1_b, bs->data.size()));
+    PRISMA_CUDA_OK(cudaMemcpy(w.convf1_w, wt->data.data(), wt->data.size() * 4, cudaMemcpyHostToDevice));
+    PRISMA_CUDA_OK(cudaMemcpy(w.convf1_b, bs->data.data(), bs->data.size() * 4, cudaMemcpyHostToDevice));
+  }
+  for (int pass = 0; pass < 2; ++pass) {  // SepConvGRU: (1,5) then (5,1); z and r stacked into one N = 256 conv
+    const std::string s = std::to_string(pass + 1);
+    const int kh = pass == 0 ? 1 : 5, kw = pass == 0 ? 5 : 1;
+    const HostTensor *wz = get(u + "gru.convz" + s + ".weight"), *wr = get(u + "gru.convr" + s + ".weight");
+    const HostTensor *bz = get(u + "gru.convz" + s + ".bias"), *br = get(u + "gru.convr" + s + ".bias");
+    if (!wz || !wr || !bz || !br) return -1;
+    HostTensor wzr, bzr;
+    wzr.data = wz->data; wzr.data.insert(wzr.data.end(), wr->data.begin(), wr->data.end());
+    bzr.data = bz->data; bzr.data.insert(bzr.data.end(), br->data.begin(), br->data.end());
+    host[u + "gru.zr" + s + ".weight"] = wzr;
+    host[u + "gru.zr" + s + ".bias"] = bzr;
+    PRISMA_TRY(up_conv(u + "gru.zr" + s, "", 256, 384, kh, kw, 256, 1.f, &w.zr[pass]));
+    PRISMA_TRY(up_conv(u + "gru.convq" + s, "", 128, 384, kh, kw, 128, 1.f, &w.q[pass]));
+  }
+  PRISMA_TRY(up_conv(u + "flow_head.conv1", "", 256, 128, 3, 3, 256, 1.f, &w.fh1));
+  PRISMA_TRY(up_conv(u + "flow_head.conv2", "", 2, 256, 3, 3, 4, 1.f, &w.fh2));
+  PRISMA_TRY(up_conv(u + "mask.0", "", 256, 128, 3, 3, 256, 1.f, &w.mk1));
+  PRISMA_TRY(up_conv(u + "mask.2", "", 576, 256, 1, 1, 576, 0.25f, &w.mk2));  // mask = .25 * conv (update.py:135)
+  host.clear();
+  finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ plan helpers
+int RaftEngine::new_map(RMap* m, int B, int H, int W, int C, int pad) {
+  m->B = B; m->H = H; m->W = W; m->C = C; m->pad = pad;
+  return r_alloc(plan_allocs, &m->p, (size_t)m->rows() * C);
+}
+
+void RaftEngine::add(const char* name, std::function<int(cudaStream_t)> fn) { steps.push_back({0, name, std::move(fn)}); }
+
+// conv (kh x kw, 'same') on channels [c0, c0+cin) of a padded map; epilogue filled in by the caller
+int RaftEngine::add_conv(const char* name, const RMap& in, int c0, const ConvW& cw, GemmEpilogue ep, int sub) {
+  PRISMA_CHECK(cw.kh / 2 <= in.pad && cw.kw / 2 <= in.pad, "conv halo exceeds the map border");
+  int off[GEMM_MAX_TAPS];
+  for (int ky = 0; ky < cw.kh; ++ky)
+    for (int kx = 0; kx < cw.kw; ++kx) off[ky * cw.kw + kx] = (ky - cw.kh / 2) * in.Wp() + (kx - cw.kw / 2);
+  if (ep.row_map == ROW_LINEAR) ep.row_map = ROW_PADDED;
+  ep.in_w = in.Wp(); ep.in_h = in.Hp(); ep.img_rows = (int)in.img_rows(); ep.pad = in.pad; ep.sub = sub;
+  if (!ep.bias) ep.bias = cw.b;
+  GemmLaunch g;
+  PRISMA_TRY(gemm_prepare(&g, in.p + c0, in.rows(), cw.cin, in.C, cw.w, round_up(cw.cout, 256), (int)in.rows(), cw.cout,
+                          cw.kh * cw.kw, off, ep, num_sms));
+  flops += 2.0 * in.B * (double)(in.H / sub) * (in.W / sub) * cw.kh * cw.kw * cw.cin * cw.cout;
+  add(name, [g](cudaStream_t s) { return gemm_run(g, s); });
+  return 0;
+}
+
+// destination = interior of another padded map (possibly different border / stride-2 sub-sampled geometry)
+static void to_map(GemmEpilogue& ep, const RMap& dst, int col0, bool relu_copy = false) {
+  ep.row_map = ROW_PADDED;
+  ep.out_wp = dst.Wp(); ep.out_img_rows = (int)dst.img_rows(); ep.out_pad = dst.pad;
+  if (relu_copy) { ep.out_f16_relu = dst.p + col0; ep.out_f16_relu_ld = dst.C; }
+  else { ep.out_f16 = dst.p + col0; ep.out_f16_ld = dst.C; }
+}
+
+// fnet: conv -> dense fp32 -> InstanceNorm statistics; returns the dense buffer slot used
+int RaftEngine::add_conv_in(const char* name, const RMap& in, const ConvW& cw, int sub, float* dense, float* stats) {
+  GemmEpilogue ep;
+  ep.row_map = ROW_PAD2TOK;
+  ep.out_f32 = dense; ep.out_f32_ld = cw.cout;
+  PRISMA_TRY(add_conv(name, in, 0, cw, ep, sub));
+  const int Ho = in.H / sub, Wo = in.W / sub, C = cw.cout, B = in.B;
+  float* part = in_part;
+  add("instnorm_stats", [=](cudaStream_t s) { return instnorm_stats(dense, B, Ho * Wo, C, part, stats, s); });
+  return 0;
+}
+
+int RaftEngine::build_encoder(const EncW& e, bool inorm, const __half* stem_cols, RMap* out_map128) {
+  const int B = 2, H2 = Hp_ / 2, W2 = Wp_ / 2;
+  RMap x;
+  PRISMA_TRY(new_map(&x, B, H2, W2, 64, 1));
+  const int zero_off[1] = {0};
+  {  // stem GEMM over the im2col matrix
+    GemmEpilogue ep;
+    ep.bias = e.stem.b;
+    GemmLaunch g;
+    if (inorm) {
+      ep.out_f32 = dense_a; ep.out_f32_ld = 64;
+      PRISMA_TRY(gemm_prepare(&g, stem_cols, (long long)B * H2 * W2, 192, 192, e.stem.w, 256, B * H2 * W2, 64, 1, zero_off, ep, num_sms));
+      add("stem_gemm", [g](cudaStream_t s) { return gemm_run(g, s); });
+      float* d = dense_a; float* st = stats_a; float* part = in_part; __half* o = x.p;
+      add("instnorm_stats", [=](cudaStream_t s) { return instnorm_stats(d, B, H2 * W2, 64, part, st, s); });
+      add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, H2, W2, 64, nullptr, nullptr, nullptr, o, 1, s); });
+    } else {
+      ep.act = 2;
+      ep.row_map = ROW_TOK2PAD; ep.in_w = W2; ep.in_h = H2; ep.out_wp = x.Wp(); ep.out_img_rows = (int)x.img_rows(); ep.out_pad = 1;
+      ep.out_f16 = x.p; ep.out_f16_ld = 64;
+      PRISMA_TRY(gemm_prepare(&g, stem_cols, (long long)B * H2 * W2, 192, 192, e.stem.w, 256, B * H2 * W2, 64, 1, zero_off, ep, num_sms));
+      add("stem_gemm", [g](cudaStream_t s) { return gemm_run(g, s); });
+    }
+    flops += 2.0 * B * H2 * (double)W2 * 147 * 64;
+  }
+  const int dims[3] = {64, 96, 128};
+  for (int li = 0; li < 3; ++li)
+    for (int bi = 0; bi < 2; ++bi) {
+      const ResW& r = e.blk[li][bi];
+      const int sub = r.has_ds ? 2 : 1;
+      const int Ho = x.H / sub, Wo = x.W / sub, C = dims[li];
+      RMap y, o;
+      PRISMA_TRY(new_map(&y, B, Ho, Wo, C, 1));
+      PRISMA_TRY(new_map(&o, B, Ho, Wo, C, 1));
+      if (inorm) {
+        // y = relu(IN(conv1(x))) ; z = conv2(y) ; out = relu(skip + relu(IN(z))), skip = x or IN(downsample(x))
+        PRISMA_TRY(add_conv_in("res_conv1", x, r.c1, sub, dense_a, stats_a));
+        { float* d = dense_a; float* st = stats_a; __half* yo = y.p;
+          add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, Ho, Wo, C, nullptr, nullptr, nullptr, yo, 1, s); }); }
+        PRISMA_TRY(add_conv_in("res_conv2", y, r.c2, 1, dense_a, stats_a));
+        if (r.has_ds) {
+          PRISMA_TRY(add_conv_in("res_downsample", x, r.ds, 2, dense_b, stats_b));
+          float* d = dense_a; float* st = stats_a; float* d2 = dense_b; float* st2 = stats_b; __half* oo = o.p;
+          add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, Ho, Wo, C, nullptr, d2, st2, oo, 1, s); });
+        } else {
+          float* d = dense_a; float* st = stats_a; const __half* sk = x.p; __half* oo = o.p;
+          add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, Ho, Wo, C, sk, nullptr, nullptr, oo, 1, s); });
+        }
+      } else {
+        // BatchNorm folded: y = relu(conv1'(x)) ; out = relu(skip + relu(conv2'(y)))
+        { GemmEpilogue ep; ep.act = 2;
+          if (sub > 1) to_map(ep, y, 0); else { ep.out_f16 = y.p; ep.out_f16_ld = C; }
+          PRISMA_TRY(add_conv("res_conv1", x, 0, r.c1, ep, sub)); }
+        const __half* skip = x.p;
+        if (r.has_ds) {
+          RMap d;
+          PRISMA_TRY(new_map(&d, B, Ho, Wo, C, 1));
+          GemmEpilogue ep; to_map(ep, d, 0);
+          PRISMA_TRY(add_conv("res_downsample", x, 0, r.ds, ep, 2));
+          skip = d.p;
+        }
+        { GemmEpilogue ep; ep.act = 2; ep.res_a = skip; ep.res_a_ld = C; ep.out_f16_relu = o.p; ep.out_f16_relu_ld = C;
+          PRISMA_TRY(add_conv("res_conv2", y, 0, r.c2, ep, 1)); }
+      }
+      x = o;
+    }
+  *out_map128 = x;
+  return 0;
+}
+
+int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
+  PRISMA_CHECK(finalized, "weights not finalized");
+  PRISMA_CHECK(iters_ >= 1 && iters_ <= 64, "iterations must be in [1,64]");
+  if (plan_H == H && plan_W == W && plan_scale == scale && iters == iters_) return 0;
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  for (void* q : plan_allocs) cudaFree(q);
+  plan_allocs.clear();
+  steps.clear();
+  taps.clear();
+  delete corr; corr = nullptr;
+  if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  plan_H = plan_W = 0; flops = 0; iters = iters_;
+
+  Hs = (int)nearbyint((double)H * scale); Ws = (int)nearbyint((double)W * scale);
+  const int pad_h = (((Hs / 8) + 1) * 8 - Hs) % 8, pad_w = (((Ws / 8) + 1) * 8 - Ws) % 8;  // common/flow.py:46-53
+  pads[0] = pad_w / 2; pads[1] = pad_w - pad_w / 2; pads[2] = pad_h / 2; pads[3] = pad_h - pad_h / 2;
+  Hp_ = Hs + pad_h; Wp_ = Ws + pad_w;
+  H8 = Hp_ / 8; W8 = Wp_ / 8;
+  const int B = 2, P = H8 * W8;
+
+  PRISMA_TRY(r_alloc(plan_allocs, &b.img, (size_t)2 * H * W * 3));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.resized, (size_t)2 * Hs * Ws * 3));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.chw, (size_t)2 * 3 * Hp_ * Wp_));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.stem_cols, (size_t)2 * (Hp_ / 2) * (Wp_ / 2) * 192));
+  const size_t dense_max = (size_t)2 * (Hp_ / 2) * (Wp_ / 2) * 64;  // largest conv output of the encoders (floats)
+  PRISMA_TRY(r_alloc(plan_allocs, &dense_a, dense_max));
+  PRISMA_TRY(r_alloc(plan_allocs, &dense_b, dense_max / 2));
+  PRISMA_TRY(r_alloc(plan_allocs, &stats_a, 2 * 256 * 2));
+  PRISMA_TRY(r_alloc(plan_allocs, &stats_b, 2 * 256 * 2));
+  PRISMA_TRY(r_alloc(plan_allocs, &in_part, (size_t)instnorm_partial_floats(2, (Hp_ / 2) * (Wp_ / 2), 128)));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.coords0, (size_t)B * 2 * P));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.coords1, (size_t)B * 2 * P));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.cnet_out, (size_t)B * P * 256));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.flow_up, (size_t)B * Hs * Ws * 2));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.rgb, (size_t)B * Hs * Ws * 3));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.mm, 4));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.maxd, 4));
+
+  corr = new FlowCorr();
+  PRISMA_TRY(corr->init(device, B, H8, W8));
+
+  // ---- K11 pre-process of both frames, stem im2col (shared by fnet and cnet)
+  {
+    const uint8_t* img = b.img; uint8_t* rs = b.resized; float* chw = b.chw; __half* cols = b.stem_cols;
+    const int Hs_ = Hs, Ws_ = Ws, Hpp = Hp_, Wpp = Wp_;
+    int pd[4] = {pads[0], pads[1], pads[2], pads[3]};
+    add("raft_preprocess", [=](cudaStream_t s) {
+      for (int i = 0; i < 2; ++i)
+        PRISMA_TRY(raft_preprocess(img + (size_t)i * H * W * 3, H, W, Hs_, Ws_, pd, rs + (size_t)i * Hs_ * Ws_ * 3,
+                                   chw + (size_t)i * 3 * Hpp * Wpp, s));
+      return 0;
+    });
+    add("stem_im2col", [=](cudaStream_t s) { return raft_im2col_stem(chw, 2, Hpp, Wpp, cols, s); });
+  }
+  // ---- fnet (instance norm) -> feature maps straight into the correlation operand buffers
+  RMap f128, c128;
+  PRISMA_TRY(build_encoder(w.fnet, true, b.stem_cols, &f128));
+  { GemmEpilogue ep; ep.row_map = ROW_PAD2TOK; ep.out_img_rows = corr->rows_pad;
+    ep.out_f16 = corr->fmap1; ep.out_f16_ld = 256;
+    PRISMA_TRY(add_conv("fnet_out", f128, 0, w.fnet.out, ep, 1)); }
+  {  // image pair b uses fmap1 = frame b, fmap2 = the other frame (flow_raft.py:105-106)
+    FlowCorr* c = corr;
+    add("fmap_swap", [c](cudaStream_t s) {
+      const size_t n = (size_t)c->rows_pad * c->C * sizeof(__half);
+      PRISMA_CUDA_OK(cudaMemcpyAsync(c->fmap2[0], c->fmap1 + (size_t)c->rows_pad * c->C, n, cudaMemcpyDeviceToDevice, s));
+      PRISMA_CUDA_OK(cudaMemcpyAsync(c->fmap2[0] + (size_t)c->rows_pad * c->C, c->fmap1, n, cudaMemcpyDeviceToDevice, s));
+      return 0;
+    });
+    add("corr_build", [c](cudaStream_t s) { return c->build(s); });
+    flops += c->flops_build;
+  }
+  // ---- cnet (batch norm folded) -> tanh / relu split into the GRU operand maps
+  PRISMA_TRY(build_encoder(w.cnet, false, b.stem_cols, &c128));
+  RMap hx, rhx, corrf, c1, c2, f1, zr, q, fh, delta, mk, mask;
+  PRISMA_TRY(new_map(&hx, B, H8, W8, 384, 2));
+  PRISMA_TRY(new_map(&rhx, B, H8, W8, 384, 2));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.h_master, (size_t)hx.rows() * 128));
+  { GemmEpilogue ep; ep.row_map = ROW_PAD2TOK; ep.out_f32 = b.cnet_out; ep.out_f32_ld = 256;
+    PRISMA_TRY(add_conv("cnet_out", c128, 0, w.cnet.out, ep, 1)); }
+  {
+    const float* cn = b.cnet_out; float* hm = b.h_master; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
+    float* c0 = b.coords0; float* c1p = b.coords1;
+    add("cnet_split", [=](cudaStream_t s) { return raft_cnet_split(cn, 2, h8, w8, 2, hm, hxp, rhp, s); });
+    add("coords_init", [=](cudaStream_t s) { return raft_coords_init(c0, c1p, 2, h8, w8, s); });
+  }
+  // ---- update block, `iters` times (raft.py:123-141)
+  PRISMA_TRY(new_map(&corrf, B, H8, W8, 384, 2));
+  PRISMA_TRY(new_map(&c1, B, H8, W8, 256, 2));
+  PRISMA_TRY(new_map(&c2, B, H8, W8, 256, 2));   // [convc2 out (192) | convf2 out (64)]
+  PRISMA_TRY(new_map(&f1, B, H8, W8, 128, 2));
+  PRISMA_TRY(new_map(&zr, B, H8, W8, 256, 2));
+  PRISMA_TRY(new_map(&q, B, H8, W8, 128, 2));
+  PRISMA_TRY(new_map(&fh, B, H8, W8, 256, 2));
+  PRISMA_TRY(new_map(&mk, B, H8, W8, 256, 2));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.delta, (size_t)hx.rows() * 4));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.mask, (size_t)hx.rows() * 576));
+  const long long rows = hx.rows();
+  for (int it = 0; it < iters; ++it) {
+    {
+      FlowCorr* c = corr; const float* c1p = b.coords1; __half* dst = corrf.p; const int wp = corrf.Wp(), ir = (int)corrf.img_rows();
+      add("corr_lookup", [=](cudaStream_t s) { return c->lookup_to(c1p, dst, 384, wp, 2, ir, s); });
+    }
+    { GemmEpilogue ep; ep.act = 2; ep.out_f16 = c1.p; ep.out_f16_ld = 256;            // convc1 1x1 324 -> 256
+      ConvW cw = w.convc1; cw.cin = 384;  // the lookup map is zero padded to 384 channels, so are the weights' K
+      PRISMA_TRY(add_conv("convc1", corrf, 0, cw, ep, 1)); }
+    { GemmEpilogue ep; ep.act = 2; ep.out_f16 = c2.p; ep.out_f16_ld = 256;            // convc2 3x3 256 -> 192
+      PRISMA_TRY(add_conv("convc2", c1, 0, w.convc2, ep, 1)); }
+    {
+      const float* c0 = b.coords0; const float* c1p = b.coords1; const float* wt = w.convf1_w; const float* bs = w.convf1_b;
+      __half* o = f1.p; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
+      add("convf1_direct", [=](cudaStream_t s) { return raft_flow_conv7(c0, c1p, wt, bs, 2, h8, w8, 2, o, hxp, rhp, s); });
+    }
+    { GemmEpilogue ep; ep.act = 2; ep.out_f16 = c2.p + 192; ep.out_f16_ld = 256;      // convf2 3x3 128 -> 64
+      PRISMA_TRY(add_conv("convf2", f1, 0, w.convf2, ep, 1)); }
+    { // conv 3x3 256 -> 126 (+2 zero channels); the 126 motion channels go to cols 256..381 of hx and rhx; the two
+      // trailing columns are rewritten with the flow by convf1_direct of the NEXT iteration -- so restore them here
+      GemmEpilogue ep; ep.act = 2; ep.out_f16 = hx.p + 256; ep.out_f16_ld = 384; ep.out_f16_relu = rhx.p + 256; ep.out_f16_relu_ld = 384;
+      PRISMA_TRY(add_conv("motion_conv", c2, 0, w.conv, ep, 1));
+      const float* c0 = b.coords0; const float* c1p = b.coords1; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
+      add("flow_cols", [=](cudaStream_t s) { return raft_flow_cols(c0, c1p, 2, h8, w8, 2, hxp, rhp, s); });
+    }
+    for (int pass = 0; pass < 2; ++pass) {  // SepConvGRU horizontal then vertical (update.py:45-60)
+      { GemmEpilogue ep; ep.act = 3; ep.out_f16 = zr.p; ep.out_f16_ld = 256;
+        PRISMA_TRY(add_conv("gru_zr", hx, 0, w.zr[pass], ep, 1)); }
+      { const __half* z = zr.p; const float* hm = b.h_master; __half* rhp = rhx.p;
+        add("gru_rh", [=](cudaStream_t s) { return raft_gru_rh(z, hm, rhp, rows, s); }); }
+      { GemmEpilogue ep; ep.act = 4; ep.out_f16 = q.p; ep.out_f16_ld = 128;
+        PRISMA_TRY(add_conv("gru_q", rhx, 0, w.q[pass], ep, 1)); }
+      { const __half* z = zr.p; const __half* qq = q.p; float* hm = b.h_master; __half* hxp = hx.p;
+        add("gru_update", [=](cudaStream_t s) { return raft_gru_update(z, qq, hm, hxp, rows, s); }); }
+    }
+    { GemmEpilogue ep; ep.act = 2; ep.out_f16 = fh.p; ep.out_f16_ld = 256;            // flow head
+      ConvW cw = w.fh1;
+      PRISMA_TRY(add_conv("flow_head1", hx, 0, cw, ep, 1)); }
+    { GemmEpilogue ep; ep.out_f32 = b.delta; ep.out_f32_ld = 4;
+      PRISMA_TRY(add_conv("flow_head2", fh, 0, w.fh2, ep, 1)); }
+    { const float* d = b.delta; float* c1p = b.coords1; const int h8 = H8, w8 = W8;
+      add("coords_update", [=](cudaStream_t s) { return raft_coords_update(d, 2, h8, w8, 2, c1p, s); }); }
+    if (debug_taps && it == 0) {
+      PRISMA_TRY(r_alloc(plan_allocs, &b.h_tap, (size_t)hx.rows() * 128));
+      PRISMA_TRY(r_alloc(plan_allocs, &b.coords_tap, (size_t)B * 2 * P));
+      float* ht = b.h_tap; const float* hm = b.h_master; float* ct = b.coords_tap; const float* c1p = b.coords1;
+      const size_t n1 = (size_t)hx.rows() * 128 * 4, n2 = (size_t)B * 2 * P * 4;
+      add("tap_iter0", [=](cudaStream_t s) {
+        PRISMA_CUDA_OK(cudaMemcpyAsync(ht, hm, n1, cudaMemcpyDeviceToDevice, s));
+        PRISMA_CUDA_OK(cudaMemcpyAsync(ct, c1p, n2, cudaMemcpyDeviceToDevice, s));
+        return 0;
+      });
+    }
+  }
+  // ---- up-sampling mask (last iteration only) + convex up-sampling + unpad + HWC
+  { GemmEpilogue ep; ep.act = 2; ep.out_f16 = mk.p; ep.out_f16_ld = 256;
+    PRISMA_TRY(add_conv("mask_head1", hx, 0, w.mk1, ep, 1)); }
+  { GemmEpilogue ep; ep.alpha = 0.25f; ep.out_f32 = b.mask; ep.out_f32_ld = 576;
+    PRISMA_TRY(add_conv("mask_head2", mk, 0, w.mk2, ep, 1)); }
+  {
+    const float* m = b.mask; const float* c0 = b.coords0; const float* c1p = b.coords1; float* up = b.flow_up;
+    const int h8 = H8, w8 = W8, Hs_ = Hs, Ws_ = Ws, pt = pads[2], pl = pads[0];
+    add("convex_upsample", [=](cudaStream_t s) { return raft_convex_upsample(m, c0, c1p, 2, h8, w8, 2, Hs_, Ws_, pt, pl, up, s); });
+    uint8_t* rgb = b.rgb; uint32_t* mm = b.mm; float* mx = b.maxd; const int sms = num_sms;
+    add("flow_encode", [=](cudaStream_t s) {
+      for (int i = 0; i < 2; ++i)
+        PRISMA_TRY(flow_encode(up + (size_t)i * Hs_ * Ws_ * 2, Hs_, Ws_, rgb + (size_t)i * Hs_ * Ws_ * 3, mm + i, mx + i, sms, s));
+      return 0;
+    });
+  }
+  taps["resized"] = {b.resized, 2 * Hs, Ws * 3, 1, 3};
+  taps["fmap"] = {corr->fmap1, 0, 0, 0, 4};
+  taps["cnet_out"] = {b.cnet_out, B * P, 256, 1, 0};
+  taps["coords1_iter0"] = {b.coords_tap, B * 2, P, 1, 0};
+  taps["h_iter0"] = {b.h_tap, (int)hx.rows(), 128, 1, 0};
+  taps["coords1"] = {b.coords1, B * 2, P, 1, 0};
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  plan_H = H; plan_W = W; plan_scale = scale;
+  if (use_graph) {
+    PRISMA_TRY(run_direct(stream));
+    PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+    cudaGraph_t graph = nullptr;
+    PRISMA_CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    int r = run_direct(stream);
+    cudaError_t e = cudaStreamEndCapture(stream, &graph);
+    if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+    PRISMA_CUDA_OK(e);
+    PRISMA_CUDA_OK(cudaGraphInstantiate(&graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  return 0;
+}
+
+int RaftEngine::run_direct(cudaStream_t s) {
+  for (auto& st : steps) PRISMA_TRY(st.fn(s));
+  return 0;
+}
+
+int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, float scale, int iters_, float* fwd, float* bwd,
+                      uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd, float* ms_out) {
+  PRISMA_CHECK(prev && curr && H > 0 && W > 0, "bad frame pair");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_TRY(build_plan(H, W, scale, iters_));
+  const size_t fb = (size_t)H * W * 3;
+  PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, prev, fb, cudaMemcpyHostToDevice, stream));
+  PRISMA_CUDA_OK(cudaMemcpyAsync(b.img + fb, curr, fb, cudaMemcpyHostToDevice, stream));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ms_out) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
+  if (graph_exec) PRISMA_CUDA_OK(cudaGraphLaunch(graph_exec, stream));
+  else PRISMA_TRY(run_direct(stream));
+  if (ms_out) cudaEventRecord(e1, stream);
+  const size_t n = (size_t)Hs * Ws;
+  float mx[2] = {0, 0};
+  if (fwd) PRISMA_CUDA_OK(cudaMemcpyAsync(fwd, b.flow_up, n * 8, cudaMemcpyDeviceToHost, stream));
+  if (bwd) PRISMA_CUDA_OK(cudaMemcpyAsync(bwd, b.flow_up + n * 2, n * 8, cudaMemcpyDeviceToHost, stream));
+  if (fwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(fwd_rgb, b.rgb, n * 3, cudaMemcpyDeviceToHost, stream));
+  if (bwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(bwd_rgb, b.rgb + n * 3, n * 3, cudaMemcpyDeviceToHost, stream));
+  PRISMA_CUDA_OK(cudaMemcpyAsync(mx, b.maxd, 8, cudaMemcpyDeviceToHost, stream));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  if (ms_out) { cudaEventElapsedTime(ms_out, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+  if (max_fwd) *max_fwd = mx[0];
+  if (max_bwd) *max_bwd = mx[1];
+  return 0;
+}
+
+long long RaftEngine::read_tap(const std::string& name, float* out, long long capacity) {
+  auto it = taps.find(name);
+  if (it == taps.end()) { set_last_error("unknown tap '" + name + "'"); return -1; }
+  cudaSetDevice(device);
+  const Tap& t = it->second;
+  if (t.kind == 4) {  // fnet feature maps: fp16 [2][rows_pad][256] -> dense f32 [2][P][256]
+    const long long P = (long long)H8 * W8, n = 2 * P * 256;
+    if (n > capacity) { set_last_error("tap buffer too small"); return -1; }
+    std::vector<__half> h((size_t)2 * corr->rows_pad * 256);
+    if (cudaMemcpy(h.data(), t.p, h.size() * 2, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+    for (int b2 = 0; b2 < 2; ++b2)
+      for (long long i = 0; i < P * 256; ++i) out[b2 * P * 256 + i] = __half2float(h[(size_t)b2 * corr->rows_pad * 256 + i]);
+    return n;
+  }
+  const long long n = (long long)t.a * t.b;
+  if (n > capacity) { set_last_error("tap buffer too small"); return -1; }
+  if (t.kind == 0) {
+    if (cudaMemcpy(out, t.p, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+  } else {  // u8
+    std::vector<uint8_t> h(n);
+    if (cudaMemcpy(h.data(), t.p, n, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+    for (long long i = 0; i < n; ++i) out[i] = h[i];
+  }
+  return n;
+}
+
+}  // namespace prisma

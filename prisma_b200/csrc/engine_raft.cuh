@@ -1,0 +1,71 @@
+// prisma_b200 -- RAFT optical-flow engine declaration (see engine_raft.cu).
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "engine_da.cuh"  // HostTensor, Step, Tap
+#include "flow.cuh"
+#include "raft_kernels.cuh"
+
+namespace prisma {
+
+struct ConvW { __half* w = nullptr; float* b = nullptr; int cout = 0, cin = 0, kh = 1, kw = 1; };
+struct ResW { ConvW c1, c2, ds; bool has_ds = false; };
+struct EncW { ConvW stem; ResW blk[3][2]; ConvW out; };
+struct RaftWeights {
+  EncW fnet, cnet;
+  ConvW convc1, convc2, convf2, conv, zr[2], q[2], fh1, fh2, mk1, mk2;
+  float *convf1_w = nullptr, *convf1_b = nullptr;
+};
+struct RaftBuffers {
+  uint8_t* img; uint8_t* resized; float* chw; __half* stem_cols; float *coords0, *coords1, *cnet_out, *h_master, *delta, *mask;
+  float* flow_up; uint8_t* rgb; uint32_t* mm; float* maxd; float* h_tap = nullptr; float* coords_tap = nullptr;
+};
+struct RMap;
+
+class RaftEngine {
+ public:
+  ~RaftEngine();
+  int init(int device);
+  int load_tensor(const std::string& name, const float* data, const int64_t* shape, int ndim);
+  int finalize();
+  // prev/curr: h*w*3 u8 RGB; fwd/bwd: hs*ws*2 f32 (may be NULL); *_rgb: hs*ws*3 u8 (may be NULL)
+  int infer(const uint8_t* prev, const uint8_t* curr, int H, int W, float scale, int iters, float* fwd, float* bwd,
+            uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd, float* ms_out);
+  long long read_tap(const std::string& name, float* out, long long capacity);
+  int build_plan(int H, int W, float scale, int iters);
+  int Hs = 0, Ws = 0, H8 = 0, W8 = 0;
+  double flops = 0;
+  std::vector<Step> steps;
+  bool debug_taps = true;
+
+ private:
+  const HostTensor* get(const std::string& name);
+  int up_conv(const std::string& name, const std::string& bn, int Cout, int Cin, int kh, int kw, int Npad, float out_scale,
+              ConvW* out);
+  int up_encoder(const std::string& prefix, bool bn, EncW* e);
+  int new_map(RMap* m, int B, int H, int W, int C, int pad);
+  void add(const char* name, std::function<int(cudaStream_t)> fn);
+  int add_conv(const char* name, const RMap& in, int c0, const ConvW& cw, GemmEpilogue ep, int sub);
+  int add_conv_in(const char* name, const RMap& in, const ConvW& cw, int sub, float* dense, float* stats);
+  int build_encoder(const EncW& e, bool inorm, const __half* stem_cols, RMap* out_map128);
+  int run_direct(cudaStream_t s);
+
+  int device = 0, num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool use_graph = true, finalized = false;
+  std::map<std::string, HostTensor> host;
+  std::vector<void*> allocs, plan_allocs;
+  RaftWeights w;
+  RaftBuffers b;
+  FlowCorr* corr = nullptr;
+  std::map<std::string, Tap> taps;
+  float *dense_a = nullptr, *dense_b = nullptr, *stats_a = nullptr, *stats_b = nullptr, *in_part = nullptr;
+  int plan_H = 0, plan_W = 0, iters = 0, Hp_ = 0, Wp_ = 0, pads[4] = {0, 0, 0, 0};
+  float plan_scale = 0.f;
+};
+
+}  // namespace prisma

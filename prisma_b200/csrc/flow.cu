@@ -177,11 +177,15 @@ __global__ void k_pool_fmap(const __half* __restrict__ f, int H8, int W8, int C,
 __global__ void k_corr_lookup(const float* __restrict__ v0, const float* __restrict__ v1, const float* __restrict__ v2,
                               const float* __restrict__ v3, int B, int P, int H8, int W8, int lh0, int lw0, int lp0,
                               int lh1, int lw1, int lp1, int lh2, int lw2, int lp2, int lh3, int lw3, int lp3,
-                              const float* __restrict__ coords, __half* __restrict__ out, int out_ld) {
+                              const float* __restrict__ coords, __half* __restrict__ out, int out_ld, int out_wp,
+                              int out_pad, int out_img_rows) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= B * P) return;
   const int b = wid / P, i = wid - b * P;
+  // destination row: dense (b*P + i) or a zero-bordered image (the A operand layout of the motion encoder)
+  const size_t orow = out_wp > 0 ? (size_t)b * out_img_rows + (size_t)(i / W8 + out_pad) * out_wp + (i % W8) + out_pad
+                                 : (size_t)wid;
   const float cx = coords[((size_t)b * 2 + 0) * P + i], cy = coords[((size_t)b * 2 + 1) * P + i];
   const int grp = lane / 10, col = lane - grp * 10;  // lanes 30,31 idle
 #pragma unroll
@@ -208,7 +212,7 @@ __global__ void k_corr_lookup(const float* __restrict__ v0, const float* __restr
 #pragma unroll
     for (int r = 0; r < 10; ++r) vn[r] = __shfl_down_sync(0xffffffffu, v[r], 1);
     if (active && col < 9) {
-      __half* o = out + (size_t)wid * out_ld + lvl * 81 + col * 9;
+      __half* o = out + orow * out_ld + lvl * 81 + col * 9;
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
         const float s = wy0 * (wx0 * v[j] + wx1 * vn[j]) + wy1 * (wx0 * v[j + 1] + wx1 * vn[j + 1]);
@@ -307,10 +311,16 @@ int FlowCorr::build(cudaStream_t s) {
 }
 
 int FlowCorr::lookup(const float* d_coords, cudaStream_t s) {
+  return lookup_to(d_coords, lookup_out, 384, 0, 0, 0, s);
+}
+
+int FlowCorr::lookup_to(const float* d_coords, __half* dst, int dst_ld, int dst_wp, int dst_pad, int dst_img_rows,
+                        cudaStream_t s) {
   const int warps = B * P;
   k_corr_lookup<<<ceil_div(warps * 32, 256), 256, 0, s>>>(vol[0], vol[1], vol[2], vol[3], B, P, H8, W8, lh[0], lw[0],
                                                           lpitch[0], lh[1], lw[1], lpitch[1], lh[2], lw[2], lpitch[2],
-                                                          lh[3], lw[3], lpitch[3], d_coords, lookup_out, 384);
+                                                          lh[3], lw[3], lpitch[3], d_coords, dst, dst_ld, dst_wp,
+                                                          dst_pad, dst_img_rows);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }

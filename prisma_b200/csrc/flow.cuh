@@ -20,6 +20,9 @@ class FlowCorr {
   int set_fmaps(const float* fmap1_nchw, const float* fmap2_nchw);  // host fp32 [B][256][h8][w8]
   int build(cudaStream_t s);                                        // K13 + K14
   int lookup(const float* d_coords, cudaStream_t s);                // K15: coords device fp32 [B][2][h8][w8]
+  int lookup_to(const float* d_coords, __half* dst, int dst_ld, int dst_wp, int dst_pad, int dst_img_rows,
+                cudaStream_t s);                                    // same, into a zero-bordered fp16 map
+  int set_fmaps_device(const __half* f1, const __half* f2, cudaStream_t s);  // device fp16 [B][P][C] (engine path)
   int lookup_host(const float* coords, float* out_nchw, int iters, float* ms);
   int time_build(int iters, float* ms);
   int read_level(int level, int b, int row0, int nrows, float* out);

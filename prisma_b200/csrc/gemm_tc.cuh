@@ -31,6 +31,7 @@ enum RowMap : int {
   ROW_LINEAR = 0,   // dst row = m                                   (valid: m < M)
   ROW_PADDED = 1,   // m indexes a zero-bordered [Hp][Wp] image; only interior pixels are stored (borders stay zero)
   ROW_TOK2PAD = 2,  // m = y*W + x (dense tokens)  -> dst row (y+1)*out_wp + x+1
+  ROW_PAD2TOK = 5,  // m indexes a zero-bordered image; interior pixel (y,x) -> dense dst row img*H*W + y*W + x
   ROW_TOKSKIP = 4,  // m = b*P + p (patch tokens of image b) -> dst row b*(P+1) + 1 + p  (skips the cls rows; in_w = P)
   ROW_SHUFFLE = 3,  // ConvTranspose k == s: m = y*W + x, n = (dy*s+dx)*cout + co -> dst row (y*s+dy+1)*out_wp + x*s+dx+1
 };
@@ -39,7 +40,7 @@ struct GemmEpilogue {
   float alpha = 1.0f;            // accumulator scale (e.g. 1/sqrt(C) of the RAFT correlation), applied first
   const float* bias = nullptr;   // [N]
   const float* gamma = nullptr;  // [N]  LayerScale
-  int act = 0;                   // 0 none, 1 exact-erf GELU, 2 ReLU
+  int act = 0;                   // 0 none, 1 exact-erf GELU, 2 ReLU, 3 sigmoid, 4 tanh
   const float* res_f32 = nullptr;  // + residual (fp32), indexed by dst row
   int res_f32_ld = 0;
   const __half* res_a = nullptr;  // + residual (fp16), indexed by dst row
@@ -59,6 +60,8 @@ struct GemmEpilogue {
   int out_wp = 0;    // destination padded width
   int out_img_rows = 0;  // destination rows per image
   int sub = 1;       // ROW_PADDED: keep every sub-th pixel (stride-2 conv evaluated at stride 1)
+  int pad = 1;       // ROW_PADDED / ROW_PAD2TOK: border width of the input geometry; out_pad: of the destination
+  int out_pad = 1;
   int shuf_s = 1;
   int shuf_cout = 0;
   // fused DPT output head (dpt.py:96-100): depth = relu(head_b + sum_j head_w[j] * relu(acc[j] + bias[j])), N == 32,
@@ -90,6 +93,7 @@ struct GemmCfg {
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -121,6 +125,12 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   } else if (ep.act == 2) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
+  } else if (ep.act == 3) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i].x = sigmoid_f(v[i].x); v[i].y = sigmoid_f(v[i].y); v[i].z = sigmoid_f(v[i].z); v[i].w = sigmoid_f(v[i].w); }
+  } else if (ep.act == 4) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i].x = tanhf(v[i].x); v[i].y = tanhf(v[i].y); v[i].z = tanhf(v[i].z); v[i].w = tanhf(v[i].w); }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) { v[i].x *= gamma.x; v[i].y *= gamma.y; v[i].z *= gamma.z; v[i].w *= gamma.w; }
@@ -276,14 +286,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int valid = m < args.M;
       int drow = m;
       int ty = 0, tx = 0, img_base = 0;  // token coordinates / image base row for ROW_SHUFFLE
-      if (ep.row_map == ROW_PADDED) {
+      if (ep.row_map == ROW_PADDED || ep.row_map == ROW_PAD2TOK) {
         int img = 0, r = m;
         if (ep.img_rows > 0) { img = m / ep.img_rows; r = m - img * ep.img_rows; }
         const int y = r / ep.in_w, x = r - y * ep.in_w;
-        valid = valid && y >= 1 && y <= ep.in_h - 2 && x >= 1 && x <= ep.in_w - 2;
-        if (ep.sub > 1) {
-          valid = valid && ((y - 1) % ep.sub == 0) && ((x - 1) % ep.sub == 0);
-          drow = img * ep.out_img_rows + ((y - 1) / ep.sub + 1) * ep.out_wp + (x - 1) / ep.sub + 1;
+        const int pd = ep.pad;
+        valid = valid && y >= pd && y < ep.in_h - pd && x >= pd && x < ep.in_w - pd;
+        if (ep.row_map == ROW_PAD2TOK) {
+          const int ho = (ep.in_h - 2 * pd + ep.sub - 1) / ep.sub, wo = (ep.in_w - 2 * pd + ep.sub - 1) / ep.sub;
+          valid = valid && ((y - pd) % ep.sub == 0) && ((x - pd) % ep.sub == 0);
+          drow = img * (ep.out_img_rows > 0 ? ep.out_img_rows : ho * wo) + ((y - pd) / ep.sub) * wo + (x - pd) / ep.sub;
+        } else if (ep.sub > 1 || ep.out_wp > 0) {
+          // destination geometry differs from the source one (stride-2 sub-sampling and / or another border width)
+          valid = valid && ((y - pd) % ep.sub == 0) && ((x - pd) % ep.sub == 0);
+          drow = img * ep.out_img_rows + ((y - pd) / ep.sub + ep.out_pad) * ep.out_wp + (x - pd) / ep.sub + ep.out_pad;
         }
       } else if (ep.row_map == ROW_TOKSKIP) {
         drow = m + m / ep.in_w + 1;
@@ -292,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int img = m / per, r = m - img * per;
         ty = r / ep.in_w; tx = r - ty * ep.in_w;
         img_base = img * ep.out_img_rows;
-        drow = img_base + (ty + 1) * ep.out_wp + tx + 1;
+        drow = img_base + (ty + ep.out_pad) * ep.out_wp + tx + ep.out_pad;
       }
       // row mapping of the 8 rows this lane stores in the coalesced phase (constant over the tile's chunks)
       int dr8[8], ty8[8], tx8[8], ib8[8];
@@ -325,8 +341,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               acc = fmaf(fmaxf(__uint_as_float(r[j]) + __ldg(ep.bias + j), 0.f), __ldg(ep.head_w + j), acc);
             int img = 0, rpix = m;
             if (ep.img_rows > 0) { img = m / ep.img_rows; rpix = m - img * ep.img_rows; }
-            const int y = rpix / ep.in_w, x = rpix - y * ep.in_w;
-            ep.head_out[((size_t)img * (ep.in_h - 2) + (y - 1)) * (ep.in_w - 2) + (x - 1)] = fmaxf(acc, 0.f);
+            const int y = rpix / ep.in_w, x = rpix - y * ep.in_w, pd = ep.pad;
+            ep.head_out[((size_t)img * (ep.in_h - 2 * pd) + (y - pd)) * (ep.in_w - 2 * pd) + (x - pd)] = fmaxf(acc, 0.f);
           }
           continue;
         }
@@ -357,7 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int drs[8];
 #pragma unroll
           for (int rr = 0; rr < 8; ++rr)
-            drs[rr] = ib8[rr] + (ty8[rr] * ep.shuf_s + sdy + 1) * ep.out_wp + tx8[rr] * ep.shuf_s + sdx + 1;
+            drs[rr] = ib8[rr] + (ty8[rr] * ep.shuf_s + sdy + ep.out_pad) * ep.out_wp + tx8[rr] * ep.shuf_s + sdx + ep.out_pad;
           epilogue_rows8(ep, v, drs, ncol_ok ? okrows : 0u, bias4, gamma4, col);
         } else {
           epilogue_rows8(ep, v, dr8, ncol_ok ? okrows : 0u, bias4, gamma4, col);

@@ -1,0 +1,357 @@
+// prisma_b200 -- RAFT band: the pointwise / gather kernels around the tcgen05 conv core
+// (instance norm, im2col of the 7x7 stem, cnet split, GRU gate algebra, coords update, convex up-sampling).
+// Reference: bands/raft/{extractor,update,raft}.py.  All feature maps are NHWC fp16 with a zero border.
+#include "raft_kernels.cuh"
+
+namespace prisma {
+
+// ------------------------------------------------------------------------------------------------
+// stem im2col: conv1 = Conv2d(3, 64, 7, stride 2, padding 3) (extractor.py:133) on the normalised CHW fp32 image
+// -> fp16 [B*Ho*Wo][192], k = c*49 + ky*7 + kx (zero padded 147..191).  Stride 2 is applied here, no wasted rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_im2col_stem(const float* __restrict__ x, int B, int H, int W, __half* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long pix = blockIdx.x;  // b*Ho*Wo + oy*Wo + ox
+  const int b = (int)(pix / ((long long)Ho * Wo));
+  const int r = (int)(pix - (long long)b * Ho * Wo);
+  const int oy = r / Wo, ox = r - oy * Wo;
+  const float* img = x + (size_t)b * 3 * H * W;
+  for (int k = threadIdx.x; k < 192; k += blockDim.x) {
+    float v = 0.f;
+    if (k < 147) {
+      const int c = k / 49, t = k - c * 49, ky = t / 7, kx = t - ky * 7;
+      const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[((size_t)c * H + iy) * W + ix];
+    }
+    out[(size_t)pix * 192 + k] = __float2half_rn(v);
+  }
+}
+int raft_im2col_stem(const float* x, int B, int H, int W, __half* out, cudaStream_t s) {
+  k_im2col_stem<<<(unsigned)((long long)B * (H / 2) * (W / 2)), 64, 0, s>>>(x, B, H, W, out);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// InstanceNorm2d (no affine, biased variance, eps 1e-5, per image & channel; extractor.py:28-32,129-130):
+// deterministic two-stage statistics over a dense fp32 [B][HW][C] conv output, then normalise + ReLU (+ skip) into
+// a zero-bordered NHWC fp16 map.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_in_partial(const float* __restrict__ x, int HW, int C, int rows_per_block, float* __restrict__ part) {
+  extern __shared__ float sh[];  // [groups][C][2]
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int groups = blockDim.x / C;
+  const int g = threadIdx.x / C, c = threadIdx.x - g * C;
+  const int r0 = blk * rows_per_block, r1 = min(HW, r0 + rows_per_block);
+  float s = 0.f, q = 0.f;
+  if (g < groups) {
+    const float* p = x + ((size_t)b * HW) * C + c;
+    for (int r = r0 + g; r < r1; r += groups) {
+      const float v = p[(size_t)r * C];
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    sh[(g * C + c) * 2] = s;
+    sh[(g * C + c) * 2 + 1] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float ss = 0.f, qq = 0.f;
+    for (int gg = 0; gg < groups; ++gg) { ss += sh[(gg * C + threadIdx.x) * 2]; qq += sh[(gg * C + threadIdx.x) * 2 + 1]; }
+    float* o = part + (((size_t)b * gridDim.x + blk) * C + threadIdx.x) * 2;
+    o[0] = ss;
+    o[1] = qq;
+  }
+}
+__global__ void k_in_final(const float* __restrict__ part, int nblk, int C, int HW, float eps, float* __restrict__ stats) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < nblk; ++k) {
+    const float* p = part + (((size_t)b * nblk + k) * C + c) * 2;
+    s += p[0];
+    q += p[1];
+  }
+  const double mean = s / HW;
+  const double var = fmax(q / HW - mean * mean, 0.0);
+  stats[((size_t)b * C + c) * 2] = (float)mean;
+  stats[((size_t)b * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+int instnorm_stats(const float* x, int B, int HW, int C, float* part, float* stats, cudaStream_t s) {
+  const int threads = C <= 64 ? 4 * C : 2 * C;
+  const int rows_per_block = 512;
+  const int nblk = ceil_div(HW, rows_per_block);
+  k_in_partial<<<dim3(nblk, B), threads, threads * 2 * sizeof(float), s>>>(x, HW, C, rows_per_block, part);
+  k_in_final<<<B, 128, 0, s>>>(part, nblk, C, HW, 1e-5f, stats);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int instnorm_partial_floats(int B, int HW, int C) { return B * ceil_div(HW, 512) * C * 2; }
+
+// out = relu( skip + relu(norm(x)) )   [skip optional: an fp16 padded map, or a raw fp32 dense map with its own stats]
+__global__ void k_in_apply(const float* __restrict__ x, const float* __restrict__ stats, int H, int W, int C,
+                           const __half* __restrict__ skip_map, const float* __restrict__ skip_raw,
+                           const float* __restrict__ skip_stats, __half* __restrict__ out, int pad) {
+  const int c4 = C >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_img = (long long)H * W * c4;
+  const int b = blockIdx.y;
+  if (idx >= per_img) return;
+  const int c = (int)(idx % c4) * 4;
+  const int px = (int)((idx / c4) % W), py = (int)(idx / ((long long)c4 * W));
+  const size_t dense = (((size_t)b * H + py) * W + px) * C + c;
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const size_t padded = (((size_t)b * Hp + py + pad) * Wp + px + pad) * C + c;
+  const float4 v = *reinterpret_cast<const float4*>(x + dense);
+  const float* st = stats + ((size_t)b * C + c) * 2;
+  float y[4] = {fmaxf((v.x - st[0]) * st[1], 0.f), fmaxf((v.y - st[2]) * st[3], 0.f), fmaxf((v.z - st[4]) * st[5], 0.f),
+                fmaxf((v.w - st[6]) * st[7], 0.f)};
+  if (skip_map) {
+    const uint2 r = *reinterpret_cast<const uint2*>(skip_map + padded);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 bb = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    y[0] = fmaxf(y[0] + a.x, 0.f); y[1] = fmaxf(y[1] + a.y, 0.f); y[2] = fmaxf(y[2] + bb.x, 0.f); y[3] = fmaxf(y[3] + bb.y, 0.f);
+  } else if (skip_raw) {
+    const float4 r = *reinterpret_cast<const float4*>(skip_raw + dense);
+    const float* s2 = skip_stats + ((size_t)b * C + c) * 2;
+    y[0] = fmaxf(y[0] + (r.x - s2[0]) * s2[1], 0.f); y[1] = fmaxf(y[1] + (r.y - s2[2]) * s2[3], 0.f);
+    y[2] = fmaxf(y[2] + (r.z - s2[4]) * s2[5], 0.f); y[3] = fmaxf(y[3] + (r.w - s2[6]) * s2[7], 0.f);
+  }
+  *reinterpret_cast<uint2*>(out + padded) = make_uint2(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]));
+}
+int instnorm_apply(const float* x, const float* stats, int B, int H, int W, int C, const __half* skip_map,
+                   const float* skip_raw, const float* skip_stats, __half* out, int pad, cudaStream_t s) {
+  const long long per_img = (long long)H * W * (C / 4);
+  k_in_apply<<<dim3((unsigned)((per_img + 255) / 256), B), 256, 0, s>>>(x, stats, H, W, C, skip_map, skip_raw, skip_stats,
+                                                                       out, pad);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cnet output split (raft.py:113-116): net = tanh(cnet[:, :128]) -> h (fp32 master + fp16 operand), inp = relu(rest).
+// Destination: the GRU operand maps hx = [h | inp | motion] and rhx = [r*h | inp | motion], 384 channels, pad 2.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, int pad, float* __restrict__ h_master,
+                             __half* __restrict__ hx, __half* __restrict__ rhx) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W*256
+  const long long total = (long long)B * H * W * 256;
+  if (idx >= total) return;
+  const int c = (int)(idx & 255);
+  const long long p = idx >> 8;
+  const int b = (int)(p / ((long long)H * W));
+  const int r = (int)(p - (long long)b * H * W);
+  const int y = r / W, x = r - y * W;
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const size_t prow = ((size_t)b * Hp + y + pad) * Wp + x + pad;
+  const float v = cn[idx];
+  if (c < 128) {
+    const float t = tanhf(v);
+    h_master[prow * 128 + c] = t;
+    hx[prow * 384 + c] = __float2half_rn(t);
+  } else {
+    const __half i = __float2half_rn(fmaxf(v, 0.f));
+    hx[prow * 384 + c] = i;
+    rhx[prow * 384 + c] = i;
+  }
+}
+int raft_cnet_split(const float* cn, int B, int H, int W, int pad, float* h_master, __half* hx, __half* rhx,
+                    cudaStream_t s) {
+  const long long total = (long long)B * H * W * 256;
+  k_cnet_split<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(cn, B, H, W, pad, h_master, hx, rhx);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// convf1 = Conv2d(2, 128, 7, padding 3) + ReLU on the current flow (update.py:84,91): Cin = 2 is too thin for the
+// tensor core; direct conv, one thread per (pixel, 4 output channels), weights [128][2][7][7] fp32 read through L1.
+// Also refreshes the flow channels (382,383) of the GRU operand maps (update.py:97: cat([out, flow])).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_flow_conv7(const float* __restrict__ coords0, const float* __restrict__ coords1,
+                             const float* __restrict__ w, const float* __restrict__ bias, int B, int H, int W, int pad,
+                             __half* __restrict__ out128, __half* __restrict__ hx, __half* __restrict__ rhx) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W*32
+  const long long total = (long long)B * H * W * 32;
+  if (idx >= total) return;
+  const int cg = (int)(idx & 31) * 4;
+  const long long p = idx >> 5;
+  const int P = H * W;
+  const int b = (int)(p / P), r = (int)(p - (long long)b * P);
+  const int y = r / W, x = r - y * W;
+  const float* c0 = coords0 + (size_t)b * 2 * P;
+  const float* c1 = coords1 + (size_t)b * 2 * P;
+  float acc[4] = {bias[cg], bias[cg + 1], bias[cg + 2], bias[cg + 3]};
+  for (int ch = 0; ch < 2; ++ch)
+    for (int ky = 0; ky < 7; ++ky) {
+      const int yy = y + ky - 3;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < 7; ++kx) {
+        const int xx = x + kx - 3;
+        if (xx < 0 || xx >= W) continue;
+        const float f = c1[(size_t)ch * P + yy * W + xx] - c0[(size_t)ch * P + yy * W + xx];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(f, __ldg(w + (((size_t)(cg + j) * 2 + ch) * 7 + ky) * 7 + kx), acc[j]);
+      }
+    }
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const size_t prow = ((size_t)b * Hp + y + pad) * Wp + x + pad;
+  *reinterpret_cast<uint2*>(out128 + prow * 128 + cg) =
+      make_uint2(pack_half2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f)), pack_half2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f)));
+  (void)hx; (void)rhx;
+}
+// motion features = cat([conv_out(126), flow(2)]) (update.py:97): the two flow channels of the GRU operand maps
+__global__ void k_flow_cols(const float* __restrict__ c0, const float* __restrict__ c1, int B, int H, int W, int pad,
+                            __half* __restrict__ hx, __half* __restrict__ rhx) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int P = H * W;
+  if (idx >= (long long)B * P) return;
+  const int b = (int)(idx / P), r = (int)(idx - (long long)b * P);
+  const int y = r / W, x = r - y * W;
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const size_t prow = ((size_t)b * Hp + y + pad) * Wp + x + pad;
+  const float* a0 = c0 + (size_t)b * 2 * P;
+  const float* a1 = c1 + (size_t)b * 2 * P;
+  const uint32_t fl = pack_half2(a1[r] - a0[r], a1[(size_t)P + r] - a0[(size_t)P + r]);
+  *reinterpret_cast<uint32_t*>(hx + prow * 384 + 382) = fl;
+  *reinterpret_cast<uint32_t*>(rhx + prow * 384 + 382) = fl;
+}
+int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pad, __half* hx, __half* rhx, cudaStream_t s) {
+  k_flow_cols<<<(unsigned)(((long long)B * H * W + 255) / 256), 256, 0, s>>>(c0, c1, B, H, W, pad, hx, rhx);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int raft_flow_conv7(const float* coords0, const float* coords1, const float* w, const float* bias, int B, int H, int W,
+                    int pad, __half* out128, __half* hx, __half* rhx, cudaStream_t s) {
+  const long long total = (long long)B * H * W * 32;
+  k_flow_conv7<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(coords0, coords1, w, bias, B, H, W, pad, out128, hx, rhx);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SepConvGRU gate algebra (update.py:45-60) on padded rows:  rh = r * h ;  h = (1 - z) * h + z * q
+// zr: fp16 [rows][256] = [z | r] (sigmoid applied in the conv epilogue), q: fp16 [rows][128] (tanh applied).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gru_rh(const __half* __restrict__ zr, const float* __restrict__ h_master, __half* __restrict__ rhx,
+                         long long rows) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // rows * 32 (4 channels each)
+  if (idx >= rows * 32) return;
+  const long long row = idx >> 5;
+  const int c = (int)(idx & 31) * 4;
+  const uint2 r = *reinterpret_cast<const uint2*>(zr + row * 256 + 128 + c);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  const float4 h = *reinterpret_cast<const float4*>(h_master + row * 128 + c);
+  *reinterpret_cast<uint2*>(rhx + row * 384 + c) = make_uint2(pack_half2(a.x * h.x, a.y * h.y), pack_half2(b.x * h.z, b.y * h.w));
+}
+__global__ void k_gru_update(const __half* __restrict__ zr, const __half* __restrict__ q, float* __restrict__ h_master,
+                             __half* __restrict__ hx, long long rows) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * 32) return;
+  const long long row = idx >> 5;
+  const int c = (int)(idx & 31) * 4;
+  const uint2 zz = *reinterpret_cast<const uint2*>(zr + row * 256 + c);
+  const uint2 qq = *reinterpret_cast<const uint2*>(q + row * 128 + c);
+  const float2 z0 = __half22float2(*reinterpret_cast<const __half2*>(&zz.x)), z1 = __half22float2(*reinterpret_cast<const __half2*>(&zz.y));
+  const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&qq.x)), q1 = __half22float2(*reinterpret_cast<const __half2*>(&qq.y));
+  float4 h = *reinterpret_cast<float4*>(h_master + row * 128 + c);
+  h.x = (1.f - z0.x) * h.x + z0.x * q0.x;
+  h.y = (1.f - z0.y) * h.y + z0.y * q0.y;
+  h.z = (1.f - z1.x) * h.z + z1.x * q1.x;
+  h.w = (1.f - z1.y) * h.w + z1.y * q1.y;
+  *reinterpret_cast<float4*>(h_master + row * 128 + c) = h;
+  *reinterpret_cast<uint2*>(hx + row * 384 + c) = make_uint2(pack_half2(h.x, h.y), pack_half2(h.z, h.w));
+}
+int raft_gru_rh(const __half* zr, const float* h_master, __half* rhx, long long rows, cudaStream_t s) {
+  k_gru_rh<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(zr, h_master, rhx, rows);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int raft_gru_update(const __half* zr, const __half* q, float* h_master, __half* hx, long long rows, cudaStream_t s) {
+  k_gru_update<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(zr, q, h_master, hx, rows);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// coords1 += delta_flow (raft.py:133); delta: fp32 padded rows [rows][4] (cols 0,1 used)
+__global__ void k_coords_update(const float* __restrict__ delta, int B, int H, int W, int pad, float* __restrict__ coords1) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int P = H * W;
+  if (idx >= (long long)B * P) return;
+  const int b = (int)(idx / P), r = (int)(idx - (long long)b * P);
+  const int y = r / W, x = r - y * W;
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const size_t prow = ((size_t)b * Hp + y + pad) * Wp + x + pad;
+  coords1[(size_t)b * 2 * P + r] += delta[prow * 4];
+  coords1[(size_t)b * 2 * P + P + r] += delta[prow * 4 + 1];
+}
+int raft_coords_update(const float* delta, int B, int H, int W, int pad, float* coords1, cudaStream_t s) {
+  k_coords_update<<<(unsigned)(((long long)B * H * W + 255) / 256), 256, 0, s>>>(delta, B, H, W, pad, coords1);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+__global__ void k_coords_init(float* __restrict__ c0, float* __restrict__ c1, int B, int H, int W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int P = H * W;
+  if (idx >= (long long)B * P) return;
+  const int b = (int)(idx / P), r = (int)(idx - (long long)b * P);
+  const float x = (float)(r % W), y = (float)(r / W);
+  c0[(size_t)b * 2 * P + r] = x; c0[(size_t)b * 2 * P + P + r] = y;
+  c1[(size_t)b * 2 * P + r] = x; c1[(size_t)b * 2 * P + P + r] = y;
+}
+int raft_coords_init(float* c0, float* c1, int B, int H, int W, cudaStream_t s) {
+  k_coords_init<<<(unsigned)(((long long)B * H * W + 255) / 256), 256, 0, s>>>(c0, c1, B, H, W);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Convex up-sampling (raft.py:73-84) fused with InputPadder.unpad and the HWC permute of flow_raft.py:58-61:
+// out[b][Y][X][ch] for the un-padded Hs x Ws image; Y = 8y+a - pad_top, X = 8x+b - pad_left.
+// mask: fp32 padded rows [rows][576] (already scaled by 0.25), channel k*64 + a*8 + b, softmax over k = 0..8;
+// neighbourhood = unfold(8*flow, 3x3, padding 1) (zero outside).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_convex_upsample(const float* __restrict__ mask, const float* __restrict__ c0,
+                                  const float* __restrict__ c1, int B, int H, int W, int pad, int Hs, int Ws, int pad_top,
+                                  int pad_left, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x;  // coarse pixel
+  const int y = r / W, x = r - y * W;
+  const int sub = threadIdx.x;  // 0..63: a*8 + bcol
+  const int P = H * W;
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const float* m = mask + (((size_t)b * Hp + y + pad) * Wp + x + pad) * 576;
+  float w[9];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { w[k] = m[k * 64 + sub]; mx = fmaxf(mx, w[k]); }
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { w[k] = expf(w[k] - mx); den += w[k]; }
+  float fx = 0.f, fy = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const int rr = yy * W + xx;
+      const float wk = w[k] / den;
+      fx += wk * 8.f * (c1[(size_t)b * 2 * P + rr] - c0[(size_t)b * 2 * P + rr]);
+      fy += wk * 8.f * (c1[(size_t)b * 2 * P + P + rr] - c0[(size_t)b * 2 * P + P + rr]);
+    }
+  }
+  const int Y = 8 * y + (sub >> 3) - pad_top, X = 8 * x + (sub & 7) - pad_left;
+  if (Y >= 0 && Y < Hs && X >= 0 && X < Ws) {
+    float* o = out + (((size_t)b * Hs + Y) * Ws + X) * 2;
+    o[0] = fx;
+    o[1] = fy;
+  }
+}
+int raft_convex_upsample(const float* mask, const float* c0, const float* c1, int B, int H, int W, int pad, int Hs, int Ws,
+                         int pad_top, int pad_left, float* out, cudaStream_t s) {
+  k_convex_upsample<<<dim3(H * W, B), 64, 0, s>>>(mask, c0, c1, B, H, W, pad, Hs, Ws, pad_top, pad_left, out);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace prisma

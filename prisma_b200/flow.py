@@ -1,0 +1,72 @@
+"""Host-side mirror of the reference RAFT band interface (bands/flow_raft.py) on top of the C ABI.
+
+`RaftFlowEngine(state_dict)` ≙ `init_model(args)` (:38-48); `infer_pair(prev, curr)` ≙ the loop body of
+`process_video` (:100-113): resize x`scale`, `infer(args, image1, image2)` with image1=[prev,curr], image2=[curr,prev]
+(forward and backward flow in one pass), `process_flow` of both.  All arithmetic happens in libprisma_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import PrismaError, check, fptr, lib, u8ptr, c_i64_p
+
+
+class RaftFlowEngine:
+    def __init__(self, state_dict=None, device=0, iterations=20, scale=0.75):
+        self._h = C.c_void_p()
+        self.iterations, self.scale = iterations, scale  # defaults of flow_raft.py:32,183
+        check(lib().prisma_flow_create(device, C.byref(self._h)))
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    def load_state_dict(self, state_dict):
+        l = lib()
+        for name, t in state_dict.items():
+            a = t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+            if a.dtype.kind != "f":
+                continue  # num_batches_tracked
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            shape = (C.c_int64 * max(a.ndim, 1))(*(a.shape if a.ndim else (1,)))
+            check(l.prisma_flow_load_tensor(self._h, name.encode(), fptr(a), C.cast(shape, c_i64_p), max(a.ndim, 1)))
+        check(l.prisma_flow_finalize(self._h))
+
+    def out_size(self, h, w):
+        return int(np.rint(h * self.scale)), int(np.rint(w * self.scale))
+
+    def infer_pair(self, prev, curr, want_rgb=False):
+        """prev/curr: HxWx3 u8 RGB -> dict(fwd, bwd [hs,ws,2] f32, max_fwd, max_bwd[, fwd_rgb, bwd_rgb], ms)."""
+        prev, curr = np.ascontiguousarray(prev), np.ascontiguousarray(curr)
+        if prev.shape != curr.shape or prev.dtype != np.uint8 or prev.ndim != 3:
+            raise PrismaError("expected two HxWx3 uint8 RGB frames of the same size")
+        h, w = prev.shape[:2]
+        hs, ws = self.out_size(h, w)
+        fwd = np.empty((hs, ws, 2), np.float32)
+        bwd = np.empty((hs, ws, 2), np.float32)
+        frgb = np.empty((hs, ws, 3), np.uint8) if want_rgb else None
+        brgb = np.empty((hs, ws, 3), np.uint8) if want_rgb else None
+        mf, mb, ms = C.c_float(), C.c_float(), C.c_float()
+        check(lib().prisma_flow_infer(self._h, u8ptr(prev), u8ptr(curr), h, w, self.scale, self.iterations, fptr(fwd),
+                                      fptr(bwd), u8ptr(frgb), u8ptr(brgb), C.byref(mf), C.byref(mb), C.byref(ms)))
+        return dict(fwd=fwd, bwd=bwd, max_fwd=mf.value, max_bwd=mb.value, fwd_rgb=frgb, bwd_rgb=brgb, ms=ms.value)
+
+    def read_tap(self, name, shape):
+        out = np.empty(int(np.prod(shape)), np.float32)
+        n = check(lib().prisma_flow_read_tap(self._h, name.encode(), fptr(out), out.size))
+        assert n == out.size, (name, n, out.size)
+        return out.reshape(shape)
+
+    def work(self, h, w):
+        out = (C.c_double * 4)()
+        check(lib().prisma_flow_work(self._h, h, w, self.scale, self.iterations, out))
+        return dict(flop=out[0], launches=int(out[1]), hs=int(out[2]), ws=int(out[3]))
+
+    def close(self):
+        if self._h:
+            lib().prisma_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
