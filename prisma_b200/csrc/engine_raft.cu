@@ -372,7 +372,7 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
   }
   // ---- cnet (batch norm folded) -> tanh / relu split into the GRU operand maps
   PRISMA_TRY(build_encoder(w.cnet, false, b.stem_cols, &c128));
-  RMap hx, rhx, corrf, c1, c2, f1, zr, q, fh, delta, mk, mask;
+  RMap hx, rhx, corrf, c1, c2, f1, fh, mk;
   PRISMA_TRY(new_map(&hx, B, H8, W8, 384, 2));
   PRISMA_TRY(new_map(&rhx, B, H8, W8, 384, 2));
   PRISMA_TRY(r_alloc(plan_allocs, &b.h_master, (size_t)hx.rows() * 128));
@@ -389,8 +389,9 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
   PRISMA_TRY(new_map(&c1, B, H8, W8, 256, 2));
   PRISMA_TRY(new_map(&c2, B, H8, W8, 256, 2));   // [convc2 out (192) | convf2 out (64)]
   PRISMA_TRY(new_map(&f1, B, H8, W8, 128, 2));
-  PRISMA_TRY(new_map(&zr, B, H8, W8, 256, 2));
-  PRISMA_TRY(new_map(&q, B, H8, W8, 128, 2));
+  float *zr_f = nullptr, *q_f = nullptr;  // gates in fp32, padded-row layout of the pad-2 maps
+  PRISMA_TRY(r_alloc(plan_allocs, &zr_f, (size_t)hx.rows() * 256));
+  PRISMA_TRY(r_alloc(plan_allocs, &q_f, (size_t)hx.rows() * 128));
   PRISMA_TRY(new_map(&fh, B, H8, W8, 256, 2));
   PRISMA_TRY(new_map(&mk, B, H8, W8, 256, 2));
   PRISMA_TRY(r_alloc(plan_allocs, &b.delta, (size_t)hx.rows() * 4));
@@ -421,13 +422,13 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
       add("flow_cols", [=](cudaStream_t s) { return raft_flow_cols(c0, c1p, 2, h8, w8, 2, hxp, rhp, s); });
     }
     for (int pass = 0; pass < 2; ++pass) {  // SepConvGRU horizontal then vertical (update.py:45-60)
-      { GemmEpilogue ep; ep.act = 3; ep.out_f16 = zr.p; ep.out_f16_ld = 256;
+      { GemmEpilogue ep; ep.act = 3; ep.out_f32 = zr_f; ep.out_f32_ld = 256;
         PRISMA_TRY(add_conv("gru_zr", hx, 0, w.zr[pass], ep, 1)); }
-      { const __half* z = zr.p; const float* hm = b.h_master; __half* rhp = rhx.p;
+      { const float* z = zr_f; const float* hm = b.h_master; __half* rhp = rhx.p;
         add("gru_rh", [=](cudaStream_t s) { return raft_gru_rh(z, hm, rhp, rows, s); }); }
-      { GemmEpilogue ep; ep.act = 4; ep.out_f16 = q.p; ep.out_f16_ld = 128;
+      { GemmEpilogue ep; ep.act = 4; ep.out_f32 = q_f; ep.out_f32_ld = 128;
         PRISMA_TRY(add_conv("gru_q", rhx, 0, w.q[pass], ep, 1)); }
-      { const __half* z = zr.p; const __half* qq = q.p; float* hm = b.h_master; __half* hxp = hx.p;
+      { const float* z = zr_f; const float* qq = q_f; float* hm = b.h_master; __half* hxp = hx.p;
         add("gru_update", [=](cudaStream_t s) { return raft_gru_update(z, qq, hm, hxp, rows, s); }); }
     }
     { GemmEpilogue ep; ep.act = 2; ep.out_f16 = fh.p; ep.out_f16_ld = 256;            // flow head
@@ -452,7 +453,7 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
   // ---- up-sampling mask (last iteration only) + convex up-sampling + unpad + HWC
   { GemmEpilogue ep; ep.act = 2; ep.out_f16 = mk.p; ep.out_f16_ld = 256;
     PRISMA_TRY(add_conv("mask_head1", hx, 0, w.mk1, ep, 1)); }
-  { GemmEpilogue ep; ep.alpha = 0.25f; ep.out_f32 = b.mask; ep.out_f32_ld = 576;
+  { GemmEpilogue ep; ep.out_f32 = b.mask; ep.out_f32_ld = 576;  // the 0.25 is folded (exactly) into the fp16 weights and the bias
     PRISMA_TRY(add_conv("mask_head2", mk, 0, w.mk2, ep, 1)); }
   {
     const float* m = b.mask; const float* c0 = b.coords0; const float* c1p = b.coords1; float* up = b.flow_up;

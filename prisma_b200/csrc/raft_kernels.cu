@@ -233,42 +233,39 @@ int raft_flow_conv7(const float* coords0, const float* coords1, const float* w, 
 // SepConvGRU gate algebra (update.py:45-60) on padded rows:  rh = r * h ;  h = (1 - z) * h + z * q
 // zr: fp16 [rows][256] = [z | r] (sigmoid applied in the conv epilogue), q: fp16 [rows][128] (tanh applied).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_gru_rh(const __half* __restrict__ zr, const float* __restrict__ h_master, __half* __restrict__ rhx,
+// The gates stay fp32 end to end (conv epilogue -> these kernels): only conv OPERANDS are fp16 in the recurrence.
+__global__ void k_gru_rh(const float* __restrict__ zr, const float* __restrict__ h_master, __half* __restrict__ rhx,
                          long long rows) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // rows * 32 (4 channels each)
   if (idx >= rows * 32) return;
   const long long row = idx >> 5;
   const int c = (int)(idx & 31) * 4;
-  const uint2 r = *reinterpret_cast<const uint2*>(zr + row * 256 + 128 + c);
-  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
-  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  const float4 r = *reinterpret_cast<const float4*>(zr + row * 256 + 128 + c);
   const float4 h = *reinterpret_cast<const float4*>(h_master + row * 128 + c);
-  *reinterpret_cast<uint2*>(rhx + row * 384 + c) = make_uint2(pack_half2(a.x * h.x, a.y * h.y), pack_half2(b.x * h.z, b.y * h.w));
+  *reinterpret_cast<uint2*>(rhx + row * 384 + c) = make_uint2(pack_half2(r.x * h.x, r.y * h.y), pack_half2(r.z * h.z, r.w * h.w));
 }
-__global__ void k_gru_update(const __half* __restrict__ zr, const __half* __restrict__ q, float* __restrict__ h_master,
+__global__ void k_gru_update(const float* __restrict__ zr, const float* __restrict__ q, float* __restrict__ h_master,
                              __half* __restrict__ hx, long long rows) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * 32) return;
   const long long row = idx >> 5;
   const int c = (int)(idx & 31) * 4;
-  const uint2 zz = *reinterpret_cast<const uint2*>(zr + row * 256 + c);
-  const uint2 qq = *reinterpret_cast<const uint2*>(q + row * 128 + c);
-  const float2 z0 = __half22float2(*reinterpret_cast<const __half2*>(&zz.x)), z1 = __half22float2(*reinterpret_cast<const __half2*>(&zz.y));
-  const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&qq.x)), q1 = __half22float2(*reinterpret_cast<const __half2*>(&qq.y));
+  const float4 z = *reinterpret_cast<const float4*>(zr + row * 256 + c);
+  const float4 qq = *reinterpret_cast<const float4*>(q + row * 128 + c);
   float4 h = *reinterpret_cast<float4*>(h_master + row * 128 + c);
-  h.x = (1.f - z0.x) * h.x + z0.x * q0.x;
-  h.y = (1.f - z0.y) * h.y + z0.y * q0.y;
-  h.z = (1.f - z1.x) * h.z + z1.x * q1.x;
-  h.w = (1.f - z1.y) * h.w + z1.y * q1.y;
+  h.x = (1.f - z.x) * h.x + z.x * qq.x;
+  h.y = (1.f - z.y) * h.y + z.y * qq.y;
+  h.z = (1.f - z.z) * h.z + z.z * qq.z;
+  h.w = (1.f - z.w) * h.w + z.w * qq.w;
   *reinterpret_cast<float4*>(h_master + row * 128 + c) = h;
   *reinterpret_cast<uint2*>(hx + row * 384 + c) = make_uint2(pack_half2(h.x, h.y), pack_half2(h.z, h.w));
 }
-int raft_gru_rh(const __half* zr, const float* h_master, __half* rhx, long long rows, cudaStream_t s) {
+int raft_gru_rh(const float* zr, const float* h_master, __half* rhx, long long rows, cudaStream_t s) {
   k_gru_rh<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(zr, h_master, rhx, rows);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int raft_gru_update(const __half* zr, const __half* q, float* h_master, __half* hx, long long rows, cudaStream_t s) {
+int raft_gru_update(const float* zr, const float* q, float* h_master, __half* hx, long long rows, cudaStream_t s) {
   k_gru_update<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(zr, q, h_master, hx, rows);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
