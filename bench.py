@@ -135,6 +135,51 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def raft_extras(device, peaks):
+    """Second workload (BASELINE configs[2]): flow_raft on synthetic 1080p pairs, 12 GRU iterations, forward+backward
+    flow per pass, plus the correlation-volume build (HBM-bound) against the measured copy bandwidth."""
+    import ctypes as C
+    from prisma_b200._lib import check, fptr, lib
+    from prisma_b200.flow import RaftFlowEngine
+    from prisma_b200.seeded_weights import make_raft_weights
+    from oracle.frames import synthetic_frame
+    eng = RaftFlowEngine(make_raft_weights(0), device=device, iterations=12, scale=0.75)
+    f = [synthetic_frame(1080, 1920, t) for t in range(2)]
+    for _ in range(3):
+        eng.infer_pair(f[0], f[1])
+    n = 8
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for i in range(n):
+        r = eng.infer_pair(f[i % 2], f[(i + 1) % 2], want_rgb=True)
+        dev_ms += r["ms"]
+    e2e_s = time.perf_counter() - t0
+    w = eng.work(1080, 1920)
+    eng.close()
+    # correlation pyramid build alone (K13+K14), fwd+bwd, P = 18360
+    l = lib()
+    h = C.c_void_p()
+    rng = np.random.default_rng(0)
+    fm = rng.standard_normal((2, 256, 102, 180), dtype=np.float32)
+    check(l.prisma_flowcorr_create(device, 2, 102, 180, C.byref(h)))
+    check(l.prisma_flowcorr_set_fmaps(h, fptr(fm), fptr(np.ascontiguousarray(fm[::-1]))))
+    ms = C.c_float()
+    check(l.prisma_flowcorr_build(h, 10, C.byref(ms)))
+    work = (C.c_double * 2)()
+    check(l.prisma_flowcorr_work(h, work))
+    l.prisma_engine_destroy(h)
+    gbs = work[1] / (ms.value * 1e-3) / 1e9
+    return {
+        "flow_raft_1080p": {"workload": "synthetic 1080p pairs, flow_raft 12 GRU iterations, fwd+bwd per pass (BASELINE configs[2])",
+                            "frame_steps_per_s_device": n / (dev_ms * 1e-3), "frame_steps_per_s_e2e": n / e2e_s,
+                            "ms_per_pass_device": dev_ms / n, "algorithmic_gflop_per_pass": w["flop"] / 1e9,
+                            "tflops": w["flop"] / (dev_ms / n * 1e-3) / 1e12, "launches_per_pass": w["launches"]},
+        "raft_corr_build": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                            "ms": ms.value, "algorithmic_bytes": work[1], "traffic": None, "peak_source": peaks["src"],
+                            "note": "4-level fp32 pyramid written once (levels 1-3 by linearity: GEMMs against pooled features)"},
+    }
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     from prisma_b200.depth import DepthAnythingEngine
@@ -213,6 +258,8 @@ def run_b200(args, rank, local_rank, world):
                          "attention_tflops": att_tf, "head_tflops": head_tf,
                          "frame_flop": (work["linear_flop"] + work["attention_flop"] + work["head_flop"]) / BATCH},
         }
+        if world == 1:
+            out["extra"] = raft_extras(local_rank, peaks)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             fps, dt = cpu_baseline_frames(2, cores)

@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 from bands.common.meta import add_band, create_metadata, is_video, set_default_band, write_metadata  # noqa: E402
 from bands.common.media import VideoReader, open_rgb  # noqa: E402
 
-ACCELERATED = {"depth_anything"}  # flow_raft / mask_mmdet / depth_midas: next rows of SURVEY.md section 8
+ACCELERATED = {"depth_anything", "flow_raft"}  # mask_mmdet / depth_midas: next rows of SURVEY.md section 8
 
 
 def run(band, folder, extra=()):
@@ -58,7 +58,12 @@ def main(argv=None):
     if "depth_anything" in bands:
         set_default_band(folder, "depth", "depth_anything")
     if a.flow:
-        run(a.flow, folder)
+        flows = ["flow_gmflow", "flow_raft"] if a.flow == "all" else [a.flow]
+        for fb in flows:
+            run(fb, folder, ["--backwards"] + (["--seeded-weights"] if a.seeded_weights else []))
+        if "flow_raft" in flows:
+            set_default_band(folder, "flow", "flow_raft")
+            set_default_band(folder, "flow_bwd", "flow_raft_bwd")
 
 
 if __name__ == "__main__":

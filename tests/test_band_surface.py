@@ -25,6 +25,14 @@ def test_metadata_contract(tmp_path):
     assert meta.is_video("a.mp4") and not meta.is_video("a.png")
 
 
+def test_flow_band_cli_matches_reference_flags():
+    sys.path.insert(0, ROOT)
+    from bands import flow_raft as band
+    a = band.build_parser().parse_args(["-i", "x", "-b", "--iterations", "12", "--scale", "0.5", "-m", "w.pth"])
+    assert (a.backwards, a.iterations, a.scale, a.model) == (True, 12, 0.5, "w.pth")
+    assert band.BAND == "flow_raft" and band.ITERATIONS == 20 and band.MODEL == "models/raft-sintel.pth"
+
+
 def test_band_cli_matches_reference_flags():
     sys.path.insert(0, ROOT)
     from bands import depth_anything as band
@@ -42,7 +50,8 @@ def test_process_runs_band_into_prisma_folder(tmp_path):
     for t in range(3):
         w.write(synthetic_frame(240, 320, t)[..., ::-1].copy())
     w.release()
-    rc = subprocess.call([sys.executable, os.path.join(ROOT, "process.py"), "-i", src, "--encoder", "vits", "--seeded-weights"])
+    rc = subprocess.call([sys.executable, os.path.join(ROOT, "process.py"), "-i", src, "--encoder", "vits", "--seeded-weights",
+                          "-f", "flow_raft"])
     assert rc == 0
     folder = str(tmp_path / "clip")
     meta = json.load(open(os.path.join(folder, "metadata.json")))
@@ -53,3 +62,8 @@ def test_process_runs_band_into_prisma_folder(tmp_path):
     maxs = [float(l) for l in open(os.path.join(folder, "depth_anything_max.csv"))]
     assert len(mins) == 3 and all(b > a for a, b in zip(mins, maxs))
     assert meta["bands"]["depth"] == band and meta["width"] == 320 and meta["frames"] == 3
+    flow = meta["bands"]["flow_raft"]
+    assert flow == {"url": "flow_raft.mp4", "values": {"dist": {"type": "float", "url": "flow_raft.csv"}}}
+    dists = [float(l) for l in open(os.path.join(folder, "flow_raft.csv"))]
+    assert len(dists) == 3 and dists[-1] == 0.0 and all(d > 0 for d in dists[:2])
+    assert meta["bands"]["flow_raft_bwd"] == {"url": "flow_raft_bwd.mp4"} and meta["bands"]["flow"] == flow

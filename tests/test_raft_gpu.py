@@ -75,3 +75,40 @@ def test_raft_stages_and_flow(raft_engine):
     assert rep["delta_iter0"][0] <= 2e-2 * max(1.0, rep["delta_iter0"][1])
     # north_star tolerance on the flow floats: 1e-3 relative (to the largest displacement)
     assert rep["flow_fwd"][0] <= 1e-3 and rep["flow_bwd"][0] <= 1e-3, rep
+
+
+def test_raft_720p_matches_oracle(raft_engine):
+    """BASELINE frame size 720p (x0.75 -> 540x960, padded 544x960): CUDA vs the CPU oracle on the same resized frames."""
+    H, W = 720, 1280
+    f0, f1 = synthetic_frame(H, W, 0), synthetic_frame(H, W, 1)
+    out = raft_engine.infer_pair(f0, f1)
+    hs, ws = raft_engine.out_size(H, W)
+    rs = raft_engine.read_tap("resized", (2, hs, ws, 3)).astype(np.uint8)
+    _, lo, up = _oracle(f0, f1, rs[0], rs[1], 12)
+    fwd_ref = up[0].permute(1, 2, 0).numpy()
+    bwd_ref = up[1].permute(1, 2, 0).numpy()
+    r = (_rel(out["fwd"], fwd_ref), _rel(out["bwd"], bwd_ref))
+    print("720p raft: fwd", r[0], "bwd", r[1], "max|flow|", float(np.abs(fwd_ref).max()), "ms", out["ms"])
+    assert r[0][0] <= 1e-3 and r[1][0] <= 1e-3
+
+
+def test_raft_1080p_properties(raft_engine):
+    """BASELINE config-3 size (1080p x0.75, 12 iterations): size-independent properties.
+    (a) swapping the two frames swaps forward and backward flow bit for bit (the two directions are independent
+        batch entries of the same pass); (b) the pass is deterministic; (c) the HSV frame / max displacement agree
+        with the oracle's process_flow applied to OUR flow."""
+    H, W = 1080, 1920
+    f0, f1 = synthetic_frame(H, W, 0), synthetic_frame(H, W, 1)
+    a = raft_engine.infer_pair(f0, f1, want_rgb=True)
+    b = raft_engine.infer_pair(f1, f0)
+    assert a["fwd"].shape == (810, 1440, 2)
+    assert np.array_equal(a["fwd"], b["bwd"]) and np.array_equal(a["bwd"], b["fwd"])
+    c = raft_engine.infer_pair(f0, f1)
+    assert np.array_equal(a["fwd"], c["fwd"])
+    ref_rgb, ref_max = oraft.process_flow(a["fwd"])
+    assert np.float32(a["max_fwd"]) == np.float32(ref_max)
+    d = np.abs(a["fwd_rgb"].astype(int) - ref_rgb.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    w = raft_engine.work(H, W)
+    print("1080p raft pass: %.2f ms  (%.1f pairs/s, %.0f GFLOP algorithmic -> %.0f TFLOP/s), %d launches" %
+          (c["ms"], 1e3 / c["ms"], w["flop"] / 1e9, w["flop"] / c["ms"] / 1e9, w["launches"]))
