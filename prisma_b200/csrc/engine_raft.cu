@@ -504,7 +504,26 @@ int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, fl
   PRISMA_CUDA_OK(cudaMemcpyAsync(b.img + fb, curr, fb, cudaMemcpyHostToDevice, stream));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ms_out) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
-  if (graph_exec) PRISMA_CUDA_OK(cudaGraphLaunch(graph_exec, stream));
+  if (getenv("PRISMA_RAFT_PROFILE")) {  // per-step CUDA-event times, aggregated by step name (diagnostics)
+    std::vector<cudaEvent_t> ev(steps.size() + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], stream);
+    for (size_t i = 0; i < steps.size(); ++i) { PRISMA_TRY(steps[i].fn(stream)); cudaEventRecord(ev[i + 1], stream); }
+    PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+    std::map<std::string, std::pair<int, float>> agg;
+    float tot = 0;
+    for (size_t i = 0; i < steps.size(); ++i) {
+      float t = 0;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      agg[steps[i].name].first++; agg[steps[i].name].second += t; tot += t;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    std::vector<std::pair<float, std::string>> v;
+    for (auto& kv : agg) v.push_back({kv.second.second, kv.first + " x" + std::to_string(kv.second.first)});
+    std::sort(v.rbegin(), v.rend());
+    printf("RAFT step profile (%.3f ms total, ungraphed):\n", tot);
+    for (auto& x : v) printf("  %8.3f ms  %5.1f %%  %s\n", x.first, 100.f * x.first / tot, x.second.c_str());
+  } else if (graph_exec) PRISMA_CUDA_OK(cudaGraphLaunch(graph_exec, stream));
   else PRISMA_TRY(run_direct(stream));
   if (ms_out) cudaEventRecord(e1, stream);
   const size_t n = (size_t)Hs * Ws;
