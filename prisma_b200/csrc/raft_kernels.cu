@@ -168,37 +168,49 @@ int raft_cnet_split(const float* cn, int B, int H, int W, int pad, float* h_mast
 // tensor core; direct conv, one thread per (pixel, 4 output channels), weights [128][2][7][7] fp32 read through L1.
 // Also refreshes the flow channels (382,383) of the GRU operand maps (update.py:97: cat([out, flow])).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_flow_conv7(const float* __restrict__ coords0, const float* __restrict__ coords1,
-                             const float* __restrict__ w, const float* __restrict__ bias, int B, int H, int W, int pad,
-                             __half* __restrict__ out128, __half* __restrict__ hx, __half* __restrict__ rhx) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W*32
-  const long long total = (long long)B * H * W * 32;
-  if (idx >= total) return;
-  const int cg = (int)(idx & 31) * 4;
-  const long long p = idx >> 5;
+// Block = 128 threads (one per output channel) x FC_PIX pixels of one image row segment: the 98x128 weight matrix is
+// staged in shared memory once per block (k-major, so the 128 lanes read consecutive words), each pixel's 7x7x2 flow
+// patch is staged next to it and broadcast; 98 FMAs per (pixel, channel).
+constexpr int FC_PIX = 32;
+__global__ void __launch_bounds__(128) k_flow_conv7(const float* __restrict__ coords0, const float* __restrict__ coords1,
+                                                    const float* __restrict__ w, const float* __restrict__ bias, int B, int H,
+                                                    int W, int pad, __half* __restrict__ out128) {
+  extern __shared__ float fc_smem[];
+  float* sw = fc_smem;                                                  // [98][128]
+  float (*sp)[100] = reinterpret_cast<float (*)[100]>(fc_smem + 98 * 128);  // [FC_PIX][100]
   const int P = H * W;
-  const int b = (int)(p / P), r = (int)(p - (long long)b * P);
-  const int y = r / W, x = r - y * W;
+  const int tiles_per_img = (P + FC_PIX - 1) / FC_PIX;
+  const int b = blockIdx.x / tiles_per_img;
+  const int p0 = (blockIdx.x - b * tiles_per_img) * FC_PIX;
+  const int c = threadIdx.x;
+  for (int k = 0; k < 98; ++k) sw[k * 128 + c] = w[(size_t)c * 98 + k];  // [co][ch][ky][kx] -> [k][co]
   const float* c0 = coords0 + (size_t)b * 2 * P;
   const float* c1 = coords1 + (size_t)b * 2 * P;
-  float acc[4] = {bias[cg], bias[cg + 1], bias[cg + 2], bias[cg + 3]};
-  for (int ch = 0; ch < 2; ++ch)
-    for (int ky = 0; ky < 7; ++ky) {
-      const int yy = y + ky - 3;
-      if (yy < 0 || yy >= H) continue;
-      for (int kx = 0; kx < 7; ++kx) {
-        const int xx = x + kx - 3;
-        if (xx < 0 || xx >= W) continue;
-        const float f = c1[(size_t)ch * P + yy * W + xx] - c0[(size_t)ch * P + yy * W + xx];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fmaf(f, __ldg(w + (((size_t)(cg + j) * 2 + ch) * 7 + ky) * 7 + kx), acc[j]);
-      }
+  for (int idx = threadIdx.x; idx < FC_PIX * 98; idx += 128) {
+    const int pp = idx / 98, k = idx - pp * 98;
+    const int r = p0 + pp;
+    float v = 0.f;
+    if (r < P) {
+      const int y = r / W, x = r - y * W;
+      const int ch = k / 49, t = k - ch * 49, ky = t / 7, kx = t - ky * 7;
+      const int yy = y + ky - 3, xx = x + kx - 3;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = c1[(size_t)ch * P + yy * W + xx] - c0[(size_t)ch * P + yy * W + xx];
     }
+    sp[pp][k] = v;
+  }
+  __syncthreads();
+  const float bs = bias[c];
   const int Wp = W + 2 * pad, Hp = H + 2 * pad;
-  const size_t prow = ((size_t)b * Hp + y + pad) * Wp + x + pad;
-  *reinterpret_cast<uint2*>(out128 + prow * 128 + cg) =
-      make_uint2(pack_half2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f)), pack_half2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f)));
-  (void)hx; (void)rhx;
+#pragma unroll 4
+  for (int pp = 0; pp < FC_PIX; ++pp) {
+    const int r = p0 + pp;
+    if (r >= P) break;
+    float acc = bs;
+#pragma unroll 14
+    for (int k = 0; k < 98; ++k) acc = fmaf(sp[pp][k], sw[k * 128 + c], acc);
+    const int y = r / W, x = r - y * W;
+    out128[(((size_t)b * Hp + y + pad) * Wp + x + pad) * 128 + c] = __float2half_rn(fmaxf(acc, 0.f));
+  }
 }
 // motion features = cat([conv_out(126), flow(2)]) (update.py:97): the two flow channels of the GRU operand maps
 __global__ void k_flow_cols(const float* __restrict__ c0, const float* __restrict__ c1, int B, int H, int W, int pad,
@@ -223,8 +235,15 @@ int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pa
 }
 int raft_flow_conv7(const float* coords0, const float* coords1, const float* w, const float* bias, int B, int H, int W,
                     int pad, __half* out128, __half* hx, __half* rhx, cudaStream_t s) {
-  const long long total = (long long)B * H * W * 32;
-  k_flow_conv7<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(coords0, coords1, w, bias, B, H, W, pad, out128, hx, rhx);
+  (void)hx; (void)rhx;
+  const int tiles = (H * W + FC_PIX - 1) / FC_PIX;
+  constexpr int smem = (98 * 128 + FC_PIX * 100) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PRISMA_CUDA_OK(cudaFuncSetAttribute(k_flow_conv7, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  k_flow_conv7<<<B * tiles, 128, smem, s>>>(coords0, coords1, w, bias, B, H, W, pad, out128);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
