@@ -70,8 +70,14 @@ int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols,
   PRISMA_CHECK(taps >= 1 && taps <= GEMM_MAX_TAPS, "gemm: bad tap count");
   PRISMA_CHECK(N % 4 == 0, "gemm: N must be a multiple of 4");
   PRISMA_CHECK(M >= 1 && a_cols >= 1, "gemm: empty problem");
-  const int bn = force_bn ? force_bn : gemm_pick_bn(M, N, num_sms);
+  // force_bn == 512 requests the CTA-pair kernel (256 x 256 tiles); otherwise it is chosen for large problems
+  static const bool pairs_off = [] { const char* e = getenv("PRISMA_GEMM_PAIRS"); return e && e[0] == '0'; }();
+  int bn = force_bn ? force_bn : gemm_pick_bn(M, N, num_sms);
+  int cg = 1;
+  if (bn == 512) { bn = 256; cg = 2; }
+  else if (!force_bn && !pairs_off && bn == 256 && M >= 1024 && N >= 256) cg = 2;
   PRISMA_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: unsupported BLOCK_N");
+  out->cg = cg;
   PRISMA_CHECK(w_rows >= round_up(N, bn), "gemm: weight rows must be padded to a multiple of BLOCK_N");
   const int kchunks = ceil_div(a_cols, GEMM_BK);
   out->bn = bn;
@@ -83,32 +89,52 @@ int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols,
   out->args.ep = ep;
   PRISMA_TRY(make_tmap_2d_f16(&out->tmA, A, (uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)a_pitch, 64, GEMM_BM));
   PRISMA_TRY(make_tmap_2d_f16(&out->tmB, W, (uint64_t)taps * kchunks * 64, (uint64_t)w_rows,
-                              (uint64_t)taps * kchunks * 64, 64, bn));
-  const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, bn);
-  out->grid = tiles < num_sms ? tiles : num_sms;
+                              (uint64_t)taps * kchunks * 64, 64, bn / cg));
+  const int tiles = ceil_div(M, GEMM_BM * cg) * ceil_div(N, bn);
+  const int groups = num_sms / cg;
+  out->grid = (tiles < groups ? tiles : groups) * cg;
   out->flops = 2.0 * M * (double)N * taps * a_cols;
   return 0;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
   static bool attr_set = false;  // per-process, per-instantiation
   if (!attr_set) {
-    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        GemmCfg<BN>::SMEM_BYTES));
+    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        GemmCfg<BN, CG>::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_tc_kernel<BN><<<g.grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(g.tmA, g.tmB, g.args);
+  if (CG == 1) {
+    gemm_tc_kernel<BN, CG><<<g.grid, GEMM_THREADS, GemmCfg<BN, CG>::SMEM_BYTES, stream>>>(g.tmA, g.tmB, g.args);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g.grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GemmCfg<BN, CG>::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, g.tmA, g.tmB, g.args));
+  }
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int gemm_run(const GemmLaunch& g, cudaStream_t stream) {
+  if (g.cg == 2) {
+    if (g.bn == 256) return launch_bn<256, 2>(g, stream);
+    set_last_error("gemm_run: CTA pairs need BLOCK_N 256");
+    return -1;
+  }
   switch (g.bn) {
-    case 256: return launch_bn<256>(g, stream);
-    case 128: return launch_bn<128>(g, stream);
-    case 64: return launch_bn<64>(g, stream);
-    case 32: return launch_bn<32>(g, stream);
+    case 256: return launch_bn<256, 1>(g, stream);
+    case 128: return launch_bn<128, 1>(g, stream);
+    case 64: return launch_bn<64, 1>(g, stream);
+    case 32: return launch_bn<32, 1>(g, stream);
   }
   set_last_error("gemm_run: unsupported BLOCK_N");
   return -1;

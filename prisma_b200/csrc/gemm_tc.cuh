@@ -80,12 +80,12 @@ struct GemmArgs {
   GemmEpilogue ep;
 };
 
-template <int BN>
+template <int BN, int CG = 1>  // CG = CTAs per MMA (cta_group): 2 = a CTA pair computes a 256 x BN tile, each loading half of W
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 7);
+  static constexpr int STAGES = (STAGE_BYTES >= 49152) ? 4 : (STAGE_BYTES >= 32768 ? 6 : 7);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 32 * 4;  // epilogue transpose staging: 32x32 fp32 per warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -180,11 +180,11 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   }
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -203,7 +203,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tiles_m = (args.M + GEMM_BM - 1) / GEMM_BM;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // position inside the CTA pair
+  const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
+  constexpr int TILE_M = GEMM_BM * CG;
+  const int tiles_m = (args.M + TILE_M - 1) / TILE_M;
   const int tiles_n = (args.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = args.taps * args.kchunks;
@@ -212,12 +215,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], GEMM_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], GEMM_EPI_WARPS * CG); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) { if (CG == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); else tmem_alloc(tmem_slot, Cfg::TMEM_COLS); }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer's barriers must exist before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -225,27 +228,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % tiles_m) * GEMM_BM;
-        const int n0 = (tile / tiles_m) * BN;
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
+        const int m0 = (tile % tiles_m) * TILE_M + rank * GEMM_BM;
+        const int n0 = (tile / tiles_m) * BN + rank * (BN / CG);
         int tap = 0, chunk = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], chunk * GEMM_BK, m0 + args.tap_off[tap]);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+          if (CG == 2) {
+            // both CTAs' bytes land on the leader's barrier; only the leader arrives (count 1) and posts the total
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], chunk * GEMM_BK, m0 + args.tap_off[tap]);
+            tma_load_2d_pair(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], chunk * GEMM_BK, m0 + args.tap_off[tap]);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+          }
           if (++chunk == args.kchunks) { chunk = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(TILE_M, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
@@ -259,12 +269,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 fp16 = 32 B along K inside the 128 B swizzled row: +2 in the (addr >> 4) field
-            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if (CG == 2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[as]);
+        if (CG == 2) umma_commit_pair(&tfull[as]); else umma_commit(&tfull[as]);
       }
     }
   } else {
@@ -276,10 +287,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cg = lane & 7;     // coalesced phase: which 4-column group of the 32-column chunk
     const int rsub = lane >> 3;  // coalesced phase: row offset inside a 4-row step
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (tile % tiles_m) * GEMM_BM;
+      const int m0 = (tile % tiles_m) * TILE_M + rank * GEMM_BM;
       const int n0 = (tile / tiles_m) * BN;
       const int m = m0 + quarter * 32 + lane;
       // ---- row mapping of "my" accumulator row (lane == row inside this warp's 32-row slab)
@@ -381,15 +392,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]); }
     }
   }
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // no CTA of a pair may exit while the other can still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 #endif  // __CUDACC__
@@ -399,6 +410,7 @@ struct GemmLaunch {
   CUtensorMap tmA, tmB;
   GemmArgs args;
   int bn = 128;
+  int cg = 1;  // 2 = CTA pairs (cta_group::2), 256 x bn tiles
   int grid = 1;
   double flops = 0;  // algorithmic 2*M*N*K (excluding border/padding waste)
 };

@@ -34,6 +34,10 @@ def _gemm(A, W, bias, act, bn):
     (333, 32, 1152, 2, 32),      # BN=32
     (40000, 256, 128, 0, 0),     # many tiles per CTA (persistent loop, TMEM double buffering)
     (64, 64, 64, 0, 0),          # smaller than a tile
+    (512, 256, 128, 0, 512),     # CTA pairs (cta_group::2, 256x256 tiles): one pair tile per pair
+    (2443, 3072, 1024, 0, 512),  # CTA pairs, ViT-L qkv: ragged M, many tiles per pair
+    (9772, 1024, 4096, 1, 512),  # CTA pairs, 4-frame fc2 shape with gelu
+    (300, 256, 200, 2, 512),     # CTA pairs: second CTA's rows partly / fully out of range, K tail
 ])
 def test_gemm_matches_fp32_reference(M, N, K, act, bn):
     rng = np.random.default_rng(M * 7 + N * 3 + K)

@@ -10,7 +10,7 @@ def run(M, N, K, bn, act, iters=30):
     assert l.prisma_debug_gemm(0, fptr(A), fptr(W), fptr(b), fptr(D), M, N, K, act, bn, iters, C.byref(ms)) == 0, l.prisma_last_error()
     return ms.value * 1e3
 print("us per launch (back-to-back): rows = K, cols = [f32-out, f16-out, no-out]")
-for (M, N, bn) in [(2443, 3072, 256), (2443, 3072, 128), (2443, 1024, 256), (128 * 148, 256, 256), (128 * 148 * 2, 256, 256), (128*148, 128, 128)]:
+for (M, N, bn) in [(2443, 3072, 256), (2443, 3072, 512), (9772, 3072, 256), (9772, 3072, 512), (9772, 1024, 256), (9772, 1024, 512), (8192, 8192, 256), (8192, 8192, 512)]:
     print("M", M, "N", N, "bn", bn)
-    for K in (64, 256, 1024, 4096):
+    for K in ((1024, 4096) if M < 8192 else (8192,)):
         print("   K=%5d  %7.1f %7.1f %7.1f" % (K, run(M, N, K, bn, 0), run(M, N, K, bn, -2), run(M, N, K, bn, -1)))
