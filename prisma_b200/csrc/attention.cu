@@ -4,8 +4,12 @@
 // One CTA per (128-query tile, head, image); 2 CTAs co-reside per SM so one CTA's softmax overlaps the other's MMAs.
 //   warp 0   : TMA producer  (Q once; K/V 128x64 fp16 tiles in a 2-stage ring, 128B swizzle, straight out of the
 //                             [tokens][3*D] qkv matrix -- no head split/transposes ever materialise)
-//   warp 1   : MMA issuer    (S = Q K^T  -> TMEM cols [0,128);  O_j = P V_j -> TMEM cols [128,192), V as MN-major B)
-//   warps 2-5: softmax       (thread = query row: tcgen05.ld S, online max/sum in fp32, P -> fp16 -> swizzled smem
+//   warp 1   : MMA issuer    (S = Q K^T  -> TMEM cols [0,128);  O += P V -> TMEM cols [128,192): A = P read from TMEM
+//                             cols [192,256) (fp16 pairs written there by the softmax warps with tcgen05.st), B = V
+//                             from smem as an MN-major operand.  P never goes through shared memory: the SM's 128 B/clk
+//                             smem port is then only used by TMA fills and the Q/K/V operand reads)
+//   warps 2-9: softmax       (thread = half a query row -- warps w and w+4 share a TMEM lane quarter and take the
+//                             column halves, so 4 warps per scheduler keep the MUFU pipe fed: tcgen05.ld S, online max/sum in fp32, P -> fp16 -> swizzled smem
 //                             as the A operand of the PV MMA).  O accumulates in TMEM across all KV tiles; the
 //                             running-max rescale is lazy: O (and l) are only rescaled -- tcgen05.ld/st of this
 //                             warp's 32 lanes -- when a row's max grew by more than 2^8, so P stays <= 256 in fp16
@@ -15,11 +19,12 @@
 namespace prisma {
 
 constexpr int ATT_BQ = 128, ATT_BKV = 128, ATT_HD = 64;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;  // TMA warp + MMA warp + 8 softmax warps (two per TMEM lane quarter: column halves)
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
 // 7 tiles + barriers = 114,816 B: two CTAs (+1 KB reserved each) fit the 228 KB of an SM; no alignment slack, the
 // dynamic smem base is declared 1024-aligned (128B-swizzle atoms are 1 KB) and checked at kernel entry.
-constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 + 2 + 2) + 128;
+// Q + 2 x (K, V) + barriers + row-max exchange; P never touches shared memory (it is the TMEM A operand of the PV MMA)
+constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 + 2) + 128 /*barriers*/ + 512 /*row-max exchange*/;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -37,8 +42,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE_BYTES;      // 2 stages
   uint8_t* sV = smem + 3 * ATT_TILE_BYTES;  // 2 stages
-  uint8_t* sP = smem + 5 * ATT_TILE_BYTES;  // 2 K-slabs of [128][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * ATT_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
@@ -47,6 +51,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* pv_done = bars + 7;
   uint64_t* s_free = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  __half* s_xmax = reinterpret_cast<__half*>(smem + 5 * ATT_TILE_BYTES + 128);  // [2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = args.tokens, D = args.D;
@@ -60,9 +65,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
-    mbar_init(s_free, 4);
+    mbar_init(s_free, 8);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
@@ -72,6 +77,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_P = tmem_base + 192;  // P as packed fp16 pairs: 64 columns = 128 keys
 
   if (warp == 0) {
     if (lane == 0) {
@@ -117,9 +123,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const uint32_t vbase = smem_u32(sV + st * ATT_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint64_t pdesc = make_sdesc_sw128(smem_u32(sP + (k >> 2) * ATT_TILE_BYTES)) + 2 * (k & 3);
           const uint64_t vdesc = make_sdesc_sw128(vbase + k * 2048);
-          umma_f16(tmem_O, pdesc, vdesc, idesc_o, (j | k) != 0);  // O accumulates over all KV tiles
+          umma_f16_ts(tmem_O, tmem_P + k * 8, vdesc, idesc_o, (j | k) != 0);  // A = P from TMEM; O accumulates over all tiles
         }
         umma_commit(pv_done);
         umma_commit(&kv_empty[st]);
@@ -127,10 +132,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     }
   } else {
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;   // which 64 score columns (= which K-slab of P, which 32 columns of O)
     const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
-    float m_used = -INFINITY, l_run = 0.f;  // m_used: the max P / O are currently scaled by
+    float m_used = -INFINITY, l_part = 0.f;  // m_used: the max P / O are currently scaled by; l_part: my half's row sum
+    const uint32_t bar_id = 1 + quarter;  // named barrier of the two warps that share this lane quarter
 #ifdef PRISMA_ATTN_PROFILE
     long long t_wait = 0, t_p1 = 0, t_p2 = 0, t_tot = clock64();
     const bool prof = args.dbg != nullptr && threadIdx.x == 64 && blockIdx.x == 1 && blockIdx.y == 1;
@@ -138,34 +145,36 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #else
 #define ATT_CLK(x)
 #endif
-    uint8_t* prow = sP + r * 128;
-    const int rsw = r & 7;
 
     for (int j = 0; j < n_kv; ++j) {
-      const int valid = min(ATT_BKV, T - j * ATT_BKV);  // >= 1
+      const int valid = min(64, max(0, T - j * ATT_BKV - half * 64));  // valid columns of my half (0..64)
       ATT_CLK(c0_);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       ATT_CLK(c1_);
-      // ---- the whole S row (128 fp32) into registers with one wait; the TMEM buffer is then free for S(j+1)
-      uint32_t v[128];
-      tmem_ld32(tmem_S + lane_sel + 0, v);
-      tmem_ld32(tmem_S + lane_sel + 32, v + 32);
-      tmem_ld32(tmem_S + lane_sel + 64, v + 64);
-      tmem_ld32(tmem_S + lane_sel + 96, v + 96);
+      // ---- my half of the S row (64 fp32) into registers with one wait; then the TMEM buffer is free for S(j+1)
+      uint32_t v[64];
+      tmem_ld32(tmem_S + lane_sel + half * 64, v);
+      tmem_ld32(tmem_S + lane_sel + half * 64 + 32, v + 32);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
       float mx = -INFINITY;
-      if (valid == ATT_BKV) {
+      if (valid == 64) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
       } else {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 64; ++i) if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
-      // ---- lazy rescale (warp-uniform decision; each warp owns its 32 TMEM lanes)
+      // ---- row max across the two halves: exchanged as fp16 rounded UP (both threads then use the identical value,
+      // which is all the online softmax needs; >= the true max, so p <= 1 up to the lazy-rescale slack)
+      s_xmax[half * 128 + r] = __float2half_ru(fmaxf(mx, -60000.f));
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      mx = fmaxf(__half2float(s_xmax[r]), __half2float(s_xmax[128 + r]));
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");  // both have read before the next tile overwrites
+      // ---- lazy rescale (identical decision in both warps of the quarter; each owns 32 columns of O)
       if (j == 0) {
         m_used = mx;
       } else {
@@ -175,17 +184,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           const float alpha = ex2_approx((m_used - m_new) * LOG2E);  // 1 for rows that keep their max
           mbar_wait(pv_done, (j - 1) & 1);                            // no PV may be in flight on O
           tc_fence_after();
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_sel + half * 32, o);
+          tmem_ld_wait();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t o[32];
-            tmem_ld32(tmem_O + lane_sel + h * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem_O + lane_sel + h * 32, o);
-          }
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tmem_O + lane_sel + half * 32, o);
           tmem_st_wait();
-          l_run *= alpha;
+          l_part *= alpha;
           m_used = m_new;
         }
       }
@@ -193,22 +199,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       ATT_CLK(c2_);
       // ---- P(j-1) must have been consumed by PV(j-1) before the buffer is rewritten (issued a whole softmax ago)
       if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
-      // ---- p = exp(s - m_used), row sum (4 independent partial sums), P -> fp16 -> swizzled smem chunk by chunk
+      // ---- p = exp(s - m_used), partial row sum, P -> fp16 -> swizzled smem (K-slab `half` of the PV A operand)
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      if (valid == ATT_BKV) {  // every tile but the last: no masking instructions at all
+      uint32_t pk[32];  // my 64 probabilities as 32 fp16 pairs = 32 TMEM columns of the PV A operand
+      if (valid == 64) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {  // 16-byte chunks: 8 columns each
+        for (int c = 0; c < 8; ++c) {
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[c * 8 + i]), LOG2E, -mscaled));
           sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
-          uint4 o;
-          o.x = pack_half2(e[0], e[1]); o.y = pack_half2(e[2], e[3]); o.z = pack_half2(e[4], e[5]); o.w = pack_half2(e[6], e[7]);
-          *reinterpret_cast<uint4*>(prow + (c >> 3) * ATT_TILE_BYTES + (((c & 7) ^ rsw) << 4)) = o;
+          pk[c * 4 + 0] = pack_half2(e[0], e[1]); pk[c * 4 + 1] = pack_half2(e[2], e[3]);
+          pk[c * 4 + 2] = pack_half2(e[4], e[5]); pk[c * 4 + 3] = pack_half2(e[6], e[7]);
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {  // last KV tile only; fully unrolled so v[] stays in registers
+        for (int c = 0; c < 8; ++c) {  // last KV tile only; fully unrolled so v[] stays in registers
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -216,13 +222,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             e[i] = (c * 8 + i < valid) ? x : 0.f;
           }
           sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
-          uint4 o;
-          o.x = pack_half2(e[0], e[1]); o.y = pack_half2(e[2], e[3]); o.z = pack_half2(e[4], e[5]); o.w = pack_half2(e[6], e[7]);
-          *reinterpret_cast<uint4*>(prow + (c >> 3) * ATT_TILE_BYTES + (((c & 7) ^ rsw) << 4)) = o;
+          pk[c * 4 + 0] = pack_half2(e[0], e[1]); pk[c * 4 + 1] = pack_half2(e[2], e[3]);
+          pk[c * 4 + 2] = pack_half2(e[4], e[5]); pk[c * 4 + 3] = pack_half2(e[6], e[7]);
         }
       }
-      l_run += (sum0 + sum1) + (sum2 + sum3);
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      l_part += (sum0 + sum1) + (sum2 + sum3);
+      tmem_st32(tmem_P + lane_sel + half * 32, pk);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
@@ -234,30 +240,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #ifdef PRISMA_ATTN_PROFILE
     if (prof) { args.dbg[0] = t_wait; args.dbg[1] = t_p1; args.dbg[2] = t_p2; args.dbg[3] = clock64() - t_tot; args.dbg[4] = n_kv; }
 #endif
-    // ---- O is complete once the last PV retires
+    // ---- O is complete once the last PV retires; the K stages are then idle and carry the row-sum exchange
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
-    float O[ATT_HD];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint32_t v[32];
-      tmem_ld32(tmem_O + lane_sel + h * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) O[h * 32 + i] = __uint_as_float(v[i]);
-    }
-    // ---- normalise and store: out[row][head*64 + d]
+    float* s_l = reinterpret_cast<float*>(sK);  // [2 halves][128 rows]; the K stages are idle by now
+    s_l[half * 128 + r] = l_part;
+    uint32_t ov[32];
+    tmem_ld32(tmem_O + lane_sel + half * 32, ov);
+    tmem_ld_wait();
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    const float inv = 1.0f / (s_l[r] + s_l[128 + r]);
+    // ---- normalise and store my 32 columns: out[row][head*64 + half*32 + d]
     const int q = q0 + r;
     if (q < T) {
-      const float inv = 1.0f / l_run;
-      __half* dst = args.out + (size_t)(row_base + q) * args.out_ld + head * ATT_HD;
+      __half* dst = args.out + (size_t)(row_base + q) * args.out_ld + head * ATT_HD + half * 32;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         uint4 o;
-        o.x = pack_half2(O[g * 8 + 0] * inv, O[g * 8 + 1] * inv);
-        o.y = pack_half2(O[g * 8 + 2] * inv, O[g * 8 + 3] * inv);
-        o.z = pack_half2(O[g * 8 + 4] * inv, O[g * 8 + 5] * inv);
-        o.w = pack_half2(O[g * 8 + 6] * inv, O[g * 8 + 7] * inv);
+        o.x = pack_half2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
+        o.y = pack_half2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
+        o.z = pack_half2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
+        o.w = pack_half2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
         *reinterpret_cast<uint4*>(dst + g * 8) = o;
       }
     }
