@@ -58,7 +58,7 @@ def infer(img, normalize=False):
 
 def process_image(a):
     img = open_rgb(a.input)
-    rgb, dmin, dmax, pred = model.infer_encoded(img, want_depth=True)
+    rgb, dmin, dmax, pred = model.infer_image(img, want_depth=True)  # write_depth's PNG encoding (io.py:138-166)
     if a.npy:
         np.save(os.path.splitext(a.output)[0] + ".npy", pred)
     write_rgb(a.output, rgb)

@@ -50,6 +50,14 @@ int prisma_depth_infer_resident(prisma_engine* e, int h, int w, int n, int iters
 /* Encoder-only entry used by the parity tests: encode a given h*w f32 prediction (:215-220).               */
 int prisma_depth_encode(prisma_engine* e, const float* prediction, int h, int w, int flip, uint8_t* rgb_out,
                         float* min_out, float* max_out);
+/* Still-image path = process_image (bands/depth_anything.py:146-174): the prediction is encoded by write_depth
+ * (bands/common/io.py:138-166: heat map, Sobel edges in the saturation, (min,max) packed into pixels (0,0),(0,1));
+ * png_rgb_out is the h*w*3 RGB array the reference hands to cv2.imwrite.  prisma_depth_encode_png is that encoder
+ * alone on a given prediction (parity tests).                                                               */
+int prisma_depth_infer_image(prisma_engine* e, const uint8_t* rgb, int h, int w, float* depth_out, uint8_t* png_rgb_out,
+                             float* min_out, float* max_out);
+int prisma_depth_encode_png(prisma_engine* e, const float* prediction, int h, int w, int flip, uint8_t* rgb_out,
+                            float* min_out, float* max_out);
 /* Intermediate tensors of the last prisma_depth_infer call as dense fp32 (tests only):
  * "net_input" [3][hn][wn], "tokens" [T][D], "feat0".."feat3" [T][D], "net_depth" [hn][wn], ...
  * returns the number of floats written, or negative.                                                       */

@@ -237,3 +237,41 @@ def da_infer(sd, img_u8, encoder, q=_ident):
     with torch.no_grad():
         depth = da_model(sd, x, encoder, q)
     return da_upsample(depth, h, w)
+
+
+# --------------------------------------------------------------------------- PNG variant (process_image path)
+def float_to_edge(channel, ksize=1):
+    """common/encode.py:81-95: u8 image -> Sobel (ksize=1: [-1,0,1], BORDER_REFLECT_101) magnitude, normalised to its max."""
+    img = (channel * 255).astype(np.uint8)
+    sobel_x = cv2.Sobel(img, cv2.CV_64F, 1, 0, ksize=ksize)
+    sobel_y = cv2.Sobel(img, cv2.CV_64F, 0, 1, ksize=ksize)
+    sobel_mag = np.sqrt(np.square(sobel_x) + np.square(sobel_y))
+    sobel_mag *= 255.0 / sobel_mag.max()
+    return sobel_mag / 255.0
+
+
+def float_to_rgb(value, min_value=0.0, max_value=1.0, base=256):
+    """common/encode.py:141-146 (24-bit packing of the depth range into one pixel)."""
+    L = np.clip((value - min_value) / (max_value - min_value), 0.0, 1.0) * (base * base * base - 1)
+    return ((np.floor(L % base)) / (base - 1),
+            (np.floor(L / base) % base) / (base - 1),
+            (np.floor(L / (base * base)) % base) / (base - 1))
+
+
+def da_write_depth_rgb(prediction, flip=True):
+    """write_depth(..., normalize=True, heatmap=True, encode_range=True) up to the cv2.imwrite (common/io.py:138-166):
+    HxW f32 -> HxWx3 u8 RGB: heat map, Sobel edges in the saturation, (min,max) packed into pixels (0,0) and (0,1)."""
+    depth_min = prediction.min()
+    depth_max = prediction.max()
+    depth = (prediction - depth_min) / (depth_max - depth_min)
+    if flip:
+        depth = 1.0 - depth
+    edge = float_to_edge(depth, ksize=1)
+    depth = depth.astype(np.float64)
+    rgb = heat_to_rgb(depth)
+    sat = 1.0 - edge
+    for c in range(3):  # saturation() of common/encode.py:73-78
+        rgb[..., c] = rgb[..., c] * sat + (1.0 - sat)
+    rgb[0, 0] = float_to_rgb(depth_min, 0.0, 1000.0)
+    rgb[0, 1] = float_to_rgb(depth_max, 0.0, 1000.0)
+    return (rgb * 255).astype(np.uint8), float(depth_min), float(depth_max)

@@ -172,8 +172,27 @@ def golden_raft():
     print("[raft] wrote fixture; max|flow| %.2f" % float(np.abs(fwd_r).max()))
 
 
+def golden_png():
+    """process_image path: the reference's common.io.write_depth on the reference prediction of da_vits_480x640."""
+    import types
+    import cv2
+    for m in ("av", "plyfile", "decord"):  # container / point-cloud deps of common.io that are not installed (SURVEY 8c)
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules["plyfile"].PlyData = object
+    sys.modules["plyfile"].PlyElement = object
+    import common.io as rio
+    g = np.load(os.path.join(GOLD, "da_vits_480x640.npz"))
+    out = "/tmp/prisma_write_depth.png"
+    rio.write_depth(out, g["prediction"], normalize=True, heatmap=True, encode_range=True, flip=True)
+    ref = cv2.cvtColor(cv2.imread(out), cv2.COLOR_BGR2RGB)
+    mine, _, _ = oda.da_write_depth_rgb(g["prediction"], True)
+    assert np.array_equal(ref, mine)
+    np.savez_compressed(os.path.join(GOLD, "da_png_480x640.npz"), rgb_png=ref)
+    print("[png] oracle == reference write_depth; wrote fixture")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sizes", "da_small", "da_vits", "raft"]
+    which = sys.argv[1:] or ["sizes", "da_small", "da_vits", "raft", "png"]
     if "sizes" in which:
         golden_sizes()
     if "da_small" in which:
@@ -182,4 +201,6 @@ if __name__ == "__main__":
         golden_da("vits", 480, 640, "vits_480x640")   # BASELINE config 1 stand-in
     if "raft" in which:
         golden_raft()
+    if "png" in which:
+        golden_png()
 

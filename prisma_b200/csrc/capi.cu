@@ -151,6 +151,21 @@ int prisma_depth_encode(prisma_engine* e, const float* prediction, int h, int w,
   return d ? d->encode(prediction, h, w, flip, rgb_out, min_out, max_out) : -1;
   API_GUARD_END
 }
+int prisma_depth_encode_png(prisma_engine* e, const float* prediction, int h, int w, int flip, uint8_t* rgb_out,
+                            float* min_out, float* max_out) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  PRISMA_CHECK(prediction && rgb_out, "null argument");
+  return d ? d->encode(prediction, h, w, flip, rgb_out, min_out, max_out, 1) : -1;
+  API_GUARD_END
+}
+int prisma_depth_infer_image(prisma_engine* e, const uint8_t* rgb, int h, int w, float* depth_out, uint8_t* png_rgb_out,
+                             float* min_out, float* max_out) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  return d ? d->infer_image(rgb, h, w, depth_out, png_rgb_out, min_out, max_out) : -1;
+  API_GUARD_END
+}
 long long prisma_depth_read_tap(prisma_engine* e, const char* name, float* out, long long capacity) {
   API_GUARD_BEGIN
   DepthEngine* d = as_depth(e);

@@ -563,6 +563,31 @@ int DepthEngine::infer(const uint8_t* rgb, int n, int H, int W, float* depth_out
   return 0;
 }
 
+// process_image path (bands/depth_anything.py:146-174): one frame, write_depth's PNG encoding of the prediction
+int DepthEngine::infer_image(const uint8_t* rgb, int H, int W, float* depth_out, uint8_t* png_rgb_out, float* min_out,
+                             float* max_out) {
+  PRISMA_CHECK(rgb != nullptr && png_rgb_out != nullptr, "null argument");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_TRY(build_plan(H, W, 1));
+  PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, rgb, (size_t)H * W * 3, cudaMemcpyHostToDevice, stream));
+  PRISMA_TRY(run_steps(stream));
+  unsigned long long* d_mag = nullptr;
+  PRISMA_CUDA_OK(cudaMalloc(&d_mag, 16));
+  int r = depth_encode_png(b.pred, H, W, 1, b.rgb, b.mm, d_mag, b.minmax, num_sms, stream);
+  float mm[2] = {0, 0};
+  if (r == 0) {
+    if (depth_out) cudaMemcpyAsync(depth_out, b.pred, (size_t)H * W * 4, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(png_rgb_out, b.rgb, (size_t)H * W * 3, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(mm, b.minmax, 8, cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_last_error(std::string("infer_image: ") + cudaGetErrorString(e)); r = -2; }
+  }
+  cudaFree(d_mag);
+  if (min_out) *min_out = mm[0];
+  if (max_out) *max_out = mm[1];
+  return r;
+}
+
 int DepthEngine::infer_resident(int H, int W, int n, int iters, float* ms_per_iter) {
   PRISMA_CUDA_OK(cudaSetDevice(device));
   PRISMA_TRY(build_plan(H, W, n));
@@ -576,16 +601,19 @@ int DepthEngine::infer_resident(int H, int W, int n, int iters, float* ms_per_it
   return 0;
 }
 
-int DepthEngine::encode(const float* pred, int H, int W, int flip, uint8_t* rgb_out, float* min_out, float* max_out) {
+int DepthEngine::encode(const float* pred, int H, int W, int flip, uint8_t* rgb_out, float* min_out, float* max_out,
+                        int png_variant) {
   PRISMA_CUDA_OK(cudaSetDevice(device));
   float* d_pred = nullptr; uint8_t* d_rgb = nullptr; uint32_t* d_mm = nullptr; float* d_out = nullptr;
+  unsigned long long* d_mag = nullptr;
   std::vector<void*> tmp;
   auto cleanup = [&]() { for (void* q : tmp) cudaFree(q); };
   int r = 0;
   if ((r = dev_alloc(tmp, &d_pred, (size_t)H * W, false)) || (r = dev_alloc(tmp, &d_rgb, (size_t)H * W * 3, false)) ||
-      (r = dev_alloc(tmp, &d_mm, 2)) || (r = dev_alloc(tmp, &d_out, 2))) { cleanup(); return r; }
+      (r = dev_alloc(tmp, &d_mm, 2)) || (r = dev_alloc(tmp, &d_out, 2)) || (r = dev_alloc(tmp, &d_mag, 2))) { cleanup(); return r; }
   cudaMemcpyAsync(d_pred, pred, (size_t)H * W * 4, cudaMemcpyHostToDevice, stream);
-  r = depth_encode_only(d_pred, H, W, flip, d_rgb, d_mm, d_out, num_sms, stream);
+  r = png_variant ? depth_encode_png(d_pred, H, W, flip, d_rgb, d_mm, d_mag, d_out, num_sms, stream)
+                  : depth_encode_only(d_pred, H, W, flip, d_rgb, d_mm, d_out, num_sms, stream);
   float mm[2] = {0, 0};
   if (r == 0) {
     cudaMemcpyAsync(rgb_out, d_rgb, (size_t)H * W * 3, cudaMemcpyDeviceToHost, stream);

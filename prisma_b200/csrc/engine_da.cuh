@@ -47,7 +47,8 @@ class DepthEngine {
   int finalize();
   int infer(const uint8_t* rgb, int n, int H, int W, float* depth_out, uint8_t* rgb_out, float* min_out, float* max_out);
   int infer_resident(int H, int W, int n, int iters, float* ms_per_iter);
-  int encode(const float* pred, int H, int W, int flip, uint8_t* rgb_out, float* min_out, float* max_out);
+  int encode(const float* pred, int H, int W, int flip, uint8_t* rgb_out, float* min_out, float* max_out, int png_variant = 0);
+  int infer_image(const uint8_t* rgb, int H, int W, float* depth_out, uint8_t* png_rgb_out, float* min_out, float* max_out);
   long long read_tap(const std::string& name, float* out, long long capacity);
   int profile(int H, int W, int n, float* out8);
   int build_plan(int H, int W, int batch);

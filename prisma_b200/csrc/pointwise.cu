@@ -381,6 +381,90 @@ int depth_encode_only(const float* pred, int H, int W, int flip, uint8_t* rgb_ou
 }
 
 // ------------------------------------------------------------------------------------------------
+// PNG variant of the depth encode = write_depth(normalize, heatmap, encode_range) (bands/common/io.py:138-166), used by
+// process_image (bands/depth_anything.py:173): heat map whose saturation carries the Sobel edges of the u8 depth image
+// (common/encode.py:81-95, ksize=1 -> [-1,0,1], BORDER_REFLECT_101) and whose pixels (0,0),(0,1) carry (min,max) packed
+// in 24 bits over [0,1000] (encode.py:141-146, evaluated in f32 exactly as numpy does).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int depth_u8(const float* __restrict__ p, int W, int y, int x, float dmin, float range, int flip) {
+  float d = __fdiv_rn(__fsub_rn(p[(size_t)y * W + x], dmin), range);
+  if (flip) d = __fsub_rn(1.0f, d);
+  return (int)(uint8_t)(int)__fmul_rn(d, 255.0f);
+}
+__device__ __forceinline__ double sobel_mag(const float* __restrict__ p, int H, int W, int y, int x, float dmin, float range,
+                                            int flip) {
+  const int xl = x > 0 ? x - 1 : (W > 1 ? 1 : 0), xr = x < W - 1 ? x + 1 : (W > 1 ? W - 2 : 0);
+  const int yu = y > 0 ? y - 1 : (H > 1 ? 1 : 0), yd = y < H - 1 ? y + 1 : (H > 1 ? H - 2 : 0);
+  const double sx = (double)(depth_u8(p, W, y, xr, dmin, range, flip) - depth_u8(p, W, y, xl, dmin, range, flip));
+  const double sy = (double)(depth_u8(p, W, yd, x, dmin, range, flip) - depth_u8(p, W, yu, x, dmin, range, flip));
+  return sqrt(__dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy)));
+}
+__global__ void k_sobel_max(const float* __restrict__ p, int H, int W, const uint32_t* __restrict__ mm, int flip,
+                            unsigned long long* __restrict__ magmax) {
+  const float dmin = ord2f(mm[0]), range = __fsub_rn(ord2f(mm[1]), dmin);
+  double hi = 0.0;
+  const long long total = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    hi = fmax(hi, sobel_mag(p, H, W, y, x, dmin, range, flip));
+  }
+  for (int o = 16; o > 0; o >>= 1) hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(magmax, (unsigned long long)__double_as_longlong(hi));  // hi >= 0
+}
+__device__ __forceinline__ void range_pixel(float value, uint8_t* o) {
+  // float_to_rgb(value, 0, 1000): numpy keeps everything in f32; f32(256^3 - 1) == 16777216
+  const float L = __fmul_rn(fminf(fmaxf(__fdiv_rn(value, 1000.0f), 0.0f), 1.0f), 16777216.0f);
+  const float c0 = __fdiv_rn(floorf(fmodf(L, 256.0f)), 255.0f);
+  const float c1 = __fdiv_rn(fmodf(floorf(__fdiv_rn(L, 256.0f)), 256.0f), 255.0f);
+  const float c2 = __fdiv_rn(fmodf(floorf(__fdiv_rn(L, 65536.0f)), 256.0f), 255.0f);
+  o[0] = (uint8_t)(int)__dmul_rn((double)c0, 255.0);
+  o[1] = (uint8_t)(int)__dmul_rn((double)c1, 255.0);
+  o[2] = (uint8_t)(int)__dmul_rn((double)c2, 255.0);
+}
+__device__ __forceinline__ uint8_t heat_sat_u8(double hue6, double off, double sat, double one_minus_sat) {
+  double v = fmod(__dadd_rn(hue6, off), 6.0);
+  v = __dsub_rn(fabs(__dsub_rn(v, 3.0)), 1.0);
+  v = fmin(fmax(v, 0.0), 1.0);
+  v = __dadd_rn(__dmul_rn(v, sat), one_minus_sat);
+  return (uint8_t)(int)__dmul_rn(v, 255.0);
+}
+__global__ void k_depth_encode_png(const float* __restrict__ p, int H, int W, const uint32_t* __restrict__ mm, int flip,
+                                   const unsigned long long* __restrict__ magmax, uint8_t* __restrict__ rgb,
+                                   float* __restrict__ minmax_out) {
+  const float dmin = ord2f(mm[0]), dmax = ord2f(mm[1]);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && minmax_out) { minmax_out[0] = dmin; minmax_out[1] = dmax; }
+  const float range = __fsub_rn(dmax, dmin);
+  const double k = __ddiv_rn(255.0, __longlong_as_double((long long)*magmax));  // sobel_mag *= 255.0 / sobel_mag.max()
+  const long long total = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    uint8_t* o = rgb + i * 3;
+    if (i == 0) { range_pixel(dmin, o); continue; }
+    if (i == 1) { range_pixel(dmax, o); continue; }
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    float d = __fdiv_rn(__fsub_rn(p[i], dmin), range);
+    if (flip) d = __fsub_rn(1.0f, d);
+    const double edge = __ddiv_rn(__dmul_rn(sobel_mag(p, H, W, y, x, dmin, range, flip), k), 255.0);
+    const double sat = __dsub_rn(1.0, edge), oms = __dsub_rn(1.0, sat);
+    const double hue6 = __dmul_rn(__dmul_rn(__dsub_rn(1.0, (double)d), 0.65), 6.0);
+    o[0] = heat_sat_u8(hue6, 0.0, sat, oms);
+    o[1] = heat_sat_u8(hue6, 4.0, sat, oms);
+    o[2] = heat_sat_u8(hue6, 2.0, sat, oms);
+  }
+}
+__global__ void k_zero_u64(unsigned long long* p) { *p = 0ull; }
+
+int depth_encode_png(const float* pred, int H, int W, int flip, uint8_t* rgb_out, uint32_t* mm_scratch,
+                     unsigned long long* mag_scratch, float* minmax_out, int num_sms, cudaStream_t s) {
+  k_minmax_init<<<1, 1, 0, s>>>(mm_scratch);
+  k_zero_u64<<<1, 1, 0, s>>>(mag_scratch);
+  k_minmax_plain<<<num_sms * 4, 256, 0, s>>>(pred, (long long)H * W, mm_scratch);
+  k_sobel_max<<<num_sms * 8, 256, 0, s>>>(pred, H, W, mm_scratch, flip, mag_scratch);
+  k_depth_encode_png<<<num_sms * 8, 256, 0, s>>>(pred, H, W, mm_scratch, flip, mag_scratch, rgb_out, minmax_out);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------------
 __global__ void k_f32_to_f16(const float* __restrict__ a, __half* __restrict__ b, long long n) {

@@ -18,6 +18,8 @@ int depth_postprocess(const float* depth, int hn, int wn, int H, int W, int flip
                       uint32_t* mm_scratch, float* minmax_out, int num_sms, cudaStream_t s);
 int depth_encode_only(const float* pred, int H, int W, int flip, uint8_t* rgb_out, uint32_t* mm_scratch,
                       float* minmax_out, int num_sms, cudaStream_t s);
+int depth_encode_png(const float* pred, int H, int W, int flip, uint8_t* rgb_out, uint32_t* mm_scratch,
+                     unsigned long long* mag_scratch, float* minmax_out, int num_sms, cudaStream_t s);
 int f32_to_f16(const float* a, __half* b, long long n, cudaStream_t s);
 
 }  // namespace prisma

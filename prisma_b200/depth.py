@@ -100,6 +100,27 @@ class DepthAnythingEngine:
         check(lib().prisma_depth_encode(self._h, fptr(p), h, w, int(flip), u8ptr(rgb), C.byref(dmin), C.byref(dmax)))
         return rgb, dmin.value, dmax.value
 
+    def encode_png(self, prediction, flip=True):
+        """write_depth(normalize, heatmap, encode_range) of a given prediction: the RGB array written to <band>.png."""
+        p = np.ascontiguousarray(prediction, dtype=np.float32)
+        h, w = p.shape
+        rgb = np.empty((h, w, 3), np.uint8)
+        dmin, dmax = C.c_float(), C.c_float()
+        check(lib().prisma_depth_encode_png(self._h, fptr(p), h, w, int(flip), u8ptr(rgb), C.byref(dmin), C.byref(dmax)))
+        return rgb, dmin.value, dmax.value
+
+    def infer_image(self, img, want_depth=True):
+        """Still-image path (process_image): (png_rgb u8 HxWx3, min, max, depth f32 HxW | None)."""
+        img = np.ascontiguousarray(img)
+        if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+            raise PrismaError("expected an HxWx3 uint8 RGB frame")
+        h, w = img.shape[:2]
+        pred = np.empty((h, w), np.float32) if want_depth else None
+        rgb = np.empty((h, w, 3), np.uint8)
+        dmin, dmax = C.c_float(), C.c_float()
+        check(lib().prisma_depth_infer_image(self._h, u8ptr(img), h, w, fptr(pred), u8ptr(rgb), C.byref(dmin), C.byref(dmax)))
+        return rgb, dmin.value, dmax.value, pred
+
     def read_tap(self, name, shape):
         out = np.empty(int(np.prod(shape)), np.float32)
         n = check(lib().prisma_depth_read_tap(self._h, name.encode(), fptr(out), out.size))

@@ -50,3 +50,11 @@ def test_heat_roundtrip():
     hue = np.where(mx == r, ((g - b) / (mx - mn + 1e-12)) % 6, np.where(mx == g, (b - r) / (mx - mn + 1e-12) + 2, (r - g) / (mx - mn + 1e-12) + 4)) / 6
     back = np.clip(1.0 - hue * 1.538461538, 0, 1)
     assert np.abs(back - h).max() < 1e-6
+
+
+def test_png_variant_matches_reference(golden_dir):
+    """oracle write_depth restatement vs the RGB array the reference's common.io.write_depth produced."""
+    g = np.load(os.path.join(golden_dir, "da_vits_480x640.npz"))
+    ref = np.load(os.path.join(golden_dir, "da_png_480x640.npz"))["rgb_png"]
+    rgb, dmin, dmax = oda.da_write_depth_rgb(g["prediction"], True)
+    assert np.array_equal(rgb, ref)

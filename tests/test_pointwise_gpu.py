@@ -54,3 +54,21 @@ def test_depth_encode_bit_exact(golden_dir, tag):
     ref, rmin, rmax = oda.da_encode(p)
     assert np.array_equal(rgb2, ref) and np.float32(mn) == np.float32(rmin) and np.float32(mx) == np.float32(rmax)
     eng.close()
+
+
+def test_depth_png_encode_bit_exact(golden_dir):
+    """PNG variant (write_depth: Sobel-edge saturation + range pixels) on the reference's own prediction vs the RGB array
+    the reference wrote (tests/golden/da_png_480x640.npz, recorded from common.io.write_depth) -- bit-exact."""
+    from prisma_b200.depth import DepthAnythingEngine
+    g = np.load(os.path.join(golden_dir, "da_vits_480x640.npz"))
+    ref = np.load(os.path.join(golden_dir, "da_png_480x640.npz"))["rgb_png"]
+    eng = DepthAnythingEngine("vits")
+    rgb, dmin, dmax = eng.encode_png(g["prediction"], flip=True)
+    assert np.array_equal(rgb, ref)
+    assert np.float32(dmin) == g["dmin"] and np.float32(dmax) == g["dmax"]
+    rng = np.random.default_rng(3)
+    p = (rng.random((720, 1280), dtype=np.float32) * 30 + 2).astype(np.float32)
+    rgb2, _, _ = eng.encode_png(p)
+    ref2, _, _ = oda.da_write_depth_rgb(p, True)
+    assert np.array_equal(rgb2, ref2)
+    eng.close()
