@@ -3,11 +3,11 @@
 
 Same plugin surface: BAND / ITERATIONS / MODEL constants, init_model(args), infer(args, prev, curr),
 process_video(args), the CLI flags of bands/flow_raft.py:170-189, the outputs (flow_raft.mp4, flow_raft.csv with the
-per-frame max displacement, optional flow_raft_bwd.mp4) and the metadata.json keys (:143-166).
-The model (RAFT, 12-20 GRU iterations), the x`scale` cubic resize and the HSV encode run in libprisma_b200.so.
-
-Not built yet: --mask / --output_mask / --subpath_mask (fwd/bwd consistency masks) and
-.flo export (--subpath); the script raises for them instead of falling back.  --small / --alternate_corr /
+per-frame max displacement, optional flow_raft_bwd.mp4, flow_raft_mask[_bwd].mp4, <subpath>_fwd|_bwd/%04d.flo,
+<subpath_mask>_fwd|_bwd/%04d.png) and the metadata.json keys (:143-166).
+The model (RAFT, 12-20 GRU iterations), the x`scale` cubic resize, the HSV encode, the forward/backward consistency
+masks and the 16-bit flow PNG payload are computed in libprisma_b200.so.  --small raises (commented out in the
+reference too); --alternate_corr /
 --mixed_precision are accepted for CLI compatibility: the engine has one (fp16-operand, fp32-accumulate) path and
 always builds the correlation pyramid on the GPU.
 """
@@ -44,47 +44,90 @@ def init_model(args):
     return model
 
 
-def infer(args, prev_frame, curr_frame):
-    """(fwd_flow, bwd_flow, fwd_mask, bwd_mask) like the reference's infer (:51-66); frames are HxWx3 u8 RGB at the
-    source resolution (the x scale resize of :100 happens inside the engine)."""
-    r = model.infer_pair(prev_frame, curr_frame)
-    return r["fwd"], r["bwd"], None, None
+def infer(args, prev_frame, curr_frame, want_rgb=False):
+    """(fwd_flow, bwd_flow, fwd_mask, bwd_mask) like the reference's infer (:51-66), plus the engine's result dict;
+    frames are HxWx3 u8 RGB at the source resolution (the x scale resize of :100 happens inside the engine)."""
+    from prisma_b200.flow import consistency_masks
+    r = model.infer_pair(prev_frame, curr_frame, want_rgb=want_rgb)
+    fwd_mask = bwd_mask = None
+    if args.output_mask != "" or args.subpath_mask != "":
+        fwd_mask, bwd_mask, r["fwd_u16"], r["bwd_u16"] = consistency_masks(r["fwd"], r["bwd"], want_u16=True,
+                                                                           device=args.device)
+    return r["fwd"], r["bwd"], fwd_mask, bwd_mask, r
+
+
+def write_flow(args, r, fwd_video, max_disps, idx, fwd_mask=None, fwd_mask_video=None, bwd_video=None, bwd_mask=None,
+               bwd_mask_video=None):
+    """One frame's outputs (reference common/flow.py:64-98).  The reference's .flo branch (:90-93) calls this very
+    function with (path, flow) and cannot run; the Middlebury writer it means (common/io.py:175-198) is used here."""
+    from prisma_b200.flow import write_flo
+    fwd_video.write(r["fwd_rgb"])  # VideoWriter rescales to the source size, as the reference's does
+    max_disps.append(r["max_fwd"])
+    if fwd_mask is not None and fwd_mask_video:
+        fwd_mask_video.write(np.repeat((fwd_mask.astype(np.uint8) * 255)[..., None], 3, axis=-1))
+    if bwd_mask is not None and bwd_mask_video:
+        bwd_mask_video.write(np.repeat((bwd_mask.astype(np.uint8) * 255)[..., None], 3, axis=-1))
+    if args.backwards and bwd_video:
+        bwd_video.write(r["bwd_rgb"])
+    if args.subpath != "":
+        write_flo(os.path.join(args.subpath + "_fwd", "%04d.flo" % idx), r["fwd"])
+        if args.backwards:
+            write_flo(os.path.join(args.subpath + "_bwd", "%04d.flo" % idx), r["bwd"])
+    if args.subpath_mask != "":
+        import cv2
+        cv2.imwrite(os.path.join(args.subpath_mask + "_fwd", "%04d.png" % idx), r["fwd_u16"])
+        if args.backwards:
+            cv2.imwrite(os.path.join(args.subpath_mask + "_bwd", "%04d.png" % idx), r["bwd_u16"])
 
 
 def process_video(args):
     reader = VideoReader(args.input)
     base = args.output.rsplit(".", 1)[0]
-    fwd_video = VideoWriter(reader.width, reader.height, reader.get_avg_fps(), args.output)
-    bwd_video = VideoWriter(reader.width, reader.height, reader.get_avg_fps(), base + "_bwd.mp4") if args.backwards else None
+    fps = reader.get_avg_fps()
+    new_writer = lambda name: VideoWriter(reader.width, reader.height, fps, name)
+    fwd_video = new_writer(args.output)
+    fwd_mask_video = new_writer(args.output_mask) if args.output_mask != "" else None
+    bwd_video = new_writer(base + "_bwd.mp4") if args.backwards else None
+    bwd_mask_video = None
+    if args.backwards and args.output_mask != "":
+        bwd_mask_video = new_writer(args.output_mask.rsplit(".", 1)[0] + "_bwd.mp4")
+    want_masks = args.output_mask != "" or args.subpath_mask != ""
     max_disps = []
     prev = None
-    hs = ws = 0
-    for frame in reader:
+    i = 0
+    for i, frame in enumerate(reader):
         if prev is not None:
-            r = model.infer_pair(prev, frame, want_rgb=True)
-            fwd_video.write(r["fwd_rgb"])  # VideoWriter rescales to the source size, as the reference's does
-            if bwd_video:
-                bwd_video.write(r["bwd_rgb"])
-            max_disps.append(r["max_fwd"])
-            hs, ws = r["fwd_rgb"].shape[:2]
+            _, _, fwd_mask, bwd_mask, r = infer(args, prev, frame, want_rgb=True)
+            write_flow(args, r, fwd_video, max_disps, i - 1, fwd_mask, fwd_mask_video, bwd_video, bwd_mask, bwd_mask_video)
         prev = frame
-    if prev is not None:  # last frame: zero flow (:116-126; the reference's 0/0 -> NaN -> u8 cast gives a black frame)
-        if hs == 0:
-            hs, ws = model.out_size(reader.height, reader.width)
+    if prev is not None:
+        # last frame (:116-126): zero flow (the reference's 0/0 -> NaN -> u8 cast gives a black frame), all-false masks
+        # at the SOURCE resolution, as the reference allocates them
+        hs, ws = reader.height, reader.width
+        zero = np.zeros((hs, ws, 2), np.float32)
         black = np.zeros((hs, ws, 3), np.uint8)
-        fwd_video.write(black)
-        if bwd_video:
-            bwd_video.write(black)
-        max_disps.append(0.0)
-    fwd_video.close()
-    if bwd_video:
-        bwd_video.close()
+        u16 = np.zeros((hs, ws, 3), np.uint16)
+        u16[..., :2] = 32768
+        r = dict(fwd=zero, bwd=zero, fwd_rgb=black, bwd_rgb=black, max_fwd=0.0, fwd_u16=u16, bwd_u16=u16)
+        mask = np.zeros((hs, ws), bool) if want_masks else None
+        write_flow(args, r, fwd_video, max_disps, i, mask, fwd_mask_video, bwd_video, mask, bwd_mask_video)
+    for v in (fwd_video, fwd_mask_video, bwd_video, bwd_mask_video):
+        if v:
+            v.close()
     with open(base + ".csv", "w") as f:
         f.writelines("{}\n".format(v) for v in max_disps)
     if data:
         data["bands"][BAND] = {"url": BAND + ".mp4", "values": {"dist": {"type": "float", "url": BAND + ".csv"}}}
+        if args.subpath != "":
+            data["bands"][BAND]["folder"] = args.subpath
         if args.backwards:
             data["bands"][BAND + "_bwd"] = {"url": BAND + "_bwd.mp4"}
+            if args.subpath != "":
+                data["bands"][BAND + "_bwd"]["folder"] = args.subpath + "_bwd"
+        if args.output_mask != "":
+            data["bands"][BAND + "_mask"] = {"url": BAND + "_mask.mp4"}
+            if args.backwards:
+                data["bands"][BAND + "_mask_bwd"] = {"url": BAND + "_mask_bwd.mp4"}
 
 
 def build_parser():
@@ -111,16 +154,23 @@ def build_parser():
 def main(argv=None):
     global data
     args = build_parser().parse_args(argv)
-    if args.mask or args.output_mask or args.subpath_mask or args.subpath:
-        raise NotImplementedError("consistency masks / .flo export are not built yet (SURVEY.md section 8f row 2)")
     if args.small:
         raise NotImplementedError("the small RAFT variant is commented out in the reference (raft.py:28-33) and not built")
     data = load_metadata(args.input)
     if data:
         args.input = get_url(args.input, data, "rgba")
         args.output = get_target(args.input, data, band=BAND, target=args.output)
+        if args.mask:
+            args.output_mask = get_target(args.input, data, band=BAND + "_mask")
     elif args.output == "":
         args.output = os.path.join(os.path.dirname(args.input), BAND + ".mp4")
+    input_folder = os.path.dirname(args.input)
+    for attr in ("subpath", "subpath_mask"):  # reference :208-218
+        if getattr(args, attr) != "":
+            setattr(args, attr, os.path.join(input_folder, getattr(args, attr)))
+            os.makedirs(getattr(args, attr) + "_fwd", exist_ok=True)
+            if args.backwards:
+                os.makedirs(getattr(args, attr) + "_bwd", exist_ok=True)
     init_model(args)
     process_video(args)
     write_metadata(args.input, data)

@@ -81,6 +81,11 @@ int prisma_flow_preprocess(int device, const uint8_t* rgb, int h, int w, float s
                            float* chw_padded);
 /* K20: process_flow (common/encode.py:113-126): flow f32 h*w*2 -> rgb u8 h*w*3 + max displacement.            */
 int prisma_flow_encode(int device, const float* flow, int h, int w, uint8_t* rgb_out, float* max_disp_out);
+/* compute_fwdbwd_mask (common/flow.py:28-40, incl. warp_flow = cv2.remap bilinear :19-26) and encode_flow
+ * (common/encode.py:105-110): fwd / bwd f32 h*w*2 -> masks u8 h*w (0/1) and, optionally, the 16-bit PNG payload
+ * u16 h*w*3 written by --subpath_mask.                                                                          */
+int prisma_flow_masks(int device, const float* fwd, const float* bwd, int h, int w, uint8_t* fwd_mask, uint8_t* bwd_mask,
+                      uint16_t* fwd_u16, uint16_t* bwd_u16);
 /* K13-K15: CorrBlock (raft/corr.py:12-60) for `batch` image pairs at 1/8 resolution, 256 channels.             */
 int prisma_flowcorr_create(int device, int batch, int h8, int w8, prisma_engine** out);
 /* fmap1/fmap2: host f32 [batch][256][h8][w8] (NCHW, as BasicEncoder returns them)                              */

@@ -191,3 +191,32 @@ def process_flow(flow):
     for c in range(3):
         rgb[..., c] = rgb[..., c] * rad + (1.0 - rad)
     return (rgb * 255).astype(np.uint8), max_distance
+
+
+# --------------------------------------------------------------------------- consistency masks / 16-bit flow PNG
+def warp_flow(img, flow):
+    """common/flow.py:19-26: sample `img` at (x + flow_x, y + flow_y) with cv2.remap bilinear, zero outside."""
+    h, w = flow.shape[:2]
+    flow_new = flow.copy()
+    flow_new[:, :, 0] += np.arange(w)
+    flow_new[:, :, 1] += np.arange(h)[:, np.newaxis]
+    return cv2.remap(img, flow_new, None, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+
+
+def compute_fwdbwd_mask(fwd_flow, bwd_flow, alpha_1=0.05, alpha_2=0.5):
+    """common/flow.py:28-40: forward/backward consistency masks."""
+    bwd2fwd = warp_flow(bwd_flow, fwd_flow)
+    fwd_err = np.linalg.norm(fwd_flow + bwd2fwd, axis=-1)
+    fwd_mask = fwd_err < alpha_1 * (np.linalg.norm(fwd_flow, axis=-1) + np.linalg.norm(bwd2fwd, axis=-1)) + alpha_2
+    fwd2bwd = warp_flow(fwd_flow, bwd_flow)
+    bwd_err = np.linalg.norm(bwd_flow + fwd2bwd, axis=-1)
+    bwd_mask = bwd_err < alpha_1 * (np.linalg.norm(bwd_flow, axis=-1) + np.linalg.norm(fwd2bwd, axis=-1)) + alpha_2
+    return fwd_mask, bwd_mask
+
+
+def encode_flow(flow, mask):
+    """common/encode.py:105-110: flow + validity mask -> HxWx3 u16 (the 16-bit PNG of --subpath_mask)."""
+    flow = 2 ** 15 + flow * (2 ** 8)
+    mask = mask & (np.max(flow, axis=-1) < (2 ** 16 - 1))
+    mask = mask & (0 < np.min(flow, axis=-1))
+    return np.concatenate([flow.astype(np.uint16), mask[..., None].astype(np.uint16) * (2 ** 16 - 1)], axis=-1)

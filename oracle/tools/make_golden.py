@@ -146,6 +146,13 @@ def golden_raft():
     fwd_r = padder.unpad(up_r[0]).permute(1, 2, 0).numpy()
     fwd_o, bwd_o = oraft.raft_infer(sd, i1, i2, 12)
     assert np.array_equal(fwd_r, fwd_o)
+    bwd_r = padder.unpad(up_r[1]).permute(1, 2, 0).numpy()
+    from common.flow import compute_fwdbwd_mask as ref_mask
+    fm_r, bm_r = ref_mask(fwd_r, bwd_r)
+    fm_o, bm_o = oraft.compute_fwdbwd_mask(fwd_r, bwd_r)
+    assert np.array_equal(fm_r, fm_o) and np.array_equal(bm_r, bm_o)
+    enc_r = renc.encode_flow(fwd_r.copy(), fm_r.copy())
+    assert np.array_equal(enc_r, oraft.encode_flow(fwd_r.copy(), fm_r.copy()))
     rgb_r, md_r = renc.process_flow(fwd_r)
     rgb_o, md_o = oraft.process_flow(fwd_o)
     assert np.array_equal(rgb_r, rgb_o) and md_r == md_o
@@ -168,6 +175,7 @@ def golden_raft():
         corr_l3_rows=cb.corr_pyramid[3][:64, 0].numpy().astype(np.float32),
         coords=coords.numpy().astype(np.float32), lookup=lk_r.numpy().astype(np.float16),
         flow_fwd=fwd_r.astype(np.float32), flow_rgb=rgb_r, flow_max=np.float32(md_r),
+        flow_bwd=bwd_r.astype(np.float32), fwd_mask=fm_r, bwd_mask=bm_r, flow_u16=enc_r,
     )
     print("[raft] wrote fixture; max|flow| %.2f" % float(np.abs(fwd_r).max()))
 

@@ -35,6 +35,7 @@ SIGNATURES = {
     "prisma_engine_destroy": (C.c_int, [C.c_void_p]),
     "prisma_flow_preprocess": (C.c_int, [C.c_int, c_u8_p, C.c_int, C.c_int, C.c_float, c_u8_p, c_float_p]),
     "prisma_flow_encode": (C.c_int, [C.c_int, c_float_p, C.c_int, C.c_int, c_u8_p, c_float_p]),
+    "prisma_flow_masks": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.c_int, c_u8_p, c_u8_p, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]),
     "prisma_flowcorr_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "prisma_flowcorr_set_fmaps": (C.c_int, [C.c_void_p, c_float_p, c_float_p]),
     "prisma_flowcorr_build": (C.c_int, [C.c_void_p, C.c_int, c_float_p]),

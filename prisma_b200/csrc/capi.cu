@@ -410,6 +410,34 @@ int prisma_flow_encode(int device, const float* flow, int h, int w, uint8_t* rgb
   API_GUARD_END
 }
 
+int prisma_flow_masks(int device, const float* fwd, const float* bwd, int h, int w, uint8_t* fwd_mask, uint8_t* bwd_mask,
+                      uint16_t* fwd_u16, uint16_t* bwd_u16) {
+  API_GUARD_BEGIN
+  int sms = 0;
+  PRISMA_TRY(device_sms(device, &sms));
+  PRISMA_CHECK(fwd && bwd && fwd_mask && bwd_mask, "null argument");
+  Scratch sc;
+  const size_t n = (size_t)h * w;
+  float* df = sc.alloc<float>(n * 2);
+  float* db = sc.alloc<float>(n * 2);
+  uint8_t* mf = sc.alloc<uint8_t>(n);
+  uint8_t* mb = sc.alloc<uint8_t>(n);
+  uint16_t* uf = sc.alloc<uint16_t>(n * 3);
+  uint16_t* ub = sc.alloc<uint16_t>(n * 3);
+  PRISMA_CHECK(df && db && mf && mb && uf && ub, "cudaMalloc failed");
+  PRISMA_CUDA_OK(cudaMemcpy(df, fwd, n * 8, cudaMemcpyHostToDevice));
+  PRISMA_CUDA_OK(cudaMemcpy(db, bwd, n * 8, cudaMemcpyHostToDevice));
+  PRISMA_TRY(flow_consistency_masks(df, db, h, w, mf, mb, sms, 0));
+  PRISMA_TRY(flow_encode_u16(df, mf, h, w, uf, sms, 0));
+  PRISMA_TRY(flow_encode_u16(db, mb, h, w, ub, sms, 0));
+  PRISMA_CUDA_OK(cudaMemcpy(fwd_mask, mf, n, cudaMemcpyDeviceToHost));
+  PRISMA_CUDA_OK(cudaMemcpy(bwd_mask, mb, n, cudaMemcpyDeviceToHost));
+  if (fwd_u16) PRISMA_CUDA_OK(cudaMemcpy(fwd_u16, uf, n * 6, cudaMemcpyDeviceToHost));
+  if (bwd_u16) PRISMA_CUDA_OK(cudaMemcpy(bwd_u16, ub, n * 6, cudaMemcpyDeviceToHost));
+  return 0;
+  API_GUARD_END
+}
+
 int prisma_flowcorr_create(int device, int batch, int h8, int w8, prisma_engine** out) {
   API_GUARD_BEGIN
   PRISMA_CHECK(out != nullptr, "null argument");

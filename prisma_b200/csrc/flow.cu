@@ -146,6 +146,66 @@ int flow_encode(const float* flow, int H, int W, uint8_t* rgb, uint32_t* mm_scra
 }
 
 // ------------------------------------------------------------------------------------------------
+// Forward/backward consistency mask (common/flow.py:19-40) and the 16-bit flow PNG packing (common/encode.py:105-110).
+// warp_flow = cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) of a 2-channel f32 image: OpenCV quantises the sampling position
+// to 1/32 pixel (cvRound(x*32)), takes the four taps with weights from its float bilinear table ((1-fy/32)(1-fx/32), ...)
+// and sums them left to right in f32; reproduced here so the boolean mask is bit-faithful.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 remap_bilinear_c2(const float2* __restrict__ img, int H, int W, float mx, float my) {
+  const int sx = __float2int_rn(__fmul_rn(mx, 32.f)), sy = __float2int_rn(__fmul_rn(my, 32.f));
+  const int ix = sx >> 5, iy = sy >> 5;
+  const float fx = (float)(sx & 31) * (1.f / 32.f), fy = (float)(sy & 31) * (1.f / 32.f);
+  const float vx0 = __fsub_rn(1.f, fx), vy0 = __fsub_rn(1.f, fy);
+  const float w00 = __fmul_rn(vy0, vx0), w01 = __fmul_rn(vy0, fx), w10 = __fmul_rn(fy, vx0), w11 = __fmul_rn(fy, fx);
+  auto at = [&](int y, int x) { return (x >= 0 && x < W && y >= 0 && y < H) ? img[(size_t)y * W + x] : make_float2(0.f, 0.f); };
+  const float2 a = at(iy, ix), b = at(iy, ix + 1), c = at(iy + 1, ix), d = at(iy + 1, ix + 1);
+  float2 r;
+  r.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.x, w00), __fmul_rn(b.x, w01)), __fmul_rn(c.x, w10)), __fmul_rn(d.x, w11));
+  r.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.y, w00), __fmul_rn(b.y, w01)), __fmul_rn(c.y, w10)), __fmul_rn(d.y, w11));
+  return r;
+}
+__device__ __forceinline__ float norm2_f32(float x, float y) { return __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))); }
+
+// mask[i] = |f + warp(g, f)| < a1 * (|f| + |warp(g, f)|) + a2     (f = this direction's flow, g = the other one's)
+__global__ void k_consistency_mask(const float2* __restrict__ f, const float2* __restrict__ g, int H, int W, float a1,
+                                   float a2, uint8_t* __restrict__ mask) {
+  const long long total = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    const float2 fl = f[i];
+    const float2 w = remap_bilinear_c2(g, H, W, __fadd_rn(fl.x, (float)x), __fadd_rn(fl.y, (float)y));
+    const float err = norm2_f32(__fadd_rn(fl.x, w.x), __fadd_rn(fl.y, w.y));
+    const float thr = __fadd_rn(__fmul_rn(a1, __fadd_rn(norm2_f32(fl.x, fl.y), norm2_f32(w.x, w.y))), a2);
+    mask[i] = err < thr ? 1 : 0;
+  }
+}
+int flow_consistency_masks(const float* fwd, const float* bwd, int H, int W, uint8_t* fwd_mask, uint8_t* bwd_mask,
+                           int num_sms, cudaStream_t s) {
+  k_consistency_mask<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float2*>(fwd), reinterpret_cast<const float2*>(bwd),
+                                                 H, W, 0.05f, 0.5f, fwd_mask);
+  k_consistency_mask<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float2*>(bwd), reinterpret_cast<const float2*>(fwd),
+                                                 H, W, 0.05f, 0.5f, bwd_mask);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// encode_flow: u16 (2^15 + 256 f) per component + validity channel
+__global__ void k_flow_u16(const float2* __restrict__ f, const uint8_t* __restrict__ mask, long long n,
+                           uint16_t* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float fx = __fadd_rn(32768.f, __fmul_rn(f[i].x, 256.f)), fy = __fadd_rn(32768.f, __fmul_rn(f[i].y, 256.f));
+    const bool ok = mask[i] && fmaxf(fx, fy) < 65535.f && 0.f < fminf(fx, fy);
+    out[i * 3 + 0] = (uint16_t)(int)fx;
+    out[i * 3 + 1] = (uint16_t)(int)fy;
+    out[i * 3 + 2] = ok ? 65535 : 0;
+  }
+}
+int flow_encode_u16(const float* flow, const uint8_t* mask, int H, int W, uint16_t* out, int num_sms, cudaStream_t s) {
+  k_flow_u16<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float2*>(flow), mask, (long long)H * W, out);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K14 (by linearity): avg_pool2d of the correlation volume over its last two dims == correlation with the
 // average-pooled fmap2.  Pool fmap2 (fp16 [P][C]) into the three coarser levels (floor sizes, corr.py:24-27).
 // ------------------------------------------------------------------------------------------------

@@ -12,6 +12,10 @@ int raft_preprocess(const uint8_t* img, int H, int W, int h, int w, const int pa
 int flow_encode(const float* flow, int H, int W, uint8_t* rgb, uint32_t* mm_scratch, float* max_out, int num_sms,
                 cudaStream_t s);
 
+int flow_consistency_masks(const float* fwd, const float* bwd, int H, int W, uint8_t* fwd_mask, uint8_t* bwd_mask,
+                           int num_sms, cudaStream_t s);
+int flow_encode_u16(const float* flow, const uint8_t* mask, int H, int W, uint16_t* out, int num_sms, cudaStream_t s);
+
 // All-pairs correlation pyramid + lookup for `batch` image pairs at 1/8 resolution (h8 x w8, C = 256 channels).
 class FlowCorr {
  public:

@@ -412,8 +412,8 @@ __global__ void k_sobel_max(const float* __restrict__ p, int H, int W, const uin
   if ((threadIdx.x & 31) == 0) atomicMax(magmax, (unsigned long long)__double_as_longlong(hi));  // hi >= 0
 }
 __device__ __forceinline__ void range_pixel(float value, uint8_t* o) {
-  // float_to_rgb(value, 0, 1000): numpy keeps everything in f32; f32(256^3 - 1) == 16777216
-  const float L = __fmul_rn(fminf(fmaxf(__fdiv_rn(value, 1000.0f), 0.0f), 1.0f), 16777216.0f);
+  // float_to_rgb(value, 0, 1000): numpy keeps everything in f32 (256^3 - 1 = 2^24 - 1 is exactly representable)
+  const float L = __fmul_rn(fminf(fmaxf(__fdiv_rn(value, 1000.0f), 0.0f), 1.0f), 16777215.0f);
   const float c0 = __fdiv_rn(floorf(fmodf(L, 256.0f)), 255.0f);
   const float c1 = __fdiv_rn(fmodf(floorf(__fdiv_rn(L, 256.0f)), 256.0f), 255.0f);
   const float c2 = __fdiv_rn(fmodf(floorf(__fdiv_rn(L, 65536.0f)), 256.0f), 255.0f);

@@ -11,6 +11,30 @@ import numpy as np
 from ._lib import PrismaError, check, fptr, lib, u8ptr, c_i64_p
 
 
+def consistency_masks(fwd, bwd, want_u16=False, device=0):
+    """compute_fwdbwd_mask (bands/common/flow.py:28-40) and, with want_u16, encode_flow (common/encode.py:105-110) of both
+    directions: fwd/bwd HxWx2 f32 -> (fwd_mask, bwd_mask) bool HxW [, fwd_u16, bwd_u16 HxWx3 uint16]."""
+    fwd, bwd = np.ascontiguousarray(fwd, np.float32), np.ascontiguousarray(bwd, np.float32)
+    if fwd.shape != bwd.shape or fwd.ndim != 3 or fwd.shape[2] != 2:
+        raise PrismaError("expected two HxWx2 float32 flow fields of the same size")
+    h, w = fwd.shape[:2]
+    fm, bm = np.empty((h, w), np.uint8), np.empty((h, w), np.uint8)
+    fu = np.empty((h, w, 3), np.uint16) if want_u16 else None
+    bu = np.empty((h, w, 3), np.uint16) if want_u16 else None
+    u16 = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_uint16))
+    check(lib().prisma_flow_masks(device, fptr(fwd), fptr(bwd), h, w, u8ptr(fm), u8ptr(bm), u16(fu), u16(bu)))
+    return (fm.view(bool), bm.view(bool), fu, bu) if want_u16 else (fm.view(bool), bm.view(bool))
+
+
+def write_flo(path, flow):
+    """Middlebury .flo (what common/io.py:175-198 writes): f32 magic 202021.25, i32 width, i32 height, f32 HxWx2."""
+    flow = np.ascontiguousarray(flow, np.float32)
+    with open(path, "wb") as f:
+        np.array([202021.25], np.float32).tofile(f)
+        np.array([flow.shape[1], flow.shape[0]], np.int32).tofile(f)
+        flow.tofile(f)
+
+
 class RaftFlowEngine:
     def __init__(self, state_dict=None, device=0, iterations=20, scale=0.75):
         self._h = C.c_void_p()

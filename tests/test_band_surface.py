@@ -67,3 +67,39 @@ def test_process_runs_band_into_prisma_folder(tmp_path):
     dists = [float(l) for l in open(os.path.join(folder, "flow_raft.csv"))]
     assert len(dists) == 3 and dists[-1] == 0.0 and all(d > 0 for d in dists[:2])
     assert meta["bands"]["flow_raft_bwd"] == {"url": "flow_raft_bwd.mp4"} and meta["bands"]["flow"] == flow
+
+
+@pytest.mark.gpu
+def test_flow_band_masks_flo_and_u16_png(tmp_path):
+    """--mask / --subpath / --subpath_mask outputs of bands/flow_raft.py (reference :60-66, common/flow.py:64-98)."""
+    import cv2
+    from oracle.frames import synthetic_frame
+    folder = tmp_path / "clip"
+    folder.mkdir()
+    src = str(folder / "rgba.mp4")
+    w = cv2.VideoWriter(src, cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
+    for t in range(3):
+        w.write(synthetic_frame(240, 320, t)[..., ::-1].copy())
+    w.release()
+    json.dump({"bands": {"rgba": {"url": "rgba.mp4"}}, "width": 320, "height": 240, "frames": 3, "fps": 24.0},
+              open(folder / "metadata.json", "w"))
+    rc = subprocess.call([sys.executable, os.path.join(ROOT, "bands", "flow_raft.py"), "-i", str(folder), "-b", "--mask",
+                          "--subpath", "flo", "--subpath_mask", "flow_png", "--seeded-weights", "--iterations", "6"])
+    assert rc == 0
+    meta = json.load(open(folder / "metadata.json"))
+    assert meta["bands"]["flow_raft_mask"] == {"url": "flow_raft_mask.mp4"}
+    assert meta["bands"]["flow_raft_mask_bwd"] == {"url": "flow_raft_mask_bwd.mp4"}
+    assert meta["bands"]["flow_raft"]["folder"].endswith("flo") and meta["bands"]["flow_raft_bwd"]["folder"].endswith("flo_bwd")
+    for name in ("flow_raft.mp4", "flow_raft_bwd.mp4", "flow_raft_mask.mp4", "flow_raft_mask_bwd.mp4"):
+        assert os.path.getsize(folder / name) > 0
+    for d in ("fwd", "bwd"):
+        flo = np.fromfile(folder / ("flo_" + d) / "0000.flo", np.float32)
+        assert flo[0] == np.float32(202021.25)
+        wh = flo[1:3].view(np.int32)
+        assert tuple(wh) == (240, 180) and flo.size == 3 + 240 * 180 * 2      # x0.75 working resolution
+        png = cv2.imread(str(folder / ("flow_png_" + d) / "0000.png"), cv2.IMREAD_UNCHANGED)
+        assert png.dtype == np.uint16 and png.shape == (180, 240, 3)
+        # the PNG payload is encode_flow of that same .flo (u16 truncation of 2^15 + 256 f)
+        f = flo[3:].reshape(180, 240, 2)
+        assert np.array_equal(png[..., 0], (2 ** 15 + f[..., 0] * 2 ** 8).astype(np.uint16))
+        assert len(os.listdir(folder / ("flo_" + d))) == 3

@@ -150,3 +150,35 @@ def test_corr_full_size_properties():
     assert np.abs(a.astype(np.float64).sum(axis=1) - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-2
     del bwd
     l.prisma_engine_destroy(h)
+
+
+def test_consistency_masks_and_u16_encode(golden_dir):
+    """compute_fwdbwd_mask + encode_flow vs the reference outputs in the fixture (random-weight flows: all-false masks)
+    and vs the oracle (cv2.remap) on a synthetic, mostly consistent flow pair where the mask is non-trivial."""
+    import ctypes as C
+    l = lib()
+
+    def run(fwd, bwd):
+        h, w = fwd.shape[:2]
+        fm = np.empty((h, w), np.uint8); bm = np.empty((h, w), np.uint8)
+        fu = np.empty((h, w, 3), np.uint16); bu = np.empty((h, w, 3), np.uint16)
+        check(l.prisma_flow_masks(0, fptr(fwd), fptr(bwd), h, w, u8ptr(fm), u8ptr(bm),
+                                  fu.ctypes.data_as(C.POINTER(C.c_uint16)), bu.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return fm.astype(bool), bm.astype(bool), fu, bu
+
+    g = np.load(os.path.join(golden_dir, "raft_240x320.npz"))
+    fm, bm, fu, bu = run(np.ascontiguousarray(g["flow_fwd"]), np.ascontiguousarray(g["flow_bwd"]))
+    assert np.array_equal(fm, g["fwd_mask"]) and np.array_equal(bm, g["bwd_mask"])
+    assert np.array_equal(fu, g["flow_u16"])
+    # synthetic pair: smooth forward flow, backward = -forward sampled at the target + a disturbance in one corner
+    H, W = 540, 960
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    fwd = np.stack([6 * np.sin(yy / 70) + 2.5, 4 * np.cos(xx / 90) - 1.25], -1).astype(np.float32)
+    bwd = (-fwd + 0.3 * np.sin(xx / 13)[..., None]).astype(np.float32)
+    bwd[:120, :200] += 7.0
+    fm, bm, fu, bu = run(fwd, bwd)
+    rfm, rbm = oraft.compute_fwdbwd_mask(fwd, bwd)
+    assert 0.05 < rfm.mean() < 0.999
+    assert (fm != rfm).mean() < 1e-4 and (bm != rbm).mean() < 1e-4   # remap rounding ties only
+    assert np.array_equal(fu[..., :2], oraft.encode_flow(fwd.copy(), fm)[..., :2])
+    assert np.array_equal(fu, oraft.encode_flow(fwd.copy(), fm))
