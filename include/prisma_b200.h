@@ -44,6 +44,15 @@ int prisma_depth_infer(prisma_engine* e, const uint8_t* rgb, int h, int w, float
  * tile count of every launch.  Results are identical to n calls of prisma_depth_infer.                     */
 int prisma_depth_infer_batch(prisma_engine* e, const uint8_t* rgb, int n, int h, int w, float* depth_out,
                              uint8_t* rgb_out, float* min_out, float* max_out);
+/* A chunk of the video loop (bands/depth_anything.py:203-221): n frames processed in passes of `pass_frames` (<=0: 4)
+ * with the upload of pass i+1 and the download of pass i-1 overlapping the compute of pass i (three streams, two staging
+ * slots in HBM).  Same results as n prisma_depth_infer calls.  Host buffers from prisma_host_alloc (pinned) make the
+ * copies true asynchronous DMA; pageable buffers work too (the driver stages them).                                  */
+int prisma_depth_infer_stream(prisma_engine* e, const uint8_t* rgb, int n, int h, int w, int pass_frames, float* depth_out,
+                              uint8_t* rgb_out, float* min_out, float* max_out);
+/* Page-locked host memory for frame buffers ("frame in pinned host memory", SURVEY section 8d timed region). */
+int prisma_host_alloc(size_t bytes, void** out);
+int prisma_host_free(void* p);
 /* Same computation with the n frames already resident in device memory and outputs left on the device
  * (bench.py's kernel-only leg): ms per pass (CUDA events on the engine stream) over `iters` passes.       */
 int prisma_depth_infer_resident(prisma_engine* e, int h, int w, int n, int iters, float* ms_per_iter);

@@ -137,6 +137,27 @@ int prisma_depth_infer_batch(prisma_engine* e, const uint8_t* rgb, int n, int h,
   return d ? d->infer(rgb, n, h, w, depth_out, rgb_out, min_out, max_out) : -1;
   API_GUARD_END
 }
+int prisma_depth_infer_stream(prisma_engine* e, const uint8_t* rgb, int n, int h, int w, int pass_frames, float* depth_out,
+                              uint8_t* rgb_out, float* min_out, float* max_out) {
+  API_GUARD_BEGIN
+  DepthEngine* d = as_depth(e);
+  return d ? d->infer_stream(rgb, n, h, w, pass_frames, depth_out, rgb_out, min_out, max_out) : -1;
+  API_GUARD_END
+}
+int prisma_host_alloc(size_t bytes, void** out) {
+  API_GUARD_BEGIN
+  PRISMA_CHECK(out != nullptr && bytes > 0, "bad argument");
+  *out = nullptr;
+  PRISMA_CUDA_OK(cudaMallocHost(out, bytes));
+  return 0;
+  API_GUARD_END
+}
+int prisma_host_free(void* p) {
+  API_GUARD_BEGIN
+  if (p) PRISMA_CUDA_OK(cudaFreeHost(p));
+  return 0;
+  API_GUARD_END
+}
 int prisma_depth_infer_resident(prisma_engine* e, int h, int w, int n, int iters, float* ms_per_iter) {
   API_GUARD_BEGIN
   DepthEngine* d = as_depth(e);
@@ -231,6 +252,11 @@ int prisma_debug_gemm(int device, const float* A, const float* W, const float* b
     ep.out_f32 = nullptr;
     ep.out_f16 = dH;
     ep.out_f16_ld = N;
+  }
+  if (act == -3) {  // micro-benchmark of the residual-stream epilogue: D += acc in place (fp32 read + write)
+    ep.res_f32 = dD;
+    ep.res_f32_ld = N;
+    PRISMA_CUDA_OK(cudaMemset(dD, 0, (size_t)M * N * 4));
   }
   GemmLaunch g;
   const int off[1] = {0};

@@ -46,6 +46,13 @@ DepthEngine::~DepthEngine() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  for (auto& sl : slot) {
+    cudaFree(sl.in); cudaFree(sl.rgb); cudaFree(sl.pred); cudaFree(sl.mm);
+    for (cudaEvent_t e : {sl.loaded, sl.consumed, sl.done, sl.drained}) if (e) cudaEventDestroy(e);
+  }
+  if (mm_host) cudaFreeHost(mm_host);
+  if (s_in) cudaStreamDestroy(s_in);
+  if (s_out) cudaStreamDestroy(s_out);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -563,6 +570,87 @@ int DepthEngine::infer(const uint8_t* rgb, int n, int H, int W, float* depth_out
   return 0;
 }
 
+int DepthEngine::ensure_stream_slots(int H, int W, int Bt, bool want_pred) {
+  if (!s_in) {
+    PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (auto& sl : slot)
+      for (cudaEvent_t* e : {&sl.loaded, &sl.consumed, &sl.done, &sl.drained})
+        PRISMA_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  const size_t px = (size_t)H * W;
+  if (slot_frames == (size_t)Bt && slot_bytes_frame == px && (slot_has_pred || !want_pred)) return 0;
+  PRISMA_CUDA_OK(cudaDeviceSynchronize());
+  for (auto& sl : slot) {
+    cudaFree(sl.in); cudaFree(sl.rgb); cudaFree(sl.pred); cudaFree(sl.mm);
+    sl.in = sl.rgb = nullptr; sl.pred = sl.mm = nullptr;
+    PRISMA_CUDA_OK(cudaMalloc(&sl.in, Bt * px * 3));
+    PRISMA_CUDA_OK(cudaMalloc(&sl.rgb, Bt * px * 3));
+    if (want_pred) PRISMA_CUDA_OK(cudaMalloc(&sl.pred, Bt * px * 4));
+    PRISMA_CUDA_OK(cudaMalloc(&sl.mm, Bt * 8));
+  }
+  slot_frames = Bt; slot_bytes_frame = px; slot_has_pred = want_pred;
+  return 0;
+}
+
+// The video loop of the band (bands/depth_anything.py:203-221) over a chunk of n frames.  Three streams: s_in uploads
+// pass i+1 into a staging slot while `stream` runs the graph of pass i and s_out drains the results of pass i-1; the
+// graph keeps its fixed buffers, staging is two device-to-device copies per pass (~25 MB, microseconds).
+// A ragged last pass runs the full-batch graph (frames are independent) and only its valid frames are copied out.
+int DepthEngine::infer_stream(const uint8_t* rgb, int n, int H, int W, int pass_frames, float* depth_out, uint8_t* rgb_out,
+                              float* min_out, float* max_out) {
+  PRISMA_CHECK(rgb != nullptr && H > 0 && W > 0 && n >= 1, "bad frame batch");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  const int Bt = pass_frames > 0 ? std::min(pass_frames, 64) : 4;
+  PRISMA_TRY(build_plan(H, W, Bt));
+  PRISMA_TRY(ensure_stream_slots(H, W, Bt, depth_out != nullptr));
+  if (mm_host_frames < (size_t)n) {
+    if (mm_host) cudaFreeHost(mm_host);
+    mm_host = nullptr; mm_host_frames = 0;
+    PRISMA_CUDA_OK(cudaMallocHost(&mm_host, (size_t)n * 8));
+    mm_host_frames = n;
+  }
+  const size_t px = (size_t)H * W;
+  const int passes = (n + Bt - 1) / Bt;
+  auto frames_of = [&](int i) { return std::min(Bt, n - i * Bt); };
+  auto drain = [&](int i) -> int {   // results of pass i -> host
+    StreamSlot& sl = slot[i & 1];
+    const int f = frames_of(i);
+    const size_t o = (size_t)i * Bt;
+    PRISMA_CUDA_OK(cudaStreamWaitEvent(s_out, sl.done, 0));
+    if (rgb_out) PRISMA_CUDA_OK(cudaMemcpyAsync(rgb_out + o * px * 3, sl.rgb, f * px * 3, cudaMemcpyDeviceToHost, s_out));
+    if (depth_out) PRISMA_CUDA_OK(cudaMemcpyAsync(depth_out + o * px, sl.pred, f * px * 4, cudaMemcpyDeviceToHost, s_out));
+    PRISMA_CUDA_OK(cudaMemcpyAsync(mm_host + o * 2, sl.mm, f * 8, cudaMemcpyDeviceToHost, s_out));
+    PRISMA_CUDA_OK(cudaEventRecord(sl.drained, s_out));
+    return 0;
+  };
+  for (int i = 0; i < passes; ++i) {
+    StreamSlot& sl = slot[i & 1];
+    const int f = frames_of(i);
+    if (i >= 2) PRISMA_CUDA_OK(cudaStreamWaitEvent(s_in, sl.consumed, 0));
+    PRISMA_CUDA_OK(cudaMemcpyAsync(sl.in, rgb + (size_t)i * Bt * px * 3, f * px * 3, cudaMemcpyHostToDevice, s_in));
+    PRISMA_CUDA_OK(cudaEventRecord(sl.loaded, s_in));
+    PRISMA_CUDA_OK(cudaStreamWaitEvent(stream, sl.loaded, 0));
+    PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, sl.in, f * px * 3, cudaMemcpyDeviceToDevice, stream));
+    PRISMA_CUDA_OK(cudaEventRecord(sl.consumed, stream));
+    PRISMA_TRY(run_steps(stream));
+    if (i >= 2) PRISMA_CUDA_OK(cudaStreamWaitEvent(stream, sl.drained, 0));
+    if (rgb_out) PRISMA_CUDA_OK(cudaMemcpyAsync(sl.rgb, b.rgb, f * px * 3, cudaMemcpyDeviceToDevice, stream));
+    if (depth_out) PRISMA_CUDA_OK(cudaMemcpyAsync(sl.pred, b.pred, f * px * 4, cudaMemcpyDeviceToDevice, stream));
+    PRISMA_CUDA_OK(cudaMemcpyAsync(sl.mm, b.minmax, f * 8, cudaMemcpyDeviceToDevice, stream));
+    PRISMA_CUDA_OK(cudaEventRecord(sl.done, stream));
+    if (i >= 1) PRISMA_TRY(drain(i - 1));
+  }
+  PRISMA_TRY(drain(passes - 1));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(s_out));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  for (int i = 0; i < n; ++i) {
+    if (min_out) min_out[i] = mm_host[2 * i];
+    if (max_out) max_out[i] = mm_host[2 * i + 1];
+  }
+  return 0;
+}
+
 // process_image path (bands/depth_anything.py:146-174): one frame, write_depth's PNG encoding of the prediction
 int DepthEngine::infer_image(const uint8_t* rgb, int H, int W, float* depth_out, uint8_t* png_rgb_out, float* min_out,
                              float* max_out) {
@@ -670,12 +758,26 @@ int DepthEngine::profile(int H, int W, int n, float* out8) {
   }
   PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
   for (int i = 0; i < 8; ++i) out8[i] = 0.f;
+  const bool verbose = getenv("PRISMA_DA_PROFILE") != nullptr;
+  std::vector<std::pair<std::string, std::pair<double, int>>> by_name;  // first-seen order
   for (size_t i = 0; i < steps.size(); ++i) {
     float ms = 0;
     PRISMA_CUDA_OK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
     out8[steps[i].group] += ms;
     out8[7] += ms;
+    if (verbose) {
+      // strip digits so the 24 blocks fold into one row per op
+      std::string key;
+      for (const char* c = steps[i].name; *c; ++c) if (*c < '0' || *c > '9') key.push_back(*c);
+      auto it = std::find_if(by_name.begin(), by_name.end(), [&](const auto& kv) { return kv.first == key; });
+      if (it == by_name.end()) by_name.push_back({key, {ms, 1}});
+      else { it->second.first += ms; it->second.second += 1; }
+    }
   }
+  if (verbose)
+    for (auto& kv : by_name)
+      fprintf(stderr, "[da-profile] %-28s x%-3d %8.3f ms  (%.1f us each)\n", kv.first.c_str(), kv.second.second,
+              kv.second.first, 1e3 * kv.second.first / kv.second.second);
   for (auto& e : ev) cudaEventDestroy(e);
   return 0;
 }

@@ -52,6 +52,9 @@ class DepthEngine {
   long long read_tap(const std::string& name, float* out, long long capacity);
   int profile(int H, int W, int n, float* out8);
   int build_plan(int H, int W, int batch);
+  // n frames in passes of `pass_frames`: H2D of pass i+1 and D2H of pass i-1 overlap the compute of pass i
+  int infer_stream(const uint8_t* rgb, int n, int H, int W, int pass_frames, float* depth_out, uint8_t* rgb_out,
+                   float* min_out, float* max_out);
 
   bool debug_taps = true;
   double work_linear = 0, work_attn = 0, work_head = 0;
@@ -78,6 +81,17 @@ class DepthEngine {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // streamed (double-buffered) clip path
+  struct StreamSlot {
+    uint8_t* in = nullptr; uint8_t* rgb = nullptr; float* pred = nullptr; float* mm = nullptr;
+    cudaEvent_t loaded = nullptr, consumed = nullptr, done = nullptr, drained = nullptr;
+  } slot[2];
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  float* mm_host = nullptr;  // pinned, 2 floats per frame
+  size_t mm_host_frames = 0;
+  int ensure_stream_slots(int H, int W, int Bt, bool want_pred);
+  size_t slot_frames = 0, slot_bytes_frame = 0;
+  bool slot_has_pred = false;
   cudaGraphExec_t graph_exec = nullptr;
   bool use_graph = true;
   bool finalized = false;

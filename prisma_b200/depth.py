@@ -28,6 +28,28 @@ def da_net_size(width, height):
     return constrain(sw * width), constrain(sh * height)
 
 
+class _Pinned:
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(lib().prisma_host_alloc(nbytes, C.byref(self.ptr)))
+
+    def __del__(self):
+        try:
+            lib().prisma_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory (prisma_host_alloc); freed when the array and its views are gone."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    owner = _Pinned(max(nbytes, 1))
+    buf = (C.c_uint8 * nbytes).from_address(owner.ptr.value)
+    buf._owner = owner
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
 class DepthAnythingEngine:
     """One engine per (GPU, band).  Not re-entrant; owns device memory, stream and weights."""
 
@@ -89,6 +111,22 @@ class DepthAnythingEngine:
         mins = np.empty(n, np.float32)
         maxs = np.empty(n, np.float32)
         check(lib().prisma_depth_infer_batch(self._h, u8ptr(x), n, h, w, fptr(pred), u8ptr(rgb), fptr(mins), fptr(maxs)))
+        return rgb, mins, maxs, pred
+
+    def infer_clip(self, frames, pass_frames=4, want_depth=False, want_rgb=True, out_rgb=None, out_depth=None):
+        """A chunk of the video loop: n frames [n,H,W,3] u8 in passes of `pass_frames`, copies overlapped with compute
+        (prisma_depth_infer_stream).  Returns what infer_batch returns.  `frames`/`out_*` from pinned_empty() make the
+        host<->device copies asynchronous DMA."""
+        x = frames if isinstance(frames, np.ndarray) else np.stack(frames)
+        if x.dtype != np.uint8 or x.ndim != 4 or x.shape[3] != 3 or not x.flags.c_contiguous:
+            raise PrismaError("expected a C-contiguous [n,H,W,3] uint8 RGB array")
+        n, h, w = x.shape[:3]
+        pred = (out_depth if out_depth is not None else np.empty((n, h, w), np.float32)) if want_depth else None
+        rgb = (out_rgb if out_rgb is not None else np.empty((n, h, w, 3), np.uint8)) if want_rgb else None
+        mins = np.empty(n, np.float32)
+        maxs = np.empty(n, np.float32)
+        check(lib().prisma_depth_infer_stream(self._h, u8ptr(x), n, h, w, pass_frames, fptr(pred), u8ptr(rgb), fptr(mins),
+                                              fptr(maxs)))
         return rgb, mins, maxs, pred
 
     def encode(self, prediction, flip=True):

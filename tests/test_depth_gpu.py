@@ -75,3 +75,18 @@ def test_batch_equals_single_frames(vits_engine):
         rgb, dmin, dmax, pred = vits_engine.infer_encoded(f, want_depth=True)
         assert np.array_equal(pred, pred_b[i]) and np.array_equal(rgb, rgb_b[i])
         assert np.float32(dmin) == mins_b[i] and np.float32(dmax) == maxs_b[i]
+
+
+def test_streamed_clip_equals_single_frames(vits_engine):
+    """prisma_depth_infer_stream (overlapped copies, ragged last pass, pinned and pageable buffers) == per-frame calls."""
+    from prisma_b200.depth import pinned_empty
+    frames = np.stack([synthetic_frame(240, 320, t) for t in range(7)])
+    single = [vits_engine.infer_encoded(f, want_depth=True) for f in frames]
+    pin_in = pinned_empty(frames.shape, np.uint8)
+    pin_in[...] = frames
+    pin_rgb = pinned_empty(frames.shape, np.uint8)
+    for src, out_rgb, pf in ((frames, None, 2), (pin_in, pin_rgb, 3), (pin_in, None, 4)):
+        rgb, mins, maxs, pred = vits_engine.infer_clip(src, pass_frames=pf, want_depth=True, out_rgb=out_rgb)
+        for i, (r1, mn, mx, p1) in enumerate(single):
+            assert np.array_equal(rgb[i], r1) and np.array_equal(pred[i], p1), (pf, i)
+            assert np.float32(mn) == mins[i] and np.float32(mx) == maxs[i]
