@@ -31,8 +31,11 @@ sys.path.insert(0, ROOT)
 
 H, W = 720, 1280
 ENCODER = os.environ.get("PRISMA_BENCH_ENCODER", "vitl")
-FRAMES_PER_STEP = 16
-BATCH = int(os.environ.get("PRISMA_BENCH_BATCH", "4"))  # frames per engine pass (frames are independent)
+# frames per engine pass (frames are independent).  12 frames make the attention grid (20 q-tiles x 16 heads x 12 = 3840
+# CTAs on 2 x 148 slots = 12.97 rounds) and the GEMM tile counts (230 row tiles) land just under whole waves; at 4 frames
+# both lose ~15-20 % to the last partial wave (measured)
+BATCH = int(os.environ.get("PRISMA_BENCH_BATCH", "12"))
+FRAMES_PER_STEP = int(os.environ.get("PRISMA_BENCH_FRAMES", str(4 * BATCH)))
 WORKLOAD = "synthetic 256-frame 720p video, depth_anything ViT-L, frames sharded per GPU (BASELINE configs[1])"
 
 

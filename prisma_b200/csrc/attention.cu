@@ -20,11 +20,12 @@ namespace prisma {
 
 constexpr int ATT_BQ = 128, ATT_BKV = 128, ATT_HD = 64;
 constexpr int ATT_THREADS = 320;  // TMA warp + MMA warp + 8 softmax warps (two per TMEM lane quarter: column halves)
+constexpr int ATT_SOFTMAX_WARP0 = 2;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
 // 7 tiles + barriers = 114,816 B: two CTAs (+1 KB reserved each) fit the 228 KB of an SM; no alignment slack, the
 // dynamic smem base is declared 1024-aligned (128B-swizzle atoms are 1 KB) and checked at kernel entry.
 // Q + 2 x (K, V) + barriers + row-max exchange; P never touches shared memory (it is the TMEM A operand of the PV MMA)
-constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 + 2) + 128 /*barriers*/ + 512 /*row-max exchange*/;
+constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 + 2) + 128 /*barriers*/ + 1024 /*row-max exchange, two parities*/;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -51,7 +52,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* pv_done = bars + 7;
   uint64_t* s_free = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  __half* s_xmax = reinterpret_cast<__half*>(smem + 5 * ATT_TILE_BYTES + 128);  // [2 halves][128 rows]
+  __half* s_xmax = reinterpret_cast<__half*>(smem + 5 * ATT_TILE_BYTES + 128);  // [2 parities][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = args.tokens, D = args.D;
@@ -130,16 +131,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         umma_commit(&kv_empty[st]);
       }
     }
-  } else {
+  } else if (warp >= ATT_SOFTMAX_WARP0) {
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;   // which 64 score columns (= which K-slab of P, which 32 columns of O)
+    const int half = (warp - ATT_SOFTMAX_WARP0) >> 2;   // which 64 score columns (= which K-slab of P, which 32 columns of O)
     const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
     float m_used = -INFINITY, l_part = 0.f;  // m_used: the max P / O are currently scaled by; l_part: my half's row sum
     const uint32_t bar_id = 1 + quarter;  // named barrier of the two warps that share this lane quarter
 #ifdef PRISMA_ATTN_PROFILE
-    long long t_wait = 0, t_p1 = 0, t_p2 = 0, t_tot = clock64();
+    long long t_wait = 0, t_p1 = 0, t_p2 = 0, t_ld = 0, t_max = 0, t_pvw = 0, t_exp = 0, t_tot = clock64();
     const bool prof = args.dbg != nullptr && threadIdx.x == 64 && blockIdx.x == 1 && blockIdx.y == 1;
 #define ATT_CLK(x) long long x = clock64()
 #else
@@ -157,23 +158,39 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       tmem_ld32(tmem_S + lane_sel + half * 64, v);
       tmem_ld32(tmem_S + lane_sel + half * 64 + 32, v + 32);
       tmem_ld_wait();
+      ATT_CLK(c1a_);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
       float mx = -INFINITY;
-      if (valid == 64) {
+      if (valid == 64) {  // four FMNMX3 chains
+        float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+        float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+        float m2 = fmax3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+        float m3 = fmax3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 12; i < 60; i += 8) {
+          m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+          m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+        }
+        m0 = fmax3(m0, __uint_as_float(v[60]), __uint_as_float(v[61]));
+        m1 = fmax3(m1, __uint_as_float(v[62]), __uint_as_float(v[63]));
+        mx = fmaxf(fmax3(m0, m1, m2), m3);
       } else {
 #pragma unroll
         for (int i = 0; i < 64; ++i) if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
       // ---- row max across the two halves: exchanged as fp16 rounded UP (both threads then use the identical value,
       // which is all the online softmax needs; >= the true max, so p <= 1 up to the lazy-rescale slack)
-      s_xmax[half * 128 + r] = __float2half_ru(fmaxf(mx, -60000.f));
+      ATT_CLK(c1b_);
+      // Buffers alternate with the tile parity, so one barrier per tile suffices: a buffer is rewritten two tiles later,
+      // after the barrier of the tile in between, which the partner only reaches once it has read this one.
+      __half* xm = s_xmax + (j & 1) * 256;
+      xm[half * 128 + r] = __float2half_ru(fmaxf(mx, -60000.f));
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      mx = fmaxf(__half2float(s_xmax[r]), __half2float(s_xmax[128 + r]));
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");  // both have read before the next tile overwrites
+      mx = fmaxf(__half2float(xm[r]), __half2float(xm[128 + r]));
       // ---- lazy rescale (identical decision in both warps of the quarter; each owns 32 columns of O)
       if (j == 0) {
         m_used = mx;
@@ -184,12 +201,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           const float alpha = ex2_approx((m_used - m_new) * LOG2E);  // 1 for rows that keep their max
           mbar_wait(pv_done, (j - 1) & 1);                            // no PV may be in flight on O
           tc_fence_after();
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_sel + half * 32, o);
-          tmem_ld_wait();
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {  // 16 columns at a time: keeps the S row in registers
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_sel + half * 32 + hh * 16, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tmem_O + lane_sel + half * 32, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_sel + half * 32 + hh * 16, o);
+          }
           tmem_st_wait();
           l_part *= alpha;
           m_used = m_new;
@@ -197,37 +217,42 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       }
       const float mscaled = m_used * LOG2E;
       ATT_CLK(c2_);
-      // ---- P(j-1) must have been consumed by PV(j-1) before the buffer is rewritten (issued a whole softmax ago)
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
       // ---- p = exp(s - m_used), partial row sum, P -> fp16 -> swizzled smem (K-slab `half` of the PV A operand)
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      uint32_t pk[32];  // my 64 probabilities as 32 fp16 pairs = 32 TMEM columns of the PV A operand
-      if (valid == 64) {
+      // two chunks of 32 probabilities -> 16 packed fp16 pairs -> 16 TMEM columns each (keeps the live set small)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float e[8];
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t pk[16];
+        if (valid == 64) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[c * 8 + i]), LOG2E, -mscaled));
-          sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
-          pk[c * 4 + 0] = pack_half2(e[0], e[1]); pk[c * 4 + 1] = pack_half2(e[2], e[3]);
-          pk[c * 4 + 2] = pack_half2(e[4], e[5]); pk[c * 4 + 3] = pack_half2(e[6], e[7]);
-        }
-      } else {
+          for (int c = 0; c < 4; ++c) {
+            float e[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {  // last KV tile only; fully unrolled so v[] stays in registers
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x = ex2_approx(fmaf(__uint_as_float(v[c * 8 + i]), LOG2E, -mscaled));
-            e[i] = (c * 8 + i < valid) ? x : 0.f;
+            for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[hh * 32 + c * 8 + i]), LOG2E, -mscaled));
+            sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
+            pk[c * 4 + 0] = pack_half2(e[0], e[1]); pk[c * 4 + 1] = pack_half2(e[2], e[3]);
+            pk[c * 4 + 2] = pack_half2(e[4], e[5]); pk[c * 4 + 3] = pack_half2(e[6], e[7]);
           }
-          sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
-          pk[c * 4 + 0] = pack_half2(e[0], e[1]); pk[c * 4 + 1] = pack_half2(e[2], e[3]);
-          pk[c * 4 + 2] = pack_half2(e[4], e[5]); pk[c * 4 + 3] = pack_half2(e[6], e[7]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // last KV tile only; fully unrolled so v[] stays in registers
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float x = ex2_approx(fmaf(__uint_as_float(v[hh * 32 + c * 8 + i]), LOG2E, -mscaled));
+              e[i] = (hh * 32 + c * 8 + i < valid) ? x : 0.f;
+            }
+            sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
+            pk[c * 4 + 0] = pack_half2(e[0], e[1]); pk[c * 4 + 1] = pack_half2(e[2], e[3]);
+            pk[c * 4 + 2] = pack_half2(e[4], e[5]); pk[c * 4 + 3] = pack_half2(e[6], e[7]);
+          }
         }
+        // P(j-1) must have been consumed by PV(j-1) before the buffer is rewritten (issued a whole softmax ago)
+        if (hh == 0 && j > 0) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }
+        tmem_st16(tmem_P + lane_sel + half * 32 + hh * 16, pk);
       }
       l_part += (sum0 + sum1) + (sum2 + sum3);
-      tmem_st32(tmem_P + lane_sel + half * 32, pk);
+      ATT_CLK(c2b_);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -235,15 +260,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #ifdef PRISMA_ATTN_PROFILE
       long long c3_ = clock64();
       t_wait += c1_ - c0_; t_p1 += c2_ - c1_; t_p2 += c3_ - c2_;
+      t_ld += c1a_ - c1_; t_max += c1b_ - c1a_; t_exp += c2b_ - c2_;
 #endif
     }
 #ifdef PRISMA_ATTN_PROFILE
-    if (prof) { args.dbg[0] = t_wait; args.dbg[1] = t_p1; args.dbg[2] = t_p2; args.dbg[3] = clock64() - t_tot; args.dbg[4] = n_kv; }
+    if (prof) { args.dbg[0] = t_wait; args.dbg[1] = t_p1; args.dbg[2] = t_p2; args.dbg[3] = clock64() - t_tot; args.dbg[4] = n_kv;
+                args.dbg[5] = t_ld; args.dbg[6] = t_max; args.dbg[7] = t_pvw; args.dbg[8] = t_exp; }
 #endif
     // ---- O is complete once the last PV retires; the K stages are then idle and carry the row-sum exchange
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
-    float* s_l = reinterpret_cast<float*>(sK);  // [2 halves][128 rows]; the K stages are idle by now
+    float* s_l = reinterpret_cast<float*>(sK);  // [2 parities][2 halves][128 rows]; the K stages are idle by now
     s_l[half * 128 + r] = l_part;
     uint32_t ov[32];
     tmem_ld32(tmem_O + lane_sel + half * 32, ov);

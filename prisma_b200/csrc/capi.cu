@@ -333,13 +333,15 @@ int prisma_debug_attention(int device, const float* qkv, float* out, int T, int 
   PRISMA_CUDA_OK(cudaMemcpy(dq, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   AttnLaunch a;
   PRISMA_TRY(attention_prepare(&a, dq, dO, 1, T, heads, D));
-  long long* dbg = sc.alloc<long long>(8);
+  long long* dbg = sc.alloc<long long>(16);
   if (getenv("PRISMA_ATTN_PROF")) a.args.dbg = dbg;
   PRISMA_TRY(timed(0, iters > 0 ? iters : 1, ms_out, [&]() { return attention_run(a, 0); }));
   if (a.args.dbg) {
-    long long h[8];
+    long long h[16];
     PRISMA_CUDA_OK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
-    printf("attention cycles (one softmax warp, CTA (1,1)): wait_S %lld  pass1 %lld  pass2 %lld  total %lld  tiles %lld\n", h[0], h[1], h[2], h[3], h[4]);
+    printf("attention cycles (one softmax warp, CTA (1,1)): wait_S %lld  pass1 %lld  pass2 %lld  total %lld  tiles %lld\n"
+           "   pass1: tmem_ld %lld  max %lld  exchange+rescale %lld | pass2: pv_wait %lld  exp %lld  st+arrive %lld\n",
+           h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[1] - h[5] - h[6], h[7], h[8], h[2] - h[7] - h[8]);
   }
   std::vector<__half> ho((size_t)T * D);
   PRISMA_CUDA_OK(cudaMemcpy(ho.data(), dO, ho.size() * 2, cudaMemcpyDeviceToHost));

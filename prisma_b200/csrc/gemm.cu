@@ -85,6 +85,10 @@ int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols,
   out->args.N = N;
   out->args.taps = taps;
   out->args.kchunks = kchunks;
+  {
+    static const char* r = getenv("PRISMA_GEMM_RASTER");  // "m" / "n": force (experiments)
+    out->args.raster_n = r ? (r[0] == 'n') : (M >= N);
+  }
   for (int t = 0; t < GEMM_MAX_TAPS; ++t) out->args.tap_off[t] = t < taps ? tap_off[t] : 0;
   out->args.ep = ep;
   PRISMA_TRY(make_tmap_2d_f16(&out->tmA, A, (uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)a_pitch, 64, GEMM_BM));

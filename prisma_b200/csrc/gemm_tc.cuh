@@ -77,6 +77,8 @@ struct GemmArgs {
   int taps;
   int kchunks;  // 64-wide K blocks per tap
   int tap_off[GEMM_MAX_TAPS];
+  int raster_n;  // 1: consecutive tiles walk N first (the CTAs of a wave share few A row panels and all of W: A is read
+                 // from HBM once when M >> N); 0: M first
   GemmEpilogue ep;
 };
 
@@ -229,8 +231,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = group; tile < num_tiles; tile += num_groups) {
-        const int m0 = (tile % tiles_m) * TILE_M + rank * GEMM_BM;
-        const int n0 = (tile / tiles_m) * BN + rank * (BN / CG);
+        const int tm = args.raster_n ? tile / tiles_n : tile % tiles_m;
+        const int tn = args.raster_n ? tile % tiles_n : tile / tiles_m;
+        const int m0 = tm * TILE_M + rank * GEMM_BM;
+        const int n0 = tn * BN + rank * (BN / CG);
         int tap = 0, chunk = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -290,8 +294,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (tile % tiles_m) * TILE_M + rank * GEMM_BM;
-      const int n0 = (tile / tiles_m) * BN;
+      const int tm = args.raster_n ? tile / tiles_n : tile % tiles_m;
+      const int tn = args.raster_n ? tile % tiles_n : tile / tiles_m;
+      const int m0 = tm * TILE_M + rank * GEMM_BM;
+      const int n0 = tn * BN;
       const int m = m0 + quarter * 32 + lane;
       // ---- row mapping of "my" accumulator row (lane == row inside this warp's 32-row slab)
       int valid = m < args.M;
