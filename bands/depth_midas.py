@@ -1,13 +1,15 @@
 #!/usr/bin/env python3
-"""depth_anything band on the B200 engine -- drop-in for the reference's bands/depth_anything.py.
+"""depth_midas band on the B200 engine -- drop-in for the reference's bands/depth_midas.py.
 
-Same plugin surface: module constants/globals, init_model(), infer(img, normalize),
-process_image(args), process_video(args), the CLI flags of bands/depth_anything.py:255-265, the outputs
-(<band>.mp4|png, <band>_min.csv, <band>_max.csv, optional <sub>/%05d.npy) and the metadata.json keys
-(:155-166,241-251).  The model call and the numpy encode are replaced by libprisma_b200.so; there is no CPU path.
+Same plugin surface: BAND / MODELS_VERSIONS, init_model(model_version), infer(img, model_version, normalize),
+process_image(args), process_video(args), the CLI flags of bands/depth_midas.py:182-192, the outputs (depth_midas.mp4|png,
+depth_midas_min.csv, depth_midas_max.csv, optional <sub>/%05d.npy|png) and the metadata.json keys (:87-99,163-174).
+The hub transform, the DPT_Large forward, the bicubic(align_corners=True) resize and the heat encode run in
+libprisma_b200.so; there is no CPU path.
 
-Additions: --weights (a DPT_DINOv2 state_dict: torch .pth/.pt or .npz), --seeded-weights (offline test weights),
---device, --batch.  `--metric indoor|outdoor` (ZoeDepth head) is a SURVEY section 8f "next" row and raises here.
+Built: --model midas3 (the default: DPT_Large + default_transform).  midas2 / midas2-small (the ResNeXt-101 MiDaS v2.1
+network) and midas3-small (DPT_Large behind the 256-pixel small_transform) raise instead of falling back.
+Additions: --weights (the upstream dpt_large_384.pt state_dict or .npz), --seeded-weights, --device.
 """
 import argparse
 import os
@@ -16,13 +18,14 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bands.common.meta import get_target, get_url, is_video, load_metadata, write_metadata  # noqa: E402
 from bands.common.depth_loop import process_depth_video  # noqa: E402
 from bands.common.media import open_rgb, write_rgb  # noqa: E402
+from bands.common.meta import get_target, get_url, is_video, load_metadata, write_metadata  # noqa: E402
 
-BAND = "depth_anything"
+BAND = "depth_midas"
 DEVICE = 0
-WEIGHTS = "models/depth_anything_{}14.pth"
+MODELS_VERSIONS = ["midas2-small", "midas2", "midas3-small", "midas3"]
+WEIGHTS = "models/dpt_large_384.pt"
 
 model = None
 data = None
@@ -31,10 +34,9 @@ args = None
 
 def _load_state_dict(a):
     if a.seeded_weights:
-        # seeded random weights (no checkpoint is reachable offline)
-        from prisma_b200.seeded_weights import make_da_weights
-        return make_da_weights(a.encoder, 0)
-    path = a.weights or WEIGHTS.format(a.encoder)
+        from prisma_b200.seeded_weights import make_midas_weights
+        return make_midas_weights("dpt_large", 0)
+    path = a.weights or WEIGHTS
     if path.endswith(".npz"):
         return dict(np.load(path))
     import torch
@@ -42,29 +44,31 @@ def _load_state_dict(a):
     return sd.get("state_dict", sd)
 
 
-def init_model():
-    """reference :48-76 (relative-depth branch): build the engine and upload the converted weights."""
+def init_model(model_version="midas3"):
+    """reference :29-46."""
     global model
-    from prisma_b200.depth import DepthAnythingEngine
-    model = DepthAnythingEngine(args.encoder, _load_state_dict(args), device=args.device)
+    if model_version != "midas3":
+        raise NotImplementedError("only --model midas3 (DPT_Large, default transform) is built; %s is not" % model_version)
+    from prisma_b200.depth import MidasEngine
+    model = MidasEngine(_load_state_dict(args), device=args.device if args else DEVICE)
     return model
 
 
-def infer(img, normalize=False):
-    """HxWx3 u8 RGB -> HxW f32 (reference :100-143)."""
+def infer(img, model_version="midas3", normalize=False):
+    """HxWx3 u8 RGB -> HxW f32 (reference :49-75)."""
     if model is None:
-        init_model()
-    return model.infer(img, normalize=normalize)
+        init_model(model_version)
+    return model.infer(np.asarray(img), normalize=normalize)
 
 
 def process_image(a):
     img = open_rgb(a.input)
     rgb, dmin, dmax, pred = model.infer_image(img, want_depth=True)  # write_depth's PNG encoding (io.py:138-166)
     if a.npy:
-        np.save(os.path.splitext(a.output)[0] + ".npy", pred)
+        np.save(os.path.join(os.path.dirname(a.output), BAND + ".npy"), pred)
     write_rgb(a.output, rgb)
     if data:
-        data["bands"][BAND]["values"] = {"min": {"type": "float", "value": dmin}, "max": {"type": "float", "value": dmax}}
+        data["bands"][BAND]["values"] = {"min": {"value": dmin, "type": "float"}, "max": {"value": dmax, "type": "float"}}
 
 
 def process_video(a):
@@ -78,9 +82,8 @@ def build_parser():
     p.add_argument("--npy", "-n", help="Save numpy data", action="store_true")
     p.add_argument("--ply", "-p", help="Create point cloud PLY", action="store_true")
     p.add_argument("--subpath", "-d", help="subpath to frames", type=str, default="")
-    p.add_argument("--encoder", type=str, default="vitl", choices=["vits", "vitb", "vitl"])
-    p.add_argument("--metric", help="Use a metric model", type=str, default="none", choices=["none", "indoor", "outdoor"])
-    p.add_argument("--weights", type=str, default="", help="DPT_DINOv2 state_dict (.pth/.npz)")
+    p.add_argument("--model", type=str, choices=MODELS_VERSIONS, default="midas3")
+    p.add_argument("--weights", type=str, default="", help="DPTDepthModel state_dict (.pt/.npz)")
     p.add_argument("--seeded-weights", action="store_true", help="seeded random weights (offline testing)")
     p.add_argument("--device", type=int, default=DEVICE)
     return p
@@ -89,8 +92,6 @@ def build_parser():
 def main(argv=None):
     global args, data
     args = build_parser().parse_args(argv)
-    if args.metric != "none":
-        raise NotImplementedError("--metric indoor|outdoor (ZoeDepth head) is not built yet (SURVEY.md section 8f row 1)")
     if args.ply:
         print("--ply is outside the engine's scope (optional export, SURVEY.md section 2); ignored")
     data = load_metadata(args.input)
@@ -99,7 +100,7 @@ def main(argv=None):
         args.output = get_target(args.input, data, band=BAND, target=args.output, force_extension="png")
     elif args.output == "":
         args.output = os.path.join(os.path.dirname(args.input), BAND + os.path.splitext(args.input)[1])
-    init_model()
+    init_model(args.model)
     if is_video(args.output):
         process_video(args)
     else:

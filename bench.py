@@ -188,6 +188,22 @@ def raft_extras(device, peaks):
     }
 
 
+def midas_extras(device):
+    """Third workload: depth_midas (MiDaS v3 DPT_Large, BASELINE north_star band) on the same synthetic 720p frames,
+    12-frame passes, frames resident in HBM."""
+    from prisma_b200.depth import MidasEngine
+    from prisma_b200.seeded_weights import make_midas_weights
+    eng = MidasEngine(make_midas_weights("dpt_large", 0), device=device)
+    eng.time_resident(H, W, 2, BATCH)
+    ms = eng.time_resident(H, W, 4, BATCH)
+    w = eng.work(H, W, BATCH)
+    eng.close()
+    flop = w["linear_flop"] + w["attention_flop"] + w["head_flop"]
+    return {"workload": "synthetic 720p frames, depth_midas DPT_Large (384x672 net input), frames resident",
+            "frames_per_s_device": BATCH / (ms * 1e-3), "ms_per_pass": ms, "frames_per_pass": BATCH,
+            "tflops": flop / (ms * 1e-3) / 1e12, "launches_per_pass": w["launches"]}
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     from prisma_b200.depth import DepthAnythingEngine
@@ -272,6 +288,7 @@ def run_b200(args, rank, local_rank, world):
         }
         if world == 1:
             out["extra"] = raft_extras(local_rank, peaks)
+            out["extra"]["depth_midas_720p"] = midas_extras(local_rank)
         if world == 1 and not args.no_cpu:
             cores = cpu_threads()
             fps, dt = cpu_baseline_frames(3, cores)

@@ -17,8 +17,12 @@
 namespace prisma {
 
 // ------------------------------------------------------------------------------------------------ helpers
-struct DaCfg { int D, depth, heads, F, oc[4]; };
+struct DaCfg { int D, depth, heads, F, oc[4]; int family = FAMILY_DA; int hooks[4] = {0, 0, 0, 0}; };
 static bool da_cfg(const std::string& enc, DaCfg* c) {
+  // MiDaS v3 DPT (hubconf DPT_Large -> DPTDepthModel(backbone="vitl16_384"): hooks [5,11,17,23], features 256,
+  // reassemble channels [256,512,1024,1024]); "dpt_tiny" is a test-size twin of the same graph
+  if (enc == "dpt_large") { *c = {1024, 24, 16, 256, {256, 512, 1024, 1024}, FAMILY_MIDAS, {5, 11, 17, 23}}; return true; }
+  if (enc == "dpt_tiny") { *c = {384, 8, 6, 64, {48, 96, 192, 384}, FAMILY_MIDAS, {1, 3, 5, 7}}; return true; }
   if (enc == "vits") { *c = {384, 12, 6, 64, {48, 96, 192, 384}}; return true; }
   if (enc == "vitb") { *c = {768, 12, 12, 128, {96, 192, 384, 768}}; return true; }
   if (enc == "vitl") { *c = {1024, 24, 16, 256, {256, 512, 1024, 1024}}; return true; }
@@ -37,6 +41,15 @@ void da_net_size(int W, int H, int* wn, int* hn) {
   };
   *hn = constrain(sh * H);
   *wn = constrain(sw * W);
+}
+
+// MiDaS transform (hubconf default_transform; the Resize class is the one vendored in d_anything/util/transform.py:
+// get_size :111-166 with resize_method="minimal", keep_aspect_ratio, multiple of 32, target 384 x 384).
+void midas_net_size(int W, int H, int* wn, int* hn) {
+  double sh = 384.0 / H, sw = 384.0 / W;
+  if (fabs(1.0 - sw) < fabs(1.0 - sh)) sh = sw; else sw = sh;
+  *hn = (int)(nearbyint(sh * H / 32.0) * 32.0);
+  *wn = (int)(nearbyint(sw * W / 32.0) * 32.0);
 }
 
 DepthEngine::~DepthEngine() {
@@ -68,10 +81,12 @@ static int dev_alloc(std::vector<void*>& pool, T** out, size_t n, bool zero = tr
 
 int DepthEngine::init(const std::string& enc, int dev) {
   DaCfg c;
-  PRISMA_CHECK(da_cfg(enc, &c), "unknown encoder '" + enc + "' (vits|vitb|vitl)");
+  PRISMA_CHECK(da_cfg(enc, &c), "unknown encoder '" + enc + "' (vits|vitb|vitl|dpt_large)");
   encoder = enc;
   D = c.D; depth = c.depth; heads = c.heads; F = c.F;
-  for (int i = 0; i < 4; ++i) oc[i] = c.oc[i];
+  for (int i = 0; i < 4; ++i) { oc[i] = c.oc[i]; hooks[i] = c.hooks[i]; }
+  family = c.family;
+  if (family == FAMILY_MIDAS) { patch = 16; pos_grid = 24; }
   device = dev;
   int n = 0;
   PRISMA_CUDA_OK(cudaGetDeviceCount(&n));
@@ -176,14 +191,20 @@ int DepthEngine::up_convT(const std::string& name, int Cin, int Cout, int s, __h
 int DepthEngine::finalize() {
   PRISMA_CHECK(!finalized, "finalize called twice");
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  const std::string p = "pretrained.";
+  const bool midas = family == FAMILY_MIDAS;
+  const std::string p = midas ? "pretrained.model." : "pretrained.";
+  const int n_pos = pos_grid * pos_grid + 1, pk = 3 * patch * patch, pkpad = round_up(pk, 64);
   PRISMA_TRY(up_f32(p + "cls_token", {1, 1, D}, &w.cls));
-  PRISMA_TRY(up_f32(p + "pos_embed", {1, 1370, D}, &w.pos));
+  PRISMA_TRY(up_f32(p + "pos_embed", {1, n_pos, D}, &w.pos));
+  if (midas) {
+    host_pos = get(p + "pos_embed", {1, n_pos, D})->data;
+    host_cls = get(p + "cls_token", {1, 1, D})->data;
+  }
   {
-    const HostTensor* t = get(p + "patch_embed.proj.weight", {D, 3, 14, 14});
+    const HostTensor* t = get(p + "patch_embed.proj.weight", {D, 3, patch, patch});
     if (!t) return -1;
-    PRISMA_TRY(up_matrix(allocs, &w.patch_w, D, 640, [&](int n, __half* row) {
-      for (int k = 0; k < 588; ++k) row[k] = __float2half_rn(t->data[(size_t)n * 588 + k]);
+    PRISMA_TRY(up_matrix(allocs, &w.patch_w, D, pkpad, [&](int n, __half* row) {
+      for (int k = 0; k < pk; ++k) row[k] = __float2half_rn(t->data[(size_t)n * pk + k]);
     }));
     PRISMA_TRY(up_f32(p + "patch_embed.proj.bias", {D}, &w.patch_b));
   }
@@ -198,21 +219,33 @@ int DepthEngine::finalize() {
     PRISMA_TRY(up_f32(b + "attn.qkv.bias", {3 * D}, &k.qkv_b, qscale, D));
     PRISMA_TRY(up_linear(b + "attn.proj.weight", D, D, &k.proj_w));
     PRISMA_TRY(up_f32(b + "attn.proj.bias", {D}, &k.proj_b));
-    PRISMA_TRY(up_f32(b + "ls1.gamma", {D}, &k.g1));
+    k.g1 = k.g2 = nullptr;  // timm ViT blocks of MiDaS have no LayerScale
+    if (!midas) PRISMA_TRY(up_f32(b + "ls1.gamma", {D}, &k.g1));
     PRISMA_TRY(up_f32(b + "norm2.weight", {D}, &k.n2w));
     PRISMA_TRY(up_f32(b + "norm2.bias", {D}, &k.n2b));
     PRISMA_TRY(up_linear(b + "mlp.fc1.weight", 4 * D, D, &k.fc1_w));
     PRISMA_TRY(up_f32(b + "mlp.fc1.bias", {4 * D}, &k.fc1_b));
     PRISMA_TRY(up_linear(b + "mlp.fc2.weight", D, 4 * D, &k.fc2_w));
     PRISMA_TRY(up_f32(b + "mlp.fc2.bias", {D}, &k.fc2_b));
-    PRISMA_TRY(up_f32(b + "ls2.gamma", {D}, &k.g2));
+    if (!midas) PRISMA_TRY(up_f32(b + "ls2.gamma", {D}, &k.g2));
   }
-  PRISMA_TRY(up_f32(p + "norm.weight", {D}, &w.nw));
-  PRISMA_TRY(up_f32(p + "norm.bias", {D}, &w.nb));
+  w.nw = w.nb = nullptr;  // MiDaS hooks the raw block outputs; the final norm only feeds the unused `glob`
+  if (!midas) {
+    PRISMA_TRY(up_f32(p + "norm.weight", {D}, &w.nw));
+    PRISMA_TRY(up_f32(p + "norm.bias", {D}, &w.nb));
+  }
 
+  // head tensor names: Depth-Anything DPTHead (d_anything/dpt.py:39-100) / MiDaS DPT (midas/backbones/vit.py
+  // act_postprocessN = [readout, Transpose, Unflatten, Conv1x1, resize], midas/dpt_depth.py scratch.*)
   const std::string h = "depth_head.";
+  auto pp = [&](int i) { return "pretrained.act_postprocess" + std::to_string(i + 1) + "."; };
+  if (midas)
+    for (int i = 0; i < 4; ++i) {
+      PRISMA_TRY(up_linear(pp(i) + "0.project.0.weight", D, 2 * D, &w.ro_w[i]));
+      PRISMA_TRY(up_f32(pp(i) + "0.project.0.bias", {D}, &w.ro_b[i]));
+    }
   for (int i = 0; i < 4; ++i) {
-    const std::string n = h + "projects." + std::to_string(i);
+    const std::string n = midas ? pp(i) + "3" : h + "projects." + std::to_string(i);
     const HostTensor* t = get(n + ".weight", {oc[i], D, 1, 1});
     if (!t) return -1;
     const int K = D, N = oc[i];
@@ -221,11 +254,13 @@ int DepthEngine::finalize() {
     }));
     PRISMA_TRY(up_f32(n + ".bias", {oc[i]}, &w.proj_b[i]));
   }
-  PRISMA_TRY(up_convT(h + "resize_layers.0", oc[0], oc[0], 4, &w.rs0_w, &w.rs0_b));
-  PRISMA_TRY(up_convT(h + "resize_layers.1", oc[1], oc[1], 2, &w.rs1_w, &w.rs1_b));
-  PRISMA_TRY(up_conv(h + "resize_layers.3.weight", oc[3], oc[3], 3, 3, &w.rs3_w));
-  PRISMA_TRY(up_f32(h + "resize_layers.3.bias", {oc[3]}, &w.rs3_b));
-  const std::string s = h + "scratch.";
+  PRISMA_TRY(up_convT(midas ? pp(0) + "4" : h + "resize_layers.0", oc[0], oc[0], 4, &w.rs0_w, &w.rs0_b));
+  PRISMA_TRY(up_convT(midas ? pp(1) + "4" : h + "resize_layers.1", oc[1], oc[1], 2, &w.rs1_w, &w.rs1_b));
+  PRISMA_TRY(up_conv((midas ? pp(3) + "4" : h + "resize_layers.3") + ".weight", oc[3], oc[3], 3, 3, &w.rs3_w));
+  PRISMA_TRY(up_f32((midas ? pp(3) + "4" : h + "resize_layers.3") + ".bias", {oc[3]}, &w.rs3_b));
+  const std::string s = midas ? "scratch." : h + "scratch.";
+  const std::string o1 = s + (midas ? "output_conv.0" : "output_conv1"), o2 = s + (midas ? "output_conv.2" : "output_conv2.0"),
+                    o3 = s + (midas ? "output_conv.4" : "output_conv2.2");
   for (int i = 0; i < 4; ++i)
     PRISMA_TRY(up_conv(s + "layer" + std::to_string(i + 1) + "_rn.weight", F, oc[i], 3, 3, &w.rn_w[i]));
   for (int i = 0; i < 4; ++i) {
@@ -248,13 +283,13 @@ int DepthEngine::finalize() {
       PRISMA_TRY(up_f32(ru + "conv2.bias", {F}, &k.c2_b[u]));
     }
   }
-  PRISMA_TRY(up_conv(s + "output_conv1.weight", F / 2, F, 3, 3, &w.oc1_w));
-  PRISMA_TRY(up_f32(s + "output_conv1.bias", {F / 2}, &w.oc1_b));
-  PRISMA_TRY(up_conv(s + "output_conv2.0.weight", 32, F / 2, 3, 3, &w.oc2_w));
-  PRISMA_TRY(up_f32(s + "output_conv2.0.bias", {32}, &w.oc2_b));
-  PRISMA_TRY(up_f32(s + "output_conv2.2.weight", {1, 32, 1, 1}, &w.oc3_w));
+  PRISMA_TRY(up_conv(o1 + ".weight", F / 2, F, 3, 3, &w.oc1_w));
+  PRISMA_TRY(up_f32(o1 + ".bias", {F / 2}, &w.oc1_b));
+  PRISMA_TRY(up_conv(o2 + ".weight", 32, F / 2, 3, 3, &w.oc2_w));
+  PRISMA_TRY(up_f32(o2 + ".bias", {32}, &w.oc2_b));
+  PRISMA_TRY(up_f32(o3 + ".weight", {1, 32, 1, 1}, &w.oc3_w));
   {
-    const HostTensor* t = get(s + "output_conv2.2.bias", {1});
+    const HostTensor* t = get(o3 + ".bias", {1});
     if (!t) return -1;
     w.oc3_b = t->data[0];
   }
@@ -323,8 +358,11 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
   work_linear = work_attn = work_head = 0;
   plan_H = plan_W = 0;
 
-  da_net_size(W, H, &wn, &hn);
-  ph = hn / 14; pw = wn / 14;
+  const bool midas = family == FAMILY_MIDAS;
+  if (midas) midas_net_size(W, H, &wn, &hn); else da_net_size(W, H, &wn, &hn);
+  PRISMA_CHECK(hn >= patch * 2 && wn >= patch * 2, "frame too small for the network input");
+  ph = hn / patch; pw = wn / patch;
+  const int pkpad = round_up(3 * patch * patch, 64);
   const int P = ph * pw;
   T = P + 1;
   const int BP = Bt * P, BT = Bt * T;
@@ -333,7 +371,8 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
   // ---- frame-level buffers
   PRISMA_TRY(dev_alloc(plan_allocs, &b.img, (size_t)Bt * H * W * 3));
   PRISMA_TRY(dev_alloc(plan_allocs, &b.net_in, (size_t)Bt * 3 * hn * wn));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b.patches, (size_t)BP * 640));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.patches, (size_t)BP * pkpad));
+  if (midas) PRISMA_TRY(dev_alloc(plan_allocs, &ro_cat, (size_t)BP * 2 * D));
   PRISMA_TRY(dev_alloc(plan_allocs, &b.pos, (size_t)BT * D));
   PRISMA_TRY(dev_alloc(plan_allocs, &b.x, (size_t)BT * D));
   PRISMA_TRY(dev_alloc(plan_allocs, &b.tokens_tap, (size_t)BT * D));
@@ -349,7 +388,33 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
   PRISMA_TRY(dev_alloc(plan_allocs, &b.minmax, 2 * Bt));
 
   // pos-embed for this resolution (constant per resolution): computed once, here
-  PRISMA_TRY(da_pos_embed(w.pos, w.cls, 37, D, ph, pw, b.pos, stream));
+  if (!midas) {
+    PRISMA_TRY(da_pos_embed(w.pos, w.cls, 37, D, ph, pw, b.pos, stream));
+  } else {
+    // _resize_pos_embed (midas/backbones/vit.py): F.interpolate(grid, size=(ph, pw), mode="bilinear"), align_corners
+    // False: src = (dst + 0.5) * in/out - 0.5 clamped at 0, fp32; row 0 = cls + pos[0]
+    std::vector<float> pe((size_t)T * D);
+    const int S = pos_grid;
+    for (int d = 0; d < D; ++d) pe[d] = host_cls[d] + host_pos[d];
+    const float scy = (float)S / (float)ph, scx = (float)S / (float)pw;
+    for (int oy = 0; oy < ph; ++oy) {
+      const float ry = std::max(scy * (oy + 0.5f) - 0.5f, 0.f);
+      const int y0 = (int)ry, y1 = y0 + (y0 < S - 1 ? 1 : 0);
+      const float ly = ry - y0, hy = 1.f - ly;
+      for (int ox = 0; ox < pw; ++ox) {
+        const float rx = std::max(scx * (ox + 0.5f) - 0.5f, 0.f);
+        const int x0 = (int)rx, x1 = x0 + (x0 < S - 1 ? 1 : 0);
+        const float lx = rx - x0, hx = 1.f - lx;
+        const float* g = host_pos.data() + D;  // grid part
+        float* o = pe.data() + (size_t)(1 + oy * pw + ox) * D;
+        for (int d = 0; d < D; ++d)
+          o[d] = hy * (hx * g[(size_t)(y0 * S + x0) * D + d] + lx * g[(size_t)(y0 * S + x1) * D + d]) +
+                 ly * (hx * g[(size_t)(y1 * S + x0) * D + d] + lx * g[(size_t)(y1 * S + x1) * D + d]);
+      }
+    }
+    PRISMA_CUDA_OK(cudaMemcpyAsync(b.pos, pe.data(), pe.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  }
   for (int i = 1; i < Bt; ++i)  // one copy per image so that residual rows and destination rows coincide
     PRISMA_CUDA_OK(cudaMemcpyAsync(b.pos + (size_t)i * T * D, b.pos, (size_t)T * D * sizeof(float), cudaMemcpyDeviceToDevice, stream));
 
@@ -359,17 +424,18 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
     const int hn_ = hn, wn_ = wn;
     add(G_PRE, "da_preprocess", [=](cudaStream_t s) {
       for (int i = 0; i < Bt; ++i)
-        PRISMA_TRY(da_preprocess(img + (size_t)i * H * W * 3, H, W, net + (size_t)i * 3 * hn_ * wn_, hn_, wn_, s));
+        PRISMA_TRY(da_preprocess(img + (size_t)i * H * W * 3, H, W, net + (size_t)i * 3 * hn_ * wn_, hn_, wn_, s, midas));
       return 0;
     });
-    add(G_PRE, "patchify", [=](cudaStream_t s) { return da_patchify(net, Bt, hn_, wn_, pat, 640, s); });
+    const int patch_ = patch;
+    add(G_PRE, "patchify", [=](cudaStream_t s) { return da_patchify(net, Bt, hn_, wn_, pat, pkpad, s, patch_); });
     GemmEpilogue ep;
     ep.bias = w.patch_b;
     ep.row_map = ROW_TOKSKIP; ep.in_w = P;       // patch rows b*P+p -> token rows b*T+1+p
     ep.res_f32 = b.pos; ep.res_f32_ld = D;       // + pos-embed of the same token row
     ep.out_f32 = b.x; ep.out_f32_ld = D;
-    PRISMA_TRY(add_gemm(G_LINEAR, "patch_embed", b.patches, BP, 640, 640, w.patch_w, BP, D, 1, zero_off, ep,
-                        2.0 * BP * D * 588.0));
+    PRISMA_TRY(add_gemm(G_LINEAR, "patch_embed", b.patches, BP, pkpad, pkpad, w.patch_w, BP, D, 1, zero_off, ep,
+                        2.0 * BP * D * 3.0 * patch * patch));
     float* x = b.x; const float* pos = b.pos; const int D_ = D, T_ = T;
     add(G_PRE, "cls_rows", [=](cudaStream_t s) {  // token 0 of every image = cls + pos[0]
       PRISMA_CUDA_OK(cudaMemcpy2DAsync(x, (size_t)T_ * D_ * sizeof(float), pos, (size_t)T_ * D_ * sizeof(float),
@@ -402,17 +468,28 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
       PRISMA_TRY(add_gemm(G_LINEAR, "fc1", b.ln, BT, D, D, k.fc1_w, BT, 4 * D, 1, zero_off, ep, 2.0 * BT * 4.0 * D * D)); }
     { GemmEpilogue ep; ep.bias = k.fc2_b; ep.gamma = k.g2; ep.res_f32 = b.x; ep.res_f32_ld = D; ep.out_f32 = b.x; ep.out_f32_ld = D;
       PRISMA_TRY(add_gemm(G_LINEAR, "fc2", b.hid, BT, 4 * D, 4 * D, k.fc2_w, BT, D, 1, zero_off, ep, 2.0 * BT * 4.0 * D * D)); }
-    if (i >= depth - 4) {
+    if (!midas && i >= depth - 4) {
       __half* f = b.feat[i - (depth - 4)];
       const float* nw = w.nw; const float* nb = w.nb;
       // final norm of the tapped block, patch tokens only (use_clstoken=False, dpt.py:110-111): dense [B*P][D]
       add(G_LN, "ln_out", [=](cudaStream_t s) { return layernorm_f16(x, nw, nb, f, BP, D_, 1e-6f, s, P); });
     }
+    if (midas)
+      for (int hk = 0; hk < 4; ++hk)
+        if (hooks[hk] == i) {
+          // forward hook on blocks[i] (raw block output) -> ProjectReadout: GELU(Linear([token | cls]))
+          __half* cat = ro_cat; const int Tt = T;
+          add(G_LN, "readout_concat", [=](cudaStream_t s) { return readout_concat_f16(x, Bt, Tt, D_, cat, s); });
+          GemmEpilogue ep; ep.bias = w.ro_b[hk]; ep.act = 1; ep.out_f16 = b.feat[hk]; ep.out_f16_ld = D;
+          PRISMA_TRY(add_gemm(G_HEAD, "readout_project", ro_cat, BP, 2 * D, 2 * D, w.ro_w[hk], BP, D, 1, zero_off, ep,
+                              2.0 * BP * 2.0 * D * D));
+        }
   }
 
   // ---- DPT head (dpt.py:103-136), all maps zero-bordered NHWC fp16
   PMap L[4], R[4], Rr[4];
   const int h4 = (ph - 1) / 2 + 1, w4 = (pw - 1) / 2 + 1;
+  PRISMA_CHECK(!midas || (ph % 2 == 0 && pw % 2 == 0), "MiDaS input sides are multiples of 32");
   PRISMA_TRY(new_map(&L[0], 4 * ph, 4 * pw, oc[0]));
   PRISMA_TRY(new_map(&L[1], 2 * ph, 2 * pw, oc[1]));
   PRISMA_TRY(new_map(&L[2], ph, pw, oc[2]));
@@ -507,12 +584,22 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
   {
     const float* d = b.depth; float* pred = b.pred; uint8_t* rgb = b.rgb; uint32_t* mm = b.mm; float* mmo = b.minmax;
     const int hn_ = hn, wn_ = wn, sms = num_sms;
-    add(G_POST, "depth_postprocess", [=](cudaStream_t s) {
-      for (int i = 0; i < Bt; ++i)
-        PRISMA_TRY(depth_postprocess(d + (size_t)i * hn_ * wn_, hn_, wn_, H, W, 1, pred + (size_t)i * H * W,
-                                     rgb + (size_t)i * H * W * 3, mm + 2 * i, mmo + 2 * i, sms, s));
-      return 0;
-    });
+    if (!midas)
+      add(G_POST, "depth_postprocess", [=](cudaStream_t s) {
+        for (int i = 0; i < Bt; ++i)
+          PRISMA_TRY(depth_postprocess(d + (size_t)i * hn_ * wn_, hn_, wn_, H, W, 1, pred + (size_t)i * H * W,
+                                       rgb + (size_t)i * H * W * 3, mm + 2 * i, mmo + 2 * i, sms, s));
+        return 0;
+      });
+    else  // depth_midas.py:58-63 bicubic(align_corners=True) to the frame size, then the video loop's encode (:141-146)
+      add(G_POST, "depth_postprocess", [=](cudaStream_t s) {
+        for (int i = 0; i < Bt; ++i) {
+          PRISMA_TRY(upsample_bicubic_ac_f32(d + (size_t)i * hn_ * wn_, hn_, wn_, pred + (size_t)i * H * W, H, W, sms, s));
+          PRISMA_TRY(depth_encode_only(pred + (size_t)i * H * W, H, W, 1 | 2, rgb + (size_t)i * H * W * 3, mm + 2 * i,
+                                       mmo + 2 * i, sms, s));
+        }
+        return 0;
+      });
   }
   taps["net_input"] = {b.net_in, Bt * 3, hn * wn, 1, 0};
   taps["tokens"] = {b.tokens_tap, BT, D, 1, 0};

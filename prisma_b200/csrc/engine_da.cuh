@@ -27,6 +27,8 @@ struct DaWeights {
   __half *rs0_w, *rs1_w, *rs3_w; float *rs0_b, *rs1_b, *rs3_b;
   __half* rn_w[4];
   RefineW ref[4];
+  __half* ro_w[4] = {nullptr, nullptr, nullptr, nullptr};  // MiDaS "project" readout Linear(2D -> D)
+  float* ro_b[4] = {nullptr, nullptr, nullptr, nullptr};
   __half *oc1_w, *oc2_w; float *oc1_b, *oc2_b, *oc3_w; float oc3_b;
 };
 struct DaBuffers {
@@ -38,6 +40,8 @@ struct Step { int group; const char* name; std::function<int(cudaStream_t)> fn; 
 struct PMap;
 
 void da_net_size(int W, int H, int* wn, int* hn);
+void midas_net_size(int W, int H, int* wn, int* hn);
+enum DepthFamily { FAMILY_DA = 0, FAMILY_MIDAS = 1 };
 
 class DepthEngine {
  public:
@@ -78,6 +82,10 @@ class DepthEngine {
 
   std::string encoder;
   int D = 0, depth = 0, heads = 0, F = 0, oc[4] = {0, 0, 0, 0};
+  // family switches: Depth-Anything (DINOv2 ViT/14 + DPT head) or MiDaS DPT (timm ViT/16, "project" readout, hooks)
+  int family = FAMILY_DA, patch = 14, pos_grid = 37, hooks[4] = {0, 0, 0, 0};
+  std::vector<float> host_pos, host_cls;  // MiDaS: pos-embed resized on the host per resolution (bilinear)
+  __half* ro_cat = nullptr;               // MiDaS: [B*P][2D] readout operand
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

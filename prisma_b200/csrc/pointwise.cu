@@ -21,8 +21,10 @@ __device__ __forceinline__ void cv_cubic_coeffs(float x, float* c) {
   c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c[0]), c[1]), c[2]);
 }
 
+struct MeanStd { double mean[3], stdv[3]; };
+
 __global__ void k_da_preprocess(const uint8_t* __restrict__ img, int H, int W, float* __restrict__ out, int h, int w,
-                                double scale_x, double scale_y) {
+                                double scale_x, double scale_y, MeanStd ms) {
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   const int oy = blockIdx.y;
   if (ox >= w) return;
@@ -41,8 +43,6 @@ __global__ void k_da_preprocess(const uint8_t* __restrict__ img, int H, int W, f
     xs[k] = min(max(sx - 1 + k, 0), W - 1);
     ys[k] = min(max(sy - 1 + k, 0), H - 1);
   }
-  const double mean[3] = {0.485, 0.456, 0.406};
-  const double stdv[3] = {0.229, 0.224, 0.225};
   double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -65,15 +65,17 @@ __global__ void k_da_preprocess(const uint8_t* __restrict__ img, int H, int W, f
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c)
-    out[((size_t)c * h + oy) * w + ox] = (float)__ddiv_rn(__dsub_rn(acc[c], mean[c]), stdv[c]);
+    out[((size_t)c * h + oy) * w + ox] = (float)__ddiv_rn(__dsub_rn(acc[c], ms.mean[c]), ms.stdv[c]);
 }
 
-int da_preprocess(const uint8_t* img, int H, int W, float* out, int h, int w, cudaStream_t s) {
+int da_preprocess(const uint8_t* img, int H, int W, float* out, int h, int w, cudaStream_t s, int midas_norm) {
   dim3 block(128), grid(ceil_div(w, 128), h);
   // cv::resize: inv_scale = dsize/ssize ; scale = 1./inv_scale
   const double scale_x = 1.0 / ((double)w / (double)W);
   const double scale_y = 1.0 / ((double)h / (double)H);
-  k_da_preprocess<<<grid, block, 0, s>>>(img, H, W, out, h, w, scale_x, scale_y);
+  // NormalizeImage: ImageNet statistics (depth_anything.py:72) or mean = std = 0.5 (MiDaS hubconf default_transform)
+  const MeanStd ms = midas_norm ? MeanStd{{0.5, 0.5, 0.5}, {0.5, 0.5, 0.5}} : MeanStd{{0.485, 0.456, 0.406}, {0.229, 0.224, 0.225}};
+  k_da_preprocess<<<grid, block, 0, s>>>(img, H, W, out, h, w, scale_x, scale_y, ms);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -83,7 +85,7 @@ int da_preprocess(const uint8_t* img, int H, int W, float* out, int h, int w, cu
 // = im2col of the 14x14/stride-14 patch-embed conv (dinov2/layers/patch_embed.py:66,76-78).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_patchify(const float* __restrict__ x_all, int h, int w, __half* __restrict__ out, int pw, int kpad,
-                           int per_img) {
+                           int per_img, int ps) {
   const int img = blockIdx.x / per_img;
   const int p = blockIdx.x;             // output row (image-major)
   const int pl = p - img * per_img;     // patch index inside the image
@@ -91,16 +93,16 @@ __global__ void k_patchify(const float* __restrict__ x_all, int h, int w, __half
   const int py = pl / pw, px = pl - py * pw;
   for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
     float v = 0.f;
-    if (k < 588) {
-      const int c = k / 196, r = k - c * 196, ky = r / 14, kx = r - ky * 14;
-      v = x[((size_t)c * h + py * 14 + ky) * w + px * 14 + kx];
+    if (k < 3 * ps * ps) {
+      const int c = k / (ps * ps), r = k - c * ps * ps, ky = r / ps, kx = r - ky * ps;
+      v = x[((size_t)c * h + py * ps + ky) * w + px * ps + kx];
     }
     out[(size_t)p * kpad + k] = __float2half_rn(v);
   }
 }
-int da_patchify(const float* x, int batch, int h, int w, __half* out, int kpad, cudaStream_t s) {
-  const int ph = h / 14, pw = w / 14;
-  k_patchify<<<batch * ph * pw, 160, 0, s>>>(x, h, w, out, pw, kpad, ph * pw);
+int da_patchify(const float* x, int batch, int h, int w, __half* out, int kpad, cudaStream_t s, int patch) {
+  const int ph = h / patch, pw = w / patch;
+  k_patchify<<<batch * ph * pw, 160, 0, s>>>(x, h, w, out, pw, kpad, ph * pw, patch);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -337,14 +339,22 @@ __global__ void k_depth_encode(const float* __restrict__ d, int hn, int wn, cons
     if (pred_in) p = pred_in[i];
     else { const int oy = (int)(i / W), ox = (int)(i - (long long)oy * W); p = bilinear_af(d, hn, wn, sy, sx, oy, ox); }
     float x = __fdiv_rn(__fsub_rn(p, dmin), range);
-    if (flip) x = __fsub_rn(1.0f, x);
+    if (flip & 1) x = __fsub_rn(1.0f, x);
     // heat_to_rgb(h) = hue_to_rgb((1-h)*0.65); rgb = hue*6 + {0,4,2}
-    const double hue = __dmul_rn(__dsub_rn(1.0, (double)x), 0.65);
-    const double hue6 = __dmul_rn(hue, 6.0);
     uint8_t* o = rgb + i * 3;
-    o[0] = hue_channel_u8(hue6, 0.0);
-    o[1] = hue_channel_u8(hue6, 4.0);
-    o[2] = hue_channel_u8(hue6, 2.0);
+    if (flip & 2) {
+      // depth_midas.py:144 passes the f32 array: (1-h)*0.65, *6 and +{4,2} round in f32 before the f64 rgb array
+      const float hue6 = __fmul_rn(__fmul_rn(__fsub_rn(1.0f, x), 0.65f), 6.0f);
+      o[0] = hue_channel_u8((double)hue6, 0.0);
+      o[1] = hue_channel_u8((double)__fadd_rn(hue6, 4.0f), 0.0);
+      o[2] = hue_channel_u8((double)__fadd_rn(hue6, 2.0f), 0.0);
+    } else {  // depth_anything.py:219 casts to f64 first
+      const double hue = __dmul_rn(__dsub_rn(1.0, (double)x), 0.65);
+      const double hue6 = __dmul_rn(hue, 6.0);
+      o[0] = hue_channel_u8(hue6, 0.0);
+      o[1] = hue_channel_u8(hue6, 4.0);
+      o[2] = hue_channel_u8(hue6, 2.0);
+    }
   }
 }
 
@@ -473,6 +483,64 @@ __global__ void k_f32_to_f16(const float* __restrict__ a, __half* __restrict__ b
 }
 int f32_to_f16(const float* a, __half* b, long long n, cudaStream_t s) {
   k_f32_to_f16<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, b, n);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// MiDaS DPT "project" readout (midas/backbones/utils.py ProjectReadout): A[b*P + p] = [ x[b][1+p] | x[b][0] ] as fp16,
+// the operand of Linear(2D -> D) + GELU.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_readout_concat(const float* __restrict__ x, int T, int D, __half* __restrict__ out) {
+  const int P = T - 1;
+  const int row = blockIdx.x, b = row / P, p = row - b * P;
+  const float* tok = x + ((size_t)b * T + 1 + p) * D;
+  const float* cls = x + (size_t)b * T * D;
+  __half* o = out + (size_t)row * 2 * D;
+  for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+    const float4 a = *reinterpret_cast<const float4*>(tok + d);
+    const float4 c = *reinterpret_cast<const float4*>(cls + d);
+    *reinterpret_cast<uint2*>(o + d) = make_uint2(pack_half2(a.x, a.y), pack_half2(a.z, a.w));
+    *reinterpret_cast<uint2*>(o + D + d) = make_uint2(pack_half2(c.x, c.y), pack_half2(c.z, c.w));
+  }
+}
+int readout_concat_f16(const float* x, int batch, int T, int D, __half* out, cudaStream_t s) {
+  k_readout_concat<<<batch * (T - 1), 128, 0, s>>>(x, T, D, out);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// F.interpolate(mode="bicubic", align_corners=True) of one f32 map (bands/depth_midas.py:58-63): torch's
+// upsample_bicubic2d: src = dst * (in-1)/(out-1), A = -0.75, clamped taps, fp32 accumulation, rows then columns.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cubic_interp1d_t(float x0, float x1, float x2, float x3, float t) {
+  const float A = -0.75f;
+  return x0 * cubic2(t + 1.f, A) + x1 * cubic1(t, A) + x2 * cubic1(1.f - t, A) + x3 * cubic2(2.f - t, A);
+}
+__global__ void k_upsample_bicubic_ac(const float* __restrict__ in, int ih, int iw, float* __restrict__ out, int oh, int ow,
+                                      float sy, float sx) {
+  const long long total = (long long)oh * ow;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int oy = (int)(i / ow), ox = (int)(i - (long long)oy * ow);
+    const float ry = sy * oy, rx = sx * ox;
+    const int iy = (int)floorf(ry), ix = (int)floorf(rx);
+    const float ty = ry - iy, tx = rx - ix;
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* row = in + (size_t)min(max(iy - 1 + k, 0), ih - 1) * iw;
+      r[k] = cubic_interp1d_t(row[min(max(ix - 1, 0), iw - 1)], row[min(max(ix, 0), iw - 1)], row[min(max(ix + 1, 0), iw - 1)],
+                              row[min(max(ix + 2, 0), iw - 1)], tx);
+    }
+    out[i] = cubic_interp1d_t(r[0], r[1], r[2], r[3], ty);
+  }
+}
+int upsample_bicubic_ac_f32(const float* in, int ih, int iw, float* out, int oh, int ow, int num_sms, cudaStream_t s) {
+  const float sy = oh > 1 ? (float)(ih - 1) / (float)(oh - 1) : 0.f;
+  const float sx = ow > 1 ? (float)(iw - 1) / (float)(ow - 1) : 0.f;
+  k_upsample_bicubic_ac<<<num_sms * 8, 256, 0, s>>>(in, ih, iw, out, oh, ow, sy, sx);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -192,3 +192,12 @@ class DepthAnythingEngine:
             self.close()
         except Exception:
             pass
+
+
+class MidasEngine(DepthAnythingEngine):
+    """depth_midas band (bands/depth_midas.py): MiDaS v3 DPT_Large on the same engine -- timm ViT-L/16 encoder with the
+    "project" readout at blocks 5/11/17/23, the DPT RefineNet head, bicubic(align_corners=True) to the frame size.
+    `state_dict` is the upstream DPTDepthModel checkpoint (dpt_large_384.pt) as is."""
+
+    def __init__(self, state_dict=None, device=0, variant="dpt_large"):
+        super().__init__(variant, state_dict, device)

@@ -109,6 +109,74 @@ def make_da_weights(encoder="vits", seed=0):
     return sd
 
 
+MIDAS_CONFIGS = {
+    # MiDaS v3 DPT_Large (hub "intel-isl/MiDaS": DPTDepthModel(backbone="vitl16_384"); timm vit_large_patch16_384):
+    # hooks/features/reassemble channels from midas/dpt_depth.py + midas/backbones/vit.py (un-vendored)
+    "dpt_large": dict(dim=1024, depth=24, heads=16, hooks=[5, 11, 17, 23], features=256, out_channels=[256, 512, 1024, 1024]),
+    # test-size twin of the same graph (CPU oracle in seconds)
+    "dpt_tiny": dict(dim=384, depth=8, heads=6, hooks=[1, 3, 5, 7], features=64, out_channels=[48, 96, 192, 384]),
+}
+
+
+def make_midas_weights(variant="dpt_large", seed=0):
+    """state_dict of MiDaS DPTDepthModel with the upstream tensor names (pretrained.model.* = timm ViT/16,
+    pretrained.act_postprocessN.* = readout / 1x1 / resize, scratch.* = RefineNet fusion + output head)."""
+    c = MIDAS_CONFIGS[variant]
+    D, depth, F, oc = c["dim"], c["depth"], c["features"], c["out_channels"]
+    sd = {}
+
+    def lin(name, out_f, in_f, std=0.02):
+        sd[name + ".weight"] = _normal(name + ".weight", seed, (out_f, in_f), std)
+        sd[name + ".bias"] = _normal(name + ".bias", seed, (out_f,), 0.01)
+
+    def conv(name, out_c, in_c, kh, kw, bias=True, transpose=False):
+        fan_in = (out_c if transpose else in_c) * kh * kw
+        b = (1.0 / fan_in) ** 0.5
+        shape = (in_c, out_c, kh, kw) if transpose else (out_c, in_c, kh, kw)
+        sd[name + ".weight"] = _uniform(name + ".weight", seed, shape, -b, b)
+        if bias:
+            sd[name + ".bias"] = _uniform(name + ".bias", seed, (out_c,), -b, b)
+
+    def ln(name, dim):
+        sd[name + ".weight"] = _normal(name + ".weight", seed, (dim,), 0.1, 1.0)
+        sd[name + ".bias"] = _normal(name + ".bias", seed, (dim,), 0.05)
+
+    p = "pretrained.model."
+    sd[p + "cls_token"] = _normal(p + "cls_token", seed, (1, 1, D), 0.02)
+    sd[p + "pos_embed"] = _normal(p + "pos_embed", seed, (1, 24 * 24 + 1, D), 0.02)
+    sd[p + "patch_embed.proj.weight"] = _normal(p + "patch_embed.proj.weight", seed, (D, 3, 16, 16), 0.02)
+    sd[p + "patch_embed.proj.bias"] = _normal(p + "patch_embed.proj.bias", seed, (D,), 0.02)
+    for i in range(depth):
+        b = f"{p}blocks.{i}."
+        ln(b + "norm1", D)
+        lin(b + "attn.qkv", 3 * D, D, std=0.04)
+        lin(b + "attn.proj", D, D)
+        ln(b + "norm2", D)
+        lin(b + "mlp.fc1", 4 * D, D)
+        lin(b + "mlp.fc2", D, 4 * D)
+    ln(p + "norm", D)
+    for i, c_out in enumerate(oc):
+        a = f"pretrained.act_postprocess{i + 1}."
+        lin(a + "0.project.0", D, 2 * D)
+        conv(a + "3", c_out, D, 1, 1)
+    conv("pretrained.act_postprocess1.4", oc[0], oc[0], 4, 4, transpose=True)
+    conv("pretrained.act_postprocess2.4", oc[1], oc[1], 2, 2, transpose=True)
+    conv("pretrained.act_postprocess4.4", oc[3], oc[3], 3, 3)
+    for i in range(4):
+        conv(f"scratch.layer{i + 1}_rn", F, oc[i], 3, 3, bias=False)
+    for i in range(1, 5):
+        r = f"scratch.refinenet{i}."
+        conv(r + "out_conv", F, F, 1, 1)
+        for u in (1, 2):
+            conv(f"{r}resConfUnit{u}.conv1", F, F, 3, 3)
+            conv(f"{r}resConfUnit{u}.conv2", F, F, 3, 3)
+    conv("scratch.output_conv.0", F // 2, F, 3, 3)
+    conv("scratch.output_conv.2", 32, F // 2, 3, 3)
+    conv("scratch.output_conv.4", 1, 32, 1, 1)
+    sd["scratch.output_conv.4.bias"] = torch.full((1,), 0.25)  # positive map, see make_da_weights
+    return sd
+
+
 def make_raft_weights(seed=0):
     """state_dict of RAFT(args) (bands/raft/raft.py:24-57), seeded.
 

@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 from bands.common.meta import add_band, create_metadata, is_video, set_default_band, write_metadata  # noqa: E402
 from bands.common.media import VideoReader, open_rgb  # noqa: E402
 
-ACCELERATED = {"depth_anything", "flow_raft"}  # mask_mmdet / depth_midas: next rows of SURVEY.md section 8
+ACCELERATED = {"depth_anything", "depth_midas", "flow_raft"}  # mask_mmdet: next row of SURVEY.md section 8
 
 
 def run(band, folder, extra=()):

@@ -103,3 +103,42 @@ def test_flow_band_masks_flo_and_u16_png(tmp_path):
         f = flo[3:].reshape(180, 240, 2)
         assert np.array_equal(png[..., 0], (2 ** 15 + f[..., 0] * 2 ** 8).astype(np.uint16))
         assert len(os.listdir(folder / ("flo_" + d))) == 3
+
+
+def test_midas_band_cli_matches_reference_flags():
+    sys.path.insert(0, ROOT)
+    from bands import depth_midas as band
+    a = band.build_parser().parse_args(["-i", "x.mp4", "-o", "y.mp4", "-n", "-d", "frames", "--model", "midas3"])
+    assert (a.input, a.output, a.npy, a.subpath, a.model) == ("x.mp4", "y.mp4", True, "frames", "midas3")
+    assert band.BAND == "depth_midas" and band.MODELS_VERSIONS == ["midas2-small", "midas2", "midas3-small", "midas3"]
+    with pytest.raises(NotImplementedError):
+        band.init_model("midas2")
+
+
+@pytest.mark.gpu
+def test_midas_band_writes_video_csv_and_frames(tmp_path):
+    import cv2
+    from oracle.frames import synthetic_frame
+    folder = tmp_path / "clip"
+    folder.mkdir()
+    w = cv2.VideoWriter(str(folder / "rgba.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
+    for t in range(3):
+        w.write(synthetic_frame(240, 320, t)[..., ::-1].copy())
+    w.release()
+    json.dump({"bands": {"rgba": {"url": "rgba.mp4"}}, "width": 320, "height": 240, "frames": 3, "fps": 24.0},
+              open(folder / "metadata.json", "w"))
+    rc = subprocess.call([sys.executable, os.path.join(ROOT, "bands", "depth_midas.py"), "-i", str(folder), "-n", "-d",
+                          "depth_midas_frames", "--seeded-weights"])
+    assert rc == 0
+    meta = json.load(open(folder / "metadata.json"))
+    band = meta["bands"]["depth_midas"]
+    assert band["url"] == "depth_midas.mp4" and band["folder"] == "depth_midas_frames"
+    assert band["values"] == {"min": {"type": "float", "url": "depth_midas_min.csv"},
+                              "max": {"type": "float", "url": "depth_midas_max.csv"}}
+    mins = [float(l) for l in open(folder / "depth_midas_min.csv")]
+    maxs = [float(l) for l in open(folder / "depth_midas_max.csv")]
+    assert len(mins) == 3 and all(b > a for a, b in zip(mins, maxs))
+    frames = sorted(os.listdir(folder / "depth_midas_frames"))
+    assert frames == ["00000.npy", "00000.png", "00001.npy", "00001.png", "00002.npy", "00002.png"]
+    pred = np.load(folder / "depth_midas_frames" / "00001.npy")
+    assert pred.shape == (240, 320) and pred.dtype == np.float32 and np.float32(pred.min()) == np.float32(mins[1])
