@@ -188,6 +188,16 @@ def raft_extras(device, peaks):
     }
 
 
+def measured_traffic():
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        return t["traffic_bytes_per_launch"], t
+    except Exception:
+        return None, None
+
+
 def midas_extras(device):
     """Third workload: depth_midas (MiDaS v3 DPT_Large, BASELINE north_star band) on the same synthetic 720p frames,
     12-frame passes, frames resident in HBM."""
@@ -281,7 +291,8 @@ def run_b200(args, rank, local_rank, world):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (encoder linears: qkv/proj/fc1/fc2/patch-embed)",
                          "achieved": lin_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": lin_tf / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["src"],
+                         "frac": lin_tf / peaks["tf_sustained"], "traffic": measured_traffic()[0],
+                         "traffic_detail": measured_traffic()[1], "peak_source": peaks["src"],
                          "groups_ms_per_pass": prof,
                          "attention_tflops": att_tf, "head_tflops": head_tf,
                          "frame_flop": (work["linear_flop"] + work["attention_flop"] + work["head_flop"]) / BATCH},
