@@ -1,0 +1,121 @@
+#!/usr/bin/env python3
+"""mask band (mask_mmdet) on the B200 engine -- drop-in for the reference's bands/mask_mmdet.py.
+
+Same plugin surface: BAND / CLASSES / CONFIDENCE_THRESHOLD constants, init_model(), process_image(args),
+process_video(args), the CLI flags of bands/mask_mmdet.py:165-174 (-i -o -c --sdf --subpath), the outputs (mask.png|mp4,
+optional <subpath>/%05d.png with the inverted mask for COLMAP) and the metadata.json keys (bands.mask.{url,ids,folder},
+:159-161).  SOLOv2 (inference_detector) and the union of the instance masks run in libprisma_b200.so; there is no CPU path.
+
+Not built: --sdf (snowy.generate_sdf) raises instead of falling back.
+Additions: --weights (the mmdet checkpoint .pth or .npz), --seeded-weights, --device.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bands.common.media import VideoReader, VideoWriter, create_folder, open_rgb, write_rgb  # noqa: E402
+from bands.common.meta import get_target, get_url, is_video, load_metadata, write_metadata  # noqa: E402
+
+BAND = "mask"
+DEVICE = 0
+CONFIG = "models/solov2_r101_fpn_3x_coco.py"
+MODEL = "models/solov2_r101_fpn_3x_coco_20220511_095119-c559a076.pth"
+CLASSES = ['person', 'bird', 'cat', 'dog', 'horse', 'sheep', 'cow', 'elephant', 'bear', 'zebra', 'giraffe']
+CONFIDENCE_THRESHOLD = 0.5
+
+model = None
+data = None
+args = None
+
+
+def _load_state_dict(a):
+    if a.seeded_weights:
+        from prisma_b200.seeded_weights import make_solo_weights
+        return make_solo_weights("r101", 0)
+    path = a.weights or MODEL
+    if path.endswith(".npz"):
+        return dict(np.load(path))
+    import torch
+    sd = torch.load(path, map_location="cpu")
+    return sd.get("state_dict", sd)  # mmcv checkpoints: {state_dict, meta{CLASSES}} (apis/inference.py:46-48)
+
+
+def init_model():
+    """reference :38-41."""
+    global model
+    from prisma_b200.mask import SoloV2Engine
+    model = SoloV2Engine(_load_state_dict(args), device=args.device)
+    return model
+
+
+def frame_masks(rgb, confidence):
+    """The loop body of process_image / process_video (:113-146): HxWx3 u8 mask frame (the union on every channel)."""
+    u = model.infer(rgb, confidence=confidence)["union"]
+    return np.repeat(u[..., None], 3, axis=-1)
+
+
+def process_image(a):
+    masks = frame_masks(open_rgb(a.input), a.confidence)
+    write_rgb(a.output, masks)
+    if data is not None:
+        data["bands"][BAND] = {"url": os.path.basename(a.output), "ids": CLASSES}
+
+
+def process_video(a):
+    reader = VideoReader(a.input)
+    out = VideoWriter(reader.width, reader.height, reader.get_avg_fps(), a.output)
+    folder = os.path.dirname(a.output)
+    sub = ""
+    if a.subpath != "":
+        sub = os.path.join(folder, a.subpath)
+        create_folder(sub)
+    for f, frame in enumerate(reader):
+        masks = frame_masks(frame, a.confidence)
+        if sub:  # COLMAP wants black-on-white masks (:148-149)
+            write_rgb(os.path.join(sub, "{:05d}.png".format(f)), 255 - masks)
+        out.write(masks)
+    out.close()
+    if data is not None:
+        data["bands"][BAND] = {"url": os.path.basename(a.output), "ids": CLASSES}
+        if a.subpath != "":
+            data["bands"][BAND]["folder"] = a.subpath
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--input", "-i", help="input", type=str, required=True)
+    p.add_argument("--output", "-o", help="output", type=str, default="")
+    p.add_argument("--confidence", "-c", help="confidence threshold", type=float, default=CONFIDENCE_THRESHOLD)
+    p.add_argument("--sdf", "-s", help="Encode SDF on GREEN channel", action="store_true")
+    p.add_argument("--subpath", help="Mask Subpath to frames", type=str, default="")
+    p.add_argument("--weights", type=str, default="", help="mmdet SOLOv2 checkpoint (.pth/.npz)")
+    p.add_argument("--seeded-weights", action="store_true", help="seeded random weights (offline testing)")
+    p.add_argument("--device", type=int, default=DEVICE)
+    return p
+
+
+def main(argv=None):
+    global args, data
+    args = build_parser().parse_args(argv)
+    if args.sdf:
+        raise NotImplementedError("--sdf (snowy.generate_sdf) is not built yet (SURVEY.md section 8f row 3)")
+    data = load_metadata(args.input)
+    if data:
+        args.input = get_url(args.input, data, "rgba")
+        args.output = get_target(args.input, data, band=BAND, target=args.output, force_extension="png")
+    elif args.output == "":
+        args.output = os.path.join(os.path.dirname(args.input), BAND + os.path.splitext(args.input)[1])
+    init_model()
+    if is_video(args.output):
+        process_video(args)
+    else:
+        process_image(args)
+    if data:
+        write_metadata(args.input, data)
+
+
+if __name__ == "__main__":
+    main()

@@ -126,6 +126,26 @@ long long prisma_flow_read_tap(prisma_engine* e, const char* name, float* out, l
 /* out[0] = algorithmic FLOP of one pass, out[1] = kernel launches per pass, out[2] = hs, out[3] = ws               */
 int prisma_flow_work(prisma_engine* e, int h, int w, float scale, int iters, double* out4);
 
+/* ---- mask_mmdet band: SOLOv2 (bands/mask_mmdet.py; bands/mmdet/apis/inference.py:99-162 inference_detector) ----
+ * prisma_mask_create("r101") + load_tensor x N + finalize replace init_detector(CONFIG, MODEL) (mask_mmdet.py:38-41,
+ * apis/inference.py:19-61); tensors by the mmdet checkpoint's state_dict names (backbone.*, neck.*, mask_head.*), fp32.
+ * prisma_mask_infer replaces inference_detector(model, img) AND the band's union loop (mask_mmdet.py:43-61,134-146):
+ *   rgb          h*w*3 u8 RGB frame (the band converts to BGR and the pipeline back, to_rgb=True)
+ *   confidence   args.confidence (the band additionally applies its fixed 0.5, getTotalMasks)
+ *   union_mask   h*w u8: (255 * number of overlapping instances of the 11 band classes above the thresholds) mod 256
+ *   n_inst, scores[100], labels[100]: the kept instances of InstanceData (all 80 classes), sorted by score
+ *   inst_masks   optional n_inst*h*w u8 0/1 (results.masks)                                                          */
+int prisma_mask_create(const char* variant, int device, prisma_engine** out);
+int prisma_mask_load_tensor(prisma_engine* e, const char* name, const float* data, const int64_t* shape, int ndim);
+int prisma_mask_finalize(prisma_engine* e);
+int prisma_mask_infer(prisma_engine* e, const uint8_t* rgb, int h, int w, float confidence, uint8_t* union_mask, int* n_inst,
+                      float* scores, int32_t* labels, uint8_t* inst_masks, float* ms_out);
+/* intermediate tensors of the last pass (tests): "resized", "net_input", "fpn0..4", "mask_feats", "cls0..4", "kernel0..4",
+ * "cand_count", "n_top"; returns the number of floats written                                                        */
+long long prisma_mask_read_tap(prisma_engine* e, const char* name, float* out, long long capacity);
+/* out[0] = algorithmic FLOP of the last planned pass, out[1] = launches, out[2..5] = resized h, w, padded h, w        */
+int prisma_mask_work(prisma_engine* e, int h, int w, double* out8);
+
 /* ---- kernel-level entry points (parity tests and micro-benchmarks call the kernels through the C ABI) ---- */
 /* D = A[M,K] * W[N,K]^T (+bias) with fp16 operands / fp32 accumulate on the tcgen05 core; A, W, D host fp32.
  * act: 0 none, 1 gelu, 2 relu.  force_bn: 0 = auto, else 32/64/128/256.  ms_out (may be NULL): kernel time.   */

@@ -38,6 +38,13 @@ SIGNATURES = {
     "prisma_engine_destroy": (C.c_int, [C.c_void_p]),
     "prisma_flow_preprocess": (C.c_int, [C.c_int, c_u8_p, C.c_int, C.c_int, C.c_float, c_u8_p, c_float_p]),
     "prisma_flow_encode": (C.c_int, [C.c_int, c_float_p, C.c_int, C.c_int, c_u8_p, c_float_p]),
+    "prisma_mask_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "prisma_mask_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, c_float_p, c_i64_p, C.c_int]),
+    "prisma_mask_finalize": (C.c_int, [C.c_void_p]),
+    "prisma_mask_infer": (C.c_int, [C.c_void_p, c_u8_p, C.c_int, C.c_int, C.c_float, c_u8_p, C.POINTER(C.c_int), c_float_p,
+                                    C.POINTER(C.c_int32), c_u8_p, c_float_p]),
+    "prisma_mask_read_tap": (C.c_longlong, [C.c_void_p, C.c_char_p, c_float_p, C.c_longlong]),
+    "prisma_mask_work": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "prisma_flow_masks": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.c_int, c_u8_p, c_u8_p, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]),
     "prisma_flowcorr_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "prisma_flowcorr_set_fmaps": (C.c_int, [C.c_void_p, c_float_p, c_float_p]),

@@ -7,6 +7,7 @@
 
 #include "engine_da.cuh"
 #include "engine_raft.cuh"
+#include "engine_solo.cuh"
 #include "flow.cuh"
 
 using namespace prisma;
@@ -16,6 +17,7 @@ struct prisma_engine {
   DepthEngine* depth;
   FlowCorr* corr;
   RaftEngine* raft = nullptr;
+  SoloEngine* solo = nullptr;  // kind 4
 };
 
 #define API_GUARD_BEGIN try {
@@ -217,6 +219,7 @@ int prisma_engine_destroy(prisma_engine* e) {
   delete e->depth;
   delete e->corr;
   delete e->raft;
+  delete e->solo;
   delete e;
   return 0;
   API_GUARD_END
@@ -517,6 +520,61 @@ static RaftEngine* as_raft(prisma_engine* e) {
   if (!e || e->kind != 3 || !e->raft) { set_last_error("not a RAFT engine handle"); return nullptr; }
   return e->raft;
 }
+static SoloEngine* as_solo(prisma_engine* e) {
+  if (!e || e->kind != 4 || !e->solo) { set_last_error("not a mask (SOLOv2) engine handle"); return nullptr; }
+  return e->solo;
+}
+int prisma_mask_create(const char* variant, int device, prisma_engine** out) {
+  API_GUARD_BEGIN
+  PRISMA_CHECK(out != nullptr && variant != nullptr, "null argument");
+  SoloEngine* m = new SoloEngine();
+  int rc = m->init(variant, device);
+  if (rc != 0) { delete m; return rc; }
+  prisma_engine* e = new prisma_engine{4, nullptr, nullptr};
+  e->solo = m;
+  *out = e;
+  return 0;
+  API_GUARD_END
+}
+int prisma_mask_load_tensor(prisma_engine* e, const char* name, const float* data, const int64_t* shape, int ndim) {
+  API_GUARD_BEGIN
+  SoloEngine* m = as_solo(e);
+  if (!m) return -1;
+  PRISMA_CHECK(name && data && shape && ndim >= 1 && ndim <= 4, "bad tensor");
+  return m->load_tensor(name, data, shape, ndim);
+  API_GUARD_END
+}
+int prisma_mask_finalize(prisma_engine* e) {
+  API_GUARD_BEGIN
+  SoloEngine* m = as_solo(e);
+  return m ? m->finalize() : -1;
+  API_GUARD_END
+}
+int prisma_mask_infer(prisma_engine* e, const uint8_t* rgb, int h, int w, float confidence, uint8_t* union_mask, int* n_inst,
+                      float* scores, int32_t* labels, uint8_t* inst_masks, float* ms_out) {
+  API_GUARD_BEGIN
+  SoloEngine* m = as_solo(e);
+  return m ? m->infer(rgb, h, w, confidence, union_mask, n_inst, scores, labels, inst_masks, ms_out) : -1;
+  API_GUARD_END
+}
+long long prisma_mask_read_tap(prisma_engine* e, const char* name, float* out, long long capacity) {
+  API_GUARD_BEGIN
+  SoloEngine* m = as_solo(e);
+  return m ? m->read_tap(name, out, capacity) : -1;
+  API_GUARD_END
+}
+int prisma_mask_work(prisma_engine* e, int h, int w, double* out8) {
+  API_GUARD_BEGIN
+  SoloEngine* m = as_solo(e);
+  if (!m) return -1;
+  PRISMA_CHECK(out8 != nullptr, "null argument");
+  int nh, nw, hp, wp;
+  m->net_shape(h, w, &nh, &nw, &hp, &wp);
+  out8[0] = m->flops; out8[1] = m->launches; out8[2] = nh; out8[3] = nw; out8[4] = hp; out8[5] = wp; out8[6] = 0; out8[7] = 0;
+  return 0;
+  API_GUARD_END
+}
+
 int prisma_flow_create(int device, prisma_engine** out) {
   API_GUARD_BEGIN
   PRISMA_CHECK(out != nullptr, "null argument");

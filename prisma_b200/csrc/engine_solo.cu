@@ -1,0 +1,546 @@
+// prisma_b200 -- SOLOv2 engine: inference_detector(model, img) of the mask_mmdet band (bands/mask_mmdet.py:133,
+// bands/mmdet/apis/inference.py:99-162) for one frame, plus the band's union frame (mask_mmdet.py:43-61,134-146).
+//
+// Graph of one pass (all paths relative to bands/mmdet/; config values from the un-vendored
+// models/solov2_r101_fpn_3x_coco.py):
+//   test pipeline (datasets/pipelines/transforms.py Resize/Normalize/Pad)          -> k_solo_preprocess
+//   ResNet-101, style "pytorch", frozen BatchNorm (models/backbones/resnet.py)     -> stem im2col GEMM, max-pool, 33 bottlenecks
+//       = 100 tcgen05 shifted-row GEMMs on zero-bordered NHWC fp16 maps, BN folded into weights / bias, ReLU and the
+//       residual add in the epilogue, stride-2 convs evaluated at stride 1 and sub-sampled by the row map
+//   FPN (models/necks/fpn.py:151-204)                                               -> 1x1 / 3x3 GEMMs, nearest-add, [::2]
+//   MaskFeatModule + SOLOV2Head towers (models/dense_heads/solov2_head.py)          -> GEMM -> dense fp32 -> GroupNorm+ReLU
+//   get_results (solov2_head.py:582-766) + mask_matrix_nms (core/post_processing)   -> candidate list, dynamic conv as ONE GEMM
+//       (kernels [n][256] x mask features [HW][256]^T, sigmoid epilogue), mask statistics, rank, binary-mask GEMM for the
+//       pairwise intersections, Matrix NMS, two nested bilinear resizes + threshold + the band's union, all on the device
+//       with fixed capacities (4096 candidates, nms_pre 500, 100 kept) -- no host round trip inside the pass.
+#include "engine_solo.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+
+#include "raft_kernels.cuh"
+
+namespace prisma {
+
+constexpr int SOLO_CAP = 4096, SOLO_NMS_PRE = 500, SOLO_NMS_PAD = 512, SOLO_MAX = 100, SOLO_NC = 80;
+
+template <typename T>
+static int s_alloc(std::vector<void*>& pool, T** out, size_t n) {
+  void* p = nullptr;
+  PRISMA_CUDA_OK(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 256)));
+  PRISMA_CUDA_OK(cudaMemset(p, 0, std::max<size_t>(n * sizeof(T), 256)));
+  pool.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+
+SoloEngine::~SoloEngine() {
+  cudaSetDevice(device);
+  for (void* p : allocs) cudaFree(p);
+  for (void* p : plan_allocs) cudaFree(p);
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int SoloEngine::init(const std::string& v, int dev) {
+  variant = v;
+  if (v == "r101") { const int l[4] = {3, 4, 23, 3}; std::copy(l, l + 4, layers); scale_long = 1333; scale_short = 800; }
+  else if (v == "tiny") { const int l[4] = {1, 1, 1, 1}; std::copy(l, l + 4, layers); scale_long = 448; scale_short = 256; }
+  else { set_last_error("unknown SOLOv2 variant '" + v + "' (r101)"); return -1; }
+  device = dev;
+  int n = 0;
+  PRISMA_CUDA_OK(cudaGetDeviceCount(&n));
+  PRISMA_CHECK(dev >= 0 && dev < n, "bad device ordinal");
+  PRISMA_CUDA_OK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  PRISMA_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  PRISMA_CHECK(prop.major == 10, "prisma_b200 kernels are sm_100a only; there is no fallback path");
+  num_sms = prop.multiProcessorCount;
+  PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  PRISMA_CUDA_OK(cudaEventCreate(&ev0));
+  PRISMA_CUDA_OK(cudaEventCreate(&ev1));
+  const char* ng = getenv("PRISMA_NO_GRAPH");
+  use_graph = !(ng && ng[0] == '1');
+  return 0;
+}
+
+int SoloEngine::load_tensor(const std::string& name, const float* data, const int64_t* shape, int ndim) {
+  PRISMA_CHECK(!finalized, "load_tensor after finalize");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(data, data + n);
+  host[name] = std::move(t);
+  return 0;
+}
+
+const HostTensor* SoloEngine::get(const std::string& name) {
+  auto it = host.find(name);
+  if (it == host.end()) { set_last_error("missing SOLOv2 weight tensor '" + name + "'"); return nullptr; }
+  return &it->second;
+}
+
+// conv weight [Cout][Cin][k][k] -> fp16 [round_up(Cout,256)][k*k*ceil(Cin/64)*64]; eval BatchNorm folded (eps 1e-5);
+// GroupNorm affine kept separately (applied by the GN kernel on the fp32 conv output).
+int SoloEngine::up_conv(const std::string& name, const std::string& bn, const std::string& gn, int Cout, int Cin, int k,
+                        bool bias, SoloConvW* out) {
+  const HostTensor* w = get(name + ".weight");
+  if (!w) return -1;
+  PRISMA_CHECK((long long)w->data.size() == (long long)Cout * Cin * k * k, "SOLOv2 weight '" + name + "' has an unexpected size");
+  std::vector<float> sc(Cout, 1.f), sh(Cout, 0.f);
+  if (bias) {
+    const HostTensor* b = get(name + ".bias");
+    if (!b) return -1;
+    for (int n = 0; n < Cout; ++n) sh[n] = b->data[n];
+  }
+  if (!bn.empty()) {
+    const HostTensor *g = get(bn + ".weight"), *be = get(bn + ".bias"), *mu = get(bn + ".running_mean"), *var = get(bn + ".running_var");
+    if (!g || !be || !mu || !var) return -1;
+    for (int n = 0; n < Cout; ++n) {
+      const float s = g->data[n] / sqrtf(var->data[n] + 1e-5f);
+      sc[n] = s;
+      sh[n] = (sh[n] - mu->data[n]) * s + be->data[n];
+    }
+  }
+  const int taps = k * k, kc = ceil_div(Cin, 64), K = taps * kc * 64, rows = round_up(Cout, 256);
+  std::vector<__half> h((size_t)rows * K, __float2half_rn(0.f));
+  for (int n = 0; n < Cout; ++n)
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < Cin; ++c)
+        h[(size_t)n * K + (size_t)t * kc * 64 + c] = __float2half_rn(w->data[((size_t)n * Cin + c) * taps + t] * sc[n]);
+  PRISMA_TRY(s_alloc(allocs, &out->w, h.size()));
+  PRISMA_CUDA_OK(cudaMemcpy(out->w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> bv(round_up(Cout, 8), 0.f);
+  for (int n = 0; n < Cout; ++n) bv[n] = sh[n];
+  PRISMA_TRY(s_alloc(allocs, &out->b, bv.size()));
+  PRISMA_CUDA_OK(cudaMemcpy(out->b, bv.data(), bv.size() * 4, cudaMemcpyHostToDevice));
+  if (!gn.empty()) {
+    const HostTensor *g = get(gn + ".weight"), *be = get(gn + ".bias");
+    if (!g || !be) return -1;
+    PRISMA_TRY(s_alloc(allocs, &out->gn_w, (size_t)Cout));
+    PRISMA_TRY(s_alloc(allocs, &out->gn_b, (size_t)Cout));
+    PRISMA_CUDA_OK(cudaMemcpy(out->gn_w, g->data.data(), Cout * 4, cudaMemcpyHostToDevice));
+    PRISMA_CUDA_OK(cudaMemcpy(out->gn_b, be->data.data(), Cout * 4, cudaMemcpyHostToDevice));
+  }
+  out->cout = Cout; out->cin = Cin; out->k = k;
+  return 0;
+}
+
+int SoloEngine::finalize() {
+  PRISMA_CHECK(!finalized, "finalize called twice");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  {  // stem 7x7/2: im2col K = 147 (k = c*49 + ky*7 + kx) -> a "1x1 conv" with Cin 147
+    const HostTensor* w = get("backbone.conv1.weight");
+    if (!w) return -1;
+    host["backbone.conv1_flat.weight"] = *w;
+    PRISMA_TRY(up_conv("backbone.conv1_flat", "backbone.bn1", "", 64, 147, 1, false, &stem));
+  }
+  int inplanes = 64;
+  const int planes_of[4] = {64, 128, 256, 512};
+  for (int li = 0; li < 4; ++li) {
+    blocks[li].resize(layers[li]);
+    for (int b = 0; b < layers[li]; ++b) {
+      const std::string p = "backbone.layer" + std::to_string(li + 1) + "." + std::to_string(b) + ".";
+      Block& k = blocks[li][b];
+      const int pl = planes_of[li];
+      k.stride = (b == 0 && li > 0) ? 2 : 1;
+      PRISMA_TRY(up_conv(p + "conv1", p + "bn1", "", pl, inplanes, 1, false, &k.c1));
+      PRISMA_TRY(up_conv(p + "conv2", p + "bn2", "", pl, pl, 3, false, &k.c2));
+      PRISMA_TRY(up_conv(p + "conv3", p + "bn3", "", pl * 4, pl, 1, false, &k.c3));
+      k.has_ds = b == 0;
+      if (k.has_ds) PRISMA_TRY(up_conv(p + "downsample.0", p + "downsample.1", "", pl * 4, inplanes, 1, false, &k.ds));
+      inplanes = pl * 4;
+    }
+  }
+  const int cins[4] = {256, 512, 1024, 2048};
+  for (int i = 0; i < 4; ++i) {
+    PRISMA_TRY(up_conv("neck.lateral_convs." + std::to_string(i) + ".conv", "", "", 256, cins[i], 1, true, &lateral[i]));
+    PRISMA_TRY(up_conv("neck.fpn_convs." + std::to_string(i) + ".conv", "", "", 256, 256, 3, true, &fpnc[i]));
+  }
+  const std::string m = "mask_head.mask_feature_head.";
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < std::max(i, 1); ++j) {
+      const std::string n = m + "convs_all_levels." + std::to_string(i) + ".conv" + std::to_string(j);
+      const int cin = j == 0 ? (i == 3 ? 258 : 256) : 128;
+      PRISMA_TRY(up_conv(n + ".conv", "", n + ".gn", 128, cin, 3, false, &mf[i][j]));
+    }
+  PRISMA_TRY(up_conv(m + "conv_pred.conv", "", m + "conv_pred.gn", 256, 128, 1, false, &mf_pred));
+  for (int i = 0; i < 4; ++i) {
+    const std::string kn = "mask_head.kernel_convs." + std::to_string(i), cn = "mask_head.cls_convs." + std::to_string(i);
+    PRISMA_TRY(up_conv(kn + ".conv", "", kn + ".gn", 512, i == 0 ? 258 : 512, 3, false, &kconv[i]));
+    PRISMA_TRY(up_conv(cn + ".conv", "", cn + ".gn", 512, i == 0 ? 256 : 512, 3, false, &cconv[i]));
+  }
+  PRISMA_TRY(up_conv("mask_head.conv_cls", "", "", SOLO_NC, 512, 3, true, &conv_cls));
+  PRISMA_TRY(up_conv("mask_head.conv_kernel", "", "", 256, 512, 3, true, &conv_kernel));
+  host.clear();
+  finalized = true;
+  return 0;
+}
+
+// mmcv.imrescale((1333, 800), keep_ratio) + Pad(size_divisor=32) sizes
+int SoloEngine::net_shape(int H, int W, int* nh_, int* nw_, int* hp_, int* wp_) const {
+  const double s = std::min((double)scale_long / std::max(H, W), (double)scale_short / std::min(H, W));
+  *nw_ = (int)(W * s + 0.5);
+  *nh_ = (int)(H * s + 0.5);
+  *hp_ = round_up(*nh_, 32);
+  *wp_ = round_up(*nw_, 32);
+  return 0;
+}
+
+int SoloEngine::build_plan(int H, int W) {
+  PRISMA_CHECK(finalized, "weights not finalized");
+  if (plan_H == H && plan_W == W) return 0;
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  for (void* q : plan_allocs) cudaFree(q);
+  plan_allocs.clear();
+  steps.clear();
+  taps.clear();
+  flops = 0;
+  plan_H = plan_W = 0;
+  d_inst = nullptr;
+  net_shape(H, W, &nh, &nw, &hp, &wp);
+  const int zero_off[1] = {0};
+
+  auto new_map = [&](SMap* mm, int h, int w, int c) -> int {
+    mm->H = h; mm->W = w; mm->C = c;
+    return s_alloc(plan_allocs, &mm->p, (size_t)mm->rows() * c);
+  };
+  // conv on a zero-bordered map.  dst_map: zero-bordered fp16 output (stride `sub`); dst_dense: dense fp32 [H*W][Cout]
+  auto conv = [&](const SMap& in, int cin_cols, const SoloConvW& w, int sub, GemmEpilogue ep, const SMap* dst_map,
+                  float* dst_dense) -> int {
+    int off[9], taps_n = w.k * w.k;
+    if (w.k == 3) { for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky - 1) * in.Wp() + (kx - 1); }
+    else off[0] = 0;
+    ep.in_w = in.Wp(); ep.in_h = in.Hp(); ep.img_rows = 0; ep.sub = sub; ep.pad = 1;
+    if (dst_map) {
+      ep.row_map = ROW_PADDED;
+      if (sub > 1) { ep.out_wp = dst_map->Wp(); ep.out_img_rows = (int)dst_map->rows(); ep.out_pad = 1; }
+    } else {
+      ep.row_map = ROW_PAD2TOK;
+      ep.out_f32 = dst_dense; ep.out_f32_ld = w.cout;
+    }
+    GemmLaunch g;
+    PRISMA_TRY(gemm_prepare(&g, in.p, in.rows(), cin_cols, in.C, w.w, round_up(w.cout, 256), (int)in.rows(), w.cout, taps_n, off,
+                            ep, num_sms));
+    flops += 2.0 * (in.H / sub) * (double)(in.W / sub) * taps_n * w.cin * w.cout;
+    steps.push_back([g](cudaStream_t s) { return gemm_run(g, s); });
+    return 0;
+  };
+  float* gn_part = nullptr; float* gn_stats = nullptr; float* gn_raw = nullptr;
+  const size_t raw_max = (size_t)(hp / 4) * (wp / 4) * 256;
+  PRISMA_TRY(s_alloc(plan_allocs, &gn_raw, raw_max));
+  PRISMA_TRY(s_alloc(plan_allocs, &gn_part, (size_t)gn_partial_floats((hp / 4) * (wp / 4), 512)));
+  PRISMA_TRY(s_alloc(plan_allocs, &gn_stats, 1024));
+  // ConvModule(norm GN-32): conv (no bias) -> dense fp32 -> GroupNorm + ReLU -> fp16 map (and / or dense fp16)
+  auto gnconv = [&](const SMap& in, int cin_cols, const SoloConvW& w, const SMap* dst_map, __half* dst_dense) -> int {
+    GemmEpilogue ep;
+    PRISMA_TRY(conv(in, cin_cols, w, 1, ep, nullptr, gn_raw));
+    const int h = in.H, ww = in.W, c = w.cout; const float* gw = w.gn_w; const float* gb = w.gn_b;
+    __half* dm = dst_map ? dst_map->p : nullptr;
+    steps.push_back([=](cudaStream_t s) { return groupnorm_relu_f16(gn_raw, h, ww, c, 32, gw, gb, gn_part, gn_stats, dm, dst_dense, s); });
+    return 0;
+  };
+
+  // ---- test pipeline
+  PRISMA_TRY(s_alloc(plan_allocs, &d_img, (size_t)H * W * 3));
+  PRISMA_TRY(s_alloc(plan_allocs, &d_resized, (size_t)nh * nw * 3));
+  PRISMA_TRY(s_alloc(plan_allocs, &d_net, (size_t)3 * hp * wp));
+  {
+    const uint8_t* img = d_img; uint8_t* rs = d_resized; float* net = d_net;
+    const int nh_ = nh, nw_ = nw, hp_ = hp, wp_ = wp;
+    steps.push_back([=](cudaStream_t s) { return solo_preprocess(img, H, W, nh_, nw_, hp_, wp_, net, rs, s); });
+  }
+  // ---- ResNet stem: 7x7/2 conv + BN + ReLU (im2col GEMM), 3x3/2 max-pool
+  SMap s1, x;
+  PRISMA_TRY(new_map(&s1, hp / 2, wp / 2, 64));
+  {
+    __half* cols = nullptr;
+    PRISMA_TRY(s_alloc(plan_allocs, &cols, (size_t)(hp / 2) * (wp / 2) * 192));
+    const float* net = d_net; const int hp_ = hp, wp_ = wp;
+    steps.push_back([=](cudaStream_t s) { return raft_im2col_stem(net, 1, hp_, wp_, cols, s); });
+    GemmEpilogue ep; ep.bias = stem.b; ep.act = 2; ep.out_f16 = s1.p; ep.out_f16_ld = 64;
+    ep.row_map = ROW_TOK2PAD; ep.in_w = wp / 2; ep.in_h = hp / 2; ep.out_wp = s1.Wp(); ep.out_img_rows = (int)s1.rows(); ep.out_pad = 1;
+    GemmLaunch g;
+    const int M = (hp / 2) * (wp / 2);
+    PRISMA_TRY(gemm_prepare(&g, cols, M, 192, 192, stem.w, 256, M, 64, 1, zero_off, ep, num_sms));
+    flops += 2.0 * M * 147.0 * 64;
+    steps.push_back([g](cudaStream_t s) { return gemm_run(g, s); });
+  }
+  PRISMA_TRY(new_map(&x, hp / 4, wp / 4, 64));
+  { const SMap a = s1, o = x; steps.push_back([=](cudaStream_t s) { return maxpool3s2_f16(a.p, a.H, a.W, 64, o.p, o.H, o.W, s); }); }
+  // ---- bottlenecks (resnet.py:255-300): 1x1 -> 3x3 (stride) -> 1x1, + identity / downsample, ReLU
+  SMap C[4];
+  for (int li = 0; li < 4; ++li) {
+    for (size_t b = 0; b < blocks[li].size(); ++b) {
+      const Block& k = blocks[li][b];
+      const int ho = x.H / k.stride, wo = x.W / k.stride;
+      SMap a, m2, o, idn = x;
+      PRISMA_TRY(new_map(&a, x.H, x.W, k.c1.cout));
+      PRISMA_TRY(new_map(&m2, ho, wo, k.c2.cout));
+      PRISMA_TRY(new_map(&o, ho, wo, k.c3.cout));
+      { GemmEpilogue ep; ep.bias = k.c1.b; ep.act = 2; ep.out_f16 = a.p; ep.out_f16_ld = a.C;
+        PRISMA_TRY(conv(x, x.C, k.c1, 1, ep, &a, nullptr)); }
+      { GemmEpilogue ep; ep.bias = k.c2.b; ep.act = 2; ep.out_f16 = m2.p; ep.out_f16_ld = m2.C;
+        PRISMA_TRY(conv(a, a.C, k.c2, k.stride, ep, &m2, nullptr)); }
+      if (k.has_ds) {
+        PRISMA_TRY(new_map(&idn, ho, wo, k.ds.cout));
+        GemmEpilogue ep; ep.bias = k.ds.b; ep.out_f16 = idn.p; ep.out_f16_ld = idn.C;
+        PRISMA_TRY(conv(x, x.C, k.ds, k.stride, ep, &idn, nullptr));
+      }
+      { GemmEpilogue ep; ep.bias = k.c3.b; ep.res_a = idn.p; ep.res_a_ld = idn.C; ep.out_f16_relu = o.p; ep.out_f16_relu_ld = o.C;
+        PRISMA_TRY(conv(m2, m2.C, k.c3, 1, ep, &o, nullptr)); }
+      x = o;
+    }
+    C[li] = x;
+  }
+  // ---- FPN
+  SMap L[4], P[5];
+  for (int i = 0; i < 4; ++i) {
+    PRISMA_TRY(new_map(&L[i], C[i].H, C[i].W, 256));
+    GemmEpilogue ep; ep.bias = lateral[i].b; ep.out_f16 = L[i].p; ep.out_f16_ld = 256;
+    PRISMA_TRY(conv(C[i], C[i].C, lateral[i], 1, ep, &L[i], nullptr));
+  }
+  for (int i = 3; i > 0; --i) {
+    const SMap f = L[i - 1], c = L[i];
+    steps.push_back([=](cudaStream_t s) { return nearest_add_f16(f.p, f.H, f.W, c.p, c.H, c.W, 256, s); });
+  }
+  for (int i = 0; i < 4; ++i) {
+    PRISMA_TRY(new_map(&P[i], L[i].H, L[i].W, 256));
+    GemmEpilogue ep; ep.bias = fpnc[i].b; ep.out_f16 = P[i].p; ep.out_f16_ld = 256;
+    PRISMA_TRY(conv(L[i], 256, fpnc[i], 1, ep, &P[i], nullptr));
+  }
+  PRISMA_TRY(new_map(&P[4], (P[3].H - 1) / 2 + 1, (P[3].W - 1) / 2 + 1, 256));
+  { const SMap a = P[3], o = P[4]; steps.push_back([=](cudaStream_t s) { return subsample2_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, s); }); }
+  for (int i = 0; i < 5; ++i) taps["fpn" + std::to_string(i)] = {P[i].p, 1, P[i].H, P[i].W, 256};
+
+  // ---- mask feature head (solov2_head.py:133-150)
+  fh = P[0].H; fw = P[0].W;
+  const int HW = fh * fw;
+  SMap acc;
+  PRISMA_TRY(new_map(&acc, fh, fw, 128));
+  PRISMA_TRY(gnconv(P[0], 256, mf[0][0], &acc, nullptr));
+  for (int i = 1; i < 4; ++i) {
+    SMap cur = P[i];
+    int cin_cols = 256;
+    if (i == 3) {  // + generate_coordinate channels: 258 -> 320-channel operand
+      SMap cc;
+      PRISMA_TRY(new_map(&cc, P[3].H, P[3].W, 320));
+      const SMap a = P[3];
+      steps.push_back([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, cc.p, cc.H, cc.W, 320, 1, 0, s); });
+      cur = cc; cin_cols = 320;
+    }
+    for (int j = 0; j < i; ++j) {
+      SMap t, u;
+      PRISMA_TRY(new_map(&t, cur.H, cur.W, 128));
+      PRISMA_TRY(gnconv(cur, cin_cols, mf[i][j], &t, nullptr));
+      const bool last = j == i - 1;
+      if (last) u = acc; else PRISMA_TRY(new_map(&u, 2 * t.H, 2 * t.W, 128));
+      PRISMA_CHECK(u.H == 2 * t.H && u.W == 2 * t.W, "solo: FPN levels are not exact halvings (pad to a multiple of 32)");
+      steps.push_back([=](cudaStream_t s) { return resize_bilinear_f16(t.p, t.H, t.W, 128, u.p, u.H, u.W, 128, 0, last ? 1 : 0, s); });
+      cur = u; cin_cols = 128;
+    }
+  }
+  __half* mfeat = nullptr;  // dense [HW][256] fp16, rows padded for its role as the "weight" of the dynamic-conv GEMM
+  PRISMA_TRY(s_alloc(plan_allocs, &mfeat, (size_t)round_up(HW, 256) * 256));
+  PRISMA_TRY(gnconv(acc, 128, mf_pred, nullptr, mfeat));
+  taps["mask_feats"] = {mfeat, 2, HW, 256, 0};
+
+  // ---- head towers (solov2_head.py:253-292, resize_feats solo_head.py:133-153)
+  SMap R0, R4;
+  PRISMA_TRY(new_map(&R0, P[1].H, P[1].W, 256));
+  PRISMA_TRY(new_map(&R4, P[3].H, P[3].W, 256));
+  { const SMap a = P[0], o = R0; steps.push_back([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, 256, 0, 0, s); }); }
+  { const SMap a = P[4], o = R4; steps.push_back([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, 256, 0, 0, s); }); }
+  const SMap lvl_in[5] = {R0, P[1], P[2], P[3], R4};
+  float* cls_out[5]; float* ker_out[5];
+  int cell0[5], cells = 0;
+  for (int l = 0; l < 5; ++l) {
+    const int S = num_grids[l];
+    cell0[l] = cells; cells += S * S;
+    SMap g0, ka, kb, ca, cb;
+    PRISMA_TRY(new_map(&g0, S, S, 320));
+    PRISMA_TRY(new_map(&ka, S, S, 512)); PRISMA_TRY(new_map(&kb, S, S, 512));
+    PRISMA_TRY(new_map(&ca, S, S, 512)); PRISMA_TRY(new_map(&cb, S, S, 512));
+    const SMap a = lvl_in[l];
+    steps.push_back([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, g0.p, S, S, 320, 1, 0, s); });
+    PRISMA_TRY(gnconv(g0, 320, kconv[0], &ka, nullptr));
+    PRISMA_TRY(gnconv(ka, 512, kconv[1], &kb, nullptr));
+    PRISMA_TRY(gnconv(kb, 512, kconv[2], &ka, nullptr));
+    PRISMA_TRY(gnconv(ka, 512, kconv[3], &kb, nullptr));
+    PRISMA_TRY(s_alloc(plan_allocs, &ker_out[l], (size_t)S * S * 256));
+    { GemmEpilogue ep; ep.bias = conv_kernel.b; PRISMA_TRY(conv(kb, 512, conv_kernel, 1, ep, nullptr, ker_out[l])); }
+    PRISMA_TRY(gnconv(g0, 256, cconv[0], &ca, nullptr));
+    PRISMA_TRY(gnconv(ca, 512, cconv[1], &cb, nullptr));
+    PRISMA_TRY(gnconv(cb, 512, cconv[2], &ca, nullptr));
+    PRISMA_TRY(gnconv(ca, 512, cconv[3], &cb, nullptr));
+    PRISMA_TRY(s_alloc(plan_allocs, &cls_out[l], (size_t)S * S * SOLO_NC));
+    { GemmEpilogue ep; ep.bias = conv_cls.b; PRISMA_TRY(conv(cb, 512, conv_cls, 1, ep, nullptr, cls_out[l])); }
+    taps["cls" + std::to_string(l)] = {cls_out[l], 0, S * S, SOLO_NC, 0};
+    taps["kernel" + std::to_string(l)] = {ker_out[l], 0, S * S, 256, 0};
+  }
+
+  // ---- decode (solov2_head.py:582-766)
+  SoloCand *cand_raw = nullptr, *cand = nullptr;
+  PRISMA_TRY(s_alloc(plan_allocs, &cand_raw, (size_t)SOLO_CAP));
+  PRISMA_TRY(s_alloc(plan_allocs, &cand, (size_t)SOLO_CAP));
+  PRISMA_TRY(s_alloc(plan_allocs, &d_count, 4));
+  PRISMA_TRY(s_alloc(plan_allocs, &d_ntop, 4));
+  PRISMA_TRY(s_alloc(plan_allocs, &d_nkeep, 4));
+  PRISMA_TRY(s_alloc(plan_allocs, &d_top, (size_t)SOLO_NMS_PAD));
+  PRISMA_TRY(s_alloc(plan_allocs, &d_keep, (size_t)SOLO_MAX));
+  PRISMA_TRY(s_alloc(plan_allocs, &d_keep_label, (size_t)SOLO_MAX));
+  PRISMA_TRY(s_alloc(plan_allocs, &d_keep_score, (size_t)SOLO_MAX));
+  { int* cnt = d_count; steps.push_back([=](cudaStream_t s) { PRISMA_CUDA_OK(cudaMemsetAsync(cnt, 0, 4, s)); return 0; }); }
+  for (int l = 0; l < 5; ++l) {
+    const float* lg = cls_out[l]; const int S = num_grids[l], c0 = cell0[l]; const float st = strides[l]; int* cnt = d_count;
+    steps.push_back([=](cudaStream_t s) { return solo_candidates(lg, S, c0, SOLO_NC, 0.1f, st, cand_raw, cnt, SOLO_CAP, s); });
+  }
+  { int* cnt = d_count; steps.push_back([=](cudaStream_t s) { return solo_sort_candidates(cand_raw, cnt, SOLO_CAP, cand, s); }); }
+  __half* kmat = nullptr;
+  PRISMA_TRY(s_alloc(plan_allocs, &kmat, (size_t)SOLO_CAP * 256));
+  const float** d_lvl_ptr = nullptr; int* d_cell0 = nullptr;
+  PRISMA_TRY(s_alloc(plan_allocs, &d_lvl_ptr, 8));
+  PRISMA_TRY(s_alloc(plan_allocs, &d_cell0, 8));
+  PRISMA_CUDA_OK(cudaMemcpy(d_lvl_ptr, ker_out, 5 * sizeof(float*), cudaMemcpyHostToDevice));
+  PRISMA_CUDA_OK(cudaMemcpy(d_cell0, cell0, 5 * sizeof(int), cudaMemcpyHostToDevice));
+  { const int* cnt = d_count;
+    steps.push_back([=](cudaStream_t s) { return solo_gather_kernels(cand, cnt, SOLO_CAP, d_lvl_ptr, d_cell0, 5, SOLO_NC, 256, kmat, s); }); }
+  // dynamic conv: mask_preds = sigmoid(kernels [n][256] . mask_feats [HW][256]^T) as one GEMM (solov2_head.py:717-722)
+  __half* masks = nullptr;
+  PRISMA_TRY(s_alloc(plan_allocs, &masks, (size_t)SOLO_CAP * HW));
+  d_masks = masks;
+  {
+    GemmEpilogue ep; ep.act = 3; ep.out_f16 = masks; ep.out_f16_ld = HW;
+    GemmLaunch g;
+    PRISMA_TRY(gemm_prepare(&g, kmat, SOLO_CAP, 256, 256, mfeat, round_up(HW, 256), SOLO_CAP, HW, 1, zero_off, ep, num_sms));
+    flops += 2.0 * SOLO_CAP * (double)HW * 256;
+    steps.push_back([g](cudaStream_t s) { return gemm_run(g, s); });
+  }
+  { const int* cnt = d_count; const int hw = HW;
+    steps.push_back([=](cudaStream_t s) { return solo_mask_stats(masks, hw, 0.5f, cand, cnt, SOLO_CAP, s); });
+    int* top = d_top; int* ntop = d_ntop;
+    steps.push_back([=](cudaStream_t s) { return solo_rank(cand, cnt, SOLO_CAP, SOLO_NMS_PRE, top, ntop, s); }); }
+  __half* bin = nullptr; float* inter = nullptr;
+  PRISMA_TRY(s_alloc(plan_allocs, &bin, (size_t)SOLO_NMS_PAD * HW));
+  PRISMA_TRY(s_alloc(plan_allocs, &inter, (size_t)SOLO_NMS_PAD * SOLO_NMS_PAD));
+  { const int* top = d_top; const int* ntop = d_ntop; const int hw = HW;
+    steps.push_back([=](cudaStream_t s) { return solo_binarize(masks, hw, 0.5f, top, ntop, SOLO_NMS_PAD, bin, s); }); }
+  {  // inter_matrix = M M^T over binary masks (matrix_nms.py:70-71): exact in fp32 (counts < 2^24)
+    GemmEpilogue ep; ep.out_f32 = inter; ep.out_f32_ld = SOLO_NMS_PAD;
+    GemmLaunch g;
+    PRISMA_TRY(gemm_prepare(&g, bin, SOLO_NMS_PAD, HW, HW, bin, SOLO_NMS_PAD, SOLO_NMS_PAD, SOLO_NMS_PAD, 1, zero_off, ep, num_sms));
+    flops += 2.0 * SOLO_NMS_PAD * (double)SOLO_NMS_PAD * HW;
+    steps.push_back([g](cudaStream_t s) { return gemm_run(g, s); });
+  }
+  { const int* top = d_top; const int* ntop = d_ntop; int* keep = d_keep; float* ks = d_keep_score; int* kl = d_keep_label; int* nk = d_nkeep;
+    steps.push_back([=](cudaStream_t s) {
+      return solo_matrix_nms(inter, SOLO_NMS_PAD, cand, top, ntop, SOLO_NC, 2.0f, 0.05f, SOLO_MAX, keep, ks, kl, nk, s); }); }
+  PRISMA_TRY(s_alloc(plan_allocs, &d_union, (size_t)H * W));
+  taps["resized"] = {d_resized, 3, nh * nw, 3, 0};
+  taps["net_input"] = {d_net, 0, 3 * hp, wp, 0};
+  taps["cand_count"] = {d_count, 4, 1, 1, 0};
+  taps["n_top"] = {d_ntop, 4, 1, 1, 0};
+  launches = (int)steps.size();
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  plan_H = H; plan_W = W;
+  if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  if (use_graph) {
+    PRISMA_TRY(run(stream));  // warm: per-kernel attributes are set outside the capture
+    PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+    cudaGraph_t graph = nullptr;
+    PRISMA_CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    int r = 0;
+    for (auto& st : steps) { r = st(stream); if (r != 0) break; }
+    cudaError_t e = cudaStreamEndCapture(stream, &graph);
+    if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+    PRISMA_CUDA_OK(e);
+    PRISMA_CUDA_OK(cudaGraphInstantiate(&graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  return 0;
+}
+
+int SoloEngine::run(cudaStream_t s) {
+  if (graph_exec) { PRISMA_CUDA_OK(cudaGraphLaunch(graph_exec, s)); return 0; }
+  for (auto& st : steps) PRISMA_TRY(st(s));
+  return 0;
+}
+
+int SoloEngine::infer(const uint8_t* rgb, int H, int W, float confidence, uint8_t* union_out, int* n_out, float* scores_out,
+                      int* labels_out, uint8_t* inst_masks_out, float* ms_out) {
+  PRISMA_CHECK(rgb != nullptr && H > 0 && W > 0, "bad frame");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_TRY(build_plan(H, W));
+  if (inst_masks_out && !d_inst) PRISMA_TRY(s_alloc(plan_allocs, &d_inst, (size_t)SOLO_MAX * H * W));
+  PRISMA_CUDA_OK(cudaMemcpyAsync(d_img, rgb, (size_t)H * W * 3, cudaMemcpyHostToDevice, stream));
+  PRISMA_CUDA_OK(cudaEventRecord(ev0, stream));
+  PRISMA_TRY(run(stream));
+  PRISMA_TRY(solo_final_masks(d_masks, fh, fw, nh, nw, H, W, 0.5f, d_keep, d_keep_score, d_keep_label, d_nkeep, SOLO_MAX,
+                              confidence, inst_masks_out ? d_inst : nullptr, d_union, stream));
+  PRISMA_CUDA_OK(cudaEventRecord(ev1, stream));
+  int n = 0, cnt = 0;
+  PRISMA_CUDA_OK(cudaMemcpyAsync(&n, d_nkeep, 4, cudaMemcpyDeviceToHost, stream));
+  PRISMA_CUDA_OK(cudaMemcpyAsync(&cnt, d_count, 4, cudaMemcpyDeviceToHost, stream));
+  if (union_out) PRISMA_CUDA_OK(cudaMemcpyAsync(union_out, d_union, (size_t)H * W, cudaMemcpyDeviceToHost, stream));
+  if (scores_out) PRISMA_CUDA_OK(cudaMemcpyAsync(scores_out, d_keep_score, SOLO_MAX * 4, cudaMemcpyDeviceToHost, stream));
+  if (labels_out) PRISMA_CUDA_OK(cudaMemcpyAsync(labels_out, d_keep_label, SOLO_MAX * 4, cudaMemcpyDeviceToHost, stream));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  PRISMA_CHECK(cnt <= SOLO_CAP, "solo: more than 4096 grid cells passed score_thr (candidate capacity exceeded)");
+  if (inst_masks_out && n > 0) PRISMA_CUDA_OK(cudaMemcpy(inst_masks_out, d_inst, (size_t)n * H * W, cudaMemcpyDeviceToHost));
+  if (n_out) *n_out = n;
+  if (ms_out) { float ms = 0; PRISMA_CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); *ms_out = ms; }
+  return 0;
+}
+
+long long SoloEngine::read_tap(const std::string& name, float* out, long long capacity) {
+  auto it = taps.find(name);
+  if (it == taps.end()) { set_last_error("unknown tap '" + name + "'"); return -1; }
+  const SoloTap& t = it->second;
+  cudaSetDevice(device);
+  cudaStreamSynchronize(stream);
+  if (t.kind == 0) {
+    const long long n = (long long)t.a * t.b;
+    if (n > capacity) { set_last_error("tap buffer too small"); return -1; }
+    if (cudaMemcpy(out, t.p, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+    return n;
+  }
+  if (t.kind == 2) {
+    const long long n = (long long)t.a * t.b;
+    if (n > capacity) { set_last_error("tap buffer too small"); return -1; }
+    std::vector<__half> h(n);
+    if (cudaMemcpy(h.data(), t.p, n * 2, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+    for (long long i = 0; i < n; ++i) out[i] = __half2float(h[i]);
+    return n;
+  }
+  if (t.kind == 3) {
+    const long long n = (long long)t.a * t.b;
+    if (n > capacity) { set_last_error("tap buffer too small"); return -1; }
+    std::vector<uint8_t> h(n);
+    if (cudaMemcpy(h.data(), t.p, n, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+    for (long long i = 0; i < n; ++i) out[i] = (float)h[i];
+    return n;
+  }
+  if (t.kind == 4) {
+    int v = 0;
+    if (capacity < 1 || cudaMemcpy(&v, t.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+    out[0] = (float)v;
+    return 1;
+  }
+  // padded fp16 map -> dense [H][W][C]
+  const long long n = (long long)t.a * t.b * t.c;
+  if (n > capacity) { set_last_error("tap buffer too small"); return -1; }
+  const long long tot = (long long)(t.a + 2) * (t.b + 2) * t.c;
+  std::vector<__half> h(tot);
+  if (cudaMemcpy(h.data(), t.p, tot * 2, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+  for (int y = 0; y < t.a; ++y)
+    for (int x = 0; x < t.b; ++x)
+      for (int c = 0; c < t.c; ++c)
+        out[((long long)y * t.b + x) * t.c + c] = __half2float(h[((long long)(y + 1) * (t.b + 2) + x + 1) * t.c + c]);
+  return n;
+}
+
+}  // namespace prisma

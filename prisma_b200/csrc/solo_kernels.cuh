@@ -1,0 +1,46 @@
+// prisma_b200 -- SOLOv2 (mask_mmdet band) pointwise / reduction / decode kernels (see solo_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace prisma {
+
+struct SoloCand {       // one candidate (grid cell, class) above score_thr, solov2_head.py:694-703
+  float score;          // cls score, later x maskness
+  int flat;             // cell * num_classes + class: the reference's nonzero() order, used as the stable tie-break
+  float area;           // sum of (p > mask_thr)
+  float stride;
+};
+
+int solo_preprocess(const uint8_t* rgb, int H, int W, int nh, int nw, int hp, int wp, float* out_chw, uint8_t* resized_u8,
+                    cudaStream_t s);
+int maxpool3s2_f16(const __half* in, int H, int W, int C, __half* out, int Ho, int Wo, cudaStream_t s);
+int nearest_add_f16(__half* fine, int Hf, int Wf, const __half* coarse, int Hc, int Wc, int C, cudaStream_t s);
+int subsample2_f16(const __half* in, int H, int W, int C, __half* out, int Ho, int Wo, cudaStream_t s);
+int gn_partial_floats(int HW, int C);
+int groupnorm_relu_f16(const float* x, int H, int W, int C, int groups, const float* gamma, const float* beta, float* part,
+                       float* stats, __half* out_padded, __half* out_dense, cudaStream_t s);
+// bilinear, align_corners=False, padded NHWC fp16 -> padded NHWC fp16 (pitch Cdst >= Csrc); coord: append the
+// generate_coordinate channels (x, y in [-1,1] of the SOURCE grid, interpolated like the features) at [Csrc, Csrc+2);
+// accumulate: dst += value
+int resize_bilinear_f16(const __half* src, int Hs, int Ws, int Csrc, __half* dst, int Hd, int Wd, int Cdst, int coord,
+                        int accumulate, cudaStream_t s);
+// decode (solov2_head.py:582-766, matrix_nms.py)
+int solo_candidates(const float* cls_logits, int S, int cell0, int num_classes, float score_thr, float stride, SoloCand* cand,
+                    int* count, int cap, cudaStream_t s);
+int solo_sort_candidates(const SoloCand* cand, int* count, int cap, SoloCand* sorted, cudaStream_t s);  // nonzero() order
+int solo_gather_kernels(const SoloCand* cand, const int* count, int cap, const float* const* lvl_kernels,
+                        const int* lvl_cell0, int levels, int num_classes, int C, __half* out, cudaStream_t s);
+int solo_mask_stats(const __half* masks, int HW, float mask_thr, SoloCand* cand, const int* count, int cap,
+                    cudaStream_t s);
+int solo_rank(const SoloCand* cand, const int* count, int cap, int nms_pre, int* top, int* n_top,
+              cudaStream_t s);
+int solo_binarize(const __half* masks, int HW, float mask_thr, const int* top, const int* n_top, int nms_pre, __half* bin,
+                  cudaStream_t s);
+int solo_matrix_nms(const float* inter, int ld, const SoloCand* cand, const int* top, const int* n_top, int num_classes,
+                    float sigma, float filter_thr, int max_num, int* keep, float* keep_score, int* keep_label, int* n_keep,
+                    cudaStream_t s);
+int solo_final_masks(const __half* masks, int fh, int fw, int h, int w, int H, int W, float mask_thr, const int* keep,
+                     const float* keep_score, const int* keep_label, const int* n_keep, int max_num, float confidence,
+                     uint8_t* inst_masks, uint8_t* union_mask, cudaStream_t s);
+
+}  // namespace prisma

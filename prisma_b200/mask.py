@@ -1,0 +1,89 @@
+"""Host-side mirror of the reference mask band interface (bands/mask_mmdet.py) on top of the C ABI.
+
+`SoloV2Engine(state_dict)` ≙ `init_detector(CONFIG, MODEL)` (mask_mmdet.py:38-41); `infer(rgb)` ≙
+`inference_detector(model, img)` (apis/inference.py:99-162) plus the band's union loop (mask_mmdet.py:43-61,134-146);
+`inference_detector(rgb)` returns the reference's (bbox_results, mask_results) structure
+(models/detectors/single_stage_instance_seg.py:184-250).  All arithmetic happens in libprisma_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import PrismaError, check, fptr, lib, u8ptr, c_i64_p
+
+CLASSES = ['person', 'bird', 'cat', 'dog', 'horse', 'sheep', 'cow', 'elephant', 'bear', 'zebra', 'giraffe']  # mask_mmdet.py:29
+NUM_CLASSES = 80
+MAX_PER_IMG = 100
+
+
+class SoloV2Engine:
+    def __init__(self, state_dict=None, device=0, variant="r101"):
+        self._h = C.c_void_p()
+        check(lib().prisma_mask_create(variant.encode(), device, C.byref(self._h)))
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    def load_state_dict(self, state_dict):
+        l = lib()
+        for name, t in state_dict.items():
+            a = t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+            if a.dtype.kind != "f":
+                continue  # num_batches_tracked
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            shape = (C.c_int64 * max(a.ndim, 1))(*(a.shape if a.ndim else (1,)))
+            check(l.prisma_mask_load_tensor(self._h, name.encode(), fptr(a), C.cast(shape, c_i64_p), max(a.ndim, 1)))
+        check(l.prisma_mask_finalize(self._h))
+
+    def infer(self, rgb, confidence=0.5, want_instances=False):
+        """HxWx3 u8 RGB -> dict(union HxW u8, scores [n], labels [n], masks [n,H,W] bool | None, ms)."""
+        rgb = np.ascontiguousarray(rgb)
+        if rgb.dtype != np.uint8 or rgb.ndim != 3 or rgb.shape[2] != 3:
+            raise PrismaError("expected an HxWx3 uint8 RGB frame")
+        h, w = rgb.shape[:2]
+        union = np.empty((h, w), np.uint8)
+        scores = np.zeros(MAX_PER_IMG, np.float32)
+        labels = np.zeros(MAX_PER_IMG, np.int32)
+        inst = np.empty((MAX_PER_IMG, h, w), np.uint8) if want_instances else None
+        n, ms = C.c_int(), C.c_float()
+        check(lib().prisma_mask_infer(self._h, u8ptr(rgb), h, w, float(confidence), u8ptr(union), C.byref(n), fptr(scores),
+                                      labels.ctypes.data_as(C.POINTER(C.c_int32)), u8ptr(inst), C.byref(ms)))
+        k = n.value
+        return dict(union=union, scores=scores[:k].copy(), labels=labels[:k].copy(),
+                    masks=inst[:k].astype(bool) if want_instances else None, ms=ms.value)
+
+    def inference_detector(self, rgb):
+        """(bbox_results, mask_results) as the reference's format_results: 80 arrays (n,5) [0,0,0,0,score] and 80 lists of
+        HxW bool masks."""
+        r = self.infer(rgb, want_instances=True)
+        bbox = [np.zeros((0, 5), np.float32) for _ in range(NUM_CLASSES)]
+        masks = [[] for _ in range(NUM_CLASSES)]
+        for c in range(NUM_CLASSES):
+            sel = r["labels"] == c
+            if sel.any():
+                b = np.zeros((int(sel.sum()), 5), np.float32)
+                b[:, 4] = r["scores"][sel]
+                bbox[c] = b
+                masks[c] = [m for m in r["masks"][sel]]
+        return bbox, masks
+
+    def read_tap(self, name, shape):
+        out = np.empty(int(np.prod(shape)), np.float32)
+        n = check(lib().prisma_mask_read_tap(self._h, name.encode(), fptr(out), out.size))
+        assert n == out.size, (name, n, out.size)
+        return out.reshape(shape)
+
+    def work(self, h, w):
+        out = (C.c_double * 8)()
+        check(lib().prisma_mask_work(self._h, h, w, out))
+        return dict(flop=out[0], launches=int(out[1]), resized=(int(out[2]), int(out[3])), padded=(int(out[4]), int(out[5])))
+
+    def close(self):
+        if self._h:
+            lib().prisma_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

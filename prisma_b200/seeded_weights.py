@@ -177,6 +177,84 @@ def make_midas_weights(variant="dpt_large", seed=0):
     return sd
 
 
+SOLO_CONFIGS = {
+    # models/solov2_r101_fpn_3x_coco.py (downloaded config, not in tree; values from upstream mmdet 2.x):
+    # ResNet-101 (3,4,23,3), FPN 256 x 5 levels, SOLOV2Head(feat 512, 4 stacked convs, grids 40/36/24/16/12,
+    # strides 8/8/16/32/32, mask feature head 128 -> 256 at stride 4, GN-32), test pipeline scale (1333, 800)
+    "r101": dict(layers=[3, 4, 23, 3], img_scale=(1333, 800), num_grids=[40, 36, 24, 16, 12], strides=[8, 8, 16, 32, 32],
+                 feat=512, mask_feat=128, mask_out=256, num_classes=80),
+    # test-size twin of the same graph (CPU oracle in seconds): one bottleneck per stage, small test scale
+    "tiny": dict(layers=[1, 1, 1, 1], img_scale=(448, 256), num_grids=[40, 36, 24, 16, 12], strides=[8, 8, 16, 32, 32],
+                 feat=512, mask_feat=128, mask_out=256, num_classes=80),
+}
+
+
+def make_solo_weights(variant="r101", seed=0):
+    """state_dict of mmdet SOLOv2 (backbone.* ResNet, neck.* FPN, mask_head.* SOLOV2Head) with seeded values.
+
+    Backbone convs: kaiming-normal(fan_out) as mmdet's ResNet init; BatchNorm (eval, frozen) with non-trivial affine and
+    running statistics so the fold is tested.  Head: wider than mmdet's std = 0.01 / bias_prob = 0.01 init so that, with
+    random features, a few hundred grid cells pass score_thr, a few dozen end above 0.5 and the dynamic-conv masks are
+    structured blobs instead of sigmoid(0) noise -- the decode path (NMS, thresholds, resizes) is then exercised."""
+    c = SOLO_CONFIGS[variant]
+    sd = {}
+
+    def conv(name, out_c, in_c, k, std=None, bias=None):
+        std = std if std is not None else (2.0 / (out_c * k * k)) ** 0.5
+        sd[name + ".weight"] = _normal(name + ".weight", seed, (out_c, in_c, k, k), std)
+        if bias is not None:
+            sd[name + ".bias"] = _normal(name + ".bias", seed, (out_c,), 0.02, bias)
+
+    def bn(name, ch, gain=1.0):
+        sd[name + ".weight"] = _normal(name + ".weight", seed, (ch,), 0.1, gain)
+        sd[name + ".bias"] = _normal(name + ".bias", seed, (ch,), 0.05)
+        sd[name + ".running_mean"] = _normal(name + ".running_mean", seed, (ch,), 0.1)
+        sd[name + ".running_var"] = _uniform(name + ".running_var", seed, (ch,), 0.5, 1.5)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    def gn(name, ch):
+        sd[name + ".weight"] = _normal(name + ".weight", seed, (ch,), 0.1, 1.0)
+        sd[name + ".bias"] = _normal(name + ".bias", seed, (ch,), 0.05)
+
+    conv("backbone.conv1", 64, 3, 7)
+    bn("backbone.bn1", 64)
+    inplanes = 64
+    for li, (planes, blocks) in enumerate(zip([64, 128, 256, 512], c["layers"])):
+        for b in range(blocks):
+            p = f"backbone.layer{li + 1}.{b}."
+            conv(p + "conv1", planes, inplanes, 1)
+            bn(p + "bn1", planes)
+            conv(p + "conv2", planes, planes, 3)
+            bn(p + "bn2", planes)
+            conv(p + "conv3", planes * 4, planes, 1)
+            bn(p + "bn3", planes * 4, gain=0.5)  # keeps the residual stream bounded over 33 blocks
+            if b == 0:
+                conv(p + "downsample.0", planes * 4, inplanes, 1)
+                bn(p + "downsample.1", planes * 4, gain=0.5)
+            inplanes = planes * 4
+    for i, cin in enumerate([256, 512, 1024, 2048]):
+        conv(f"neck.lateral_convs.{i}.conv", 256, cin, 1, std=(1.0 / cin) ** 0.5, bias=0.0)
+        conv(f"neck.fpn_convs.{i}.conv", 256, 256, 3, std=(1.0 / (256 * 9)) ** 0.5, bias=0.0)
+    m = "mask_head.mask_feature_head."
+    F = c["mask_feat"]
+    for i in range(4):
+        for j in range(max(i, 1)):
+            cin = (256 + (2 if i == 3 else 0)) if j == 0 else F
+            conv(f"{m}convs_all_levels.{i}.conv{j}.conv", F, cin, 3, std=(2.0 / (cin * 9)) ** 0.5)
+            gn(f"{m}convs_all_levels.{i}.conv{j}.gn", F)
+    conv(m + "conv_pred.conv", c["mask_out"], F, 1, std=(2.0 / F) ** 0.5)
+    gn(m + "conv_pred.gn", c["mask_out"])
+    h = "mask_head."
+    for i in range(4):
+        conv(f"{h}kernel_convs.{i}.conv", c["feat"], 258 if i == 0 else c["feat"], 3, std=(2.0 / ((258 if i == 0 else c["feat"]) * 9)) ** 0.5)
+        gn(f"{h}kernel_convs.{i}.gn", c["feat"])
+        conv(f"{h}cls_convs.{i}.conv", c["feat"], 256 if i == 0 else c["feat"], 3, std=(2.0 / ((256 if i == 0 else c["feat"]) * 9)) ** 0.5)
+        gn(f"{h}cls_convs.{i}.gn", c["feat"])
+    conv(h + "conv_cls", c["num_classes"], c["feat"], 3, std=0.045, bias=-8.0)
+    conv(h + "conv_kernel", c["mask_out"], c["feat"], 3, std=0.006, bias=0.0)
+    return sd
+
+
 def make_raft_weights(seed=0):
     """state_dict of RAFT(args) (bands/raft/raft.py:24-57), seeded.
 

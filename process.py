@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 from bands.common.meta import add_band, create_metadata, is_video, set_default_band, write_metadata  # noqa: E402
 from bands.common.media import VideoReader, open_rgb  # noqa: E402
 
-ACCELERATED = {"depth_anything", "depth_midas", "flow_raft"}  # mask_mmdet: next row of SURVEY.md section 8
+ACCELERATED = {"depth_anything", "depth_midas", "flow_raft", "mask_mmdet"}
 
 
 def run(band, folder, extra=()):
@@ -35,6 +35,7 @@ def main(argv=None):
     p.add_argument("--depth", "-d", type=str, default="depth_anything")
     p.add_argument("--flow", "-f", type=str, default="")
     p.add_argument("--encoder", type=str, default="vitl")
+    p.add_argument("--mask", action="store_true", help="also run the mask band (the reference always does, process.py:207)")
     p.add_argument("--seeded-weights", action="store_true")
     a = p.parse_args(argv)
     base, ext = os.path.splitext(os.path.basename(a.input))
@@ -51,10 +52,12 @@ def main(argv=None):
         img = open_rgb(a.input)
         data.update(width=img.shape[1], height=img.shape[0])
     write_metadata(folder, data)
+    if a.mask:  # reference process.py:207: run("mask_mmdet", folder, subpath=True, ...)
+        run("mask_mmdet", folder, ["--subpath", "mask"] + (["--seeded-weights"] if a.seeded_weights else []))
     extra = ["--encoder", a.encoder] + (["--seeded-weights"] if a.seeded_weights else [])
     bands = ["depth_anything", "depth_midas"] if a.depth == "all" else [a.depth]
     for b in bands:
-        run(b, folder, extra if b == "depth_anything" else ())
+        run(b, folder, extra if b == "depth_anything" else (["--seeded-weights"] if a.seeded_weights else []))
     if "depth_anything" in bands:
         set_default_band(folder, "depth", "depth_anything")
     if a.flow:

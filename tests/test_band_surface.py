@@ -142,3 +142,13 @@ def test_midas_band_writes_video_csv_and_frames(tmp_path):
     assert frames == ["00000.npy", "00000.png", "00001.npy", "00001.png", "00002.npy", "00002.png"]
     pred = np.load(folder / "depth_midas_frames" / "00001.npy")
     assert pred.shape == (240, 320) and pred.dtype == np.float32 and np.float32(pred.min()) == np.float32(mins[1])
+
+
+def test_mask_band_cli_matches_reference_flags():
+    sys.path.insert(0, ROOT)
+    from bands import mask_mmdet as band
+    a = band.build_parser().parse_args(["-i", "x.mp4", "-o", "y.mp4", "-c", "0.6", "--subpath", "mask"])
+    assert (a.input, a.output, a.confidence, a.subpath, a.sdf) == ("x.mp4", "y.mp4", 0.6, "mask", False)
+    assert band.BAND == "mask" and band.CONFIDENCE_THRESHOLD == 0.5 and len(band.CLASSES) == 11
+    with pytest.raises(NotImplementedError):
+        band.main(["-i", "x.png", "--sdf"])
