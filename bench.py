@@ -214,6 +214,29 @@ def midas_extras(device):
             "tflops": flop / (ms * 1e-3) / 1e12, "launches_per_pass": w["launches"]}
 
 
+def mask_extras(device):
+    """Fourth workload: the mask band (SOLOv2 R-101, BASELINE north_star band) on synthetic 1080p frames: host frame in,
+    union mask + instance list out (H2D / D2H inside the wall time; `ms` is the device time of the pass)."""
+    from prisma_b200.mask import SoloV2Engine
+    from prisma_b200.seeded_weights import make_solo_weights
+    from oracle.frames import synthetic_frame
+    eng = SoloV2Engine(make_solo_weights("r101", 0), device=device)
+    f = [synthetic_frame(1080, 1920, t) for t in range(2)]
+    for i in range(3):
+        eng.infer(f[i % 2])
+    n, dev_ms = 8, 0.0
+    t0 = time.perf_counter()
+    for i in range(n):
+        dev_ms += eng.infer(f[i % 2])["ms"]
+    e2e_s = time.perf_counter() - t0
+    w = eng.work(1080, 1920)
+    eng.close()
+    return {"workload": "synthetic 1080p frames, mask_mmdet SOLOv2 R-101 (768x1344 net input), one frame per pass",
+            "frames_per_s_device": n / (dev_ms * 1e-3), "frames_per_s_e2e": n / e2e_s, "ms_per_pass_device": dev_ms / n,
+            "algorithmic_gflop_per_pass": w["flop"] / 1e9, "tflops": w["flop"] / (dev_ms / n * 1e-3) / 1e12,
+            "launches_per_pass": w["launches"]}
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     from prisma_b200.depth import DepthAnythingEngine
@@ -300,6 +323,7 @@ def run_b200(args, rank, local_rank, world):
         if world == 1:
             out["extra"] = raft_extras(local_rank, peaks)
             out["extra"]["depth_midas_720p"] = midas_extras(local_rank)
+            out["extra"]["mask_mmdet_1080p"] = mask_extras(local_rank)
         if world == 1 and not args.no_cpu:
             cores = cpu_threads()
             fps, dt = cpu_baseline_frames(3, cores)

@@ -152,3 +152,28 @@ def test_mask_band_cli_matches_reference_flags():
     assert band.BAND == "mask" and band.CONFIDENCE_THRESHOLD == 0.5 and len(band.CLASSES) == 11
     with pytest.raises(NotImplementedError):
         band.main(["-i", "x.png", "--sdf"])
+
+
+@pytest.mark.gpu
+def test_mask_band_writes_mask_video_and_colmap_frames(tmp_path):
+    import cv2
+    from oracle.frames import synthetic_frame
+    folder = tmp_path / "clip"
+    folder.mkdir()
+    w = cv2.VideoWriter(str(folder / "rgba.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
+    for t in range(2):
+        w.write(synthetic_frame(240, 320, t)[..., ::-1].copy())
+    w.release()
+    json.dump({"bands": {"rgba": {"url": "rgba.mp4"}}, "width": 320, "height": 240, "frames": 2, "fps": 24.0},
+              open(folder / "metadata.json", "w"))
+    rc = subprocess.call([sys.executable, os.path.join(ROOT, "bands", "mask_mmdet.py"), "-i", str(folder), "--subpath", "mask",
+                          "--seeded-weights", "-c", "0.5"])
+    assert rc == 0
+    meta = json.load(open(folder / "metadata.json"))
+    assert meta["bands"]["mask"] == {"url": "mask.mp4", "ids": ['person', 'bird', 'cat', 'dog', 'horse', 'sheep', 'cow', 'elephant',
+                                                              'bear', 'zebra', 'giraffe'], "folder": "mask"}
+    assert os.path.getsize(folder / "mask.mp4") > 0
+    frames = sorted(os.listdir(folder / "mask"))
+    assert frames == ["00000.png", "00001.png"]
+    png = cv2.imread(str(folder / "mask" / "00000.png"))
+    assert png.shape == (240, 320, 3) and set(np.unique(png)) <= {0, 1, 254, 255}   # 255 - (255 * count mod 256)
