@@ -11,7 +11,7 @@ import numpy as np
 from .media import VideoReader, VideoWriter, create_folder, write_rgb
 
 
-def process_depth_video(model, a, data, band, chunk=24, pass_frames=12):
+def process_depth_video(model, a, data, band, chunk=24, pass_frames=12, flip=True):
     reader = VideoReader(a.input)
     out = VideoWriter(reader.width, reader.height, reader.get_avg_fps(), a.output)
     folder = os.path.dirname(a.output)
@@ -35,7 +35,7 @@ def process_depth_video(model, a, data, band, chunk=24, pass_frames=12):
             if a.npy:
                 np.save(os.path.join(sub or folder, "{:05d}.npy".format(index)), pred[k])
             if sub:  # reference :222-223 / depth_midas.py:150-151: write_depth(normalize, flip, heatmap, encode_range)
-                png, _, _ = model.encode_png(pred[k], flip=True)
+                png, _, _ = model.encode_png(pred[k], flip=flip)
                 write_rgb(os.path.join(sub, "{:05d}.png".format(index)), png)
             out.write(rgb[k])
             mins.append(float(mn[k]))

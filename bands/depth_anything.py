@@ -6,8 +6,8 @@ process_image(args), process_video(args), the CLI flags of bands/depth_anything.
 (<band>.mp4|png, <band>_min.csv, <band>_max.csv, optional <sub>/%05d.npy) and the metadata.json keys
 (:155-166,241-251).  The model call and the numpy encode are replaced by libprisma_b200.so; there is no CPU path.
 
-Additions: --weights (a DPT_DINOv2 state_dict: torch .pth/.pt or .npz), --seeded-weights (offline test weights),
---device, --batch.  `--metric indoor|outdoor` (ZoeDepth head) is a SURVEY section 8f "next" row and raises here.
+`--metric indoor|outdoor` runs the ZoeDepth metric head (one frame per pass, no flip in the encode, reference :188).
+Additions: --weights (state_dict: torch .pth/.pt or .npz), --seeded-weights (offline test weights), --device.
 """
 import argparse
 import os
@@ -23,6 +23,8 @@ from bands.common.media import open_rgb, write_rgb  # noqa: E402
 BAND = "depth_anything"
 DEVICE = 0
 WEIGHTS = "models/depth_anything_{}14.pth"
+METRIC_WEIGHTS = {"indoor": "models/depth_anything_metric_depth_indoor.pt",     # reference :38-39
+                  "outdoor": "models/depth_anything_metric_depth_outdoor.pt"}
 
 model = None
 data = None
@@ -32,9 +34,9 @@ args = None
 def _load_state_dict(a):
     if a.seeded_weights:
         # seeded random weights (no checkpoint is reachable offline)
-        from prisma_b200.seeded_weights import make_da_weights
-        return make_da_weights(a.encoder, 0)
-    path = a.weights or WEIGHTS.format(a.encoder)
+        from prisma_b200.seeded_weights import make_da_weights, make_zoe_weights
+        return make_zoe_weights(a.encoder, 0) if a.metric != "none" else make_da_weights(a.encoder, 0)
+    path = a.weights or (METRIC_WEIGHTS[a.metric] if a.metric != "none" else WEIGHTS.format(a.encoder))
     if path.endswith(".npz"):
         return dict(np.load(path))
     import torch
@@ -43,10 +45,13 @@ def _load_state_dict(a):
 
 
 def init_model():
-    """reference :48-76 (relative-depth branch): build the engine and upload the converted weights."""
+    """reference :48-76: relative model, or (--metric indoor|outdoor, :52-57) the ZoeDepth metric model."""
     global model
-    from prisma_b200.depth import DepthAnythingEngine
-    model = DepthAnythingEngine(args.encoder, _load_state_dict(args), device=args.device)
+    from prisma_b200.depth import DepthAnythingEngine, ZoeDepthEngine
+    if args.metric != "none":
+        model = ZoeDepthEngine(_load_state_dict(args), device=args.device, encoder=args.encoder)
+    else:
+        model = DepthAnythingEngine(args.encoder, _load_state_dict(args), device=args.device)
     return model
 
 
@@ -68,7 +73,7 @@ def process_image(a):
 
 
 def process_video(a):
-    process_depth_video(model, a, data, BAND)
+    process_depth_video(model, a, data, BAND, flip=(a.metric == "none"))  # reference :188
 
 
 def build_parser():
@@ -89,8 +94,8 @@ def build_parser():
 def main(argv=None):
     global args, data
     args = build_parser().parse_args(argv)
-    if args.metric != "none":
-        raise NotImplementedError("--metric indoor|outdoor (ZoeDepth head) is not built yet (SURVEY.md section 8f row 1)")
+    if args.metric != "none" and args.encoder != "vitl" and not args.seeded_weights:
+        raise ValueError("the metric checkpoints are ViT-L models (base_models/depth_anything.py:339)")
     if args.ply:
         print("--ply is outside the engine's scope (optional export, SURVEY.md section 2); ignored")
     data = load_metadata(args.input)

@@ -214,6 +214,20 @@ def midas_extras(device):
             "tflops": flop / (ms * 1e-3) / 1e12, "launches_per_pass": w["launches"]}
 
 
+def zoe_extras(device):
+    """depth_anything --metric outdoor (what the reference's process.py passes by default): ZoeDepth metric head on ViT-L,
+    392x518 network input, one frame per pass, frames resident."""
+    from prisma_b200.depth import ZoeDepthEngine
+    from prisma_b200.seeded_weights import make_zoe_weights
+    eng = ZoeDepthEngine(make_zoe_weights("vitl", 0), device=device, encoder="vitl")
+    eng.time_resident(H, W, 5, 1)
+    ms = eng.time_resident(H, W, 30, 1)
+    w = eng.work(H, W, 1)
+    eng.close()
+    return {"workload": "synthetic 720p frames, depth_anything --metric (ZoeDepth head, 392x518 net input), one frame per pass",
+            "frames_per_s_device": 1e3 / ms, "ms_per_pass": ms, "launches_per_pass": w["launches"]}
+
+
 def mask_extras(device):
     """Fourth workload: the mask band (SOLOv2 R-101, BASELINE north_star band) on synthetic 1080p frames: host frame in,
     union mask + instance list out (H2D / D2H inside the wall time; `ms` is the device time of the pass)."""
@@ -324,6 +338,7 @@ def run_b200(args, rank, local_rank, world):
             out["extra"] = raft_extras(local_rank, peaks)
             out["extra"]["depth_midas_720p"] = midas_extras(local_rank)
             out["extra"]["mask_mmdet_1080p"] = mask_extras(local_rank)
+            out["extra"]["depth_anything_metric_720p"] = zoe_extras(local_rank)
         if world == 1 and not args.no_cpu:
             cores = cpu_threads()
             fps, dt = cpu_baseline_frames(3, cores)

@@ -179,6 +179,8 @@ def dpt_head(sd, feats, ph, pw, q=_ident, taps=None):
     o = _conv(p1, sd[s + "output_conv1.weight"], sd[s + "output_conv1.bias"], q, padding=1)
     o = F.interpolate(o, (ph * 14, pw * 14), mode="bilinear", align_corners=True)
     o = F.relu(_conv(o, sd[s + "output_conv2.0.weight"], sd[s + "output_conv2.0.bias"], q, padding=1))
+    if taps is not None:
+        taps["out_conv_act"] = o  # output of output_conv2[1] (the hook of the metric head, base_models/depth_anything.py:302-304)
     o = F.relu(_conv(o, sd[s + "output_conv2.2.weight"], sd[s + "output_conv2.2.bias"], q))
     return o
 

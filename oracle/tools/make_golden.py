@@ -199,8 +199,68 @@ def golden_png():
     print("[png] oracle == reference write_depth; wrote fixture")
 
 
+def golden_zoe(encoder="vits", H=240, W=320):
+    """Metric path of the depth_anything band: ZoeDepth(DepthAnythingCore(DPT_DINOv2)) built exactly as ZoeDepth.build
+    does minus the checkpoint loads (zoedepth_v1.py:249-260, base_models/depth_anything.py:330-349), seeded weights
+    loaded strict, band pre/post of bands/depth_anything.py:106-119 and the video-loop encode (:215-220, flip=False)."""
+    import json
+    import types
+    from PIL import Image
+    from torchvision import transforms
+    sys.modules["json5"] = types.ModuleType("json5")  # utils/config.py:25 imports json5; the config file is plain JSON
+    sys.modules["json5"].load = json.load
+    sys.modules["json5"].loads = json.loads
+    from patchfusion.zoedepth.utils.config import get_org_config
+    from patchfusion.zoedepth.models.zoedepth.zoedepth_v1 import ZoeDepth
+    from patchfusion.zoedepth.models.base_models.depth_anything import DepthAnythingCore
+    from patchfusion.zoedepth.models.base_models.dpt_dinov2.dpt import DPT_DINOv2
+    import common.encode as renc
+    from oracle import zoe as ozoe
+    from oracle.weights import make_zoe_weights, ZOE_CONFIG
+
+    cfg = get_org_config("zoedepth", "eval", dataset=None)
+    for k in ("n_bins", "bin_embedding_dim", "n_attractors", "attractor_alpha", "attractor_gamma", "min_temp", "max_temp"):
+        assert cfg[k] == ZOE_CONFIG[k], (k, cfg[k], ZOE_CONFIG[k])
+    assert tuple(cfg["img_size"]) == ZOE_CONFIG["img_size"] and cfg["bin_centers_type"] == "softplus"
+    assert cfg["attractor_kind"] == "mean" and cfg["attractor_type"] == "inv"
+    c = DA_CONFIGS[encoder]
+    net = DPT_DINOv2(encoder, c["features"], False, c["out_channels"], use_clstoken=False)
+    kw = DepthAnythingCore.parse_img_size(dict(img_size=list(cfg["img_size"])))
+    core = DepthAnythingCore(net, trainable=False, fetch_features=True, freeze_bn=True, img_size=kw["img_size"],
+                             keep_aspect_ratio=cfg.get("force_keep_ar", False))
+    core.output_channels = [c["features"]] * 5  # set_output_channels() hard-codes ViT-L's 256
+    model = ZoeDepth(core, **{k: v for k, v in cfg.items() if k not in ("midas_model_type", "pretrained_resource", "use_pretrained_midas",
+                                                                         "train_midas", "freeze_midas_bn")}).eval()
+    sd = make_zoe_weights(encoder, 0)
+    print("[zoe] load_state_dict strict:", model.load_state_dict(sd, strict=True))
+    img = synthetic_frame(H, W, 0)
+    # --- reference: bands/depth_anything.py:106-119
+    img_pil = Image.fromarray(img)
+    image = transforms.ToTensor()(img_pil).unsqueeze(0)
+    pred_dict = model(image, dataset=None)
+    depth = pred_dict["metric_depth"].squeeze().detach()
+    pred_ref = np.asarray(Image.fromarray(depth.numpy()).resize(img_pil.size))
+    # --- oracle
+    taps = {}
+    pred_or = ozoe.zoe_infer(sd, img, encoder, taps)
+    e_net = rel(taps["metric"].squeeze().numpy(), depth.numpy())
+    e = rel(pred_or, pred_ref)
+    print(f"[zoe] metric depth (392x518) err {e_net:.3e}; prediction at frame size err {e:.3e}")
+    assert e_net == 0.0 and np.array_equal(pred_or, pred_ref)
+    dmin, dmax = pred_ref.min(), pred_ref.max()
+    dn = (pred_ref - dmin) / (dmax - dmin)  # flip = (args.metric == 'none') = False
+    rgb_ref = (renc.heat_to_rgb(dn.astype(np.float64)) * 255).astype(np.uint8)
+    rgb_or, mn, mx = oda.da_encode(pred_or, flip=False)
+    assert np.array_equal(rgb_or, rgb_ref)
+    np.savez_compressed(os.path.join(GOLD, f"zoe_{encoder}_{H}x{W}.npz"), image=img, metric_net=depth.numpy(), prediction=pred_ref,
+                        rgb=rgb_ref, dmin=np.float32(dmin), dmax=np.float32(dmax))
+    print("[zoe] oracle == reference; wrote fixture")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sizes", "da_small", "da_vits", "raft", "png"]
+    which = sys.argv[1:] or ["sizes", "da_small", "da_vits", "raft", "png", "zoe"]
+    if "zoe" in which:
+        golden_zoe()
     if "sizes" in which:
         golden_sizes()
     if "da_small" in which:

@@ -17,12 +17,14 @@
 namespace prisma {
 
 // ------------------------------------------------------------------------------------------------ helpers
-struct DaCfg { int D, depth, heads, F, oc[4]; int family = FAMILY_DA; int hooks[4] = {0, 0, 0, 0}; };
+struct DaCfg { int D, depth, heads, F, oc[4]; int family = FAMILY_DA; int hooks[4] = {0, 0, 0, 0}; bool metric = false; };
 static bool da_cfg(const std::string& enc, DaCfg* c) {
   // MiDaS v3 DPT (hubconf DPT_Large -> DPTDepthModel(backbone="vitl16_384"): hooks [5,11,17,23], features 256,
   // reassemble channels [256,512,1024,1024]); "dpt_tiny" is a test-size twin of the same graph
   if (enc == "dpt_large") { *c = {1024, 24, 16, 256, {256, 512, 1024, 1024}, FAMILY_MIDAS, {5, 11, 17, 23}}; return true; }
   if (enc == "dpt_tiny") { *c = {384, 8, 6, 64, {48, 96, 192, 384}, FAMILY_MIDAS, {1, 3, 5, 7}}; return true; }
+  if (enc == "zoe_vits") { *c = {384, 12, 6, 64, {48, 96, 192, 384}}; c->metric = true; return true; }
+  if (enc == "zoe_vitl") { *c = {1024, 24, 16, 256, {256, 512, 1024, 1024}}; c->metric = true; return true; }
   if (enc == "vits") { *c = {384, 12, 6, 64, {48, 96, 192, 384}}; return true; }
   if (enc == "vitb") { *c = {768, 12, 12, 128, {96, 192, 384, 768}}; return true; }
   if (enc == "vitl") { *c = {1024, 24, 16, 256, {256, 512, 1024, 1024}}; return true; }
@@ -86,6 +88,7 @@ int DepthEngine::init(const std::string& enc, int dev) {
   D = c.D; depth = c.depth; heads = c.heads; F = c.F;
   for (int i = 0; i < 4; ++i) { oc[i] = c.oc[i]; hooks[i] = c.hooks[i]; }
   family = c.family;
+  metric = c.metric;
   if (family == FAMILY_MIDAS) { patch = 16; pos_grid = 24; }
   device = dev;
   int n = 0;
@@ -192,7 +195,8 @@ int DepthEngine::finalize() {
   PRISMA_CHECK(!finalized, "finalize called twice");
   PRISMA_CUDA_OK(cudaSetDevice(device));
   const bool midas = family == FAMILY_MIDAS;
-  const std::string p = midas ? "pretrained.model." : "pretrained.";
+  const std::string core = metric ? "core.core." : "";  // ZoeDepth wraps the relative model (zoedepth_v1.py:68, DepthAnythingCore.core)
+  const std::string p = midas ? "pretrained.model." : core + "pretrained.";
   const int n_pos = pos_grid * pos_grid + 1, pk = 3 * patch * patch, pkpad = round_up(pk, 64);
   PRISMA_TRY(up_f32(p + "cls_token", {1, 1, D}, &w.cls));
   PRISMA_TRY(up_f32(p + "pos_embed", {1, n_pos, D}, &w.pos));
@@ -237,7 +241,7 @@ int DepthEngine::finalize() {
 
   // head tensor names: Depth-Anything DPTHead (d_anything/dpt.py:39-100) / MiDaS DPT (midas/backbones/vit.py
   // act_postprocessN = [readout, Transpose, Unflatten, Conv1x1, resize], midas/dpt_depth.py scratch.*)
-  const std::string h = "depth_head.";
+  const std::string h = core + "depth_head.";
   auto pp = [&](int i) { return "pretrained.act_postprocess" + std::to_string(i + 1) + "."; };
   if (midas)
     for (int i = 0; i < 4; ++i) {
@@ -293,8 +297,37 @@ int DepthEngine::finalize() {
     if (!t) return -1;
     w.oc3_b = t->data[0];
   }
+  if (metric) {
+    PRISMA_TRY(up_lin1x1("conv2", F, F, &w.z_conv2));
+    PRISMA_TRY(up_lin1x1("seed_bin_regressor._net.0", 256, F, &w.z_seed0));
+    PRISMA_TRY(up_lin1x1("seed_bin_regressor._net.2", 64, 256, &w.z_seed2));
+    PRISMA_TRY(up_lin1x1("seed_projector._net.0", 128, F, &w.z_sproj0));
+    PRISMA_TRY(up_lin1x1("seed_projector._net.2", 128, 128, &w.z_sproj2));
+    const int n_attr[4] = {16, 8, 4, 1};
+    for (int i = 0; i < 4; ++i) {
+      const std::string si = std::to_string(i);
+      PRISMA_TRY(up_lin1x1("projectors." + si + "._net.0", 128, F, &w.z_proj0[i]));
+      PRISMA_TRY(up_lin1x1("projectors." + si + "._net.2", 128, 128, &w.z_proj2[i]));
+      PRISMA_TRY(up_lin1x1("attractors." + si + "._net.0", 128, 128, &w.z_att0[i]));
+      PRISMA_TRY(up_lin1x1("attractors." + si + "._net.2", n_attr[i], 128, &w.z_att2[i]));
+    }
+    PRISMA_TRY(up_lin1x1("conditional_log_binomial.mlp.0", 80, 161, &w.z_clb0));
+    PRISMA_TRY(up_lin1x1("conditional_log_binomial.mlp.2", 4, 80, &w.z_clb2));
+  }
   host.clear();
   finalized = true;
+  return 0;
+}
+
+// 1x1 conv weight [N][K][1][1] + bias -> fp16 [round_up(N,256)][round_up(K,64)], fp32 bias padded to a multiple of 8
+int DepthEngine::up_lin1x1(const std::string& name, int N, int K, DaWeights::Lin* out) {
+  const HostTensor* t = get(name + ".weight", {N, K, 1, 1});
+  if (!t) return -1;
+  PRISMA_TRY(up_matrix(allocs, &out->w, N, round_up(K, 64), [&](int n, __half* row) {
+    for (int k = 0; k < K; ++k) row[k] = __float2half_rn(t->data[(size_t)n * K + k]);
+  }));
+  PRISMA_TRY(up_f32(name + ".bias", {N}, &out->b));
+  out->n = N; out->k = K;
   return 0;
 }
 
@@ -348,6 +381,8 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
   PRISMA_CHECK(finalized, "weights not finalized");
   PRISMA_CHECK(Bt >= 1 && Bt <= 64, "batch must be in [1,64]");
   if (plan_H == H && plan_W == W && batch == Bt) return 0;
+  PRISMA_CHECK(!metric || Bt == 1, "the metric (ZoeDepth) head runs one frame per pass");
+  plan_W_req = W;
   batch = Bt;
   PRISMA_CUDA_OK(cudaSetDevice(device));
   PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
@@ -359,7 +394,9 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
   plan_H = plan_W = 0;
 
   const bool midas = family == FAMILY_MIDAS;
-  if (midas) midas_net_size(W, H, &wn, &hn); else da_net_size(W, H, &wn, &hn);
+  if (midas) midas_net_size(W, H, &wn, &hn);
+  else if (metric) { hn = 392; wn = 518; }  // config_zoedepth.json img_size, keep_aspect_ratio False (PrepForMidas)
+  else da_net_size(W, H, &wn, &hn);
   PRISMA_CHECK(hn >= patch * 2 && wn >= patch * 2, "frame too small for the network input");
   ph = hn / patch; pw = wn / patch;
   const int pkpad = round_up(3 * patch * patch, 64);
@@ -422,9 +459,12 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
   {
     const uint8_t* img = b.img; float* net = b.net_in; __half* pat = b.patches;
     const int hn_ = hn, wn_ = wn;
+    const bool metric_ = metric;
     add(G_PRE, "da_preprocess", [=](cudaStream_t s) {
-      for (int i = 0; i < Bt; ++i)
-        PRISMA_TRY(da_preprocess(img + (size_t)i * H * W * 3, H, W, net + (size_t)i * 3 * hn_ * wn_, hn_, wn_, s, midas));
+      for (int i = 0; i < Bt; ++i) {
+        if (metric_) PRISMA_TRY(zoe_preprocess(img + (size_t)i * H * W * 3, H, W, net + (size_t)i * 3 * hn_ * wn_, hn_, wn_, s));
+        else PRISMA_TRY(da_preprocess(img + (size_t)i * H * W * 3, H, W, net + (size_t)i * 3 * hn_ * wn_, hn_, wn_, s, midas));
+      }
       return 0;
     });
     const int patch_ = patch;
@@ -533,6 +573,7 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
   // refinenet4..1 (blocks.py:126-153).  The 1x1 out_conv commutes with the bilinear resize (both linear, the
   // interpolation weights sum to 1), so it runs before the resize on 4x fewer pixels.
   PMap path;  // output of the previous fusion block (already resized to this level)
+  PMap r_maps[4];  // refinenet4..1 outputs (the r4..r1 hooks of the metric head)
   for (int lvl = 3; lvl >= 0; --lvl) {
     const RefineW& k = w.ref[lvl];
     PMap t1, S, Sr, U, V;
@@ -566,6 +607,7 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
     { const __half* src = V.p; __half* dst = nxt.p; const int ih = V.H, iw = V.W, C = F;
       add(G_RESAMPLE, "upsample_ac", [=](cudaStream_t s) { return upsample_ac_f16(src, Bt, ih, iw, C, dst, oh, ow, nullptr, s); }); }
     path = nxt;
+    r_maps[3 - lvl] = nxt;
     if (lvl == 0) taps["path1"] = {path.p, path.H, path.W, path.C, 1};
   }
   // output_conv1 (3x3 F -> F/2) ; bilinear(align_corners=True) to (14ph,14pw) ; output_conv2 (3x3 -> 32, ReLU, 1x1 -> 1, ReLU)
@@ -576,15 +618,30 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
     PRISMA_TRY(add_conv3x3("output_conv1", path, w.oc1_w, F / 2, ep, 1, nullptr)); }
   { const __half* src = O1.p; __half* dst = O1u.p; const int ih = O1.H, iw = O1.W, C = F / 2, oh = hn, ow = wn;
     add(G_RESAMPLE, "upsample_ac", [=](cudaStream_t s) { return upsample_ac_f16(src, Bt, ih, iw, C, dst, oh, ow, nullptr, s); }); }
+  __half* act32 = nullptr;
+  if (metric) PRISMA_TRY(dev_alloc(plan_allocs, &act32, (size_t)Bt * hn * wn * 32));
   { GemmEpilogue ep; ep.bias = w.oc2_b; ep.act = 2; ep.head_w = w.oc3_w; ep.head_b = w.oc3_b; ep.head_out = b.depth;
+    if (metric) { ep.out_f16 = act32; ep.out_f16_ld = 32; }
     PRISMA_TRY(add_conv3x3("output_conv2_fused", O1u, w.oc2_w, 32, ep, 1, nullptr)); }
+  if (metric) PRISMA_TRY(build_metric_head(R[3], r_maps, act32, Bt));
   // (dpt.py:163-164: the final F.interpolate to (h,w) is the identity at equal size and the ReLU is idempotent)
 
   // ---- post-process (K10)
   {
     const float* d = b.depth; float* pred = b.pred; uint8_t* rgb = b.rgb; uint32_t* mm = b.mm; float* mmo = b.minmax;
     const int hn_ = hn, wn_ = wn, sms = num_sms;
-    if (!midas)
+    if (metric) {
+      // bands/depth_anything.py:113-119: PIL resize (mode "F", BICUBIC) of the metric depth to the frame, then the video
+      // loop's encode with flip = False (:188,215-220)
+      const float* md = zoe_metric; float* tmp = zoe_tmp;
+      add(G_POST, "depth_postprocess", [=](cudaStream_t s) {
+        for (int i = 0; i < Bt; ++i) {
+          PRISMA_TRY(pil_bicubic_resize_f32(md + (size_t)i * hn_ * wn_, hn_, wn_, tmp, pred + (size_t)i * H * W, H, W, s));
+          PRISMA_TRY(depth_encode_only(pred + (size_t)i * H * W, H, W, 0, rgb + (size_t)i * H * W * 3, mm + 2 * i, mmo + 2 * i, sms, s));
+        }
+        return 0;
+      });
+    } else if (!midas)
       add(G_POST, "depth_postprocess", [=](cudaStream_t s) {
         for (int i = 0; i < Bt; ++i)
           PRISMA_TRY(depth_postprocess(d + (size_t)i * hn_ * wn_, hn_, wn_, H, W, 1, pred + (size_t)i * H * W,
@@ -601,6 +658,7 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
         return 0;
       });
   }
+  if (metric) taps["metric_net"] = {zoe_metric, Bt * hn, wn, 1, 0};
   taps["net_input"] = {b.net_in, Bt * 3, hn * wn, 1, 0};
   taps["tokens"] = {b.tokens_tap, BT, D, 1, 0};
   for (int i = 0; i < 4; ++i) taps["feat" + std::to_string(i)] = {b.feat[i], BP, D, 1, 2};  // patch tokens only
@@ -622,6 +680,76 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
     PRISMA_CUDA_OK(cudaGraphInstantiate(&graph_exec, graph, 0));
     cudaGraphDestroy(graph);
   }
+  return 0;
+}
+
+// ZoeDepth.forward after the core (zoedepth_v1.py:150-199): every 1x1 conv is a GEMM over dense pixel rows (the first one
+// of each level reads the zero-bordered map and writes dense rows), the interpolations / attractors / log-binomial are the
+// zoe_kernels.  Embeddings and bin centres stay fp32 between levels; GEMM operands are fp16.
+int DepthEngine::build_metric_head(const PMap& btlnck, const PMap* r_maps, const __half* act32, int Bt) {
+  PRISMA_CHECK(Bt == 1, "the metric head runs one frame per pass");
+  const int zero_off[1] = {0};
+  auto lin = [&](const char* name, const __half* A, long long a_rows, int a_pitch, const DaWeights::Lin& L, int M, int act,
+                 __half* out16, float* out32, int out_ld, const PMap* padded_src) -> int {
+    GemmEpilogue ep; ep.bias = L.b; ep.act = act;
+    if (out16) { ep.out_f16 = out16; ep.out_f16_ld = out_ld; } else { ep.out_f32 = out32; ep.out_f32_ld = out_ld; }
+    if (padded_src) { ep.row_map = ROW_PAD2TOK; ep.in_w = padded_src->Wp(); ep.in_h = padded_src->Hp(); ep.img_rows = 0; ep.pad = 1; }
+    const int n_pad = round_up(L.n, 4);  // N % 4: the single attractor of the last level is padded with zero rows
+    return add_gemm(G_HEAD, name, A, a_rows, round_up(L.k, 64), a_pitch, L.w, M, n_pad, 1, zero_off, ep, 2.0 * M * (double)L.k * L.n);
+  };
+  // ---- bottleneck level: x_d0 = conv2(layer4_rn) ; seed bins ; seed embedding
+  const int P0 = btlnck.H * btlnck.W;
+  __half *x0 = nullptr, *s1 = nullptr, *e1 = nullptr;
+  float *b_prev = nullptr, *emb_prev = nullptr;
+  PRISMA_TRY(dev_alloc(plan_allocs, &x0, (size_t)P0 * round_up(F, 64)));
+  PRISMA_TRY(dev_alloc(plan_allocs, &s1, (size_t)P0 * 256));
+  PRISMA_TRY(dev_alloc(plan_allocs, &e1, (size_t)P0 * 128));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b_prev, (size_t)P0 * 64));
+  PRISMA_TRY(dev_alloc(plan_allocs, &emb_prev, (size_t)P0 * 128));
+  PRISMA_TRY(lin("zoe_conv2", btlnck.p, btlnck.rows(), F, w.z_conv2, (int)btlnck.rows(), 0, x0, nullptr, round_up(F, 64), &btlnck));
+  PRISMA_TRY(lin("zoe_seed0", x0, P0, round_up(F, 64), w.z_seed0, P0, 2, s1, nullptr, 256, nullptr));
+  PRISMA_TRY(lin("zoe_seed2", s1, P0, 256, w.z_seed2, P0, 5, nullptr, b_prev, 64, nullptr));
+  PRISMA_TRY(lin("zoe_sproj0", x0, P0, round_up(F, 64), w.z_sproj0, P0, 2, e1, nullptr, 128, nullptr));
+  PRISMA_TRY(lin("zoe_sproj2", e1, P0, 128, w.z_sproj2, P0, 0, nullptr, emb_prev, 128, nullptr));
+  int Hp_ = btlnck.H, Wp_ = btlnck.W;
+  const int n_attr[4] = {16, 8, 4, 1};
+  for (int i = 0; i < 4; ++i) {
+    const PMap& xb = r_maps[i];
+    const int Hi = xb.H, Wi = xb.W, Pi = Hi * Wi;
+    __half *t1 = nullptr, *xa = nullptr, *t2 = nullptr;
+    float *emb = nullptr, *Aout = nullptr, *bnew = nullptr;
+    PRISMA_TRY(dev_alloc(plan_allocs, &t1, (size_t)Pi * 128));
+    PRISMA_TRY(dev_alloc(plan_allocs, &xa, (size_t)Pi * 128));
+    PRISMA_TRY(dev_alloc(plan_allocs, &t2, (size_t)Pi * 128));
+    PRISMA_TRY(dev_alloc(plan_allocs, &emb, (size_t)Pi * 128));
+    PRISMA_TRY(dev_alloc(plan_allocs, &Aout, (size_t)Pi * 16));
+    PRISMA_TRY(dev_alloc(plan_allocs, &bnew, (size_t)Pi * 64));
+    PRISMA_TRY(lin("zoe_proj0", xb.p, xb.rows(), xb.C, w.z_proj0[i], (int)xb.rows(), 2, t1, nullptr, 128, &xb));
+    PRISMA_TRY(lin("zoe_proj2", t1, Pi, 128, w.z_proj2[i], Pi, 0, nullptr, emb, 128, nullptr));
+    { const float* ep_ = emb_prev; const int hp = Hp_, wp = Wp_;
+      add(G_RESAMPLE, "zoe_embed_add", [=](cudaStream_t s) { return zoe_embed_add(emb, Hi, Wi, 128, ep_, hp, wp, xa, s); }); }
+    PRISMA_TRY(lin("zoe_att0", xa, Pi, 128, w.z_att0[i], Pi, 2, t2, nullptr, 128, nullptr));
+    const int lda = round_up(n_attr[i], 4);
+    PRISMA_TRY(lin("zoe_att2", t2, Pi, 128, w.z_att2[i], Pi, 5, nullptr, Aout, lda, nullptr));
+    { const float* bp = b_prev; const int hp = Hp_, wp = Wp_, na = n_attr[i];
+      add(G_RESAMPLE, "zoe_attractor", [=](cudaStream_t s) { return zoe_attractor(Aout, lda, na, bp, hp, wp, Hi, Wi, 64, bnew, s); }); }
+    b_prev = bnew; emb_prev = emb; Hp_ = Hi; Wp_ = Wi;
+  }
+  // ---- conditional log-binomial at the network resolution
+  const int Pf = hn * wn;
+  __half *cat = nullptr, *hid = nullptr;
+  float* pt = nullptr;
+  PRISMA_TRY(dev_alloc(plan_allocs, &cat, (size_t)Pf * 192));
+  PRISMA_TRY(dev_alloc(plan_allocs, &hid, (size_t)Pf * 128));
+  PRISMA_TRY(dev_alloc(plan_allocs, &pt, (size_t)Pf * 4));
+  PRISMA_TRY(dev_alloc(plan_allocs, &zoe_metric, (size_t)Pf));
+  PRISMA_TRY(dev_alloc(plan_allocs, &zoe_tmp, (size_t)hn * std::max(plan_W_req, wn)));
+  { const float* rel = b.depth; const float* ep_ = emb_prev; const int he = Hp_, we = Wp_, h_ = hn, w_ = wn;
+    add(G_RESAMPLE, "zoe_concat", [=](cudaStream_t s) { return zoe_concat(act32, rel, ep_, he, we, h_, w_, cat, s); }); }
+  PRISMA_TRY(lin("zoe_clb0", cat, Pf, 192, w.z_clb0, Pf, 1, hid, nullptr, 128, nullptr));
+  PRISMA_TRY(lin("zoe_clb2", hid, Pf, 128, w.z_clb2, Pf, 5, nullptr, pt, 4, nullptr));
+  { const float* bc = b_prev; const int hc = Hp_, wc = Wp_, h_ = hn, w_ = wn; float* out = zoe_metric;
+    add(G_POST, "zoe_final", [=](cudaStream_t s) { return zoe_final(pt, bc, hc, wc, h_, w_, 64, 0.0212f, 50.0f, out, s); }); }
   return 0;
 }
 
@@ -688,7 +816,7 @@ int DepthEngine::infer_stream(const uint8_t* rgb, int n, int H, int W, int pass_
                               float* min_out, float* max_out) {
   PRISMA_CHECK(rgb != nullptr && H > 0 && W > 0 && n >= 1, "bad frame batch");
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  const int Bt = pass_frames > 0 ? std::min(pass_frames, 64) : 4;
+  const int Bt = metric ? 1 : (pass_frames > 0 ? std::min(pass_frames, 64) : 4);
   PRISMA_TRY(build_plan(H, W, Bt));
   PRISMA_TRY(ensure_stream_slots(H, W, Bt, depth_out != nullptr));
   if (mm_host_frames < (size_t)n) {
@@ -748,7 +876,7 @@ int DepthEngine::infer_image(const uint8_t* rgb, int H, int W, float* depth_out,
   PRISMA_TRY(run_steps(stream));
   unsigned long long* d_mag = nullptr;
   PRISMA_CUDA_OK(cudaMalloc(&d_mag, 16));
-  int r = depth_encode_png(b.pred, H, W, 1, b.rgb, b.mm, d_mag, b.minmax, num_sms, stream);
+  int r = depth_encode_png(b.pred, H, W, metric ? 0 : 1, b.rgb, b.mm, d_mag, b.minmax, num_sms, stream);  // flip = (metric == none)
   float mm[2] = {0, 0};
   if (r == 0) {
     if (depth_out) cudaMemcpyAsync(depth_out, b.pred, (size_t)H * W * 4, cudaMemcpyDeviceToHost, stream);

@@ -8,6 +8,7 @@
 #include "attention.cuh"
 #include "gemm_tc.cuh"
 #include "pointwise.cuh"
+#include "zoe_kernels.cuh"
 
 namespace prisma {
 
@@ -30,6 +31,9 @@ struct DaWeights {
   __half* ro_w[4] = {nullptr, nullptr, nullptr, nullptr};  // MiDaS "project" readout Linear(2D -> D)
   float* ro_b[4] = {nullptr, nullptr, nullptr, nullptr};
   __half *oc1_w, *oc2_w; float *oc1_b, *oc2_b, *oc3_w; float oc3_b;
+  // ZoeDepth metric head (zoedepth_v1.py:90-125): 1x1 convs as [N_pad][K_pad] fp16 + fp32 bias
+  struct Lin { __half* w = nullptr; float* b = nullptr; int n = 0, k = 0; };
+  Lin z_conv2, z_seed0, z_seed2, z_sproj0, z_sproj2, z_proj0[4], z_proj2[4], z_att0[4], z_att2[4], z_clb0, z_clb2;
 };
 struct DaBuffers {
   uint8_t* img; float* net_in; __half* patches; float* pos; float* x; float* tokens_tap; __half* ln; __half* qkv;
@@ -71,6 +75,8 @@ class DepthEngine {
   int up_linear(const std::string& name, int N, int K, __half** out, float scale = 1.f, int n_scaled = 0);
   int up_conv(const std::string& name, int Cout, int Cin, int kh, int kw, __half** out);
   int up_convT(const std::string& name, int Cin, int Cout, int s, __half** out, float** bias_out);
+  int up_lin1x1(const std::string& name, int N, int K, DaWeights::Lin* out);
+  int build_metric_head(const PMap& btlnck, const PMap* r_maps, const __half* act32, int Bt);
   int new_map(PMap* m, int H, int W, int C);
   void add(int group, const char* name, std::function<int(cudaStream_t)> fn);
   int add_gemm(int group, const char* name, const __half* A, long long a_rows, int a_cols, int a_pitch, const __half* W,
@@ -84,6 +90,8 @@ class DepthEngine {
   int D = 0, depth = 0, heads = 0, F = 0, oc[4] = {0, 0, 0, 0};
   // family switches: Depth-Anything (DINOv2 ViT/14 + DPT head) or MiDaS DPT (timm ViT/16, "project" readout, hooks)
   int family = FAMILY_DA, patch = 14, pos_grid = 37, hooks[4] = {0, 0, 0, 0};
+  float* zoe_metric = nullptr; float* zoe_tmp = nullptr; int plan_W_req = 0;
+  bool metric = false;  // --metric indoor|outdoor: ZoeDepth head on the relative model, fixed 392 x 518 network input
   std::vector<float> host_pos, host_cls;  // MiDaS: pos-embed resized on the host per resolution (bilinear)
   __half* ro_cat = nullptr;               // MiDaS: [B*P][2D] readout operand
   int num_sms = 148;

@@ -96,6 +96,7 @@ struct GemmCfg {
 #ifdef __CUDACC__
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // nn.Softplus(beta 1, threshold 20)
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -133,6 +134,9 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   } else if (ep.act == 4) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i].x = tanhf(v[i].x); v[i].y = tanhf(v[i].y); v[i].z = tanhf(v[i].z); v[i].w = tanhf(v[i].w); }
+  } else if (ep.act == 5) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i].x = softplus_f(v[i].x); v[i].y = softplus_f(v[i].y); v[i].z = softplus_f(v[i].z); v[i].w = softplus_f(v[i].w); }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) { v[i].x *= gamma.x; v[i].y *= gamma.y; v[i].z *= gamma.z; v[i].w *= gamma.w; }
@@ -359,7 +363,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int img = 0, rpix = m;
             if (ep.img_rows > 0) { img = m / ep.img_rows; rpix = m - img * ep.img_rows; }
             const int y = rpix / ep.in_w, x = rpix - y * ep.in_w, pd = ep.pad;
-            ep.head_out[((size_t)img * (ep.in_h - 2 * pd) + (y - pd)) * (ep.in_w - 2 * pd) + (x - pd)] = fmaxf(acc, 0.f);
+            const size_t pix = ((size_t)img * (ep.in_h - 2 * pd) + (y - pd)) * (ep.in_w - 2 * pd) + (x - pd);
+            ep.head_out[pix] = fmaxf(acc, 0.f);
+            if (ep.out_f16) {  // also keep the 32 ReLU'd activations (the out_conv hook of the metric head), dense rows
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                pk[j] = pack_half2(fmaxf(__uint_as_float(r[2 * j]) + __ldg(ep.bias + 2 * j), 0.f),
+                                   fmaxf(__uint_as_float(r[2 * j + 1]) + __ldg(ep.bias + 2 * j + 1), 0.f));
+              uint4* dst = reinterpret_cast<uint4*>(ep.out_f16 + pix * ep.out_f16_ld);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
           }
           continue;
         }

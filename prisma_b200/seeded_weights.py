@@ -109,6 +109,50 @@ def make_da_weights(encoder="vits", seed=0):
     return sd
 
 
+ZOE_CONFIG = dict(  # patchfusion/zoedepth/models/zoedepth/config_zoedepth.json ("model" section) as read by get_org_config
+    n_bins=64, bin_embedding_dim=128, n_attractors=[16, 8, 4, 1], attractor_alpha=1000, attractor_gamma=2, min_temp=0.0212,
+    max_temp=50.0, img_size=(392, 518))
+
+
+def make_zoe_weights(encoder="vitl", seed=0):
+    """state_dict of ZoeDepth(DepthAnythingCore(DPT_DINOv2)) (patchfusion/zoedepth/models/zoedepth/zoedepth_v1.py:40-125):
+    the relative model under core.core.* plus the metric head.  The reference only instantiates ViT-L; "vits" is the
+    same head on the small encoder (btlnck / decoder features 64) for fast pinning."""
+    c = DA_CONFIGS[encoder]
+    F = c["features"]
+    sd = {"core.core." + k: v for k, v in make_da_weights(encoder, seed).items()}
+
+    def conv(name, out_c, in_c, bias_mean=0.0):
+        b = (1.0 / in_c) ** 0.5
+        sd[name + ".weight"] = _uniform(name + ".weight", seed, (out_c, in_c, 1, 1), -b, b)
+        sd[name + ".bias"] = _uniform(name + ".bias", seed, (out_c,), -b, b) + bias_mean
+
+    conv("conv2", F, F)
+    conv("seed_bin_regressor._net.0", 256, F)
+    conv("seed_bin_regressor._net.2", 64, 256, bias_mean=1.0)
+    conv("seed_projector._net.0", 128, F)
+    conv("seed_projector._net.2", 128, 128)
+    for i, na in enumerate(ZOE_CONFIG["n_attractors"]):
+        conv(f"projectors.{i}._net.0", 128, F)
+        conv(f"projectors.{i}._net.2", 128, 128)
+        conv(f"attractors.{i}._net.0", 128, 128)
+        conv(f"attractors.{i}._net.2", na, 128, bias_mean=1.0)
+    bott = (33 + 128) // 2
+    conv("conditional_log_binomial.mlp.0", bott, 33 + 128)
+    conv("conditional_log_binomial.mlp.2", 4, bott)
+    sd["conditional_log_binomial.log_binomial_transform.k_idx"] = torch.arange(0, 64).view(1, -1, 1, 1)       # buffers of
+    sd["conditional_log_binomial.log_binomial_transform.K_minus_1"] = torch.Tensor([63]).view(1, -1, 1, 1)  # LogBinomial
+    # Shape the head like a trained one, so that parity is measured on a depth map with real dynamic range: seed bin
+    # centres spread over 0.5..8, a low temperature (peaked distribution over the 64 bins) and wider output weights.
+    sd["seed_bin_regressor._net.2.bias"] = sd["seed_bin_regressor._net.2.bias"] + torch.linspace(-0.5, 7.0, 64)
+    sd["conditional_log_binomial.mlp.0.weight"] = sd["conditional_log_binomial.mlp.0.weight"] * 3.0
+    sd["conditional_log_binomial.mlp.2.weight"] = sd["conditional_log_binomial.mlp.2.weight"] * torch.tensor([24.0, 24.0, 4.0, 4.0]).view(4, 1, 1, 1)
+    sd["conditional_log_binomial.mlp.2.bias"] = sd["conditional_log_binomial.mlp.2.bias"] + torch.tensor([0.0, 0.0, -5.0, 2.0])
+    for i in range(4):
+        sd[f"attractors.{i}._net.2.bias"] = sd[f"attractors.{i}._net.2.bias"] + torch.linspace(0.0, 5.0, ZOE_CONFIG["n_attractors"][i])
+    return sd
+
+
 MIDAS_CONFIGS = {
     # MiDaS v3 DPT_Large (hub "intel-isl/MiDaS": DPTDepthModel(backbone="vitl16_384"); timm vit_large_patch16_384):
     # hooks/features/reassemble channels from midas/dpt_depth.py + midas/backbones/vit.py (un-vendored, SURVEY.md 8c)
