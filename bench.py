@@ -79,9 +79,10 @@ class ClockSampler:
                     reasons=reasons, samples=len(sm))
 
 
-def make_frames(n, h, w, rank):
+def make_frames(n, h, w, start):
+    """Frames [start, start + n) of the synthetic clip (this rank's shard, prisma_b200.shard.frame_range)."""
     from oracle.frames import synthetic_frame  # seeded synthetic clip shared with the tests (bench infrastructure)
-    base = [synthetic_frame(h, w, t + 4 * rank) for t in range(min(n, 4))]
+    base = [synthetic_frame(h, w, (start + t) % 256) for t in range(min(n, 4))]
     # 4 distinct generated frames (the generator is pure numpy and slow), then cheap deterministic variants
     frames = []
     for i in range(n):
@@ -267,15 +268,14 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(local_rank)
 
+    from prisma_b200.shard import frame_range, max_over_ranks as _max_over_ranks
+
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max_over_ranks(x, dist, f"cuda:{local_rank}")
 
     eng = DepthAnythingEngine(ENCODER, make_da_weights(ENCODER, 0), device=local_rank)
-    frames = make_frames(FRAMES_PER_STEP, H, W, rank)
+    shard_start, shard_stop, _ = frame_range(rank, world, FRAMES_PER_STEP * world)  # weak scaling: 48 frames per GPU
+    frames = make_frames(shard_stop - shard_start, H, W, shard_start)
     work = eng.work(H, W, BATCH)
     assert FRAMES_PER_STEP % BATCH == 0
     passes = FRAMES_PER_STEP // BATCH
