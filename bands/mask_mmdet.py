@@ -6,7 +6,8 @@ process_video(args), the CLI flags of bands/mask_mmdet.py:165-174 (-i -o -c --sd
 optional <subpath>/%05d.png with the inverted mask for COLMAP) and the metadata.json keys (bands.mask.{url,ids,folder},
 :159-161).  SOLOv2 (inference_detector) and the union of the instance masks run in libprisma_b200.so; there is no CPU path.
 
-Not built: --sdf (snowy.generate_sdf) raises instead of falling back.
+--sdf: the clamped signed distance field of the union (snowy.generate_sdf in the reference) is an exact Euclidean
+distance transform on the GPU (prisma_mask_sdf).
 Additions: --weights (the mmdet checkpoint .pth or .npz), --seeded-weights, --device.
 """
 import argparse
@@ -57,8 +58,18 @@ def frame_masks(rgb, confidence):
     return np.repeat(u[..., None], 3, axis=-1)
 
 
+def encode_sdf(masks):
+    """--sdf (:116-118,150-152): a clamped signed distance field of the union in the GREEN channel."""
+    from prisma_b200.mask import sdf_green
+    masks = masks.copy()
+    masks[..., 1] = sdf_green(masks[..., 0], device=args.device)
+    return masks
+
+
 def process_image(a):
     masks = frame_masks(open_rgb(a.input), a.confidence)
+    if a.sdf:
+        masks = encode_sdf(masks)
     write_rgb(a.output, masks)
     if data is not None:
         data["bands"][BAND] = {"url": os.path.basename(a.output), "ids": CLASSES}
@@ -76,6 +87,8 @@ def process_video(a):
         masks = frame_masks(frame, a.confidence)
         if sub:  # COLMAP wants black-on-white masks (:148-149)
             write_rgb(os.path.join(sub, "{:05d}.png".format(f)), 255 - masks)
+        if a.sdf:
+            masks = encode_sdf(masks)
         out.write(masks)
     out.close()
     if data is not None:
@@ -100,8 +113,6 @@ def build_parser():
 def main(argv=None):
     global args, data
     args = build_parser().parse_args(argv)
-    if args.sdf:
-        raise NotImplementedError("--sdf (snowy.generate_sdf) is not built yet (SURVEY.md section 8f row 3)")
     data = load_metadata(args.input)
     if data:
         args.input = get_url(args.input, data, "rgba")

@@ -140,6 +140,9 @@ int prisma_mask_load_tensor(prisma_engine* e, const char* name, const float* dat
 int prisma_mask_finalize(prisma_engine* e);
 int prisma_mask_infer(prisma_engine* e, const uint8_t* rgb, int h, int w, float confidence, uint8_t* union_mask, int* n_inst,
                       float* scores, int32_t* labels, uint8_t* inst_masks, float* ms_out);
+/* --sdf (bands/mask_mmdet.py:64-69,150-152): green channel = 255 * (1 - clip(((sdf + 127)/255 - 0.25) * 2, 0, 1)) with sdf the
+ * exact Euclidean signed distance of the union mask (what snowy.generate_sdf computes); union_mask / green_out: h*w u8    */
+int prisma_mask_sdf(int device, const uint8_t* union_mask, int h, int w, uint8_t* green_out);
 /* intermediate tensors of the last pass (tests): "resized", "net_input", "fpn0..4", "mask_feats", "cls0..4", "kernel0..4",
  * "cand_count", "n_top"; returns the number of floats written                                                        */
 long long prisma_mask_read_tap(prisma_engine* e, const char* name, float* out, long long capacity);

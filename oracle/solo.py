@@ -205,3 +205,17 @@ def band_union(scores, labels, masks, confidence=0.5):
             acc += 255 * m.astype(np.int64)
     u = (acc % 256).astype(np.uint8)
     return np.stack([u] * 3, axis=-1)
+
+
+def sdf_green(union_u8):
+    """getSDF + the green-channel write (bands/mask_mmdet.py:64-69,150-152).  snowy (prideout/snowy, un-vendored) defines
+    generate_sdf(mask) = generate_udf(mask) - generate_udf(~mask), udf = sqrt of the exact squared Euclidean distance to
+    the nearest set pixel (Felzenszwalb-Huttenlocher); scipy's exact EDT is the independent implementation used here."""
+    from scipy import ndimage
+    m = union_u8 != 0
+    ua = ndimage.distance_transform_edt(~m) if m.any() else np.full(m.shape, 1e10)
+    ub = ndimage.distance_transform_edt(m) if (~m).any() else np.full(m.shape, 1e10)
+    sdf = ua - ub
+    sdf = (sdf + 127.0) / 255.0
+    sdf = (sdf - 0.25) * 2.0
+    return ((1.0 - np.clip(sdf, 0.0, 1.0)) * 255).astype(np.uint8)

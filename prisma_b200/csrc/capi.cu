@@ -563,6 +563,23 @@ long long prisma_mask_read_tap(prisma_engine* e, const char* name, float* out, l
   return m ? m->read_tap(name, out, capacity) : -1;
   API_GUARD_END
 }
+int prisma_mask_sdf(int device, const uint8_t* union_mask, int h, int w, uint8_t* green_out) {
+  API_GUARD_BEGIN
+  int sms = 0;
+  PRISMA_TRY(device_sms(device, &sms));
+  PRISMA_CHECK(union_mask && green_out && h > 0 && w > 0 && w <= 3000, "bad argument (frames up to 3000 pixels wide)");
+  Scratch sc;
+  const size_t n = (size_t)h * w;
+  uint8_t* dm = sc.alloc<uint8_t>(n);
+  uint8_t* dg = sc.alloc<uint8_t>(n);
+  int* ds = sc.alloc<int>(2 * n);
+  PRISMA_CHECK(dm && dg && ds, "cudaMalloc failed");
+  PRISMA_CUDA_OK(cudaMemcpy(dm, union_mask, n, cudaMemcpyHostToDevice));
+  PRISMA_TRY(mask_sdf_green(dm, h, w, ds, dg, 0));
+  PRISMA_CUDA_OK(cudaMemcpy(green_out, dg, n, cudaMemcpyDeviceToHost));
+  return 0;
+  API_GUARD_END
+}
 int prisma_mask_work(prisma_engine* e, int h, int w, double* out8) {
   API_GUARD_BEGIN
   SoloEngine* m = as_solo(e);

@@ -531,4 +531,65 @@ int solo_final_masks(const __half* masks, int fh, int fw, int h, int w, int H, i
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// SDF of the union mask for --sdf (bands/mask_mmdet.py:64-69,150-152): snowy.generate_sdf(mask != 0) = udf(mask) - udf(~mask)
+// with udf = exact Euclidean distance to the nearest set pixel (snowy: Felzenszwalb-Huttenlocher EDT, INF = 1e20, sqrt).
+// Exact integer squared distances: pass 1 per column (nearest set pixel above / below), pass 2 per row by exhaustive
+// minimisation over the row (W^2 H integer ops, ~1 ms at 1080p) -- same result as the lower-envelope algorithm.
+// ------------------------------------------------------------------------------------------------
+constexpr int SDF_INF = 1 << 28;
+__global__ void k_sdf_columns(const uint8_t* __restrict__ mask, int H, int W, int* __restrict__ ga, int* __restrict__ gb) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  int da = SDF_INF, db = SDF_INF;  // distance to the last seen set (a) / unset (b) pixel above
+  for (int y = 0; y < H; ++y) {
+    const bool m = mask[(size_t)y * W + x] != 0;
+    da = m ? 0 : (da >= SDF_INF ? SDF_INF : da + 1);
+    db = !m ? 0 : (db >= SDF_INF ? SDF_INF : db + 1);
+    ga[(size_t)y * W + x] = da; gb[(size_t)y * W + x] = db;
+  }
+  da = db = SDF_INF;
+  for (int y = H - 1; y >= 0; --y) {
+    const bool m = mask[(size_t)y * W + x] != 0;
+    da = m ? 0 : (da >= SDF_INF ? SDF_INF : da + 1);
+    db = !m ? 0 : (db >= SDF_INF ? SDF_INF : db + 1);
+    ga[(size_t)y * W + x] = min(ga[(size_t)y * W + x], da);
+    gb[(size_t)y * W + x] = min(gb[(size_t)y * W + x], db);
+  }
+}
+__global__ void k_sdf_rows(const int* __restrict__ ga, const int* __restrict__ gb, int W, uint8_t* __restrict__ green) {
+  extern __shared__ long long sq[];  // [2][W] squared column distances of this row
+  const int y = blockIdx.x;
+  long long* sa = sq; long long* sb = sq + W;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int a = ga[(size_t)y * W + x], b = gb[(size_t)y * W + x];
+    sa[x] = a >= SDF_INF ? -1 : (long long)a * a;
+    sb[x] = b >= SDF_INF ? -1 : (long long)b * b;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    long long da = -1, db = -1;
+    for (int xp = 0; xp < W; ++xp) {
+      const long long dx2 = (long long)(x - xp) * (x - xp);
+      if (sa[xp] >= 0) { const long long v = sa[xp] + dx2; da = (da < 0 || v < da) ? v : da; }
+      if (sb[xp] >= 0) { const long long v = sb[xp] + dx2; db = (db < 0 || v < db) ? v : db; }
+    }
+    // snowy: sqrt of the squared EDT, 1e20 where no set pixel exists at all
+    const double ua = da < 0 ? 1e10 : sqrt((double)da), ub = db < 0 ? 1e10 : sqrt((double)db);
+    double sdf = ua - ub;
+    sdf = (sdf + 127.0) / 255.0;
+    sdf = (sdf - 0.25) * 2.0;
+    const double g = 1.0 - fmin(fmax(sdf, 0.0), 1.0);
+    green[(size_t)y * W + x] = (uint8_t)(int)(g * 255.0);
+  }
+}
+int mask_sdf_green(const uint8_t* mask, int H, int W, int* d_scratch, uint8_t* green, cudaStream_t s) {
+  int* ga = d_scratch; int* gb = d_scratch + (size_t)H * W;
+  k_sdf_columns<<<ceil_div(W, 128), 128, 0, s>>>(mask, H, W, ga, gb);
+  k_sdf_rows<<<H, 256, 2 * W * sizeof(long long), s>>>(ga, gb, W, green);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace prisma

@@ -44,3 +44,10 @@ int solo_final_masks(const __half* masks, int fh, int fw, int h, int w, int H, i
                      uint8_t* inst_masks, uint8_t* union_mask, cudaStream_t s);
 
 }  // namespace prisma
+
+namespace prisma {
+// getSDF (bands/mask_mmdet.py:64-69): exact Euclidean signed distance of the union mask (snowy.generate_sdf = udf(mask) -
+// udf(~mask), Felzenszwalb exact EDT), remapped to the green channel: 255 * (1 - clip(((sdf + 127)/255 - 0.25) * 2, 0, 1)).
+// mask: H x W u8 (non-zero = inside), d_scratch: 2 * H * W ints, green: H x W u8.  All on the device.
+int mask_sdf_green(const uint8_t* mask, int H, int W, int* d_scratch, uint8_t* green, cudaStream_t s);
+}  // namespace prisma

@@ -16,6 +16,16 @@ NUM_CLASSES = 80
 MAX_PER_IMG = 100
 
 
+def sdf_green(union, device=0):
+    """getSDF (bands/mask_mmdet.py:64-69) of an HxW u8 union mask -> the HxW u8 green channel written with --sdf."""
+    union = np.ascontiguousarray(union, dtype=np.uint8)
+    if union.ndim != 2:
+        raise PrismaError("expected an HxW uint8 mask")
+    out = np.empty_like(union)
+    check(lib().prisma_mask_sdf(device, u8ptr(union), union.shape[0], union.shape[1], u8ptr(out)))
+    return out
+
+
 class SoloV2Engine:
     def __init__(self, state_dict=None, device=0, variant="r101"):
         self._h = C.c_void_p()

@@ -150,8 +150,7 @@ def test_mask_band_cli_matches_reference_flags():
     a = band.build_parser().parse_args(["-i", "x.mp4", "-o", "y.mp4", "-c", "0.6", "--subpath", "mask"])
     assert (a.input, a.output, a.confidence, a.subpath, a.sdf) == ("x.mp4", "y.mp4", 0.6, "mask", False)
     assert band.BAND == "mask" and band.CONFIDENCE_THRESHOLD == 0.5 and len(band.CLASSES) == 11
-    with pytest.raises(NotImplementedError):
-        band.main(["-i", "x.png", "--sdf"])
+    assert band.build_parser().parse_args(["-i", "x.png", "--sdf"]).sdf is True
 
 
 @pytest.mark.gpu

@@ -118,3 +118,21 @@ def test_solo_r101_720p_matches_oracle():
         assert m < 1e-2 and l2 < 4e-3, (f"fpn{i}", m, l2)   # 33 bottlenecks of fp16 maps
     eng.close()
     check_instances(res, scores, labels, masks, min_match=0.8)
+
+
+@pytest.mark.gpu
+def test_sdf_green_channel_bit_exact():
+    """--sdf: exact Euclidean signed distance of the union -> green channel, vs scipy's exact EDT (integer squared
+    distances, correctly rounded sqrt: bit-exact)."""
+    from prisma_b200.mask import sdf_green
+    rng = np.random.default_rng(0)
+    H, W = 270, 480
+    yy, xx = np.mgrid[0:H, 0:W]
+    m = np.zeros((H, W), np.uint8)
+    for _ in range(7):  # a few discs and boxes, some overlapping (254 = two instances)
+        cy, cx, r = rng.integers(0, H), rng.integers(0, W), rng.integers(8, 60)
+        m[(yy - cy) ** 2 + (xx - cx) ** 2 < r * r] += 255
+    m[100:140, 200:330] = 255
+    assert np.array_equal(sdf_green(m), osolo.sdf_green(m))
+    for special in (np.zeros((64, 96), np.uint8), np.full((64, 96), 255, np.uint8)):
+        assert np.array_equal(sdf_green(special), osolo.sdf_green(special))
