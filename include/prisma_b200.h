@@ -149,6 +149,11 @@ long long prisma_mask_read_tap(prisma_engine* e, const char* name, float* out, l
 /* out[0] = algorithmic FLOP of the last planned pass, out[1] = launches, out[2..5] = resized h, w, padded h, w        */
 int prisma_mask_work(prisma_engine* e, int h, int w, double* out8);
 
+/* Size of the resized (un-padded) network input each band's transform produces for a w x h frame: depth_anything
+ * (d_anything/util/transform.py:111-166 lower_bound x14), depth_midas (minimal x32), depth_anything_metric (392 x 518),
+ * mask_mmdet (mmcv.imrescale (1333, 800)).  Pure host arithmetic, usable without a GPU.                              */
+int prisma_net_size(const char* band, int w, int h, int* wn, int* hn);
+
 /* ---- kernel-level entry points (parity tests and micro-benchmarks call the kernels through the C ABI) ---- */
 /* D = A[M,K] * W[N,K]^T (+bias) with fp16 operands / fp32 accumulate on the tcgen05 core; A, W, D host fp32.
  * act: 0 none, 1 gelu, 2 relu.  force_bn: 0 = auto, else 32/64/128/256.  ms_out (may be NULL): kernel time.   */

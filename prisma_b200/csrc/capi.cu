@@ -563,6 +563,23 @@ long long prisma_mask_read_tap(prisma_engine* e, const char* name, float* out, l
   return m ? m->read_tap(name, out, capacity) : -1;
   API_GUARD_END
 }
+// network-input size arithmetic of each band's transform (host logic only: no GPU needed)
+int prisma_net_size(const char* band, int w, int h, int* wn, int* hn) {
+  API_GUARD_BEGIN
+  PRISMA_CHECK(band && wn && hn && w > 0 && h > 0, "bad argument");
+  const std::string b(band);
+  if (b == "depth_anything") da_net_size(w, h, wn, hn);
+  else if (b == "depth_midas") midas_net_size(w, h, wn, hn);
+  else if (b == "depth_anything_metric") { *wn = 518; *hn = 392; }
+  else if (b == "mask_mmdet") {
+    SoloEngine e;  // only its size rule is used
+    int nh, nw, hp, wp;
+    e.net_shape(h, w, &nh, &nw, &hp, &wp);
+    *wn = nw; *hn = nh;
+  } else { set_last_error("unknown band '" + b + "'"); return -1; }
+  return 0;
+  API_GUARD_END
+}
 int prisma_mask_sdf(int device, const uint8_t* union_mask, int h, int w, uint8_t* green_out) {
   API_GUARD_BEGIN
   int sms = 0;
