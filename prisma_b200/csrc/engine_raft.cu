@@ -159,6 +159,15 @@ int RaftEngine::finalize() {
     PRISMA_TRY(r_alloc(allocs, &w.convf1_b, bs->data.size()));
     PRISMA_CUDA_OK(cudaMemcpy(w.convf1_w, wt->data.data(), wt->data.size() * 4, cudaMemcpyHostToDevice));
     PRISMA_CUDA_OK(cudaMemcpy(w.convf1_b, bs->data.data(), bs->data.size() * 4, cudaMemcpyHostToDevice));
+    PRISMA_CHECK(wt->data.size() == (size_t)128 * 98, "RAFT convf1 weight has an unexpected size");
+    std::vector<__half> hw((size_t)256 * 256, __float2half_rn(0.f));
+    for (int co = 0; co < 128; ++co)
+      for (int k = 0; k < 98; ++k) {  // [co][ch][ky][kx] flattens to k = ch*49 + ky*7 + kx, the im2col order
+        hw[(size_t)co * 256 + k] = __float2half_rn(wt->data[(size_t)co * 98 + k]);
+        hw[(size_t)co * 256 + 128 + k] = hw[(size_t)co * 256 + k];
+      }
+    PRISMA_TRY(r_alloc(allocs, &w.convf1_gemm_w, hw.size()));
+    PRISMA_CUDA_OK(cudaMemcpy(w.convf1_gemm_w, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
   }
   for (int pass = 0; pass < 2; ++pass) {  // SepConvGRU: (1,5) then (5,1); z and r stacked into one N = 256 conv
     const std::string s = std::to_string(pass + 1);
@@ -389,6 +398,8 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
   PRISMA_TRY(new_map(&c1, B, H8, W8, 256, 2));
   PRISMA_TRY(new_map(&c2, B, H8, W8, 256, 2));   // [convc2 out (192) | convf2 out (64)]
   PRISMA_TRY(new_map(&f1, B, H8, W8, 128, 2));
+  __half* f1_cols = nullptr;
+  PRISMA_TRY(r_alloc(plan_allocs, &f1_cols, (size_t)B * H8 * W8 * 256));
   float *zr_f = nullptr, *q_f = nullptr;  // gates in fp32, padded-row layout of the pad-2 maps
   PRISMA_TRY(r_alloc(plan_allocs, &zr_f, (size_t)hx.rows() * 256));
   PRISMA_TRY(r_alloc(plan_allocs, &q_f, (size_t)hx.rows() * 128));
@@ -408,9 +419,16 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
     { GemmEpilogue ep; ep.act = 2; ep.out_f16 = c2.p; ep.out_f16_ld = 256;            // convc2 3x3 256 -> 192
       PRISMA_TRY(add_conv("convc2", c1, 0, w.convc2, ep, 1)); }
     {
-      const float* c0 = b.coords0; const float* c1p = b.coords1; const float* wt = w.convf1_w; const float* bs = w.convf1_b;
-      __half* o = f1.p; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
-      add("convf1_direct", [=](cudaStream_t s) { return raft_flow_conv7(c0, c1p, wt, bs, 2, h8, w8, 2, o, hxp, rhp, s); });
+      // convf1 7x7 on the flow: im2col with an fp16 hi/lo split of every value (K = 256) + one GEMM, ReLU, -> padded map
+      const float* c0 = b.coords0; const float* c1p = b.coords1; __half* cols = f1_cols; const int h8 = H8, w8 = W8;
+      add("convf1_im2col", [=](cudaStream_t s) { return raft_flow_im2col(c0, c1p, 2, h8, w8, cols, s); });
+      GemmEpilogue ep; ep.bias = w.convf1_b; ep.act = 2; ep.out_f16 = f1.p; ep.out_f16_ld = 128;
+      ep.row_map = ROW_TOK2PAD; ep.in_w = W8; ep.in_h = H8; ep.out_wp = f1.Wp(); ep.out_img_rows = (int)f1.img_rows(); ep.out_pad = 2;
+      GemmLaunch g;
+      const int zoff[1] = {0};
+      PRISMA_TRY(gemm_prepare(&g, f1_cols, 2LL * H8 * W8, 256, 256, w.convf1_gemm_w, 256, 2 * H8 * W8, 128, 1, zoff, ep, num_sms));
+      flops += 2.0 * 2 * H8 * (double)W8 * 98.0 * 128;
+      add("convf1_gemm", [g](cudaStream_t s) { return gemm_run(g, s); });
     }
     { GemmEpilogue ep; ep.act = 2; ep.out_f16 = c2.p + 192; ep.out_f16_ld = 256;      // convf2 3x3 128 -> 64
       PRISMA_TRY(add_conv("convf2", f1, 0, w.convf2, ep, 1)); }

@@ -18,6 +18,7 @@ struct RaftWeights {
   EncW fnet, cnet;
   ConvW convc1, convc2, convf2, conv, zr[2], q[2], fh1, fh2, mk1, mk2;
   float *convf1_w = nullptr, *convf1_b = nullptr;
+  __half* convf1_gemm_w = nullptr;  // [256][256]: k = [98 weights | 0 | the same 98 (for the fp16 'lo' half of the flow) | 0]
 };
 struct RaftBuffers {
   uint8_t* img; uint8_t* resized; float* chw; __half* stem_cols; float *coords0, *coords1, *cnet_out, *h_master, *delta, *mask;

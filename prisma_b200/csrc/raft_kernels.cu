@@ -212,6 +212,38 @@ __global__ void __launch_bounds__(128) k_flow_conv7(const float* __restrict__ co
     out128[(((size_t)b * Hp + y + pad) * Wp + x + pad) * 128 + c] = __float2half_rn(fmaxf(acc, 0.f));
   }
 }
+// convf1 (7x7, 2 -> 128, update.py:84) as a GEMM: im2col of the flow with every fp32 value split into an fp16 pair
+// (hi = fp16(v), lo = fp16(v - hi)) so the tensor-core product keeps ~22 bits of the flow (values reach tens of pixels;
+// a single fp16 would cost 8e-4 of the 1e-3 budget).  Row = pixel, K = [98 hi | 30 zero | 98 lo | 30 zero].
+__global__ void k_flow_im2col(const float* __restrict__ coords0, const float* __restrict__ coords1, int B, int H, int W,
+                              __half* __restrict__ out) {
+  const int P = H * W;
+  const long long total = (long long)B * P * 128;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i & 127);
+    const long long row = i >> 7;
+    const int b = (int)(row / P), r = (int)(row - (long long)b * P);
+    float v = 0.f;
+    if (k < 98) {
+      const int y = r / W, x = r - y * W;
+      const int ch = k / 49, t = k - ch * 49, ky = t / 7, kx = t - ky * 7;
+      const int yy = y + ky - 3, xx = x + kx - 3;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const size_t o = ((size_t)b * 2 + ch) * P + (size_t)yy * W + xx;
+        v = coords1[o] - coords0[o];
+      }
+    }
+    const __half hi = __float2half_rn(v);
+    out[row * 256 + k] = hi;
+    out[row * 256 + 128 + k] = __float2half_rn(v - __half2float(hi));
+  }
+}
+int raft_flow_im2col(const float* coords0, const float* coords1, int B, int H, int W, __half* out, cudaStream_t s) {
+  k_flow_im2col<<<148 * 8, 256, 0, s>>>(coords0, coords1, B, H, W, out);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // motion features = cat([conv_out(126), flow(2)]) (update.py:97): the two flow channels of the GRU operand maps
 __global__ void k_flow_cols(const float* __restrict__ c0, const float* __restrict__ c1, int B, int H, int W, int pad,
                             __half* __restrict__ hx, __half* __restrict__ rhx) {

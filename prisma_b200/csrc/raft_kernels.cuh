@@ -13,6 +13,7 @@ int raft_cnet_split(const float* cn, int B, int H, int W, int pad, float* h_mast
                     cudaStream_t s);
 int raft_flow_conv7(const float* coords0, const float* coords1, const float* w, const float* bias, int B, int H, int W,
                     int pad, __half* out128, __half* hx, __half* rhx, cudaStream_t s);
+int raft_flow_im2col(const float* c0, const float* c1, int B, int H, int W, __half* out, cudaStream_t s);
 int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pad, __half* hx, __half* rhx, cudaStream_t s);
 int raft_gru_rh(const float* zr, const float* h_master, __half* rhx, long long rows, cudaStream_t s);
 int raft_gru_update(const float* zr, const float* q, float* h_master, __half* hx, long long rows, cudaStream_t s);
