@@ -151,7 +151,7 @@ int RaftEngine::finalize() {
   PRISMA_TRY(up_conv(u + "encoder.convc2", "", 192, 256, 3, 3, 192, 1.f, &w.convc2));
   PRISMA_TRY(up_conv(u + "encoder.convf2", "", 64, 128, 3, 3, 64, 1.f, &w.convf2));
   PRISMA_TRY(up_conv(u + "encoder.conv", "", 126, 256, 3, 3, 128, 1.f, &w.conv));  // 126 -> 128 (two zero channels)
-  {  // convf1 7x7 on the 2-channel flow: direct kernel, fp32 weights
+  {  // convf1 7x7 on the 2-channel flow: im2col GEMM (K = hi/lo split of 98 taps), fp32 bias
     const HostTensor* wt = get(u + "encoder.convf1.weight");
     const HostTensor* bs = get(u + "encoder.convf1.bias");
     if (!wt || !bs) return -1;
@@ -433,7 +433,7 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
     { GemmEpilogue ep; ep.act = 2; ep.out_f16 = c2.p + 192; ep.out_f16_ld = 256;      // convf2 3x3 128 -> 64
       PRISMA_TRY(add_conv("convf2", f1, 0, w.convf2, ep, 1)); }
     { // conv 3x3 256 -> 126 (+2 zero channels); the 126 motion channels go to cols 256..381 of hx and rhx; the two
-      // trailing columns are rewritten with the flow by convf1_direct of the NEXT iteration -- so restore them here
+      // trailing columns are rewritten with the flow by flow_cols every iteration -- so restore them here
       GemmEpilogue ep; ep.act = 2; ep.out_f16 = hx.p + 256; ep.out_f16_ld = 384; ep.out_f16_relu = rhx.p + 256; ep.out_f16_relu_ld = 384;
       PRISMA_TRY(add_conv("motion_conv", c2, 0, w.conv, ep, 1));
       const float* c0 = b.coords0; const float* c1p = b.coords1; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;

@@ -204,6 +204,9 @@ int SoloEngine::build_plan(int H, int W) {
   d_inst = nullptr;
   net_shape(H, W, &nh, &nw, &hp, &wp);
   const int zero_off[1] = {0};
+  const char* cur_tag = "pre";
+  step_tag.clear();
+  auto push_step = [&](std::function<int(cudaStream_t)> fn) { steps.push_back(std::move(fn)); step_tag.push_back(cur_tag); };
 
   auto new_map = [&](SMap* mm, int h, int w, int c) -> int {
     mm->H = h; mm->W = w; mm->C = c;
@@ -227,7 +230,7 @@ int SoloEngine::build_plan(int H, int W) {
     PRISMA_TRY(gemm_prepare(&g, in.p, in.rows(), cin_cols, in.C, w.w, round_up(w.cout, 256), (int)in.rows(), w.cout, taps_n, off,
                             ep, num_sms));
     flops += 2.0 * (in.H / sub) * (double)(in.W / sub) * taps_n * w.cin * w.cout;
-    steps.push_back([g](cudaStream_t s) { return gemm_run(g, s); });
+    push_step([g](cudaStream_t s) { return gemm_run(g, s); });
     return 0;
   };
   float* gn_part = nullptr; float* gn_stats = nullptr; float* gn_raw = nullptr;
@@ -241,7 +244,7 @@ int SoloEngine::build_plan(int H, int W) {
     PRISMA_TRY(conv(in, cin_cols, w, 1, ep, nullptr, gn_raw));
     const int h = in.H, ww = in.W, c = w.cout; const float* gw = w.gn_w; const float* gb = w.gn_b;
     __half* dm = dst_map ? dst_map->p : nullptr;
-    steps.push_back([=](cudaStream_t s) { return groupnorm_relu_f16(gn_raw, h, ww, c, 32, gw, gb, gn_part, gn_stats, dm, dst_dense, s); });
+    push_step([=](cudaStream_t s) { return groupnorm_relu_f16(gn_raw, h, ww, c, 32, gw, gb, gn_part, gn_stats, dm, dst_dense, s); });
     return 0;
   };
 
@@ -252,8 +255,9 @@ int SoloEngine::build_plan(int H, int W) {
   {
     const uint8_t* img = d_img; uint8_t* rs = d_resized; float* net = d_net;
     const int nh_ = nh, nw_ = nw, hp_ = hp, wp_ = wp;
-    steps.push_back([=](cudaStream_t s) { return solo_preprocess(img, H, W, nh_, nw_, hp_, wp_, net, rs, s); });
+    push_step([=](cudaStream_t s) { return solo_preprocess(img, H, W, nh_, nw_, hp_, wp_, net, rs, s); });
   }
+  cur_tag = "backbone";
   // ---- ResNet stem: 7x7/2 conv + BN + ReLU (im2col GEMM), 3x3/2 max-pool
   SMap s1, x;
   PRISMA_TRY(new_map(&s1, hp / 2, wp / 2, 64));
@@ -261,17 +265,17 @@ int SoloEngine::build_plan(int H, int W) {
     __half* cols = nullptr;
     PRISMA_TRY(s_alloc(plan_allocs, &cols, (size_t)(hp / 2) * (wp / 2) * 192));
     const float* net = d_net; const int hp_ = hp, wp_ = wp;
-    steps.push_back([=](cudaStream_t s) { return raft_im2col_stem(net, 1, hp_, wp_, cols, s); });
+    push_step([=](cudaStream_t s) { return raft_im2col_stem(net, 1, hp_, wp_, cols, s); });
     GemmEpilogue ep; ep.bias = stem.b; ep.act = 2; ep.out_f16 = s1.p; ep.out_f16_ld = 64;
     ep.row_map = ROW_TOK2PAD; ep.in_w = wp / 2; ep.in_h = hp / 2; ep.out_wp = s1.Wp(); ep.out_img_rows = (int)s1.rows(); ep.out_pad = 1;
     GemmLaunch g;
     const int M = (hp / 2) * (wp / 2);
     PRISMA_TRY(gemm_prepare(&g, cols, M, 192, 192, stem.w, 256, M, 64, 1, zero_off, ep, num_sms));
     flops += 2.0 * M * 147.0 * 64;
-    steps.push_back([g](cudaStream_t s) { return gemm_run(g, s); });
+    push_step([g](cudaStream_t s) { return gemm_run(g, s); });
   }
   PRISMA_TRY(new_map(&x, hp / 4, wp / 4, 64));
-  { const SMap a = s1, o = x; steps.push_back([=](cudaStream_t s) { return maxpool3s2_f16(a.p, a.H, a.W, 64, o.p, o.H, o.W, s); }); }
+  { const SMap a = s1, o = x; push_step([=](cudaStream_t s) { return maxpool3s2_f16(a.p, a.H, a.W, 64, o.p, o.H, o.W, s); }); }
   // ---- bottlenecks (resnet.py:255-300): 1x1 -> 3x3 (stride) -> 1x1, + identity / downsample, ReLU
   SMap C[4];
   for (int li = 0; li < 4; ++li) {
@@ -297,6 +301,7 @@ int SoloEngine::build_plan(int H, int W) {
     }
     C[li] = x;
   }
+  cur_tag = "fpn";
   // ---- FPN
   SMap L[4], P[5];
   for (int i = 0; i < 4; ++i) {
@@ -306,7 +311,7 @@ int SoloEngine::build_plan(int H, int W) {
   }
   for (int i = 3; i > 0; --i) {
     const SMap f = L[i - 1], c = L[i];
-    steps.push_back([=](cudaStream_t s) { return nearest_add_f16(f.p, f.H, f.W, c.p, c.H, c.W, 256, s); });
+    push_step([=](cudaStream_t s) { return nearest_add_f16(f.p, f.H, f.W, c.p, c.H, c.W, 256, s); });
   }
   for (int i = 0; i < 4; ++i) {
     PRISMA_TRY(new_map(&P[i], L[i].H, L[i].W, 256));
@@ -314,9 +319,10 @@ int SoloEngine::build_plan(int H, int W) {
     PRISMA_TRY(conv(L[i], 256, fpnc[i], 1, ep, &P[i], nullptr));
   }
   PRISMA_TRY(new_map(&P[4], (P[3].H - 1) / 2 + 1, (P[3].W - 1) / 2 + 1, 256));
-  { const SMap a = P[3], o = P[4]; steps.push_back([=](cudaStream_t s) { return subsample2_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, s); }); }
+  { const SMap a = P[3], o = P[4]; push_step([=](cudaStream_t s) { return subsample2_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, s); }); }
   for (int i = 0; i < 5; ++i) taps["fpn" + std::to_string(i)] = {P[i].p, 1, P[i].H, P[i].W, 256};
 
+  cur_tag = "mask_feature_head";
   // ---- mask feature head (solov2_head.py:133-150)
   fh = P[0].H; fw = P[0].W;
   const int HW = fh * fw;
@@ -330,7 +336,7 @@ int SoloEngine::build_plan(int H, int W) {
       SMap cc;
       PRISMA_TRY(new_map(&cc, P[3].H, P[3].W, 320));
       const SMap a = P[3];
-      steps.push_back([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, cc.p, cc.H, cc.W, 320, 1, 0, s); });
+      push_step([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, cc.p, cc.H, cc.W, 320, 1, 0, s); });
       cur = cc; cin_cols = 320;
     }
     for (int j = 0; j < i; ++j) {
@@ -340,7 +346,7 @@ int SoloEngine::build_plan(int H, int W) {
       const bool last = j == i - 1;
       if (last) u = acc; else PRISMA_TRY(new_map(&u, 2 * t.H, 2 * t.W, 128));
       PRISMA_CHECK(u.H == 2 * t.H && u.W == 2 * t.W, "solo: FPN levels are not exact halvings (pad to a multiple of 32)");
-      steps.push_back([=](cudaStream_t s) { return resize_bilinear_f16(t.p, t.H, t.W, 128, u.p, u.H, u.W, 128, 0, last ? 1 : 0, s); });
+      push_step([=](cudaStream_t s) { return resize_bilinear_f16(t.p, t.H, t.W, 128, u.p, u.H, u.W, 128, 0, last ? 1 : 0, s); });
       cur = u; cin_cols = 128;
     }
   }
@@ -349,12 +355,13 @@ int SoloEngine::build_plan(int H, int W) {
   PRISMA_TRY(gnconv(acc, 128, mf_pred, nullptr, mfeat));
   taps["mask_feats"] = {mfeat, 2, HW, 256, 0};
 
+  cur_tag = "towers";
   // ---- head towers (solov2_head.py:253-292, resize_feats solo_head.py:133-153)
   SMap R0, R4;
   PRISMA_TRY(new_map(&R0, P[1].H, P[1].W, 256));
   PRISMA_TRY(new_map(&R4, P[3].H, P[3].W, 256));
-  { const SMap a = P[0], o = R0; steps.push_back([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, 256, 0, 0, s); }); }
-  { const SMap a = P[4], o = R4; steps.push_back([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, 256, 0, 0, s); }); }
+  { const SMap a = P[0], o = R0; push_step([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, 256, 0, 0, s); }); }
+  { const SMap a = P[4], o = R4; push_step([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, 256, 0, 0, s); }); }
   const SMap lvl_in[5] = {R0, P[1], P[2], P[3], R4};
   float* cls_out[5]; float* ker_out[5];
   int cell0[5], cells = 0;
@@ -366,7 +373,7 @@ int SoloEngine::build_plan(int H, int W) {
     PRISMA_TRY(new_map(&ka, S, S, 512)); PRISMA_TRY(new_map(&kb, S, S, 512));
     PRISMA_TRY(new_map(&ca, S, S, 512)); PRISMA_TRY(new_map(&cb, S, S, 512));
     const SMap a = lvl_in[l];
-    steps.push_back([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, g0.p, S, S, 320, 1, 0, s); });
+    push_step([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, g0.p, S, S, 320, 1, 0, s); });
     PRISMA_TRY(gnconv(g0, 320, kconv[0], &ka, nullptr));
     PRISMA_TRY(gnconv(ka, 512, kconv[1], &kb, nullptr));
     PRISMA_TRY(gnconv(kb, 512, kconv[2], &ka, nullptr));
@@ -383,6 +390,7 @@ int SoloEngine::build_plan(int H, int W) {
     taps["kernel" + std::to_string(l)] = {ker_out[l], 0, S * S, 256, 0};
   }
 
+  cur_tag = "decode";
   // ---- decode (solov2_head.py:582-766)
   SoloCand *cand_raw = nullptr, *cand = nullptr;
   PRISMA_TRY(s_alloc(plan_allocs, &cand_raw, (size_t)SOLO_CAP));
@@ -394,12 +402,12 @@ int SoloEngine::build_plan(int H, int W) {
   PRISMA_TRY(s_alloc(plan_allocs, &d_keep, (size_t)SOLO_MAX));
   PRISMA_TRY(s_alloc(plan_allocs, &d_keep_label, (size_t)SOLO_MAX));
   PRISMA_TRY(s_alloc(plan_allocs, &d_keep_score, (size_t)SOLO_MAX));
-  { int* cnt = d_count; steps.push_back([=](cudaStream_t s) { PRISMA_CUDA_OK(cudaMemsetAsync(cnt, 0, 4, s)); return 0; }); }
+  { int* cnt = d_count; push_step([=](cudaStream_t s) { PRISMA_CUDA_OK(cudaMemsetAsync(cnt, 0, 4, s)); return 0; }); }
   for (int l = 0; l < 5; ++l) {
     const float* lg = cls_out[l]; const int S = num_grids[l], c0 = cell0[l]; const float st = strides[l]; int* cnt = d_count;
-    steps.push_back([=](cudaStream_t s) { return solo_candidates(lg, S, c0, SOLO_NC, 0.1f, st, cand_raw, cnt, SOLO_CAP, s); });
+    push_step([=](cudaStream_t s) { return solo_candidates(lg, S, c0, SOLO_NC, 0.1f, st, cand_raw, cnt, SOLO_CAP, s); });
   }
-  { int* cnt = d_count; steps.push_back([=](cudaStream_t s) { return solo_sort_candidates(cand_raw, cnt, SOLO_CAP, cand, s); }); }
+  { int* cnt = d_count; push_step([=](cudaStream_t s) { return solo_sort_candidates(cand_raw, cnt, SOLO_CAP, cand, s); }); }
   __half* kmat = nullptr;
   PRISMA_TRY(s_alloc(plan_allocs, &kmat, (size_t)SOLO_CAP * 256));
   const float** d_lvl_ptr = nullptr; int* d_cell0 = nullptr;
@@ -408,7 +416,7 @@ int SoloEngine::build_plan(int H, int W) {
   PRISMA_CUDA_OK(cudaMemcpy(d_lvl_ptr, ker_out, 5 * sizeof(float*), cudaMemcpyHostToDevice));
   PRISMA_CUDA_OK(cudaMemcpy(d_cell0, cell0, 5 * sizeof(int), cudaMemcpyHostToDevice));
   { const int* cnt = d_count;
-    steps.push_back([=](cudaStream_t s) { return solo_gather_kernels(cand, cnt, SOLO_CAP, d_lvl_ptr, d_cell0, 5, SOLO_NC, 256, kmat, s); }); }
+    push_step([=](cudaStream_t s) { return solo_gather_kernels(cand, cnt, SOLO_CAP, d_lvl_ptr, d_cell0, 5, SOLO_NC, 256, kmat, s); }); }
   // dynamic conv: mask_preds = sigmoid(kernels [n][256] . mask_feats [HW][256]^T) as one GEMM (solov2_head.py:717-722)
   __half* masks = nullptr;
   PRISMA_TRY(s_alloc(plan_allocs, &masks, (size_t)SOLO_CAP * HW));
@@ -418,26 +426,26 @@ int SoloEngine::build_plan(int H, int W) {
     GemmLaunch g;
     PRISMA_TRY(gemm_prepare(&g, kmat, SOLO_CAP, 256, 256, mfeat, round_up(HW, 256), SOLO_CAP, HW, 1, zero_off, ep, num_sms));
     flops += 2.0 * SOLO_CAP * (double)HW * 256;
-    steps.push_back([g](cudaStream_t s) { return gemm_run(g, s); });
+    push_step([g](cudaStream_t s) { return gemm_run(g, s); });
   }
   { const int* cnt = d_count; const int hw = HW;
-    steps.push_back([=](cudaStream_t s) { return solo_mask_stats(masks, hw, 0.5f, cand, cnt, SOLO_CAP, s); });
+    push_step([=](cudaStream_t s) { return solo_mask_stats(masks, hw, 0.5f, cand, cnt, SOLO_CAP, s); });
     int* top = d_top; int* ntop = d_ntop;
-    steps.push_back([=](cudaStream_t s) { return solo_rank(cand, cnt, SOLO_CAP, SOLO_NMS_PRE, top, ntop, s); }); }
+    push_step([=](cudaStream_t s) { return solo_rank(cand, cnt, SOLO_CAP, SOLO_NMS_PRE, top, ntop, s); }); }
   __half* bin = nullptr; float* inter = nullptr;
   PRISMA_TRY(s_alloc(plan_allocs, &bin, (size_t)SOLO_NMS_PAD * HW));
   PRISMA_TRY(s_alloc(plan_allocs, &inter, (size_t)SOLO_NMS_PAD * SOLO_NMS_PAD));
   { const int* top = d_top; const int* ntop = d_ntop; const int hw = HW;
-    steps.push_back([=](cudaStream_t s) { return solo_binarize(masks, hw, 0.5f, top, ntop, SOLO_NMS_PAD, bin, s); }); }
+    push_step([=](cudaStream_t s) { return solo_binarize(masks, hw, 0.5f, top, ntop, SOLO_NMS_PAD, bin, s); }); }
   {  // inter_matrix = M M^T over binary masks (matrix_nms.py:70-71): exact in fp32 (counts < 2^24)
     GemmEpilogue ep; ep.out_f32 = inter; ep.out_f32_ld = SOLO_NMS_PAD;
     GemmLaunch g;
     PRISMA_TRY(gemm_prepare(&g, bin, SOLO_NMS_PAD, HW, HW, bin, SOLO_NMS_PAD, SOLO_NMS_PAD, SOLO_NMS_PAD, 1, zero_off, ep, num_sms));
     flops += 2.0 * SOLO_NMS_PAD * (double)SOLO_NMS_PAD * HW;
-    steps.push_back([g](cudaStream_t s) { return gemm_run(g, s); });
+    push_step([g](cudaStream_t s) { return gemm_run(g, s); });
   }
   { const int* top = d_top; const int* ntop = d_ntop; int* keep = d_keep; float* ks = d_keep_score; int* kl = d_keep_label; int* nk = d_nkeep;
-    steps.push_back([=](cudaStream_t s) {
+    push_step([=](cudaStream_t s) {
       return solo_matrix_nms(inter, SOLO_NMS_PAD, cand, top, ntop, SOLO_NC, 2.0f, 0.05f, SOLO_MAX, keep, ks, kl, nk, s); }); }
   PRISMA_TRY(s_alloc(plan_allocs, &d_union, (size_t)H * W));
   taps["resized"] = {d_resized, 3, nh * nw, 3, 0};
@@ -477,6 +485,21 @@ int SoloEngine::infer(const uint8_t* rgb, int H, int W, float confidence, uint8_
   PRISMA_TRY(build_plan(H, W));
   if (inst_masks_out && !d_inst) PRISMA_TRY(s_alloc(plan_allocs, &d_inst, (size_t)SOLO_MAX * H * W));
   PRISMA_CUDA_OK(cudaMemcpyAsync(d_img, rgb, (size_t)H * W * 3, cudaMemcpyHostToDevice, stream));
+  if (getenv("PRISMA_SOLO_PROFILE")) {  // per-stage device times of one ungraphed pass (stderr)
+    std::map<std::string, float> acc;
+    cudaEvent_t a, b2;
+    cudaEventCreate(&a); cudaEventCreate(&b2);
+    for (size_t i = 0; i < steps.size(); ++i) {
+      cudaEventRecord(a, stream);
+      PRISMA_TRY(steps[i](stream));
+      cudaEventRecord(b2, stream);
+      cudaEventSynchronize(b2);
+      float ms = 0; cudaEventElapsedTime(&ms, a, b2);
+      acc[step_tag[i]] += ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b2);
+    for (auto& kv : acc) fprintf(stderr, "[solo-profile] %-20s %8.3f ms\n", kv.first.c_str(), kv.second);
+  }
   PRISMA_CUDA_OK(cudaEventRecord(ev0, stream));
   PRISMA_TRY(run(stream));
   PRISMA_TRY(solo_final_masks(d_masks, fh, fw, nh, nw, H, W, 0.5f, d_keep, d_keep_score, d_keep_label, d_nkeep, SOLO_MAX,

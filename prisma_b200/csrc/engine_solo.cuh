@@ -49,6 +49,7 @@ class SoloEngine {
   std::map<std::string, HostTensor> host;
   std::vector<void*> allocs, plan_allocs;
   std::vector<std::function<int(cudaStream_t)>> steps;
+  std::vector<const char*> step_tag;  // stage of each step (PRISMA_SOLO_PROFILE)
   std::map<std::string, SoloTap> taps;
   // weights
   SoloConvW stem;

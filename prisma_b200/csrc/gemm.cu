@@ -97,6 +97,31 @@ int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols,
   const int tiles = ceil_div(M, GEMM_BM * cg) * ceil_div(N, bn);
   const int groups = num_sms / cg;
   out->grid = (tiles < groups ? tiles : groups) * cg;
+  // Tail tiles: when the last wave is partial, cut its tiles into narrower ones so that it costs a fraction of a full
+  // wave (same measured per-tile costs as gemm_pick_bn).  Only when the narrow tiles still fit one wave.
+  out->args.n_main = tiles;
+  out->args.tail_split = 1;
+  out->tmBt = out->tmB;
+  {
+    static const bool tail_off = [] { const char* e = getenv("PRISMA_GEMM_TAIL"); return e && e[0] == '0'; }();
+    const int full = tiles / groups, rem = tiles % groups;
+    auto cost = [](int w) { return w >= 256 ? 134.0 : (w >= 128 ? 100.0 : (w >= 64 ? 68.0 : 51.0)); };
+    if (!tail_off && !force_bn && full >= 1 && rem > 0) {
+      int best_split = 1;
+      double best = cost(bn);
+      for (int split = 2; split <= 4; split *= 2) {
+        const int bw = bn / split;
+        if (bw < 32 * cg || rem * split > groups) continue;
+        if (cost(bw) < best) { best = cost(bw); best_split = split; }
+      }
+      if (best_split > 1) {
+        out->args.n_main = full * groups;
+        out->args.tail_split = best_split;
+        PRISMA_TRY(make_tmap_2d_f16(&out->tmBt, W, (uint64_t)taps * kchunks * 64, (uint64_t)w_rows,
+                                    (uint64_t)taps * kchunks * 64, 64, bn / best_split / cg));
+      }
+    }
+  }
   out->flops = 2.0 * M * (double)N * taps * a_cols;
   return 0;
 }
@@ -110,7 +135,7 @@ static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
     attr_set = true;
   }
   if (CG == 1) {
-    gemm_tc_kernel<BN, CG><<<g.grid, GEMM_THREADS, GemmCfg<BN, CG>::SMEM_BYTES, stream>>>(g.tmA, g.tmB, g.args);
+    gemm_tc_kernel<BN, CG><<<g.grid, GEMM_THREADS, GemmCfg<BN, CG>::SMEM_BYTES, stream>>>(g.tmA, g.tmB, g.tmBt, g.args);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.grid);
@@ -122,7 +147,7 @@ static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, g.tmA, g.tmB, g.args));
+    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, g.tmA, g.tmB, g.tmBt, g.args));
   }
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;

@@ -77,6 +77,8 @@ struct GemmArgs {
   int taps;
   int kchunks;  // 64-wide K blocks per tap
   int tap_off[GEMM_MAX_TAPS];
+  int n_main;      // work items [0, n_main) are full BN-wide tiles; the remaining tiles are each cut into `tail_split`
+  int tail_split;  // narrower tiles (BN / tail_split wide) so the last partial wave costs a fraction of a full one; 1 = off
   int raster_n;  // 1: consecutive tiles walk N first (the CTAs of a wave share few A row panels and all of W: A is read
                  // from HBM once when M >> N); 0: M first
   GemmEpilogue ep;
@@ -189,7 +191,7 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
 template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ GemmArgs args) {
+               const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ GemmArgs args) {
   using Cfg = GemmCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -216,6 +218,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_n = (args.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = args.taps * args.kchunks;
+  // work items: full tiles first, then the tail tiles cut into `split` narrow ones (see GemmArgs::n_main)
+  const int split = args.tail_split, n_main = split > 1 ? args.n_main : num_tiles;
+  const int num_items = n_main + (num_tiles - n_main) * split;
+  const int bw_tail = BN / split;  // width of a tail tile
+  auto item_tile = [&](int item, int* tm, int* tn, int* nsub, int* bw) {
+    int big = item;
+    *nsub = 0; *bw = BN;
+    if (item >= n_main) { const int u = item - n_main; big = n_main + u / split; *nsub = (u % split) * bw_tail; *bw = bw_tail; }
+    *tm = args.raster_n ? big / tiles_n : big % tiles_m;
+    *tn = args.raster_n ? big % tiles_n : big / tiles_m;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -234,23 +247,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = group; tile < num_tiles; tile += num_groups) {
-        const int tm = args.raster_n ? tile / tiles_n : tile % tiles_m;
-        const int tn = args.raster_n ? tile % tiles_n : tile / tiles_m;
+      for (int tile = group; tile < num_items; tile += num_groups) {
+        int tm, tn, nsub, bw;
+        item_tile(tile, &tm, &tn, &nsub, &bw);
         const int m0 = tm * TILE_M + rank * GEMM_BM;
-        const int n0 = tn * BN + rank * (BN / CG);
+        const int n0 = tn * BN + nsub + rank * (bw / CG);
+        const CUtensorMap* tb = bw == BN ? &tmB : &tmBt;               // the tail map has a (bw / CG)-row box
+        const uint32_t stage_bytes = Cfg::A_BYTES + (bw / CG) * GEMM_BK * 2;
         int tap = 0, chunk = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (CG == 2) {
             // both CTAs' bytes land on the leader's barrier; only the leader arrives (count 1) and posts the total
-            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * stage_bytes);
             tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], chunk * GEMM_BK, m0 + args.tap_off[tap]);
-            tma_load_2d_pair(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+            tma_load_2d_pair(sB + stage * Cfg::B_BYTES, tb, &full[stage], kb * GEMM_BK, n0);
           } else {
-            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            mbar_arrive_expect_tx(&full[stage], stage_bytes);
             tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], chunk * GEMM_BK, m0 + args.tap_off[tap]);
-            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, tb, &full[stage], kb * GEMM_BK, n0);
           }
           if (++chunk == args.kchunks) { chunk = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -260,10 +275,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(TILE_M, BN);
+      constexpr uint32_t idesc_full = make_idesc_f16(TILE_M, BN);
+      const uint32_t idesc_tail = make_idesc_f16(TILE_M, bw_tail);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
+      for (int tile = group; tile < num_items; tile += num_groups, ++it) {
+        const uint32_t idesc = tile < n_main ? idesc_full : idesc_tail;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
@@ -295,13 +312,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cg = lane & 7;     // coalesced phase: which 4-column group of the 32-column chunk
     const int rsub = lane >> 3;  // coalesced phase: row offset inside a 4-row step
     int it = 0;
-    for (int tile = group; tile < num_tiles; tile += num_groups, ++it) {
+    for (int tile = group; tile < num_items; tile += num_groups, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int tm = args.raster_n ? tile / tiles_n : tile % tiles_m;
-      const int tn = args.raster_n ? tile % tiles_n : tile / tiles_m;
+      int tm, tn, nsub, bw;
+      item_tile(tile, &tm, &tn, &nsub, &bw);
       const int m0 = tm * TILE_M + rank * GEMM_BM;
-      const int n0 = tn * BN;
+      const int n0 = tn * BN + nsub;
       const int m = m0 + quarter * 32 + lane;
       // ---- row mapping of "my" accumulator row (lane == row inside this warp's 32-row slab)
       int valid = m < args.M;
@@ -349,7 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c0 = chunk_par * 32; c0 < BN; c0 += 64) {
+      for (int c0 = chunk_par * 32; c0 < bw; c0 += 64) {
         if (n0 + c0 >= args.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
@@ -428,7 +445,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // Host-side prepared launch: tensor maps encoded once, replayed every frame (also inside CUDA graphs).
 struct GemmLaunch {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmBt;  // tmBt: W with the narrow box of the tail tiles (== tmB when there is no tail)
   GemmArgs args;
   int bn = 128;
   int cg = 1;  // 2 = CTA pairs (cta_group::2), 256 x bn tiles

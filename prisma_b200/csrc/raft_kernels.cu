@@ -10,24 +10,34 @@ namespace prisma {
 // -> fp16 [B*Ho*Wo][192], k = c*49 + ky*7 + kx (zero padded 147..191).  Stride 2 is applied here, no wasted rows.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_im2col_stem(const float* __restrict__ x, int B, int H, int W, __half* __restrict__ out) {
+  // one thread = 8 consecutive k of one output pixel (a 16-byte store); consecutive threads = consecutive k groups, so a
+  // warp writes 512 contiguous bytes and its gathers walk the same few image rows
   const int Ho = H / 2, Wo = W / 2;
-  const long long pix = blockIdx.x;  // b*Ho*Wo + oy*Wo + ox
-  const int b = (int)(pix / ((long long)Ho * Wo));
-  const int r = (int)(pix - (long long)b * Ho * Wo);
-  const int oy = r / Wo, ox = r - oy * Wo;
-  const float* img = x + (size_t)b * 3 * H * W;
-  for (int k = threadIdx.x; k < 192; k += blockDim.x) {
-    float v = 0.f;
-    if (k < 147) {
-      const int c = k / 49, t = k - c * 49, ky = t / 7, kx = t - ky * 7;
-      const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[((size_t)c * H + iy) * W + ix];
+  const long long total = (long long)B * Ho * Wo * 24;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % 24);
+    const long long pix = i / 24;  // b*Ho*Wo + oy*Wo + ox
+    const int b = (int)(pix / ((long long)Ho * Wo));
+    const int r = (int)(pix - (long long)b * Ho * Wo);
+    const int oy = r / Wo, ox = r - oy * Wo;
+    const float* img = x + (size_t)b * 3 * H * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      v[j] = 0.f;
+      if (k < 147) {
+        const int c = k / 49, t = k - c * 49, ky = t / 7, kx = t - ky * 7;
+        const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[j] = img[((size_t)c * H + iy) * W + ix];
+      }
     }
-    out[(size_t)pix * 192 + k] = __float2half_rn(v);
+    *reinterpret_cast<uint4*>(out + (size_t)pix * 192 + g * 8) =
+        make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
   }
 }
 int raft_im2col_stem(const float* x, int B, int H, int W, __half* out, cudaStream_t s) {
-  k_im2col_stem<<<(unsigned)((long long)B * (H / 2) * (W / 2)), 64, 0, s>>>(x, B, H, W, out);
+  k_im2col_stem<<<148 * 16, 256, 0, s>>>(x, B, H, W, out);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -164,54 +174,6 @@ int raft_cnet_split(const float* cn, int B, int H, int W, int pad, float* h_mast
 }
 
 // ------------------------------------------------------------------------------------------------
-// convf1 = Conv2d(2, 128, 7, padding 3) + ReLU on the current flow (update.py:84,91): Cin = 2 is too thin for the
-// tensor core; direct conv, one thread per (pixel, 4 output channels), weights [128][2][7][7] fp32 read through L1.
-// Also refreshes the flow channels (382,383) of the GRU operand maps (update.py:97: cat([out, flow])).
-// ------------------------------------------------------------------------------------------------
-// Block = 128 threads (one per output channel) x FC_PIX pixels of one image row segment: the 98x128 weight matrix is
-// staged in shared memory once per block (k-major, so the 128 lanes read consecutive words), each pixel's 7x7x2 flow
-// patch is staged next to it and broadcast; 98 FMAs per (pixel, channel).
-constexpr int FC_PIX = 32;
-__global__ void __launch_bounds__(128) k_flow_conv7(const float* __restrict__ coords0, const float* __restrict__ coords1,
-                                                    const float* __restrict__ w, const float* __restrict__ bias, int B, int H,
-                                                    int W, int pad, __half* __restrict__ out128) {
-  extern __shared__ float fc_smem[];
-  float* sw = fc_smem;                                                  // [98][128]
-  float (*sp)[100] = reinterpret_cast<float (*)[100]>(fc_smem + 98 * 128);  // [FC_PIX][100]
-  const int P = H * W;
-  const int tiles_per_img = (P + FC_PIX - 1) / FC_PIX;
-  const int b = blockIdx.x / tiles_per_img;
-  const int p0 = (blockIdx.x - b * tiles_per_img) * FC_PIX;
-  const int c = threadIdx.x;
-  for (int k = 0; k < 98; ++k) sw[k * 128 + c] = w[(size_t)c * 98 + k];  // [co][ch][ky][kx] -> [k][co]
-  const float* c0 = coords0 + (size_t)b * 2 * P;
-  const float* c1 = coords1 + (size_t)b * 2 * P;
-  for (int idx = threadIdx.x; idx < FC_PIX * 98; idx += 128) {
-    const int pp = idx / 98, k = idx - pp * 98;
-    const int r = p0 + pp;
-    float v = 0.f;
-    if (r < P) {
-      const int y = r / W, x = r - y * W;
-      const int ch = k / 49, t = k - ch * 49, ky = t / 7, kx = t - ky * 7;
-      const int yy = y + ky - 3, xx = x + kx - 3;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = c1[(size_t)ch * P + yy * W + xx] - c0[(size_t)ch * P + yy * W + xx];
-    }
-    sp[pp][k] = v;
-  }
-  __syncthreads();
-  const float bs = bias[c];
-  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
-#pragma unroll 4
-  for (int pp = 0; pp < FC_PIX; ++pp) {
-    const int r = p0 + pp;
-    if (r >= P) break;
-    float acc = bs;
-#pragma unroll 14
-    for (int k = 0; k < 98; ++k) acc = fmaf(sp[pp][k], sw[k * 128 + c], acc);
-    const int y = r / W, x = r - y * W;
-    out128[(((size_t)b * Hp + y + pad) * Wp + x + pad) * 128 + c] = __float2half_rn(fmaxf(acc, 0.f));
-  }
-}
 // convf1 (7x7, 2 -> 128, update.py:84) as a GEMM: im2col of the flow with every fp32 value split into an fp16 pair
 // (hi = fp16(v), lo = fp16(v - hi)) so the tensor-core product keeps ~22 bits of the flow (values reach tens of pixels;
 // a single fp16 would cost 8e-4 of the 1e-3 budget).  Row = pixel, K = [98 hi | 30 zero | 98 lo | 30 zero].
@@ -265,21 +227,6 @@ int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pa
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int raft_flow_conv7(const float* coords0, const float* coords1, const float* w, const float* bias, int B, int H, int W,
-                    int pad, __half* out128, __half* hx, __half* rhx, cudaStream_t s) {
-  (void)hx; (void)rhx;
-  const int tiles = (H * W + FC_PIX - 1) / FC_PIX;
-  constexpr int smem = (98 * 128 + FC_PIX * 100) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PRISMA_CUDA_OK(cudaFuncSetAttribute(k_flow_conv7, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  k_flow_conv7<<<B * tiles, 128, smem, s>>>(coords0, coords1, w, bias, B, H, W, pad, out128);
-  PRISMA_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
 // ------------------------------------------------------------------------------------------------
 // SepConvGRU gate algebra (update.py:45-60) on padded rows:  rh = r * h ;  h = (1 - z) * h + z * q
 // zr: fp16 [rows][256] = [z | r] (sigmoid applied in the conv epilogue), q: fp16 [rows][128] (tanh applied).

@@ -11,8 +11,6 @@ int instnorm_apply(const float* x, const float* stats, int B, int H, int W, int 
                    const float* skip_raw, const float* skip_stats, __half* out, int pad, cudaStream_t s);
 int raft_cnet_split(const float* cn, int B, int H, int W, int pad, float* h_master, __half* hx, __half* rhx,
                     cudaStream_t s);
-int raft_flow_conv7(const float* coords0, const float* coords1, const float* w, const float* bias, int B, int H, int W,
-                    int pad, __half* out128, __half* hx, __half* rhx, cudaStream_t s);
 int raft_flow_im2col(const float* c0, const float* c1, int B, int H, int W, __half* out, cudaStream_t s);
 int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pad, __half* hx, __half* rhx, cudaStream_t s);
 int raft_gru_rh(const float* zr, const float* h_master, __half* rhx, long long rows, cudaStream_t s);

@@ -176,3 +176,27 @@ def test_mask_band_writes_mask_video_and_colmap_frames(tmp_path):
     assert frames == ["00000.png", "00001.png"]
     png = cv2.imread(str(folder / "mask" / "00000.png"))
     assert png.shape == (240, 320, 3) and set(np.unique(png)) <= {0, 1, 254, 255}   # 255 - (255 * count mod 256)
+
+
+@pytest.mark.gpu
+def test_depth_band_metric_path(tmp_path):
+    """--metric outdoor (what the reference's process.py passes by default): ZoeDepth head, no flip in the encode."""
+    import cv2
+    from oracle.frames import synthetic_frame
+    folder = tmp_path / "clip"
+    folder.mkdir()
+    w = cv2.VideoWriter(str(folder / "rgba.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
+    for t in range(3):
+        w.write(synthetic_frame(240, 320, t)[..., ::-1].copy())
+    w.release()
+    json.dump({"bands": {"rgba": {"url": "rgba.mp4"}}, "width": 320, "height": 240, "frames": 3, "fps": 24.0},
+              open(folder / "metadata.json", "w"))
+    rc = subprocess.call([sys.executable, os.path.join(ROOT, "bands", "depth_anything.py"), "-i", str(folder), "--metric", "outdoor",
+                          "--encoder", "vits", "--seeded-weights", "-n", "-d", "frames"])
+    assert rc == 0
+    mins = [float(l) for l in open(folder / "depth_anything_min.csv")]
+    maxs = [float(l) for l in open(folder / "depth_anything_max.csv")]
+    assert len(mins) == 3 and all(1.0 < a < b < 10.0 for a, b in zip(mins, maxs))      # metric depths of the seeded head
+    pred = np.load(folder / "frames" / "00000.npy")
+    assert pred.shape == (240, 320) and np.float32(pred.min()) == np.float32(mins[0])
+    assert sorted(os.listdir(folder / "frames"))[:2] == ["00000.npy", "00000.png"]

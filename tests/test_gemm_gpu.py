@@ -38,6 +38,11 @@ def _gemm(A, W, bias, act, bn):
     (2443, 3072, 1024, 0, 512),  # CTA pairs, ViT-L qkv: ragged M, many tiles per pair
     (9772, 1024, 4096, 1, 512),  # CTA pairs, 4-frame fc2 shape with gelu
     (300, 256, 200, 2, 512),     # CTA pairs: second CTA's rows partly / fully out of range, K tail
+    # auto tile choice with a partial last wave -> mixed-width tail tiles (GemmArgs::tail_split)
+    (29316, 1024, 192, 0, 0),    # CTA pairs: 460 pair tiles = 6 waves + 16 -> the 16 cut into 4 x 64-wide tiles
+    (26624, 256, 128, 2, 0),     # CTA pairs: 104 pair tiles = 1 wave + 30 -> cut into 2 x 128-wide tiles
+    (39008, 128, 384, 1, 0),     # single CTAs, 128-wide: 305 tiles = 2 waves + 9 -> 2 x 64-wide tiles, gelu
+    (20000, 64, 128, 0, 0),      # 64-wide: 157 tiles = 1 wave + 9 -> 2 x 32-wide tiles
 ])
 def test_gemm_matches_fp32_reference(M, N, K, act, bn):
     rng = np.random.default_rng(M * 7 + N * 3 + K)
