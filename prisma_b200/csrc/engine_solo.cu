@@ -363,31 +363,65 @@ int SoloEngine::build_plan(int H, int W) {
   { const SMap a = P[0], o = R0; push_step([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, 256, 0, 0, s); }); }
   { const SMap a = P[4], o = R4; push_step([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, 256, 0, 0, s); }); }
   const SMap lvl_in[5] = {R0, P[1], P[2], P[3], R4};
-  float* cls_out[5]; float* ker_out[5];
+  // The five levels share the tower weights: they run as one stack of F x F frames (F = largest grid), level l in the
+  // top-left S_l x S_l of frame l; pixels outside stay zero = the convs' zero padding.  10 GEMMs + 8 GroupNorms in total.
+  const int F = *std::max_element(num_grids, num_grids + 5), FP = (F + 2) * (F + 2);
+  GridSizes gs;
+  for (int l = 0; l < 8; ++l) gs.s[l] = l < 5 ? num_grids[l] : 0;
+  struct TMap { __half* p; int C; };
+  auto new_tmap = [&](TMap* t, int c) -> int { t->C = c; return s_alloc(plan_allocs, &t->p, (size_t)5 * FP * c); };
+  float* tower_raw = nullptr;  // dense fp32 conv output [5][F*F][512]
+  PRISMA_TRY(s_alloc(plan_allocs, &tower_raw, (size_t)5 * F * F * 512));
+  auto conv_t = [&](const TMap& in, int cin_cols, const SoloConvW& w, GemmEpilogue ep, float* dst_dense) -> int {
+    int off[9];
+    for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky - 1) * (F + 2) + (kx - 1);
+    ep.in_w = F + 2; ep.in_h = F + 2; ep.img_rows = FP; ep.sub = 1; ep.pad = 1;
+    ep.row_map = ROW_PAD2TOK; ep.out_f32 = dst_dense; ep.out_f32_ld = w.cout;
+    GemmLaunch g;
+    PRISMA_TRY(gemm_prepare(&g, in.p, 5LL * FP, cin_cols, in.C, w.w, round_up(w.cout, 256), 5 * FP, w.cout, 9, off, ep, num_sms));
+    double px = 0; for (int l = 0; l < 5; ++l) px += (double)num_grids[l] * num_grids[l];
+    flops += 2.0 * px * 9 * w.cin * w.cout;
+    push_step([g](cudaStream_t s) { return gemm_run(g, s); });
+    return 0;
+  };
+  auto gnconv_t = [&](const TMap& in, int cin_cols, const SoloConvW& w, const TMap& out) -> int {
+    GemmEpilogue ep;
+    PRISMA_TRY(conv_t(in, cin_cols, w, ep, tower_raw));
+    const float* gw = w.gn_w; const float* gb = w.gn_b; __half* o = out.p; const int c = w.cout;
+    push_step([=](cudaStream_t s) { return groupnorm_relu_grid_f16(tower_raw, 5, F, gs, c, 32, gw, gb, o, s); });
+    return 0;
+  };
+  TMap g0, ka, kb, ca, cb;
+  PRISMA_TRY(new_tmap(&g0, 320));
+  PRISMA_TRY(new_tmap(&ka, 512)); PRISMA_TRY(new_tmap(&kb, 512));
+  PRISMA_TRY(new_tmap(&ca, 512)); PRISMA_TRY(new_tmap(&cb, 512));
   int cell0[5], cells = 0;
   for (int l = 0; l < 5; ++l) {
     const int S = num_grids[l];
     cell0[l] = cells; cells += S * S;
-    SMap g0, ka, kb, ca, cb;
-    PRISMA_TRY(new_map(&g0, S, S, 320));
-    PRISMA_TRY(new_map(&ka, S, S, 512)); PRISMA_TRY(new_map(&kb, S, S, 512));
-    PRISMA_TRY(new_map(&ca, S, S, 512)); PRISMA_TRY(new_map(&cb, S, S, 512));
     const SMap a = lvl_in[l];
-    push_step([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, g0.p, S, S, 320, 1, 0, s); });
-    PRISMA_TRY(gnconv(g0, 320, kconv[0], &ka, nullptr));
-    PRISMA_TRY(gnconv(ka, 512, kconv[1], &kb, nullptr));
-    PRISMA_TRY(gnconv(kb, 512, kconv[2], &ka, nullptr));
-    PRISMA_TRY(gnconv(ka, 512, kconv[3], &kb, nullptr));
-    PRISMA_TRY(s_alloc(plan_allocs, &ker_out[l], (size_t)S * S * 256));
-    { GemmEpilogue ep; ep.bias = conv_kernel.b; PRISMA_TRY(conv(kb, 512, conv_kernel, 1, ep, nullptr, ker_out[l])); }
-    PRISMA_TRY(gnconv(g0, 256, cconv[0], &ca, nullptr));
-    PRISMA_TRY(gnconv(ca, 512, cconv[1], &cb, nullptr));
-    PRISMA_TRY(gnconv(cb, 512, cconv[2], &ca, nullptr));
-    PRISMA_TRY(gnconv(ca, 512, cconv[3], &cb, nullptr));
-    PRISMA_TRY(s_alloc(plan_allocs, &cls_out[l], (size_t)S * S * SOLO_NC));
-    { GemmEpilogue ep; ep.bias = conv_cls.b; PRISMA_TRY(conv(cb, 512, conv_cls, 1, ep, nullptr, cls_out[l])); }
-    taps["cls" + std::to_string(l)] = {cls_out[l], 0, S * S, SOLO_NC, 0};
-    taps["kernel" + std::to_string(l)] = {ker_out[l], 0, S * S, 256, 0};
+    __half* dst = g0.p + (size_t)l * FP * 320;
+    push_step([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, dst, S, S, 320, 1, 0, s, F); });
+  }
+  float *ker_all = nullptr, *cls_all = nullptr;  // dense fp32 [5][F*F][256] / [5][F*F][80]
+  PRISMA_TRY(s_alloc(plan_allocs, &ker_all, (size_t)5 * F * F * 256));
+  PRISMA_TRY(s_alloc(plan_allocs, &cls_all, (size_t)5 * F * F * SOLO_NC));
+  PRISMA_TRY(gnconv_t(g0, 320, kconv[0], ka));
+  PRISMA_TRY(gnconv_t(ka, 512, kconv[1], kb));
+  PRISMA_TRY(gnconv_t(kb, 512, kconv[2], ka));
+  PRISMA_TRY(gnconv_t(ka, 512, kconv[3], kb));
+  { GemmEpilogue ep; ep.bias = conv_kernel.b; PRISMA_TRY(conv_t(kb, 512, conv_kernel, ep, ker_all)); }
+  PRISMA_TRY(gnconv_t(g0, 256, cconv[0], ca));
+  PRISMA_TRY(gnconv_t(ca, 512, cconv[1], cb));
+  PRISMA_TRY(gnconv_t(cb, 512, cconv[2], ca));
+  PRISMA_TRY(gnconv_t(ca, 512, cconv[3], cb));
+  { GemmEpilogue ep; ep.bias = conv_cls.b; PRISMA_TRY(conv_t(cb, 512, conv_cls, ep, cls_all)); }
+  float* cls_out[5]; float* ker_out[5];
+  for (int l = 0; l < 5; ++l) {
+    cls_out[l] = cls_all + (size_t)l * F * F * SOLO_NC;
+    ker_out[l] = ker_all + (size_t)l * F * F * 256;
+    taps["cls" + std::to_string(l)] = {cls_out[l], 5, num_grids[l], SOLO_NC, F};
+    taps["kernel" + std::to_string(l)] = {ker_out[l], 5, num_grids[l], 256, F};
   }
 
   cur_tag = "decode";
@@ -405,7 +439,7 @@ int SoloEngine::build_plan(int H, int W) {
   { int* cnt = d_count; push_step([=](cudaStream_t s) { PRISMA_CUDA_OK(cudaMemsetAsync(cnt, 0, 4, s)); return 0; }); }
   for (int l = 0; l < 5; ++l) {
     const float* lg = cls_out[l]; const int S = num_grids[l], c0 = cell0[l]; const float st = strides[l]; int* cnt = d_count;
-    push_step([=](cudaStream_t s) { return solo_candidates(lg, S, c0, SOLO_NC, 0.1f, st, cand_raw, cnt, SOLO_CAP, s); });
+    push_step([=](cudaStream_t s) { return solo_candidates(lg, S, c0, SOLO_NC, 0.1f, st, cand_raw, cnt, SOLO_CAP, s, F); });
   }
   { int* cnt = d_count; push_step([=](cudaStream_t s) { return solo_sort_candidates(cand_raw, cnt, SOLO_CAP, cand, s); }); }
   __half* kmat = nullptr;
@@ -415,8 +449,11 @@ int SoloEngine::build_plan(int H, int W) {
   PRISMA_TRY(s_alloc(plan_allocs, &d_cell0, 8));
   PRISMA_CUDA_OK(cudaMemcpy(d_lvl_ptr, ker_out, 5 * sizeof(float*), cudaMemcpyHostToDevice));
   PRISMA_CUDA_OK(cudaMemcpy(d_cell0, cell0, 5 * sizeof(int), cudaMemcpyHostToDevice));
+  int* d_lvl_S = nullptr;
+  PRISMA_TRY(s_alloc(plan_allocs, &d_lvl_S, 8));
+  PRISMA_CUDA_OK(cudaMemcpy(d_lvl_S, num_grids, 5 * sizeof(int), cudaMemcpyHostToDevice));
   { const int* cnt = d_count;
-    push_step([=](cudaStream_t s) { return solo_gather_kernels(cand, cnt, SOLO_CAP, d_lvl_ptr, d_cell0, 5, SOLO_NC, 256, kmat, s); }); }
+    push_step([=](cudaStream_t s) { return solo_gather_kernels(cand, cnt, SOLO_CAP, d_lvl_ptr, d_cell0, 5, SOLO_NC, 256, kmat, s, d_lvl_S, F); }); }
   // dynamic conv: mask_preds = sigmoid(kernels [n][256] . mask_feats [HW][256]^T) as one GEMM (solov2_head.py:717-722)
   __half* masks = nullptr;
   PRISMA_TRY(s_alloc(plan_allocs, &masks, (size_t)SOLO_CAP * HW));
@@ -545,6 +582,16 @@ long long SoloEngine::read_tap(const std::string& name, float* out, long long ca
     std::vector<uint8_t> h(n);
     if (cudaMemcpy(h.data(), t.p, n, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
     for (long long i = 0; i < n; ++i) out[i] = (float)h[i];
+    return n;
+  }
+  if (t.kind == 5) {  // S x S grid of an F-wide dense fp32 frame: a = S, b = channels, c = F
+    const long long n = (long long)t.a * t.a * t.b;
+    if (n > capacity) { set_last_error("tap buffer too small"); return -1; }
+    std::vector<float> h((size_t)t.c * t.c * t.b);
+    if (cudaMemcpy(h.data(), t.p, h.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+    for (int y = 0; y < t.a; ++y)
+      for (int x = 0; x < t.a; ++x)
+        for (int c = 0; c < t.b; ++c) out[((long long)y * t.a + x) * t.b + c] = h[((size_t)y * t.c + x) * t.b + c];
     return n;
   }
   if (t.kind == 4) {

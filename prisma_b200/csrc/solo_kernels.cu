@@ -199,6 +199,41 @@ int groupnorm_relu_f16(const float* x, int H, int W, int C, int groups, const fl
   return 0;
 }
 
+// Stacked-grid variant for the head towers: one block per (frame, group); deterministic (fixed per-thread strides, fixed
+// smem tree).  x: dense fp32 [B][F*F][C]; valid pixels of frame b: y, x < S[b].
+__global__ void k_gn_grid(const float* __restrict__ x, int F, GridSizes S, int C, int groups, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, __half* __restrict__ out) {
+  const int b = blockIdx.y, g = blockIdx.x, Sb = S.s[b], cpg = C / groups, n = Sb * Sb * cpg;
+  const float* xb = x + (size_t)b * F * F * C + g * cpg;
+  __shared__ double sh_s[256], sh_q[256];
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i % cpg, p = i / cpg, yy = p / Sb, xx = p - yy * Sb;
+    const float v = xb[(size_t)(yy * F + xx) * C + c];
+    s += v; q += (double)v * v;
+  }
+  sh_s[threadIdx.x] = s; sh_q[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { sh_s[threadIdx.x] += sh_s[threadIdx.x + o]; sh_q[threadIdx.x] += sh_q[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const double mean = sh_s[0] / n, var = fmax(sh_q[0] / n - mean * mean, 0.0);
+  const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + 1e-5));
+  __half* ob = out + (size_t)b * (F + 2) * (F + 2) * C + g * cpg;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i % cpg, p = i / cpg, yy = p / Sb, xx = p - yy * Sb;
+    const float v = xb[(size_t)(yy * F + xx) * C + c];
+    ob[prow(yy, xx, F) * C + c] = __float2half_rn(fmaxf(fmaf((v - mu) * rstd, gamma[g * cpg + c], beta[g * cpg + c]), 0.f));
+  }
+}
+int groupnorm_relu_grid_f16(const float* x, int B, int F, GridSizes S, int C, int groups, const float* gamma, const float* beta,
+                            __half* out_padded, cudaStream_t s) {
+  k_gn_grid<<<dim3(groups, B), 256, 0, s>>>(x, F, S, C, groups, gamma, beta, out_padded);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // F.interpolate(mode="bilinear", align_corners=False) between zero-bordered NHWC fp16 maps (nn.Upsample x2 of the mask
 // feature head solov2_head.py:101-121, resize_feats solo_head.py:133-153, the S x S grid resize solov2_head.py:266-270),
@@ -211,7 +246,7 @@ __device__ __forceinline__ float linspace_m1_1(int i, int n) {  // torch.linspac
   return i < n / 2 ? -1.f + step * (float)i : 1.f - step * (float)(n - 1 - i);
 }
 __global__ void k_resize_bilinear(const __half* __restrict__ src, int Hs, int Ws, int Cs, __half* __restrict__ dst, int Hd, int Wd,
-                                  int Cd, float sy, float sx, int coord, int accumulate) {
+                                  int Cd, float sy, float sx, int coord, int accumulate, int Wdf) {
   const int cv = Cs / 8 + (coord ? 1 : 0);
   const long long total = (long long)Hd * Wd * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -221,7 +256,7 @@ __global__ void k_resize_bilinear(const __half* __restrict__ src, int Hs, int Ws
     const int y0 = (int)fy, x0 = (int)fx;
     const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
     const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    __half* d = dst + prow(y, x, Wd) * Cd + c8 * 8;
+    __half* d = dst + prow(y, x, Wdf) * Cd + c8 * 8;
     if (c8 * 8 >= Cs) {  // the two coordinate channels (+ six zero channels of the 8-vector)
       const float cx = hy * (hx * linspace_m1_1(x0, Ws) + lx * linspace_m1_1(x1, Ws)) + ly * (hx * linspace_m1_1(x0, Ws) + lx * linspace_m1_1(x1, Ws));
       const float cy = hy * (hx * linspace_m1_1(y0, Hs) + lx * linspace_m1_1(y0, Hs)) + ly * (hx * linspace_m1_1(y1, Hs) + lx * linspace_m1_1(y1, Hs));
@@ -249,9 +284,9 @@ __global__ void k_resize_bilinear(const __half* __restrict__ src, int Hs, int Ws
   }
 }
 int resize_bilinear_f16(const __half* src, int Hs, int Ws, int Csrc, __half* dst, int Hd, int Wd, int Cdst, int coord,
-                        int accumulate, cudaStream_t s) {
+                        int accumulate, cudaStream_t s, int dst_frame_w) {
   k_resize_bilinear<<<148 * 4, 256, 0, s>>>(src, Hs, Ws, Csrc, dst, Hd, Wd, Cdst, (float)Hs / (float)Hd, (float)Ws / (float)Wd,
-                                           coord, accumulate);
+                                           coord, accumulate, dst_frame_w > 0 ? dst_frame_w : Wd);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -262,16 +297,17 @@ int resize_bilinear_f16(const __half* src, int Hs, int Ws, int Csrc, __half* dst
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 __global__ void k_solo_candidates(const float* __restrict__ logits, int S, int cell0, int NC, float thr, float stride,
-                                  SoloCand* __restrict__ cand, int* __restrict__ count, int cap) {
+                                  SoloCand* __restrict__ cand, int* __restrict__ count, int cap, int F) {
   const int total = S * S * NC;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % NC, cell = i / NC, y = cell / S, x = cell % S;
-    const float v = sigmoid_ref(logits[i]);
+    const size_t row = (size_t)y * F + x;  // the logits live in an F-wide frame (F == S when not stacked)
+    const float v = sigmoid_ref(logits[row * NC + c]);
     // local_max[y][x] of max_pool2d(k=2, stride 1, padding 1)[:-1, :-1] = max over (y-1..y, x-1..x)
     float m = v;
-    if (x > 0) m = fmaxf(m, sigmoid_ref(logits[(size_t)(cell - 1) * NC + c]));
-    if (y > 0) m = fmaxf(m, sigmoid_ref(logits[(size_t)(cell - S) * NC + c]));
-    if (x > 0 && y > 0) m = fmaxf(m, sigmoid_ref(logits[(size_t)(cell - S - 1) * NC + c]));
+    if (x > 0) m = fmaxf(m, sigmoid_ref(logits[(row - 1) * NC + c]));
+    if (y > 0) m = fmaxf(m, sigmoid_ref(logits[(row - F) * NC + c]));
+    if (x > 0 && y > 0) m = fmaxf(m, sigmoid_ref(logits[(row - F - 1) * NC + c]));
     if (m == v && v > thr) {
       const int k = atomicAdd(count, 1);
       if (k < cap) { cand[k].score = v; cand[k].flat = (cell0 + cell) * NC + c; cand[k].area = 0.f; cand[k].stride = stride; }
@@ -279,8 +315,8 @@ __global__ void k_solo_candidates(const float* __restrict__ logits, int S, int c
   }
 }
 int solo_candidates(const float* cls_logits, int S, int cell0, int num_classes, float score_thr, float stride, SoloCand* cand,
-                    int* count, int cap, cudaStream_t s) {
-  k_solo_candidates<<<64, 256, 0, s>>>(cls_logits, S, cell0, num_classes, score_thr, stride, cand, count, cap);
+                    int* count, int cap, cudaStream_t s, int frame) {
+  k_solo_candidates<<<64, 256, 0, s>>>(cls_logits, S, cell0, num_classes, score_thr, stride, cand, count, cap, frame > 0 ? frame : S);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -323,7 +359,7 @@ int solo_sort_candidates(const SoloCand* cand, int* count, int cap, SoloCand* so
 // kernel_preds[inds[:, 0]] (solov2_head.py:703): gather the 256-vector of each candidate's cell as an fp16 GEMM operand row
 __global__ void k_solo_gather(const SoloCand* __restrict__ cand, const int* __restrict__ count, int cap,
                               const float* const* __restrict__ lvl_kernels, const int* __restrict__ lvl_cell0, int levels, int NC,
-                              int C, __half* __restrict__ out) {
+                              int C, __half* __restrict__ out, const int* __restrict__ lvl_S, int F) {
   const int r = blockIdx.x;
   const int n = min(*count, cap);
   __half* o = out + (size_t)r * C;
@@ -334,12 +370,15 @@ __global__ void k_solo_gather(const SoloCand* __restrict__ cand, const int* __re
   const int cell = cand[r].flat / NC;
   int lvl = 0;
   while (lvl + 1 < levels && cell >= lvl_cell0[lvl + 1]) ++lvl;
-  const float* k = lvl_kernels[lvl] + (size_t)(cell - lvl_cell0[lvl]) * C;
+  int local = cell - lvl_cell0[lvl];
+  if (lvl_S) { const int S = lvl_S[lvl]; local = (local / S) * F + local % S; }  // cell (y, x) inside an F-wide frame
+  const float* k = lvl_kernels[lvl] + (size_t)local * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = __float2half_rn(k[c]);
 }
 int solo_gather_kernels(const SoloCand* cand, const int* count, int cap, const float* const* lvl_kernels,
-                        const int* lvl_cell0, int levels, int num_classes, int C, __half* out, cudaStream_t s) {
-  k_solo_gather<<<cap, 64, 0, s>>>(cand, count, cap, lvl_kernels, lvl_cell0, levels, num_classes, C, out);
+                        const int* lvl_cell0, int levels, int num_classes, int C, __half* out, cudaStream_t s,
+                        const int* lvl_S, int frame) {
+  k_solo_gather<<<cap, 64, 0, s>>>(cand, count, cap, lvl_kernels, lvl_cell0, levels, num_classes, C, out, lvl_S, frame);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }

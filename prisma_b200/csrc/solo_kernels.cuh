@@ -23,13 +23,21 @@ int groupnorm_relu_f16(const float* x, int H, int W, int C, int groups, const fl
 // generate_coordinate channels (x, y in [-1,1] of the SOURCE grid, interpolated like the features) at [Csrc, Csrc+2);
 // accumulate: dst += value
 int resize_bilinear_f16(const __half* src, int Hs, int Ws, int Csrc, __half* dst, int Hd, int Wd, int Cdst, int coord,
-                        int accumulate, cudaStream_t s);
+                        int accumulate, cudaStream_t s, int dst_frame_w = 0);  // dst_frame_w: row pitch of dst if wider than Wd
+// The five head levels share their tower weights, so they run as ONE stack of F x F frames (F = the largest grid, 40): level
+// l occupies the top-left S_l x S_l of frame l, everything else stays zero (which is exactly the convs' zero padding).
+struct GridSizes { int s[8]; };
+// GroupNorm(32)+ReLU of a stacked conv output x: dense fp32 [B][F*F][C]; statistics over the valid S_l x S_l pixels of each
+// frame; writes the valid pixels of the stacked zero-bordered fp16 map [B][(F+2)^2][C].  One block per (frame, group).
+int groupnorm_relu_grid_f16(const float* x, int B, int F, GridSizes S, int C, int groups, const float* gamma, const float* beta,
+                            __half* out_padded, cudaStream_t s);
 // decode (solov2_head.py:582-766, matrix_nms.py)
 int solo_candidates(const float* cls_logits, int S, int cell0, int num_classes, float score_thr, float stride, SoloCand* cand,
-                    int* count, int cap, cudaStream_t s);
+                    int* count, int cap, cudaStream_t s, int frame = 0);  // frame: row pitch (in cells) of the logits, 0 = S
 int solo_sort_candidates(const SoloCand* cand, int* count, int cap, SoloCand* sorted, cudaStream_t s);  // nonzero() order
 int solo_gather_kernels(const SoloCand* cand, const int* count, int cap, const float* const* lvl_kernels,
-                        const int* lvl_cell0, int levels, int num_classes, int C, __half* out, cudaStream_t s);
+                        const int* lvl_cell0, int levels, int num_classes, int C, __half* out, cudaStream_t s,
+                        const int* lvl_S = nullptr, int frame = 0);  // lvl_S/frame: kernels stored in F x F frames
 int solo_mask_stats(const __half* masks, int HW, float mask_thr, SoloCand* cand, const int* count, int cap,
                     cudaStream_t s);
 int solo_rank(const SoloCand* cand, const int* count, int cap, int nms_pre, int* top, int* n_top,
