@@ -6,7 +6,7 @@ process_image(args), process_video(args), the CLI flags of bands/depth_anything.
 (<band>.mp4|png, <band>_min.csv, <band>_max.csv, optional <sub>/%05d.npy) and the metadata.json keys
 (:155-166,241-251).  The model call and the numpy encode are replaced by libprisma_b200.so; there is no CPU path.
 
-`--metric indoor|outdoor` runs the ZoeDepth metric head (one frame per pass, no flip in the encode, reference :188).
+`--metric indoor|outdoor` runs the ZoeDepth metric head (no flip in the encode, reference :188).
 Additions: --weights (state_dict: torch .pth/.pt or .npz), --seeded-weights (offline test weights), --device.
 """
 import argparse

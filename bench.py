@@ -217,16 +217,16 @@ def midas_extras(device):
 
 def zoe_extras(device):
     """depth_anything --metric outdoor (what the reference's process.py passes by default): ZoeDepth metric head on ViT-L,
-    392x518 network input, one frame per pass, frames resident."""
+    392x518 network input, 12-frame passes, frames resident."""
     from prisma_b200.depth import ZoeDepthEngine
     from prisma_b200.seeded_weights import make_zoe_weights
     eng = ZoeDepthEngine(make_zoe_weights("vitl", 0), device=device, encoder="vitl")
-    eng.time_resident(H, W, 5, 1)
-    ms = eng.time_resident(H, W, 30, 1)
-    w = eng.work(H, W, 1)
+    eng.time_resident(H, W, 3, BATCH)
+    ms = eng.time_resident(H, W, 8, BATCH)
+    w = eng.work(H, W, BATCH)
     eng.close()
-    return {"workload": "synthetic 720p frames, depth_anything --metric (ZoeDepth head, 392x518 net input), one frame per pass",
-            "frames_per_s_device": 1e3 / ms, "ms_per_pass": ms, "launches_per_pass": w["launches"]}
+    return {"workload": "synthetic 720p frames, depth_anything --metric (ZoeDepth head, 392x518 net input), frames resident",
+            "frames_per_s_device": BATCH / (ms * 1e-3), "ms_per_pass": ms, "frames_per_pass": BATCH, "launches_per_pass": w["launches"]}
 
 
 def mask_extras(device):

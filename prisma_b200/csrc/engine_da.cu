@@ -381,7 +381,6 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
   PRISMA_CHECK(finalized, "weights not finalized");
   PRISMA_CHECK(Bt >= 1 && Bt <= 64, "batch must be in [1,64]");
   if (plan_H == H && plan_W == W && batch == Bt) return 0;
-  PRISMA_CHECK(!metric || Bt == 1, "the metric (ZoeDepth) head runs one frame per pass");
   plan_W_req = W;
   batch = Bt;
   PRISMA_CUDA_OK(cudaSetDevice(device));
@@ -687,30 +686,32 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
 // of each level reads the zero-bordered map and writes dense rows), the interpolations / attractors / log-binomial are the
 // zoe_kernels.  Embeddings and bin centres stay fp32 between levels; GEMM operands are fp16.
 int DepthEngine::build_metric_head(const PMap& btlnck, const PMap* r_maps, const __half* act32, int Bt) {
-  PRISMA_CHECK(Bt == 1, "the metric head runs one frame per pass");
   const int zero_off[1] = {0};
+  // 1x1 conv over the pixel rows of all Bt frames; the first conv of a level reads the stacked zero-bordered maps
   auto lin = [&](const char* name, const __half* A, long long a_rows, int a_pitch, const DaWeights::Lin& L, int M, int act,
                  __half* out16, float* out32, int out_ld, const PMap* padded_src) -> int {
     GemmEpilogue ep; ep.bias = L.b; ep.act = act;
     if (out16) { ep.out_f16 = out16; ep.out_f16_ld = out_ld; } else { ep.out_f32 = out32; ep.out_f32_ld = out_ld; }
-    if (padded_src) { ep.row_map = ROW_PAD2TOK; ep.in_w = padded_src->Wp(); ep.in_h = padded_src->Hp(); ep.img_rows = 0; ep.pad = 1; }
+    if (padded_src) {
+      ep.row_map = ROW_PAD2TOK; ep.in_w = padded_src->Wp(); ep.in_h = padded_src->Hp(); ep.img_rows = (int)padded_src->img_rows(); ep.pad = 1;
+    }
     const int n_pad = round_up(L.n, 4);  // N % 4: the single attractor of the last level is padded with zero rows
     return add_gemm(G_HEAD, name, A, a_rows, round_up(L.k, 64), a_pitch, L.w, M, n_pad, 1, zero_off, ep, 2.0 * M * (double)L.k * L.n);
   };
   // ---- bottleneck level: x_d0 = conv2(layer4_rn) ; seed bins ; seed embedding
-  const int P0 = btlnck.H * btlnck.W;
+  const int P0 = btlnck.H * btlnck.W, Fp = round_up(F, 64);
   __half *x0 = nullptr, *s1 = nullptr, *e1 = nullptr;
   float *b_prev = nullptr, *emb_prev = nullptr;
-  PRISMA_TRY(dev_alloc(plan_allocs, &x0, (size_t)P0 * round_up(F, 64)));
-  PRISMA_TRY(dev_alloc(plan_allocs, &s1, (size_t)P0 * 256));
-  PRISMA_TRY(dev_alloc(plan_allocs, &e1, (size_t)P0 * 128));
-  PRISMA_TRY(dev_alloc(plan_allocs, &b_prev, (size_t)P0 * 64));
-  PRISMA_TRY(dev_alloc(plan_allocs, &emb_prev, (size_t)P0 * 128));
-  PRISMA_TRY(lin("zoe_conv2", btlnck.p, btlnck.rows(), F, w.z_conv2, (int)btlnck.rows(), 0, x0, nullptr, round_up(F, 64), &btlnck));
-  PRISMA_TRY(lin("zoe_seed0", x0, P0, round_up(F, 64), w.z_seed0, P0, 2, s1, nullptr, 256, nullptr));
-  PRISMA_TRY(lin("zoe_seed2", s1, P0, 256, w.z_seed2, P0, 5, nullptr, b_prev, 64, nullptr));
-  PRISMA_TRY(lin("zoe_sproj0", x0, P0, round_up(F, 64), w.z_sproj0, P0, 2, e1, nullptr, 128, nullptr));
-  PRISMA_TRY(lin("zoe_sproj2", e1, P0, 128, w.z_sproj2, P0, 0, nullptr, emb_prev, 128, nullptr));
+  PRISMA_TRY(dev_alloc(plan_allocs, &x0, (size_t)Bt * P0 * Fp));
+  PRISMA_TRY(dev_alloc(plan_allocs, &s1, (size_t)Bt * P0 * 256));
+  PRISMA_TRY(dev_alloc(plan_allocs, &e1, (size_t)Bt * P0 * 128));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b_prev, (size_t)Bt * P0 * 64));
+  PRISMA_TRY(dev_alloc(plan_allocs, &emb_prev, (size_t)Bt * P0 * 128));
+  PRISMA_TRY(lin("zoe_conv2", btlnck.p, btlnck.rows(), F, w.z_conv2, (int)btlnck.rows(), 0, x0, nullptr, Fp, &btlnck));
+  PRISMA_TRY(lin("zoe_seed0", x0, (long long)Bt * P0, Fp, w.z_seed0, Bt * P0, 2, s1, nullptr, 256, nullptr));
+  PRISMA_TRY(lin("zoe_seed2", s1, (long long)Bt * P0, 256, w.z_seed2, Bt * P0, 5, nullptr, b_prev, 64, nullptr));
+  PRISMA_TRY(lin("zoe_sproj0", x0, (long long)Bt * P0, Fp, w.z_sproj0, Bt * P0, 2, e1, nullptr, 128, nullptr));
+  PRISMA_TRY(lin("zoe_sproj2", e1, (long long)Bt * P0, 128, w.z_sproj2, Bt * P0, 0, nullptr, emb_prev, 128, nullptr));
   int Hp_ = btlnck.H, Wp_ = btlnck.W;
   const int n_attr[4] = {16, 8, 4, 1};
   for (int i = 0; i < 4; ++i) {
@@ -718,38 +719,57 @@ int DepthEngine::build_metric_head(const PMap& btlnck, const PMap* r_maps, const
     const int Hi = xb.H, Wi = xb.W, Pi = Hi * Wi;
     __half *t1 = nullptr, *xa = nullptr, *t2 = nullptr;
     float *emb = nullptr, *Aout = nullptr, *bnew = nullptr;
-    PRISMA_TRY(dev_alloc(plan_allocs, &t1, (size_t)Pi * 128));
-    PRISMA_TRY(dev_alloc(plan_allocs, &xa, (size_t)Pi * 128));
-    PRISMA_TRY(dev_alloc(plan_allocs, &t2, (size_t)Pi * 128));
-    PRISMA_TRY(dev_alloc(plan_allocs, &emb, (size_t)Pi * 128));
-    PRISMA_TRY(dev_alloc(plan_allocs, &Aout, (size_t)Pi * 16));
-    PRISMA_TRY(dev_alloc(plan_allocs, &bnew, (size_t)Pi * 64));
+    PRISMA_TRY(dev_alloc(plan_allocs, &t1, (size_t)Bt * Pi * 128));
+    PRISMA_TRY(dev_alloc(plan_allocs, &xa, (size_t)Bt * Pi * 128));
+    PRISMA_TRY(dev_alloc(plan_allocs, &t2, (size_t)Bt * Pi * 128));
+    PRISMA_TRY(dev_alloc(plan_allocs, &emb, (size_t)Bt * Pi * 128));
+    PRISMA_TRY(dev_alloc(plan_allocs, &Aout, (size_t)Bt * Pi * 16));
+    PRISMA_TRY(dev_alloc(plan_allocs, &bnew, (size_t)Bt * Pi * 64));
     PRISMA_TRY(lin("zoe_proj0", xb.p, xb.rows(), xb.C, w.z_proj0[i], (int)xb.rows(), 2, t1, nullptr, 128, &xb));
-    PRISMA_TRY(lin("zoe_proj2", t1, Pi, 128, w.z_proj2[i], Pi, 0, nullptr, emb, 128, nullptr));
+    PRISMA_TRY(lin("zoe_proj2", t1, (long long)Bt * Pi, 128, w.z_proj2[i], Bt * Pi, 0, nullptr, emb, 128, nullptr));
     { const float* ep_ = emb_prev; const int hp = Hp_, wp = Wp_;
-      add(G_RESAMPLE, "zoe_embed_add", [=](cudaStream_t s) { return zoe_embed_add(emb, Hi, Wi, 128, ep_, hp, wp, xa, s); }); }
-    PRISMA_TRY(lin("zoe_att0", xa, Pi, 128, w.z_att0[i], Pi, 2, t2, nullptr, 128, nullptr));
+      add(G_RESAMPLE, "zoe_embed_add", [=](cudaStream_t s) {
+        for (int f = 0; f < Bt; ++f)
+          PRISMA_TRY(zoe_embed_add(emb + (size_t)f * Pi * 128, Hi, Wi, 128, ep_ + (size_t)f * hp * wp * 128, hp, wp, xa + (size_t)f * Pi * 128, s));
+        return 0;
+      }); }
+    PRISMA_TRY(lin("zoe_att0", xa, (long long)Bt * Pi, 128, w.z_att0[i], Bt * Pi, 2, t2, nullptr, 128, nullptr));
     const int lda = round_up(n_attr[i], 4);
-    PRISMA_TRY(lin("zoe_att2", t2, Pi, 128, w.z_att2[i], Pi, 5, nullptr, Aout, lda, nullptr));
+    PRISMA_TRY(lin("zoe_att2", t2, (long long)Bt * Pi, 128, w.z_att2[i], Bt * Pi, 5, nullptr, Aout, lda, nullptr));
     { const float* bp = b_prev; const int hp = Hp_, wp = Wp_, na = n_attr[i];
-      add(G_RESAMPLE, "zoe_attractor", [=](cudaStream_t s) { return zoe_attractor(Aout, lda, na, bp, hp, wp, Hi, Wi, 64, bnew, s); }); }
+      add(G_RESAMPLE, "zoe_attractor", [=](cudaStream_t s) {
+        for (int f = 0; f < Bt; ++f)
+          PRISMA_TRY(zoe_attractor(Aout + (size_t)f * Pi * lda, lda, na, bp + (size_t)f * hp * wp * 64, hp, wp, Hi, Wi, 64,
+                                   bnew + (size_t)f * Pi * 64, s));
+        return 0;
+      }); }
     b_prev = bnew; emb_prev = emb; Hp_ = Hi; Wp_ = Wi;
   }
   // ---- conditional log-binomial at the network resolution
   const int Pf = hn * wn;
   __half *cat = nullptr, *hid = nullptr;
   float* pt = nullptr;
-  PRISMA_TRY(dev_alloc(plan_allocs, &cat, (size_t)Pf * 192));
-  PRISMA_TRY(dev_alloc(plan_allocs, &hid, (size_t)Pf * 128));
-  PRISMA_TRY(dev_alloc(plan_allocs, &pt, (size_t)Pf * 4));
-  PRISMA_TRY(dev_alloc(plan_allocs, &zoe_metric, (size_t)Pf));
+  PRISMA_TRY(dev_alloc(plan_allocs, &cat, (size_t)Bt * Pf * 192));
+  PRISMA_TRY(dev_alloc(plan_allocs, &hid, (size_t)Bt * Pf * 128));
+  PRISMA_TRY(dev_alloc(plan_allocs, &pt, (size_t)Bt * Pf * 4));
+  PRISMA_TRY(dev_alloc(plan_allocs, &zoe_metric, (size_t)Bt * Pf));
   PRISMA_TRY(dev_alloc(plan_allocs, &zoe_tmp, (size_t)hn * std::max(plan_W_req, wn)));
   { const float* rel = b.depth; const float* ep_ = emb_prev; const int he = Hp_, we = Wp_, h_ = hn, w_ = wn;
-    add(G_RESAMPLE, "zoe_concat", [=](cudaStream_t s) { return zoe_concat(act32, rel, ep_, he, we, h_, w_, cat, s); }); }
-  PRISMA_TRY(lin("zoe_clb0", cat, Pf, 192, w.z_clb0, Pf, 1, hid, nullptr, 128, nullptr));
-  PRISMA_TRY(lin("zoe_clb2", hid, Pf, 128, w.z_clb2, Pf, 5, nullptr, pt, 4, nullptr));
+    add(G_RESAMPLE, "zoe_concat", [=](cudaStream_t s) {
+      for (int f = 0; f < Bt; ++f)
+        PRISMA_TRY(zoe_concat(act32 + (size_t)f * Pf * 32, rel + (size_t)f * Pf, ep_ + (size_t)f * he * we * 128, he, we, h_, w_,
+                              cat + (size_t)f * Pf * 192, s));
+      return 0;
+    }); }
+  PRISMA_TRY(lin("zoe_clb0", cat, (long long)Bt * Pf, 192, w.z_clb0, Bt * Pf, 1, hid, nullptr, 128, nullptr));
+  PRISMA_TRY(lin("zoe_clb2", hid, (long long)Bt * Pf, 128, w.z_clb2, Bt * Pf, 5, nullptr, pt, 4, nullptr));
   { const float* bc = b_prev; const int hc = Hp_, wc = Wp_, h_ = hn, w_ = wn; float* out = zoe_metric;
-    add(G_POST, "zoe_final", [=](cudaStream_t s) { return zoe_final(pt, bc, hc, wc, h_, w_, 64, 0.0212f, 50.0f, out, s); }); }
+    add(G_POST, "zoe_final", [=](cudaStream_t s) {
+      for (int f = 0; f < Bt; ++f)
+        PRISMA_TRY(zoe_final(pt + (size_t)f * Pf * 4, bc + (size_t)f * hc * wc * 64, hc, wc, h_, w_, 64, 0.0212f, 50.0f,
+                             out + (size_t)f * Pf, s));
+      return 0;
+    }); }
   return 0;
 }
 
@@ -816,7 +836,7 @@ int DepthEngine::infer_stream(const uint8_t* rgb, int n, int H, int W, int pass_
                               float* min_out, float* max_out) {
   PRISMA_CHECK(rgb != nullptr && H > 0 && W > 0 && n >= 1, "bad frame batch");
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  const int Bt = metric ? 1 : (pass_frames > 0 ? std::min(pass_frames, 64) : 4);
+  const int Bt = pass_frames > 0 ? std::min(pass_frames, 64) : 4;
   PRISMA_TRY(build_plan(H, W, Bt));
   PRISMA_TRY(ensure_stream_slots(H, W, Bt, depth_out != nullptr));
   if (mm_host_frames < (size_t)n) {

@@ -206,7 +206,7 @@ class MidasEngine(DepthAnythingEngine):
 class ZoeDepthEngine(DepthAnythingEngine):
     """depth_anything --metric indoor|outdoor (bands/depth_anything.py:52-57,106-119): the ZoeDepth metric head on the
     Depth-Anything core, fixed 392x518 network input, PIL-bicubic resize of the metric depth to the frame size.
-    `state_dict` is depth_anything_metric_depth_{indoor,outdoor}.pt as is (core.core.* + the head).  One frame per pass."""
+    `state_dict` is depth_anything_metric_depth_{indoor,outdoor}.pt as is (core.core.* + the head)."""
 
     def __init__(self, state_dict=None, device=0, encoder="vitl"):
         super().__init__("zoe_" + encoder, state_dict, device)

@@ -56,3 +56,15 @@ def test_zoe_720p_matches_oracle(zoe_s):
     ref = ozoe.zoe_infer(sd, img, "vits")
     m, l2 = rel(pred, ref)
     assert m < 1e-3 and l2 < 1e-3, (m, l2)
+
+
+@pytest.mark.gpu
+def test_zoe_batch_equals_single_frames(zoe_s):
+    """The metric head over a stack of frames (GEMMs over all frames' pixel rows) == frame-by-frame."""
+    eng, sd = zoe_s
+    frames = np.stack([synthetic_frame(240, 320, t) for t in range(5)])
+    single = [eng.infer_encoded(f, want_depth=True) for f in frames]
+    rgb, mins, maxs, pred = eng.infer_clip(frames, pass_frames=3, want_depth=True)   # 3 + ragged 2
+    for i, (r1, mn, mx, p1) in enumerate(single):
+        assert np.array_equal(pred[i], p1) and np.array_equal(rgb[i], r1), i
+        assert np.float32(mn) == mins[i] and np.float32(mx) == maxs[i]
