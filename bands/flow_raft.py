@@ -44,11 +44,11 @@ def init_model(args):
     return model
 
 
-def infer(args, prev_frame, curr_frame, want_rgb=False):
+def infer(args, prev_frame, curr_frame, want_rgb=False, reuse_prev=False):
     """(fwd_flow, bwd_flow, fwd_mask, bwd_mask) like the reference's infer (:51-66), plus the engine's result dict;
     frames are HxWx3 u8 RGB at the source resolution (the x scale resize of :100 happens inside the engine)."""
     from prisma_b200.flow import consistency_masks
-    r = model.infer_pair(prev_frame, curr_frame, want_rgb=want_rgb)
+    r = model.infer_pair(prev_frame, curr_frame, want_rgb=want_rgb, reuse_prev=reuse_prev)
     fwd_mask = bwd_mask = None
     if args.output_mask != "" or args.subpath_mask != "":
         fwd_mask, bwd_mask, r["fwd_u16"], r["bwd_u16"] = consistency_masks(r["fwd"], r["bwd"], want_u16=True,
@@ -97,7 +97,8 @@ def process_video(args):
     i = 0
     for i, frame in enumerate(reader):
         if prev is not None:
-            _, _, fwd_mask, bwd_mask, r = infer(args, prev, frame, want_rgb=True)
+            # from the second pair on, `prev` is the previous call's `curr`: its encoder features are still in the engine
+            _, _, fwd_mask, bwd_mask, r = infer(args, prev, frame, want_rgb=True, reuse_prev=(i > 1))
             write_flow(args, r, fwd_video, max_disps, i - 1, fwd_mask, fwd_mask_video, bwd_video, bwd_mask, bwd_mask_video)
         prev = frame
     if prev is not None:

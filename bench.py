@@ -159,8 +159,8 @@ def raft_extras(device, peaks):
     n = 8
     t0 = time.perf_counter()
     dev_ms = 0.0
-    for i in range(n):
-        r = eng.infer_pair(f[i % 2], f[(i + 1) % 2], want_rgb=True)
+    for i in range(n):  # a video loop: every pair's `prev` is the previous pair's `curr` (features reused, same results)
+        r = eng.infer_pair(f[i % 2], f[(i + 1) % 2], want_rgb=True, reuse_prev=True)
         dev_ms += r["ms"]
     e2e_s = time.perf_counter() - t0
     w = eng.work(1080, 1920)

@@ -120,6 +120,13 @@ int prisma_flow_finalize(prisma_engine* e);
 int prisma_flow_infer(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, float scale, int iters,
                       float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd,
                       float* ms_out);
+/* The loop body of process_video in a video loop (bands/flow_raft.py:97-115): with reuse_prev != 0, `prev` is the `curr` of the
+ * previous call -- the engine keeps that frame's fnet / cnet features, so only `curr` is uploaded and encoded (each frame is
+ * encoded once per clip instead of twice; results are identical).  prev may be NULL then.  Falls back to the full pass when
+ * no valid cache exists (first call, or after a change of resolution / scale / iterations).                              */
+int prisma_flow_infer_video(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, float scale, int iters,
+                            int reuse_prev, float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd,
+                            float* max_bwd, float* ms_out);
 /* intermediate tensors of the last pass (tests): "fmap" [2][P][256], "cnet_out" [2P][256], "coords1_iter0",
  * "h_iter0", "coords1"; returns the number of floats written                                                       */
 long long prisma_flow_read_tap(prisma_engine* e, const char* name, float* out, long long capacity);

@@ -59,6 +59,8 @@ SIGNATURES = {
     "prisma_flow_finalize": (C.c_int, [C.c_void_p]),
     "prisma_flow_infer": (C.c_int, [C.c_void_p, c_u8_p, c_u8_p, C.c_int, C.c_int, C.c_float, C.c_int, c_float_p, c_float_p,
                                     c_u8_p, c_u8_p, c_float_p, c_float_p, c_float_p]),
+    "prisma_flow_infer_video": (C.c_int, [C.c_void_p, c_u8_p, c_u8_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, c_float_p,
+                                          c_float_p, c_u8_p, c_u8_p, c_float_p, c_float_p, c_float_p]),
     "prisma_flow_read_tap": (C.c_longlong, [C.c_void_p, C.c_char_p, c_float_p, C.c_longlong]),
     "prisma_flow_work": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, c_double_p]),
     "prisma_debug_gemm": (C.c_int, [C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,

@@ -643,6 +643,14 @@ int prisma_flow_infer(prisma_engine* e, const uint8_t* prev, const uint8_t* curr
   return r ? r->infer(prev, curr, h, w, scale, iters, fwd, bwd, fwd_rgb, bwd_rgb, max_fwd, max_bwd, ms_out) : -1;
   API_GUARD_END
 }
+int prisma_flow_infer_video(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, float scale, int iters,
+                            int reuse_prev, float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd,
+                            float* max_bwd, float* ms_out) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  return r ? r->infer(prev, curr, h, w, scale, iters, fwd, bwd, fwd_rgb, bwd_rgb, max_fwd, max_bwd, ms_out, reuse_prev) : -1;
+  API_GUARD_END
+}
 long long prisma_flow_read_tap(prisma_engine* e, const char* name, float* out, long long capacity) {
   API_GUARD_BEGIN
   RaftEngine* r = as_raft(e);

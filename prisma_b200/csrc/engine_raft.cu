@@ -41,6 +41,7 @@ RaftEngine::~RaftEngine() {
   for (void* p : plan_allocs) cudaFree(p);
   delete corr;
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (graph_cached) cudaGraphExecDestroy(graph_cached);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -198,7 +199,7 @@ int RaftEngine::new_map(RMap* m, int B, int H, int W, int C, int pad) {
   return r_alloc(plan_allocs, &m->p, (size_t)m->rows() * C);
 }
 
-void RaftEngine::add(const char* name, std::function<int(cudaStream_t)> fn) { steps.push_back({0, name, std::move(fn)}); }
+void RaftEngine::add(const char* name, std::function<int(cudaStream_t)> fn) { steps.push_back({cur_mask, name, std::move(fn)}); }
 
 // conv (kh x kw, 'same') on channels [c0, c0+cin) of a padded map; epilogue filled in by the caller
 int RaftEngine::add_conv(const char* name, const RMap& in, int c0, const ConvW& cw, GemmEpilogue ep, int sub) {
@@ -212,7 +213,7 @@ int RaftEngine::add_conv(const char* name, const RMap& in, int c0, const ConvW& 
   GemmLaunch g;
   PRISMA_TRY(gemm_prepare(&g, in.p + c0, in.rows(), cw.cin, in.C, cw.w, round_up(cw.cout, 256), (int)in.rows(), cw.cout,
                           cw.kh * cw.kw, off, ep, num_sms));
-  flops += 2.0 * in.B * (double)(in.H / sub) * (in.W / sub) * cw.kh * cw.kw * cw.cin * cw.cout;
+  if (cur_mask & 1) flops += 2.0 * in.B * (double)(in.H / sub) * (in.W / sub) * cw.kh * cw.kw * cw.cin * cw.cout;
   add(name, [g](cudaStream_t s) { return gemm_run(g, s); });
   return 0;
 }
@@ -237,8 +238,8 @@ int RaftEngine::add_conv_in(const char* name, const RMap& in, const ConvW& cw, i
   return 0;
 }
 
-int RaftEngine::build_encoder(const EncW& e, bool inorm, const __half* stem_cols, RMap* out_map128) {
-  const int B = 2, H2 = Hp_ / 2, W2 = Wp_ / 2;
+int RaftEngine::build_encoder(const EncW& e, bool inorm, const __half* stem_cols, RMap* out_map128, int B) {
+  const int H2 = Hp_ / 2, W2 = Wp_ / 2;
   RMap x;
   PRISMA_TRY(new_map(&x, B, H2, W2, 64, 1));
   const int zero_off[1] = {0};
@@ -260,7 +261,7 @@ int RaftEngine::build_encoder(const EncW& e, bool inorm, const __half* stem_cols
       PRISMA_TRY(gemm_prepare(&g, stem_cols, (long long)B * H2 * W2, 192, 192, e.stem.w, 256, B * H2 * W2, 64, 1, zero_off, ep, num_sms));
       add("stem_gemm", [g](cudaStream_t s) { return gemm_run(g, s); });
     }
-    flops += 2.0 * B * H2 * (double)W2 * 147 * 64;
+    if (cur_mask & 1) flops += 2.0 * B * H2 * (double)W2 * 147 * 64;
   }
   const int dims[3] = {64, 96, 128};
   for (int li = 0; li < 3; ++li)
@@ -319,6 +320,8 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
   taps.clear();
   delete corr; corr = nullptr;
   if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+  if (graph_cached) { cudaGraphExecDestroy(graph_cached); graph_cached = nullptr; }
+  cache_valid = false; cur_mask = 3;
   plan_H = plan_W = 0; flops = 0; iters = iters_;
 
   Hs = (int)nearbyint((double)H * scale); Ws = (int)nearbyint((double)W * scale);
@@ -354,6 +357,8 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
     const uint8_t* img = b.img; uint8_t* rs = b.resized; float* chw = b.chw; __half* cols = b.stem_cols;
     const int Hs_ = Hs, Ws_ = Ws, Hpp = Hp_, Wpp = Wp_;
     int pd[4] = {pads[0], pads[1], pads[2], pads[3]};
+    int pdc[4] = {pads[0], pads[1], pads[2], pads[3]};
+    cur_mask = 1;
     add("raft_preprocess", [=](cudaStream_t s) {
       for (int i = 0; i < 2; ++i)
         PRISMA_TRY(raft_preprocess(img + (size_t)i * H * W * 3, H, W, Hs_, Ws_, pd, rs + (size_t)i * Hs_ * Ws_ * 3,
@@ -361,13 +366,41 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
       return 0;
     });
     add("stem_im2col", [=](cudaStream_t s) { return raft_im2col_stem(chw, 2, Hpp, Wpp, cols, s); });
+    // video pass: slot 0 (prev) <- slot 1 (the previous call's curr) for the encoder outputs; only `curr` is pre-processed
+    cur_mask = 2;
+    {
+      FlowCorr* c = corr; float* cn = b.cnet_out; uint8_t* rsz = rs; const size_t rbytes = (size_t)Hs_ * Ws_ * 3;
+      const size_t cn_n = (size_t)P * 256 * sizeof(float);
+      add("reuse_prev", [=](cudaStream_t s) {
+        const size_t n = (size_t)c->rows_pad * c->C * sizeof(__half);
+        PRISMA_CUDA_OK(cudaMemcpyAsync(c->fmap1, c->fmap1 + (size_t)c->rows_pad * c->C, n, cudaMemcpyDeviceToDevice, s));
+        PRISMA_CUDA_OK(cudaMemcpyAsync(cn, reinterpret_cast<const char*>(cn) + cn_n, cn_n, cudaMemcpyDeviceToDevice, s));
+        PRISMA_CUDA_OK(cudaMemcpyAsync(rsz, rsz + rbytes, rbytes, cudaMemcpyDeviceToDevice, s));
+        return 0;
+      });
+    }
+    add("raft_preprocess", [=](cudaStream_t s) {
+      return raft_preprocess(img + (size_t)H * W * 3, H, W, Hs_, Ws_, pdc, rs + (size_t)Hs_ * Ws_ * 3, chw + (size_t)3 * Hpp * Wpp, s);
+    });
+    add("stem_im2col", [=](cudaStream_t s) {
+      return raft_im2col_stem(chw + (size_t)3 * Hpp * Wpp, 1, Hpp, Wpp, cols + (size_t)(Hpp / 2) * (Wpp / 2) * 192, s);
+    });
+    cur_mask = 3;
   }
   // ---- fnet (instance norm) -> feature maps straight into the correlation operand buffers
-  RMap f128, c128;
-  PRISMA_TRY(build_encoder(w.fnet, true, b.stem_cols, &f128));
+  RMap f128, c128, f128c, c128c;
+  const __half* cols1 = b.stem_cols + (size_t)(Hp_ / 2) * (Wp_ / 2) * 192;  // im2col rows of frame 1 (`curr`)
+  cur_mask = 1;
+  PRISMA_TRY(build_encoder(w.fnet, true, b.stem_cols, &f128, 2));
   { GemmEpilogue ep; ep.row_map = ROW_PAD2TOK; ep.out_img_rows = corr->rows_pad;
     ep.out_f16 = corr->fmap1; ep.out_f16_ld = 256;
     PRISMA_TRY(add_conv("fnet_out", f128, 0, w.fnet.out, ep, 1)); }
+  cur_mask = 2;  // video pass: encode `curr` alone, into slot 1
+  PRISMA_TRY(build_encoder(w.fnet, true, cols1, &f128c, 1));
+  { GemmEpilogue ep; ep.row_map = ROW_PAD2TOK; ep.out_img_rows = corr->rows_pad;
+    ep.out_f16 = corr->fmap1 + (size_t)corr->rows_pad * 256; ep.out_f16_ld = 256;
+    PRISMA_TRY(add_conv("fnet_out", f128c, 0, w.fnet.out, ep, 1)); }
+  cur_mask = 3;
   {  // image pair b uses fmap1 = frame b, fmap2 = the other frame (flow_raft.py:105-106)
     FlowCorr* c = corr;
     add("fmap_swap", [c](cudaStream_t s) {
@@ -380,13 +413,22 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
     flops += c->flops_build;
   }
   // ---- cnet (batch norm folded) -> tanh / relu split into the GRU operand maps
-  PRISMA_TRY(build_encoder(w.cnet, false, b.stem_cols, &c128));
+  cur_mask = 1;
+  PRISMA_TRY(build_encoder(w.cnet, false, b.stem_cols, &c128, 2));
+  cur_mask = 2;
+  PRISMA_TRY(build_encoder(w.cnet, false, cols1, &c128c, 1));
+  cur_mask = 3;
   RMap hx, rhx, corrf, c1, c2, f1, fh, mk;
   PRISMA_TRY(new_map(&hx, B, H8, W8, 384, 2));
   PRISMA_TRY(new_map(&rhx, B, H8, W8, 384, 2));
   PRISMA_TRY(r_alloc(plan_allocs, &b.h_master, (size_t)hx.rows() * 128));
+  cur_mask = 1;
   { GemmEpilogue ep; ep.row_map = ROW_PAD2TOK; ep.out_f32 = b.cnet_out; ep.out_f32_ld = 256;
     PRISMA_TRY(add_conv("cnet_out", c128, 0, w.cnet.out, ep, 1)); }
+  cur_mask = 2;
+  { GemmEpilogue ep; ep.row_map = ROW_PAD2TOK; ep.out_f32 = b.cnet_out + (size_t)P * 256; ep.out_f32_ld = 256;
+    PRISMA_TRY(add_conv("cnet_out", c128c, 0, w.cnet.out, ep, 1)); }
+  cur_mask = 3;
   {
     const float* cn = b.cnet_out; float* hm = b.h_master; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
     float* c0 = b.coords0; float* c1p = b.coords1;
@@ -493,32 +535,38 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
   PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
   plan_H = H; plan_W = W; plan_scale = scale;
   if (use_graph) {
-    PRISMA_TRY(run_direct(stream));
-    PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
-    cudaGraph_t graph = nullptr;
-    PRISMA_CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-    int r = run_direct(stream);
-    cudaError_t e = cudaStreamEndCapture(stream, &graph);
-    if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
-    PRISMA_CUDA_OK(e);
-    PRISMA_CUDA_OK(cudaGraphInstantiate(&graph_exec, graph, 0));
-    cudaGraphDestroy(graph);
+    for (int which = 1; which <= 2; ++which) {
+      PRISMA_TRY(run_direct(stream, which));  // warm: per-kernel attributes are set outside the capture
+      PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+      cudaGraph_t graph = nullptr;
+      PRISMA_CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      int r = run_direct(stream, which);
+      cudaError_t e = cudaStreamEndCapture(stream, &graph);
+      if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+      PRISMA_CUDA_OK(e);
+      PRISMA_CUDA_OK(cudaGraphInstantiate(which == 1 ? &graph_exec : &graph_cached, graph, 0));
+      cudaGraphDestroy(graph);
+    }
   }
   return 0;
 }
 
-int RaftEngine::run_direct(cudaStream_t s) {
-  for (auto& st : steps) PRISMA_TRY(st.fn(s));
+int RaftEngine::run_direct(cudaStream_t s, int which) {
+  for (auto& st : steps)
+    if (st.group & which) PRISMA_TRY(st.fn(s));
   return 0;
 }
 
 int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, float scale, int iters_, float* fwd, float* bwd,
-                      uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd, float* ms_out) {
-  PRISMA_CHECK(prev && curr && H > 0 && W > 0, "bad frame pair");
+                      uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd, float* ms_out, int reuse_prev) {
+  PRISMA_CHECK(curr && (prev || reuse_prev) && H > 0 && W > 0, "bad frame pair");
   PRISMA_CUDA_OK(cudaSetDevice(device));
   PRISMA_TRY(build_plan(H, W, scale, iters_));
+  const int which = (reuse_prev && cache_valid) ? 2 : 1;
+  PRISMA_CHECK(which == 2 || prev != nullptr, "no cached features for the previous frame: pass it");
+  cache_valid = false;
   const size_t fb = (size_t)H * W * 3;
-  PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, prev, fb, cudaMemcpyHostToDevice, stream));
+  if (which == 1) PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, prev, fb, cudaMemcpyHostToDevice, stream));
   PRISMA_CUDA_OK(cudaMemcpyAsync(b.img + fb, curr, fb, cudaMemcpyHostToDevice, stream));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ms_out) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
@@ -526,7 +574,7 @@ int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, fl
     std::vector<cudaEvent_t> ev(steps.size() + 1);
     for (auto& e : ev) cudaEventCreate(&e);
     cudaEventRecord(ev[0], stream);
-    for (size_t i = 0; i < steps.size(); ++i) { PRISMA_TRY(steps[i].fn(stream)); cudaEventRecord(ev[i + 1], stream); }
+    for (size_t i = 0; i < steps.size(); ++i) { if (steps[i].group & which) PRISMA_TRY(steps[i].fn(stream)); cudaEventRecord(ev[i + 1], stream); }
     PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
     std::map<std::string, std::pair<int, float>> agg;
     float tot = 0;
@@ -541,8 +589,8 @@ int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, fl
     std::sort(v.rbegin(), v.rend());
     printf("RAFT step profile (%.3f ms total, ungraphed):\n", tot);
     for (auto& x : v) printf("  %8.3f ms  %5.1f %%  %s\n", x.first, 100.f * x.first / tot, x.second.c_str());
-  } else if (graph_exec) PRISMA_CUDA_OK(cudaGraphLaunch(graph_exec, stream));
-  else PRISMA_TRY(run_direct(stream));
+  } else if (graph_exec) PRISMA_CUDA_OK(cudaGraphLaunch(which == 1 ? graph_exec : graph_cached, stream));
+  else PRISMA_TRY(run_direct(stream, which));
   if (ms_out) cudaEventRecord(e1, stream);
   const size_t n = (size_t)Hs * Ws;
   float mx[2] = {0, 0};
@@ -555,6 +603,7 @@ int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, fl
   if (ms_out) { cudaEventElapsedTime(ms_out, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
   if (max_fwd) *max_fwd = mx[0];
   if (max_bwd) *max_bwd = mx[1];
+  cache_valid = true;  // slot 1 now holds the features of `curr`
   return 0;
 }
 

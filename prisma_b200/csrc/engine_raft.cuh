@@ -33,8 +33,10 @@ class RaftEngine {
   int load_tensor(const std::string& name, const float* data, const int64_t* shape, int ndim);
   int finalize();
   // prev/curr: h*w*3 u8 RGB; fwd/bwd: hs*ws*2 f32 (may be NULL); *_rgb: hs*ws*3 u8 (may be NULL)
+  // reuse_prev: `prev` is the `curr` of the previous call (a video loop): its fnet / cnet features are reused, only `curr`
+  // is uploaded and encoded.  Ignored (full pass) when no valid cache exists.
   int infer(const uint8_t* prev, const uint8_t* curr, int H, int W, float scale, int iters, float* fwd, float* bwd,
-            uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd, float* ms_out);
+            uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd, float* ms_out, int reuse_prev = 0);
   long long read_tap(const std::string& name, float* out, long long capacity);
   int build_plan(int H, int W, float scale, int iters);
   int Hs = 0, Ws = 0, H8 = 0, W8 = 0;
@@ -51,12 +53,14 @@ class RaftEngine {
   void add(const char* name, std::function<int(cudaStream_t)> fn);
   int add_conv(const char* name, const RMap& in, int c0, const ConvW& cw, GemmEpilogue ep, int sub);
   int add_conv_in(const char* name, const RMap& in, const ConvW& cw, int sub, float* dense, float* stats);
-  int build_encoder(const EncW& e, bool inorm, const __half* stem_cols, RMap* out_map128);
-  int run_direct(cudaStream_t s);
+  int build_encoder(const EncW& e, bool inorm, const __half* stem_cols, RMap* out_map128, int B);
+  int run_direct(cudaStream_t s, int which = 1);  // which: 1 = full pass, 2 = video pass reusing the previous frame's features
 
   int device = 0, num_sms = 148;
   cudaStream_t stream = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
+  cudaGraphExec_t graph_exec = nullptr, graph_cached = nullptr;
+  int cur_mask = 3;          // steps carry a mask (Step::group): bit 0 = full pass, bit 1 = video pass
+  bool cache_valid = false;  // slot 1 of the feature buffers holds the last call's `curr`
   bool use_graph = true, finalized = false;
   std::map<std::string, HostTensor> host;
   std::vector<void*> allocs, plan_allocs;

@@ -57,8 +57,9 @@ class RaftFlowEngine:
     def out_size(self, h, w):
         return int(np.rint(h * self.scale)), int(np.rint(w * self.scale))
 
-    def infer_pair(self, prev, curr, want_rgb=False):
-        """prev/curr: HxWx3 u8 RGB -> dict(fwd, bwd [hs,ws,2] f32, max_fwd, max_bwd[, fwd_rgb, bwd_rgb], ms)."""
+    def infer_pair(self, prev, curr, want_rgb=False, reuse_prev=False):
+        """prev/curr: HxWx3 u8 RGB -> dict(fwd, bwd [hs,ws,2] f32, max_fwd, max_bwd[, fwd_rgb, bwd_rgb], ms).
+        reuse_prev: `prev` is the `curr` of the previous call (video loop): its encoder features are reused (same results)."""
         prev, curr = np.ascontiguousarray(prev), np.ascontiguousarray(curr)
         if prev.shape != curr.shape or prev.dtype != np.uint8 or prev.ndim != 3:
             raise PrismaError("expected two HxWx3 uint8 RGB frames of the same size")
@@ -69,8 +70,8 @@ class RaftFlowEngine:
         frgb = np.empty((hs, ws, 3), np.uint8) if want_rgb else None
         brgb = np.empty((hs, ws, 3), np.uint8) if want_rgb else None
         mf, mb, ms = C.c_float(), C.c_float(), C.c_float()
-        check(lib().prisma_flow_infer(self._h, u8ptr(prev), u8ptr(curr), h, w, self.scale, self.iterations, fptr(fwd),
-                                      fptr(bwd), u8ptr(frgb), u8ptr(brgb), C.byref(mf), C.byref(mb), C.byref(ms)))
+        check(lib().prisma_flow_infer_video(self._h, u8ptr(prev), u8ptr(curr), h, w, self.scale, self.iterations, int(reuse_prev),
+                                            fptr(fwd), fptr(bwd), u8ptr(frgb), u8ptr(brgb), C.byref(mf), C.byref(mb), C.byref(ms)))
         return dict(fwd=fwd, bwd=bwd, max_fwd=mf.value, max_bwd=mb.value, fwd_rgb=frgb, bwd_rgb=brgb, ms=ms.value)
 
     def read_tap(self, name, shape):
