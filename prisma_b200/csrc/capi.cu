@@ -662,7 +662,9 @@ int prisma_flow_work(prisma_engine* e, int h, int w, float scale, int iters, dou
   RaftEngine* r = as_raft(e);
   if (!r) return -1;
   PRISMA_TRY(r->build_plan(h, w, scale, iters));
-  out4[0] = r->flops; out4[1] = (double)r->steps.size(); out4[2] = r->Hs; out4[3] = r->Ws;
+  int full_steps = 0;
+  for (const auto& st : r->steps) full_steps += (st.group & 1) ? 1 : 0;  // steps of the full pass (the video pass has fewer)
+  out4[0] = r->flops; out4[1] = (double)full_steps; out4[2] = r->Hs; out4[3] = r->Ws;
   return 0;
   API_GUARD_END
 }
