@@ -216,25 +216,25 @@ int layernorm_f16(const float* x, const float* g, const float* b, __half* y, int
 // ------------------------------------------------------------------------------------------------
 __global__ void k_upsample_ac(const __half* __restrict__ in_all, int ih, int iw, int C, __half* __restrict__ out_all,
                               int oh, int ow, float sy, float sx, int relu_copy, __half* __restrict__ out_relu_all) {
-  const __half* in = in_all + (size_t)blockIdx.y * (ih + 2) * (iw + 2) * C;
-  __half* out = out_all + (size_t)blockIdx.y * (oh + 2) * (ow + 2) * C;
-  __half* out_relu = relu_copy ? out_relu_all + (size_t)blockIdx.y * (oh + 2) * (ow + 2) * C : nullptr;
-  const int c8 = C >> 3;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)oh * ow * c8;
-  if (idx >= total) return;
-  const int c = (int)(idx % c8);
-  const int ox = (int)((idx / c8) % ow);
-  const int oy = (int)(idx / ((long long)c8 * ow));
+  // grid = (ceil(ow * C/8 / 256), oh, batch): the row and the image come from the block index, so the only division per
+  // thread is a 32-bit one by C/8
+  const __half* in = in_all + (size_t)blockIdx.z * (ih + 2) * (iw + 2) * C;
+  __half* out = out_all + (size_t)blockIdx.z * (oh + 2) * (ow + 2) * C;
+  __half* out_relu = relu_copy ? out_relu_all + (size_t)blockIdx.z * (oh + 2) * (ow + 2) * C : nullptr;
+  const unsigned c8 = (unsigned)C >> 3;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)ow * c8) return;
+  const int ox = (int)(t / c8), c = (int)(t - (unsigned)ox * c8);
+  const int oy = blockIdx.y;
   const float fy = sy * oy, fx = sx * ox;
   const int y0 = (int)fy, x0 = (int)fx;
   const int y1 = y0 + (y0 < ih - 1 ? 1 : 0), x1 = x0 + (x0 < iw - 1 ? 1 : 0);
   const float ly1 = fy - y0, ly0 = 1.f - ly1, lx1 = fx - x0, lx0 = 1.f - lx1;
   const int iwp = iw + 2, owp = ow + 2;
-  auto ld = [&](int y, int x) {
-    return *reinterpret_cast<const uint4*>(in + ((size_t)(y + 1) * iwp + x + 1) * C + c * 8);
-  };
-  const uint4 a = ld(y0, x0), b = ld(y0, x1), cc = ld(y1, x0), d = ld(y1, x1);
+  const __half* r0 = in + ((size_t)(y0 + 1) * iwp + 1) * C + c * 8;
+  const __half* r1 = in + ((size_t)(y1 + 1) * iwp + 1) * C + c * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(r0 + (size_t)x0 * C), b = *reinterpret_cast<const uint4*>(r0 + (size_t)x1 * C);
+  const uint4 cc = *reinterpret_cast<const uint4*>(r1 + (size_t)x0 * C), d = *reinterpret_cast<const uint4*>(r1 + (size_t)x1 * C);
   const __half2* ha = reinterpret_cast<const __half2*>(&a);
   const __half2* hb = reinterpret_cast<const __half2*>(&b);
   const __half2* hc = reinterpret_cast<const __half2*>(&cc);
@@ -244,10 +244,10 @@ __global__ void k_upsample_ac(const __half* __restrict__ in_all, int ih, int iw,
   for (int j = 0; j < 4; ++j) {
     const float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]), fc = __half22float2(hc[j]),
                  fd = __half22float2(hd[j]);
-    const float r0 = ly0 * (lx0 * fa.x + lx1 * fb.x) + ly1 * (lx0 * fc.x + lx1 * fd.x);
-    const float r1 = ly0 * (lx0 * fa.y + lx1 * fb.y) + ly1 * (lx0 * fc.y + lx1 * fd.y);
-    o[j] = pack_half2(r0, r1);
-    orl[j] = pack_half2(fmaxf(r0, 0.f), fmaxf(r1, 0.f));
+    const float r0v = ly0 * (lx0 * fa.x + lx1 * fb.x) + ly1 * (lx0 * fc.x + lx1 * fd.x);
+    const float r1v = ly0 * (lx0 * fa.y + lx1 * fb.y) + ly1 * (lx0 * fc.y + lx1 * fd.y);
+    o[j] = pack_half2(r0v, r1v);
+    orl[j] = pack_half2(fmaxf(r0v, 0.f), fmaxf(r1v, 0.f));
   }
   const size_t off = ((size_t)(oy + 1) * owp + ox + 1) * C + c * 8;
   *reinterpret_cast<uint4*>(out + off) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -258,8 +258,8 @@ int upsample_ac_f16(const __half* in, int batch, int ih, int iw, int C, __half* 
   PRISMA_CHECK(C % 8 == 0, "upsample: C must be a multiple of 8");
   const float sy = oh > 1 ? (float)(ih - 1) / (float)(oh - 1) : 0.f;
   const float sx = ow > 1 ? (float)(iw - 1) / (float)(ow - 1) : 0.f;
-  const long long total = (long long)oh * ow * (C / 8);
-  k_upsample_ac<<<dim3((unsigned)((total + 255) / 256), batch), 256, 0, s>>>(
+  const unsigned per_row = (unsigned)ow * (unsigned)(C / 8);
+  k_upsample_ac<<<dim3((per_row + 255) / 256, oh, batch), 256, 0, s>>>(
       in, ih, iw, C, out, oh, ow, sy, sx, out_relu != nullptr, out_relu);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
