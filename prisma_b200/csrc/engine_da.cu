@@ -422,6 +422,7 @@ int DepthEngine::build_plan(int H, int W, int Bt) {
   PRISMA_TRY(dev_alloc(plan_allocs, &b.rgb, (size_t)Bt * H * W * 3));
   PRISMA_TRY(dev_alloc(plan_allocs, &b.mm, 2 * Bt));
   PRISMA_TRY(dev_alloc(plan_allocs, &b.minmax, 2 * Bt));
+  PRISMA_TRY(dev_alloc(plan_allocs, &b.mag, 2));
 
   // pos-embed for this resolution (constant per resolution): computed once, here
   if (!midas) {
@@ -894,9 +895,7 @@ int DepthEngine::infer_image(const uint8_t* rgb, int H, int W, float* depth_out,
   PRISMA_TRY(build_plan(H, W, 1));
   PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, rgb, (size_t)H * W * 3, cudaMemcpyHostToDevice, stream));
   PRISMA_TRY(run_steps(stream));
-  unsigned long long* d_mag = nullptr;
-  PRISMA_CUDA_OK(cudaMalloc(&d_mag, 16));
-  int r = depth_encode_png(b.pred, H, W, metric ? 0 : 1, b.rgb, b.mm, d_mag, b.minmax, num_sms, stream);  // flip = (metric == none)
+  int r = depth_encode_png(b.pred, H, W, metric ? 0 : 1, b.rgb, b.mm, b.mag, b.minmax, num_sms, stream);  // flip = (metric == none)
   float mm[2] = {0, 0};
   if (r == 0) {
     if (depth_out) cudaMemcpyAsync(depth_out, b.pred, (size_t)H * W * 4, cudaMemcpyDeviceToHost, stream);
@@ -905,7 +904,6 @@ int DepthEngine::infer_image(const uint8_t* rgb, int H, int W, float* depth_out,
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) { set_last_error(std::string("infer_image: ") + cudaGetErrorString(e)); r = -2; }
   }
-  cudaFree(d_mag);
   if (min_out) *min_out = mm[0];
   if (max_out) *max_out = mm[1];
   return r;

@@ -38,6 +38,7 @@ struct DaWeights {
 struct DaBuffers {
   uint8_t* img; float* net_in; __half* patches; float* pos; float* x; float* tokens_tap; __half* ln; __half* qkv;
   __half* attn; __half* hid; __half* feat[4]; float* depth; float* pred; uint8_t* rgb; uint32_t* mm; float* minmax;
+  unsigned long long* mag;  // Sobel-magnitude maximum of the PNG encode
 };
 struct Tap { const void* p; int a, b, c; int kind; };  // kind 0: f32 [a][b], 1: padded NHWC f16 (H=a,W=b,C=c), 2: f16 [a][b]
 struct Step { int group; const char* name; std::function<int(cudaStream_t)> fn; };

@@ -90,3 +90,14 @@ def test_streamed_clip_equals_single_frames(vits_engine):
         for i, (r1, mn, mx, p1) in enumerate(single):
             assert np.array_equal(rgb[i], r1) and np.array_equal(pred[i], p1), (pf, i)
             assert np.float32(mn) == mins[i] and np.float32(mx) == maxs[i]
+
+
+def test_still_image_path_matches_video_path_and_png_oracle(vits_engine):
+    """process_image (bands/depth_anything.py:146-174): prisma_depth_infer_image = the same prediction as the video path,
+    encoded with write_depth's PNG variant (bit-exact against the pinned oracle on the engine's own prediction)."""
+    img = synthetic_frame(240, 320, 3)
+    png, dmin, dmax, pred = vits_engine.infer_image(img, want_depth=True)
+    assert np.array_equal(pred, vits_engine.infer(img))
+    ref_png, rmin, rmax = oda.da_write_depth_rgb(pred, True)
+    assert np.array_equal(png, ref_png)
+    assert np.float32(dmin) == np.float32(pred.min()) and np.float32(dmax) == np.float32(pred.max())
