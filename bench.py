@@ -184,7 +184,9 @@ def raft_extras(device, peaks):
                             "ms_per_pass_device": dev_ms / n, "algorithmic_gflop_per_pass": w["flop"] / 1e9,
                             "tflops": w["flop"] / (dev_ms / n * 1e-3) / 1e12, "launches_per_pass": w["launches"]},
         "raft_corr_build": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                            "ms": ms.value, "algorithmic_bytes": work[1], "traffic": None, "peak_source": peaks["src"],
+                            "ms": ms.value, "algorithmic_bytes": work[1],
+                            "traffic": (measured_traffic()[1] or {}).get("corr_level0", {}).get("traffic_bytes_per_launch"),
+                            "traffic_detail": (measured_traffic()[1] or {}).get("corr_level0"), "peak_source": peaks["src"],
                             "note": "4-level fp32 pyramid written once (levels 1-3 by linearity: GEMMs against pooled features)"},
     }
 
