@@ -33,6 +33,10 @@ class VideoReader:
     def get_avg_fps(self):
         return self.fps
 
+    def seek(self, index):
+        """Next frame returned by the iterator = frame `index` (a frame-range worker starts mid-clip)."""
+        self.cap.set(cv2.CAP_PROP_POS_FRAMES, int(index))
+
 
 class VideoWriter:
     def __init__(self, width, height, frame_rate, filename):

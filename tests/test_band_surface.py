@@ -200,3 +200,32 @@ def test_depth_band_metric_path(tmp_path):
     pred = np.load(folder / "frames" / "00000.npy")
     assert pred.shape == (240, 320) and np.float32(pred.min()) == np.float32(mins[0])
     assert sorted(os.listdir(folder / "frames"))[:2] == ["00000.npy", "00000.png"]
+
+
+@pytest.mark.gpu
+def test_depth_band_sharded_over_two_workers_equals_single(tmp_path):
+    """--gpus 2 (both workers on device 0 here): frame-range workers + parent assembly == the single-process run."""
+    import cv2
+    from oracle.frames import synthetic_frame
+    outs = {}
+    for tag, extra in (("one", []), ("two", ["--gpus", "2", "--device-list", "0,0"])):
+        folder = tmp_path / tag
+        folder.mkdir()
+        w = cv2.VideoWriter(str(folder / "rgba.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
+        for t in range(5):
+            w.write(synthetic_frame(240, 320, t)[..., ::-1].copy())
+        w.release()
+        json.dump({"bands": {"rgba": {"url": "rgba.mp4"}}, "width": 320, "height": 240, "frames": 5, "fps": 24.0},
+                  open(folder / "metadata.json", "w"))
+        rc = subprocess.call([sys.executable, os.path.join(ROOT, "bands", "depth_anything.py"), "-i", str(folder), "--encoder", "vits",
+                              "--seeded-weights", "-n", "-d", "frames"] + extra)
+        assert rc == 0
+        outs[tag] = dict(mins=open(folder / "depth_anything_min.csv").read(), maxs=open(folder / "depth_anything_max.csv").read(),
+                         npy=[np.load(folder / "frames" / ("%05d.npy" % i)) for i in range(5)],
+                         meta=json.load(open(folder / "metadata.json"))["bands"]["depth_anything"],
+                         left=sorted(f for f in os.listdir(folder) if "part" in f))
+        cap = cv2.VideoCapture(str(folder / "depth_anything.mp4"))
+        outs[tag]["frames"] = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    assert outs["one"]["mins"] == outs["two"]["mins"] and outs["one"]["maxs"] == outs["two"]["maxs"]
+    assert all(np.array_equal(a, b) for a, b in zip(outs["one"]["npy"], outs["two"]["npy"]))
+    assert outs["one"]["meta"] == outs["two"]["meta"] and outs["two"]["frames"] == 5 and outs["two"]["left"] == []

@@ -54,3 +54,10 @@ def test_flo_writer_and_metadata_roundtrip(tmp_path):
     assert back["bands"]["rgba"]["url"] == "rgba.mp4" and back["bands"]["depth"] == back["bands"]["rgba"]
     assert meta.get_url(str(folder), back, "rgba") == os.path.join(str(folder), "rgba.mp4")
     assert json.load(open(folder / "metadata.json")) == back
+
+
+def test_shard_flag_stripping_and_frame_spec():
+    from bands.common.depth_loop import parse_frames, strip_shard_flags
+    argv = ["-i", "clip", "--gpus", "4", "--encoder", "vits", "--device-list", "0,1,2,3", "-o", "x.mp4", "--seeded-weights", "-n"]
+    assert strip_shard_flags(argv) == ["-i", "clip", "--encoder", "vits", "--seeded-weights", "-n"]
+    assert parse_frames("", 100) == (0, 100) and parse_frames("10:40", 100) == (10, 40) and parse_frames("90:200", 100) == (90, 100)
