@@ -10,6 +10,7 @@ bands/d_anything/util/transform.py:54-166 (same ``get_size``), which pins the si
 
 The fusion blocks and residual units are the same modules as Depth-Anything's (d_anything/blocks.py copies
 midas/blocks.py), so oracle.da._rcu/_fusion -- which ARE pinned against the reference -- are reused.
+Independent cross-check (tests/test_oracle_crosschecks.py): _block() equals torchvision's ViT EncoderBlock.
 """
 import math
 

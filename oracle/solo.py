@@ -7,6 +7,7 @@ This file restates, function by function, the vendored sources it cites (all pat
 three mmcv primitives restated from their documented behaviour: ConvModule = conv -> GroupNorm/BatchNorm -> ReLU,
 imrescale = cv2 INTER_LINEAR to (int(w*s+.5), int(h*s+.5)) with s = min(long/max(h,w), short/min(h,w)),
 imnormalize = f32 BGR->RGB, subtract mean, multiply by 1/std.
+Independent cross-check (tests/test_oracle_crosschecks.py): resnet() and fpn() equal torchvision's ResNet / FPN.
 """
 import cv2
 import numpy as np
