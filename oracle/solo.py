@@ -1,13 +1,20 @@
 """CPU oracle: mask_mmdet band hot path -- SOLOv2 (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
 
-PARITY UNPINNED.  ``mmdet`` is vendored under bands/mmdet but cannot be imported: bands/mmdet/__init__.py:19-27 asserts
-mmcv 1.3.17-1.8.0 and apis/inference.py:5-10 imports mmcv / mmcv.ops / mmcv.runner, and mmcv-full is neither vendored
-nor installed; the model config (models/solov2_r101_fpn_3x_coco.py) is downloaded, not in tree.
-This file restates, function by function, the vendored sources it cites (all paths relative to bands/mmdet/), with the
-three mmcv primitives restated from their documented behaviour: ConvModule = conv -> GroupNorm/BatchNorm -> ReLU,
-imrescale = cv2 INTER_LINEAR to (int(w*s+.5), int(h*s+.5)) with s = min(long/max(h,w), short/min(h,w)),
-imnormalize = f32 BGR->RGB, subtract mean, multiply by 1/std.
-Independent cross-check (tests/test_oracle_crosschecks.py): resnet() and fpn() equal torchvision's ResNet / FPN.
+PARITY PINNED AGAINST THE VENDORED SOURCES, WITH mmcv's PRIMITIVES STUBBED.  ``mmdet`` is vendored under bands/mmdet but
+cannot be imported as a package: bands/mmdet/__init__.py:19-27 asserts mmcv 1.3.17-1.8.0 and mmcv-full is neither vendored
+nor installed; the model config (models/solov2_r101_fpn_3x_coco.py) is downloaded, not in tree (its
+values are taken from upstream mmdet 2.x).  oracle/tools/make_golden.py (golden_solo) therefore loads the vendored files BY
+PATH -- models/backbones/resnet.py, models/utils/res_layer.py, models/necks/fpn.py, models/dense_heads/{base_mask_head,
+solo_head,solov2_head}.py, core/post_processing/matrix_nms.py, generate_coordinate of core/utils/misc.py -- into a stub package
+tree in which only mmcv's primitives are restated from their documented behaviour (ConvModule = conv -> GroupNorm -> ReLU
+with sub-modules conv / gn / activate, build_conv_layer = nn.Conv2d, build_norm_layer = BatchNorm2d named bn<i>, BaseModule
+= nn.Module, auto_fp16 / force_fp32 = identity), loads the seeded state_dict STRICT into the vendored ResNet, FPN and
+SOLOV2Head, and asserts this file equal to them bit for bit (recorded differences 0.0: FPN levels, mask features, kernel
+and class predictions, get_results scores / labels / masks incl. mask_matrix_nms).  Fixture: tests/golden/solo_tiny_head.npz,
+replayed by tests/test_oracle_solo_golden.py.  Still restated without a runnable counterpart: the three mmcv image
+primitives of the test pipeline (imrescale = cv2 INTER_LINEAR to (int(w*s+.5), int(h*s+.5)) with s = min(long/max(h,w),
+short/min(h,w)); imnormalize = f32, subtract mean, multiply by 1/std; impad to a multiple of 32) and the detector glue.
+Independent cross-check (tests/test_oracle_crosschecks.py): resnet() and fpn() also equal torchvision's ResNet / FPN.
 """
 import cv2
 import numpy as np

@@ -257,8 +257,194 @@ def golden_zoe(encoder="vits", H=240, W=320):
     print("[zoe] oracle == reference; wrote fixture")
 
 
+def _load_vendored_solo_head():
+    """Import the VENDORED bands/mmdet SOLOv2 head sources with mmcv absent: mmdet/__init__.py asserts an mmcv version, so the
+    package is never imported; the needed files are loaded by path into a stub package tree, and the three mmcv primitives
+    they use are stubbed from their documented behaviour: ConvModule (conv -> norm -> ReLU, sub-module names conv / gn /
+    activate), BaseModule (= nn.Module), auto_fp16 / force_fp32 (identity decorators).  Everything else that runs -- the head
+    construction, MaskFeatModule / SOLOV2Head forward, get_results, mask_matrix_nms, generate_coordinate -- is the
+    reference's own code."""
+    import importlib.util
+    import types
+    import torch.nn as nn
+    root = os.path.join(REF, "bands", "mmdet")
+
+    def module(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    def from_file(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    class ConvModule(nn.Module):
+        def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, conv_cfg=None, norm_cfg=None,
+                     act_cfg=dict(type="ReLU"), inplace=True, bias="auto"):
+            super().__init__()
+            assert conv_cfg is None
+            if bias == "auto":
+                bias = norm_cfg is None
+            self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding, bias=bias)
+            self.with_norm = norm_cfg is not None
+            if self.with_norm:
+                assert norm_cfg["type"] == "GN"
+                self.gn = nn.GroupNorm(norm_cfg["num_groups"], out_channels)
+            self.activate = nn.ReLU(inplace=inplace) if act_cfg is not None else None
+
+        def forward(self, x):
+            x = self.conv(x)
+            if self.with_norm:
+                x = self.gn(x)
+            return self.activate(x) if self.activate is not None else x
+
+    class BaseModule(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+            self.init_cfg = init_cfg
+
+    ident = lambda *a, **k: (lambda f: f)
+    def build_conv_layer(cfg, *a, **k):  # mmcv.cnn.build_conv_layer(None, ...) = nn.Conv2d
+        assert cfg is None
+        return nn.Conv2d(*a, **k)
+
+    def build_norm_layer(cfg, num_features, postfix=""):  # mmcv.cnn.build_norm_layer(dict(type='BN'), n, postfix) -> ('bn<postfix>', BatchNorm2d)
+        assert cfg["type"] == "BN"
+        return "bn" + str(postfix), nn.BatchNorm2d(num_features)
+
+    class Sequential(BaseModule, nn.Sequential):
+        def __init__(self, *args, init_cfg=None):
+            BaseModule.__init__(self, init_cfg)
+            nn.Sequential.__init__(self, *args)
+
+    mmcv = module("mmcv")
+    mmcv.cnn = module("mmcv.cnn", ConvModule=ConvModule, build_conv_layer=build_conv_layer, build_norm_layer=build_norm_layer,
+                      build_plugin_layer=None)
+    mmcv.runner = module("mmcv.runner", BaseModule=BaseModule, Sequential=Sequential, auto_fp16=ident, force_fp32=ident)
+
+    class InstanceData:  # mmdet/core/data_structures/instance_data.py, reduced to what get_results touches
+        def __init__(self, meta=None):
+            object.__setattr__(self, "_fields", {})
+            for k, v in (meta or {}).items():
+                object.__setattr__(self, k, v)
+
+        def __setattr__(self, k, v):
+            self._fields[k] = v
+            object.__setattr__(self, k, v)
+
+        def keys(self):
+            return list(self._fields)
+
+        def __len__(self):
+            return len(next(iter(self._fields.values()))) if self._fields else 0
+
+    nms = from_file("_ref_matrix_nms", "core/post_processing/matrix_nms.py")
+    src = open(os.path.join(root, "core/utils/misc.py")).read()
+    ns = {"torch": torch}
+    start = src.index("def generate_coordinate(")
+    exec(src[start:], ns)  # generate_coordinate is the last function of the file
+    pkg = module("mmdet")
+    pkg.__path__ = [root]
+    module("mmdet.core", InstanceData=InstanceData, mask_matrix_nms=nms.mask_matrix_nms,
+           multi_apply=lambda f, *a, **k: tuple(map(list, zip(*map(lambda *x: f(*x, **k), *a)))))
+    module("mmdet.core.utils", center_of_mass=None, generate_coordinate=ns["generate_coordinate"])
+    models = module("mmdet.models")
+    models.__path__ = [os.path.join(root, "models")]
+
+    class _Reg:
+        def register_module(self, *a, **k):
+            return lambda c: c
+
+    module("mmdet.models.builder", HEADS=_Reg(), BACKBONES=_Reg(), NECKS=_Reg(), build_loss=lambda cfg: None)
+    module("mmdet.utils")
+    module("mmdet.utils.misc", floordiv=lambda a, b: torch.div(a, b, rounding_mode="floor"))
+    dh = module("mmdet.models.dense_heads")
+    dh.__path__ = [os.path.join(root, "models", "dense_heads")]
+    from_file("mmdet.models.dense_heads.base_mask_head", "models/dense_heads/base_mask_head.py")
+    from_file("mmdet.models.dense_heads.solo_head", "models/dense_heads/solo_head.py")
+    ut = module("mmdet.models.utils")
+    ut.ResLayer = from_file("mmdet.models.utils.res_layer", "models/utils/res_layer.py").ResLayer
+    bb = module("mmdet.models.backbones")
+    bb.__path__ = [os.path.join(root, "models", "backbones")]
+    nk = module("mmdet.models.necks")
+    nk.__path__ = [os.path.join(root, "models", "necks")]
+    resnet = from_file("mmdet.models.backbones.resnet", "models/backbones/resnet.py")
+    fpn = from_file("mmdet.models.necks.fpn", "models/necks/fpn.py")
+    return from_file("mmdet.models.dense_heads.solov2_head", "models/dense_heads/solov2_head.py"), nms, resnet, fpn
+
+
+def golden_solo():
+    """SOLOv2 head + decode of oracle/solo.py against the vendored reference sources (mmcv primitives stubbed)."""
+    from oracle import solo as osolo
+    from oracle.weights import make_solo_weights, SOLO_CONFIGS
+    mod, nms, resnet_mod, fpn_mod = _load_vendored_solo_head()
+    c = SOLO_CONFIGS["tiny"]
+    cfgd = dict(nms_pre=500, score_thr=0.1, mask_thr=0.5, filter_thr=0.05, kernel="gaussian", sigma=2.0, max_per_img=100)
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+
+    head = mod.SOLOV2Head(num_classes=80, in_channels=256, feat_channels=512, stacked_convs=4, strides=[8, 8, 16, 32, 32],
+                          scale_ranges=((1, 96), (48, 192), (96, 384), (192, 768), (384, 2048)), pos_scale=0.2,
+                          num_grids=[40, 36, 24, 16, 12], cls_down_index=0,
+                          mask_feature_head=dict(feat_channels=128, start_level=0, end_level=3, out_channels=256, mask_stride=4,
+                                                 norm_cfg=dict(type="GN", num_groups=32, requires_grad=True)),
+                          loss_mask=None, loss_cls=None, norm_cfg=dict(type="GN", num_groups=32, requires_grad=True),
+                          test_cfg=Cfg(cfgd)).eval()
+    sd = make_solo_weights("tiny", 0)
+    hsd = {k[len("mask_head."):]: v for k, v in sd.items() if k.startswith("mask_head.")}
+    print("[solo] load_state_dict strict:", head.load_state_dict(hsd, strict=True))
+    g = torch.Generator().manual_seed(0)
+    sizes = [(64, 88), (32, 44), (16, 22), (8, 11), (4, 6)]
+    feats = [(torch.randn(1, 256, h, w, generator=g) * 0.3).half().float() for h, w in sizes]  # fp16-representable: stored as fp16
+    meta = dict(img_shape=(250, 333, 3), ori_shape=(240, 320, 3), pad_shape=(256, 352, 3))
+    kernels_ref, cls_ref, mf_ref = head(tuple(feats))
+    res = head.get_results([k.clone() for k in kernels_ref], [t.clone() for t in cls_ref], mf_ref, img_metas=[meta])[0]
+    # --- oracle
+    mf = osolo.mask_feat(sd, feats)
+    kernels, cls = osolo.head(sd, feats, c["num_grids"])
+    e_mf = rel(mf.numpy(), mf_ref.numpy())
+    e_k = max(rel(a.numpy(), b.numpy()) for a, b in zip(kernels, kernels_ref))
+    e_c = max(rel(a.numpy(), b.numpy()) for a, b in zip(cls, cls_ref))
+    print(f"[solo] mask feats err {e_mf:.3e}, kernel preds err {e_k:.3e}, cls preds err {e_c:.3e}")
+    assert e_mf == 0.0 and e_k == 0.0 and e_c == 0.0
+    scores, labels, masks = osolo.get_results(kernels, cls, mf, dict(img_shape=(250, 333), ori_shape=(240, 320)), osolo.TEST_CFG,
+                                              c["strides"], c["num_grids"])
+    print(f"[solo] instances: reference {len(res.scores)}, oracle {len(scores)}")
+    assert len(res.scores) == len(scores) and torch.equal(res.labels, labels)
+    assert torch.allclose(res.scores, scores, rtol=0, atol=0) and torch.equal(res.masks, masks)
+    # --- backbone + neck: the vendored ResNet (depth 50 machinery, one bottleneck per stage = the "tiny" twin) and FPN
+    class TinyResNet(resnet_mod.ResNet):
+        arch_settings = {50: (resnet_mod.Bottleneck, (1, 1, 1, 1))}
+
+    backbone = TinyResNet(depth=50, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1, norm_cfg=dict(type="BN", requires_grad=True),
+                          norm_eval=True, style="pytorch")
+    backbone.eval()  # the vendored ResNet.train() does not return self (resnet.py:648-660)
+    neck = fpn_mod.FPN(in_channels=[256, 512, 1024, 2048], out_channels=256, start_level=0, num_outs=5).eval()
+    print("[solo] backbone strict:", backbone.load_state_dict({k[9:]: v for k, v in sd.items() if k.startswith("backbone.")}, strict=True))
+    print("[solo] neck strict:", neck.load_state_dict({k[5:]: v for k, v in sd.items() if k.startswith("neck.")}, strict=True))
+    x = torch.randn(1, 3, 96, 128, generator=g)
+    fpn_ref = neck(backbone(x))
+    fpn_or = osolo.fpn(sd, osolo.resnet(sd, x, c["layers"]))
+    e_f = max(rel(a.numpy(), b.numpy()) for a, b in zip(fpn_or, fpn_ref))
+    print(f"[solo] ResNet + FPN (5 levels) err {e_f:.3e}")
+    assert e_f == 0.0 and len(fpn_ref) == 5
+    np.savez_compressed(os.path.join(GOLD, "solo_tiny_head.npz"), **{f"feat{i}": f.numpy().astype(np.float16) for i, f in enumerate(feats)},
+                        net_x=x.numpy(), **{f"fpn{i}": f.numpy() for i, f in enumerate(fpn_ref)},
+                        mask_feats_sub=mf_ref.numpy()[:, ::8], cls0=cls_ref[0].numpy(), kernel4=kernels_ref[4].numpy(),
+                        scores=res.scores.numpy(), labels=res.labels.numpy(),
+                        masks=np.packbits(res.masks.numpy(), axis=-1), n=len(res.scores))
+    print("[solo] oracle == vendored SOLOV2Head forward + get_results + mask_matrix_nms; wrote fixture")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sizes", "da_small", "da_vits", "raft", "png", "zoe"]
+    which = sys.argv[1:] or ["sizes", "da_small", "da_vits", "raft", "png", "zoe", "solo"]
+    if "solo" in which:
+        golden_solo()
     if "zoe" in which:
         golden_zoe()
     if "sizes" in which:
