@@ -10,7 +10,10 @@ bands/d_anything/util/transform.py:54-166 (same ``get_size``), which pins the si
 
 The fusion blocks and residual units are the same modules as Depth-Anything's (d_anything/blocks.py copies
 midas/blocks.py), so oracle.da._rcu/_fusion -- which ARE pinned against the reference -- are reused.
-Independent cross-check (tests/test_oracle_crosschecks.py): _block() equals torchvision's ViT EncoderBlock.
+Independent cross-checks: the WHOLE network (patch embed, pos-embed resize, blocks, hooks, project readout, reassemble, fusion,
+head) agrees to < 2e-5 with HuggingFace transformers' DPTForDepthEstimation -- the port of MiDaS v3 DPT-Large behind
+`Intel/dpt-large` -- with the seeded weights mapped onto its parameter names (tests/test_oracle_midas_hf.py); _block() equals
+torchvision's ViT EncoderBlock (tests/test_oracle_crosschecks.py).
 """
 import math
 
