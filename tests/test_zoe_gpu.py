@@ -68,3 +68,17 @@ def test_zoe_batch_equals_single_frames(zoe_s):
     for i, (r1, mn, mx, p1) in enumerate(single):
         assert np.array_equal(pred[i], p1) and np.array_equal(rgb[i], r1), i
         assert np.float32(mn) == mins[i] and np.float32(mx) == maxs[i]
+
+
+@pytest.mark.gpu
+def test_zoe_vitl_matches_oracle():
+    """The configuration the reference actually ships (ViT-L core, 256-channel decoder features) on a 720p frame."""
+    from prisma_b200.depth import ZoeDepthEngine
+    sd = make_zoe_weights("vitl", 0)
+    eng = ZoeDepthEngine(sd, encoder="vitl")
+    img = synthetic_frame(720, 1280, 1)
+    pred = eng.infer(img)
+    eng.close()
+    ref = ozoe.zoe_infer(sd, img, "vitl")
+    m, l2 = rel(pred, ref)
+    assert m < 1e-3 and l2 < 1e-3, (m, l2)
