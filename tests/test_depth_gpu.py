@@ -101,3 +101,17 @@ def test_still_image_path_matches_video_path_and_png_oracle(vits_engine):
     ref_png, rmin, rmax = oda.da_write_depth_rgb(pred, True)
     assert np.array_equal(png, ref_png)
     assert np.float32(dmin) == np.float32(pred.min()) and np.float32(dmax) == np.float32(pred.max())
+
+
+def test_depth_vitl_720p_matches_oracle():
+    """The bench configuration itself (BASELINE configs[1]): ViT-L on a 720p frame, CUDA vs the pinned oracle."""
+    from prisma_b200.depth import DepthAnythingEngine
+    sd = make_da_weights("vitl", 0)
+    eng = DepthAnythingEngine("vitl", sd)
+    img = synthetic_frame(720, 1280, 5)
+    pred = eng.infer(img)
+    eng.close()
+    ref = oda.da_infer(sd, img, "vitl")
+    err = float(np.abs(pred - ref).max() / np.abs(ref).max())
+    l2 = float(np.linalg.norm(pred - ref) / np.linalg.norm(ref))
+    assert err < 1e-3 and l2 < 1e-3, (err, l2)
