@@ -116,20 +116,20 @@ def test_raft_1080p_properties(raft_engine):
 
 @pytest.mark.gpu
 def test_video_pass_reuses_features_bit_identically():
-    """prisma_flow_infer_video(reuse_prev): pair (f1, f2) after pair (f0, f1) with f1's encoder features reused == a fresh
-    pass over (f1, f2); and the fallback to the full pass when nothing is cached."""
+    """prisma_flow_infer_video(reuse_prev): pair (f1, f2) right after pair (f0, f1), with f1's encoder features taken from the
+    engine instead of being recomputed, equals a fresh full pass over (f1, f2) bit for bit; reuse_prev means "prev is the last
+    call's curr" -- after (f1, f2) it makes the engine pair f2 (not the f0 handed in) with the new frame."""
     from prisma_b200.flow import RaftFlowEngine
     from oracle.frames import synthetic_frame
     from oracle.weights import make_raft_weights
     eng = RaftFlowEngine(make_raft_weights(0), iterations=4, scale=0.75)
     f = [synthetic_frame(240, 320, t) for t in range(3)]
-    fresh = eng.infer_pair(f[1], f[2], want_rgb=True)
-    first = eng.infer_pair(f[0], f[1], want_rgb=True, reuse_prev=True)      # cache holds f2, not f0's predecessor... full pass? no:
-    # reuse_prev=True right after (f1, f2) would reuse f2 as prev; so restart the sequence explicitly with a full pass
-    a = eng.infer_pair(f[0], f[1], want_rgb=True)
-    b = eng.infer_pair(f[1], f[2], want_rgb=True, reuse_prev=True)
+    fresh = eng.infer_pair(f[1], f[2], want_rgb=True)                       # full pass; the cache now holds f2
+    misused = eng.infer_pair(f[0], f[1], want_rgb=True, reuse_prev=True)   # -> computes the pair (f2, f1)
+    a = eng.infer_pair(f[0], f[1], want_rgb=True)                          # full pass (f0, f1); the cache now holds f1
+    b = eng.infer_pair(f[1], f[2], want_rgb=True, reuse_prev=True)         # video pass: only f2 is encoded
     for k in ("fwd", "bwd", "fwd_rgb", "bwd_rgb"):
         assert np.array_equal(b[k], fresh[k]), k
     assert b["max_fwd"] == fresh["max_fwd"] and b["max_bwd"] == fresh["max_bwd"]
-    assert not np.array_equal(first["fwd"], a["fwd"])      # the mis-used call really did take f2 as its `prev`
+    assert not np.array_equal(misused["fwd"], a["fwd"])
     eng.close()
