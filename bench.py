@@ -81,7 +81,7 @@ class ClockSampler:
 
 def make_frames(n, h, w, start):
     """Frames [start, start + n) of the synthetic clip (this rank's shard, prisma_b200.shard.frame_range)."""
-    from oracle.frames import synthetic_frame  # seeded synthetic clip shared with the tests (bench infrastructure)
+    from prisma_b200.synthetic import synthetic_frame  # seeded synthetic clip shared with the tests
     base = [synthetic_frame(h, w, (start + t) % 256) for t in range(min(n, 4))]
     # 4 distinct generated frames (the generator is pure numpy and slow), then cheap deterministic variants
     frames = []
@@ -151,7 +151,7 @@ def raft_extras(device, peaks):
     from prisma_b200._lib import check, fptr, lib
     from prisma_b200.flow import RaftFlowEngine
     from prisma_b200.seeded_weights import make_raft_weights
-    from oracle.frames import synthetic_frame
+    from prisma_b200.synthetic import synthetic_frame
     eng = RaftFlowEngine(make_raft_weights(0), device=device, iterations=12, scale=0.75)
     f = [synthetic_frame(1080, 1920, t) for t in range(2)]
     for _ in range(3):
@@ -236,7 +236,7 @@ def mask_extras(device):
     union mask + instance list out (H2D / D2H inside the wall time; `ms` is the device time of the pass)."""
     from prisma_b200.mask import SoloV2Engine
     from prisma_b200.seeded_weights import make_solo_weights
-    from oracle.frames import synthetic_frame
+    from prisma_b200.synthetic import synthetic_frame
     eng = SoloV2Engine(make_solo_weights("r101", 0), device=device)
     f = [synthetic_frame(1080, 1920, t) for t in range(2)]
     for i in range(3):
@@ -257,7 +257,7 @@ def mask_extras(device):
 def run_b200(args, rank, local_rank, world):
     import torch
     from prisma_b200.depth import DepthAnythingEngine
-    from oracle.weights import make_da_weights
+    from prisma_b200.seeded_weights import make_da_weights   # the B200 arm never touches oracle/
 
     dist = None
     if world > 1:

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oracle import da as oda
 from oracle.weights import make_da_weights
-from oracle.frames import synthetic_frame
+from prisma_b200.synthetic import synthetic_frame
 sd = make_da_weights("vitl", 0); f = synthetic_frame(720, 1280, 0)
 for t in (8, 16, 32, 64, 128):
     if t > (os.cpu_count() or 1): break

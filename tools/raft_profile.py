@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["PRISMA_RAFT_PROFILE"] = "1"
 from prisma_b200.flow import RaftFlowEngine
 from prisma_b200.seeded_weights import make_raft_weights
-from oracle.frames import synthetic_frame
+from prisma_b200.synthetic import synthetic_frame
 eng = RaftFlowEngine(make_raft_weights(0), iterations=12)
 f0, f1 = synthetic_frame(1080, 1920, 0), synthetic_frame(1080, 1920, 1)
 eng.infer_pair(f0, f1); eng.infer_pair(f0, f1)

@@ -6,7 +6,7 @@ import os, sys
 sys.path.insert(0, os.getcwd())
 from prisma_b200.mask import SoloV2Engine
 from prisma_b200.seeded_weights import make_solo_weights
-from oracle.frames import synthetic_frame
+from prisma_b200.synthetic import synthetic_frame
 eng = SoloV2Engine(make_solo_weights("r101", 0))
 f = synthetic_frame(1080, 1920, 0)
 eng.infer(f)
