@@ -64,3 +64,19 @@ def test_product_never_imports_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     src = open(os.path.join(dp, f)).read()
                     assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+
+
+def test_bench_b200_arm_never_imports_oracle():
+    """Only bench.py's cpu_baseline / --impl reference legs may touch oracle/ (the measured arm must be the CUDA product)."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    allowed = {"cpu_baseline_frames", "run_reference"}
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        mods = []
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom):
+                mods.append(node.module or "")
+            elif isinstance(node, ast.Import):
+                mods.extend(a.name for a in node.names)
+        bad = [m for m in mods if m.split(".")[0] == "oracle"]
+        assert not bad or fn.name in allowed, (fn.name, bad)
