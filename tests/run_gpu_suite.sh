@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 rc=0
-for f in tests/test_*_gpu.py; do
+for f in tests/test_*_gpu.py tests/test_band_surface.py; do
   echo "=== $f"
   timeout 600 python -m pytest "$f" -q -m gpu -x --tb=short -s 2>&1 | tail -40
   r=${PIPESTATUS[0]}
