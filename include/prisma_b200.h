@@ -85,8 +85,10 @@ int prisma_engine_destroy(prisma_engine* e);
  *      the ConvGRU update block are the next rows of SURVEY.md section 8)                                        */
 /* K11: cv2.resize(frame, fx=fy=scale, INTER_CUBIC) + load_image + InputPadder('sintel').pad + 2*(x/255)-1
  * (flow_raft.py:100-101, common/flow.py:13-16,46-56, raft/raft.py:90-91).  rgb u8 h*w*3 -> resized u8 hs*ws*3
- * (may be NULL) and chw_padded f32 [3][hp][wp]; hs=round(h*scale), hp/wp = hs/ws rounded up to a multiple of 8.  */
-int prisma_flow_preprocess(int device, const uint8_t* rgb, int h, int w, float scale, uint8_t* resized,
+ * (may be NULL) and chw_padded f32 [3][hp][wp]; hs = cvRound(h*scale) (half to even, as cv::resize derives dsize from fx),
+ * hp/wp = hs/ws rounded up to a multiple of 8.  `scale` is a double on purpose: the sampling step is 1/fx on both axes and
+ * host and engine must agree on cvRound(h*scale) (argparse hands the band a Python float = double).                        */
+int prisma_flow_preprocess(int device, const uint8_t* rgb, int h, int w, double scale, uint8_t* resized,
                            float* chw_padded);
 /* K20: process_flow (common/encode.py:113-126): flow f32 h*w*2 -> rgb u8 h*w*3 + max displacement.            */
 int prisma_flow_encode(int device, const float* flow, int h, int w, uint8_t* rgb_out, float* max_disp_out);
@@ -117,21 +119,34 @@ int prisma_flow_finalize(prisma_engine* e);
 /* prev / curr: h*w*3 u8 RGB frames.  scale = args.scale (0.75), iters = args.iterations.  Outputs (each may be NULL):
  * fwd / bwd: hs*ws*2 f32 flows (hs = round(h*scale)), fwd_rgb / bwd_rgb: hs*ws*3 u8 HSV encodings, max_*: the
  * per-frame max displacement written to <band>.csv.  ms_out: device time of the pass (CUDA events), may be NULL.    */
-int prisma_flow_infer(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, float scale, int iters,
+int prisma_flow_infer(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, double scale, int iters,
                       float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd,
                       float* ms_out);
 /* The loop body of process_video in a video loop (bands/flow_raft.py:97-115): with reuse_prev != 0, `prev` is the `curr` of the
  * previous call -- the engine keeps that frame's fnet / cnet features, so only `curr` is uploaded and encoded (each frame is
  * encoded once per clip instead of twice; results are identical).  prev may be NULL then.  Falls back to the full pass when
  * no valid cache exists (first call, or after a change of resolution / scale / iterations).                              */
-int prisma_flow_infer_video(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, float scale, int iters,
+int prisma_flow_infer_video(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, double scale, int iters,
                             int reuse_prev, float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd,
                             float* max_bwd, float* ms_out);
+/* A chunk of process_video's loop (bands/flow_raft.py:97-115): frames = n*h*w*3 u8 RGB, consecutive frames of one clip.
+ * continue_clip == 0: a new clip -- pair j = (frame j, frame j+1), n-1 pairs.  continue_clip != 0: the chunk continues the
+ * clip of the previous call (the engine still holds the features of the frame before frames[0]) -- pair j = (frame j-1,
+ * frame j), n pairs.  Every frame is uploaded and encoded once; the upload of the next frame and the download of the
+ * previous pair overlap the compute (three streams, two staging slots; pinned host buffers from prisma_host_alloc make
+ * the copies asynchronous DMA).  Outputs are pair-major (fwd / bwd: pairs*hs*ws*2 f32, *_rgb: pairs*hs*ws*3 u8, max_*:
+ * pairs floats), each may be NULL; *pairs_out = number of pairs.  Same results as prisma_flow_infer per pair.            */
+int prisma_flow_infer_stream(prisma_engine* e, const uint8_t* frames, int n, int h, int w, double scale, int iters,
+                             int continue_clip, float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd,
+                             float* max_bwd, int* pairs_out);
+/* `reps` passes over the frame pair already resident on the device (video pass when a previous call left its features,
+ * else the full pass), outputs left on the device: ms per pass by CUDA events on the engine stream (bench.py).          */
+int prisma_flow_infer_resident(prisma_engine* e, int h, int w, double scale, int iters, int reps, float* ms_per_pass);
 /* intermediate tensors of the last pass (tests): "fmap" [2][P][256], "cnet_out" [2P][256], "coords1_iter0",
  * "h_iter0", "coords1"; returns the number of floats written                                                       */
 long long prisma_flow_read_tap(prisma_engine* e, const char* name, float* out, long long capacity);
 /* out[0] = algorithmic FLOP of one pass, out[1] = kernel launches per pass, out[2] = hs, out[3] = ws               */
-int prisma_flow_work(prisma_engine* e, int h, int w, float scale, int iters, double* out4);
+int prisma_flow_work(prisma_engine* e, int h, int w, double scale, int iters, double* out4);
 
 /* ---- mask_mmdet band: SOLOv2 (bands/mask_mmdet.py; bands/mmdet/apis/inference.py:99-162 inference_detector) ----
  * prisma_mask_create("r101") + load_tensor x N + finalize replace init_detector(CONFIG, MODEL) (mask_mmdet.py:38-41,

@@ -19,6 +19,31 @@ def raft_preprocess(frame_u8, scale=0.75):
     return torch.from_numpy(np.array(ds)).permute(2, 0, 1).float()
 
 
+def cubic_resize_f64(frame_u8, scale=0.75):
+    """The real-valued result of cv2.resize(frame, None, fx=fy=scale, INTER_CUBIC) before rounding, in float64
+    (cv::resize with dsize empty: sampling step 1/fx on both axes, dsize = cvRound(src*fx); cv::interpolateCubic with
+    A = -0.75; replicate border).  Test infrastructure: used to show that every byte where the CUDA resize differs from
+    cv2 (= IPP's float pipeline in this OpenCV build) is a .5 tie of this value to within float32 rounding (~255 * 2^-23 * a few)."""
+    H, W = frame_u8.shape[:2]
+    h, w = int(np.rint(H * scale)), int(np.rint(W * scale))
+
+    def axis(n_out, n_in):
+        f = (np.arange(n_out, dtype=np.float64) + 0.5) * (1.0 / scale) - 0.5
+        s = np.floor(f).astype(np.int64)
+        x = f - s
+        A = -0.75
+        c0 = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A
+        c1 = ((A + 2) * x - (A + 3)) * x * x + 1
+        c2 = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1
+        c = np.stack([c0, c1, c2, 1.0 - c0 - c1 - c2], -1)
+        return np.clip(s[:, None] + np.arange(-1, 3)[None], 0, n_in - 1), c
+    ix, cx = axis(w, W)
+    iy, cy = axis(h, H)
+    src = frame_u8.astype(np.float64)
+    hb = sum(src[:, ix[:, k], :] * cx[None, :, k, None] for k in range(4))
+    return sum(hb[iy[:, k]] * cy[:, k, None, None] for k in range(4))
+
+
 def input_pad(ht, wd):
     """InputPadder(mode='sintel')._pad (common/flow.py:46-53): [left, right, top, bottom]."""
     pad_ht = (((ht // 8) + 1) * 8 - ht) % 8

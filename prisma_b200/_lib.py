@@ -36,7 +36,7 @@ SIGNATURES = {
     "prisma_depth_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p]),
     "prisma_depth_work": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "prisma_engine_destroy": (C.c_int, [C.c_void_p]),
-    "prisma_flow_preprocess": (C.c_int, [C.c_int, c_u8_p, C.c_int, C.c_int, C.c_float, c_u8_p, c_float_p]),
+    "prisma_flow_preprocess": (C.c_int, [C.c_int, c_u8_p, C.c_int, C.c_int, C.c_double, c_u8_p, c_float_p]),
     "prisma_flow_encode": (C.c_int, [C.c_int, c_float_p, C.c_int, C.c_int, c_u8_p, c_float_p]),
     "prisma_mask_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "prisma_mask_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, c_float_p, c_i64_p, C.c_int]),
@@ -57,12 +57,15 @@ SIGNATURES = {
     "prisma_flow_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "prisma_flow_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, c_float_p, c_i64_p, C.c_int]),
     "prisma_flow_finalize": (C.c_int, [C.c_void_p]),
-    "prisma_flow_infer": (C.c_int, [C.c_void_p, c_u8_p, c_u8_p, C.c_int, C.c_int, C.c_float, C.c_int, c_float_p, c_float_p,
+    "prisma_flow_infer": (C.c_int, [C.c_void_p, c_u8_p, c_u8_p, C.c_int, C.c_int, C.c_double, C.c_int, c_float_p, c_float_p,
                                     c_u8_p, c_u8_p, c_float_p, c_float_p, c_float_p]),
-    "prisma_flow_infer_video": (C.c_int, [C.c_void_p, c_u8_p, c_u8_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, c_float_p,
+    "prisma_flow_infer_video": (C.c_int, [C.c_void_p, c_u8_p, c_u8_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_float_p,
                                           c_float_p, c_u8_p, c_u8_p, c_float_p, c_float_p, c_float_p]),
     "prisma_flow_read_tap": (C.c_longlong, [C.c_void_p, C.c_char_p, c_float_p, C.c_longlong]),
-    "prisma_flow_work": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, c_double_p]),
+    "prisma_flow_work": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p]),
+    "prisma_flow_infer_stream": (C.c_int, [C.c_void_p, c_u8_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_float_p,
+                                           c_float_p, c_u8_p, c_u8_p, c_float_p, c_float_p, C.POINTER(C.c_int)]),
+    "prisma_flow_infer_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_float_p]),
     "prisma_debug_gemm": (C.c_int, [C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, c_float_p]),
     "prisma_debug_conv": (C.c_int, [C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,

@@ -398,11 +398,11 @@ static FlowCorr* as_corr(prisma_engine* e) {
   return e->corr;
 }
 
-int prisma_flow_preprocess(int device, const uint8_t* rgb, int h, int w, float scale, uint8_t* resized, float* chw) {
+int prisma_flow_preprocess(int device, const uint8_t* rgb, int h, int w, double scale, uint8_t* resized, float* chw) {
   API_GUARD_BEGIN
   int sms = 0;
   PRISMA_TRY(device_sms(device, &sms));
-  PRISMA_CHECK(rgb && chw && h > 0 && w > 0 && scale > 0.f, "bad argument");
+  PRISMA_CHECK(rgb && chw && h > 0 && w > 0 && scale > 0.0, "bad argument");
   const int hs = (int)nearbyint((double)h * scale), ws = (int)nearbyint((double)w * scale);
   const int pad_h = (((hs / 8) + 1) * 8 - hs) % 8, pad_w = (((ws / 8) + 1) * 8 - ws) % 8;  // common/flow.py:46-53
   const int pad[4] = {pad_w / 2, pad_w - pad_w / 2, pad_h / 2, pad_h - pad_h / 2};
@@ -413,7 +413,7 @@ int prisma_flow_preprocess(int device, const uint8_t* rgb, int h, int w, float s
   float* dc = sc.alloc<float>((size_t)3 * hp * wp);
   PRISMA_CHECK(di && dr && dc, "cudaMalloc failed");
   PRISMA_CUDA_OK(cudaMemcpy(di, rgb, (size_t)h * w * 3, cudaMemcpyHostToDevice));
-  PRISMA_TRY(raft_preprocess(di, h, w, hs, ws, pad, dr, dc, 0));
+  PRISMA_TRY(raft_preprocess(di, h, w, hs, ws, scale, pad, dr, dc, 0));
   if (resized) PRISMA_CUDA_OK(cudaMemcpy(resized, dr, (size_t)hs * ws * 3, cudaMemcpyDeviceToHost));
   PRISMA_CUDA_OK(cudaMemcpy(chw, dc, (size_t)3 * hp * wp * 4, cudaMemcpyDeviceToHost));
   return 0;
@@ -635,7 +635,7 @@ int prisma_flow_finalize(prisma_engine* e) {
   return r ? r->finalize() : -1;
   API_GUARD_END
 }
-int prisma_flow_infer(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, float scale, int iters,
+int prisma_flow_infer(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, double scale, int iters,
                       float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd,
                       float* ms_out) {
   API_GUARD_BEGIN
@@ -643,12 +643,26 @@ int prisma_flow_infer(prisma_engine* e, const uint8_t* prev, const uint8_t* curr
   return r ? r->infer(prev, curr, h, w, scale, iters, fwd, bwd, fwd_rgb, bwd_rgb, max_fwd, max_bwd, ms_out) : -1;
   API_GUARD_END
 }
-int prisma_flow_infer_video(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, float scale, int iters,
+int prisma_flow_infer_video(prisma_engine* e, const uint8_t* prev, const uint8_t* curr, int h, int w, double scale, int iters,
                             int reuse_prev, float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd,
                             float* max_bwd, float* ms_out) {
   API_GUARD_BEGIN
   RaftEngine* r = as_raft(e);
   return r ? r->infer(prev, curr, h, w, scale, iters, fwd, bwd, fwd_rgb, bwd_rgb, max_fwd, max_bwd, ms_out, reuse_prev) : -1;
+  API_GUARD_END
+}
+int prisma_flow_infer_stream(prisma_engine* e, const uint8_t* frames, int n, int h, int w, double scale, int iters,
+                             int continue_clip, float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd,
+                             float* max_bwd, int* pairs_out) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  return r ? r->infer_stream(frames, n, h, w, scale, iters, continue_clip, fwd, bwd, fwd_rgb, bwd_rgb, max_fwd, max_bwd, pairs_out) : -1;
+  API_GUARD_END
+}
+int prisma_flow_infer_resident(prisma_engine* e, int h, int w, double scale, int iters, int reps, float* ms_per_pass) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  return r ? r->time_resident(h, w, scale, iters, reps, ms_per_pass) : -1;
   API_GUARD_END
 }
 long long prisma_flow_read_tap(prisma_engine* e, const char* name, float* out, long long capacity) {
@@ -657,7 +671,7 @@ long long prisma_flow_read_tap(prisma_engine* e, const char* name, float* out, l
   return r ? r->read_tap(name, out, capacity) : -1;
   API_GUARD_END
 }
-int prisma_flow_work(prisma_engine* e, int h, int w, float scale, int iters, double* out4) {
+int prisma_flow_work(prisma_engine* e, int h, int w, double scale, int iters, double* out4) {
   API_GUARD_BEGIN
   RaftEngine* r = as_raft(e);
   if (!r) return -1;

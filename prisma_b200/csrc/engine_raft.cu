@@ -42,6 +42,13 @@ RaftEngine::~RaftEngine() {
   delete corr;
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (graph_cached) cudaGraphExecDestroy(graph_cached);
+  for (auto& sl : slot) {
+    cudaFree(sl.in); cudaFree(sl.flow); cudaFree(sl.rgb); cudaFree(sl.mx);
+    for (cudaEvent_t e : {sl.loaded, sl.consumed, sl.done, sl.drained}) if (e) cudaEventDestroy(e);
+  }
+  if (mx_host) cudaFreeHost(mx_host);
+  if (s_in) cudaStreamDestroy(s_in);
+  if (s_out) cudaStreamDestroy(s_out);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -308,7 +315,7 @@ int RaftEngine::build_encoder(const EncW& e, bool inorm, const __half* stem_cols
   return 0;
 }
 
-int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
+int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   PRISMA_CHECK(finalized, "weights not finalized");
   PRISMA_CHECK(iters_ >= 1 && iters_ <= 64, "iterations must be in [1,64]");
   if (plan_H == H && plan_W == W && plan_scale == scale && iters == iters_) return 0;
@@ -324,7 +331,7 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
   cache_valid = false; cur_mask = 3;
   plan_H = plan_W = 0; flops = 0; iters = iters_;
 
-  Hs = (int)nearbyint((double)H * scale); Ws = (int)nearbyint((double)W * scale);
+  Hs = (int)nearbyint((double)H * scale); Ws = (int)nearbyint((double)W * scale);  // cv::resize: dsize = cvRound(src * fx)
   const int pad_h = (((Hs / 8) + 1) * 8 - Hs) % 8, pad_w = (((Ws / 8) + 1) * 8 - Ws) % 8;  // common/flow.py:46-53
   pads[0] = pad_w / 2; pads[1] = pad_w - pad_w / 2; pads[2] = pad_h / 2; pads[3] = pad_h - pad_h / 2;
   Hp_ = Hs + pad_h; Wp_ = Ws + pad_w;
@@ -356,12 +363,13 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
   {
     const uint8_t* img = b.img; uint8_t* rs = b.resized; float* chw = b.chw; __half* cols = b.stem_cols;
     const int Hs_ = Hs, Ws_ = Ws, Hpp = Hp_, Wpp = Wp_;
+    const double fx = scale;
     int pd[4] = {pads[0], pads[1], pads[2], pads[3]};
     int pdc[4] = {pads[0], pads[1], pads[2], pads[3]};
     cur_mask = 1;
     add("raft_preprocess", [=](cudaStream_t s) {
       for (int i = 0; i < 2; ++i)
-        PRISMA_TRY(raft_preprocess(img + (size_t)i * H * W * 3, H, W, Hs_, Ws_, pd, rs + (size_t)i * Hs_ * Ws_ * 3,
+        PRISMA_TRY(raft_preprocess(img + (size_t)i * H * W * 3, H, W, Hs_, Ws_, fx, pd, rs + (size_t)i * Hs_ * Ws_ * 3,
                                    chw + (size_t)i * 3 * Hpp * Wpp, s));
       return 0;
     });
@@ -380,7 +388,7 @@ int RaftEngine::build_plan(int H, int W, float scale, int iters_) {
       });
     }
     add("raft_preprocess", [=](cudaStream_t s) {
-      return raft_preprocess(img + (size_t)H * W * 3, H, W, Hs_, Ws_, pdc, rs + (size_t)Hs_ * Ws_ * 3, chw + (size_t)3 * Hpp * Wpp, s);
+      return raft_preprocess(img + (size_t)H * W * 3, H, W, Hs_, Ws_, fx, pdc, rs + (size_t)Hs_ * Ws_ * 3, chw + (size_t)3 * Hpp * Wpp, s);
     });
     add("stem_im2col", [=](cudaStream_t s) {
       return raft_im2col_stem(chw + (size_t)3 * Hpp * Wpp, 1, Hpp, Wpp, cols + (size_t)(Hpp / 2) * (Wpp / 2) * 192, s);
@@ -557,7 +565,7 @@ int RaftEngine::run_direct(cudaStream_t s, int which) {
   return 0;
 }
 
-int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, float scale, int iters_, float* fwd, float* bwd,
+int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, double scale, int iters_, float* fwd, float* bwd,
                       uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd, float* ms_out, int reuse_prev) {
   PRISMA_CHECK(curr && (prev || reuse_prev) && H > 0 && W > 0, "bad frame pair");
   PRISMA_CUDA_OK(cudaSetDevice(device));
@@ -604,6 +612,122 @@ int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, fl
   if (max_fwd) *max_fwd = mx[0];
   if (max_bwd) *max_bwd = mx[1];
   cache_valid = true;  // slot 1 now holds the features of `curr`
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------ streamed clip path
+int RaftEngine::ensure_stream_slots(int H, int W) {
+  if (!s_in) {
+    PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (auto& sl : slot)
+      for (cudaEvent_t* e : {&sl.loaded, &sl.consumed, &sl.done, &sl.drained})
+        PRISMA_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  const size_t in_bytes = (size_t)H * W * 3, out_px = (size_t)Hs * Ws;
+  if (slot_in_bytes == in_bytes && slot_out_px == out_px) return 0;
+  PRISMA_CUDA_OK(cudaDeviceSynchronize());
+  for (auto& sl : slot) {
+    cudaFree(sl.in); cudaFree(sl.flow); cudaFree(sl.rgb); cudaFree(sl.mx);
+    sl.in = sl.rgb = nullptr; sl.flow = sl.mx = nullptr;
+    PRISMA_CUDA_OK(cudaMalloc(&sl.in, in_bytes));
+    PRISMA_CUDA_OK(cudaMalloc(&sl.flow, 2 * out_px * 2 * sizeof(float)));
+    PRISMA_CUDA_OK(cudaMalloc(&sl.rgb, 2 * out_px * 3));
+    PRISMA_CUDA_OK(cudaMalloc(&sl.mx, 8));
+  }
+  slot_in_bytes = in_bytes; slot_out_px = out_px;
+  return 0;
+}
+
+// process_video's loop (bands/flow_raft.py:97-115) over a chunk: every frame is uploaded once and encoded once (video
+// pass); s_in uploads frame j+1 into a staging slot while `stream` replays the graph of pair j and s_out drains pair j-1.
+int RaftEngine::infer_stream(const uint8_t* frames, int n, int H, int W, double scale, int iters_, int continue_clip,
+                             float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd,
+                             int* pairs_out) {
+  PRISMA_CHECK(frames != nullptr && H > 0 && W > 0 && n >= 1, "bad frame chunk");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  const bool same_plan = (plan_H == H && plan_W == W && plan_scale == scale && iters == iters_);
+  PRISMA_TRY(build_plan(H, W, scale, iters_));
+  PRISMA_TRY(ensure_stream_slots(H, W));
+  const bool cont = continue_clip && cache_valid && same_plan;
+  const int pairs = cont ? n : n - 1;
+  if (pairs_out) *pairs_out = pairs;
+  if (pairs <= 0) {  // a single frame without history: nothing to pair it with; keep it as the next chunk's `prev`?  No:
+    cache_valid = false;  // its features are not computed by any pass, so the next chunk must start a new clip
+    return 0;
+  }
+  if (mx_host_pairs < (size_t)pairs) {
+    if (mx_host) cudaFreeHost(mx_host);
+    mx_host = nullptr; mx_host_pairs = 0;
+    PRISMA_CUDA_OK(cudaMallocHost(&mx_host, (size_t)pairs * 8));
+    mx_host_pairs = pairs;
+  }
+  const size_t fb = (size_t)H * W * 3, px = (size_t)Hs * Ws;
+  const int first_curr = cont ? 0 : 1;  // index of the `curr` frame of pair 0
+  cache_valid = false;
+  if (!cont) PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, frames, fb, cudaMemcpyHostToDevice, stream));  // `prev` of pair 0
+  auto drain = [&](int j) -> int {
+    StreamSlot& sl = slot[j & 1];
+    PRISMA_CUDA_OK(cudaStreamWaitEvent(s_out, sl.done, 0));
+    if (fwd) PRISMA_CUDA_OK(cudaMemcpyAsync(fwd + (size_t)j * px * 2, sl.flow, px * 8, cudaMemcpyDeviceToHost, s_out));
+    if (bwd) PRISMA_CUDA_OK(cudaMemcpyAsync(bwd + (size_t)j * px * 2, sl.flow + px * 2, px * 8, cudaMemcpyDeviceToHost, s_out));
+    if (fwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(fwd_rgb + (size_t)j * px * 3, sl.rgb, px * 3, cudaMemcpyDeviceToHost, s_out));
+    if (bwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(bwd_rgb + (size_t)j * px * 3, sl.rgb + px * 3, px * 3, cudaMemcpyDeviceToHost, s_out));
+    PRISMA_CUDA_OK(cudaMemcpyAsync(mx_host + (size_t)j * 2, sl.mx, 8, cudaMemcpyDeviceToHost, s_out));
+    PRISMA_CUDA_OK(cudaEventRecord(sl.drained, s_out));
+    return 0;
+  };
+  for (int j = 0; j < pairs; ++j) {
+    StreamSlot& sl = slot[j & 1];
+    const int which = (j == 0 && !cont) ? 1 : 2;
+    if (j >= 2) PRISMA_CUDA_OK(cudaStreamWaitEvent(s_in, sl.consumed, 0));
+    PRISMA_CUDA_OK(cudaMemcpyAsync(sl.in, frames + (size_t)(first_curr + j) * fb, fb, cudaMemcpyHostToDevice, s_in));
+    PRISMA_CUDA_OK(cudaEventRecord(sl.loaded, s_in));
+    PRISMA_CUDA_OK(cudaStreamWaitEvent(stream, sl.loaded, 0));
+    PRISMA_CUDA_OK(cudaMemcpyAsync(b.img + fb, sl.in, fb, cudaMemcpyDeviceToDevice, stream));
+    PRISMA_CUDA_OK(cudaEventRecord(sl.consumed, stream));
+    if (graph_exec) PRISMA_CUDA_OK(cudaGraphLaunch(which == 1 ? graph_exec : graph_cached, stream));
+    else PRISMA_TRY(run_direct(stream, which));
+    if (j >= 2) PRISMA_CUDA_OK(cudaStreamWaitEvent(stream, sl.drained, 0));
+    if (fwd || bwd) PRISMA_CUDA_OK(cudaMemcpyAsync(sl.flow, b.flow_up, 2 * px * 8, cudaMemcpyDeviceToDevice, stream));
+    if (fwd_rgb || bwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(sl.rgb, b.rgb, 2 * px * 3, cudaMemcpyDeviceToDevice, stream));
+    PRISMA_CUDA_OK(cudaMemcpyAsync(sl.mx, b.maxd, 8, cudaMemcpyDeviceToDevice, stream));
+    PRISMA_CUDA_OK(cudaEventRecord(sl.done, stream));
+    if (j >= 1) PRISMA_TRY(drain(j - 1));
+  }
+  PRISMA_TRY(drain(pairs - 1));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(s_out));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  for (int j = 0; j < pairs; ++j) {
+    if (max_fwd) max_fwd[j] = mx_host[2 * j];
+    if (max_bwd) max_bwd[j] = mx_host[2 * j + 1];
+  }
+  cache_valid = true;  // slot 1 of the feature buffers holds the last frame of the chunk
+  return 0;
+}
+
+int RaftEngine::time_resident(int H, int W, double scale, int iters_, int reps, float* ms_per_pass) {
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_TRY(build_plan(H, W, scale, iters_));
+  const int which = cache_valid ? 2 : 1;
+  auto once = [&]() -> int {
+    if (graph_exec) PRISMA_CUDA_OK(cudaGraphLaunch(which == 1 ? graph_exec : graph_cached, stream));
+    else PRISMA_TRY(run_direct(stream, which));
+    return 0;
+  };
+  cudaEvent_t e0, e1;
+  PRISMA_CUDA_OK(cudaEventCreate(&e0));
+  PRISMA_CUDA_OK(cudaEventCreate(&e1));
+  PRISMA_TRY(once());
+  PRISMA_CUDA_OK(cudaEventRecord(e0, stream));
+  for (int i = 0; i < std::max(reps, 1); ++i) PRISMA_TRY(once());
+  PRISMA_CUDA_OK(cudaEventRecord(e1, stream));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  float t = 0;
+  PRISMA_CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (ms_per_pass) *ms_per_pass = t / std::max(reps, 1);
   return 0;
 }
 

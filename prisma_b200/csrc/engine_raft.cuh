@@ -35,10 +35,18 @@ class RaftEngine {
   // prev/curr: h*w*3 u8 RGB; fwd/bwd: hs*ws*2 f32 (may be NULL); *_rgb: hs*ws*3 u8 (may be NULL)
   // reuse_prev: `prev` is the `curr` of the previous call (a video loop): its fnet / cnet features are reused, only `curr`
   // is uploaded and encoded.  Ignored (full pass) when no valid cache exists.
-  int infer(const uint8_t* prev, const uint8_t* curr, int H, int W, float scale, int iters, float* fwd, float* bwd,
+  int infer(const uint8_t* prev, const uint8_t* curr, int H, int W, double scale, int iters, float* fwd, float* bwd,
             uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd, float* ms_out, int reuse_prev = 0);
+  // The video loop over a chunk of n frames (flow_raft.py:97-115): pair j = (frame j, frame j+1), or with continue_clip
+  // (the engine still holds the features of the frame before frames[0]) pair j = (frame j-1, frame j).  Three streams:
+  // the upload of frame j+1 and the download of pair j-1 overlap the graph of pair j.  Outputs are pair-major, each may
+  // be NULL.  *pairs_out = number of pairs produced.
+  int infer_stream(const uint8_t* frames, int n, int H, int W, double scale, int iters, int continue_clip, float* fwd,
+                   float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd, int* pairs_out);
+  // `reps` video passes over the frames already on the device (kernel-only leg of bench.py): ms per pass, CUDA events
+  int time_resident(int H, int W, double scale, int iters, int reps, float* ms_per_pass);
   long long read_tap(const std::string& name, float* out, long long capacity);
-  int build_plan(int H, int W, float scale, int iters);
+  int build_plan(int H, int W, double scale, int iters);
   int Hs = 0, Ws = 0, H8 = 0, W8 = 0;
   double flops = 0;
   std::vector<Step> steps;
@@ -70,7 +78,15 @@ class RaftEngine {
   std::map<std::string, Tap> taps;
   float *dense_a = nullptr, *dense_b = nullptr, *stats_a = nullptr, *stats_b = nullptr, *in_part = nullptr;
   int plan_H = 0, plan_W = 0, iters = 0, Hp_ = 0, Wp_ = 0, pads[4] = {0, 0, 0, 0};
-  float plan_scale = 0.f;
+  double plan_scale = 0.0;
+  struct StreamSlot {
+    uint8_t* in = nullptr; float* flow = nullptr; uint8_t* rgb = nullptr; float* mx = nullptr;
+    cudaEvent_t loaded = nullptr, consumed = nullptr, done = nullptr, drained = nullptr;
+  } slot[2];
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  float* mx_host = nullptr;  // pinned, 2 floats per pair
+  size_t mx_host_pairs = 0, slot_in_bytes = 0, slot_out_px = 0;
+  int ensure_stream_slots(int H, int W);
 };
 
 }  // namespace prisma

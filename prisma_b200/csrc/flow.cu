@@ -9,58 +9,56 @@
 namespace prisma {
 
 // ------------------------------------------------------------------------------------------------
-// K11: cv2.resize(frame_u8, fx=fy=scale, INTER_CUBIC) -> load_image -> InputPadder('sintel') replicate pad ->
+// K11: cv2.resize(frame_u8, None, fx=scale, fy=scale, INTER_CUBIC) -> load_image -> InputPadder('sintel') replicate pad ->
 // 2*(x/255)-1 (bands/flow_raft.py:100-101, common/flow.py:13-16,46-56, raft/raft.py:90-91).
-// OpenCV's 8-bit cubic path: tap weights (float, A=-0.75, 4th = 1-sum) scaled by 2048 and truncated to short,
-// horizontal pass in int32, vertical pass in fp32 (taps * 2^-22), round-to-nearest-even, saturate.  (The weight
-// truncation and the float vertical pass were established empirically against cv2 4.13: <0.1% of the pixels differ,
-// by 1 LSB -- OpenCV's SIMD rounding is build-dependent, see tests/test_flow_gpu.py.)
+// With dsize empty cv::resize keeps inv_scale = fx on BOTH axes (sampling step 1/fx, dsize = cvRound(src*fx)); it does
+// not re-derive the step from the rounded output size.  The 8-bit INTER_CUBIC of the reference's OpenCV build (4.13 with
+// IPP, which is what `pip install opencv-python` ships and what runs by default) is IPP's float pipeline: the a = -0.75
+// cubic evaluated in float32 and rounded half-to-even -- NOT OpenCV's own fixed-point path (2048-scaled short weights),
+// which round 1 emulated.  Measured against cv2 on random-noise frames: this kernel differs on ~1e-5 of the bytes, all of
+// them exact .5 ties of the real-valued result, where IPP's (closed, CPU-dispatched) operation order decides the
+// rounding; tests/test_flow_gpu.py asserts exactly that (every differing byte is a tie, by 1 LSB).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cv_cubic_coeffs_i(float x, int* c) {
+__device__ __forceinline__ void cv_cubic_coeffs_f(float x, float* f) {  // cv::interpolateCubic, A = -0.75, float32
   const float A = -0.75f;
   const float x1 = __fadd_rn(x, 1.f);
-  float f[4];
   f[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), __fmul_rn(5.f, A)), x1), __fmul_rn(8.f, A)), x1), __fmul_rn(4.f, A));
   f[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.f), x), __fadd_rn(A, 3.f)), x), x), 1.f);
   const float y = __fsub_rn(1.f, x);
   f[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.f), y), __fadd_rn(A, 3.f)), y), y), 1.f);
   f[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, f[0]), f[1]), f[2]);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) c[k] = (int)__fmul_rn(f[k], 2048.f);  // truncation toward zero
 }
 
+// one thread per output pixel (3 channels); the 4x4x3 source taps come through L1/L2 (each source byte is reused by
+// ~(4/step)^2 = 9 outputs), the output row is written coalesced
 __global__ void k_raft_resize(const uint8_t* __restrict__ img, int H, int W, uint8_t* __restrict__ out, int h, int w,
-                              double scale) {
+                              double step) {
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   const int oy = blockIdx.y;
   if (ox >= w) return;
-  float fx = (float)__dsub_rn(__dmul_rn((double)ox + 0.5, scale), 0.5);
-  int sx = (int)floorf(fx);
-  fx = __fsub_rn(fx, (float)sx);
-  float fy = (float)__dsub_rn(__dmul_rn((double)oy + 0.5, scale), 0.5);
-  int sy = (int)floorf(fy);
-  fy = __fsub_rn(fy, (float)sy);
-  int cx[4], cy[4];
-  cv_cubic_coeffs_i(fx, cx);
-  cv_cubic_coeffs_i(fy, cy);
-  const float vscale = 1.0f / (2048.f * 2048.f);
-  float acc[3];
+  const double px = __dsub_rn(__dmul_rn((double)ox + 0.5, step), 0.5), py = __dsub_rn(__dmul_rn((double)oy + 0.5, step), 0.5);
+  const int sx = (int)floor(px), sy = (int)floor(py);
+  float cx[4], cy[4];
+  cv_cubic_coeffs_f((float)(px - (double)sx), cx);
+  cv_cubic_coeffs_f((float)(py - (double)sy), cy);
+  int xi[4];
 #pragma unroll
-  for (int j = 3; j >= 0; --j) {  // OpenCV's vertical SIMD pass nests from the last tap outwards
-    const int yy = min(max(sy - 1 + j, 0), H - 1);
-    const uint8_t* row = img + (size_t)yy * W * 3;
-    const float b = __fmul_rn((float)cy[j], vscale);
+  for (int k = 0; k < 4; ++k) xi[k] = min(max(sx - 1 + k, 0), W - 1) * 3;
+  float hrow[4][3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      int hs = 0;
+  for (int j = 0; j < 4; ++j) {
+    const uint8_t* row = img + (size_t)min(max(sy - 1 + j, 0), H - 1) * W * 3;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) hs += (int)row[min(max(sx - 1 + k, 0), W - 1) * 3 + c] * cx[k];
-      const float t = __fmul_rn((float)hs, b);
-      acc[c] = (j == 3) ? t : __fadd_rn(t, acc[c]);
-    }
+    for (int c = 0; c < 3; ++c)
+      hrow[j][c] = __fadd_rn(__fadd_rn(__fmul_rn((float)row[xi[0] + c], cx[0]), __fmul_rn((float)row[xi[1] + c], cx[1])),
+                             __fadd_rn(__fmul_rn((float)row[xi[2] + c], cx[2]), __fmul_rn((float)row[xi[3] + c], cx[3])));
   }
 #pragma unroll
-  for (int c = 0; c < 3; ++c) out[((size_t)oy * w + ox) * 3 + c] = (uint8_t)min(max(__float2int_rn(acc[c]), 0), 255);
+  for (int c = 0; c < 3; ++c) {
+    const float v = __fadd_rn(__fadd_rn(__fmul_rn(hrow[0][c], cy[0]), __fmul_rn(hrow[1][c], cy[1])),
+                              __fadd_rn(__fmul_rn(hrow[2][c], cy[2]), __fmul_rn(hrow[3][c], cy[3])));
+    out[((size_t)oy * w + ox) * 3 + c] = (uint8_t)min(max(__float2int_rn(v), 0), 255);
+  }
 }
 
 __global__ void k_raft_pad_norm(const uint8_t* __restrict__ rs, int h, int w, float* __restrict__ chw, int hp, int wp,
@@ -76,11 +74,11 @@ __global__ void k_raft_pad_norm(const uint8_t* __restrict__ rs, int h, int w, fl
   }
 }
 
-int raft_preprocess(const uint8_t* img, int H, int W, int h, int w, const int pad[4], uint8_t* resized, float* chw,
+int raft_preprocess(const uint8_t* img, int H, int W, int h, int w, double fx, const int pad[4], uint8_t* resized, float* chw,
                     cudaStream_t s) {
-  const double scale = 1.0 / ((double)w / (double)W);  // the band passes fx=fy; cv2 derives dsize = round(src*fx)
+  const double step = 1.0 / fx;  // cv::resize with dsize empty: inv_scale_x = inv_scale_y = fx, sampling step 1 / fx
   dim3 block(128), grid(ceil_div(w, 128), h);
-  k_raft_resize<<<grid, block, 0, s>>>(img, H, W, resized, h, w, scale);
+  k_raft_resize<<<grid, block, 0, s>>>(img, H, W, resized, h, w, step);
   const int hp = h + pad[2] + pad[3], wp = w + pad[0] + pad[1];
   dim3 grid2(ceil_div(wp, 128), hp);
   k_raft_pad_norm<<<grid2, block, 0, s>>>(resized, h, w, chw, hp, wp, pad[0], pad[2]);

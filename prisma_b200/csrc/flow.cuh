@@ -7,7 +7,7 @@
 
 namespace prisma {
 
-int raft_preprocess(const uint8_t* img, int H, int W, int h, int w, const int pad[4], uint8_t* resized, float* chw,
+int raft_preprocess(const uint8_t* img, int H, int W, int h, int w, double fx, const int pad[4], uint8_t* resized, float* chw,
                     cudaStream_t s);
 int flow_encode(const float* flow, int H, int W, uint8_t* rgb, uint32_t* mm_scratch, float* max_out, int num_sms,
                 cudaStream_t s);

@@ -55,7 +55,47 @@ class RaftFlowEngine:
         check(l.prisma_flow_finalize(self._h))
 
     def out_size(self, h, w):
-        return int(np.rint(h * self.scale)), int(np.rint(w * self.scale))
+        """cv::resize(None, fx, fy): dsize = cvRound(src * fx) in double, half to even -- the same expression the engine
+        evaluates (the C ABI takes `scale` as a double for exactly this reason)."""
+        return int(np.rint(h * float(self.scale))), int(np.rint(w * float(self.scale)))
+
+    def infer_clip(self, frames, continue_clip=False, want_flow=True, want_rgb=True, out=None):
+        """A chunk of the band's video loop: frames [n,H,W,3] u8 (consecutive frames of one clip) -> dict of pair-major
+        arrays: fwd, bwd [p,hs,ws,2] f32, fwd_rgb, bwd_rgb [p,hs,ws,3] u8, max_fwd, max_bwd [p].  p = n-1 for a new clip,
+        n when the chunk continues the previous call's clip.  Uploads / downloads overlap the compute
+        (prisma_flow_infer_stream); `frames` and the arrays in `out` (same keys) may be pinned_empty() buffers."""
+        x = frames if isinstance(frames, np.ndarray) else np.stack(frames)
+        if x.dtype != np.uint8 or x.ndim != 4 or x.shape[3] != 3 or not x.flags.c_contiguous:
+            raise PrismaError("expected a C-contiguous [n,H,W,3] uint8 RGB array")
+        n, h, w = x.shape[:3]
+        hs, ws = self.out_size(h, w)
+        out = out or {}
+        cap = n  # upper bound of the number of pairs
+
+        def buf(key, shape, dtype, want):
+            if not want:
+                return None
+            a = out.get(key)
+            if a is None:
+                a = np.empty((cap,) + shape, dtype)
+            if a.shape[0] < cap or a.shape[1:] != shape or a.dtype != dtype or not a.flags.c_contiguous:
+                raise PrismaError(f"output buffer '{key}' has the wrong shape / dtype")
+            return a
+        fwd, bwd = buf("fwd", (hs, ws, 2), np.float32, want_flow), buf("bwd", (hs, ws, 2), np.float32, want_flow)
+        frgb, brgb = buf("fwd_rgb", (hs, ws, 3), np.uint8, want_rgb), buf("bwd_rgb", (hs, ws, 3), np.uint8, want_rgb)
+        mf, mb = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        pairs = C.c_int()
+        check(lib().prisma_flow_infer_stream(self._h, u8ptr(x), n, h, w, float(self.scale), self.iterations, int(continue_clip),
+                                             fptr(fwd), fptr(bwd), u8ptr(frgb), u8ptr(brgb), fptr(mf), fptr(mb), C.byref(pairs)))
+        p = pairs.value
+        cut = lambda a: None if a is None else a[:p]
+        return dict(pairs=p, fwd=cut(fwd), bwd=cut(bwd), fwd_rgb=cut(frgb), bwd_rgb=cut(brgb), max_fwd=mf[:p], max_bwd=mb[:p])
+
+    def time_resident(self, h, w, reps):
+        """ms per pass over the frame pair resident on the device (CUDA events inside the C ABI)."""
+        ms = C.c_float()
+        check(lib().prisma_flow_infer_resident(self._h, h, w, float(self.scale), self.iterations, reps, C.byref(ms)))
+        return ms.value
 
     def infer_pair(self, prev, curr, want_rgb=False, reuse_prev=False):
         """prev/curr: HxWx3 u8 RGB -> dict(fwd, bwd [hs,ws,2] f32, max_fwd, max_bwd[, fwd_rgb, bwd_rgb], ms).
