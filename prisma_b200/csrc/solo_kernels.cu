@@ -11,16 +11,24 @@ namespace prisma {
 // ------------------------------------------------------------------------------------------------
 // Test pipeline (_base_/datasets/coco_instance.py:16-32): mmcv.imrescale = cv2.resize(INTER_LINEAR) on u8, then
 // imnormalize (f32: subtract mean, multiply by 1/std), then zero pad to a multiple of 32.
-// cv2's 8-bit bilinear is fixed point: tap weights rounded to 1/2048, horizontal pass in int, vertical pass
-// (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+// cv2's 8-bit bilinear (cv::resize INTER_LINEAR on CV_8U; IPP is not used for it) is fixed point: tap weights rounded
+// to 1/2048, horizontal pass in int, vertical pass (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+// The two axes treat the image border differently: the horizontal tap table clamps the position AND zeroes the
+// fraction outside [0, W-1] (resize.cpp: "if (sx < 0) fx = 0, sx = 0"), the vertical pass keeps the fraction and only
+// clips the two row indices -- so in border rows both truncating products are applied to the same row.  Byte-equal to
+// cv2 4.13 for up- and down-scaling (tests/test_mask_gpu.py, np.array_equal).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cv_linear_tap(int d, double scale, int ssize, int* s0, int* a0, int* a1) {
+__device__ __forceinline__ void cv_linear_tap(int d, double scale, int ssize, bool clamp_fraction, int* s0, int* s1, int* a0,
+                                              int* a1) {
   float f = (float)((d + 0.5) * scale - 0.5);
   int s = (int)floorf(f);
   f -= (float)s;
-  if (s < 0) { f = 0.f; s = 0; }
-  if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
-  *s0 = s;
+  if (clamp_fraction) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+  }
+  *s0 = min(max(s, 0), ssize - 1);
+  *s1 = min(max(s + 1, 0), ssize - 1);
   *a0 = (int)(short)__float2int_rn((1.f - f) * 2048.f);
   *a1 = (int)(short)__float2int_rn(f * 2048.f);
 }
@@ -35,10 +43,9 @@ __global__ void k_solo_preprocess(const uint8_t* __restrict__ img, int H, int W,
     for (int c = 0; c < 3; ++c) out[((size_t)c * hp + y) * wp + x] = 0.f;
     return;
   }
-  int sx, ax0, ax1, sy, by0, by1;
-  cv_linear_tap(x, scale_x, W, &sx, &ax0, &ax1);
-  cv_linear_tap(y, scale_y, H, &sy, &by0, &by1);
-  const int sx1 = min(sx + 1, W - 1), sy1 = min(sy + 1, H - 1);
+  int sx, sx1, ax0, ax1, sy, sy1, by0, by1;
+  cv_linear_tap(x, scale_x, W, true, &sx, &sx1, &ax0, &ax1);
+  cv_linear_tap(y, scale_y, H, false, &sy, &sy1, &by0, &by1);
   const uint8_t* r0 = img + (size_t)sy * W * 3;
   const uint8_t* r1 = img + (size_t)sy1 * W * 3;
 #pragma unroll

@@ -52,6 +52,15 @@ def test_depth_band_matches_reference_fixture(golden_dir, vits_engine, tag):
     assert report["net_depth"][0] <= TOL and report["net_depth"][1] <= TOL
     assert report["prediction"][0] <= TOL and report["prediction"][1] <= TOL
     assert max(report["minmax"]) <= TOL
+    # the u8 heat frame (what the band writes into <band>.mp4) against the REFERENCE's frame.  heat_to_rgb has slope
+    # 6 * 0.65 per unit of normalised depth (encode.py:13-33), so an error e of the normalised depth moves a channel by at
+    # most 255 * 3.9 * e before the truncating cast: the frame may differ by the propagated float error only.  Measured on
+    # B200: max 1 LSB, mean 0.06 LSB (normalised-depth error ~1e-3: the seeded weights span only 0.236..0.280).
+    span = float(g["dmax"]) - float(g["dmin"])
+    e_norm = (float(np.abs(pred - g["prediction"]).max()) + 2 * max(report["minmax"]) * float(g["dmax"])) / span
+    lsb_bound = int(np.ceil(255 * 3.9 * e_norm)) + 1
+    assert report["rgb_max_lsb"] <= min(lsb_bound, 3), (report["rgb_max_lsb"], lsb_bound)
+    assert report["rgb_mean_lsb"] <= 0.15, report["rgb_mean_lsb"]
 
 
 def test_depth_band_matches_oracle_720p(vits_engine):
@@ -115,3 +124,25 @@ def test_depth_vitl_720p_matches_oracle():
     err = float(np.abs(pred - ref).max() / np.abs(ref).max())
     l2 = float(np.linalg.norm(pred - ref) / np.linalg.norm(ref))
     assert err < 1e-3 and l2 < 1e-3, (err, l2)
+
+
+def test_depth_vitl_1080p_matches_oracle():
+    """BASELINE metric frame size (1080p, the bench headline): ViT-L end to end, CUDA vs the pinned oracle, floats and
+    the encoded u8 frame (same propagated-error bound as the fixture test)."""
+    from prisma_b200.depth import DepthAnythingEngine
+    sd = make_da_weights("vitl", 0)
+    eng = DepthAnythingEngine("vitl", sd)
+    img = synthetic_frame(1080, 1920, 7)
+    rgb, dmin, dmax, pred = eng.infer_encoded(img, want_depth=True)
+    eng.close()
+    ref = oda.da_infer(sd, img, "vitl")
+    err = float(np.abs(pred - ref).max() / np.abs(ref).max())
+    l2 = float(np.linalg.norm(pred - ref) / np.linalg.norm(ref))
+    ref_rgb, rmin, rmax = oda.da_encode(ref)
+    lsb = np.abs(rgb.astype(int) - ref_rgb.astype(int))
+    e_norm = (float(np.abs(pred - ref).max()) + abs(dmin - rmin) + abs(dmax - rmax)) / (rmax - rmin)
+    print("1080p vitl: max-rel %.3e rel-L2 %.3e; u8 frame max %d LSB mean %.3f LSB (bound %d)" %
+          (err, l2, lsb.max(), lsb.mean(), int(np.ceil(255 * 3.9 * e_norm)) + 1))
+    assert err < 1e-3 and l2 < 1e-3, (err, l2)
+    assert abs(dmin - rmin) <= 1e-3 * abs(rmax) and abs(dmax - rmax) <= 1e-3 * abs(rmax)
+    assert lsb.max() <= int(np.ceil(255 * 3.9 * e_norm)) + 1 and lsb.mean() <= 0.25, (lsb.max(), lsb.mean())

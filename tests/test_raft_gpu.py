@@ -92,6 +92,48 @@ def test_raft_720p_matches_oracle(raft_engine):
     assert r[0][0] <= 1e-3 and r[1][0] <= 1e-3
 
 
+def test_raft_1080p_matches_oracle(raft_engine):
+    """BASELINE configs[2] itself: 1080p x0.75 -> 810x1440 (padded 816x1440), 12 iterations, forward AND backward flow,
+    CUDA vs the CPU oracle (bit-equal to the reference RAFT) on the same resized frames.  Tolerance = north_star's 1e-3
+    relative to the largest displacement.  The oracle needs ~30-60 s of host CPU at this size."""
+    H, W = 1080, 1920
+    f0, f1 = synthetic_frame(H, W, 0), synthetic_frame(H, W, 1)
+    out = raft_engine.infer_pair(f0, f1)
+    hs, ws = raft_engine.out_size(H, W)
+    assert (hs, ws) == (810, 1440)
+    rs = raft_engine.read_tap("resized", (2, hs, ws, 3)).astype(np.uint8)
+    _, lo, up = _oracle(f0, f1, rs[0], rs[1], 12)
+    fwd_ref = up[0].permute(1, 2, 0).numpy()
+    bwd_ref = up[1].permute(1, 2, 0).numpy()
+    r = (_rel(out["fwd"], fwd_ref), _rel(out["bwd"], bwd_ref))
+    print("1080p raft: fwd", r[0], "bwd", r[1], "max|flow|", float(np.abs(fwd_ref).max()), "ms", out["ms"])
+    assert r[0][0] <= 1e-3 and r[1][0] <= 1e-3, r
+    assert abs(out["max_fwd"] - float(np.sqrt((fwd_ref ** 2).sum(-1)).max())) <= 1e-3 * float(np.abs(fwd_ref).max())
+
+
+def test_raft_streamed_clip_equals_pairwise_calls():
+    """prisma_flow_infer_stream over a clip (new clip, then a continued chunk; pinned and pageable buffers) == the
+    per-pair calls of the band's loop, bit for bit (flows, HSV frames, max displacements)."""
+    from prisma_b200.depth import pinned_empty
+    from prisma_b200.flow import RaftFlowEngine
+    eng = RaftFlowEngine(make_raft_weights(0), iterations=3, scale=0.75)
+    frames = np.stack([synthetic_frame(240, 320, t) for t in range(6)])
+    ref = [eng.infer_pair(frames[i], frames[i + 1], want_rgb=True) for i in range(5)]
+    pin = pinned_empty(frames.shape, np.uint8)
+    pin[...] = frames
+    a = eng.infer_clip(pin[:4])                          # new clip: pairs (0,1) (1,2) (2,3)
+    b = eng.infer_clip(frames[4:], continue_clip=True)   # continues: pairs (3,4) (4,5)
+    assert a["pairs"] == 3 and b["pairs"] == 2
+    got = [(a, j) for j in range(3)] + [(b, j) for j in range(2)]
+    for i, (o, j) in enumerate(got):
+        for k in ("fwd", "bwd", "fwd_rgb", "bwd_rgb"):
+            assert np.array_equal(o[k][j], ref[i][k]), (i, k)
+        assert o["max_fwd"][j] == np.float32(ref[i]["max_fwd"]) and o["max_bwd"][j] == np.float32(ref[i]["max_bwd"])
+    c = eng.infer_clip(frames[:1])                       # a lone frame of a new clip: nothing to pair
+    assert c["pairs"] == 0
+    eng.close()
+
+
 def test_raft_1080p_properties(raft_engine):
     """BASELINE config-3 size (1080p x0.75, 12 iterations): size-independent properties.
     (a) swapping the two frames swaps forward and backward flow bit for bit (the two directions are independent
