@@ -147,6 +147,15 @@ int prisma_flow_infer_resident(prisma_engine* e, int h, int w, double scale, int
 long long prisma_flow_read_tap(prisma_engine* e, const char* name, float* out, long long capacity);
 /* out[0] = algorithmic FLOP of one pass, out[1] = kernel launches per pass, out[2] = hs, out[3] = ws               */
 int prisma_flow_work(prisma_engine* e, int h, int w, double scale, int iters, double* out4);
+/* out[0] / out[1] = algorithmic FLOP of the tcgen05 conv GEMMs of the full / the video pass (encoders, update block, heads;
+ * without the correlation build), out[2] / out[3] = FLOP / algorithmic bytes of one correlation-pyramid build (both
+ * directions; bytes = fp32 pyramid written once + fp16 features read once, raft/corr.py:13-27), out[4] / out[5] = kernel
+ * steps of the full / video pass, out[6], out[7] = hs, ws                                                              */
+int prisma_flow_work_detail(prisma_engine* e, int h, int w, double scale, int iters, double* out8);
+/* CUDA-event times (ms) of one pass by kernel group, for bench.py's roofline block (video pass when the previous call left
+ * its features): out[0] pre-process, [1] conv GEMMs, [2] correlation build, [3] correlation lookup, [4] InstanceNorm,
+ * [5] other pointwise kernels, [6] convex up-sampling + HSV encode, [7] total                                            */
+int prisma_flow_profile(prisma_engine* e, int h, int w, double scale, int iters, float* out8);
 
 /* ---- mask_mmdet band: SOLOv2 (bands/mask_mmdet.py; bands/mmdet/apis/inference.py:99-162 inference_detector) ----
  * prisma_mask_create("r101") + load_tensor x N + finalize replace init_detector(CONFIG, MODEL) (mask_mmdet.py:38-41,

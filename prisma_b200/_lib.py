@@ -63,6 +63,8 @@ SIGNATURES = {
                                           c_float_p, c_u8_p, c_u8_p, c_float_p, c_float_p, c_float_p]),
     "prisma_flow_read_tap": (C.c_longlong, [C.c_void_p, C.c_char_p, c_float_p, C.c_longlong]),
     "prisma_flow_work": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p]),
+    "prisma_flow_work_detail": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, c_double_p]),
+    "prisma_flow_profile": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, c_float_p]),
     "prisma_flow_infer_stream": (C.c_int, [C.c_void_p, c_u8_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_float_p,
                                            c_float_p, c_u8_p, c_u8_p, c_float_p, c_float_p, C.POINTER(C.c_int)]),
     "prisma_flow_infer_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_float_p]),

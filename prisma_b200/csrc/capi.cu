@@ -682,6 +682,27 @@ int prisma_flow_work(prisma_engine* e, int h, int w, double scale, int iters, do
   return 0;
   API_GUARD_END
 }
+int prisma_flow_work_detail(prisma_engine* e, int h, int w, double scale, int iters, double* out8) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  if (!r) return -1;
+  PRISMA_CHECK(out8 != nullptr, "null argument");
+  PRISMA_TRY(r->build_plan(h, w, scale, iters));
+  int full_steps = 0, video_steps = 0;
+  for (const auto& st : r->steps) { full_steps += (st.group & 1) ? 1 : 0; video_steps += (st.group & 2) ? 1 : 0; }
+  out8[0] = r->flops_conv; out8[1] = r->flops_conv_video;
+  out8[2] = r->corr_block()->flops_build; out8[3] = r->corr_block()->bytes_build;
+  out8[4] = full_steps; out8[5] = video_steps; out8[6] = r->Hs; out8[7] = r->Ws;
+  return 0;
+  API_GUARD_END
+}
+int prisma_flow_profile(prisma_engine* e, int h, int w, double scale, int iters, float* out8) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  PRISMA_CHECK(out8 != nullptr, "null argument");
+  return r ? r->profile(h, w, scale, iters, out8) : -1;
+  API_GUARD_END
+}
 
 #pragma GCC visibility pop
 }  // extern "C"

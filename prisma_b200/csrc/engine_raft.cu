@@ -220,7 +220,9 @@ int RaftEngine::add_conv(const char* name, const RMap& in, int c0, const ConvW& 
   GemmLaunch g;
   PRISMA_TRY(gemm_prepare(&g, in.p + c0, in.rows(), cw.cin, in.C, cw.w, round_up(cw.cout, 256), (int)in.rows(), cw.cout,
                           cw.kh * cw.kw, off, ep, num_sms));
-  if (cur_mask & 1) flops += 2.0 * in.B * (double)(in.H / sub) * (in.W / sub) * cw.kh * cw.kw * cw.cin * cw.cout;
+  { const double f = 2.0 * in.B * (double)(in.H / sub) * (in.W / sub) * cw.kh * cw.kw * cw.cin * cw.cout;
+    if (cur_mask & 1) { flops += f; flops_conv += f; }
+    if (cur_mask & 2) flops_conv_video += f; }
   add(name, [g](cudaStream_t s) { return gemm_run(g, s); });
   return 0;
 }
@@ -268,7 +270,9 @@ int RaftEngine::build_encoder(const EncW& e, bool inorm, const __half* stem_cols
       PRISMA_TRY(gemm_prepare(&g, stem_cols, (long long)B * H2 * W2, 192, 192, e.stem.w, 256, B * H2 * W2, 64, 1, zero_off, ep, num_sms));
       add("stem_gemm", [g](cudaStream_t s) { return gemm_run(g, s); });
     }
-    if (cur_mask & 1) flops += 2.0 * B * H2 * (double)W2 * 147 * 64;
+    { const double f = 2.0 * B * H2 * (double)W2 * 147 * 64;
+      if (cur_mask & 1) { flops += f; flops_conv += f; }
+      if (cur_mask & 2) flops_conv_video += f; }
   }
   const int dims[3] = {64, 96, 128};
   for (int li = 0; li < 3; ++li)
@@ -329,7 +333,7 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
   if (graph_cached) { cudaGraphExecDestroy(graph_cached); graph_cached = nullptr; }
   cache_valid = false; cur_mask = 3;
-  plan_H = plan_W = 0; flops = 0; iters = iters_;
+  plan_H = plan_W = 0; flops = flops_conv = flops_conv_video = 0; iters = iters_;
 
   Hs = (int)nearbyint((double)H * scale); Ws = (int)nearbyint((double)W * scale);  // cv::resize: dsize = cvRound(src * fx)
   const int pad_h = (((Hs / 8) + 1) * 8 - Hs) % 8, pad_w = (((Ws / 8) + 1) * 8 - Ws) % 8;  // common/flow.py:46-53
@@ -477,7 +481,7 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
       GemmLaunch g;
       const int zoff[1] = {0};
       PRISMA_TRY(gemm_prepare(&g, f1_cols, 2LL * H8 * W8, 256, 256, w.convf1_gemm_w, 256, 2 * H8 * W8, 128, 1, zoff, ep, num_sms));
-      flops += 2.0 * 2 * H8 * (double)W8 * 98.0 * 128;
+      { const double f = 2.0 * 2 * H8 * (double)W8 * 98.0 * 128; flops += f; flops_conv += f; flops_conv_video += f; }
       add("convf1_gemm", [g](cudaStream_t s) { return gemm_run(g, s); });
     }
     { GemmEpilogue ep; ep.act = 2; ep.out_f16 = c2.p + 192; ep.out_f16_ld = 256;      // convf2 3x3 128 -> 64
@@ -728,6 +732,45 @@ int RaftEngine::time_resident(int H, int W, double scale, int iters_, int reps, 
   PRISMA_CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (ms_per_pass) *ms_per_pass = t / std::max(reps, 1);
+  return 0;
+}
+
+// Per-group CUDA-event times of one ungraphed pass (video pass when the previous frame's features are cached):
+// out[0] pre-process + stem im2col, [1] conv GEMMs (encoders + update block + heads), [2] correlation build,
+// [3] correlation lookup, [4] InstanceNorm, [5] other pointwise (GRU gates, coords, flow im2col, ...), [6] convex
+// up-sampling + HSV encode, [7] total.
+int RaftEngine::profile(int H, int W, double scale, int iters_, float* out8) {
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  PRISMA_TRY(build_plan(H, W, scale, iters_));
+  const int which = cache_valid ? 2 : 1;
+  for (int i = 0; i < 8; ++i) out8[i] = 0.f;
+  std::vector<cudaEvent_t> ev(steps.size() + 1);
+  for (auto& e : ev) PRISMA_CUDA_OK(cudaEventCreate(&e));
+  PRISMA_TRY(run_direct(stream, which));  // warm
+  PRISMA_CUDA_OK(cudaEventRecord(ev[0], stream));
+  for (size_t i = 0; i < steps.size(); ++i) {
+    if (steps[i].group & which) PRISMA_TRY(steps[i].fn(stream));
+    PRISMA_CUDA_OK(cudaEventRecord(ev[i + 1], stream));
+  }
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  for (size_t i = 0; i < steps.size(); ++i) {
+    if (!(steps[i].group & which)) continue;
+    float t = 0;
+    cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+    const std::string n = steps[i].name;
+    int g = 5;
+    if (n == "raft_preprocess" || n == "stem_im2col" || n == "reuse_prev" || n == "fmap_swap") g = 0;
+    else if (n == "corr_build") g = 2;
+    else if (n == "corr_lookup") g = 3;
+    else if (n.rfind("instnorm", 0) == 0) g = 4;
+    else if (n == "convex_upsample" || n == "flow_encode") g = 6;
+    else if (n == "convf1_im2col") g = 5;
+    else if (n == "stem_gemm" || n == "convf1_gemm" || n.rfind("res_", 0) == 0 || n.rfind("conv", 0) == 0 || n == "fnet_out" ||
+             n == "cnet_out" || n == "motion_conv" || n.rfind("gru_zr", 0) == 0 || n == "gru_q" || n.rfind("flow_head", 0) == 0 ||
+             n.rfind("mask_head", 0) == 0) g = 1;
+    out8[g] += t; out8[7] += t;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
   return 0;
 }
 

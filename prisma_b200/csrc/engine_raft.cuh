@@ -48,7 +48,10 @@ class RaftEngine {
   long long read_tap(const std::string& name, float* out, long long capacity);
   int build_plan(int H, int W, double scale, int iters);
   int Hs = 0, Ws = 0, H8 = 0, W8 = 0;
-  double flops = 0;
+  double flops = 0, flops_conv = 0, flops_conv_video = 0;  // full pass total; conv GEMMs of the full / video pass
+  int profile(int H, int W, double scale, int iters, float* out8);
+  bool has_cache() const { return cache_valid; }
+  FlowCorr* corr_block() { return corr; }
   std::vector<Step> steps;
   bool debug_taps = true;
 

@@ -125,6 +125,19 @@ class RaftFlowEngine:
         check(lib().prisma_flow_work(self._h, h, w, self.scale, self.iterations, out))
         return dict(flop=out[0], launches=int(out[1]), hs=int(out[2]), ws=int(out[3]))
 
+    def work_detail(self, h, w):
+        out = (C.c_double * 8)()
+        check(lib().prisma_flow_work_detail(self._h, h, w, float(self.scale), self.iterations, out))
+        return dict(conv_flop_full=out[0], conv_flop_video=out[1], corr_flop=out[2], corr_bytes=out[3],
+                    launches_full=int(out[4]), launches_video=int(out[5]), hs=int(out[6]), ws=int(out[7]))
+
+    def profile(self, h, w):
+        """ms per kernel group of one pass (CUDA events, ungraphed): see prisma_flow_profile."""
+        out = (C.c_float * 8)()
+        check(lib().prisma_flow_profile(self._h, h, w, float(self.scale), self.iterations, out))
+        keys = ["pre", "conv_gemm", "corr_build", "corr_lookup", "instnorm", "pointwise", "post", "total"]
+        return dict(zip(keys, [float(v) for v in out]))
+
     def close(self):
         if self._h:
             lib().prisma_engine_destroy(self._h)

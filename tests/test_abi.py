@@ -70,7 +70,7 @@ def test_bench_b200_arm_never_imports_oracle():
     """Only bench.py's cpu_baseline / --impl reference legs may touch oracle/ (the measured arm must be the CUDA product)."""
     import ast
     tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
-    allowed = {"cpu_baseline_frames", "run_reference"}
+    allowed = {"cpu_reference_step", "run_reference"}
     for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
         mods = []
         for node in ast.walk(fn):
