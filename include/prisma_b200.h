@@ -187,7 +187,8 @@ int prisma_net_size(const char* band, int w, int h, int* wn, int* hn);
 
 /* ---- kernel-level entry points (parity tests and micro-benchmarks call the kernels through the C ABI) ---- */
 /* D = A[M,K] * W[N,K]^T (+bias) with fp16 operands / fp32 accumulate on the tcgen05 core; A, W, D host fp32.
- * act: 0 none, 1 gelu, 2 relu.  force_bn: 0 = auto, else 32/64/128/256.  ms_out (may be NULL): kernel time.   */
+ * act: 0 none, 1 gelu, 2 relu; -4 = the TMA-store epilogue (no bias, accumulator scaled by 1/16: the RAFT correlation path).
+ * force_bn: 0 = auto, else 32/64/128/256, 512 = CTA pairs.  ms_out (may be NULL): kernel time.                               */
 int prisma_debug_gemm(int device, const float* A, const float* W, const float* bias, float* D, int M, int N, int K,
                       int act, int force_bn, int iters, float* ms_out);
 /* 3x3 (kh x kw) stride-1 'same' convolution, NHWC fp32 host in/out, through the shifted-row GEMM.           */

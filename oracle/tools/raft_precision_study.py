@@ -10,7 +10,7 @@ from oracle.frames import synthetic_frame
 
 torch.set_grad_enabled(False)
 sd = make_raft_weights(0)
-H, W = 240, 320
+H, W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (240, 320)
 a = oraft.raft_preprocess(synthetic_frame(H, W, 0))[None]; b = oraft.raft_preprocess(synthetic_frame(H, W, 1))[None]
 i1, i2 = torch.cat([a, b]), torch.cat([b, a])
 pad = oraft.input_pad(*i1.shape[-2:])

@@ -256,6 +256,11 @@ int prisma_debug_gemm(int device, const float* A, const float* W, const float* b
     ep.out_f16 = dH;
     ep.out_f16_ld = N;
   }
+  if (act == -4) {  // TMA-store epilogue (dense fp32, scaled): the path of the RAFT correlation volume
+    ep.bias = nullptr;
+    ep.alpha = 0.0625f;
+    ep.tma_store = true;
+  }
   if (act == -3) {  // micro-benchmark of the residual-stream epilogue: D += acc in place (fp32 read + write)
     ep.res_f32 = dD;
     ep.res_f32_ld = N;

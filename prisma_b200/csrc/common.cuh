@@ -119,6 +119,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// TMA store: a swizzled shared-memory box -> global (bulk async group of the issuing thread); out-of-range rows / columns
+// of the box are clipped by the tensor map
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {  // at most N groups of this thread still READING shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- CTA pairs (cta_group::2): cluster rank / sync, TMA and commits that target the pair ------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -299,6 +308,9 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // 2-D fp16 tensor [rows][cols] with row pitch `pitch_elems`; box = box_cols x box_rows, 128B swizzle
 // (box_cols must be 64 -> 128-byte inner box).  Out-of-bounds elements (either sign) read as zero.
 int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
+                     uint32_t box_cols, uint32_t box_rows);
+// the same for an fp32 tensor (box_cols must be 32 -> 128-byte inner box): the destination of the TMA-store epilogue
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
                      uint32_t box_cols, uint32_t box_rows);
 
 }  // namespace prisma

@@ -16,12 +16,14 @@
 
 namespace prisma {
 
-struct RMap {  // B zero-bordered NHWC fp16 maps
+struct RMap {  // B NHWC fp16 maps in the shared-border layout: `pad` zero columns after every row, `pad` zero rows after every
+               // image (see GemmEpilogue::lead); a 1/8-resolution 1080p pair is 2 x 104 x 182 = 37 856 rows = 296 row tiles =
+               // exactly two waves of 148 CTAs (the symmetric border made it 305 tiles = 2.06 waves)
   __half* p = nullptr;
   int B = 0, H = 0, W = 0, C = 0, pad = 1;
-  int Hp() const { return H + 2 * pad; }
-  int Wp() const { return W + 2 * pad; }
-  long long img_rows() const { return (long long)Hp() * Wp(); }
+  int Hp() const { return H + pad; }
+  int Wp() const { return W + pad; }
+  long long img_rows() const { return ((long long)Hp() * Wp() + 31) / 32 * 32; }  // a 32-row epilogue slab never straddles two images
   long long rows() const { return B * img_rows(); }
 };
 
@@ -89,7 +91,7 @@ const HostTensor* RaftEngine::get(const std::string& name) {
 // conv weight [Cout][Cin][kh][kw] (+bias) -> fp16 [round_up(Npad,256)][taps*kc*64], fp32 bias [Npad]; optional eval-mode
 // BatchNorm folding (y = (conv(x) - mean) * gamma / sqrt(var + eps) + beta, eps = 1e-5) and output scale.
 int RaftEngine::up_conv(const std::string& name, const std::string& bn, int Cout, int Cin, int kh, int kw, int Npad,
-                        float out_scale, ConvW* out) {
+                        float out_scale, ConvW* out, int wsplit) {
   const HostTensor* w = get(name + ".weight");
   const HostTensor* b = get(name + ".bias");
   if (!w || !b) return -1;
@@ -105,19 +107,26 @@ int RaftEngine::up_conv(const std::string& name, const std::string& bn, int Cout
       sh[n] = (b->data[n] - mu->data[n]) * k + be->data[n];
     }
   }
-  const int taps = kh * kw, kc = ceil_div(Cin, 64), K = taps * kc * 64, rows = round_up(Npad, 256);
+  // wsplit == 2: the weights keep ~22 bits as an fp16 pair.  Weight rounding is a SYSTEMATIC error (the same perturbed
+  // filter at every pixel and iteration) and dominates the flow error of the update block; activations' rounding is random
+  // and 7x smaller (oracle/tools/raft_precision_study.py).  Tap t occupies the K slabs 2t (hi) and 2t + 1 (lo).
+  const int taps = kh * kw, kc = ceil_div(Cin, 64), K = taps * wsplit * kc * 64, rows = round_up(Npad, 256);
   std::vector<__half> h((size_t)rows * K, __float2half_rn(0.f));
   for (int n = 0; n < Cout; ++n)
     for (int t = 0; t < taps; ++t)
-      for (int c = 0; c < Cin; ++c)
-        h[(size_t)n * K + (size_t)t * kc * 64 + c] = __float2half_rn(w->data[((size_t)n * Cin + c) * taps + t] * sc[n]);
+      for (int c = 0; c < Cin; ++c) {
+        const float v = w->data[((size_t)n * Cin + c) * taps + t] * sc[n];
+        const __half hi = __float2half_rn(v);
+        h[(size_t)n * K + (size_t)t * wsplit * kc * 64 + c] = hi;
+        if (wsplit == 2) h[(size_t)n * K + (size_t)(t * 2 + 1) * kc * 64 + c] = __float2half_rn(v - __half2float(hi));
+      }
   PRISMA_TRY(r_alloc(allocs, &out->w, h.size()));
   PRISMA_CUDA_OK(cudaMemcpy(out->w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   std::vector<float> bias(round_up(Npad, 8), 0.f);
   for (int n = 0; n < Cout; ++n) bias[n] = sh[n];
   PRISMA_TRY(r_alloc(allocs, &out->b, bias.size()));
   PRISMA_CUDA_OK(cudaMemcpy(out->b, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
-  out->cout = Npad; out->cin = Cin; out->kh = kh; out->kw = kw;
+  out->cout = Npad; out->cin = Cin; out->kh = kh; out->kw = kw; out->wsplit = wsplit;
   return 0;
 }
 
@@ -191,8 +200,24 @@ int RaftEngine::finalize() {
     PRISMA_TRY(up_conv(u + "gru.zr" + s, "", 256, 384, kh, kw, 256, 1.f, &w.zr[pass]));
     PRISMA_TRY(up_conv(u + "gru.convq" + s, "", 128, 384, kh, kw, 128, 1.f, &w.q[pass]));
   }
-  PRISMA_TRY(up_conv(u + "flow_head.conv1", "", 256, 128, 3, 3, 256, 1.f, &w.fh1));
-  PRISMA_TRY(up_conv(u + "flow_head.conv2", "", 2, 256, 3, 3, 4, 1.f, &w.fh2));
+  PRISMA_TRY(up_conv(u + "flow_head.conv1", "", 256, 128, 3, 3, 256, 1.f, &w.fh1, 2));  // hi/lo weights: the largest error term
+  {  // FlowHead.conv2 (256 -> 2) stays fp32 and runs on the CUDA cores (k_flow_head2): [tap][q][lane][4]
+    const HostTensor* wt = get(u + "flow_head.conv2.weight");
+    const HostTensor* bs = get(u + "flow_head.conv2.bias");
+    if (!wt || !bs) return -1;
+    PRISMA_CHECK(wt->data.size() == (size_t)2 * 256 * 9 && bs->data.size() == 2, "RAFT flow_head.conv2 has an unexpected size");
+    std::vector<float> pk((size_t)9 * 4 * 32 * 4);
+    for (int t = 0; t < 9; ++t)
+      for (int q = 0; q < 4; ++q)
+        for (int lane = 0; lane < 32; ++lane)
+          for (int j = 0; j < 4; ++j) {
+            const int o = q >> 1, ch = lane * 8 + (q & 1) * 4 + j;
+            pk[(((size_t)t * 4 + q) * 32 + lane) * 4 + j] = wt->data[((size_t)o * 256 + ch) * 9 + t];
+          }
+    PRISMA_TRY(r_alloc(allocs, &w.fh2_w, pk.size()));
+    PRISMA_CUDA_OK(cudaMemcpy(w.fh2_w, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+    w.fh2_b[0] = bs->data[0]; w.fh2_b[1] = bs->data[1];
+  }
   PRISMA_TRY(up_conv(u + "mask.0", "", 256, 128, 3, 3, 256, 1.f, &w.mk1));
   PRISMA_TRY(up_conv(u + "mask.2", "", 576, 256, 1, 1, 576, 0.25f, &w.mk2));  // mask = .25 * conv (update.py:135)
   host.clear();
@@ -212,14 +237,18 @@ void RaftEngine::add(const char* name, std::function<int(cudaStream_t)> fn) { st
 int RaftEngine::add_conv(const char* name, const RMap& in, int c0, const ConvW& cw, GemmEpilogue ep, int sub) {
   PRISMA_CHECK(cw.kh / 2 <= in.pad && cw.kw / 2 <= in.pad, "conv halo exceeds the map border");
   int off[GEMM_MAX_TAPS];
+  PRISMA_CHECK(cw.kh * cw.kw * cw.wsplit <= GEMM_MAX_TAPS, "conv: too many taps");
   for (int ky = 0; ky < cw.kh; ++ky)
-    for (int kx = 0; kx < cw.kw; ++kx) off[ky * cw.kw + kx] = (ky - cw.kh / 2) * in.Wp() + (kx - cw.kw / 2);
+    for (int kx = 0; kx < cw.kw; ++kx)
+      for (int sp = 0; sp < cw.wsplit; ++sp)  // hi / lo weight slabs re-read the same shifted rows
+        off[(ky * cw.kw + kx) * cw.wsplit + sp] = (ky - cw.kh / 2) * in.Wp() + (kx - cw.kw / 2);
   if (ep.row_map == ROW_LINEAR) ep.row_map = ROW_PADDED;
   ep.in_w = in.Wp(); ep.in_h = in.Hp(); ep.img_rows = (int)in.img_rows(); ep.pad = in.pad; ep.sub = sub;
+  ep.lead = 0; ep.out_lead = 0;  // shared-border maps on both sides
   if (!ep.bias) ep.bias = cw.b;
   GemmLaunch g;
   PRISMA_TRY(gemm_prepare(&g, in.p + c0, in.rows(), cw.cin, in.C, cw.w, round_up(cw.cout, 256), (int)in.rows(), cw.cout,
-                          cw.kh * cw.kw, off, ep, num_sms));
+                          cw.kh * cw.kw * cw.wsplit, off, ep, num_sms));
   { const double f = 2.0 * in.B * (double)(in.H / sub) * (in.W / sub) * cw.kh * cw.kw * cw.cin * cw.cout;
     if (cur_mask & 1) { flops += f; flops_conv += f; }
     if (cur_mask & 2) flops_conv_video += f; }
@@ -240,10 +269,13 @@ int RaftEngine::add_conv_in(const char* name, const RMap& in, const ConvW& cw, i
   GemmEpilogue ep;
   ep.row_map = ROW_PAD2TOK;
   ep.out_f32 = dense; ep.out_f32_ld = cw.cout;
+  ep.stat_part = slab_part;  // sum / sum of squares per 32-row slab, written by the conv epilogue itself
   PRISMA_TRY(add_conv(name, in, 0, cw, ep, sub));
   const int Ho = in.H / sub, Wo = in.W / sub, C = cw.cout, B = in.B;
-  float* part = in_part;
-  add("instnorm_stats", [=](cudaStream_t s) { return instnorm_stats(dense, B, Ho * Wo, C, part, stats, s); });
+  const int spi = (int)(in.img_rows() / 32);
+  PRISMA_CHECK((size_t)round_up((int)in.rows(), 256) / 32 * 2 * C <= slab_part_floats, "instnorm slab partials exceed their buffer");
+  float* sp = slab_part; double* p2 = slab_part2;
+  add("instnorm_stats", [=](cudaStream_t s) { return instnorm_stats_from_slabs(sp, B, spi, C, Ho * Wo, p2, stats, s); });
   return 0;
 }
 
@@ -262,10 +294,11 @@ int RaftEngine::build_encoder(const EncW& e, bool inorm, const __half* stem_cols
       add("stem_gemm", [g](cudaStream_t s) { return gemm_run(g, s); });
       float* d = dense_a; float* st = stats_a; float* part = in_part; __half* o = x.p;
       add("instnorm_stats", [=](cudaStream_t s) { return instnorm_stats(d, B, H2 * W2, 64, part, st, s); });
-      add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, H2, W2, 64, nullptr, nullptr, nullptr, o, 1, s); });
+      const long long ir = x.img_rows();
+      add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, H2, W2, 64, nullptr, nullptr, nullptr, o, 1, ir, s); });
     } else {
       ep.act = 2;
-      ep.row_map = ROW_TOK2PAD; ep.in_w = W2; ep.in_h = H2; ep.out_wp = x.Wp(); ep.out_img_rows = (int)x.img_rows(); ep.out_pad = 1;
+      ep.row_map = ROW_TOK2PAD; ep.in_w = W2; ep.in_h = H2; ep.out_wp = x.Wp(); ep.out_img_rows = (int)x.img_rows(); ep.out_pad = 1; ep.out_lead = 0;
       ep.out_f16 = x.p; ep.out_f16_ld = 64;
       PRISMA_TRY(gemm_prepare(&g, stem_cols, (long long)B * H2 * W2, 192, 192, e.stem.w, 256, B * H2 * W2, 64, 1, zero_off, ep, num_sms));
       add("stem_gemm", [g](cudaStream_t s) { return gemm_run(g, s); });
@@ -287,15 +320,18 @@ int RaftEngine::build_encoder(const EncW& e, bool inorm, const __half* stem_cols
         // y = relu(IN(conv1(x))) ; z = conv2(y) ; out = relu(skip + relu(IN(z))), skip = x or IN(downsample(x))
         PRISMA_TRY(add_conv_in("res_conv1", x, r.c1, sub, dense_a, stats_a));
         { float* d = dense_a; float* st = stats_a; __half* yo = y.p;
-          add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, Ho, Wo, C, nullptr, nullptr, nullptr, yo, 1, s); }); }
+          const long long ir = y.img_rows();
+          add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, Ho, Wo, C, nullptr, nullptr, nullptr, yo, 1, ir, s); }); }
         PRISMA_TRY(add_conv_in("res_conv2", y, r.c2, 1, dense_a, stats_a));
         if (r.has_ds) {
           PRISMA_TRY(add_conv_in("res_downsample", x, r.ds, 2, dense_b, stats_b));
           float* d = dense_a; float* st = stats_a; float* d2 = dense_b; float* st2 = stats_b; __half* oo = o.p;
-          add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, Ho, Wo, C, nullptr, d2, st2, oo, 1, s); });
+          const long long ir = o.img_rows();
+          add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, Ho, Wo, C, nullptr, d2, st2, oo, 1, ir, s); });
         } else {
           float* d = dense_a; float* st = stats_a; const __half* sk = x.p; __half* oo = o.p;
-          add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, Ho, Wo, C, sk, nullptr, nullptr, oo, 1, s); });
+          const long long ir = o.img_rows();
+          add("instnorm_apply", [=](cudaStream_t s) { return instnorm_apply(d, st, B, Ho, Wo, C, sk, nullptr, nullptr, oo, 1, ir, s); });
         }
       } else {
         // BatchNorm folded: y = relu(conv1'(x)) ; out = relu(skip + relu(conv2'(y)))
@@ -352,6 +388,12 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   PRISMA_TRY(r_alloc(plan_allocs, &stats_a, 2 * 256 * 2));
   PRISMA_TRY(r_alloc(plan_allocs, &stats_b, 2 * 256 * 2));
   PRISMA_TRY(r_alloc(plan_allocs, &in_part, (size_t)instnorm_partial_floats(2, (Hp_ / 2) * (Wp_ / 2), 128)));
+  {  // per-slab (32 rows) column sums of the conv epilogues: the largest conv input is a pad-1 half-resolution map
+    const long long ir = (((long long)(Hp_ / 2 + 1) * (Wp_ / 2 + 1) + 31) / 32) * 32;
+    slab_part_floats = (size_t)(round_up((int)(2 * ir), 256) / 32) * 2 * 128;  // CTA-pair tiles cover 256 rows
+    PRISMA_TRY(r_alloc(plan_allocs, &slab_part, slab_part_floats));
+    PRISMA_TRY(r_alloc(plan_allocs, &slab_part2, (size_t)2 * INSTNORM_STAGE1_BLOCKS * 128 * 2));
+  }
   PRISMA_TRY(r_alloc(plan_allocs, &b.coords0, (size_t)B * 2 * P));
   PRISMA_TRY(r_alloc(plan_allocs, &b.coords1, (size_t)B * 2 * P));
   PRISMA_TRY(r_alloc(plan_allocs, &b.cnet_out, (size_t)B * P * 256));
@@ -443,8 +485,8 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   cur_mask = 3;
   {
     const float* cn = b.cnet_out; float* hm = b.h_master; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
-    float* c0 = b.coords0; float* c1p = b.coords1;
-    add("cnet_split", [=](cudaStream_t s) { return raft_cnet_split(cn, 2, h8, w8, 2, hm, hxp, rhp, s); });
+    float* c0 = b.coords0; float* c1p = b.coords1; const long long ir8 = hx.img_rows();
+    add("cnet_split", [=](cudaStream_t s) { return raft_cnet_split(cn, 2, h8, w8, 2, ir8, hm, hxp, rhp, s); });
     add("coords_init", [=](cudaStream_t s) { return raft_coords_init(c0, c1p, 2, h8, w8, s); });
   }
   // ---- update block, `iters` times (raft.py:123-141)
@@ -459,13 +501,12 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   PRISMA_TRY(r_alloc(plan_allocs, &q_f, (size_t)hx.rows() * 128));
   PRISMA_TRY(new_map(&fh, B, H8, W8, 256, 2));
   PRISMA_TRY(new_map(&mk, B, H8, W8, 256, 2));
-  PRISMA_TRY(r_alloc(plan_allocs, &b.delta, (size_t)hx.rows() * 4));
   PRISMA_TRY(r_alloc(plan_allocs, &b.mask, (size_t)hx.rows() * 576));
   const long long rows = hx.rows();
   for (int it = 0; it < iters; ++it) {
     {
       FlowCorr* c = corr; const float* c1p = b.coords1; __half* dst = corrf.p; const int wp = corrf.Wp(), ir = (int)corrf.img_rows();
-      add("corr_lookup", [=](cudaStream_t s) { return c->lookup_to(c1p, dst, 384, wp, 2, ir, s); });
+      add("corr_lookup", [=](cudaStream_t s) { return c->lookup_to(c1p, dst, 384, wp, 0, ir, s); });  // shared-border map: no leading border
     }
     { GemmEpilogue ep; ep.act = 2; ep.out_f16 = c1.p; ep.out_f16_ld = 256;            // convc1 1x1 324 -> 256
       ConvW cw = w.convc1; cw.cin = 384;  // the lookup map is zero padded to 384 channels, so are the weights' K
@@ -477,7 +518,7 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
       const float* c0 = b.coords0; const float* c1p = b.coords1; __half* cols = f1_cols; const int h8 = H8, w8 = W8;
       add("convf1_im2col", [=](cudaStream_t s) { return raft_flow_im2col(c0, c1p, 2, h8, w8, cols, s); });
       GemmEpilogue ep; ep.bias = w.convf1_b; ep.act = 2; ep.out_f16 = f1.p; ep.out_f16_ld = 128;
-      ep.row_map = ROW_TOK2PAD; ep.in_w = W8; ep.in_h = H8; ep.out_wp = f1.Wp(); ep.out_img_rows = (int)f1.img_rows(); ep.out_pad = 2;
+      ep.row_map = ROW_TOK2PAD; ep.in_w = W8; ep.in_h = H8; ep.out_wp = f1.Wp(); ep.out_img_rows = (int)f1.img_rows(); ep.out_pad = 2; ep.out_lead = 0;
       GemmLaunch g;
       const int zoff[1] = {0};
       PRISMA_TRY(gemm_prepare(&g, f1_cols, 2LL * H8 * W8, 256, 256, w.convf1_gemm_w, 256, 2 * H8 * W8, 128, 1, zoff, ep, num_sms));
@@ -491,7 +532,8 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
       GemmEpilogue ep; ep.act = 2; ep.out_f16 = hx.p + 256; ep.out_f16_ld = 384; ep.out_f16_relu = rhx.p + 256; ep.out_f16_relu_ld = 384;
       PRISMA_TRY(add_conv("motion_conv", c2, 0, w.conv, ep, 1));
       const float* c0 = b.coords0; const float* c1p = b.coords1; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
-      add("flow_cols", [=](cudaStream_t s) { return raft_flow_cols(c0, c1p, 2, h8, w8, 2, hxp, rhp, s); });
+      const long long ir8 = hx.img_rows();
+      add("flow_cols", [=](cudaStream_t s) { return raft_flow_cols(c0, c1p, 2, h8, w8, 2, ir8, hxp, rhp, s); });
     }
     for (int pass = 0; pass < 2; ++pass) {  // SepConvGRU horizontal then vertical (update.py:45-60)
       { GemmEpilogue ep; ep.act = 3; ep.out_f32 = zr_f; ep.out_f32_ld = 256;
@@ -506,10 +548,11 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
     { GemmEpilogue ep; ep.act = 2; ep.out_f16 = fh.p; ep.out_f16_ld = 256;            // flow head
       ConvW cw = w.fh1;
       PRISMA_TRY(add_conv("flow_head1", hx, 0, cw, ep, 1)); }
-    { GemmEpilogue ep; ep.out_f32 = b.delta; ep.out_f32_ld = 4;
-      PRISMA_TRY(add_conv("flow_head2", fh, 0, w.fh2, ep, 1)); }
-    { const float* d = b.delta; float* c1p = b.coords1; const int h8 = H8, w8 = W8;
-      add("coords_update", [=](cudaStream_t s) { return raft_coords_update(d, 2, h8, w8, 2, c1p, s); }); }
+    { // flow_head.conv2 (fp32 weights, CUDA cores) + coords1 += delta (raft.py:133) in one kernel
+      const __half* fhp = fh.p; const float* wp2 = w.fh2_w; const float b0 = w.fh2_b[0], b1 = w.fh2_b[1]; float* c1p = b.coords1;
+      const int h8 = H8, w8 = W8; const long long ir8 = fh.img_rows();
+      flops += 2.0 * 2 * H8 * (double)W8 * 9 * 256 * 2;
+      add("flow_head2", [=](cudaStream_t s) { return raft_flow_head2(fhp, 2, h8, w8, 2, ir8, wp2, b0, b1, c1p, nullptr, s); }); }
     if (debug_taps && it == 0) {
       PRISMA_TRY(r_alloc(plan_allocs, &b.h_tap, (size_t)hx.rows() * 128));
       PRISMA_TRY(r_alloc(plan_allocs, &b.coords_tap, (size_t)B * 2 * P));
@@ -530,7 +573,8 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   {
     const float* m = b.mask; const float* c0 = b.coords0; const float* c1p = b.coords1; float* up = b.flow_up;
     const int h8 = H8, w8 = W8, Hs_ = Hs, Ws_ = Ws, pt = pads[2], pl = pads[0];
-    add("convex_upsample", [=](cudaStream_t s) { return raft_convex_upsample(m, c0, c1p, 2, h8, w8, 2, Hs_, Ws_, pt, pl, up, s); });
+    const long long ir8 = hx.img_rows();
+    add("convex_upsample", [=](cudaStream_t s) { return raft_convex_upsample(m, c0, c1p, 2, h8, w8, 2, ir8, Hs_, Ws_, pt, pl, up, s); });
     uint8_t* rgb = b.rgb; uint32_t* mm = b.mm; float* mx = b.maxd; const int sms = num_sms;
     add("flow_encode", [=](cudaStream_t s) {
       for (int i = 0; i < 2; ++i)
@@ -764,9 +808,9 @@ int RaftEngine::profile(int H, int W, double scale, int iters_, float* out8) {
     else if (n == "corr_lookup") g = 3;
     else if (n.rfind("instnorm", 0) == 0) g = 4;
     else if (n == "convex_upsample" || n == "flow_encode") g = 6;
-    else if (n == "convf1_im2col") g = 5;
+    else if (n == "convf1_im2col" || n == "flow_head2") g = 5;
     else if (n == "stem_gemm" || n == "convf1_gemm" || n.rfind("res_", 0) == 0 || n.rfind("conv", 0) == 0 || n == "fnet_out" ||
-             n == "cnet_out" || n == "motion_conv" || n.rfind("gru_zr", 0) == 0 || n == "gru_q" || n.rfind("flow_head", 0) == 0 ||
+             n == "cnet_out" || n == "motion_conv" || n.rfind("gru_zr", 0) == 0 || n == "gru_q" || n == "flow_head1" ||
              n.rfind("mask_head", 0) == 0) g = 1;
     out8[g] += t; out8[7] += t;
   }

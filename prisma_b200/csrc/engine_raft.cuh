@@ -11,13 +11,15 @@
 
 namespace prisma {
 
-struct ConvW { __half* w = nullptr; float* b = nullptr; int cout = 0, cin = 0, kh = 1, kw = 1; };
+struct ConvW { __half* w = nullptr; float* b = nullptr; int cout = 0, cin = 0, kh = 1, kw = 1;
+               int wsplit = 1; };  // wsplit 2: every tap's K slab is stored twice, [fp16(w) | fp16(w - fp16(w))], the tap is walked twice
 struct ResW { ConvW c1, c2, ds; bool has_ds = false; };
 struct EncW { ConvW stem; ResW blk[3][2]; ConvW out; };
 struct RaftWeights {
   EncW fnet, cnet;
   ConvW convc1, convc2, convf2, conv, zr[2], q[2], fh1, fh2, mk1, mk2;
   float *convf1_w = nullptr, *convf1_b = nullptr;
+  float* fh2_w = nullptr; float fh2_b[2] = {0.f, 0.f};  // FlowHead.conv2 in fp32, packed for k_flow_head2
   __half* convf1_gemm_w = nullptr;  // [256][256]: k = [98 weights | 0 | the same 98 (for the fp16 'lo' half of the flow) | 0]
 };
 struct RaftBuffers {
@@ -58,7 +60,7 @@ class RaftEngine {
  private:
   const HostTensor* get(const std::string& name);
   int up_conv(const std::string& name, const std::string& bn, int Cout, int Cin, int kh, int kw, int Npad, float out_scale,
-              ConvW* out);
+              ConvW* out, int wsplit = 1);
   int up_encoder(const std::string& prefix, bool bn, EncW* e);
   int new_map(RMap* m, int B, int H, int W, int C, int pad);
   void add(const char* name, std::function<int(cudaStream_t)> fn);
@@ -80,6 +82,7 @@ class RaftEngine {
   FlowCorr* corr = nullptr;
   std::map<std::string, Tap> taps;
   float *dense_a = nullptr, *dense_b = nullptr, *stats_a = nullptr, *stats_b = nullptr, *in_part = nullptr;
+  float* slab_part = nullptr; double* slab_part2 = nullptr; size_t slab_part_floats = 0;
   int plan_H = 0, plan_W = 0, iters = 0, Hp_ = 0, Wp_ = 0, pads[4] = {0, 0, 0, 0};
   double plan_scale = 0.0;
   struct StreamSlot {

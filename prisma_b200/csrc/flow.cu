@@ -326,7 +326,10 @@ int FlowCorr::init(int dev, int batch, int h8, int w8) {
       ep.alpha = 1.0f / sqrtf((float)C);
       ep.out_f32 = vol[l] + (size_t)b * P * lpitch[l];
       ep.out_f32_ld = lpitch[l];
+      // the volume is store-bound (131 KB per 128 x 256 tile against 4 K-blocks of MMA): leave through TMA bulk stores
+      static const bool tma_off = [] { const char* e = getenv("PRISMA_CORR_TMA_STORE"); return e && e[0] == '0'; }();
       GemmLaunch g;
+      ep.tma_store = !tma_off && gemm_pick_bn(P, lpitch[l], num_sms) >= 128;
       const int wk = l == 0 ? 1 : 2;  // coarse levels: fmap1 against [hi | lo] pooled features = two K-slabs
       PRISMA_TRY(gemm_prepare(&g, fmap1 + (size_t)b * rows_pad * C, P, C, C, fmap2[l] + (size_t)b * lrows_pad[l] * C * wk,
                               lrows_pad[l], P, lpitch[l], wk, off, ep, num_sms));

@@ -44,6 +44,24 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t
   return 0;
 }
 
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
+                     uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  PRISMA_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  PRISMA_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  PRISMA_CHECK((pitch_elems * 4) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  PRISMA_CHECK(box_cols * 4 == 128 && box_rows >= 1 && box_rows <= 256, "TMA box must be 32 fp32 wide, <=256 rows");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PRISMA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32) failed (code " + std::to_string((int)r) + ")");
+  return 0;
+}
+
 // Tile-N choice: minimise waves x per-tile time.  Per-tile costs are MEASURED on B200 (8192^3 sweep, relative units
 // per 64-wide K block): the 128x256 tile runs at 1351 TF/s, 128x128 at 919 TF/s (L2->SM operand traffic per MMA is
 // 1.5x higher), narrower tiles are smem-read bound; plus a per-tile constant for the drain / epilogue hand-off.
@@ -123,37 +141,56 @@ int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols,
     }
   }
   out->flops = 2.0 * M * (double)N * taps * a_cols;
+  // TMA-store epilogue: a plain dense fp32 output (scale only) leaves through swizzled shared-memory boxes and
+  // cp.async.bulk.tensor stores instead of per-lane st.global (the store-bound RAFT correlation volume)
+  out->tma_store = false;
+  out->tmD = out->tmA;
+  if (ep.tma_store) {
+    PRISMA_CHECK(ep.out_f32 && !ep.out_f16 && !ep.out_f16_relu && !ep.bias && !ep.gamma && ep.act == 0 && !ep.res_f32 && !ep.res_a &&
+                     !ep.res_b && ep.row_map == ROW_LINEAR && !ep.head_w && !ep.stat_part,
+                 "gemm: the TMA-store epilogue handles a scaled dense fp32 output only");
+    PRISMA_CHECK(bn >= 128, "gemm: the TMA-store epilogue is built for BLOCK_N 128 / 256");
+    PRISMA_TRY(make_tmap_2d_f32(&out->tmD, ep.out_f32, (uint64_t)N, (uint64_t)M, (uint64_t)ep.out_f32_ld, 32, 32));
+    out->tma_store = true;
+  }
   return 0;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool TMAST = false>
 static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
   static bool attr_set = false;  // per-process, per-instantiation
+  using Cfg = GemmCfg<BN, CG, TMAST>;
   if (!attr_set) {
-    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        GemmCfg<BN, CG>::SMEM_BYTES));
+    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, TMAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   if (CG == 1) {
-    gemm_tc_kernel<BN, CG><<<g.grid, GEMM_THREADS, GemmCfg<BN, CG>::SMEM_BYTES, stream>>>(g.tmA, g.tmB, g.tmBt, g.args);
+    gemm_tc_kernel<BN, CG, TMAST><<<g.grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(g.tmA, g.tmB, g.tmBt, g.tmD, g.args);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.grid);
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GemmCfg<BN, CG>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, g.tmA, g.tmB, g.tmBt, g.args));
+    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, TMAST>, g.tmA, g.tmB, g.tmBt, g.tmD, g.args));
   }
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int gemm_run(const GemmLaunch& g, cudaStream_t stream) {
+  if (g.tma_store) {
+    if (g.cg == 2 && g.bn == 256) return launch_bn<256, 2, true>(g, stream);
+    if (g.cg == 1 && g.bn == 256) return launch_bn<256, 1, true>(g, stream);
+    if (g.cg == 1 && g.bn == 128) return launch_bn<128, 1, true>(g, stream);
+    set_last_error("gemm_run: no TMA-store instantiation for this tile shape");
+    return -1;
+  }
   if (g.cg == 2) {
     if (g.bn == 256) return launch_bn<256, 2>(g, stream);
     set_last_error("gemm_run: CTA pairs need BLOCK_N 256");

@@ -62,6 +62,13 @@ struct GemmEpilogue {
   int sub = 1;       // ROW_PADDED: keep every sub-th pixel (stride-2 conv evaluated at stride 1)
   int pad = 1;       // ROW_PADDED / ROW_PAD2TOK: border width of the input geometry; out_pad: of the destination
   int out_pad = 1;
+  // Border placement.  lead < 0 (default): symmetric border, `pad` pixels on every side (in_h = H + 2 pad).
+  // lead == 0: "shared border" layout -- `pad` zero columns only at the END of every row and `pad` zero rows only at the END
+  // of every image (in_h = H + pad, in_w = W + pad).  A negative tap shift then lands in the previous row's / previous
+  // image's trailing zeros (or before row 0, where TMA zero-fills), so the halo is still all zeros but the GEMM walks
+  // (H + pad)(W + pad) rows instead of (H + 2 pad)(W + 2 pad).  out_lead: the same for the destination map.
+  int lead = -1;
+  int out_lead = -1;
   int shuf_s = 1;
   int shuf_cout = 0;
   // fused DPT output head (dpt.py:96-100): depth = relu(head_b + sum_j head_w[j] * relu(acc[j] + bias[j])), N == 32,
@@ -69,6 +76,13 @@ struct GemmEpilogue {
   const float* head_w = nullptr;
   float head_b = 0.f;
   float* head_out = nullptr;
+  // Column statistics of the stored values, for a normalisation that follows the conv (RAFT's InstanceNorm2d): every
+  // 32-row slab of the output space (slab = m / 32; image row counts are multiples of 32, so a slab lies in one image)
+  // writes sum and sum of squares over its VALID rows: stat_part[(slab * 2 + {0,1}) * N + n], fp32, deterministic
+  // (fixed shuffle tree; a second kernel adds the slabs in double precision in a fixed order).
+  float* stat_part = nullptr;
+  // dense fp32 output (row_map LINEAR, scale only) stored by TMA: tcgen05.ld -> swizzled smem box -> cp.async.bulk.tensor
+  bool tma_store = false;
 };
 
 struct GemmArgs {
@@ -84,14 +98,14 @@ struct GemmArgs {
   GemmEpilogue ep;
 };
 
-template <int BN, int CG = 1>  // CG = CTAs per MMA (cta_group): 2 = a CTA pair computes a 256 x BN tile, each loading half of W
-struct GemmCfg {
+template <int BN, int CG = 1, bool TMAST = false>  // CG = CTAs per MMA (cta_group): 2 = a CTA pair computes a 256 x BN tile, each loading half of W
+struct GemmCfg {                                   // TMAST: TMA-store epilogue (double-buffered staging, one operand stage fewer)
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (STAGE_BYTES >= 49152) ? 4 : (STAGE_BYTES >= 32768 ? 6 : 7);
+  static constexpr int STAGES = ((STAGE_BYTES >= 49152) ? 4 : (STAGE_BYTES >= 32768 ? 6 : 7)) - (TMAST ? 1 : 0);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 32 * 4;  // epilogue transpose staging: 32x32 fp32 per warp
+  static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 32 * 4 * (TMAST ? 2 : 1);  // epilogue staging: 32x32 fp32 per warp (x2 buffers)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -188,11 +202,12 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   }
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool TMAST>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ GemmArgs args) {
-  using Cfg = GemmCfg<BN, CG>;
+               const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmD,
+               const __grid_constant__ GemmArgs args) {
+  using Cfg = GemmCfg<BN, CG, TMAST>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -308,7 +323,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
     const int chunk_par = (warp - 2) >> 2;  // the two warps of a quarter take even / odd 32-column chunks
     const GemmEpilogue& ep = args.ep;
-    const uint32_t stg = smem_u32(stg_all) + (warp - 2) * 4096;
+    const uint32_t stg = smem_u32(stg_all) + (warp - 2) * (TMAST ? 8192 : 4096);
+    uint32_t st_cnt = 0;  // TMAST: chunks stored so far by this warp (staging buffer parity)
     const int cg = lane & 7;     // coalesced phase: which 4-column group of the 32-column chunk
     const int rsub = lane >> 3;  // coalesced phase: row offset inside a 4-row step
     int it = 0;
@@ -324,20 +340,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int valid = m < args.M;
       int drow = m;
       int ty = 0, tx = 0, img_base = 0;  // token coordinates / image base row for ROW_SHUFFLE
+      const int out_ld = ep.out_lead < 0 ? ep.out_pad : ep.out_lead;  // leading border of the destination map
       if (ep.row_map == ROW_PADDED || ep.row_map == ROW_PAD2TOK) {
         int img = 0, r = m;
         if (ep.img_rows > 0) { img = m / ep.img_rows; r = m - img * ep.img_rows; }
         const int y = r / ep.in_w, x = r - y * ep.in_w;
-        const int pd = ep.pad;
-        valid = valid && y >= pd && y < ep.in_h - pd && x >= pd && x < ep.in_w - pd;
+        const int pd = ep.pad, ld = ep.lead < 0 ? ep.pad : ep.lead;
+        valid = valid && y >= ld && y < ep.in_h - pd && x >= ld && x < ep.in_w - pd;
         if (ep.row_map == ROW_PAD2TOK) {
-          const int ho = (ep.in_h - 2 * pd + ep.sub - 1) / ep.sub, wo = (ep.in_w - 2 * pd + ep.sub - 1) / ep.sub;
-          valid = valid && ((y - pd) % ep.sub == 0) && ((x - pd) % ep.sub == 0);
-          drow = img * (ep.out_img_rows > 0 ? ep.out_img_rows : ho * wo) + ((y - pd) / ep.sub) * wo + (x - pd) / ep.sub;
+          const int ho = (ep.in_h - pd - ld + ep.sub - 1) / ep.sub, wo = (ep.in_w - pd - ld + ep.sub - 1) / ep.sub;
+          valid = valid && ((y - ld) % ep.sub == 0) && ((x - ld) % ep.sub == 0);
+          drow = img * (ep.out_img_rows > 0 ? ep.out_img_rows : ho * wo) + ((y - ld) / ep.sub) * wo + (x - ld) / ep.sub;
         } else if (ep.sub > 1 || ep.out_wp > 0) {
           // destination geometry differs from the source one (stride-2 sub-sampling and / or another border width)
-          valid = valid && ((y - pd) % ep.sub == 0) && ((x - pd) % ep.sub == 0);
-          drow = img * ep.out_img_rows + ((y - pd) / ep.sub + ep.out_pad) * ep.out_wp + (x - pd) / ep.sub + ep.out_pad;
+          valid = valid && ((y - ld) % ep.sub == 0) && ((x - ld) % ep.sub == 0);
+          drow = img * ep.out_img_rows + ((y - ld) / ep.sub + out_ld) * ep.out_wp + (x - ld) / ep.sub + out_ld;
         }
       } else if (ep.row_map == ROW_TOKSKIP) {
         drow = m + m / ep.in_w + 1;
@@ -346,7 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int img = m / per, r = m - img * per;
         ty = r / ep.in_w; tx = r - ty * ep.in_w;
         img_base = img * ep.out_img_rows;
-        drow = img_base + (ty + ep.out_pad) * ep.out_wp + tx + ep.out_pad;
+        drow = img_base + (ty + out_ld) * ep.out_wp + tx + out_ld;
       }
       // row mapping of the 8 rows this lane stores in the coalesced phase (constant over the tile's chunks)
       int dr8[8], ty8[8], tx8[8], ib8[8];
@@ -371,6 +388,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
+        if (TMAST) {
+          // ---- TMA-store path: registers -> swizzled 32 x 128 B box (the XOR of the 16-byte slot with row & 7 IS the
+          // 128-byte TMA swizzle of a 1024-aligned buffer) -> one cp.async.bulk.tensor store by lane 0; two boxes per warp
+          // so the store of chunk i reads shared memory while chunk i + 1 is being staged
+          const uint32_t buf = stg + (st_cnt & 1) * 4096;
+          if (st_cnt >= 2) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(buf + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]) * ep.alpha, __uint_as_float(r[4 * j + 1]) * ep.alpha,
+                   __uint_as_float(r[4 * j + 2]) * ep.alpha, __uint_as_float(r[4 * j + 3]) * ep.alpha);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmD)),
+                         "r"(buf), "r"(n0 + c0), "r"(m0 + quarter * 32)
+                         : "memory");
+            tma_store_commit();
+          }
+          ++st_cnt;
+          continue;
+        }
         if (ep.head_w != nullptr) {
           if (valid) {
             float acc = ep.head_b;
@@ -422,16 +461,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int drs[8];
 #pragma unroll
           for (int rr = 0; rr < 8; ++rr)
-            drs[rr] = ib8[rr] + (ty8[rr] * ep.shuf_s + sdy + ep.out_pad) * ep.out_wp + tx8[rr] * ep.shuf_s + sdx + ep.out_pad;
+            drs[rr] = ib8[rr] + (ty8[rr] * ep.shuf_s + sdy + out_ld) * ep.out_wp + tx8[rr] * ep.shuf_s + sdx + out_ld;
           epilogue_rows8(ep, v, drs, ncol_ok ? okrows : 0u, bias4, gamma4, col);
         } else {
           epilogue_rows8(ep, v, dr8, ncol_ok ? okrows : 0u, bias4, gamma4, col);
+        }
+        if (ep.stat_part != nullptr) {
+          float4 sm = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr)
+            if ((okrows >> rr) & 1) {
+              sm.x += v[rr].x; sm.y += v[rr].y; sm.z += v[rr].z; sm.w += v[rr].w;
+              sq.x = fmaf(v[rr].x, v[rr].x, sq.x); sq.y = fmaf(v[rr].y, v[rr].y, sq.y);
+              sq.z = fmaf(v[rr].z, v[rr].z, sq.z); sq.w = fmaf(v[rr].w, v[rr].w, sq.w);
+            }
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {  // the 4 lanes that hold the same 4 columns (rows rsub, rsub + 4, ...)
+            sm.x += __shfl_xor_sync(0xffffffffu, sm.x, o); sm.y += __shfl_xor_sync(0xffffffffu, sm.y, o);
+            sm.z += __shfl_xor_sync(0xffffffffu, sm.z, o); sm.w += __shfl_xor_sync(0xffffffffu, sm.w, o);
+            sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
+            sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
+          }
+          if (rsub == 0 && ncol_ok) {
+            const size_t slab = (size_t)(m0 + quarter * 32) >> 5;
+            *reinterpret_cast<float4*>(ep.stat_part + (slab * 2) * args.N + n) = sm;
+            *reinterpret_cast<float4*>(ep.stat_part + (slab * 2 + 1) * args.N + n) = sq;
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]); }
     }
+    if (TMAST && lane == 0) tma_store_wait_all();  // shared memory must outlive the last bulk stores
   }
   __syncwarp();
   tc_fence_before();
@@ -446,6 +508,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Host-side prepared launch: tensor maps encoded once, replayed every frame (also inside CUDA graphs).
 struct GemmLaunch {
   CUtensorMap tmA, tmB, tmBt;  // tmBt: W with the narrow box of the tail tiles (== tmB when there is no tail)
+  CUtensorMap tmD;             // fp32 output, 32 x 32 boxes (TMA-store epilogue only)
+  bool tma_store = false;
   GemmArgs args;
   int bn = 128;
   int cg = 1;  // 2 = CTA pairs (cta_group::2), 256 x bn tiles

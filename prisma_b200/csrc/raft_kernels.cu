@@ -1,6 +1,8 @@
 // prisma_b200 -- RAFT band: the pointwise / gather kernels around the tcgen05 conv core
 // (instance norm, im2col of the 7x7 stem, cnet split, GRU gate algebra, coords update, convex up-sampling).
-// Reference: bands/raft/{extractor,update,raft}.py.  All feature maps are NHWC fp16 with a zero border.
+// Reference: bands/raft/{extractor,update,raft}.py.  All feature maps are NHWC fp16 in the "shared border" layout: `pad`
+// zero columns after every row and `pad` zero rows after every image (gemm_tc.cuh GemmEpilogue::lead), so pixel (y, x) of
+// image b sits at row (b (H + pad) + y)(W + pad) + x.
 #include "raft_kernels.cuh"
 
 namespace prisma {
@@ -96,12 +98,62 @@ int instnorm_stats(const float* x, int B, int HW, int C, float* part, float* sta
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
+// Statistics from the slab partials the conv epilogue wrote (GemmEpilogue::stat_part): image b owns the slabs
+// [b * spi, (b + 1) * spi).  Stage 1: nblk blocks per image add stripes of slabs in double (fixed order); stage 2: one
+// block per image adds the nblk partial sums and writes (mean, 1 / sqrt(var + eps)).  HW = number of pixels normalised.
+__global__ void k_in_slab_stage1(const float* __restrict__ part, int spi, int C, double* __restrict__ part2) {
+  extern __shared__ double shd[];  // [groups][C][2]
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int groups = blockDim.x / C;
+  const int g = threadIdx.x / C, c = threadIdx.x - g * C;
+  const int s0 = (int)((long long)spi * blk / nblk), s1 = (int)((long long)spi * (blk + 1) / nblk);
+  double s = 0.0, q = 0.0;
+  if (g < groups) {
+    for (int k = s0 + g; k < s1; k += groups) {
+      const float* p = part + ((size_t)b * spi + k) * 2 * C;
+      s += (double)p[c];
+      q += (double)p[C + c];
+    }
+    shd[(g * C + c) * 2] = s;
+    shd[(g * C + c) * 2 + 1] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    double ss = 0.0, qq = 0.0;
+    for (int gg = 0; gg < groups; ++gg) { ss += shd[(gg * C + threadIdx.x) * 2]; qq += shd[(gg * C + threadIdx.x) * 2 + 1]; }
+    double* o = part2 + (((size_t)b * nblk + blk) * C + threadIdx.x) * 2;
+    o[0] = ss;
+    o[1] = qq;
+  }
+}
+__global__ void k_in_slab_stage2(const double* __restrict__ part2, int nblk, int C, int HW, float eps, float* __restrict__ stats) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < nblk; ++k) {
+    const double* p = part2 + (((size_t)b * nblk + k) * C + c) * 2;
+    s += p[0];
+    q += p[1];
+  }
+  const double mean = s / HW;
+  const double var = fmax(q / HW - mean * mean, 0.0);
+  stats[((size_t)b * C + c) * 2] = (float)mean;
+  stats[((size_t)b * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+int instnorm_stats_from_slabs(const float* slab_part, int B, int slabs_per_image, int C, int HW, double* part2, float* stats,
+                              cudaStream_t s) {
+  const int threads = C <= 64 ? 4 * C : 2 * C, nblk = INSTNORM_STAGE1_BLOCKS;
+  k_in_slab_stage1<<<dim3(nblk, B), threads, threads * 2 * sizeof(double), s>>>(slab_part, slabs_per_image, C, part2);
+  k_in_slab_stage2<<<B, 128, 0, s>>>(part2, nblk, C, HW, 1e-5f, stats);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 int instnorm_partial_floats(int B, int HW, int C) { return B * ceil_div(HW, 512) * C * 2; }
 
 // out = relu( skip + relu(norm(x)) )   [skip optional: an fp16 padded map, or a raw fp32 dense map with its own stats]
 __global__ void k_in_apply(const float* __restrict__ x, const float* __restrict__ stats, int H, int W, int C,
                            const __half* __restrict__ skip_map, const float* __restrict__ skip_raw,
-                           const float* __restrict__ skip_stats, __half* __restrict__ out, int pad) {
+                           const float* __restrict__ skip_stats, __half* __restrict__ out, int pad, long long img_rows) {
   const int c4 = C >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per_img = (long long)H * W * c4;
@@ -110,8 +162,8 @@ __global__ void k_in_apply(const float* __restrict__ x, const float* __restrict_
   const int c = (int)(idx % c4) * 4;
   const int px = (int)((idx / c4) % W), py = (int)(idx / ((long long)c4 * W));
   const size_t dense = (((size_t)b * H + py) * W + px) * C + c;
-  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
-  const size_t padded = (((size_t)b * Hp + py + pad) * Wp + px + pad) * C + c;
+  const int Wp = W + pad;  // shared-border layout: zeros only after each row / image
+  const size_t padded = ((size_t)b * img_rows + (size_t)py * Wp + px) * C + c;
   const float4 v = *reinterpret_cast<const float4*>(x + dense);
   const float* st = stats + ((size_t)b * C + c) * 2;
   float y[4] = {fmaxf((v.x - st[0]) * st[1], 0.f), fmaxf((v.y - st[2]) * st[3], 0.f), fmaxf((v.z - st[4]) * st[5], 0.f),
@@ -130,10 +182,10 @@ __global__ void k_in_apply(const float* __restrict__ x, const float* __restrict_
   *reinterpret_cast<uint2*>(out + padded) = make_uint2(pack_half2(y[0], y[1]), pack_half2(y[2], y[3]));
 }
 int instnorm_apply(const float* x, const float* stats, int B, int H, int W, int C, const __half* skip_map,
-                   const float* skip_raw, const float* skip_stats, __half* out, int pad, cudaStream_t s) {
+                   const float* skip_raw, const float* skip_stats, __half* out, int pad, long long img_rows, cudaStream_t s) {
   const long long per_img = (long long)H * W * (C / 4);
   k_in_apply<<<dim3((unsigned)((per_img + 255) / 256), B), 256, 0, s>>>(x, stats, H, W, C, skip_map, skip_raw, skip_stats,
-                                                                       out, pad);
+                                                                       out, pad, img_rows);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -142,7 +194,7 @@ int instnorm_apply(const float* x, const float* stats, int B, int H, int W, int 
 // cnet output split (raft.py:113-116): net = tanh(cnet[:, :128]) -> h (fp32 master + fp16 operand), inp = relu(rest).
 // Destination: the GRU operand maps hx = [h | inp | motion] and rhx = [r*h | inp | motion], 384 channels, pad 2.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, int pad, float* __restrict__ h_master,
+__global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, int pad, long long img_rows, float* __restrict__ h_master,
                              __half* __restrict__ hx, __half* __restrict__ rhx) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W*256
   const long long total = (long long)B * H * W * 256;
@@ -152,8 +204,8 @@ __global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, 
   const int b = (int)(p / ((long long)H * W));
   const int r = (int)(p - (long long)b * H * W);
   const int y = r / W, x = r - y * W;
-  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
-  const size_t prow = ((size_t)b * Hp + y + pad) * Wp + x + pad;
+  const int Wp = W + pad;  // shared-border layout: zeros only after each row / image
+  const size_t prow = (size_t)b * img_rows + (size_t)y * Wp + x;
   const float v = cn[idx];
   if (c < 128) {
     const float t = tanhf(v);
@@ -165,10 +217,10 @@ __global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, 
     rhx[prow * 384 + c] = i;
   }
 }
-int raft_cnet_split(const float* cn, int B, int H, int W, int pad, float* h_master, __half* hx, __half* rhx,
+int raft_cnet_split(const float* cn, int B, int H, int W, int pad, long long img_rows, float* h_master, __half* hx, __half* rhx,
                     cudaStream_t s) {
   const long long total = (long long)B * H * W * 256;
-  k_cnet_split<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(cn, B, H, W, pad, h_master, hx, rhx);
+  k_cnet_split<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(cn, B, H, W, pad, img_rows, h_master, hx, rhx);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -179,25 +231,37 @@ int raft_cnet_split(const float* cn, int B, int H, int W, int pad, float* h_mast
 // a single fp16 would cost 8e-4 of the 1e-3 budget).  Row = pixel, K = [98 hi | 30 zero | 98 lo | 30 zero].
 __global__ void k_flow_im2col(const float* __restrict__ coords0, const float* __restrict__ coords1, int B, int H, int W,
                               __half* __restrict__ out) {
+  // one thread = 8 consecutive k of one pixel: two 16-byte stores (hi and lo halves); a warp covers two whole rows
   const int P = H * W;
-  const long long total = (long long)B * P * 128;
+  const long long total = (long long)B * P * 16;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i & 127);
-    const long long row = i >> 7;
+    const int g = (int)(i & 15);
+    const long long row = i >> 4;
     const int b = (int)(row / P), r = (int)(row - (long long)b * P);
-    float v = 0.f;
-    if (k < 98) {
-      const int y = r / W, x = r - y * W;
-      const int ch = k / 49, t = k - ch * 49, ky = t / 7, kx = t - ky * 7;
-      const int yy = y + ky - 3, xx = x + kx - 3;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        const size_t o = ((size_t)b * 2 + ch) * P + (size_t)yy * W + xx;
-        v = coords1[o] - coords0[o];
+    const int y = r / W, x = r - y * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      v[j] = 0.f;
+      if (k < 98) {
+        const int ch = k / 49, t = k - ch * 49, ky = t / 7, kx = t - ky * 7;
+        const int yy = y + ky - 3, xx = x + kx - 3;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const size_t o = ((size_t)b * 2 + ch) * P + (size_t)yy * W + xx;
+          v[j] = coords1[o] - coords0[o];
+        }
       }
     }
-    const __half hi = __float2half_rn(v);
-    out[row * 256 + k] = hi;
-    out[row * 256 + 128 + k] = __float2half_rn(v - __half2float(hi));
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half h0 = __float2half_rn(v[2 * j]), h1 = __float2half_rn(v[2 * j + 1]);
+      hi[j] = pack_half2(__half2float(h0), __half2float(h1));
+      lo[j] = pack_half2(v[2 * j] - __half2float(h0), v[2 * j + 1] - __half2float(h1));
+    }
+    *reinterpret_cast<uint4*>(out + row * 256 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out + row * 256 + 128 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 int raft_flow_im2col(const float* coords0, const float* coords1, int B, int H, int W, __half* out, cudaStream_t s) {
@@ -208,22 +272,23 @@ int raft_flow_im2col(const float* coords0, const float* coords1, int B, int H, i
 
 // motion features = cat([conv_out(126), flow(2)]) (update.py:97): the two flow channels of the GRU operand maps
 __global__ void k_flow_cols(const float* __restrict__ c0, const float* __restrict__ c1, int B, int H, int W, int pad,
-                            __half* __restrict__ hx, __half* __restrict__ rhx) {
+                            long long img_rows, __half* __restrict__ hx, __half* __restrict__ rhx) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int P = H * W;
   if (idx >= (long long)B * P) return;
   const int b = (int)(idx / P), r = (int)(idx - (long long)b * P);
   const int y = r / W, x = r - y * W;
-  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
-  const size_t prow = ((size_t)b * Hp + y + pad) * Wp + x + pad;
+  const int Wp = W + pad;  // shared-border layout: zeros only after each row / image
+  const size_t prow = (size_t)b * img_rows + (size_t)y * Wp + x;
   const float* a0 = c0 + (size_t)b * 2 * P;
   const float* a1 = c1 + (size_t)b * 2 * P;
   const uint32_t fl = pack_half2(a1[r] - a0[r], a1[(size_t)P + r] - a0[(size_t)P + r]);
   *reinterpret_cast<uint32_t*>(hx + prow * 384 + 382) = fl;
   *reinterpret_cast<uint32_t*>(rhx + prow * 384 + 382) = fl;
 }
-int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pad, __half* hx, __half* rhx, cudaStream_t s) {
-  k_flow_cols<<<(unsigned)(((long long)B * H * W + 255) / 256), 256, 0, s>>>(c0, c1, B, H, W, pad, hx, rhx);
+int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pad, long long img_rows, __half* hx, __half* rhx,
+                   cudaStream_t s) {
+  k_flow_cols<<<(unsigned)(((long long)B * H * W + 255) / 256), 256, 0, s>>>(c0, c1, B, H, W, pad, img_rows, hx, rhx);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -270,22 +335,75 @@ int raft_gru_update(const float* zr, const float* q, float* h_master, __half* hx
 }
 
 // coords1 += delta_flow (raft.py:133); delta: fp32 padded rows [rows][4] (cols 0,1 used)
-__global__ void k_coords_update(const float* __restrict__ delta, int B, int H, int W, int pad, float* __restrict__ coords1) {
+__global__ void k_coords_update(const float* __restrict__ delta, int B, int H, int W, int pad, long long img_rows,
+                                float* __restrict__ coords1) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int P = H * W;
   if (idx >= (long long)B * P) return;
   const int b = (int)(idx / P), r = (int)(idx - (long long)b * P);
   const int y = r / W, x = r - y * W;
-  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
-  const size_t prow = ((size_t)b * Hp + y + pad) * Wp + x + pad;
+  const int Wp = W + pad;  // shared-border layout: zeros only after each row / image
+  const size_t prow = (size_t)b * img_rows + (size_t)y * Wp + x;
   coords1[(size_t)b * 2 * P + r] += delta[prow * 4];
   coords1[(size_t)b * 2 * P + P + r] += delta[prow * 4 + 1];
 }
-int raft_coords_update(const float* delta, int B, int H, int W, int pad, float* coords1, cudaStream_t s) {
-  k_coords_update<<<(unsigned)(((long long)B * H * W + 255) / 256), 256, 0, s>>>(delta, B, H, W, pad, coords1);
+int raft_coords_update(const float* delta, int B, int H, int W, int pad, long long img_rows, float* coords1, cudaStream_t s) {
+  k_coords_update<<<(unsigned)(((long long)B * H * W + 255) / 256), 256, 0, s>>>(delta, B, H, W, pad, img_rows, coords1);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
+// ------------------------------------------------------------------------------------------------
+// FlowHead.conv2 (3x3, 256 -> 2, update.py:19-22) fused with coords1 += delta_flow (raft.py:133).
+// N = 2 is no tensor-core shape (the narrowest tcgen05 tile wastes 94 % of its columns and cost 38 us per iteration);
+// here one warp owns one pixel: every lane takes 8 of the 256 channels of each of the 9 taps (one 16-byte load per tap
+// from the shared-border fp16 map, whose trailing zeros are the conv's padding), multiplies by the FP32 weights
+// (shared memory, conflict-free float4 layout) and the two sums are reduced with shuffles.  The weights are not
+// rounded to fp16: their rounding is the largest single term of the flow error (oracle/tools/raft_precision_study.py).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_flow_head2(const __half* __restrict__ fh, int B, int H, int W, int pad, long long img_rows, const float* __restrict__ wsm,
+             float b0, float b1, float* __restrict__ coords1, float* __restrict__ delta_out) {
+  __shared__ float4 w[9 * 4 * 32];  // [tap][q][lane]: q = 0,1 -> channels 8*lane + 0..3 / 4..7 of output 0; q = 2,3 of output 1
+  for (int i = threadIdx.x; i < 9 * 4 * 32; i += blockDim.x) w[i] = reinterpret_cast<const float4*>(wsm)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int P = H * W, Wp = W + pad;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)B * P) return;
+  const int b = (int)(wid / P), r = (int)(wid - (long long)b * P);
+  const int y = r / W, x = r - y * W;
+  const long long row0 = (long long)b * img_rows + (long long)y * Wp + x;
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const long long row = row0 + (t / 3 - 1) * Wp + (t % 3 - 1);
+    if (row < 0) continue;  // above the first image (warp-uniform); every other out-of-image tap lands on stored zeros
+    const uint4 v = *reinterpret_cast<const uint4*>(fh + row * 256 + lane * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+    const float4 w00 = w[(t * 4 + 0) * 32 + lane], w01 = w[(t * 4 + 1) * 32 + lane];
+    const float4 w10 = w[(t * 4 + 2) * 32 + lane], w11 = w[(t * 4 + 3) * 32 + lane];
+    a0 = fmaf(f0.x, w00.x, a0); a0 = fmaf(f0.y, w00.y, a0); a0 = fmaf(f1.x, w00.z, a0); a0 = fmaf(f1.y, w00.w, a0);
+    a0 = fmaf(f2.x, w01.x, a0); a0 = fmaf(f2.y, w01.y, a0); a0 = fmaf(f3.x, w01.z, a0); a0 = fmaf(f3.y, w01.w, a0);
+    a1 = fmaf(f0.x, w10.x, a1); a1 = fmaf(f0.y, w10.y, a1); a1 = fmaf(f1.x, w10.z, a1); a1 = fmaf(f1.y, w10.w, a1);
+    a1 = fmaf(f2.x, w11.x, a1); a1 = fmaf(f2.y, w11.y, a1); a1 = fmaf(f3.x, w11.z, a1); a1 = fmaf(f3.y, w11.w, a1);
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1);
+  if (lane == 0) {
+    a0 += b0; a1 += b1;
+    coords1[(size_t)b * 2 * P + r] += a0;
+    coords1[(size_t)b * 2 * P + P + r] += a1;
+    if (delta_out) { delta_out[wid * 2] = a0; delta_out[wid * 2 + 1] = a1; }
+  }
+}
+int raft_flow_head2(const __half* fh, int B, int H, int W, int pad, long long img_rows, const float* w_packed, float b0, float b1,
+                    float* coords1, float* delta_out, cudaStream_t s) {
+  const long long warps = (long long)B * H * W;
+  k_flow_head2<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(fh, B, H, W, pad, img_rows, w_packed, b0, b1, coords1, delta_out);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 __global__ void k_coords_init(float* __restrict__ c0, float* __restrict__ c1, int B, int H, int W) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int P = H * W;
@@ -308,15 +426,15 @@ int raft_coords_init(float* c0, float* c1, int B, int H, int W, cudaStream_t s) 
 // neighbourhood = unfold(8*flow, 3x3, padding 1) (zero outside).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_convex_upsample(const float* __restrict__ mask, const float* __restrict__ c0,
-                                  const float* __restrict__ c1, int B, int H, int W, int pad, int Hs, int Ws, int pad_top,
-                                  int pad_left, float* __restrict__ out) {
+                                  const float* __restrict__ c1, int B, int H, int W, int pad, long long img_rows, int Hs,
+                                  int Ws, int pad_top, int pad_left, float* __restrict__ out) {
   const int b = blockIdx.y;
   const int r = blockIdx.x;  // coarse pixel
   const int y = r / W, x = r - y * W;
   const int sub = threadIdx.x;  // 0..63: a*8 + bcol
   const int P = H * W;
-  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
-  const float* m = mask + (((size_t)b * Hp + y + pad) * Wp + x + pad) * 576;
+  const int Wp = W + pad;  // shared-border layout: zeros only after each row / image
+  const float* m = mask + ((size_t)b * img_rows + (size_t)y * Wp + x) * 576;
   float w[9];
   float mx = -INFINITY;
 #pragma unroll
@@ -342,9 +460,9 @@ __global__ void k_convex_upsample(const float* __restrict__ mask, const float* _
     o[1] = fy;
   }
 }
-int raft_convex_upsample(const float* mask, const float* c0, const float* c1, int B, int H, int W, int pad, int Hs, int Ws,
-                         int pad_top, int pad_left, float* out, cudaStream_t s) {
-  k_convex_upsample<<<dim3(H * W, B), 64, 0, s>>>(mask, c0, c1, B, H, W, pad, Hs, Ws, pad_top, pad_left, out);
+int raft_convex_upsample(const float* mask, const float* c0, const float* c1, int B, int H, int W, int pad, long long img_rows,
+                         int Hs, int Ws, int pad_top, int pad_left, float* out, cudaStream_t s) {
+  k_convex_upsample<<<dim3(H * W, B), 64, 0, s>>>(mask, c0, c1, B, H, W, pad, img_rows, Hs, Ws, pad_top, pad_left, out);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -7,3 +7,5 @@ from prisma_b200.synthetic import synthetic_frame
 eng = RaftFlowEngine(make_raft_weights(0), iterations=12)
 f0, f1 = synthetic_frame(1080, 1920, 0), synthetic_frame(1080, 1920, 1)
 eng.infer_pair(f0, f1); eng.infer_pair(f0, f1)
+print("---- video pass (reuse_prev)")
+eng.infer_pair(f0, f1, reuse_prev=True)
