@@ -181,7 +181,7 @@ long long prisma_mask_read_tap(prisma_engine* e, const char* name, float* out, l
 int prisma_mask_work(prisma_engine* e, int h, int w, double* out8);
 
 /* Size of the resized (un-padded) network input each band's transform produces for a w x h frame: depth_anything
- * (d_anything/util/transform.py:111-166 lower_bound x14), depth_midas (minimal x32), depth_anything_metric (392 x 518),
+ * (d_anything/util/transform.py:111-166 lower_bound x14), depth_midas (upper_bound x32: fits 384 x 384), depth_anything_metric (392 x 518),
  * mask_mmdet (mmcv.imrescale (1333, 800)).  Pure host arithmetic, usable without a GPU.                              */
 int prisma_net_size(const char* band, int w, int h, int* wn, int* hn);
 

@@ -27,23 +27,31 @@ from .weights import MIDAS_CONFIGS
 
 
 def midas_get_size(width, height, target=384, multiple=32):
-    """Resize.get_size with resize_method="minimal", keep_aspect_ratio=True (d_anything/util/transform.py:111-166)."""
+    """Resize.get_size with resize_method="upper_bound", keep_aspect_ratio=True (the Resize class of midas/transforms.py is
+    the one vendored at d_anything/util/transform.py:111-166; constrain_to_multiple_of :98-109 with max_val = target)."""
     scale_h, scale_w = target / height, target / width
-    if abs(1 - scale_w) < abs(1 - scale_h):
+    if scale_w < scale_h:
         scale_h = scale_w
     else:
         scale_w = scale_h
-    c = lambda x: int(np.round(x / multiple) * multiple)
+
+    def c(x):
+        y = int(np.round(x / multiple) * multiple)
+        if y > target:
+            y = int(np.floor(x / multiple) * multiple)
+        return y
     return c(scale_w * width), c(scale_h * height)
 
 
 def midas_preprocess(img_u8):
-    """hubconf.transforms().default_transform: /255 (f64), Resize(384, 384, keep AR, x32, "minimal", INTER_CUBIC),
-    NormalizeImage(mean = std = 0.5), PrepareForNet (CHW f32)."""
+    """hubconf.transforms().default_transform -- what bands/depth_midas.py:37-40 selects for "midas3" (DPT_Large): /255 (f64),
+    Resize(384, 384, keep AR, x32, "upper_bound", INTER_CUBIC), NormalizeImage(ImageNet mean / std), PrepareForNet (CHW f32).
+    (Upstream's README pairs DPT models with dpt_transform ("minimal", mean = std = 0.5); the reference band does not, and the
+    engine mirrors the band.  The hub code is not vendored: this is restated from the published intel-isl/MiDaS hubconf.py.)"""
     image = img_u8 / 255.0
     w, h = midas_get_size(image.shape[1], image.shape[0])
     image = cv2.resize(image, (w, h), interpolation=cv2.INTER_CUBIC)
-    image = (image - 0.5) / 0.5
+    image = (image - np.array([0.485, 0.456, 0.406])) / np.array([0.229, 0.224, 0.225])
     return np.ascontiguousarray(np.transpose(image, (2, 0, 1))).astype(np.float32)
 
 

@@ -45,13 +45,19 @@ void da_net_size(int W, int H, int* wn, int* hn) {
   *wn = constrain(sw * W);
 }
 
-// MiDaS transform (hubconf default_transform; the Resize class is the one vendored in d_anything/util/transform.py:
-// get_size :111-166 with resize_method="minimal", keep_aspect_ratio, multiple of 32, target 384 x 384).
+// MiDaS transform = hubconf default_transform, which bands/depth_midas.py:37-40 selects for DPT_Large: the Resize class
+// vendored in d_anything/util/transform.py (get_size :111-166, constrain_to_multiple_of :98-109) with
+// resize_method="upper_bound", keep_aspect_ratio, multiple of 32, target 384 x 384: the frame is scaled to FIT 384 x 384.
 void midas_net_size(int W, int H, int* wn, int* hn) {
   double sh = 384.0 / H, sw = 384.0 / W;
-  if (fabs(1.0 - sw) < fabs(1.0 - sh)) sh = sw; else sw = sh;
-  *hn = (int)(nearbyint(sh * H / 32.0) * 32.0);
-  *wn = (int)(nearbyint(sw * W / 32.0) * 32.0);
+  if (sw < sh) sh = sw; else sw = sh;
+  auto constrain = [](double x) {
+    int y = (int)(nearbyint(x / 32.0) * 32.0);   // np.round: half to even, as nearbyint
+    if (y > 384) y = (int)(floor(x / 32.0) * 32.0);
+    return y;
+  };
+  *hn = constrain(sh * H);
+  *wn = constrain(sw * W);
 }
 
 DepthEngine::~DepthEngine() {

@@ -73,8 +73,9 @@ int da_preprocess(const uint8_t* img, int H, int W, float* out, int h, int w, cu
   // cv::resize: inv_scale = dsize/ssize ; scale = 1./inv_scale
   const double scale_x = 1.0 / ((double)w / (double)W);
   const double scale_y = 1.0 / ((double)h / (double)H);
-  // NormalizeImage: ImageNet statistics (depth_anything.py:72) or mean = std = 0.5 (MiDaS hubconf default_transform)
-  const MeanStd ms = midas_norm ? MeanStd{{0.5, 0.5, 0.5}, {0.5, 0.5, 0.5}} : MeanStd{{0.485, 0.456, 0.406}, {0.229, 0.224, 0.225}};
+  // NormalizeImage: ImageNet statistics, for Depth-Anything (depth_anything.py:72) and for the hubconf default_transform the
+  // MiDaS band selects (depth_midas.py:37-40); midas_norm == 2 would be upstream's dpt_transform (mean = std = 0.5), unused
+  const MeanStd ms = midas_norm == 2 ? MeanStd{{0.5, 0.5, 0.5}, {0.5, 0.5, 0.5}} : MeanStd{{0.485, 0.456, 0.406}, {0.229, 0.224, 0.225}};
   k_da_preprocess<<<grid, block, 0, s>>>(img, H, W, out, h, w, scale_x, scale_y, ms);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;

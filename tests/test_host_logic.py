@@ -33,7 +33,7 @@ def test_survey_sizes():
     for w, h in ((1280, 720), (1920, 1080)):
         assert net_size("depth_anything", w, h) == (924, 518)
         assert net_size("mask_mmdet", w, h) == (1333, 750)
-    assert net_size("depth_anything", 640, 480) == (686, 518) and net_size("depth_midas", 640, 480) == (512, 384)
+    assert net_size("depth_anything", 640, 480) == (686, 518) and net_size("depth_midas", 640, 480) == (384, 288)
 
 
 def test_flo_writer_and_metadata_roundtrip(tmp_path):

@@ -14,10 +14,10 @@ from oracle.weights import make_midas_weights
 
 
 def test_midas_size_arithmetic_and_pos_embed():
-    # hubconf default_transform on the reference's config-1 frame: 640x480 -> 512x384
-    assert om.midas_get_size(640, 480) == (512, 384)
-    assert om.midas_get_size(1280, 720) == (672, 384) and om.midas_get_size(1920, 1080) == (672, 384)
-    assert om.midas_get_size(480, 640) == (384, 512)
+    # hubconf default_transform ("upper_bound": fit inside 384 x 384, multiples of 32) on the reference's config-1 frame
+    assert om.midas_get_size(640, 480) == (384, 288)
+    assert om.midas_get_size(1280, 720) == (384, 224) and om.midas_get_size(1920, 1080) == (384, 224)
+    assert om.midas_get_size(480, 640) == (288, 384) and om.midas_get_size(1000, 1000) == (384, 384)
     pos = torch.randn(1, 577, 8)
     assert torch.equal(om._resize_pos_embed(pos, 24, 24), pos)  # native grid: identity
 
