@@ -90,21 +90,24 @@ const HostTensor* RaftEngine::get(const std::string& name) {
 
 // conv weight [Cout][Cin][kh][kw] (+bias) -> fp16 [round_up(Npad,256)][taps*kc*64], fp32 bias [Npad]; optional eval-mode
 // BatchNorm folding (y = (conv(x) - mean) * gamma / sqrt(var + eps) + beta, eps = 1e-5) and output scale.
-int RaftEngine::up_conv(const std::string& name, const std::string& bn, int Cout, int Cin, int kh, int kw, int Npad,
-                        float out_scale, ConvW* out, int wsplit) {
+// chans: use only these input channels, in this order (the packed conv then has cin = chans->size()); with_bias = false drops
+// the bias (when one conv is evaluated as the sum of two convs over disjoint channel sets, only one of them carries it).
+int RaftEngine::up_conv(const std::string& name, const std::string& bn, int Cout, int CinSrc, int kh, int kw, int Npad,
+                        float out_scale, ConvW* out, int wsplit, const std::vector<int>* chans, bool with_bias) {
   const HostTensor* w = get(name + ".weight");
   const HostTensor* b = get(name + ".bias");
   if (!w || !b) return -1;
-  PRISMA_CHECK((long long)w->data.size() == (long long)Cout * Cin * kh * kw, "RAFT weight '" + name + "' has an unexpected size");
+  PRISMA_CHECK((long long)w->data.size() == (long long)Cout * CinSrc * kh * kw, "RAFT weight '" + name + "' has an unexpected size");
+  const int Cin = chans ? (int)chans->size() : CinSrc;
   std::vector<float> sc(Cout, out_scale), sh(Cout, 0.f);
-  for (int n = 0; n < Cout; ++n) sh[n] = b->data[n] * out_scale;
+  for (int n = 0; n < Cout; ++n) sh[n] = with_bias ? b->data[n] * out_scale : 0.f;
   if (!bn.empty()) {
     const HostTensor *g = get(bn + ".weight"), *be = get(bn + ".bias"), *mu = get(bn + ".running_mean"), *var = get(bn + ".running_var");
     if (!g || !be || !mu || !var) return -1;
     for (int n = 0; n < Cout; ++n) {
       const float k = g->data[n] / sqrtf(var->data[n] + 1e-5f);
       sc[n] = k;
-      sh[n] = (b->data[n] - mu->data[n]) * k + be->data[n];
+      sh[n] = ((with_bias ? b->data[n] : 0.f) - mu->data[n]) * k + be->data[n];
     }
   }
   // wsplit == 2: the weights keep ~22 bits as an fp16 pair.  Weight rounding is a SYSTEMATIC error (the same perturbed
@@ -115,7 +118,7 @@ int RaftEngine::up_conv(const std::string& name, const std::string& bn, int Cout
   for (int n = 0; n < Cout; ++n)
     for (int t = 0; t < taps; ++t)
       for (int c = 0; c < Cin; ++c) {
-        const float v = w->data[((size_t)n * Cin + c) * taps + t] * sc[n];
+        const float v = w->data[((size_t)n * CinSrc + (chans ? (*chans)[c] : c)) * taps + t] * sc[n];
         const __half hi = __float2half_rn(v);
         h[(size_t)n * K + (size_t)t * wsplit * kc * 64 + c] = hi;
         if (wsplit == 2) h[(size_t)n * K + (size_t)(t * 2 + 1) * kc * 64 + c] = __float2half_rn(v - __half2float(hi));
@@ -197,25 +200,33 @@ int RaftEngine::finalize() {
     bzr.data = bz->data; bzr.data.insert(bzr.data.end(), br->data.begin(), br->data.end());
     host[u + "gru.zr" + s + ".weight"] = wzr;
     host[u + "gru.zr" + s + ".bias"] = bzr;
-    PRISMA_TRY(up_conv(u + "gru.zr" + s, "", 256, 384, kh, kw, 256, 1.f, &w.zr[pass]));
-    PRISMA_TRY(up_conv(u + "gru.convq" + s, "", 128, 384, kh, kw, 128, 1.f, &w.q[pass]));
+    // conv(cat[h, inp, motion]) = conv_{h,motion}(...) + conv_inp(inp): `inp` = relu(cnet[128:]) does not change over the
+    // iterations (raft.py:113-116), so its third of every GRU conv is evaluated once per pass and enters the per-iteration
+    // conv as a pre-activation term (GemmEpilogue::pre_f32).  Operand maps are laid out [h | motion | inp] accordingly.
+    std::vector<int> ch_iter, ch_inp;
+    for (int c = 0; c < 128; ++c) ch_iter.push_back(c);
+    for (int c = 256; c < 384; ++c) ch_iter.push_back(c);
+    for (int c = 128; c < 256; ++c) ch_inp.push_back(c);
+    PRISMA_TRY(up_conv(u + "gru.zr" + s, "", 256, 384, kh, kw, 256, 1.f, &w.zr[pass], 1, &ch_iter));
+    PRISMA_TRY(up_conv(u + "gru.convq" + s, "", 128, 384, kh, kw, 128, 1.f, &w.q[pass], 1, &ch_iter));
+    PRISMA_TRY(up_conv(u + "gru.zr" + s, "", 256, 384, kh, kw, 256, 1.f, &w.zr_inp[pass], 1, &ch_inp, false));
+    PRISMA_TRY(up_conv(u + "gru.convq" + s, "", 128, 384, kh, kw, 128, 1.f, &w.q_inp[pass], 1, &ch_inp, false));
   }
   PRISMA_TRY(up_conv(u + "flow_head.conv1", "", 256, 128, 3, 3, 256, 1.f, &w.fh1, 2));  // hi/lo weights: the largest error term
-  {  // FlowHead.conv2 (256 -> 2) stays fp32 and runs on the CUDA cores (k_flow_head2): [tap][q][lane][4]
+  {  // FlowHead.conv2 (3x3, 256 -> 2) as a 1x1 conv to 18 partial products u[tap*2 + out] (see k_flow_head2_gather)
     const HostTensor* wt = get(u + "flow_head.conv2.weight");
     const HostTensor* bs = get(u + "flow_head.conv2.bias");
     if (!wt || !bs) return -1;
     PRISMA_CHECK(wt->data.size() == (size_t)2 * 256 * 9 && bs->data.size() == 2, "RAFT flow_head.conv2 has an unexpected size");
-    std::vector<float> pk((size_t)9 * 4 * 32 * 4);
+    HostTensor wu, bu;
+    wu.data.assign((size_t)18 * 256, 0.f);
     for (int t = 0; t < 9; ++t)
-      for (int q = 0; q < 4; ++q)
-        for (int lane = 0; lane < 32; ++lane)
-          for (int j = 0; j < 4; ++j) {
-            const int o = q >> 1, ch = lane * 8 + (q & 1) * 4 + j;
-            pk[(((size_t)t * 4 + q) * 32 + lane) * 4 + j] = wt->data[((size_t)o * 256 + ch) * 9 + t];
-          }
-    PRISMA_TRY(r_alloc(allocs, &w.fh2_w, pk.size()));
-    PRISMA_CUDA_OK(cudaMemcpy(w.fh2_w, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+      for (int o = 0; o < 2; ++o)
+        for (int c = 0; c < 256; ++c) wu.data[((size_t)(t * 2 + o)) * 256 + c] = wt->data[((size_t)o * 256 + c) * 9 + t];
+    bu.data.assign(18, 0.f);
+    host[u + "flow_head.conv2_u.weight"] = wu;
+    host[u + "flow_head.conv2_u.bias"] = bu;
+    PRISMA_TRY(up_conv(u + "flow_head.conv2_u", "", 18, 256, 1, 1, 32, 1.f, &w.fh2u, 2));  // hi/lo weights: exact to ~22 bits
     w.fh2_b[0] = bs->data[0]; w.fh2_b[1] = bs->data[1];
   }
   PRISMA_TRY(up_conv(u + "mask.0", "", 256, 128, 3, 3, 256, 1.f, &w.mk1));
@@ -489,6 +500,16 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
     add("cnet_split", [=](cudaStream_t s) { return raft_cnet_split(cn, 2, h8, w8, 2, ir8, hm, hxp, rhp, s); });
     add("coords_init", [=](cudaStream_t s) { return raft_coords_init(c0, c1p, 2, h8, w8, s); });
   }
+  // the `inp` third of the four GRU convs, once per pass (fp32, padded-row layout like the gates)
+  float *zr_pre[2] = {nullptr, nullptr}, *q_pre[2] = {nullptr, nullptr};
+  for (int pass = 0; pass < 2; ++pass) {
+    PRISMA_TRY(r_alloc(plan_allocs, &zr_pre[pass], (size_t)hx.rows() * 256));
+    PRISMA_TRY(r_alloc(plan_allocs, &q_pre[pass], (size_t)hx.rows() * 128));
+    { GemmEpilogue ep; ep.out_f32 = zr_pre[pass]; ep.out_f32_ld = 256;
+      PRISMA_TRY(add_conv("gru_inp", hx, 256, w.zr_inp[pass], ep, 1)); }
+    { GemmEpilogue ep; ep.out_f32 = q_pre[pass]; ep.out_f32_ld = 128;
+      PRISMA_TRY(add_conv("gru_inp", hx, 256, w.q_inp[pass], ep, 1)); }
+  }
   // ---- update block, `iters` times (raft.py:123-141)
   PRISMA_TRY(new_map(&corrf, B, H8, W8, 384, 2));
   PRISMA_TRY(new_map(&c1, B, H8, W8, 256, 2));
@@ -500,6 +521,8 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   PRISMA_TRY(r_alloc(plan_allocs, &zr_f, (size_t)hx.rows() * 256));
   PRISMA_TRY(r_alloc(plan_allocs, &q_f, (size_t)hx.rows() * 128));
   PRISMA_TRY(new_map(&fh, B, H8, W8, 256, 2));
+  float* fh2_u = nullptr;
+  PRISMA_TRY(r_alloc(plan_allocs, &fh2_u, (size_t)hx.rows() * 32));
   PRISMA_TRY(new_map(&mk, B, H8, W8, 256, 2));
   PRISMA_TRY(r_alloc(plan_allocs, &b.mask, (size_t)hx.rows() * 576));
   const long long rows = hx.rows();
@@ -529,18 +552,18 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
       PRISMA_TRY(add_conv("convf2", f1, 0, w.convf2, ep, 1)); }
     { // conv 3x3 256 -> 126 (+2 zero channels); the 126 motion channels go to cols 256..381 of hx and rhx; the two
       // trailing columns are rewritten with the flow by flow_cols every iteration -- so restore them here
-      GemmEpilogue ep; ep.act = 2; ep.out_f16 = hx.p + 256; ep.out_f16_ld = 384; ep.out_f16_relu = rhx.p + 256; ep.out_f16_relu_ld = 384;
+      GemmEpilogue ep; ep.act = 2; ep.out_f16 = hx.p + 128; ep.out_f16_ld = 384; ep.out_f16_relu = rhx.p + 128; ep.out_f16_relu_ld = 384;
       PRISMA_TRY(add_conv("motion_conv", c2, 0, w.conv, ep, 1));
       const float* c0 = b.coords0; const float* c1p = b.coords1; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
       const long long ir8 = hx.img_rows();
       add("flow_cols", [=](cudaStream_t s) { return raft_flow_cols(c0, c1p, 2, h8, w8, 2, ir8, hxp, rhp, s); });
     }
     for (int pass = 0; pass < 2; ++pass) {  // SepConvGRU horizontal then vertical (update.py:45-60)
-      { GemmEpilogue ep; ep.act = 3; ep.out_f32 = zr_f; ep.out_f32_ld = 256;
+      { GemmEpilogue ep; ep.act = 3; ep.out_f32 = zr_f; ep.out_f32_ld = 256; ep.pre_f32 = zr_pre[pass]; ep.pre_f32_ld = 256;
         PRISMA_TRY(add_conv("gru_zr", hx, 0, w.zr[pass], ep, 1)); }
       { const float* z = zr_f; const float* hm = b.h_master; __half* rhp = rhx.p;
         add("gru_rh", [=](cudaStream_t s) { return raft_gru_rh(z, hm, rhp, rows, s); }); }
-      { GemmEpilogue ep; ep.act = 4; ep.out_f32 = q_f; ep.out_f32_ld = 128;
+      { GemmEpilogue ep; ep.act = 4; ep.out_f32 = q_f; ep.out_f32_ld = 128; ep.pre_f32 = q_pre[pass]; ep.pre_f32_ld = 128;
         PRISMA_TRY(add_conv("gru_q", rhx, 0, w.q[pass], ep, 1)); }
       { const float* z = zr_f; const float* qq = q_f; float* hm = b.h_master; __half* hxp = hx.p;
         add("gru_update", [=](cudaStream_t s) { return raft_gru_update(z, qq, hm, hxp, rows, s); }); }
@@ -548,11 +571,12 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
     { GemmEpilogue ep; ep.act = 2; ep.out_f16 = fh.p; ep.out_f16_ld = 256;            // flow head
       ConvW cw = w.fh1;
       PRISMA_TRY(add_conv("flow_head1", hx, 0, cw, ep, 1)); }
-    { // flow_head.conv2 (fp32 weights, CUDA cores) + coords1 += delta (raft.py:133) in one kernel
-      const __half* fhp = fh.p; const float* wp2 = w.fh2_w; const float b0 = w.fh2_b[0], b1 = w.fh2_b[1]; float* c1p = b.coords1;
+    { // flow_head.conv2: 1x1 GEMM to the 18 per-tap partial products, then the nine-tap gather + coords1 += delta (raft.py:133)
+      GemmEpilogue ep; ep.out_f32 = fh2_u; ep.out_f32_ld = 32;
+      PRISMA_TRY(add_conv("flow_head2", fh, 0, w.fh2u, ep, 1));
+      const float* up = fh2_u; const float b0 = w.fh2_b[0], b1 = w.fh2_b[1]; float* c1p = b.coords1;
       const int h8 = H8, w8 = W8; const long long ir8 = fh.img_rows();
-      flops += 2.0 * 2 * H8 * (double)W8 * 9 * 256 * 2;
-      add("flow_head2", [=](cudaStream_t s) { return raft_flow_head2(fhp, 2, h8, w8, 2, ir8, wp2, b0, b1, c1p, nullptr, s); }); }
+      add("coords_update", [=](cudaStream_t s) { return raft_flow_head2_gather(up, 2, h8, w8, 2, ir8, b0, b1, c1p, s); }); }
     if (debug_taps && it == 0) {
       PRISMA_TRY(r_alloc(plan_allocs, &b.h_tap, (size_t)hx.rows() * 128));
       PRISMA_TRY(r_alloc(plan_allocs, &b.coords_tap, (size_t)B * 2 * P));
@@ -808,9 +832,9 @@ int RaftEngine::profile(int H, int W, double scale, int iters_, float* out8) {
     else if (n == "corr_lookup") g = 3;
     else if (n.rfind("instnorm", 0) == 0) g = 4;
     else if (n == "convex_upsample" || n == "flow_encode") g = 6;
-    else if (n == "convf1_im2col" || n == "flow_head2") g = 5;
+    else if (n == "convf1_im2col") g = 5;
     else if (n == "stem_gemm" || n == "convf1_gemm" || n.rfind("res_", 0) == 0 || n.rfind("conv", 0) == 0 || n == "fnet_out" ||
-             n == "cnet_out" || n == "motion_conv" || n.rfind("gru_zr", 0) == 0 || n == "gru_q" || n == "flow_head1" ||
+             n == "cnet_out" || n == "motion_conv" || n.rfind("gru_zr", 0) == 0 || n == "gru_q" || n == "gru_inp" || n.rfind("flow_head", 0) == 0 ||
              n.rfind("mask_head", 0) == 0) g = 1;
     out8[g] += t; out8[7] += t;
   }

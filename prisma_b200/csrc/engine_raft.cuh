@@ -18,8 +18,9 @@ struct EncW { ConvW stem; ResW blk[3][2]; ConvW out; };
 struct RaftWeights {
   EncW fnet, cnet;
   ConvW convc1, convc2, convf2, conv, zr[2], q[2], fh1, fh2, mk1, mk2;
+  ConvW zr_inp[2], q_inp[2];  // the `inp` (context) input channels of the GRU convs: constant over the iterations, applied once per pass
   float *convf1_w = nullptr, *convf1_b = nullptr;
-  float* fh2_w = nullptr; float fh2_b[2] = {0.f, 0.f};  // FlowHead.conv2 in fp32, packed for k_flow_head2
+  ConvW fh2u; float fh2_b[2] = {0.f, 0.f};  // FlowHead.conv2 as a 1x1 conv to 18 per-tap partial products (hi/lo weights)
   __half* convf1_gemm_w = nullptr;  // [256][256]: k = [98 weights | 0 | the same 98 (for the fp16 'lo' half of the flow) | 0]
 };
 struct RaftBuffers {
@@ -60,7 +61,7 @@ class RaftEngine {
  private:
   const HostTensor* get(const std::string& name);
   int up_conv(const std::string& name, const std::string& bn, int Cout, int Cin, int kh, int kw, int Npad, float out_scale,
-              ConvW* out, int wsplit = 1);
+              ConvW* out, int wsplit = 1, const std::vector<int>* chans = nullptr, bool with_bias = true);
   int up_encoder(const std::string& prefix, bool bn, EncW* e);
   int new_map(RMap* m, int B, int H, int W, int C, int pad);
   void add(const char* name, std::function<int(cudaStream_t)> fn);

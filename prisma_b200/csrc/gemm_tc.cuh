@@ -41,6 +41,8 @@ struct GemmEpilogue {
   const float* bias = nullptr;   // [N]
   const float* gamma = nullptr;  // [N]  LayerScale
   int act = 0;                   // 0 none, 1 exact-erf GELU, 2 ReLU, 3 sigmoid, 4 tanh
+  const float* pre_f32 = nullptr;  // + a per-element fp32 term BEFORE the activation, indexed by dst row (e.g. the part of a
+  int pre_f32_ld = 0;              //   conv over concatenated inputs that does not change between iterations)
   const float* res_f32 = nullptr;  // + residual (fp32), indexed by dst row
   int res_f32_ld = 0;
   const __half* res_a = nullptr;  // + residual (fp16), indexed by dst row
@@ -137,6 +139,15 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   for (int i = 0; i < 8; ++i) {
     v[i].x = fmaf(v[i].x, ep.alpha, bias.x); v[i].y = fmaf(v[i].y, ep.alpha, bias.y);
     v[i].z = fmaf(v[i].z, ep.alpha, bias.z); v[i].w = fmaf(v[i].w, ep.alpha, bias.w);
+  }
+  if (ep.pre_f32) {
+    float4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      t[i] = (okm >> i) & 1 ? *reinterpret_cast<const float4*>(ep.pre_f32 + (size_t)dr[i] * ep.pre_f32_ld + col)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i].x += t[i].x; v[i].y += t[i].y; v[i].z += t[i].z; v[i].w += t[i].w; }
   }
   if (ep.act == 1) {
 #pragma unroll

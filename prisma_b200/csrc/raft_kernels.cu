@@ -192,7 +192,8 @@ int instnorm_apply(const float* x, const float* stats, int B, int H, int W, int 
 
 // ------------------------------------------------------------------------------------------------
 // cnet output split (raft.py:113-116): net = tanh(cnet[:, :128]) -> h (fp32 master + fp16 operand), inp = relu(rest).
-// Destination: the GRU operand maps hx = [h | inp | motion] and rhx = [r*h | inp | motion], 384 channels, pad 2.
+// Destination: the GRU operand maps hx = [h | motion | inp] and rhx = [r*h | motion | inp], 384 channels, pad 2 (inp last:
+// the per-iteration convs read the first 256 channels, the once-per-pass `inp` convs the last 128).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, int pad, long long img_rows, float* __restrict__ h_master,
                              __half* __restrict__ hx, __half* __restrict__ rhx) {
@@ -213,8 +214,8 @@ __global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, 
     hx[prow * 384 + c] = __float2half_rn(t);
   } else {
     const __half i = __float2half_rn(fmaxf(v, 0.f));
-    hx[prow * 384 + c] = i;
-    rhx[prow * 384 + c] = i;
+    hx[prow * 384 + 128 + c] = i;   // inp occupies channels 256..383
+    rhx[prow * 384 + 128 + c] = i;
   }
 }
 int raft_cnet_split(const float* cn, int B, int H, int W, int pad, long long img_rows, float* h_master, __half* hx, __half* rhx,
@@ -283,8 +284,8 @@ __global__ void k_flow_cols(const float* __restrict__ c0, const float* __restric
   const float* a0 = c0 + (size_t)b * 2 * P;
   const float* a1 = c1 + (size_t)b * 2 * P;
   const uint32_t fl = pack_half2(a1[r] - a0[r], a1[(size_t)P + r] - a0[(size_t)P + r]);
-  *reinterpret_cast<uint32_t*>(hx + prow * 384 + 382) = fl;
-  *reinterpret_cast<uint32_t*>(rhx + prow * 384 + 382) = fl;
+  *reinterpret_cast<uint32_t*>(hx + prow * 384 + 254) = fl;   // motion = channels 128..255, its last two are the flow
+  *reinterpret_cast<uint32_t*>(rhx + prow * 384 + 254) = fl;
 }
 int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pad, long long img_rows, __half* hx, __half* rhx,
                    cudaStream_t s) {
@@ -353,53 +354,35 @@ int raft_coords_update(const float* delta, int B, int H, int W, int pad, long lo
   return 0;
 }
 // ------------------------------------------------------------------------------------------------
-// FlowHead.conv2 (3x3, 256 -> 2, update.py:19-22) fused with coords1 += delta_flow (raft.py:133).
-// N = 2 is no tensor-core shape (the narrowest tcgen05 tile wastes 94 % of its columns and cost 38 us per iteration);
-// here one warp owns one pixel: every lane takes 8 of the 256 channels of each of the 9 taps (one 16-byte load per tap
-// from the shared-border fp16 map, whose trailing zeros are the conv's padding), multiplies by the FP32 weights
-// (shared memory, conflict-free float4 layout) and the two sums are reduced with shuffles.  The weights are not
-// rounded to fp16: their rounding is the largest single term of the flow error (oracle/tools/raft_precision_study.py).
+// FlowHead.conv2 (3x3, 256 -> 2, update.py:19-22) + coords1 += delta_flow (raft.py:133).
+// A 3x3 conv with two output channels is no tensor-core shape as such (the narrowest tile wastes 94 % of its columns and
+// re-reads the 256-channel map nine times).  It is evaluated as  delta(p) = b + sum_t u_t(p + t),  u_t = W2[t] . x :
+// the 18 per-tap, per-output partial products u are ONE 1x1 GEMM (N = 18 -> 32, K = 256 read once, hi/lo fp16 weights =
+// exact fp32 weights), and this kernel adds the nine shifted taps per pixel and moves the coordinates.
+// u: fp32 [rows][32] in the shared-border row layout (pad rows are zero = the conv's zero padding), column t*2 + o.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_flow_head2(const __half* __restrict__ fh, int B, int H, int W, int pad, long long img_rows, const float* __restrict__ wsm,
-             float b0, float b1, float* __restrict__ coords1, float* __restrict__ delta_out) {
-  __shared__ float4 w[9 * 4 * 32];  // [tap][q][lane]: q = 0,1 -> channels 8*lane + 0..3 / 4..7 of output 0; q = 2,3 of output 1
-  for (int i = threadIdx.x; i < 9 * 4 * 32; i += blockDim.x) w[i] = reinterpret_cast<const float4*>(wsm)[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
+__global__ void k_flow_head2_gather(const float* __restrict__ u, int B, int H, int W, int pad, long long img_rows, float b0,
+                                    float b1, float* __restrict__ coords1) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int P = H * W, Wp = W + pad;
-  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wid >= (long long)B * P) return;
-  const int b = (int)(wid / P), r = (int)(wid - (long long)b * P);
+  if (idx >= (long long)B * P) return;
+  const int b = (int)(idx / P), r = (int)(idx - (long long)b * P);
   const int y = r / W, x = r - y * W;
   const long long row0 = (long long)b * img_rows + (long long)y * Wp + x;
-  float a0 = 0.f, a1 = 0.f;
+  float a0 = b0, a1 = b1;
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const long long row = row0 + (t / 3 - 1) * Wp + (t % 3 - 1);
-    if (row < 0) continue;  // above the first image (warp-uniform); every other out-of-image tap lands on stored zeros
-    const uint4 v = *reinterpret_cast<const uint4*>(fh + row * 256 + lane * 8);
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
-    const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-    const float4 w00 = w[(t * 4 + 0) * 32 + lane], w01 = w[(t * 4 + 1) * 32 + lane];
-    const float4 w10 = w[(t * 4 + 2) * 32 + lane], w11 = w[(t * 4 + 3) * 32 + lane];
-    a0 = fmaf(f0.x, w00.x, a0); a0 = fmaf(f0.y, w00.y, a0); a0 = fmaf(f1.x, w00.z, a0); a0 = fmaf(f1.y, w00.w, a0);
-    a0 = fmaf(f2.x, w01.x, a0); a0 = fmaf(f2.y, w01.y, a0); a0 = fmaf(f3.x, w01.z, a0); a0 = fmaf(f3.y, w01.w, a0);
-    a1 = fmaf(f0.x, w10.x, a1); a1 = fmaf(f0.y, w10.y, a1); a1 = fmaf(f1.x, w10.z, a1); a1 = fmaf(f1.y, w10.w, a1);
-    a1 = fmaf(f2.x, w11.x, a1); a1 = fmaf(f2.y, w11.y, a1); a1 = fmaf(f3.x, w11.z, a1); a1 = fmaf(f3.y, w11.w, a1);
+    if (row < 0) continue;  // above the first image; every other out-of-image tap reads stored zeros
+    const float2 v = *reinterpret_cast<const float2*>(u + row * 32 + t * 2);
+    a0 += v.x; a1 += v.y;
   }
-  a0 = warp_sum(a0); a1 = warp_sum(a1);
-  if (lane == 0) {
-    a0 += b0; a1 += b1;
-    coords1[(size_t)b * 2 * P + r] += a0;
-    coords1[(size_t)b * 2 * P + P + r] += a1;
-    if (delta_out) { delta_out[wid * 2] = a0; delta_out[wid * 2 + 1] = a1; }
-  }
+  coords1[(size_t)b * 2 * P + r] += a0;
+  coords1[(size_t)b * 2 * P + P + r] += a1;
 }
-int raft_flow_head2(const __half* fh, int B, int H, int W, int pad, long long img_rows, const float* w_packed, float b0, float b1,
-                    float* coords1, float* delta_out, cudaStream_t s) {
-  const long long warps = (long long)B * H * W;
-  k_flow_head2<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(fh, B, H, W, pad, img_rows, w_packed, b0, b1, coords1, delta_out);
+int raft_flow_head2_gather(const float* u, int B, int H, int W, int pad, long long img_rows, float b0, float b1, float* coords1,
+                           cudaStream_t s) {
+  k_flow_head2_gather<<<(unsigned)(((long long)B * H * W + 255) / 256), 256, 0, s>>>(u, B, H, W, pad, img_rows, b0, b1, coords1);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -21,9 +21,9 @@ int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pa
 int raft_gru_rh(const float* zr, const float* h_master, __half* rhx, long long rows, cudaStream_t s);
 int raft_gru_update(const float* zr, const float* q, float* h_master, __half* hx, long long rows, cudaStream_t s);
 int raft_coords_update(const float* delta, int B, int H, int W, int pad, long long img_rows, float* coords1, cudaStream_t s);
-// FlowHead.conv2 (3x3, 256 -> 2) + coords1 += delta; w_packed: fp32 [9][4][32][4] (see k_flow_head2), fh: shared-border fp16 map
-int raft_flow_head2(const __half* fh, int B, int H, int W, int pad, long long img_rows, const float* w_packed, float b0, float b1,
-                    float* coords1, float* delta_out, cudaStream_t s);
+// FlowHead.conv2 as 1x1 GEMM partial products u [rows][32] (column tap*2 + out) + this nine-tap gather; coords1 += delta
+int raft_flow_head2_gather(const float* u, int B, int H, int W, int pad, long long img_rows, float b0, float b1, float* coords1,
+                           cudaStream_t s);
 int raft_coords_init(float* c0, float* c1, int B, int H, int W, cudaStream_t s);
 int raft_convex_upsample(const float* mask, const float* c0, const float* c1, int B, int H, int W, int pad, long long img_rows,
                          int Hs, int Ws, int pad_top, int pad_left, float* out, cudaStream_t s);
