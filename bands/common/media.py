@@ -34,8 +34,16 @@ class VideoReader:
         return self.fps
 
     def seek(self, index):
-        """Next frame returned by the iterator = frame `index` (a frame-range worker starts mid-clip)."""
-        self.cap.set(cv2.CAP_PROP_POS_FRAMES, int(index))
+        """Next frame returned by the iterator = frame `index` (a frame-range worker starts mid-clip).  OpenCV seeks to the
+        preceding key frame and decodes forward; the position is verified, and if the container's index is inexact (B-frame
+        streams) the reader falls back to decoding from the first frame and discarding."""
+        index = int(index)
+        self.cap.set(cv2.CAP_PROP_POS_FRAMES, index)
+        if int(round(self.cap.get(cv2.CAP_PROP_POS_FRAMES))) != index:
+            self.cap.set(cv2.CAP_PROP_POS_FRAMES, 0)
+            for _ in range(index):
+                if not self.cap.grab():
+                    break
 
 
 class VideoWriter:

@@ -18,7 +18,8 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bands.common.depth_loop import process_depth_video, run_sharded, strip_shard_flags  # noqa: E402
+from bands.common.depth_loop import process_depth_video  # noqa: E402
+from bands.common.sharded import ENV_RANK, ShardContext, launch  # noqa: E402
 from bands.common.media import open_rgb, write_rgb  # noqa: E402
 from bands.common.meta import get_target, get_url, is_video, load_metadata, write_metadata  # noqa: E402
 
@@ -71,8 +72,8 @@ def process_image(a):
         data["bands"][BAND]["values"] = {"min": {"value": dmin, "type": "float"}, "max": {"value": dmax, "type": "float"}}
 
 
-def process_video(a):
-    process_depth_video(model, a, data, BAND)
+def process_video(a, ctx=None):
+    process_depth_video(model, a, data, BAND, ctx)
 
 
 def build_parser():
@@ -88,8 +89,6 @@ def build_parser():
     p.add_argument("--device", type=int, default=DEVICE)
     p.add_argument("--gpus", type=int, default=1, help="shard the frames of a video over this many GPUs (one worker each)")
     p.add_argument("--device-list", type=str, default="", help="GPU ordinals of the workers (default 0..gpus-1)")
-    p.add_argument("--frames", type=str, default="", help="[worker] frame range start:stop")
-    p.add_argument("--part", type=int, default=-1, help="[worker] shard index")
     return p
 
 
@@ -104,18 +103,19 @@ def main(argv=None):
         args.output = get_target(args.input, data, band=BAND, target=args.output, force_extension="png")
     elif args.output == "":
         args.output = os.path.join(os.path.dirname(args.input), BAND + os.path.splitext(args.input)[1])
-    if args.gpus > 1 and args.part < 0 and is_video(args.output):
+    if args.gpus > 1 and ENV_RANK not in os.environ and is_video(args.output):
         devices = [int(d) for d in args.device_list.split(",")] if args.device_list else None
-        run_sharded(os.path.abspath(__file__), strip_shard_flags(argv if argv is not None else sys.argv[1:]), args, data, BAND,
-                    args.gpus, devices)
+        launch(os.path.abspath(__file__), argv if argv is not None else sys.argv[1:], args.gpus, devices)
+        return  # rank 0 of the workers wrote the video, the csv pair and the metadata
+    ctx = ShardContext.from_env(args.device)
+    init_model(args.model)
+    if is_video(args.output):
+        process_video(args, ctx)
     else:
-        init_model(args.model)
-        if is_video(args.output):
-            process_video(args)
-        else:
-            process_image(args)
-    if args.part < 0:  # frame-range workers leave the metadata to the parent
+        process_image(args)
+    if ctx.is_writer():
         write_metadata(args.input, data)
+    ctx.close()
 
 
 if __name__ == "__main__":

@@ -56,19 +56,19 @@ def infer(args, prev_frame, curr_frame, want_rgb=False, reuse_prev=False):
     return r["fwd"], r["bwd"], fwd_mask, bwd_mask, r
 
 
-def write_flow(args, r, fwd_video, max_disps, idx, fwd_mask=None, fwd_mask_video=None, bwd_video=None, bwd_mask=None,
-               bwd_mask_video=None):
-    """One frame's outputs (reference common/flow.py:64-98).  The reference's .flo branch (:90-93) calls this very
-    function with (path, flow) and cannot run; the Middlebury writer it means (common/io.py:175-198) is used here."""
+def write_flow(args, r, streams, idx, fwd_mask=None, bwd_mask=None):
+    """One frame's outputs (reference common/flow.py:64-98): ordered video frames + the max displacement go to `streams`
+    (bands/common/sharded.OrderedStreams), per-frame files are written here.  The reference's .flo branch (:90-93) calls
+    this very function with (path, flow) and cannot run; the Middlebury writer it means (common/io.py:175-198) is used."""
     from prisma_b200.flow import write_flo
-    fwd_video.write(r["fwd_rgb"])  # VideoWriter rescales to the source size, as the reference's does
-    max_disps.append(r["max_fwd"])
-    if fwd_mask is not None and fwd_mask_video:
-        fwd_mask_video.write(np.repeat((fwd_mask.astype(np.uint8) * 255)[..., None], 3, axis=-1))
-    if bwd_mask is not None and bwd_mask_video:
-        bwd_mask_video.write(np.repeat((bwd_mask.astype(np.uint8) * 255)[..., None], 3, axis=-1))
-    if args.backwards and bwd_video:
-        bwd_video.write(r["bwd_rgb"])
+    streams.write("fwd", r["fwd_rgb"])  # the VideoWriter rescales to the source size, as the reference's does
+    streams.scalars(r["max_fwd"])
+    if fwd_mask is not None and args.output_mask != "":
+        streams.write("fwd_mask", np.repeat((fwd_mask.astype(np.uint8) * 255)[..., None], 3, axis=-1))
+    if bwd_mask is not None and args.output_mask != "" and args.backwards:
+        streams.write("bwd_mask", np.repeat((bwd_mask.astype(np.uint8) * 255)[..., None], 3, axis=-1))
+    if args.backwards:
+        streams.write("bwd", r["bwd_rgb"])
     if args.subpath != "":
         write_flo(os.path.join(args.subpath + "_fwd", "%04d.flo" % idx), r["fwd"])
         if args.backwards:
@@ -80,43 +80,72 @@ def write_flow(args, r, fwd_video, max_disps, idx, fwd_mask=None, fwd_mask_video
             cv2.imwrite(os.path.join(args.subpath_mask + "_bwd", "%04d.png" % idx), r["bwd_u16"])
 
 
-def process_video(args):
+def process_video(args, ctx=None, chunk=16):
+    """The reference's loop (:97-141) over this rank's frames.  Output index j = the flow from frame j to frame j + 1
+    (j < T - 1) and the all-zero last frame (j = T - 1).  A rank that owns the `curr` frames [start, stop) reads from
+    start - 1 (one halo frame) and produces the outputs [start - 1, stop - 1); the rank that owns the last frame appends
+    the zero frame.  Frames go through the engine in chunks (prisma_flow_infer_stream: uploads / downloads overlapped, each
+    frame encoded once)."""
+    from bands.common.sharded import OrderedStreams, ShardContext
+    from prisma_b200.flow import consistency_masks
+    ctx = ctx or ShardContext()
     reader = VideoReader(args.input)
+    T = len(reader)
     base = args.output.rsplit(".", 1)[0]
     fps = reader.get_avg_fps()
-    new_writer = lambda name: VideoWriter(reader.width, reader.height, fps, name)
-    fwd_video = new_writer(args.output)
-    fwd_mask_video = new_writer(args.output_mask) if args.output_mask != "" else None
-    bwd_video = new_writer(base + "_bwd.mp4") if args.backwards else None
-    bwd_mask_video = None
-    if args.backwards and args.output_mask != "":
-        bwd_mask_video = new_writer(args.output_mask.rsplit(".", 1)[0] + "_bwd.mp4")
+    new_writer = lambda name: (lambda: VideoWriter(reader.width, reader.height, fps, name))
+    mask_base = args.output_mask.rsplit(".", 1)[0] if args.output_mask != "" else ""
+    streams = OrderedStreams(ctx, {"fwd": new_writer(args.output), "bwd": new_writer(base + "_bwd.mp4"),
+                                   "fwd_mask": new_writer(args.output_mask), "bwd_mask": new_writer(mask_base + "_bwd.mp4")})
     want_masks = args.output_mask != "" or args.subpath_mask != ""
-    max_disps = []
-    prev = None
-    i = 0
-    for i, frame in enumerate(reader):
-        if prev is not None:
-            # from the second pair on, `prev` is the previous call's `curr`: its encoder features are still in the engine
-            _, _, fwd_mask, bwd_mask, r = infer(args, prev, frame, want_rgb=True, reuse_prev=(i > 1))
-            write_flow(args, r, fwd_video, max_disps, i - 1, fwd_mask, fwd_mask_video, bwd_video, bwd_mask, bwd_mask_video)
-        prev = frame
-    if prev is not None:
-        # last frame (:116-126): zero flow (the reference's 0/0 -> NaN -> u8 cast gives a black frame), all-false masks
-        # at the SOURCE resolution, as the reference allocates them
-        hs, ws = reader.height, reader.width
+    want_flow = want_masks or args.subpath != ""
+    start, stop, first = ctx.frames(T, halo=1)
+    if first > 0:
+        reader.seek(first)
+    state = dict(cont=False, idx=first)
+
+    def flush(frs):
+        r = model.infer_clip(np.ascontiguousarray(np.stack(frs)), continue_clip=state["cont"], want_flow=want_flow, want_rgb=True)
+        state["cont"] = True
+        for j in range(r["pairs"]):
+            rec = dict(fwd_rgb=r["fwd_rgb"][j], bwd_rgb=r["bwd_rgb"][j], max_fwd=float(r["max_fwd"][j]))
+            fm = bm = None
+            if want_flow:
+                rec["fwd"], rec["bwd"] = r["fwd"][j], r["bwd"][j]
+            if want_masks:
+                fm, bm, rec["fwd_u16"], rec["bwd_u16"] = consistency_masks(rec["fwd"], rec["bwd"], want_u16=True, device=args.device)
+            write_flow(args, rec, streams, state["idx"], fm, bm)
+            state["idx"] += 1
+
+    pending, n_read = [], 0
+    if stop > first:
+        for frame in reader:
+            pending.append(frame)
+            n_read += 1
+            if len(pending) == chunk:
+                flush(pending)
+                pending = []
+            if first + n_read >= stop:
+                break
+        if pending:
+            flush(pending)
+    if stop == T and T > 0 and start < stop:
+        # last frame (:116-126): zero flow (the reference's 0/0 -> NaN -> u8 cast gives a black frame) and all-false masks.
+        # Emitted at the engine's output size; the reference allocates them at the source size, and the writer rescales
+        # either to the same black frame.
+        hs, ws = model.out_size(reader.height, reader.width)
         zero = np.zeros((hs, ws, 2), np.float32)
         black = np.zeros((hs, ws, 3), np.uint8)
         u16 = np.zeros((hs, ws, 3), np.uint16)
         u16[..., :2] = 32768
-        r = dict(fwd=zero, bwd=zero, fwd_rgb=black, bwd_rgb=black, max_fwd=0.0, fwd_u16=u16, bwd_u16=u16)
+        rec = dict(fwd=zero, bwd=zero, fwd_rgb=black, bwd_rgb=black, max_fwd=0.0, fwd_u16=u16, bwd_u16=u16)
         mask = np.zeros((hs, ws), bool) if want_masks else None
-        write_flow(args, r, fwd_video, max_disps, i, mask, fwd_mask_video, bwd_video, mask, bwd_mask_video)
-    for v in (fwd_video, fwd_mask_video, bwd_video, bwd_mask_video):
-        if v:
-            v.close()
+        write_flow(args, rec, streams, T - 1, mask, mask)
+    table = streams.finish()
+    if not ctx.is_writer():
+        return
     with open(base + ".csv", "w") as f:
-        f.writelines("{}\n".format(v) for v in max_disps)
+        f.writelines("{}\n".format(row[0]) for row in table)
     if data:
         data["bands"][BAND] = {"url": BAND + ".mp4", "values": {"dist": {"type": "float", "url": BAND + ".csv"}}}
         if args.subpath != "":
@@ -149,6 +178,8 @@ def build_parser():
     p.add_argument("--alternate_corr", action="store_true", help="[RAFT] use efficent correlation implementation")
     p.add_argument("--seeded-weights", action="store_true", help="seeded random weights (offline testing)")
     p.add_argument("--device", type=int, default=0)
+    p.add_argument("--gpus", type=int, default=1, help="shard the frames over this many GPUs (one worker each, 1-frame halo)")
+    p.add_argument("--device-list", type=str, default="", help="GPU ordinals of the workers (default 0..gpus-1)")
     return p
 
 
@@ -172,9 +203,17 @@ def main(argv=None):
             os.makedirs(getattr(args, attr) + "_fwd", exist_ok=True)
             if args.backwards:
                 os.makedirs(getattr(args, attr) + "_bwd", exist_ok=True)
+    from bands.common.sharded import ENV_RANK, ShardContext, launch
+    if args.gpus > 1 and ENV_RANK not in os.environ:
+        devices = [int(d) for d in args.device_list.split(",")] if args.device_list else None
+        launch(os.path.abspath(__file__), argv if argv is not None else sys.argv[1:], args.gpus, devices)
+        return  # rank 0 of the workers wrote the videos, the csv and the metadata
+    ctx = ShardContext.from_env(args.device)
     init_model(args)
-    process_video(args)
-    write_metadata(args.input, data)
+    process_video(args, ctx)
+    if ctx.is_writer():
+        write_metadata(args.input, data)
+    ctx.close()
 
 
 if __name__ == "__main__":

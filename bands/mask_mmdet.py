@@ -75,23 +75,33 @@ def process_image(a):
         data["bands"][BAND] = {"url": os.path.basename(a.output), "ids": CLASSES}
 
 
-def process_video(a):
+def process_video(a, ctx=None):
+    """reference :131-161 over this rank's frames (independent frames: no halo); ordered frames go to the writer rank."""
+    from bands.common.sharded import OrderedStreams, ShardContext
+    ctx = ctx or ShardContext()
     reader = VideoReader(a.input)
-    out = VideoWriter(reader.width, reader.height, reader.get_avg_fps(), a.output)
+    streams = OrderedStreams(ctx, {"mask": lambda: VideoWriter(reader.width, reader.height, reader.get_avg_fps(), a.output)})
     folder = os.path.dirname(a.output)
     sub = ""
     if a.subpath != "":
         sub = os.path.join(folder, a.subpath)
         create_folder(sub)
-    for f, frame in enumerate(reader):
-        masks = frame_masks(frame, a.confidence)
-        if sub:  # COLMAP wants black-on-white masks (:148-149)
-            write_rgb(os.path.join(sub, "{:05d}.png".format(f)), 255 - masks)
-        if a.sdf:
-            masks = encode_sdf(masks)
-        out.write(masks)
-    out.close()
-    if data is not None:
+    start, stop, _ = ctx.frames(len(reader))
+    if start > 0:
+        reader.seek(start)
+    if stop > start:
+        for k, frame in enumerate(reader):
+            f = start + k
+            masks = frame_masks(frame, a.confidence)
+            if sub:  # COLMAP wants black-on-white masks (:148-149)
+                write_rgb(os.path.join(sub, "{:05d}.png".format(f)), 255 - masks)
+            if a.sdf:
+                masks = encode_sdf(masks)
+            streams.write("mask", masks)
+            if f + 1 >= stop:
+                break
+    streams.finish()
+    if ctx.is_writer() and data is not None:
         data["bands"][BAND] = {"url": os.path.basename(a.output), "ids": CLASSES}
         if a.subpath != "":
             data["bands"][BAND]["folder"] = a.subpath
@@ -107,6 +117,8 @@ def build_parser():
     p.add_argument("--weights", type=str, default="", help="mmdet SOLOv2 checkpoint (.pth/.npz)")
     p.add_argument("--seeded-weights", action="store_true", help="seeded random weights (offline testing)")
     p.add_argument("--device", type=int, default=DEVICE)
+    p.add_argument("--gpus", type=int, default=1, help="shard the frames of a video over this many GPUs (one worker each)")
+    p.add_argument("--device-list", type=str, default="", help="GPU ordinals of the workers (default 0..gpus-1)")
     return p
 
 
@@ -119,13 +131,20 @@ def main(argv=None):
         args.output = get_target(args.input, data, band=BAND, target=args.output, force_extension="png")
     elif args.output == "":
         args.output = os.path.join(os.path.dirname(args.input), BAND + os.path.splitext(args.input)[1])
+    from bands.common.sharded import ENV_RANK, ShardContext, launch
+    if args.gpus > 1 and ENV_RANK not in os.environ and is_video(args.output):
+        devices = [int(d) for d in args.device_list.split(",")] if args.device_list else None
+        launch(os.path.abspath(__file__), argv if argv is not None else sys.argv[1:], args.gpus, devices)
+        return  # rank 0 of the workers wrote the video and the metadata
+    ctx = ShardContext.from_env(args.device)
     init_model()
     if is_video(args.output):
-        process_video(args)
+        process_video(args, ctx)
     else:
         process_image(args)
-    if data:
+    if data and ctx.is_writer():
         write_metadata(args.input, data)
+    ctx.close()
 
 
 if __name__ == "__main__":

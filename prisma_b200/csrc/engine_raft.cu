@@ -200,17 +200,8 @@ int RaftEngine::finalize() {
     bzr.data = bz->data; bzr.data.insert(bzr.data.end(), br->data.begin(), br->data.end());
     host[u + "gru.zr" + s + ".weight"] = wzr;
     host[u + "gru.zr" + s + ".bias"] = bzr;
-    // conv(cat[h, inp, motion]) = conv_{h,motion}(...) + conv_inp(inp): `inp` = relu(cnet[128:]) does not change over the
-    // iterations (raft.py:113-116), so its third of every GRU conv is evaluated once per pass and enters the per-iteration
-    // conv as a pre-activation term (GemmEpilogue::pre_f32).  Operand maps are laid out [h | motion | inp] accordingly.
-    std::vector<int> ch_iter, ch_inp;
-    for (int c = 0; c < 128; ++c) ch_iter.push_back(c);
-    for (int c = 256; c < 384; ++c) ch_iter.push_back(c);
-    for (int c = 128; c < 256; ++c) ch_inp.push_back(c);
-    PRISMA_TRY(up_conv(u + "gru.zr" + s, "", 256, 384, kh, kw, 256, 1.f, &w.zr[pass], 1, &ch_iter));
-    PRISMA_TRY(up_conv(u + "gru.convq" + s, "", 128, 384, kh, kw, 128, 1.f, &w.q[pass], 1, &ch_iter));
-    PRISMA_TRY(up_conv(u + "gru.zr" + s, "", 256, 384, kh, kw, 256, 1.f, &w.zr_inp[pass], 1, &ch_inp, false));
-    PRISMA_TRY(up_conv(u + "gru.convq" + s, "", 128, 384, kh, kw, 128, 1.f, &w.q_inp[pass], 1, &ch_inp, false));
+    PRISMA_TRY(up_conv(u + "gru.zr" + s, "", 256, 384, kh, kw, 256, 1.f, &w.zr[pass]));
+    PRISMA_TRY(up_conv(u + "gru.convq" + s, "", 128, 384, kh, kw, 128, 1.f, &w.q[pass]));
   }
   PRISMA_TRY(up_conv(u + "flow_head.conv1", "", 256, 128, 3, 3, 256, 1.f, &w.fh1, 2));  // hi/lo weights: the largest error term
   {  // FlowHead.conv2 (3x3, 256 -> 2) as a 1x1 conv to 18 partial products u[tap*2 + out] (see k_flow_head2_gather)
@@ -500,16 +491,6 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
     add("cnet_split", [=](cudaStream_t s) { return raft_cnet_split(cn, 2, h8, w8, 2, ir8, hm, hxp, rhp, s); });
     add("coords_init", [=](cudaStream_t s) { return raft_coords_init(c0, c1p, 2, h8, w8, s); });
   }
-  // the `inp` third of the four GRU convs, once per pass (fp32, padded-row layout like the gates)
-  float *zr_pre[2] = {nullptr, nullptr}, *q_pre[2] = {nullptr, nullptr};
-  for (int pass = 0; pass < 2; ++pass) {
-    PRISMA_TRY(r_alloc(plan_allocs, &zr_pre[pass], (size_t)hx.rows() * 256));
-    PRISMA_TRY(r_alloc(plan_allocs, &q_pre[pass], (size_t)hx.rows() * 128));
-    { GemmEpilogue ep; ep.out_f32 = zr_pre[pass]; ep.out_f32_ld = 256;
-      PRISMA_TRY(add_conv("gru_inp", hx, 256, w.zr_inp[pass], ep, 1)); }
-    { GemmEpilogue ep; ep.out_f32 = q_pre[pass]; ep.out_f32_ld = 128;
-      PRISMA_TRY(add_conv("gru_inp", hx, 256, w.q_inp[pass], ep, 1)); }
-  }
   // ---- update block, `iters` times (raft.py:123-141)
   PRISMA_TRY(new_map(&corrf, B, H8, W8, 384, 2));
   PRISMA_TRY(new_map(&c1, B, H8, W8, 256, 2));
@@ -552,18 +533,18 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
       PRISMA_TRY(add_conv("convf2", f1, 0, w.convf2, ep, 1)); }
     { // conv 3x3 256 -> 126 (+2 zero channels); the 126 motion channels go to cols 256..381 of hx and rhx; the two
       // trailing columns are rewritten with the flow by flow_cols every iteration -- so restore them here
-      GemmEpilogue ep; ep.act = 2; ep.out_f16 = hx.p + 128; ep.out_f16_ld = 384; ep.out_f16_relu = rhx.p + 128; ep.out_f16_relu_ld = 384;
+      GemmEpilogue ep; ep.act = 2; ep.out_f16 = hx.p + 256; ep.out_f16_ld = 384; ep.out_f16_relu = rhx.p + 256; ep.out_f16_relu_ld = 384;
       PRISMA_TRY(add_conv("motion_conv", c2, 0, w.conv, ep, 1));
       const float* c0 = b.coords0; const float* c1p = b.coords1; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
       const long long ir8 = hx.img_rows();
       add("flow_cols", [=](cudaStream_t s) { return raft_flow_cols(c0, c1p, 2, h8, w8, 2, ir8, hxp, rhp, s); });
     }
     for (int pass = 0; pass < 2; ++pass) {  // SepConvGRU horizontal then vertical (update.py:45-60)
-      { GemmEpilogue ep; ep.act = 3; ep.out_f32 = zr_f; ep.out_f32_ld = 256; ep.pre_f32 = zr_pre[pass]; ep.pre_f32_ld = 256;
+      { GemmEpilogue ep; ep.act = 3; ep.out_f32 = zr_f; ep.out_f32_ld = 256;
         PRISMA_TRY(add_conv("gru_zr", hx, 0, w.zr[pass], ep, 1)); }
       { const float* z = zr_f; const float* hm = b.h_master; __half* rhp = rhx.p;
         add("gru_rh", [=](cudaStream_t s) { return raft_gru_rh(z, hm, rhp, rows, s); }); }
-      { GemmEpilogue ep; ep.act = 4; ep.out_f32 = q_f; ep.out_f32_ld = 128; ep.pre_f32 = q_pre[pass]; ep.pre_f32_ld = 128;
+      { GemmEpilogue ep; ep.act = 4; ep.out_f32 = q_f; ep.out_f32_ld = 128;
         PRISMA_TRY(add_conv("gru_q", rhx, 0, w.q[pass], ep, 1)); }
       { const float* z = zr_f; const float* qq = q_f; float* hm = b.h_master; __half* hxp = hx.p;
         add("gru_update", [=](cudaStream_t s) { return raft_gru_update(z, qq, hm, hxp, rows, s); }); }

@@ -18,7 +18,6 @@ struct EncW { ConvW stem; ResW blk[3][2]; ConvW out; };
 struct RaftWeights {
   EncW fnet, cnet;
   ConvW convc1, convc2, convf2, conv, zr[2], q[2], fh1, fh2, mk1, mk2;
-  ConvW zr_inp[2], q_inp[2];  // the `inp` (context) input channels of the GRU convs: constant over the iterations, applied once per pass
   float *convf1_w = nullptr, *convf1_b = nullptr;
   ConvW fh2u; float fh2_b[2] = {0.f, 0.f};  // FlowHead.conv2 as a 1x1 conv to 18 per-tap partial products (hi/lo weights)
   __half* convf1_gemm_w = nullptr;  // [256][256]: k = [98 weights | 0 | the same 98 (for the fp16 'lo' half of the flow) | 0]

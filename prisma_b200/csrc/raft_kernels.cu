@@ -192,8 +192,7 @@ int instnorm_apply(const float* x, const float* stats, int B, int H, int W, int 
 
 // ------------------------------------------------------------------------------------------------
 // cnet output split (raft.py:113-116): net = tanh(cnet[:, :128]) -> h (fp32 master + fp16 operand), inp = relu(rest).
-// Destination: the GRU operand maps hx = [h | motion | inp] and rhx = [r*h | motion | inp], 384 channels, pad 2 (inp last:
-// the per-iteration convs read the first 256 channels, the once-per-pass `inp` convs the last 128).
+// Destination: the GRU operand maps hx = [h | inp | motion] and rhx = [r*h | inp | motion], 384 channels, pad 2.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, int pad, long long img_rows, float* __restrict__ h_master,
                              __half* __restrict__ hx, __half* __restrict__ rhx) {
@@ -214,8 +213,8 @@ __global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, 
     hx[prow * 384 + c] = __float2half_rn(t);
   } else {
     const __half i = __float2half_rn(fmaxf(v, 0.f));
-    hx[prow * 384 + 128 + c] = i;   // inp occupies channels 256..383
-    rhx[prow * 384 + 128 + c] = i;
+    hx[prow * 384 + c] = i;
+    rhx[prow * 384 + c] = i;
   }
 }
 int raft_cnet_split(const float* cn, int B, int H, int W, int pad, long long img_rows, float* h_master, __half* hx, __half* rhx,
@@ -284,8 +283,8 @@ __global__ void k_flow_cols(const float* __restrict__ c0, const float* __restric
   const float* a0 = c0 + (size_t)b * 2 * P;
   const float* a1 = c1 + (size_t)b * 2 * P;
   const uint32_t fl = pack_half2(a1[r] - a0[r], a1[(size_t)P + r] - a0[(size_t)P + r]);
-  *reinterpret_cast<uint32_t*>(hx + prow * 384 + 254) = fl;   // motion = channels 128..255, its last two are the flow
-  *reinterpret_cast<uint32_t*>(rhx + prow * 384 + 254) = fl;
+  *reinterpret_cast<uint32_t*>(hx + prow * 384 + 382) = fl;
+  *reinterpret_cast<uint32_t*>(rhx + prow * 384 + 382) = fl;
 }
 int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pad, long long img_rows, __half* hx, __half* rhx,
                    cudaStream_t s) {

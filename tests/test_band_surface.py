@@ -51,7 +51,7 @@ def test_process_runs_band_into_prisma_folder(tmp_path):
         w.write(synthetic_frame(240, 320, t)[..., ::-1].copy())
     w.release()
     rc = subprocess.call([sys.executable, os.path.join(ROOT, "process.py"), "-i", src, "--encoder", "vits", "--seeded-weights",
-                          "-f", "flow_raft"])
+                          "-f", "flow_raft", "-b"])
     assert rc == 0
     folder = str(tmp_path / "clip")
     meta = json.load(open(os.path.join(folder, "metadata.json")))
@@ -229,3 +229,69 @@ def test_depth_band_sharded_over_two_workers_equals_single(tmp_path):
     assert outs["one"]["mins"] == outs["two"]["mins"] and outs["one"]["maxs"] == outs["two"]["maxs"]
     assert all(np.array_equal(a, b) for a, b in zip(outs["one"]["npy"], outs["two"]["npy"]))
     assert outs["one"]["meta"] == outs["two"]["meta"] and outs["two"]["frames"] == 5 and outs["two"]["left"] == []
+
+
+def _clip_folder(folder, n):
+    import cv2
+    from oracle.frames import synthetic_frame
+    folder.mkdir()
+    w = cv2.VideoWriter(str(folder / "rgba.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
+    for t in range(n):
+        w.write(synthetic_frame(240, 320, t)[..., ::-1].copy())
+    w.release()
+    json.dump({"bands": {"rgba": {"url": "rgba.mp4"}}, "width": 320, "height": 240, "frames": n, "fps": 24.0},
+              open(folder / "metadata.json", "w"))
+
+
+def _video_frames(path):
+    import cv2
+    cap = cv2.VideoCapture(str(path))
+    out = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        out.append(f)
+    return out
+
+
+@pytest.mark.gpu
+def test_flow_band_sharded_with_halo_equals_single(tmp_path):
+    """flow_raft --gpus 2 (1-frame halo per shard, in-memory gather to the writer rank over torch.distributed) == the
+    single-process run: same max-displacement csv, same .flo files, same videos, same metadata."""
+    outs = {}
+    for tag, extra in (("one", []), ("two", ["--gpus", "2", "--device-list", "0,0"])):
+        folder = tmp_path / tag
+        _clip_folder(folder, 5)
+        rc = subprocess.call([sys.executable, os.path.join(ROOT, "bands", "flow_raft.py"), "-i", str(folder), "-b", "--iterations", "4",
+                              "--subpath", "flo", "--seeded-weights"] + extra)
+        assert rc == 0
+        outs[tag] = dict(csv=open(folder / "flow_raft.csv").read(),
+                         flo=[open(folder / "flo_fwd" / ("%04d.flo" % i), "rb").read() for i in range(5)],
+                         flo_b=[open(folder / "flo_bwd" / ("%04d.flo" % i), "rb").read() for i in range(5)],
+                         fwd=_video_frames(folder / "flow_raft.mp4"), bwd=_video_frames(folder / "flow_raft_bwd.mp4"),
+                         meta=json.load(open(folder / "metadata.json"))["bands"])
+    a, b = outs["one"], outs["two"]
+    assert a["csv"] == b["csv"] and len(a["csv"].split()) == 5 and float(a["csv"].split()[-1]) == 0.0
+    assert a["flo"] == b["flo"] and a["flo_b"] == b["flo_b"]
+    assert len(b["fwd"]) == 5 and len(b["bwd"]) == 5
+    assert all(np.array_equal(x, y) for x, y in zip(a["fwd"], b["fwd"])) and all(np.array_equal(x, y) for x, y in zip(a["bwd"], b["bwd"]))
+    assert a["meta"] == b["meta"] and "flow_raft_bwd" in b["meta"]
+
+
+@pytest.mark.gpu
+def test_mask_band_sharded_equals_single(tmp_path):
+    """mask_mmdet --gpus 2 == single process (frames are independent): same mask video, same COLMAP frames, same metadata."""
+    outs = {}
+    for tag, extra in (("one", []), ("two", ["--gpus", "2", "--device-list", "0,0"])):
+        folder = tmp_path / tag
+        _clip_folder(folder, 3)
+        rc = subprocess.call([sys.executable, os.path.join(ROOT, "bands", "mask_mmdet.py"), "-i", str(folder), "--subpath", "mask",
+                              "--sdf", "--seeded-weights"] + extra)
+        assert rc == 0
+        outs[tag] = dict(video=_video_frames(folder / "mask.mp4"),
+                         png=[open(folder / "mask" / ("%05d.png" % i), "rb").read() for i in range(3)],
+                         meta=json.load(open(folder / "metadata.json"))["bands"]["mask"])
+    a, b = outs["one"], outs["two"]
+    assert len(b["video"]) == 3 and all(np.array_equal(x, y) for x, y in zip(a["video"], b["video"]))
+    assert a["png"] == b["png"] and a["meta"] == b["meta"]
