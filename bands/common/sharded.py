@@ -1,8 +1,8 @@
 """Frame sharding of a band's video loop over the GPUs of one box.
 
 `<band>.py --gpus N` re-launches itself as N worker processes (rank r on GPU devices[r], torch.distributed over
-127.0.0.1: NCCL when CUDA is present -- the encoded frames travel GPU -> NVLink -> GPU of the writer rank -- and gloo on a
-CPU-only host, which is how tests/test_shard_gloo.py runs it).  Every rank owns a contiguous range of frames
+127.0.0.1: NCCL when every rank has its own GPU -- the encoded frames travel GPU -> NVLink -> GPU of the writer rank -- and
+gloo on a CPU-only host or when ranks share a GPU, which is how the tests run it).  Every rank owns a contiguous range of frames
 (prisma_b200.shard.frame_range; flow bands read one halo frame), runs the band's normal loop over it and hands every
 ordered output (video frames, per-frame scalars) to an `OrderedStreams` sink:
 
@@ -82,7 +82,9 @@ class ShardContext:
         rank, world, port = int(os.environ[ENV_RANK]), int(os.environ[ENV_WORLD]), int(os.environ[ENV_PORT])
         import torch
         import torch.distributed as dist
-        cuda = torch.cuda.is_available() if backend is None else backend == "nccl"
+        devs = [d for d in os.environ.get(ENV_DEVS, "").split(",") if d != ""]
+        distinct = len(set(devs)) == len(devs) and len(devs) >= world  # NCCL refuses two ranks on one GPU (tests do that)
+        cuda = (torch.cuda.is_available() and distinct) if backend is None else backend == "nccl"
         if cuda:
             torch.cuda.set_device(device)
         dist.init_process_group("nccl" if cuda else "gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,

@@ -70,6 +70,8 @@ SIGNATURES = {
     "prisma_flow_infer_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_float_p]),
     "prisma_debug_gemm": (C.c_int, [C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, c_float_p]),
+    "prisma_debug_gemm_tf32x3": (C.c_int, [C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, c_float_p]),
     "prisma_debug_conv": (C.c_int, [C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_int, c_float_p]),
     "prisma_debug_attention": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, c_float_p]),

@@ -275,6 +275,51 @@ int prisma_debug_gemm(int device, const float* A, const float* W, const float* b
   API_GUARD_END
 }
 
+// D = A[M,K] * W[N,K]^T + bias through the 3xTF32 path (fp32-class products on the tensor cores): the operands are split on
+// the host into [hi | lo] / [hi | hi | lo] as gemm_prepare_tf32x3 expects.  K is padded to a multiple of 32.
+int prisma_debug_gemm_tf32x3(int device, const float* A, const float* W, const float* bias, float* Dout, int M, int N, int K,
+                             int force_bn, int iters, float* ms_out) {
+  API_GUARD_BEGIN
+  int sms = 0;
+  PRISMA_TRY(device_sms(device, &sms));
+  Scratch sc;
+  const int C = round_up(K, 32), Nw = round_up(N, 256);
+  auto hi_of = [](float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u; float h; memcpy(&h, &u, 4); return h; };
+  std::vector<float> hA((size_t)M * 2 * C, 0.f), hW((size_t)Nw * 3 * C, 0.f);
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < K; ++k) {
+      const float v = A[(size_t)m * K + k], h = hi_of(v);
+      hA[(size_t)m * 2 * C + k] = h;
+      hA[(size_t)m * 2 * C + C + k] = v - h;
+    }
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      const float v = W[(size_t)n * K + k], h = hi_of(v);
+      hW[(size_t)n * 3 * C + k] = h;
+      hW[(size_t)n * 3 * C + C + k] = h;
+      hW[(size_t)n * 3 * C + 2 * C + k] = v - h;
+    }
+  float* dA = sc.alloc<float>(hA.size());
+  float* dW = sc.alloc<float>(hW.size());
+  float* dB = sc.alloc<float>(round_up(N, 8));
+  float* dD = sc.alloc<float>((size_t)M * N);
+  PRISMA_CHECK(dA && dW && dB && dD, "cudaMalloc failed");
+  PRISMA_CUDA_OK(cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice));
+  PRISMA_CUDA_OK(cudaMemcpy(dW, hW.data(), hW.size() * 4, cudaMemcpyHostToDevice));
+  if (bias) PRISMA_CUDA_OK(cudaMemcpy(dB, bias, N * 4, cudaMemcpyHostToDevice));
+  GemmEpilogue ep;
+  ep.bias = bias ? dB : nullptr;
+  ep.out_f32 = dD;
+  ep.out_f32_ld = N;
+  GemmLaunch g;
+  const int off[1] = {0};
+  PRISMA_TRY(gemm_prepare_tf32x3(&g, dA, M, C, C, dW, Nw, M, N, 1, off, ep, sms, force_bn));
+  PRISMA_TRY(timed(0, iters > 0 ? iters : 1, ms_out, [&]() { return gemm_run(g, 0); }));
+  PRISMA_CUDA_OK(cudaMemcpy(Dout, dD, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+  return 0;
+  API_GUARD_END
+}
+
 int prisma_debug_conv(int device, const float* x, const float* w_oihw, const float* bias, float* y, int H, int W,
                       int Cin, int Cout, int kh, int kw, int relu, float* ms_out) {
   API_GUARD_BEGIN

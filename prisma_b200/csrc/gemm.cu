@@ -82,9 +82,29 @@ int gemm_pick_bn(int M, int N, int num_sms) {
   return best;
 }
 
+static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, int a_cols, int a_pitch, const void* W,
+                             int w_rows, int M, int N, int taps, const int* tap_off, const int* tap_acol, const GemmEpilogue& ep,
+                             int num_sms, int force_bn, bool tf32);
+
 int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols, int a_pitch, const __half* W,
                  int w_rows, int M, int N, int taps, const int* tap_off, const GemmEpilogue& ep, int num_sms,
                  int force_bn) {
+  return gemm_prepare_impl(out, A, a_rows, a_cols, a_pitch, W, w_rows, M, N, taps, tap_off, nullptr, ep, num_sms, force_bn, false);
+}
+
+int gemm_prepare_tf32x3(GemmLaunch* out, const float* A_split, long long a_rows, int C, int C_half, const float* W3, int w_rows,
+                        int M, int N, int taps, const int* tap_off, const GemmEpilogue& ep, int num_sms, int force_bn) {
+  PRISMA_CHECK(taps * 3 <= GEMM_MAX_TAPS, "gemm(tf32x3): too many taps");
+  PRISMA_CHECK(C % 32 == 0 && C_half % 32 == 0 && C <= C_half, "gemm(tf32x3): channel counts must be multiples of 32");
+  int off[GEMM_MAX_TAPS], acol[GEMM_MAX_TAPS];
+  for (int t = 0; t < taps; ++t)
+    for (int p = 0; p < 3; ++p) { off[t * 3 + p] = tap_off[t]; acol[t * 3 + p] = p == 1 ? C_half : 0; }
+  return gemm_prepare_impl(out, A_split, a_rows, C, 2 * C_half, W3, w_rows, M, N, taps * 3, off, acol, ep, num_sms, force_bn, true);
+}
+
+static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, int a_cols, int a_pitch, const void* W,
+                             int w_rows, int M, int N, int taps, const int* tap_off, const int* tap_acol, const GemmEpilogue& ep,
+                             int num_sms, int force_bn, bool tf32) {
   PRISMA_CHECK(taps >= 1 && taps <= GEMM_MAX_TAPS, "gemm: bad tap count");
   PRISMA_CHECK(N % 4 == 0, "gemm: N must be a multiple of 4");
   PRISMA_CHECK(M >= 1 && a_cols >= 1, "gemm: empty problem");
@@ -93,11 +113,14 @@ int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols,
   int bn = force_bn ? force_bn : gemm_pick_bn(M, N, num_sms);
   int cg = 1;
   if (bn == 512) { bn = 256; cg = 2; }
-  else if (!force_bn && !pairs_off && bn == 256 && M >= 1024 && N >= 256) cg = 2;
+  else if (!force_bn && !pairs_off && !tf32 && bn == 256 && M >= 1024 && N >= 256) cg = 2;
+  PRISMA_CHECK(!(tf32 && cg == 2), "gemm: the tf32 path has no CTA-pair instantiation");
+  out->tf32 = tf32;
+  const int bke = tf32 ? 32 : 64;  // elements per 128-byte K block
   PRISMA_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: unsupported BLOCK_N");
   out->cg = cg;
   PRISMA_CHECK(w_rows >= round_up(N, bn), "gemm: weight rows must be padded to a multiple of BLOCK_N");
-  const int kchunks = ceil_div(a_cols, GEMM_BK);
+  const int kchunks = ceil_div(a_cols, bke);
   out->bn = bn;
   out->args.M = M;
   out->args.N = N;
@@ -107,11 +130,24 @@ int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols,
     static const char* r = getenv("PRISMA_GEMM_RASTER");  // "m" / "n": force (experiments)
     out->args.raster_n = r ? (r[0] == 'n') : (M >= N);
   }
-  for (int t = 0; t < GEMM_MAX_TAPS; ++t) out->args.tap_off[t] = t < taps ? tap_off[t] : 0;
+  {
+    static const int dbg = [] { const char* e = getenv("PRISMA_GEMM_DBG"); return e ? atoi(e) : 0; }();
+    out->args.dbg_mode = dbg;
+  }
+  for (int t = 0; t < GEMM_MAX_TAPS; ++t) {
+    out->args.tap_off[t] = t < taps ? tap_off[t] : 0;
+    out->args.tap_acol[t] = (t < taps && tap_acol) ? tap_acol[t] : 0;
+  }
   out->args.ep = ep;
-  PRISMA_TRY(make_tmap_2d_f16(&out->tmA, A, (uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)a_pitch, 64, GEMM_BM));
-  PRISMA_TRY(make_tmap_2d_f16(&out->tmB, W, (uint64_t)taps * kchunks * 64, (uint64_t)w_rows,
-                              (uint64_t)taps * kchunks * 64, 64, bn / cg));
+  if (tf32) {
+    // the A map spans the [hi | lo] halves (2 * a_cols columns); out-of-range columns of a ragged last K block read as zero
+    PRISMA_TRY(make_tmap_2d_f32(&out->tmA, A, (uint64_t)a_pitch, (uint64_t)a_rows, (uint64_t)a_pitch, 32, GEMM_BM));
+    PRISMA_TRY(make_tmap_2d_f32(&out->tmB, W, (uint64_t)taps * kchunks * 32, (uint64_t)w_rows, (uint64_t)taps * kchunks * 32, 32, bn));
+  } else {
+    PRISMA_TRY(make_tmap_2d_f16(&out->tmA, A, (uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)a_pitch, 64, GEMM_BM));
+    PRISMA_TRY(make_tmap_2d_f16(&out->tmB, W, (uint64_t)taps * kchunks * 64, (uint64_t)w_rows,
+                                (uint64_t)taps * kchunks * 64, 64, bn / cg));
+  }
   const int tiles = ceil_div(M, GEMM_BM * cg) * ceil_div(N, bn);
   const int groups = num_sms / cg;
   out->grid = (tiles < groups ? tiles : groups) * cg;
@@ -135,8 +171,10 @@ int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols,
       if (best_split > 1) {
         out->args.n_main = full * groups;
         out->args.tail_split = best_split;
-        PRISMA_TRY(make_tmap_2d_f16(&out->tmBt, W, (uint64_t)taps * kchunks * 64, (uint64_t)w_rows,
-                                    (uint64_t)taps * kchunks * 64, 64, bn / best_split / cg));
+        if (tf32) PRISMA_TRY(make_tmap_2d_f32(&out->tmBt, W, (uint64_t)taps * kchunks * 32, (uint64_t)w_rows,
+                                              (uint64_t)taps * kchunks * 32, 32, bn / best_split));
+        else PRISMA_TRY(make_tmap_2d_f16(&out->tmBt, W, (uint64_t)taps * kchunks * 64, (uint64_t)w_rows,
+                                         (uint64_t)taps * kchunks * 64, 64, bn / best_split / cg));
       }
     }
   }
@@ -156,16 +194,16 @@ int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols,
   return 0;
 }
 
-template <int BN, int CG, bool TMAST = false>
+template <int BN, int CG, bool TMAST = false, bool TF32 = false>
 static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
   static bool attr_set = false;  // per-process, per-instantiation
   using Cfg = GemmCfg<BN, CG, TMAST>;
   if (!attr_set) {
-    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, TMAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, TMAST, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   if (CG == 1) {
-    gemm_tc_kernel<BN, CG, TMAST><<<g.grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(g.tmA, g.tmB, g.tmBt, g.tmD, g.args);
+    gemm_tc_kernel<BN, CG, TMAST, TF32><<<g.grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(g.tmA, g.tmB, g.tmBt, g.tmD, g.args);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.grid);
@@ -177,13 +215,23 @@ static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, TMAST>, g.tmA, g.tmB, g.tmBt, g.tmD, g.args));
+    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, TMAST, TF32>, g.tmA, g.tmB, g.tmBt, g.tmD, g.args));
   }
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int gemm_run(const GemmLaunch& g, cudaStream_t stream) {
+  if (g.tf32) {
+    switch (g.bn) {
+      case 256: return launch_bn<256, 1, false, true>(g, stream);
+      case 128: return launch_bn<128, 1, false, true>(g, stream);
+      case 64: return launch_bn<64, 1, false, true>(g, stream);
+      case 32: return launch_bn<32, 1, false, true>(g, stream);
+    }
+    set_last_error("gemm_run: unsupported BLOCK_N (tf32)");
+    return -1;
+  }
   if (g.tma_store) {
     if (g.cg == 2 && g.bn == 256) return launch_bn<256, 2, true>(g, stream);
     if (g.cg == 1 && g.bn == 256) return launch_bn<256, 1, true>(g, stream);

@@ -93,8 +93,12 @@ struct GemmArgs {
   int taps;
   int kchunks;  // 64-wide K blocks per tap
   int tap_off[GEMM_MAX_TAPS];
+  int tap_acol[GEMM_MAX_TAPS];  // first A column (elements) of each tap's K slab: 0 for plain convs; the 3xTF32 path walks
+                                // [hi | lo] activation halves: (hi, W_hi), (lo, W_hi), (hi, W_lo)
   int n_main;      // work items [0, n_main) are full BN-wide tiles; the remaining tiles are each cut into `tail_split`
   int tail_split;  // narrower tiles (BN / tail_split wide) so the last partial wave costs a fraction of a full one; 1 = off
+  int dbg_mode;  // diagnostics (PRISMA_GEMM_DBG): 1 = prologue + teardown only, 2 = loads + MMAs but the epilogue warps only
+                 // release the accumulators, 3 = loads only (the MMA warp commits without issuing)
   int raster_n;  // 1: consecutive tiles walk N first (the CTAs of a wave share few A row panels and all of W: A is read
                  // from HBM once when M >> N); 0: M first
   GemmEpilogue ep;
@@ -113,7 +117,11 @@ struct GemmCfg {                                   // TMAST: TMA-store epilogue 
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// sigmoid / tanh of the fused epilogues: ex2.approx + rcp.approx (relative error ~4e-7, absolute error of tanh ~2e-7) instead
+// of expf + IEEE division / tanhf.  Measured on the RAFT gate conv (37 888 x 256 outputs): the exact versions cost 18 us per
+// launch on top of an 18.8 us kernel; their accuracy is irrelevant next to the fp16 operand rounding (5e-4).
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // nn.Softplus(beta 1, threshold 20)
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -160,7 +168,7 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
     for (int i = 0; i < 8; ++i) { v[i].x = sigmoid_f(v[i].x); v[i].y = sigmoid_f(v[i].y); v[i].z = sigmoid_f(v[i].z); v[i].w = sigmoid_f(v[i].w); }
   } else if (ep.act == 4) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i].x = tanhf(v[i].x); v[i].y = tanhf(v[i].y); v[i].z = tanhf(v[i].z); v[i].w = tanhf(v[i].w); }
+    for (int i = 0; i < 8; ++i) { v[i].x = tanh_f(v[i].x); v[i].y = tanh_f(v[i].y); v[i].z = tanh_f(v[i].z); v[i].w = tanh_f(v[i].w); }
   } else if (ep.act == 5) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i].x = softplus_f(v[i].x); v[i].y = softplus_f(v[i].y); v[i].z = softplus_f(v[i].z); v[i].w = softplus_f(v[i].w); }
@@ -213,13 +221,14 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   }
 }
 
-template <int BN, int CG, bool TMAST>
+template <int BN, int CG, bool TMAST, bool TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmD,
                const __grid_constant__ GemmArgs args) {
   using Cfg = GemmCfg<BN, CG, TMAST>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int BKE = TF32 ? 32 : 64;  // elements per 128-byte K block (fp32 containers for kind::tf32, fp16 otherwise)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("prisma: gemm smem base not 1024-aligned\n");
@@ -269,7 +278,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (args.dbg_mode == 1) {
+    // diagnostics: nothing but the prologue and the teardown
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -286,12 +297,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (CG == 2) {
             // both CTAs' bytes land on the leader's barrier; only the leader arrives (count 1) and posts the total
             if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * stage_bytes);
-            tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], chunk * GEMM_BK, m0 + args.tap_off[tap]);
-            tma_load_2d_pair(sB + stage * Cfg::B_BYTES, tb, &full[stage], kb * GEMM_BK, n0);
+            tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], args.tap_acol[tap] + chunk * BKE, m0 + args.tap_off[tap]);
+            tma_load_2d_pair(sB + stage * Cfg::B_BYTES, tb, &full[stage], kb * BKE, n0);
           } else {
             mbar_arrive_expect_tx(&full[stage], stage_bytes);
-            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], chunk * GEMM_BK, m0 + args.tap_off[tap]);
-            tma_load_2d(sB + stage * Cfg::B_BYTES, tb, &full[stage], kb * GEMM_BK, n0);
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], args.tap_acol[tap] + chunk * BKE, m0 + args.tap_off[tap]);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, tb, &full[stage], kb * BKE, n0);
           }
           if (++chunk == args.kchunks) { chunk = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -301,8 +312,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc_full = make_idesc_f16(TILE_M, BN);
-      const uint32_t idesc_tail = make_idesc_f16(TILE_M, bw_tail);
+      constexpr uint32_t idesc_full = TF32 ? make_idesc_tf32(TILE_M, BN) : make_idesc_f16(TILE_M, BN);
+      const uint32_t idesc_tail = TF32 ? make_idesc_tf32(TILE_M, bw_tail) : make_idesc_f16(TILE_M, bw_tail);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = group; tile < num_items; tile += num_groups, ++it) {
@@ -319,8 +330,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t bdesc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
+            if (args.dbg_mode == 3) break;
             // advance 16 fp16 = 32 B along K inside the 128 B swizzled row: +2 in the (addr >> 4) field
-            if (CG == 2) umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (TF32) umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);  // K = 8 fp32 = 32 B
+            else if (CG == 2) umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           if (CG == 2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
@@ -395,7 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int c0 = chunk_par * 32; c0 < bw; c0 += 64) {
-        if (n0 + c0 >= args.N) break;  // warp-uniform
+        if (n0 + c0 >= args.N || args.dbg_mode >= 2) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
@@ -521,6 +534,7 @@ struct GemmLaunch {
   CUtensorMap tmA, tmB, tmBt;  // tmBt: W with the narrow box of the tail tiles (== tmB when there is no tail)
   CUtensorMap tmD;             // fp32 output, 32 x 32 boxes (TMA-store epilogue only)
   bool tma_store = false;
+  bool tf32 = false;           // kind::tf32 operands (fp32 containers): the 3xTF32 "fp32-class" path of the mask band
   GemmArgs args;
   int bn = 128;
   int cg = 1;  // 2 = CTA pairs (cta_group::2), 256 x bn tiles
@@ -532,6 +546,12 @@ struct GemmLaunch {
 int gemm_prepare(GemmLaunch* out, const __half* A, long long a_rows, int a_cols, int a_pitch, const __half* W,
                  int w_rows, int M, int N, int taps, const int* tap_off, const GemmEpilogue& ep, int num_sms,
                  int force_bn = 0);
+// 3xTF32: A = fp32 [a_rows][2 * C_half] holding [hi | lo] halves (hi = the top 19 bits of the value, lo = value - hi) of
+// which the first C channels enter the product, W = fp32 [w_rows][taps * 3 * C] holding per tap [W_hi | W_hi | W_lo];
+// D = sum_t (hi . W_hi + lo . W_hi + hi . W_lo): fp32-class products (the dropped lo . W_lo term is 2^-22 relative), fp32
+// accumulate.  Same epilogues.  C, C_half multiples of 32.
+int gemm_prepare_tf32x3(GemmLaunch* out, const float* A_split, long long a_rows, int C, int C_half, const float* W3, int w_rows,
+                        int M, int N, int taps, const int* tap_off, const GemmEpilogue& ep, int num_sms, int force_bn = 0);
 int gemm_run(const GemmLaunch& g, cudaStream_t stream);
 int gemm_pick_bn(int M, int N, int num_sms);
 

@@ -196,11 +196,17 @@ __global__ void k_gn_apply(const float* __restrict__ x, int H, int W, int C, con
     if (out_dense) *reinterpret_cast<uint2*>(out_dense + (size_t)pix * C + c4) = pk;
   }
 }
-int groupnorm_relu_f16(const float* x, int H, int W, int C, int groups, const float* gamma, const float* beta, float* part,
-                       float* stats, __half* out_padded, __half* out_dense, cudaStream_t s) {
-  const int HW = H * W, nchunks = ceil_div(HW, GN_CHUNK_ROWS);
+// per-channel (mean_g, rstd_g) of GroupNorm(groups) over a dense fp32 [HW][C] conv output (shared with solo_exact.cu)
+int gn_stats(const float* x, int HW, int C, int groups, float* part, float* stats, cudaStream_t s) {
+  const int nchunks = ceil_div(HW, GN_CHUNK_ROWS);
   k_gn_partial<<<nchunks, 256, 0, s>>>(x, HW, C, part);
   k_gn_final<<<1, 32, 0, s>>>(part, nchunks, HW, C, groups, stats);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int groupnorm_relu_f16(const float* x, int H, int W, int C, int groups, const float* gamma, const float* beta, float* part,
+                       float* stats, __half* out_padded, __half* out_dense, cudaStream_t s) {
+  PRISMA_TRY(gn_stats(x, H * W, C, groups, part, stats, s));
   k_gn_apply<<<148 * 4, 256, 0, s>>>(x, H, W, C, stats, gamma, beta, out_padded, out_dense);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
@@ -391,14 +397,17 @@ int solo_gather_kernels(const SoloCand* cand, const int* count, int cap, const f
 }
 
 // masks = p > thr ; sum_masks ; maskness = sum(p * mask) / sum_masks ; score *= maskness (solov2_head.py:724-739)
-__global__ void k_solo_mask_stats(const __half* __restrict__ masks, int HW, float thr, SoloCand* __restrict__ cand,
+__device__ __forceinline__ float mask_f(__half v) { return __half2float(v); }
+__device__ __forceinline__ float mask_f(float v) { return v; }
+template <typename T>
+__global__ void k_solo_mask_stats(const T* __restrict__ masks, int HW, float thr, SoloCand* __restrict__ cand,
                                   const int* __restrict__ count, int cap) {
   const int r = blockIdx.x;
   if (r >= min(*count, cap)) return;
-  const __half* p = masks + (size_t)r * HW;
+  const T* p = masks + (size_t)r * HW;
   float area = 0.f, wsum = 0.f;
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const float v = __half2float(p[i]);
+    const float v = mask_f(p[i]);
     if (v > thr) { area += 1.f; wsum += v; }
   }
   __shared__ float sa[32], sw[32];
@@ -414,7 +423,12 @@ __global__ void k_solo_mask_stats(const __half* __restrict__ masks, int HW, floa
 }
 int solo_mask_stats(const __half* masks, int HW, float mask_thr, SoloCand* cand, const int* count, int cap,
                     cudaStream_t s) {
-  k_solo_mask_stats<<<cap, 256, 0, s>>>(masks, HW, mask_thr, cand, count, cap);
+  k_solo_mask_stats<__half><<<cap, 256, 0, s>>>(masks, HW, mask_thr, cand, count, cap);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int solo_mask_stats(const float* masks, int HW, float mask_thr, SoloCand* cand, const int* count, int cap, cudaStream_t s) {
+  k_solo_mask_stats<float><<<cap, 256, 0, s>>>(masks, HW, mask_thr, cand, count, cap);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -448,18 +462,25 @@ int solo_rank(const SoloCand* cand, const int* count, int cap, int nms_pre, int*
 }
 
 // binary masks of the ranked candidates as an fp16 0/1 matrix [nms_pre_pad][HW]: the operand of inter = M M^T
-__global__ void k_solo_binarize(const __half* __restrict__ masks, int HW, float thr, const int* __restrict__ top,
+template <typename T>
+__global__ void k_solo_binarize(const T* __restrict__ masks, int HW, float thr, const int* __restrict__ top,
                                 const int* __restrict__ n_top, __half* __restrict__ bin) {
   const int k = blockIdx.x;
   __half* o = bin + (size_t)k * HW;
   const int r = k < *n_top ? top[k] : -1;
   const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
   for (int i = threadIdx.x; i < HW; i += blockDim.x)
-    o[i] = (r >= 0 && __half2float(masks[(size_t)r * HW + i]) > thr) ? one : zero;
+    o[i] = (r >= 0 && mask_f(masks[(size_t)r * HW + i]) > thr) ? one : zero;
 }
 int solo_binarize(const __half* masks, int HW, float mask_thr, const int* top, const int* n_top, int nms_pre, __half* bin,
                   cudaStream_t s) {
-  k_solo_binarize<<<nms_pre, 256, 0, s>>>(masks, HW, mask_thr, top, n_top, bin);
+  k_solo_binarize<__half><<<nms_pre, 256, 0, s>>>(masks, HW, mask_thr, top, n_top, bin);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int solo_binarize(const float* masks, int HW, float mask_thr, const int* top, const int* n_top, int nms_pre, __half* bin,
+                  cudaStream_t s) {
+  k_solo_binarize<float><<<nms_pre, 256, 0, s>>>(masks, HW, mask_thr, top, n_top, bin);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -530,16 +551,18 @@ int solo_matrix_nms(const float* inter, int ld, const SoloCand* cand, const int*
 // ori_shape, threshold -- evaluated per output pixel as two nested bilinear taps -- and the band's frame
 // (bands/mask_mmdet.py:43-61,134-146): 255 * (number of instances of the 11 classes above the confidences) mod 256.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float up4_at(const __half* __restrict__ p, int fh, int fw, int yy, int xx) {
+template <typename T>
+__device__ __forceinline__ float up4_at(const T* __restrict__ p, int fh, int fw, int yy, int xx) {
   const float fy = fmaxf(0.25f * (yy + 0.5f) - 0.5f, 0.f), fx = fmaxf(0.25f * (xx + 0.5f) - 0.5f, 0.f);
   const int y0 = (int)fy, x0 = (int)fx;
   const int y1 = y0 + (y0 < fh - 1 ? 1 : 0), x1 = x0 + (x0 < fw - 1 ? 1 : 0);
   const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-  return hy * (hx * __half2float(p[y0 * fw + x0]) + lx * __half2float(p[y0 * fw + x1])) +
-         ly * (hx * __half2float(p[y1 * fw + x0]) + lx * __half2float(p[y1 * fw + x1]));
+  return hy * (hx * mask_f(p[y0 * fw + x0]) + lx * mask_f(p[y0 * fw + x1])) +
+         ly * (hx * mask_f(p[y1 * fw + x0]) + lx * mask_f(p[y1 * fw + x1]));
 }
 __device__ __forceinline__ bool band_class(int l) { return l == 0 || (l >= 14 && l <= 23); }
-__global__ void k_solo_final(const __half* __restrict__ masks, int fh, int fw, int h, int w, int H, int W, float thr,
+template <typename T>
+__global__ void k_solo_final(const T* __restrict__ masks, int fh, int fw, int h, int w, int H, int W, float thr,
                              const int* __restrict__ keep, const float* __restrict__ keep_score, const int* __restrict__ keep_label,
                              const int* __restrict__ n_keep, float confidence, float sy, float sx, uint8_t* __restrict__ inst,
                              uint8_t* __restrict__ uni) {
@@ -556,7 +579,7 @@ __global__ void k_solo_final(const __half* __restrict__ masks, int fh, int fw, i
     for (int k = 0; k < n; ++k) {
       const bool in_band = band_class(keep_label[k]) && keep_score[k] > 0.5f && keep_score[k] > confidence;
       if (!inst && !in_band) continue;
-      const __half* p = masks + (size_t)keep[k] * fh * fw;
+      const T* p = masks + (size_t)keep[k] * fh * fw;
       (void)UH; (void)UW;
       const float v = hy * (hx * up4_at(p, fh, fw, y0, x0) + lx * up4_at(p, fh, fw, y0, x1)) +
                       ly * (hx * up4_at(p, fh, fw, y1, x0) + lx * up4_at(p, fh, fw, y1, x1));
@@ -571,8 +594,17 @@ int solo_final_masks(const __half* masks, int fh, int fw, int h, int w, int H, i
                      const float* keep_score, const int* keep_label, const int* n_keep, int max_num, float confidence,
                      uint8_t* inst_masks, uint8_t* union_mask, cudaStream_t s) {
   (void)max_num;
-  k_solo_final<<<148 * 8, 256, 0, s>>>(masks, fh, fw, h, w, H, W, mask_thr, keep, keep_score, keep_label, n_keep, confidence,
-                                      (float)h / (float)H, (float)w / (float)W, inst_masks, union_mask);
+  k_solo_final<__half><<<148 * 8, 256, 0, s>>>(masks, fh, fw, h, w, H, W, mask_thr, keep, keep_score, keep_label, n_keep, confidence,
+                                              (float)h / (float)H, (float)w / (float)W, inst_masks, union_mask);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int solo_final_masks(const float* masks, int fh, int fw, int h, int w, int H, int W, float mask_thr, const int* keep,
+                     const float* keep_score, const int* keep_label, const int* n_keep, int max_num, float confidence,
+                     uint8_t* inst_masks, uint8_t* union_mask, cudaStream_t s) {
+  (void)max_num;
+  k_solo_final<float><<<148 * 8, 256, 0, s>>>(masks, fh, fw, h, w, H, W, mask_thr, keep, keep_score, keep_label, n_keep, confidence,
+                                             (float)h / (float)H, (float)w / (float)W, inst_masks, union_mask);
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }

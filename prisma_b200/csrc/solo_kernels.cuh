@@ -51,6 +51,25 @@ int solo_final_masks(const __half* masks, int fh, int fw, int h, int w, int H, i
                      const float* keep_score, const int* keep_label, const int* n_keep, int max_num, float confidence,
                      uint8_t* inst_masks, uint8_t* union_mask, cudaStream_t s);
 
+// ---- fp32-class head (solo_exact.cu): split maps = zero-bordered NHWC rows of 2 C floats [hi | lo]; fp32 mask predictions
+int solo_mask_stats(const float* masks, int HW, float mask_thr, SoloCand* cand, const int* count, int cap, cudaStream_t s);
+int solo_binarize(const float* masks, int HW, float mask_thr, const int* top, const int* n_top, int nms_pre, __half* bin,
+                  cudaStream_t s);
+int solo_final_masks(const float* masks, int fh, int fw, int h, int w, int H, int W, float mask_thr, const int* keep,
+                     const float* keep_score, const int* keep_label, const int* n_keep, int max_num, float confidence,
+                     uint8_t* inst_masks, uint8_t* union_mask, cudaStream_t s);
+int solo_dense_to_split(const float* src, int H, int W, int Csrc, float* dst, int Cdst, cudaStream_t s);
+int solo_f16map_to_split(const __half* src, int H, int W, int C, float* dst, int Cdst, cudaStream_t s);
+int groupnorm_relu_split(const float* x, int H, int W, int C, int groups, const float* gamma, const float* beta, float* part,
+                         float* stats, float* out_split, float* out_w3, cudaStream_t s);
+int groupnorm_relu_grid_split(const float* x, int B, int F, GridSizes S, int C, int groups, const float* gamma, const float* beta,
+                              float* out_split, cudaStream_t s);
+int resize_bilinear_split(const float* src, int Hs, int Ws, int Csrc, int Csrc_pitch, float* dst, int Hd, int Wd, int Cdst, int coord,
+                          int accumulate, cudaStream_t s, int dst_frame_w = 0);
+int solo_gather_kernels_split(const SoloCand* cand, const int* count, int cap, const float* const* lvl_kernels,
+                              const int* lvl_cell0, int levels, int num_classes, int C, float* out, cudaStream_t s,
+                              const int* lvl_S = nullptr, int frame = 0);
+
 }  // namespace prisma
 
 namespace prisma {

@@ -102,3 +102,21 @@ def test_conv_matches_torch(H, W, Cin, Cout, k, relu):
     ref = ref[0].permute(1, 2, 0).numpy()
     err = np.abs(y - ref).max()
     assert err <= 2e-4 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(300, 256, 512, 0), (4096, 512, 2304, 0), (1600, 80, 4608, 0), (5000, 128, 320, 128), (64, 32, 100, 32)])
+def test_gemm_tf32x3_is_fp32_class(M, N, K, bn):
+    """The 3xTF32 path (kind::tf32 MMAs on [hi | lo] splits of both operands): against the exact product (float64) the error
+    is that of an fp32 GEMM (a few 1e-7 of sum |a||w|), three orders of magnitude below single-pass fp16 / tf32 operands."""
+    rng = np.random.default_rng(M + N + K)
+    A = (rng.standard_normal((M, K), dtype=np.float32) * rng.uniform(0.01, 30.0, (M, 1)).astype(np.float32))
+    W = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N, dtype=np.float32)
+    D = np.empty((M, N), np.float32)
+    ms = C.c_float()
+    check(lib().prisma_debug_gemm_tf32x3(0, fptr(A), fptr(W), fptr(bias), fptr(D), M, N, K, bn, 1, C.byref(ms)))
+    ref = A.astype(np.float64) @ W.astype(np.float64).T + bias
+    scale = np.abs(A).astype(np.float64) @ np.abs(W).astype(np.float64).T + np.abs(bias)
+    err = float((np.abs(D - ref) / scale).max())
+    print(f"tf32x3 {M}x{N}x{K}: max |err| / sum|a||w| = {err:.2e}, {ms.value * 1e3:.1f} us")
+    assert err <= 2e-6, err
