@@ -166,11 +166,21 @@ int prisma_flow_profile(prisma_engine* e, int h, int w, double scale, int iters,
  *   union_mask   h*w u8: (255 * number of overlapping instances of the 11 band classes above the thresholds) mod 256
  *   n_inst, scores[100], labels[100]: the kept instances of InstanceData (all 80 classes), sorted by score
  *   inst_masks   optional n_inst*h*w u8 0/1 (results.masks)                                                          */
+/* variant: "r101" (the band's SOLOv2 R-101) or "tiny" (test-size twin); a "-fast" suffix selects the single-pass fp16 head.
+ * Default = the fp32-class head: every contraction from the FPN levels to the mask predictions runs as three kind::tf32
+ * tensor-core passes over [hi | lo] splits of both operands with fp32 activations in between, so that the integer / boolean
+ * decode (score_thr, points NMS, mask_thr, Matrix NMS, the final masks) sees the reference's fp32 values to ~1e-6.        */
 int prisma_mask_create(const char* variant, int device, prisma_engine** out);
 int prisma_mask_load_tensor(prisma_engine* e, const char* name, const float* data, const int64_t* shape, int ndim);
 int prisma_mask_finalize(prisma_engine* e);
 int prisma_mask_infer(prisma_engine* e, const uint8_t* rgb, int h, int w, float confidence, uint8_t* union_mask, int* n_inst,
                       float* scores, int32_t* labels, uint8_t* inst_masks, float* ms_out);
+/* Tests: replay SOLOV2Head.forward + get_results (models/dense_heads/solov2_head.py:253-292,582-766) from GIVEN FPN levels
+ * (fp32 NCHW [256][h][w], e.g. the reference's own, tests/golden/solo_tiny_head.npz) for the frame geometry of the last
+ * prisma_mask_infer call: inject the five levels, then run head + decode.  fp32-class head only.                        */
+int prisma_mask_inject_feat(prisma_engine* e, int level, const float* nchw, int h, int w);
+int prisma_mask_infer_from_feats(prisma_engine* e, int h, int w, float confidence, uint8_t* union_mask, int* n_inst, float* scores,
+                                 int32_t* labels, uint8_t* inst_masks);
 /* --sdf (bands/mask_mmdet.py:64-69,150-152): green channel = 255 * (1 - clip(((sdf + 127)/255 - 0.25) * 2, 0, 1)) with sdf the
  * exact Euclidean signed distance of the union mask (what snowy.generate_sdf computes); union_mask / green_out: h*w u8    */
 int prisma_mask_sdf(int device, const uint8_t* union_mask, int h, int w, uint8_t* green_out);

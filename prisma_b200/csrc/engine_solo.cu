@@ -45,7 +45,11 @@ SoloEngine::~SoloEngine() {
   if (stream) cudaStreamDestroy(stream);
 }
 
-int SoloEngine::init(const std::string& v, int dev) {
+int SoloEngine::init(const std::string& vin, int dev) {
+  std::string v = vin;
+  exact_head = true;  // "<variant>-fast": the single-pass fp16 head of round 1 (not mask-id faithful, ~40 % faster per frame)
+  if (v.size() > 5 && v.substr(v.size() - 5) == "-fast") { exact_head = false; v = v.substr(0, v.size() - 5); }
+  if (const char* e = getenv("PRISMA_SOLO_HEAD")) exact_head = std::string(e) != "fast";
   variant = v;
   if (v == "r101") { const int l[4] = {3, 4, 23, 3}; std::copy(l, l + 4, layers); scale_long = 1333; scale_short = 800; }
   else if (v == "tiny") { const int l[4] = {1, 1, 1, 1}; std::copy(l, l + 4, layers); scale_long = 448; scale_short = 256; }
@@ -129,6 +133,45 @@ int SoloEngine::up_conv(const std::string& name, const std::string& bn, const st
   return 0;
 }
 
+// head conv weight [Cout][Cin][k][k] -> fp32 [round_up(Cout,256)][k*k * 3 * cin32], per tap [W_hi | W_hi | W_lo] with
+// W_hi = the weight with its low 13 mantissa bits cleared (a TF32 number), W_lo = W - W_hi: the B operand of
+// gemm_prepare_tf32x3.  GroupNorm affine kept separately, bias fp32.
+int SoloEngine::up_conv3(const std::string& name, const std::string& gn, int Cout, int Cin, int k, bool bias, SoloConvW3* out) {
+  const HostTensor* w = get(name + ".weight");
+  if (!w) return -1;
+  PRISMA_CHECK((long long)w->data.size() == (long long)Cout * Cin * k * k, "SOLOv2 weight '" + name + "' has an unexpected size");
+  const int taps = k * k, c32 = round_up(Cin, 32), K = taps * 3 * c32, rows = round_up(Cout, 256);
+  std::vector<float> h((size_t)rows * K, 0.f);
+  auto hi_of = [](float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; };
+  for (int n = 0; n < Cout; ++n)
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < Cin; ++c) {
+        const float v = w->data[((size_t)n * Cin + c) * taps + t], hi = hi_of(v);
+        float* base = h.data() + (size_t)n * K + (size_t)t * 3 * c32;
+        base[c] = hi; base[c32 + c] = hi; base[2 * c32 + c] = v - hi;
+      }
+  PRISMA_TRY(s_alloc(allocs, &out->w, h.size()));
+  PRISMA_CUDA_OK(cudaMemcpy(out->w, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<float> bv(round_up(Cout, 8), 0.f);
+  if (bias) {
+    const HostTensor* b = get(name + ".bias");
+    if (!b) return -1;
+    for (int n = 0; n < Cout; ++n) bv[n] = b->data[n];
+  }
+  PRISMA_TRY(s_alloc(allocs, &out->b, bv.size()));
+  PRISMA_CUDA_OK(cudaMemcpy(out->b, bv.data(), bv.size() * 4, cudaMemcpyHostToDevice));
+  if (!gn.empty()) {
+    const HostTensor *g = get(gn + ".weight"), *be = get(gn + ".bias");
+    if (!g || !be) return -1;
+    PRISMA_TRY(s_alloc(allocs, &out->gn_w, (size_t)Cout));
+    PRISMA_TRY(s_alloc(allocs, &out->gn_b, (size_t)Cout));
+    PRISMA_CUDA_OK(cudaMemcpy(out->gn_w, g->data.data(), Cout * 4, cudaMemcpyHostToDevice));
+    PRISMA_CUDA_OK(cudaMemcpy(out->gn_b, be->data.data(), Cout * 4, cudaMemcpyHostToDevice));
+  }
+  out->cout = Cout; out->cin = Cin; out->cin32 = c32; out->k = k;
+  return 0;
+}
+
 int SoloEngine::finalize() {
   PRISMA_CHECK(!finalized, "finalize called twice");
   PRISMA_CUDA_OK(cudaSetDevice(device));
@@ -175,6 +218,21 @@ int SoloEngine::finalize() {
   }
   PRISMA_TRY(up_conv("mask_head.conv_cls", "", "", SOLO_NC, 512, 3, true, &conv_cls));
   PRISMA_TRY(up_conv("mask_head.conv_kernel", "", "", 256, 512, 3, true, &conv_kernel));
+  if (exact_head) {  // the same head in fp32 [hi | hi | lo] for the 3xTF32 path
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < std::max(i, 1); ++j) {
+        const std::string n = m + "convs_all_levels." + std::to_string(i) + ".conv" + std::to_string(j);
+        PRISMA_TRY(up_conv3(n + ".conv", n + ".gn", 128, j == 0 ? (i == 3 ? 258 : 256) : 128, 3, false, &mf3[i][j]));
+      }
+    PRISMA_TRY(up_conv3(m + "conv_pred.conv", m + "conv_pred.gn", 256, 128, 1, false, &mf_pred3));
+    for (int i = 0; i < 4; ++i) {
+      const std::string kn = "mask_head.kernel_convs." + std::to_string(i), cn = "mask_head.cls_convs." + std::to_string(i);
+      PRISMA_TRY(up_conv3(kn + ".conv", kn + ".gn", 512, i == 0 ? 258 : 512, 3, false, &kconv3[i]));
+      PRISMA_TRY(up_conv3(cn + ".conv", cn + ".gn", 512, i == 0 ? 256 : 512, 3, false, &cconv3[i]));
+    }
+    PRISMA_TRY(up_conv3("mask_head.conv_cls", "", SOLO_NC, 512, 3, true, &conv_cls3));
+    PRISMA_TRY(up_conv3("mask_head.conv_kernel", "", 256, 512, 3, true, &conv_kernel3));
+  }
   host.clear();
   finalized = true;
   return 0;
@@ -322,10 +380,24 @@ int SoloEngine::build_plan(int H, int W) {
   { const SMap a = P[3], o = P[4]; push_step([=](cudaStream_t s) { return subsample2_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, s); }); }
   for (int i = 0; i < 5; ++i) taps["fpn" + std::to_string(i)] = {P[i].p, 1, P[i].H, P[i].W, 256};
 
-  cur_tag = "mask_feature_head";
-  // ---- mask feature head (solov2_head.py:133-150)
+  head_step0 = steps.size();
   fh = P[0].H; fw = P[0].W;
   const int HW = fh * fw;
+  const int F = *std::max_element(num_grids, num_grids + 5), FP = (F + 2) * (F + 2);
+  GridSizes gs;
+  for (int l = 0; l < 8; ++l) gs.s[l] = l < 5 ? num_grids[l] : 0;
+  int cell0[5], cells = 0;
+  for (int l = 0; l < 5; ++l) { cell0[l] = cells; cells += num_grids[l] * num_grids[l]; }
+  float *ker_all = nullptr, *cls_all = nullptr;  // dense fp32 [5][F*F][256] / [5][F*F][80]
+  PRISMA_TRY(s_alloc(plan_allocs, &ker_all, (size_t)5 * F * F * 256));
+  PRISMA_TRY(s_alloc(plan_allocs, &cls_all, (size_t)5 * F * F * SOLO_NC));
+  float* tower_raw = nullptr;  // dense fp32 conv output [5][F*F][512]
+  PRISMA_TRY(s_alloc(plan_allocs, &tower_raw, (size_t)5 * F * F * 512));
+  __half* mfeat = nullptr;   // fast head: dense [HW][256] fp16, the "weight" of the dynamic-conv GEMM
+  float* mfeat3 = nullptr;   // exact head: dense [HW][3 * 256] fp32 = [hi | hi | lo]
+  if (!exact_head) {
+  cur_tag = "mask_feature_head";
+  // ---- mask feature head (solov2_head.py:133-150)
   SMap acc;
   PRISMA_TRY(new_map(&acc, fh, fw, 128));
   PRISMA_TRY(gnconv(P[0], 256, mf[0][0], &acc, nullptr));
@@ -350,7 +422,6 @@ int SoloEngine::build_plan(int H, int W) {
       cur = u; cin_cols = 128;
     }
   }
-  __half* mfeat = nullptr;  // dense [HW][256] fp16, rows padded for its role as the "weight" of the dynamic-conv GEMM
   PRISMA_TRY(s_alloc(plan_allocs, &mfeat, (size_t)round_up(HW, 256) * 256));
   PRISMA_TRY(gnconv(acc, 128, mf_pred, nullptr, mfeat));
   taps["mask_feats"] = {mfeat, 2, HW, 256, 0};
@@ -365,13 +436,8 @@ int SoloEngine::build_plan(int H, int W) {
   const SMap lvl_in[5] = {R0, P[1], P[2], P[3], R4};
   // The five levels share the tower weights: they run as one stack of F x F frames (F = largest grid), level l in the
   // top-left S_l x S_l of frame l; pixels outside stay zero = the convs' zero padding.  10 GEMMs + 8 GroupNorms in total.
-  const int F = *std::max_element(num_grids, num_grids + 5), FP = (F + 2) * (F + 2);
-  GridSizes gs;
-  for (int l = 0; l < 8; ++l) gs.s[l] = l < 5 ? num_grids[l] : 0;
   struct TMap { __half* p; int C; };
   auto new_tmap = [&](TMap* t, int c) -> int { t->C = c; return s_alloc(plan_allocs, &t->p, (size_t)5 * FP * c); };
-  float* tower_raw = nullptr;  // dense fp32 conv output [5][F*F][512]
-  PRISMA_TRY(s_alloc(plan_allocs, &tower_raw, (size_t)5 * F * F * 512));
   auto conv_t = [&](const TMap& in, int cin_cols, const SoloConvW& w, GemmEpilogue ep, float* dst_dense) -> int {
     int off[9];
     for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky - 1) * (F + 2) + (kx - 1);
@@ -395,17 +461,12 @@ int SoloEngine::build_plan(int H, int W) {
   PRISMA_TRY(new_tmap(&g0, 320));
   PRISMA_TRY(new_tmap(&ka, 512)); PRISMA_TRY(new_tmap(&kb, 512));
   PRISMA_TRY(new_tmap(&ca, 512)); PRISMA_TRY(new_tmap(&cb, 512));
-  int cell0[5], cells = 0;
   for (int l = 0; l < 5; ++l) {
     const int S = num_grids[l];
-    cell0[l] = cells; cells += S * S;
     const SMap a = lvl_in[l];
     __half* dst = g0.p + (size_t)l * FP * 320;
     push_step([=](cudaStream_t s) { return resize_bilinear_f16(a.p, a.H, a.W, 256, dst, S, S, 320, 1, 0, s, F); });
   }
-  float *ker_all = nullptr, *cls_all = nullptr;  // dense fp32 [5][F*F][256] / [5][F*F][80]
-  PRISMA_TRY(s_alloc(plan_allocs, &ker_all, (size_t)5 * F * F * 256));
-  PRISMA_TRY(s_alloc(plan_allocs, &cls_all, (size_t)5 * F * F * SOLO_NC));
   PRISMA_TRY(gnconv_t(g0, 320, kconv[0], ka));
   PRISMA_TRY(gnconv_t(ka, 512, kconv[1], kb));
   PRISMA_TRY(gnconv_t(kb, 512, kconv[2], ka));
@@ -416,6 +477,125 @@ int SoloEngine::build_plan(int H, int W) {
   PRISMA_TRY(gnconv_t(cb, 512, cconv[2], ca));
   PRISMA_TRY(gnconv_t(ca, 512, cconv[3], cb));
   { GemmEpilogue ep; ep.bias = conv_cls.b; PRISMA_TRY(conv_t(cb, 512, conv_cls, ep, cls_all)); }
+  } else {
+  // ================================================================ fp32-class head (solo_exact.cu, gemm_prepare_tf32x3)
+  cur_tag = "mask_feature_head";
+  auto new_xmap = [&](XMap* mm, int h, int w, int c) -> int {
+    mm->H = h; mm->W = w; mm->C = c;
+    return s_alloc(plan_allocs, &mm->p, (size_t)mm->rows() * 2 * c);
+  };
+  // conv on a split map -> dense fp32 [H*W][Cout]; c_used = channels of the map that enter the product (multiple of 32)
+  auto conv_x = [&](const XMap& in, int c_used, const SoloConvW3& w, GemmEpilogue ep, float* dst_dense) -> int {
+    PRISMA_CHECK(c_used == w.cin32 && c_used <= in.C, "solo(exact): operand channels do not match the packed weights");
+    int off[9], taps_n = w.k * w.k;
+    if (w.k == 3) { for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky - 1) * in.Wp() + (kx - 1); }
+    else off[0] = 0;
+    ep.in_w = in.Wp(); ep.in_h = in.Hp(); ep.img_rows = 0; ep.sub = 1; ep.pad = 1;
+    ep.row_map = ROW_PAD2TOK; ep.out_f32 = dst_dense; ep.out_f32_ld = w.cout;
+    GemmLaunch g;
+    PRISMA_TRY(gemm_prepare_tf32x3(&g, in.p, in.rows(), c_used, in.C, w.w, round_up(w.cout, 256), (int)in.rows(), w.cout, taps_n, off,
+                                   ep, num_sms));
+    flops += 2.0 * in.H * (double)in.W * taps_n * w.cin * w.cout;
+    push_step([g](cudaStream_t s) { return gemm_run(g, s); });
+    return 0;
+  };
+  auto gnconv_x = [&](const XMap& in, int c_used, const SoloConvW3& w, const XMap* dst_map, float* dst_w3) -> int {
+    GemmEpilogue ep;
+    PRISMA_TRY(conv_x(in, c_used, w, ep, gn_raw));
+    const int h = in.H, ww = in.W, c = w.cout; const float* gw = w.gn_w; const float* gb = w.gn_b;
+    float* dm = dst_map ? dst_map->p : nullptr;
+    push_step([=](cudaStream_t s) { return groupnorm_relu_split(gn_raw, h, ww, c, 32, gw, gb, gn_part, gn_stats, dm, dst_w3, s); });
+    return 0;
+  };
+  // FPN levels as split maps: from the fp16 maps of the backbone (lo = 0), or -- tests -- from injected fp32 levels
+  XMap PX[5];
+  for (int i = 0; i < 5; ++i) {
+    PRISMA_TRY(new_xmap(&PX[i], P[i].H, P[i].W, 256));
+    PRISMA_TRY(s_alloc(plan_allocs, &d_feat_in[i], (size_t)P[i].H * P[i].W * 256));
+    feat_h[i] = P[i].H; feat_w[i] = P[i].W;
+    const SMap a = P[i]; const XMap o = PX[i]; const float* inj = d_feat_in[i]; const bool* flag = &inject;
+    push_step([=](cudaStream_t s) {
+      return *flag ? solo_dense_to_split(inj, a.H, a.W, 256, o.p, 256, s) : solo_f16map_to_split(a.p, a.H, a.W, 256, o.p, 256, s);
+    });
+  }
+  XMap accx;
+  PRISMA_TRY(new_xmap(&accx, fh, fw, 128));
+  PRISMA_TRY(gnconv_x(PX[0], 256, mf3[0][0], &accx, nullptr));
+  for (int i = 1; i < 4; ++i) {
+    XMap cur = PX[i];
+    int c_used = 256;
+    if (i == 3) {  // + generate_coordinate channels: 258 -> a 288-channel split map (zeros above 258)
+      XMap cc;
+      PRISMA_TRY(new_xmap(&cc, PX[3].H, PX[3].W, 288));
+      const XMap a = PX[3];
+      push_step([=](cudaStream_t s) { return resize_bilinear_split(a.p, a.H, a.W, 256, 256, cc.p, cc.H, cc.W, 288, 1, 0, s); });
+      cur = cc; c_used = 288;
+    }
+    for (int j = 0; j < i; ++j) {
+      XMap t, u;
+      PRISMA_TRY(new_xmap(&t, cur.H, cur.W, 128));
+      PRISMA_TRY(gnconv_x(cur, c_used, mf3[i][j], &t, nullptr));
+      const bool last = j == i - 1;
+      if (last) u = accx; else PRISMA_TRY(new_xmap(&u, 2 * t.H, 2 * t.W, 128));
+      PRISMA_CHECK(u.H == 2 * t.H && u.W == 2 * t.W, "solo: FPN levels are not exact halvings (pad to a multiple of 32)");
+      push_step([=](cudaStream_t s) { return resize_bilinear_split(t.p, t.H, t.W, 128, 128, u.p, u.H, u.W, 128, 0, last ? 1 : 0, s); });
+      cur = u; c_used = 128;
+    }
+  }
+  PRISMA_TRY(s_alloc(plan_allocs, &mfeat3, (size_t)round_up(HW, 256) * 3 * 256));
+  PRISMA_TRY(gnconv_x(accx, 128, mf_pred3, nullptr, mfeat3));
+  taps["mask_feats"] = {mfeat3, 6, HW, 256, 0};
+
+  cur_tag = "towers";
+  XMap R0x, R4x;
+  PRISMA_TRY(new_xmap(&R0x, P[1].H, P[1].W, 256));
+  PRISMA_TRY(new_xmap(&R4x, P[3].H, P[3].W, 256));
+  { const XMap a = PX[0], o = R0x; push_step([=](cudaStream_t s) { return resize_bilinear_split(a.p, a.H, a.W, 256, 256, o.p, o.H, o.W, 256, 0, 0, s); }); }
+  { const XMap a = PX[4], o = R4x; push_step([=](cudaStream_t s) { return resize_bilinear_split(a.p, a.H, a.W, 256, 256, o.p, o.H, o.W, 256, 0, 0, s); }); }
+  const XMap lvl_inx[5] = {R0x, PX[1], PX[2], PX[3], R4x};
+  struct TXMap { float* p; int C; };
+  auto new_txmap = [&](TXMap* t, int c) -> int { t->C = c; return s_alloc(plan_allocs, &t->p, (size_t)5 * FP * 2 * c); };
+  auto conv_tx = [&](const TXMap& in, int c_used, const SoloConvW3& w, GemmEpilogue ep, float* dst_dense) -> int {
+    PRISMA_CHECK(c_used == w.cin32 && c_used <= in.C, "solo(exact): tower operand channels do not match the packed weights");
+    int off[9];
+    for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky - 1) * (F + 2) + (kx - 1);
+    ep.in_w = F + 2; ep.in_h = F + 2; ep.img_rows = FP; ep.sub = 1; ep.pad = 1;
+    ep.row_map = ROW_PAD2TOK; ep.out_f32 = dst_dense; ep.out_f32_ld = w.cout;
+    GemmLaunch g;
+    PRISMA_TRY(gemm_prepare_tf32x3(&g, in.p, 5LL * FP, c_used, in.C, w.w, round_up(w.cout, 256), 5 * FP, w.cout, 9, off, ep, num_sms));
+    double px = 0; for (int l = 0; l < 5; ++l) px += (double)num_grids[l] * num_grids[l];
+    flops += 2.0 * px * 9 * w.cin * w.cout;
+    push_step([g](cudaStream_t s) { return gemm_run(g, s); });
+    return 0;
+  };
+  auto gnconv_tx = [&](const TXMap& in, int c_used, const SoloConvW3& w, const TXMap& out) -> int {
+    GemmEpilogue ep;
+    PRISMA_TRY(conv_tx(in, c_used, w, ep, tower_raw));
+    const float* gw = w.gn_w; const float* gb = w.gn_b; float* o = out.p; const int c = w.cout;
+    push_step([=](cudaStream_t s) { return groupnorm_relu_grid_split(tower_raw, 5, F, gs, c, 32, gw, gb, o, s); });
+    return 0;
+  };
+  TXMap g0x, kax, kbx, cax, cbx;
+  PRISMA_TRY(new_txmap(&g0x, 288));
+  PRISMA_TRY(new_txmap(&kax, 512)); PRISMA_TRY(new_txmap(&kbx, 512));
+  PRISMA_TRY(new_txmap(&cax, 512)); PRISMA_TRY(new_txmap(&cbx, 512));
+  for (int l = 0; l < 5; ++l) {
+    const int S = num_grids[l];
+    const XMap a = lvl_inx[l];
+    float* dst = g0x.p + (size_t)l * FP * 2 * 288;
+    push_step([=](cudaStream_t s) { return resize_bilinear_split(a.p, a.H, a.W, 256, 256, dst, S, S, 288, 1, 0, s, F); });
+  }
+  PRISMA_TRY(gnconv_tx(g0x, 288, kconv3[0], kax));
+  PRISMA_TRY(gnconv_tx(kax, 512, kconv3[1], kbx));
+  PRISMA_TRY(gnconv_tx(kbx, 512, kconv3[2], kax));
+  PRISMA_TRY(gnconv_tx(kax, 512, kconv3[3], kbx));
+  { GemmEpilogue ep; ep.bias = conv_kernel3.b; PRISMA_TRY(conv_tx(kbx, 512, conv_kernel3, ep, ker_all)); }
+  PRISMA_TRY(gnconv_tx(g0x, 256, cconv3[0], cax));
+  PRISMA_TRY(gnconv_tx(cax, 512, cconv3[1], cbx));
+  PRISMA_TRY(gnconv_tx(cbx, 512, cconv3[2], cax));
+  PRISMA_TRY(gnconv_tx(cax, 512, cconv3[3], cbx));
+  { GemmEpilogue ep; ep.bias = conv_cls3.b; PRISMA_TRY(conv_tx(cbx, 512, conv_cls3, ep, cls_all)); }
+  }
   float* cls_out[5]; float* ker_out[5];
   for (int l = 0; l < 5; ++l) {
     cls_out[l] = cls_all + (size_t)l * F * F * SOLO_NC;
@@ -442,8 +622,6 @@ int SoloEngine::build_plan(int H, int W) {
     push_step([=](cudaStream_t s) { return solo_candidates(lg, S, c0, SOLO_NC, 0.1f, st, cand_raw, cnt, SOLO_CAP, s, F); });
   }
   { int* cnt = d_count; push_step([=](cudaStream_t s) { return solo_sort_candidates(cand_raw, cnt, SOLO_CAP, cand, s); }); }
-  __half* kmat = nullptr;
-  PRISMA_TRY(s_alloc(plan_allocs, &kmat, (size_t)SOLO_CAP * 256));
   const float** d_lvl_ptr = nullptr; int* d_cell0 = nullptr;
   PRISMA_TRY(s_alloc(plan_allocs, &d_lvl_ptr, 8));
   PRISMA_TRY(s_alloc(plan_allocs, &d_cell0, 8));
@@ -452,28 +630,54 @@ int SoloEngine::build_plan(int H, int W) {
   int* d_lvl_S = nullptr;
   PRISMA_TRY(s_alloc(plan_allocs, &d_lvl_S, 8));
   PRISMA_CUDA_OK(cudaMemcpy(d_lvl_S, num_grids, 5 * sizeof(int), cudaMemcpyHostToDevice));
-  { const int* cnt = d_count;
-    push_step([=](cudaStream_t s) { return solo_gather_kernels(cand, cnt, SOLO_CAP, d_lvl_ptr, d_cell0, 5, SOLO_NC, 256, kmat, s, d_lvl_S, F); }); }
-  // dynamic conv: mask_preds = sigmoid(kernels [n][256] . mask_feats [HW][256]^T) as one GEMM (solov2_head.py:717-722)
-  __half* masks = nullptr;
-  PRISMA_TRY(s_alloc(plan_allocs, &masks, (size_t)SOLO_CAP * HW));
-  d_masks = masks;
-  {
-    GemmEpilogue ep; ep.act = 3; ep.out_f16 = masks; ep.out_f16_ld = HW;
-    GemmLaunch g;
-    PRISMA_TRY(gemm_prepare(&g, kmat, SOLO_CAP, 256, 256, mfeat, round_up(HW, 256), SOLO_CAP, HW, 1, zero_off, ep, num_sms));
-    flops += 2.0 * SOLO_CAP * (double)HW * 256;
-    push_step([g](cudaStream_t s) { return gemm_run(g, s); });
-  }
-  { const int* cnt = d_count; const int hw = HW;
-    push_step([=](cudaStream_t s) { return solo_mask_stats(masks, hw, 0.5f, cand, cnt, SOLO_CAP, s); });
-    int* top = d_top; int* ntop = d_ntop;
-    push_step([=](cudaStream_t s) { return solo_rank(cand, cnt, SOLO_CAP, SOLO_NMS_PRE, top, ntop, s); }); }
   __half* bin = nullptr; float* inter = nullptr;
   PRISMA_TRY(s_alloc(plan_allocs, &bin, (size_t)SOLO_NMS_PAD * HW));
   PRISMA_TRY(s_alloc(plan_allocs, &inter, (size_t)SOLO_NMS_PAD * SOLO_NMS_PAD));
-  { const int* top = d_top; const int* ntop = d_ntop; const int hw = HW;
-    push_step([=](cudaStream_t s) { return solo_binarize(masks, hw, 0.5f, top, ntop, SOLO_NMS_PAD, bin, s); }); }
+  d_masks = nullptr; d_masks_f = nullptr;
+  if (!exact_head) {
+    __half* kmat = nullptr;
+    PRISMA_TRY(s_alloc(plan_allocs, &kmat, (size_t)SOLO_CAP * 256));
+    { const int* cnt = d_count;
+      push_step([=](cudaStream_t s) { return solo_gather_kernels(cand, cnt, SOLO_CAP, d_lvl_ptr, d_cell0, 5, SOLO_NC, 256, kmat, s, d_lvl_S, F); }); }
+    // dynamic conv: mask_preds = sigmoid(kernels [n][256] . mask_feats [HW][256]^T) as one GEMM (solov2_head.py:717-722)
+    __half* masks = nullptr;
+    PRISMA_TRY(s_alloc(plan_allocs, &masks, (size_t)SOLO_CAP * HW));
+    d_masks = masks;
+    {
+      GemmEpilogue ep; ep.act = 3; ep.out_f16 = masks; ep.out_f16_ld = HW;
+      GemmLaunch g;
+      PRISMA_TRY(gemm_prepare(&g, kmat, SOLO_CAP, 256, 256, mfeat, round_up(HW, 256), SOLO_CAP, HW, 1, zero_off, ep, num_sms));
+      flops += 2.0 * SOLO_CAP * (double)HW * 256;
+      push_step([g](cudaStream_t s) { return gemm_run(g, s); });
+    }
+    { const int* cnt = d_count; const int hw = HW;
+      push_step([=](cudaStream_t s) { return solo_mask_stats(masks, hw, 0.5f, cand, cnt, SOLO_CAP, s); });
+      int* top = d_top; int* ntop = d_ntop;
+      push_step([=](cudaStream_t s) { return solo_rank(cand, cnt, SOLO_CAP, SOLO_NMS_PRE, top, ntop, s); }); }
+    { const int* top = d_top; const int* ntop = d_ntop; const int hw = HW;
+      push_step([=](cudaStream_t s) { return solo_binarize(masks, hw, 0.5f, top, ntop, SOLO_NMS_PAD, bin, s); }); }
+  } else {
+    float* kmatx = nullptr;  // candidate kernels as split rows [cap][2 * 256]
+    PRISMA_TRY(s_alloc(plan_allocs, &kmatx, (size_t)SOLO_CAP * 512));
+    { const int* cnt = d_count;
+      push_step([=](cudaStream_t s) { return solo_gather_kernels_split(cand, cnt, SOLO_CAP, d_lvl_ptr, d_cell0, 5, SOLO_NC, 256, kmatx, s, d_lvl_S, F); }); }
+    float* masksf = nullptr;  // fp32 sigmoid mask predictions [cap][HW]
+    PRISMA_TRY(s_alloc(plan_allocs, &masksf, (size_t)SOLO_CAP * HW));
+    d_masks_f = masksf;
+    {
+      GemmEpilogue ep; ep.act = 6; ep.out_f32 = masksf; ep.out_f32_ld = HW;
+      GemmLaunch g;
+      PRISMA_TRY(gemm_prepare_tf32x3(&g, kmatx, SOLO_CAP, 256, 256, mfeat3, round_up(HW, 256), SOLO_CAP, HW, 1, zero_off, ep, num_sms));
+      flops += 2.0 * SOLO_CAP * (double)HW * 256;
+      push_step([g](cudaStream_t s) { return gemm_run(g, s); });
+    }
+    { const int* cnt = d_count; const int hw = HW;
+      push_step([=](cudaStream_t s) { return solo_mask_stats(masksf, hw, 0.5f, cand, cnt, SOLO_CAP, s); });
+      int* top = d_top; int* ntop = d_ntop;
+      push_step([=](cudaStream_t s) { return solo_rank(cand, cnt, SOLO_CAP, SOLO_NMS_PRE, top, ntop, s); }); }
+    { const int* top = d_top; const int* ntop = d_ntop; const int hw = HW;
+      push_step([=](cudaStream_t s) { return solo_binarize(masksf, hw, 0.5f, top, ntop, SOLO_NMS_PAD, bin, s); }); }
+  }
   {  // inter_matrix = M M^T over binary masks (matrix_nms.py:70-71): exact in fp32 (counts < 2^24)
     GemmEpilogue ep; ep.out_f32 = inter; ep.out_f32_ld = SOLO_NMS_PAD;
     GemmLaunch g;
@@ -539,8 +743,12 @@ int SoloEngine::infer(const uint8_t* rgb, int H, int W, float confidence, uint8_
   }
   PRISMA_CUDA_OK(cudaEventRecord(ev0, stream));
   PRISMA_TRY(run(stream));
-  PRISMA_TRY(solo_final_masks(d_masks, fh, fw, nh, nw, H, W, 0.5f, d_keep, d_keep_score, d_keep_label, d_nkeep, SOLO_MAX,
-                              confidence, inst_masks_out ? d_inst : nullptr, d_union, stream));
+  if (exact_head)
+    PRISMA_TRY(solo_final_masks(d_masks_f, fh, fw, nh, nw, H, W, 0.5f, d_keep, d_keep_score, d_keep_label, d_nkeep, SOLO_MAX,
+                                confidence, inst_masks_out ? d_inst : nullptr, d_union, stream));
+  else
+    PRISMA_TRY(solo_final_masks(d_masks, fh, fw, nh, nw, H, W, 0.5f, d_keep, d_keep_score, d_keep_label, d_nkeep, SOLO_MAX,
+                                confidence, inst_masks_out ? d_inst : nullptr, d_union, stream));
   PRISMA_CUDA_OK(cudaEventRecord(ev1, stream));
   int n = 0, cnt = 0;
   PRISMA_CUDA_OK(cudaMemcpyAsync(&n, d_nkeep, 4, cudaMemcpyDeviceToHost, stream));
@@ -553,6 +761,44 @@ int SoloEngine::infer(const uint8_t* rgb, int H, int W, float confidence, uint8_
   if (inst_masks_out && n > 0) PRISMA_CUDA_OK(cudaMemcpy(inst_masks_out, d_inst, (size_t)n * H * W, cudaMemcpyDeviceToHost));
   if (n_out) *n_out = n;
   if (ms_out) { float ms = 0; PRISMA_CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1)); *ms_out = ms; }
+  return 0;
+}
+
+// ---- tests: head + decode replayed from given FPN levels (the reference's own levels, tests/golden/solo_tiny_head.npz)
+int SoloEngine::inject_feat(int level, const float* nchw, int h, int w) {
+  PRISMA_CHECK(exact_head, "feature injection exists for the fp32-class head only");
+  PRISMA_CHECK(level >= 0 && level < 5 && d_feat_in[level] != nullptr, "no plan yet: call infer once at the frame size");
+  PRISMA_CHECK(h == feat_h[level] && w == feat_w[level], "injected level has the wrong size for the planned frame");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  std::vector<float> nhwc((size_t)h * w * 256);
+  for (int c = 0; c < 256; ++c)
+    for (int p = 0; p < h * w; ++p) nhwc[(size_t)p * 256 + c] = nchw[(size_t)c * h * w + p];
+  PRISMA_CUDA_OK(cudaMemcpy(d_feat_in[level], nhwc.data(), nhwc.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int SoloEngine::infer_from_feats(int H, int W, float confidence, uint8_t* union_out, int* n_out, float* scores_out, int* labels_out,
+                                 uint8_t* inst_masks_out) {
+  PRISMA_CHECK(exact_head && plan_H == H && plan_W == W, "infer_from_feats: call infer once at this frame size first");
+  PRISMA_CUDA_OK(cudaSetDevice(device));
+  if (inst_masks_out && !d_inst) PRISMA_TRY(s_alloc(plan_allocs, &d_inst, (size_t)SOLO_MAX * H * W));
+  inject = true;  // the level-conversion steps read this flag when they run (here: directly, not through the graph)
+  int r = 0;
+  for (size_t i = head_step0; i < steps.size() && r == 0; ++i) r = steps[i](stream);
+  inject = false;
+  if (r != 0) return r;
+  PRISMA_TRY(solo_final_masks(d_masks_f, fh, fw, nh, nw, H, W, 0.5f, d_keep, d_keep_score, d_keep_label, d_nkeep, SOLO_MAX, confidence,
+                              inst_masks_out ? d_inst : nullptr, d_union, stream));
+  int n = 0, cnt = 0;
+  PRISMA_CUDA_OK(cudaMemcpyAsync(&n, d_nkeep, 4, cudaMemcpyDeviceToHost, stream));
+  PRISMA_CUDA_OK(cudaMemcpyAsync(&cnt, d_count, 4, cudaMemcpyDeviceToHost, stream));
+  if (union_out) PRISMA_CUDA_OK(cudaMemcpyAsync(union_out, d_union, (size_t)H * W, cudaMemcpyDeviceToHost, stream));
+  if (scores_out) PRISMA_CUDA_OK(cudaMemcpyAsync(scores_out, d_keep_score, SOLO_MAX * 4, cudaMemcpyDeviceToHost, stream));
+  if (labels_out) PRISMA_CUDA_OK(cudaMemcpyAsync(labels_out, d_keep_label, SOLO_MAX * 4, cudaMemcpyDeviceToHost, stream));
+  PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
+  PRISMA_CHECK(cnt <= SOLO_CAP, "solo: more than 4096 grid cells passed score_thr (candidate capacity exceeded)");
+  if (inst_masks_out && n > 0) PRISMA_CUDA_OK(cudaMemcpy(inst_masks_out, d_inst, (size_t)n * H * W, cudaMemcpyDeviceToHost));
+  if (n_out) *n_out = n;
   return 0;
 }
 
@@ -574,6 +820,15 @@ long long SoloEngine::read_tap(const std::string& name, float* out, long long ca
     std::vector<__half> h(n);
     if (cudaMemcpy(h.data(), t.p, n * 2, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
     for (long long i = 0; i < n; ++i) out[i] = __half2float(h[i]);
+    return n;
+  }
+  if (t.kind == 6) {  // fp32 [a][3 b] rows = [hi | hi | lo] -> dense [a][b] values
+    const long long n = (long long)t.a * t.b;
+    if (n > capacity) { set_last_error("tap buffer too small"); return -1; }
+    std::vector<float> h((size_t)t.a * 3 * t.b);
+    if (cudaMemcpy(h.data(), t.p, h.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("tap copy failed"); return -2; }
+    for (long long r = 0; r < t.a; ++r)
+      for (int c = 0; c < t.b; ++c) out[r * t.b + c] = h[(size_t)r * 3 * t.b + c] + h[(size_t)r * 3 * t.b + 2 * t.b + c];
     return n;
   }
   if (t.kind == 3) {

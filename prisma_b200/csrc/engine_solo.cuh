@@ -11,6 +11,9 @@
 namespace prisma {
 
 struct SoloConvW { __half* w = nullptr; float* b = nullptr; float* gn_w = nullptr; float* gn_b = nullptr; int cout = 0, cin = 0, k = 1; };
+struct SoloConvW3 { float* w = nullptr; float* b = nullptr; float* gn_w = nullptr; float* gn_b = nullptr; int cout = 0, cin = 0, cin32 = 0, k = 1; };
+struct XMap { float* p = nullptr; int H = 0, W = 0, C = 0;   // split map: zero-bordered NHWC rows of 2 C floats [hi | lo] (solo_exact.cu)
+              int Hp() const { return H + 2; } int Wp() const { return W + 2; } long long rows() const { return (long long)Hp() * Wp(); } };
 struct SMap { __half* p = nullptr; int H = 0, W = 0, C = 0;
               int Hp() const { return H + 2; } int Wp() const { return W + 2; } long long rows() const { return (long long)Hp() * Wp(); } };
 struct SoloTap { const void* p; int kind; int a, b, c; };  // kind 0: f32 [a][b], 1: padded f16 map (H=a,W=b,C=c), 2: f16 [a][b], 3: u8 [a][b]
@@ -24,6 +27,12 @@ class SoloEngine {
   // one frame: union mask (H x W u8, the band's frame), kept instances (<= 100): scores, labels, optional masks [n][H][W]
   int infer(const uint8_t* rgb, int H, int W, float confidence, uint8_t* union_out, int* n_out, float* scores_out,
             int* labels_out, uint8_t* inst_masks_out, float* ms_out);
+  // Tests: replace FPN level `level` of the NEXT head replay by these values (dense fp32 NCHW [256][h][w]) ...
+  int inject_feat(int level, const float* nchw, int h, int w);
+  // ... and run head + decode from the injected levels (frame geometry H x W as planned by a previous infer call)
+  int infer_from_feats(int H, int W, float confidence, uint8_t* union_out, int* n_out, float* scores_out, int* labels_out,
+                       uint8_t* inst_masks_out);
+  bool exact_head = true;   // fp32-class head + decode (3xTF32 contractions, fp32 activations): the default of the band
   long long read_tap(const std::string& name, float* out, long long capacity);
   int net_shape(int H, int W, int* nh, int* nw, int* hp, int* wp) const;
   double flops = 0;
@@ -56,6 +65,13 @@ class SoloEngine {
   struct Block { SoloConvW c1, c2, c3, ds; bool has_ds = false; int stride = 1; };
   std::vector<Block> blocks[4];
   SoloConvW lateral[4], fpnc[4], mf[4][3], mf_pred, kconv[4], cconv[4], conv_cls, conv_kernel;
+  SoloConvW3 mf3[4][3], mf_pred3, kconv3[4], cconv3[4], conv_cls3, conv_kernel3;  // the head in [hi | hi | lo] fp32 (exact_head)
+  int up_conv3(const std::string& name, const std::string& gn, int Cout, int Cin, int k, bool bias, SoloConvW3* out);
+  float* d_feat_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // injected FPN levels, dense fp32 NHWC
+  int feat_h[5] = {0, 0, 0, 0, 0}, feat_w[5] = {0, 0, 0, 0, 0};
+  bool inject = false;
+  size_t head_step0 = 0;           // first step of the head (after the FPN)
+  const float* d_masks_f = nullptr;  // exact head: fp32 sigmoid mask predictions [cap][fh*fw]
   // plan state
   int plan_H = 0, plan_W = 0, nh = 0, nw = 0, hp = 0, wp = 0, fh = 0, fw = 0;
   uint8_t* d_img = nullptr; uint8_t* d_resized = nullptr; float* d_net = nullptr;

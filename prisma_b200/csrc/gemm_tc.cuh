@@ -40,7 +40,7 @@ struct GemmEpilogue {
   float alpha = 1.0f;            // accumulator scale (e.g. 1/sqrt(C) of the RAFT correlation), applied first
   const float* bias = nullptr;   // [N]
   const float* gamma = nullptr;  // [N]  LayerScale
-  int act = 0;                   // 0 none, 1 exact-erf GELU, 2 ReLU, 3 sigmoid, 4 tanh
+  int act = 0;                   // 0 none, 1 exact-erf GELU, 2 ReLU, 3 sigmoid, 4 tanh (fast, ~4e-7), 5 softplus, 6 sigmoid (expf + IEEE div)
   const float* pre_f32 = nullptr;  // + a per-element fp32 term BEFORE the activation, indexed by dst row (e.g. the part of a
   int pre_f32_ld = 0;              //   conv over concatenated inputs that does not change between iterations)
   const float* res_f32 = nullptr;  // + residual (fp32), indexed by dst row
@@ -169,6 +169,12 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   } else if (ep.act == 4) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i].x = tanh_f(v[i].x); v[i].y = tanh_f(v[i].y); v[i].z = tanh_f(v[i].z); v[i].w = tanh_f(v[i].w); }
+  } else if (ep.act == 6) {  // sigmoid with expf and an IEEE division: the mask predictions of the fp32-class SOLOv2 head
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i].x = 1.0f / (1.0f + expf(-v[i].x)); v[i].y = 1.0f / (1.0f + expf(-v[i].y));
+      v[i].z = 1.0f / (1.0f + expf(-v[i].z)); v[i].w = 1.0f / (1.0f + expf(-v[i].w));
+    }
   } else if (ep.act == 5) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i].x = softplus_f(v[i].x); v[i].y = softplus_f(v[i].y); v[i].z = softplus_f(v[i].z); v[i].w = softplus_f(v[i].w); }

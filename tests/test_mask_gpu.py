@@ -102,6 +102,42 @@ def test_solo_tiny_stages_and_results(tiny):
 
 
 @pytest.mark.gpu
+def test_solo_head_and_decode_from_the_reference_levels_reproduce_the_reference_instances(tiny, golden_dir):
+    """north_star: mask ids bit-exact.  tests/golden/solo_tiny_head.npz holds the VENDORED mmdet SOLOV2Head's own FPN
+    levels and its final scores / labels / masks (oracle/tools/make_golden.py).  Replaying head + decode from those levels
+    on the fp32-class path (three kind::tf32 tensor-core passes per contraction, fp32 activations) must give the same
+    instance list: labels equal, in the same order; scores to 2e-5 relative (the reference's fp32 sums in another order:
+    measured ~2e-6); masks bit-equal up to razor-margin pixels (|p - 0.5| ~ 1e-6 at a mask boundary: the oracle emulation of
+    this arithmetic flips 1 of 7.68 M bits) -- at most 1e-5 of the bits, each of them a boundary pixel.
+    The single-pass fp16 head of round 1 changes a third of the list on the same input (labels differ, scores 2e-3)."""
+    import os
+    eng, sd = tiny
+    g = np.load(os.path.join(golden_dir, "solo_tiny_head.npz"))
+    frame = synthetic_frame(240, 320, 0)
+    eng.infer(frame, confidence=0.5)                       # plans the 240x320 geometry (250x333 -> padded 256x352)
+    feats = [g[f"feat{i}"].astype(np.float32) for i in range(5)]
+    res = eng.infer_from_feats(feats, (240, 320), confidence=0.5)
+    n = int(g["n"])
+    ref_masks = np.unpackbits(g["masks"], axis=-1)[..., :320].astype(bool)
+    # intermediate tensors against the reference's own
+    cls0 = eng.read_tap("cls0", (40 * 40, 80)).T.reshape(80, 40, 40)
+    k4 = eng.read_tap("kernel4", (12 * 12, 256)).T.reshape(256, 12, 12)
+    mf = eng.read_tap("mask_feats", (64 * 88, 256)).T.reshape(256, 64, 88)
+    e_cls = float(np.abs(cls0 - g["cls0"][0]).max())
+    e_k = float(np.abs(k4 - g["kernel4"][0]).max() / np.abs(g["kernel4"]).max())
+    e_mf = float(np.abs(mf[::8] - g["mask_feats_sub"][0]).max() / np.abs(g["mask_feats_sub"]).max())
+    print(f"exact head vs reference: cls logits max abs {e_cls:.2e}, kernel preds rel {e_k:.2e}, mask feats rel {e_mf:.2e}")
+    assert e_cls <= 2e-5 and e_k <= 1e-5 and e_mf <= 1e-5, (e_cls, e_k, e_mf)
+    assert len(res["scores"]) == n, (len(res["scores"]), n)
+    assert np.array_equal(res["labels"], g["labels"][:n].astype(np.int32))
+    rel = np.abs(res["scores"] - g["scores"][:n]) / np.maximum(g["scores"][:n], 1e-6)
+    diff_bits = int((res["masks"] != ref_masks[:n]).sum())
+    print(f"instances {n}: labels equal, max score rel err {rel.max():.2e}, mask bits differing {diff_bits} of {ref_masks[:n].size}")
+    assert rel.max() <= 2e-5, rel.max()
+    assert diff_bits <= 1e-5 * ref_masks[:n].size, diff_bits
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("H,W", [(160, 208), (480, 640), (720, 1280), (1080, 1920), (333, 517)])
 def test_solo_test_pipeline_resize_is_byte_equal_to_cv2(tiny, H, W):
     """mmcv.imrescale = cv2.resize(INTER_LINEAR) on u8, up- and down-scaling, noise frames (the hardest case for a

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gemm_gpu.py tests/test_mask_gpu.py tests/test_band_surface.py tests/test_raft_gpu.py -m gpu -q -s > gpurun_out/r2c5_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2c5_tests.log
+timeout 600 bash tools/gemm_overhead.sh > gpurun_out/r2c5_gemm_overhead.txt 2>&1
+timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/r2c5_bench.json 2> gpurun_out/r2c5_bench.err
+grep -E "passed|failed|rc=" gpurun_out/r2c5_tests.log | tail -3
