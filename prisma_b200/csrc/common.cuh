@@ -41,6 +41,14 @@ void set_last_error(const std::string& msg);
     if (_r != 0) return _r;                                                                      \
   } while (0)
 
+// NVTX ranges (header-only nvtx3: a no-op unless a profiler injects its library) around every engine pass and, in the
+// un-graphed direct runs, around every named step -- so an Nsight Systems / ncu --nvtx timeline reads in the reference's
+// vocabulary (the reference has no tracing hooks at all).
+struct NvtxRange {
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

@@ -781,7 +781,7 @@ int DepthEngine::build_metric_head(const PMap& btlnck, const PMap* r_maps, const
 }
 
 int DepthEngine::run_steps_direct(cudaStream_t s) {
-  for (auto& st : steps) PRISMA_TRY(st.fn(s));
+  for (auto& st : steps) { NvtxRange r(st.name); PRISMA_TRY(st.fn(s)); }
   return 0;
 }
 
@@ -796,6 +796,7 @@ int DepthEngine::run_steps(cudaStream_t s) {
 int DepthEngine::infer(const uint8_t* rgb, int n, int H, int W, float* depth_out, uint8_t* rgb_out, float* min_out,
                        float* max_out) {
   PRISMA_CHECK(rgb != nullptr && H > 0 && W > 0 && n >= 1, "bad frame batch");
+  NvtxRange nvtx_pass("prisma.depth.infer");
   PRISMA_CUDA_OK(cudaSetDevice(device));
   PRISMA_TRY(build_plan(H, W, n));
   PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, rgb, (size_t)n * H * W * 3, cudaMemcpyHostToDevice, stream));
@@ -844,6 +845,7 @@ int DepthEngine::infer_stream(const uint8_t* rgb, int n, int H, int W, int pass_
   PRISMA_CHECK(rgb != nullptr && H > 0 && W > 0 && n >= 1, "bad frame batch");
   PRISMA_CUDA_OK(cudaSetDevice(device));
   const int Bt = pass_frames > 0 ? std::min(pass_frames, 64) : 4;
+  NvtxRange nvtx_pass("prisma.depth.infer_stream");
   PRISMA_TRY(build_plan(H, W, Bt));
   PRISMA_TRY(ensure_stream_slots(H, W, Bt, depth_out != nullptr));
   if (mm_host_frames < (size_t)n) {

@@ -614,13 +614,14 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
 
 int RaftEngine::run_direct(cudaStream_t s, int which) {
   for (auto& st : steps)
-    if (st.group & which) PRISMA_TRY(st.fn(s));
+    if (st.group & which) { NvtxRange r(st.name); PRISMA_TRY(st.fn(s)); }
   return 0;
 }
 
 int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, double scale, int iters_, float* fwd, float* bwd,
                       uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd, float* ms_out, int reuse_prev) {
   PRISMA_CHECK(curr && (prev || reuse_prev) && H > 0 && W > 0, "bad frame pair");
+  NvtxRange nvtx_pass("prisma.flow_raft.infer");
   PRISMA_CUDA_OK(cudaSetDevice(device));
   PRISMA_TRY(build_plan(H, W, scale, iters_));
   const int which = (reuse_prev && cache_valid) ? 2 : 1;
@@ -699,6 +700,7 @@ int RaftEngine::infer_stream(const uint8_t* frames, int n, int H, int W, double 
                              float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd, float* max_bwd,
                              int* pairs_out) {
   PRISMA_CHECK(frames != nullptr && H > 0 && W > 0 && n >= 1, "bad frame chunk");
+  NvtxRange nvtx_pass("prisma.flow_raft.infer_stream");
   PRISMA_CUDA_OK(cudaSetDevice(device));
   const bool same_plan = (plan_H == H && plan_W == W && plan_scale == scale && iters == iters_);
   PRISMA_TRY(build_plan(H, W, scale, iters_));

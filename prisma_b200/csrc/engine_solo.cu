@@ -722,6 +722,7 @@ int SoloEngine::run(cudaStream_t s) {
 int SoloEngine::infer(const uint8_t* rgb, int H, int W, float confidence, uint8_t* union_out, int* n_out, float* scores_out,
                       int* labels_out, uint8_t* inst_masks_out, float* ms_out) {
   PRISMA_CHECK(rgb != nullptr && H > 0 && W > 0, "bad frame");
+  NvtxRange nvtx_pass("prisma.mask_mmdet.infer");
   PRISMA_CUDA_OK(cudaSetDevice(device));
   PRISMA_TRY(build_plan(H, W));
   if (inst_masks_out && !d_inst) PRISMA_TRY(s_alloc(plan_allocs, &d_inst, (size_t)SOLO_MAX * H * W));

@@ -3,7 +3,12 @@
 
 #include <mutex>
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace prisma {
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }

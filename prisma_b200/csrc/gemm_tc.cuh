@@ -412,12 +412,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c0 = chunk_par * 32; c0 < bw; c0 += 64) {
-        if (n0 + c0 >= args.N || args.dbg_mode >= 2) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        tmem_ld_wait();
+      // One 32-column chunk: `r` holds this lane's accumulator row.  The chunks are software-pipelined: the tcgen05.ld of the
+      // next chunk is in flight while this one goes through shared memory and out to global memory (the TMEM read latency
+      // was exposed once per chunk; with two 128 x 256 tiles per CTA the last tile's epilogue is not hidden by a mainloop).
+      auto process_chunk = [&](uint32_t (&r)[32], const int c0) {
         if (TMAST) {
           // ---- TMA-store path: registers -> swizzled 32 x 128 B box (the XOR of the 16-byte slot with row & 7 IS the
           // 128-byte TMA swizzle of a 1024-aligned buffer) -> one cp.async.bulk.tensor store by lane 0; two boxes per warp
@@ -438,7 +436,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_commit();
           }
           ++st_cnt;
-          continue;
+          return;
         }
         if (ep.head_w != nullptr) {
           if (valid) {
@@ -462,7 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
           }
-          continue;
+          return;
         }
         // ---- phase 1: row-per-lane registers -> swizzled smem (conflict-free 16 B slots)
 #pragma unroll
@@ -516,6 +514,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const size_t slab = (size_t)(m0 + quarter * 32) >> 5;
             *reinterpret_cast<float4*>(ep.stat_part + (slab * 2) * args.N + n) = sm;
             *reinterpret_cast<float4*>(ep.stat_part + (slab * 2 + 1) * args.N + n) = sq;
+          }
+        }
+      
+      };
+      {
+        const auto chunk_ok = [&](int c) { return c < bw && n0 + c < args.N && args.dbg_mode < 2; };  // warp-uniform
+        int c0 = chunk_par * 32;
+        uint32_t ra[32], rb[32];
+        if (chunk_ok(c0)) {
+          tmem_ld32(taddr + c0, ra);
+#pragma unroll 1
+          for (;;) {
+            tmem_ld_wait();
+            if (chunk_ok(c0 + 64)) tmem_ld32(taddr + c0 + 64, rb);
+            process_chunk(ra, c0);
+            c0 += 64;
+            if (!chunk_ok(c0)) break;
+            tmem_ld_wait();
+            if (chunk_ok(c0 + 64)) tmem_ld32(taddr + c0 + 64, ra);
+            process_chunk(rb, c0);
+            c0 += 64;
+            if (!chunk_ok(c0)) break;
           }
         }
       }

@@ -276,7 +276,10 @@ def test_flow_band_sharded_with_halo_equals_single(tmp_path):
     assert a["flo"] == b["flo"] and a["flo_b"] == b["flo_b"]
     assert len(b["fwd"]) == 5 and len(b["bwd"]) == 5
     assert all(np.array_equal(x, y) for x, y in zip(a["fwd"], b["fwd"])) and all(np.array_equal(x, y) for x, y in zip(a["bwd"], b["bwd"]))
-    assert a["meta"] == b["meta"] and "flow_raft_bwd" in b["meta"]
+    # the reference stores the --subpath folders as given joined with the input folder (flow_raft.py:208-218): compare them
+    # relative to their own clip folder
+    strip = lambda meta, tag: json.loads(json.dumps(meta).replace(str(tmp_path / tag), "<clip>"))
+    assert strip(a["meta"], "one") == strip(b["meta"], "two") and "flow_raft_bwd" in b["meta"]
 
 
 @pytest.mark.gpu
