@@ -33,6 +33,7 @@ __device__ __forceinline__ void cv_cubic_coeffs_f(float x, float* f) {  // cv::i
 // ~(4/step)^2 = 9 outputs), the output row is written coalesced
 __global__ void k_raft_resize(const uint8_t* __restrict__ img, int H, int W, uint8_t* __restrict__ out, int h, int w,
                               double step) {
+  pdl_prologue();
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   const int oy = blockIdx.y;
   if (ox >= w) return;
@@ -63,6 +64,7 @@ __global__ void k_raft_resize(const uint8_t* __restrict__ img, int H, int W, uin
 
 __global__ void k_raft_pad_norm(const uint8_t* __restrict__ rs, int h, int w, float* __restrict__ chw, int hp, int wp,
                                 int pad_l, int pad_t) {
+  pdl_prologue();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (x >= wp) return;
@@ -78,10 +80,10 @@ int raft_preprocess(const uint8_t* img, int H, int W, int h, int w, double fx, c
                     cudaStream_t s) {
   const double step = 1.0 / fx;  // cv::resize with dsize empty: inv_scale_x = inv_scale_y = fx, sampling step 1 / fx
   dim3 block(128), grid(ceil_div(w, 128), h);
-  k_raft_resize<<<grid, block, 0, s>>>(img, H, W, resized, h, w, step);
+  PRISMA_CUDA_OK(pdl_launch(k_raft_resize, dim3(grid), dim3(block), 0, s, img, H, W, resized, h, w, step));
   const int hp = h + pad[2] + pad[3], wp = w + pad[0] + pad[1];
   dim3 grid2(ceil_div(wp, 128), hp);
-  k_raft_pad_norm<<<grid2, block, 0, s>>>(resized, h, w, chw, hp, wp, pad[0], pad[2]);
+  PRISMA_CUDA_OK(pdl_launch(k_raft_pad_norm, dim3(grid2), dim3(block), 0, s, resized, h, w, chw, hp, wp, pad[0], pad[2]));
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -92,6 +94,7 @@ int raft_preprocess(const uint8_t* img, int H, int W, int h, int w, double fx, c
 __device__ __forceinline__ uint32_t f2ord_pos(float f) { return __float_as_uint(f); }  // distances are >= 0
 
 __global__ void k_flow_max(const float2* __restrict__ flow, long long n, uint32_t* __restrict__ mx) {
+  pdl_prologue();
   float hi = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float2 f = flow[i];
@@ -100,7 +103,8 @@ __global__ void k_flow_max(const float2* __restrict__ flow, long long n, uint32_
   hi = warp_max(hi);
   if ((threadIdx.x & 31) == 0) atomicMax(mx, f2ord_pos(hi));
 }
-__global__ void k_zero_u32(uint32_t* p) { *p = 0u; }
+__global__ void k_zero_u32(uint32_t* p) {
+  pdl_prologue(); *p = 0u; }
 
 __device__ __forceinline__ uint8_t polar_channel_u8(float h6f, double off, double rad, double one_minus_rad) {
   double v = fmod(__dadd_rn((double)h6f, off) , 6.0);
@@ -113,6 +117,7 @@ __device__ __forceinline__ uint8_t polar_channel_u8(float h6f, double off, doubl
 
 __global__ void k_flow_encode(const float2* __restrict__ flow, long long n, const uint32_t* __restrict__ mx,
                               uint8_t* __restrict__ rgb, float* __restrict__ max_out) {
+  pdl_prologue();
   const float maxd = __uint_as_float(*mx);
   if (blockIdx.x == 0 && threadIdx.x == 0 && max_out) *max_out = maxd;
   const float PI_F = 3.14159274101257324f;  // float32(np.pi)
@@ -136,9 +141,9 @@ __global__ void k_flow_encode(const float2* __restrict__ flow, long long n, cons
 int flow_encode(const float* flow, int H, int W, uint8_t* rgb, uint32_t* mm_scratch, float* max_out, int num_sms,
                 cudaStream_t s) {
   const long long n = (long long)H * W;
-  k_zero_u32<<<1, 1, 0, s>>>(mm_scratch);
-  k_flow_max<<<num_sms * 4, 256, 0, s>>>(reinterpret_cast<const float2*>(flow), n, mm_scratch);
-  k_flow_encode<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float2*>(flow), n, mm_scratch, rgb, max_out);
+  PRISMA_CUDA_OK(pdl_launch(k_zero_u32, dim3(1), dim3(1), 0, s, mm_scratch));
+  PRISMA_CUDA_OK(pdl_launch(k_flow_max, dim3(num_sms * 4), dim3(256), 0, s, reinterpret_cast<const float2*>(flow), n, mm_scratch));
+  PRISMA_CUDA_OK(pdl_launch(k_flow_encode, dim3(num_sms * 8), dim3(256), 0, s, reinterpret_cast<const float2*>(flow), n, mm_scratch, rgb, max_out));
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -167,6 +172,7 @@ __device__ __forceinline__ float norm2_f32(float x, float y) { return __fsqrt_rn
 // mask[i] = |f + warp(g, f)| < a1 * (|f| + |warp(g, f)|) + a2     (f = this direction's flow, g = the other one's)
 __global__ void k_consistency_mask(const float2* __restrict__ f, const float2* __restrict__ g, int H, int W, float a1,
                                    float a2, uint8_t* __restrict__ mask) {
+  pdl_prologue();
   const long long total = (long long)H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int y = (int)(i / W), x = (int)(i - (long long)y * W);
@@ -179,16 +185,17 @@ __global__ void k_consistency_mask(const float2* __restrict__ f, const float2* _
 }
 int flow_consistency_masks(const float* fwd, const float* bwd, int H, int W, uint8_t* fwd_mask, uint8_t* bwd_mask,
                            int num_sms, cudaStream_t s) {
-  k_consistency_mask<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float2*>(fwd), reinterpret_cast<const float2*>(bwd),
-                                                 H, W, 0.05f, 0.5f, fwd_mask);
-  k_consistency_mask<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float2*>(bwd), reinterpret_cast<const float2*>(fwd),
-                                                 H, W, 0.05f, 0.5f, bwd_mask);
+  PRISMA_CUDA_OK(pdl_launch(k_consistency_mask, dim3(num_sms * 8), dim3(256), 0, s, reinterpret_cast<const float2*>(fwd), reinterpret_cast<const float2*>(bwd),
+                                                 H, W, 0.05f, 0.5f, fwd_mask));
+  PRISMA_CUDA_OK(pdl_launch(k_consistency_mask, dim3(num_sms * 8), dim3(256), 0, s, reinterpret_cast<const float2*>(bwd), reinterpret_cast<const float2*>(fwd),
+                                                 H, W, 0.05f, 0.5f, bwd_mask));
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
 // encode_flow: u16 (2^15 + 256 f) per component + validity channel
 __global__ void k_flow_u16(const float2* __restrict__ f, const uint8_t* __restrict__ mask, long long n,
                            uint16_t* __restrict__ out) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float fx = __fadd_rn(32768.f, __fmul_rn(f[i].x, 256.f)), fy = __fadd_rn(32768.f, __fmul_rn(f[i].y, 256.f));
     const bool ok = mask[i] && fmaxf(fx, fy) < 65535.f && 0.f < fminf(fx, fy);
@@ -198,7 +205,7 @@ __global__ void k_flow_u16(const float2* __restrict__ f, const uint8_t* __restri
   }
 }
 int flow_encode_u16(const float* flow, const uint8_t* mask, int H, int W, uint16_t* out, int num_sms, cudaStream_t s) {
-  k_flow_u16<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float2*>(flow), mask, (long long)H * W, out);
+  PRISMA_CUDA_OK(pdl_launch(k_flow_u16, dim3(num_sms * 8), dim3(256), 0, s, reinterpret_cast<const float2*>(flow), mask, (long long)H * W, out));
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -211,6 +218,7 @@ int flow_encode_u16(const float* flow, const uint8_t* mask, int H, int W, uint16
 // GEMM) so the coarse levels carry no extra rounding beyond the fp16 feature maps themselves.
 __global__ void k_pool_fmap(const __half* __restrict__ f, int H8, int W8, int C, __half* __restrict__ out, int lh, int lw,
                             int win) {
+  pdl_prologue();
   const int cell = blockIdx.x;  // y * lw + x
   const int y = cell / lw, x = cell - y * lw;
   const float inv = 1.0f / (float)(win * win);
@@ -237,6 +245,7 @@ __global__ void k_corr_lookup(const float* __restrict__ v0, const float* __restr
                               int lh1, int lw1, int lp1, int lh2, int lw2, int lp2, int lh3, int lw3, int lp3,
                               const float* __restrict__ coords, __half* __restrict__ out, int out_ld, int out_wp,
                               int out_pad, int out_img_rows) {
+  pdl_prologue();
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= B * P) return;
@@ -364,8 +373,8 @@ int FlowCorr::set_fmaps(const float* f1, const float* f2) {
 int FlowCorr::build(cudaStream_t s) {
   for (int b = 0; b < B; ++b)
     for (int l = 1; l < 4; ++l)
-      k_pool_fmap<<<ln[l], 128, 0, s>>>(fmap2[0] + (size_t)b * lrows_pad[0] * C, H8, W8, C,
-                                        fmap2[l] + (size_t)b * lrows_pad[l] * C * 2, lh[l], lw[l], 1 << l);
+      PRISMA_CUDA_OK(pdl_launch(k_pool_fmap, dim3(ln[l]), dim3(128), 0, s, fmap2[0] + (size_t)b * lrows_pad[0] * C, H8, W8, C,
+                                        fmap2[l] + (size_t)b * lrows_pad[l] * C * 2, lh[l], lw[l], 1 << l));
   PRISMA_CUDA_OK(cudaGetLastError());
   for (auto& g : gemms) PRISMA_TRY(gemm_run(g, s));
   return 0;
@@ -378,10 +387,10 @@ int FlowCorr::lookup(const float* d_coords, cudaStream_t s) {
 int FlowCorr::lookup_to(const float* d_coords, __half* dst, int dst_ld, int dst_wp, int dst_pad, int dst_img_rows,
                         cudaStream_t s) {
   const int warps = B * P;
-  k_corr_lookup<<<ceil_div(warps * 32, 256), 256, 0, s>>>(vol[0], vol[1], vol[2], vol[3], B, P, H8, W8, lh[0], lw[0],
+  PRISMA_CUDA_OK(pdl_launch(k_corr_lookup, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, s, vol[0], vol[1], vol[2], vol[3], B, P, H8, W8, lh[0], lw[0],
                                                           lpitch[0], lh[1], lw[1], lpitch[1], lh[2], lw[2], lpitch[2],
                                                           lh[3], lw[3], lpitch[3], d_coords, dst, dst_ld, dst_wp,
-                                                          dst_pad, dst_img_rows);
+                                                          dst_pad, dst_img_rows));
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }

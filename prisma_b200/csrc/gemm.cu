@@ -10,6 +10,11 @@ namespace prisma {
 NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
 NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("PRISMA_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
@@ -207,19 +212,26 @@ static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
     PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, TMAST, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  if (CG == 1) {
-    gemm_tc_kernel<BN, CG, TMAST, TF32><<<g.grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(g.tmA, g.tmB, g.tmBt, g.tmD, g.args);
-  } else {
+  {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.grid);
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CG == 2) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (pdl_enabled()) {  // the kernel waits (griddepcontrol.wait) after its prologue: safe after any predecessor
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, TMAST, TF32>, g.tmA, g.tmB, g.tmBt, g.tmD, g.args));
   }
   PRISMA_CUDA_OK(cudaGetLastError());

@@ -250,6 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
+  pdl_launch_dependents();  // the next kernel may be scheduled behind this one (see common.cuh)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // position inside the CTA pair
@@ -283,6 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer's barriers must exist before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // barriers, TMEM and descriptors are set up; from here on the predecessor's results are read
 
   if (args.dbg_mode == 1) {
     // diagnostics: nothing but the prologue and the teardown
@@ -412,10 +414,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-      // One 32-column chunk: `r` holds this lane's accumulator row.  The chunks are software-pipelined: the tcgen05.ld of the
-      // next chunk is in flight while this one goes through shared memory and out to global memory (the TMEM read latency
-      // was exposed once per chunk; with two 128 x 256 tiles per CTA the last tile's epilogue is not hidden by a mainloop).
-      auto process_chunk = [&](uint32_t (&r)[32], const int c0) {
+#pragma unroll 1
+      for (int c0 = chunk_par * 32; c0 < bw; c0 += 64) {
+        if (n0 + c0 >= args.N || args.dbg_mode >= 2) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
         if (TMAST) {
           // ---- TMA-store path: registers -> swizzled 32 x 128 B box (the XOR of the 16-byte slot with row & 7 IS the
           // 128-byte TMA swizzle of a 1024-aligned buffer) -> one cp.async.bulk.tensor store by lane 0; two boxes per warp
@@ -436,7 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_commit();
           }
           ++st_cnt;
-          return;
+          continue;
         }
         if (ep.head_w != nullptr) {
           if (valid) {
@@ -460,7 +464,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
           }
-          return;
+          continue;
         }
         // ---- phase 1: row-per-lane registers -> swizzled smem (conflict-free 16 B slots)
 #pragma unroll
@@ -514,28 +518,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const size_t slab = (size_t)(m0 + quarter * 32) >> 5;
             *reinterpret_cast<float4*>(ep.stat_part + (slab * 2) * args.N + n) = sm;
             *reinterpret_cast<float4*>(ep.stat_part + (slab * 2 + 1) * args.N + n) = sq;
-          }
-        }
-      
-      };
-      {
-        const auto chunk_ok = [&](int c) { return c < bw && n0 + c < args.N && args.dbg_mode < 2; };  // warp-uniform
-        int c0 = chunk_par * 32;
-        uint32_t ra[32], rb[32];
-        if (chunk_ok(c0)) {
-          tmem_ld32(taddr + c0, ra);
-#pragma unroll 1
-          for (;;) {
-            tmem_ld_wait();
-            if (chunk_ok(c0 + 64)) tmem_ld32(taddr + c0 + 64, rb);
-            process_chunk(ra, c0);
-            c0 += 64;
-            if (!chunk_ok(c0)) break;
-            tmem_ld_wait();
-            if (chunk_ok(c0 + 64)) tmem_ld32(taddr + c0 + 64, ra);
-            process_chunk(rb, c0);
-            c0 += 64;
-            if (!chunk_ok(c0)) break;
           }
         }
       }
