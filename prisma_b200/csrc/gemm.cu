@@ -109,7 +109,15 @@ int gemm_prepare_tf32x3(GemmLaunch* out, const float* A_split, long long a_rows,
   int off[GEMM_MAX_TAPS], acol[GEMM_MAX_TAPS];
   for (int t = 0; t < taps; ++t)
     for (int p = 0; p < 3; ++p) { off[t * 3 + p] = tap_off[t]; acol[t * 3 + p] = p == 1 ? C_half : 0; }
-  return gemm_prepare_impl(out, A_split, a_rows, C, 2 * C_half, W3, w_rows, M, N, taps * 3, off, acol, ep, num_sms, force_bn, true);
+  // external accumulation (GemmArgs::acc_group): 128-wide tiles at most (the running sums are 64 registers per thread), no
+  // narrow tail tiles.  PRISMA_TF32_ACC_GROUP=0 keeps the whole K inside one TMEM chain (the biased, cheaper variant).
+  static const int acc_group = [] { const char* e = getenv("PRISMA_TF32_ACC_GROUP"); return e ? atoi(e) : 4; }();
+  if (acc_group > 0 && force_bn == 0) force_bn = N > 64 ? 128 : (N > 32 ? 64 : 32);
+  PRISMA_TRY(gemm_prepare_impl(out, A_split, a_rows, C, 2 * C_half, W3, w_rows, M, N, taps * 3, off, acol, ep, num_sms, force_bn, true));
+  out->args.acc_group = acc_group > 0 ? acc_group : 1;
+  out->xacc = acc_group > 0 && out->bn <= 128;
+  if (out->xacc) { out->args.n_main = ceil_div(M, GEMM_BM) * ceil_div(N, out->bn); out->args.tail_split = 1; out->tmBt = out->tmB; }
+  return 0;
 }
 
 static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, int a_cols, int a_pitch, const void* W,
@@ -126,6 +134,8 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   else if (!force_bn && !pairs_off && !tf32 && bn == 256 && M >= 1024 && N >= 256) cg = 2;
   PRISMA_CHECK(!(tf32 && cg == 2), "gemm: the tf32 path has no CTA-pair instantiation");
   out->tf32 = tf32;
+  out->xacc = false;
+  out->args.acc_group = 1;
   const int bke = tf32 ? 32 : 64;  // elements per 128-byte K block
   PRISMA_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: unsupported BLOCK_N");
   out->cg = cg;
@@ -204,12 +214,12 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   return 0;
 }
 
-template <int BN, int CG, bool TMAST = false, bool TF32 = false>
+template <int BN, int CG, bool TMAST = false, bool TF32 = false, bool XACC = false>
 static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
   static bool attr_set = false;  // per-process, per-instantiation
   using Cfg = GemmCfg<BN, CG, TMAST>;
   if (!attr_set) {
-    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, TMAST, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, TMAST, TF32, XACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   {
@@ -232,13 +242,22 @@ static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, TMAST, TF32>, g.tmA, g.tmB, g.tmBt, g.tmD, g.args));
+    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, TMAST, TF32, XACC>, g.tmA, g.tmB, g.tmBt, g.tmD, g.args));
   }
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int gemm_run(const GemmLaunch& g, cudaStream_t stream) {
+  if (g.tf32 && g.xacc) {
+    switch (g.bn) {
+      case 128: return launch_bn<128, 1, false, true, true>(g, stream);
+      case 64: return launch_bn<64, 1, false, true, true>(g, stream);
+      case 32: return launch_bn<32, 1, false, true, true>(g, stream);
+    }
+    set_last_error("gemm_run: external accumulation needs BLOCK_N <= 128");
+    return -1;
+  }
   if (g.tf32) {
     switch (g.bn) {
       case 256: return launch_bn<256, 1, false, true>(g, stream);

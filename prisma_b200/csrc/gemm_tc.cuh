@@ -97,6 +97,8 @@ struct GemmArgs {
                                 // [hi | lo] activation halves: (hi, W_hi), (lo, W_hi), (hi, W_lo)
   int n_main;      // work items [0, n_main) are full BN-wide tiles; the remaining tiles are each cut into `tail_split`
   int tail_split;  // narrower tiles (BN / tail_split wide) so the last partial wave costs a fraction of a full one; 1 = off
+  int acc_group;  // XACC kernels: K blocks accumulated inside one TMEM chain before the partial sum is added to the running
+                  // fp32 sums held in the epilogue warps' registers (see gemm_prepare_tf32x3)
   int dbg_mode;  // diagnostics (PRISMA_GEMM_DBG): 1 = prologue + teardown only, 2 = loads + MMAs but the epilogue warps only
                  // release the accumulators, 3 = loads only (the MMA warp commits without issuing)
   int raster_n;  // 1: consecutive tiles walk N first (the CTAs of a wave share few A row panels and all of W: A is read
@@ -227,7 +229,7 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   }
 }
 
-template <int BN, int CG, bool TMAST, bool TF32>
+template <int BN, int CG, bool TMAST, bool TF32, bool XACC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmD,
@@ -324,6 +326,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc_tail = TF32 ? make_idesc_tf32(TILE_M, bw_tail) : make_idesc_f16(TILE_M, bw_tail);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
+      if (XACC) {
+        // External accumulation: the tensor core adds into its fp32 accumulator by TRUNCATING the aligned addend, a bias
+        // that grows with the length of the chain (measured: 5e-6 of sum |a||w| after ~900 MMAs).  Here a chain is only
+        // `acc_group` K blocks long; every finished partial sum is handed to the epilogue warps (tfull), which add it
+        // to register-resident running sums with round-to-nearest FADDs, and the TMEM stage is reused (tempty).
+        const int G = args.acc_group;
+        int gi = 0;  // partial sums issued so far (TMEM stage = gi & 1)
+        for (int tile = group; tile < num_items; tile += num_groups) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            const int kg = kb % G;
+            if (kg == 0) { mbar_wait(&tempty[gi & 1], ((gi >> 1) & 1) ^ 1); tc_fence_after(); }
+            const uint32_t tmem_d = tmem_base + (gi & 1) * BN;
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = make_sdesc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
+            const uint64_t bdesc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              if (TF32) umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc_full, (kg | k) != 0 ? 1u : 0u);
+              else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc_full, (kg | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (kg == G - 1 || kb == num_kb - 1) { umma_commit(&tfull[gi & 1]); ++gi; }
+          }
+        }
+      } else
       for (int tile = group; tile < num_items; tile += num_groups, ++it) {
         const uint32_t idesc = tile < n_main ? idesc_full : idesc_tail;
         const int as = it & 1;
@@ -360,6 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cg = lane & 7;     // coalesced phase: which 4-column group of the 32-column chunk
     const int rsub = lane >> 3;  // coalesced phase: row offset inside a 4-row step
     int it = 0;
+    int xgi = 0;  // XACC: partial sums consumed so far
     for (int tile = group; tile < num_items; tile += num_groups, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -411,15 +441,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ib8[rr] = __shfl_sync(0xffffffffu, img_base, row);
         }
       }
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c0 = chunk_par * 32; c0 < bw; c0 += 64) {
-        if (n0 + c0 >= args.N || args.dbg_mode >= 2) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        tmem_ld_wait();
+      // one 32-column chunk of this warp's 32 accumulator rows: r[j] = row `lane`, column c0 + j
+      auto process_chunk = [&](uint32_t (&r)[32], const int c0) {
         if (TMAST) {
           // ---- TMA-store path: registers -> swizzled 32 x 128 B box (the XOR of the 16-byte slot with row & 7 IS the
           // 128-byte TMA swizzle of a 1024-aligned buffer) -> one cp.async.bulk.tensor store by lane 0; two boxes per warp
@@ -440,7 +463,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_commit();
           }
           ++st_cnt;
-          continue;
+          return;
         }
         if (ep.head_w != nullptr) {
           if (valid) {
@@ -464,7 +487,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
           }
-          continue;
+          return;
         }
         // ---- phase 1: row-per-lane registers -> swizzled smem (conflict-free 16 B slots)
 #pragma unroll
@@ -520,6 +543,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<float4*>(ep.stat_part + (slab * 2 + 1) * args.N + n) = sq;
           }
         }
+      
+      };
+      if (XACC) {
+        // running sums of this warp's chunks live in registers; partial sums arrive every `acc_group` K blocks
+        constexpr int NCH = (BN + 63) / 64;
+        float acc[NCH][32];
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[i][j] = 0.f;
+        const int ngroups = (num_kb + args.acc_group - 1) / args.acc_group;
+        for (int g = 0; g < ngroups; ++g, ++xgi) {
+          const int xs = xgi & 1;
+          mbar_wait(&tfull[xs], (xgi >> 1) & 1);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + xs * BN;
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            const int c0 = chunk_par * 32 + 64 * i;
+            if (c0 < bw && n0 + c0 < args.N) {  // warp-uniform
+              uint32_t r[32];
+              tmem_ld32(taddr + c0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[i][j] += __uint_as_float(r[j]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[xs]);
+        }
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int c0 = chunk_par * 32 + 64 * i;
+          if (c0 < bw && n0 + c0 < args.N) {
+            uint32_t r[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[i][j]);
+            process_chunk(r, c0);
+          }
+        }
+        continue;  // the TMEM stages were released group by group
+      }
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c0 = chunk_par * 32; c0 < bw; c0 += 64) {
+        if (n0 + c0 >= args.N || args.dbg_mode >= 2) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        process_chunk(r, c0);
       }
       tc_fence_before();
       __syncwarp();
@@ -542,6 +618,7 @@ struct GemmLaunch {
   CUtensorMap tmA, tmB, tmBt;  // tmBt: W with the narrow box of the tail tiles (== tmB when there is no tail)
   CUtensorMap tmD;             // fp32 output, 32 x 32 boxes (TMA-store epilogue only)
   bool tma_store = false;
+  bool xacc = false;           // external fp32 accumulation (tf32x3 only): see GemmArgs::acc_group
   bool tf32 = false;           // kind::tf32 operands (fp32 containers): the 3xTF32 "fp32-class" path of the mask band
   GemmArgs args;
   int bn = 128;

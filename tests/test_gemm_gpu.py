@@ -107,9 +107,11 @@ def test_conv_matches_torch(H, W, Cin, Cout, k, relu):
 @pytest.mark.parametrize("M,N,K,bn", [(300, 256, 512, 0), (4096, 512, 2304, 0), (1600, 80, 4608, 0), (5000, 128, 320, 128), (64, 32, 100, 32)])
 def test_gemm_tf32x3_is_fp32_class(M, N, K, bn):
     """The 3xTF32 path (kind::tf32 MMAs on [hi | lo] splits of both operands) against the exact product (float64).  The
-    products are fp32-class (the dropped lo x lo term is 2^-22); what remains is the tensor core's own fp32 ACCUMULATION, which
-    truncates the aligned addends instead of rounding them: measured 1e-6 .. 6e-6 of sum |a||w| on B200, growing with K.
-    That is two orders of magnitude below single-pass fp16 / tf32 operands (5e-4) and one above a CUDA-core fp32 GEMM."""
+    products are fp32-class (the dropped lo x lo term is 2^-22).  The tensor core's own fp32 ACCUMULATION truncates the aligned
+    addends instead of rounding them -- with the whole K in one TMEM chain that bias measured 3e-6 .. 6e-6 of sum |a||w| on
+    B200 (growing with K; PRISMA_TF32_ACC_GROUP=0 reproduces it), i.e. only 1e-4-class results for K ~ 4600.  The kernel
+    therefore keeps a TMEM chain 4 K-blocks (16 MMAs) long and adds the partial sums in registers with round-to-nearest
+    FADDs (GemmArgs::acc_group): the error is then that of a CUDA-core fp32 GEMM."""
     rng = np.random.default_rng(M + N + K)
     A = (rng.standard_normal((M, K), dtype=np.float32) * rng.uniform(0.01, 30.0, (M, 1)).astype(np.float32))
     W = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
@@ -121,4 +123,4 @@ def test_gemm_tf32x3_is_fp32_class(M, N, K, bn):
     scale = np.abs(A).astype(np.float64) @ np.abs(W).astype(np.float64).T + np.abs(bias)
     err = float((np.abs(D - ref) / scale).max())
     print(f"tf32x3 {M}x{N}x{K}: max |err| / sum|a||w| = {err:.2e}, {ms.value * 1e3:.1f} us")
-    assert err <= 1.2e-5, err
+    assert err <= 6e-7, err
