@@ -177,10 +177,11 @@ int prisma_mask_infer(prisma_engine* e, const uint8_t* rgb, int h, int w, float 
                       float* scores, int32_t* labels, uint8_t* inst_masks, float* ms_out);
 /* Tests: replay SOLOV2Head.forward + get_results (models/dense_heads/solov2_head.py:253-292,582-766) from GIVEN FPN levels
  * (fp32 NCHW [256][h][w], e.g. the reference's own, tests/golden/solo_tiny_head.npz) for the frame geometry of the last
- * prisma_mask_infer call: inject the five levels, then run head + decode.  fp32-class head only.                        */
+ * prisma_mask_infer call: inject the five levels, then run head + decode.  img_h / img_w > 0 override the resized-image size
+ * (meta img_shape) of the final mask crop.  fp32-class head only.                                                       */
 int prisma_mask_inject_feat(prisma_engine* e, int level, const float* nchw, int h, int w);
-int prisma_mask_infer_from_feats(prisma_engine* e, int h, int w, float confidence, uint8_t* union_mask, int* n_inst, float* scores,
-                                 int32_t* labels, uint8_t* inst_masks);
+int prisma_mask_infer_from_feats(prisma_engine* e, int h, int w, int img_h, int img_w, float confidence, uint8_t* union_mask,
+                                 int* n_inst, float* scores, int32_t* labels, uint8_t* inst_masks);
 /* --sdf (bands/mask_mmdet.py:64-69,150-152): green channel = 255 * (1 - clip(((sdf + 127)/255 - 0.25) * 2, 0, 1)) with sdf the
  * exact Euclidean signed distance of the union mask (what snowy.generate_sdf computes); union_mask / green_out: h*w u8    */
 int prisma_mask_sdf(int device, const uint8_t* union_mask, int h, int w, uint8_t* green_out);

@@ -44,7 +44,7 @@ SIGNATURES = {
     "prisma_mask_infer": (C.c_int, [C.c_void_p, c_u8_p, C.c_int, C.c_int, C.c_float, c_u8_p, C.POINTER(C.c_int), c_float_p,
                                     C.POINTER(C.c_int32), c_u8_p, c_float_p]),
     "prisma_mask_inject_feat": (C.c_int, [C.c_void_p, C.c_int, c_float_p, C.c_int, C.c_int]),
-    "prisma_mask_infer_from_feats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, c_u8_p, C.POINTER(C.c_int), c_float_p,
+    "prisma_mask_infer_from_feats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_u8_p, C.POINTER(C.c_int), c_float_p,
                                                C.POINTER(C.c_int32), c_u8_p]),
     "prisma_net_size": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "prisma_mask_sdf": (C.c_int, [C.c_int, c_u8_p, C.c_int, C.c_int, c_u8_p]),

@@ -614,11 +614,11 @@ int prisma_mask_inject_feat(prisma_engine* e, int level, const float* nchw, int 
   return m ? m->inject_feat(level, nchw, h, w) : -1;
   API_GUARD_END
 }
-int prisma_mask_infer_from_feats(prisma_engine* e, int h, int w, float confidence, uint8_t* union_mask, int* n_inst, float* scores,
-                                 int32_t* labels, uint8_t* inst_masks) {
+int prisma_mask_infer_from_feats(prisma_engine* e, int h, int w, int img_h, int img_w, float confidence, uint8_t* union_mask,
+                                 int* n_inst, float* scores, int32_t* labels, uint8_t* inst_masks) {
   API_GUARD_BEGIN
   SoloEngine* m = as_solo(e);
-  return m ? m->infer_from_feats(h, w, confidence, union_mask, n_inst, scores, labels, inst_masks) : -1;
+  return m ? m->infer_from_feats(h, w, img_h, img_w, confidence, union_mask, n_inst, scores, labels, inst_masks) : -1;
   API_GUARD_END
 }
 long long prisma_mask_read_tap(prisma_engine* e, const char* name, float* out, long long capacity) {

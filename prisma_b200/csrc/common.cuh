@@ -348,7 +348,8 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
                      uint32_t box_cols, uint32_t box_rows);
 
-// Launch with the programmatic-stream-serialization attribute (see pdl_prologue); PRISMA_PDL=0 launches plainly.
+// Launch with the programmatic-stream-serialization attribute when PRISMA_PDL=1 (default: a plain launch; see gemm.cu for the
+// measurement that turned it off).
 bool pdl_enabled();
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>

@@ -778,8 +778,8 @@ int SoloEngine::inject_feat(int level, const float* nchw, int h, int w) {
   return 0;
 }
 
-int SoloEngine::infer_from_feats(int H, int W, float confidence, uint8_t* union_out, int* n_out, float* scores_out, int* labels_out,
-                                 uint8_t* inst_masks_out) {
+int SoloEngine::infer_from_feats(int H, int W, int img_h, int img_w, float confidence, uint8_t* union_out, int* n_out,
+                                 float* scores_out, int* labels_out, uint8_t* inst_masks_out) {
   PRISMA_CHECK(exact_head && plan_H == H && plan_W == W, "infer_from_feats: call infer once at this frame size first");
   PRISMA_CUDA_OK(cudaSetDevice(device));
   if (inst_masks_out && !d_inst) PRISMA_TRY(s_alloc(plan_allocs, &d_inst, (size_t)SOLO_MAX * H * W));
@@ -788,8 +788,8 @@ int SoloEngine::infer_from_feats(int H, int W, float confidence, uint8_t* union_
   for (size_t i = head_step0; i < steps.size() && r == 0; ++i) r = steps[i](stream);
   inject = false;
   if (r != 0) return r;
-  PRISMA_TRY(solo_final_masks(d_masks_f, fh, fw, nh, nw, H, W, 0.5f, d_keep, d_keep_score, d_keep_label, d_nkeep, SOLO_MAX, confidence,
-                              inst_masks_out ? d_inst : nullptr, d_union, stream));
+  PRISMA_TRY(solo_final_masks(d_masks_f, fh, fw, img_h > 0 ? img_h : nh, img_w > 0 ? img_w : nw, H, W, 0.5f, d_keep, d_keep_score,
+                              d_keep_label, d_nkeep, SOLO_MAX, confidence, inst_masks_out ? d_inst : nullptr, d_union, stream));
   int n = 0, cnt = 0;
   PRISMA_CUDA_OK(cudaMemcpyAsync(&n, d_nkeep, 4, cudaMemcpyDeviceToHost, stream));
   PRISMA_CUDA_OK(cudaMemcpyAsync(&cnt, d_count, 4, cudaMemcpyDeviceToHost, stream));

@@ -30,8 +30,9 @@ class SoloEngine {
   // Tests: replace FPN level `level` of the NEXT head replay by these values (dense fp32 NCHW [256][h][w]) ...
   int inject_feat(int level, const float* nchw, int h, int w);
   // ... and run head + decode from the injected levels (frame geometry H x W as planned by a previous infer call)
-  int infer_from_feats(int H, int W, float confidence, uint8_t* union_out, int* n_out, float* scores_out, int* labels_out,
-                       uint8_t* inst_masks_out);
+  // img_h / img_w > 0 override the resized-image size used by the final mask crop (meta img_shape, solov2_head.py:751-757)
+  int infer_from_feats(int H, int W, int img_h, int img_w, float confidence, uint8_t* union_out, int* n_out, float* scores_out,
+                       int* labels_out, uint8_t* inst_masks_out);
   bool exact_head = true;   // fp32-class head + decode (3xTF32 contractions, fp32 activations): the default of the band
   long long read_tap(const std::string& name, float* out, long long capacity);
   int net_shape(int H, int W, int* nh, int* nw, int* hp, int* wp) const;

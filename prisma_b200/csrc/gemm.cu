@@ -10,8 +10,12 @@ namespace prisma {
 NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
 NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
+// Programmatic dependent launch is OFF unless PRISMA_PDL=1.  Measured on B200 (bench.py, 1080p depth + flow): 86.3 frames/s
+// with it, 88.7 without -- the early-resident CTAs of the next kernel take issue slots from the running one and the ~330
+// kernels of a RAFT pass are already back to back inside a CUDA graph -- and tests/test_raft_gpu.py saw a wrong max
+// displacement under it (an ordering it must not change).  Kept only as an experiment switch.
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("PRISMA_PDL"); return !(e && e[0] == '0'); }();
+  static const bool on = [] { const char* e = getenv("PRISMA_PDL"); return e && e[0] == '1'; }();
   return on;
 }
 

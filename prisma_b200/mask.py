@@ -61,9 +61,11 @@ class SoloV2Engine:
         return dict(union=union, scores=scores[:k].copy(), labels=labels[:k].copy(),
                     masks=inst[:k].astype(bool) if want_instances else None, ms=ms.value)
 
-    def infer_from_feats(self, feats, frame_hw, confidence=0.5, want_instances=True):
+    def infer_from_feats(self, feats, frame_hw, confidence=0.5, want_instances=True, img_shape=None):
         """Tests: head + decode replayed from five given FPN levels (each [1|,256,h,w] float32, NCHW) for a frame of size
-        frame_hw whose plan exists (call infer once on a frame of that size).  Same result dict as infer()."""
+        frame_hw whose plan exists (call infer once on a frame of that size).  img_shape = the (h, w) of the resized image the
+        reference's meta carried (default: the engine's own test-pipeline size).  Same result dict as infer()."""
+        ih, iw = img_shape if img_shape is not None else (0, 0)
         h, w = frame_hw
         for lvl, f in enumerate(feats):
             f = np.ascontiguousarray(np.asarray(f, np.float32).reshape(256, f.shape[-2], f.shape[-1]))
@@ -73,7 +75,7 @@ class SoloV2Engine:
         labels = np.zeros(MAX_PER_IMG, np.int32)
         inst = np.empty((MAX_PER_IMG, h, w), np.uint8) if want_instances else None
         n = C.c_int()
-        check(lib().prisma_mask_infer_from_feats(self._h, h, w, float(confidence), u8ptr(union), C.byref(n), fptr(scores),
+        check(lib().prisma_mask_infer_from_feats(self._h, h, w, int(ih), int(iw), float(confidence), u8ptr(union), C.byref(n), fptr(scores),
                                                  labels.ctypes.data_as(C.POINTER(C.c_int32)), u8ptr(inst)))
         k = n.value
         return dict(union=union, scores=scores[:k].copy(), labels=labels[:k].copy(),

@@ -116,7 +116,7 @@ def test_solo_head_and_decode_from_the_reference_levels_reproduce_the_reference_
     frame = synthetic_frame(240, 320, 0)
     eng.infer(frame, confidence=0.5)                       # plans the 240x320 geometry (250x333 -> padded 256x352)
     feats = [g[f"feat{i}"].astype(np.float32) for i in range(5)]
-    res = eng.infer_from_feats(feats, (240, 320), confidence=0.5)
+    res = eng.infer_from_feats(feats, (240, 320), confidence=0.5, img_shape=(250, 333))   # the fixture's meta (make_golden.py)
     n = int(g["n"])
     ref_masks = np.unpackbits(g["masks"], axis=-1)[..., :320].astype(bool)
     # intermediate tensors against the reference's own
