@@ -644,7 +644,7 @@ int SoloEngine::build_plan(int H, int W) {
     PRISMA_TRY(s_alloc(plan_allocs, &masks, (size_t)SOLO_CAP * HW));
     d_masks = masks;
     {
-      GemmEpilogue ep; ep.act = 3; ep.out_f16 = masks; ep.out_f16_ld = HW;
+      GemmEpilogue ep; ep.act = 3; ep.out_f16 = masks; ep.out_f16_ld = HW; ep.m_dev = d_count;  // only the rows of real candidates
       GemmLaunch g;
       PRISMA_TRY(gemm_prepare(&g, kmat, SOLO_CAP, 256, 256, mfeat, round_up(HW, 256), SOLO_CAP, HW, 1, zero_off, ep, num_sms));
       flops += 2.0 * SOLO_CAP * (double)HW * 256;
@@ -665,7 +665,7 @@ int SoloEngine::build_plan(int H, int W) {
     PRISMA_TRY(s_alloc(plan_allocs, &masksf, (size_t)SOLO_CAP * HW));
     d_masks_f = masksf;
     {
-      GemmEpilogue ep; ep.act = 6; ep.out_f32 = masksf; ep.out_f32_ld = HW;
+      GemmEpilogue ep; ep.act = 6; ep.out_f32 = masksf; ep.out_f32_ld = HW; ep.m_dev = d_count;  // only the rows of real candidates
       GemmLaunch g;
       PRISMA_TRY(gemm_prepare_tf32x3(&g, kmatx, SOLO_CAP, 256, 256, mfeat3, round_up(HW, 256), SOLO_CAP, HW, 1, zero_off, ep, num_sms));
       flops += 2.0 * SOLO_CAP * (double)HW * 256;

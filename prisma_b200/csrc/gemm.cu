@@ -202,6 +202,11 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
       }
     }
   }
+  if (ep.m_dev) {  // the tile count is decided on the device: no host-side tail cutting
+    out->args.n_main = tiles;
+    out->args.tail_split = 1;
+    out->tmBt = out->tmB;
+  }
   out->flops = 2.0 * M * (double)N * taps * a_cols;
   // TMA-store epilogue: a plain dense fp32 output (scale only) leaves through swizzled shared-memory boxes and
   // cp.async.bulk.tensor stores instead of per-lane st.global (the store-bound RAFT correlation volume)

@@ -83,6 +83,9 @@ struct GemmEpilogue {
   // writes sum and sum of squares over its VALID rows: stat_part[(slab * 2 + {0,1}) * N + n], fp32, deterministic
   // (fixed shuffle tree; a second kernel adds the slabs in double precision in a fixed order).
   float* stat_part = nullptr;
+  // Row count known only on the device (SOLOv2: the number of candidates of this frame): when set, only the first
+  // round_up(*m_dev, 128) rows of the output space are computed (the launch is sized for the capacity M).
+  const int* m_dev = nullptr;
   // dense fp32 output (row_map LINEAR, scale only) stored by TMA: tcgen05.ld -> swizzled smem box -> cp.async.bulk.tensor
   bool tma_store = false;
 };
@@ -258,7 +261,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // position inside the CTA pair
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
   constexpr int TILE_M = GEMM_BM * CG;
-  const int tiles_m = (args.M + TILE_M - 1) / TILE_M;
+  const int M_run = args.ep.m_dev ? min(args.M, (*args.ep.m_dev + TILE_M - 1) / TILE_M * TILE_M) : args.M;  // see GemmEpilogue::m_dev
+  const int tiles_m = (M_run + TILE_M - 1) / TILE_M;
   const int tiles_n = (args.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = args.taps * args.kchunks;
@@ -442,7 +446,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       // one 32-column chunk of this warp's 32 accumulator rows: r[j] = row `lane`, column c0 + j
-      auto process_chunk = [&](uint32_t (&r)[32], const int c0) {
+      // bias / LayerScale vectors of a chunk: issued BEFORE the TMEM read is waited for, so the global-load latency hides
+      // behind it (they used to sit between the shared-memory phases, on the critical path of every chunk)
+      auto load_bias_gamma = [&](const int c0, float4& bias4, float4& gamma4) {
+        const int n = n0 + c0 + cg * 4;
+        bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        gamma4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (n < args.N && ep.bias) bias4 = *reinterpret_cast<const float4*>(ep.bias + n);
+        if (n < args.N && ep.gamma) gamma4 = *reinterpret_cast<const float4*>(ep.gamma + n);
+      };
+      auto process_chunk = [&](uint32_t (&r)[32], const int c0, const float4& bias4, const float4& gamma4) {
         if (TMAST) {
           // ---- TMA-store path: registers -> swizzled 32 x 128 B box (the XOR of the 16-byte slot with row & 7 IS the
           // 128-byte TMA swizzle of a 1024-aligned buffer) -> one cp.async.bulk.tensor store by lane 0; two boxes per warp
@@ -498,9 +511,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---- phase 2: 8 lanes x 4 columns cover one row's 32 columns; 4 rows per step -> coalesced global access
         const int n = n0 + c0 + cg * 4;
         const bool ncol_ok = n < args.N;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), gamma4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (ncol_ok && ep.bias) bias4 = *reinterpret_cast<const float4*>(ep.bias + n);
-        if (ncol_ok && ep.gamma) gamma4 = *reinterpret_cast<const float4*>(ep.gamma + n);
         float4 v[8];
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
@@ -578,10 +588,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < NCH; ++i) {
           const int c0 = chunk_par * 32 + 64 * i;
           if (c0 < bw && n0 + c0 < args.N) {
+            float4 bias4, gamma4;
+            load_bias_gamma(c0, bias4, gamma4);
             uint32_t r[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[i][j]);
-            process_chunk(r, c0);
+            process_chunk(r, c0, bias4, gamma4);
           }
         }
         continue;  // the TMEM stages were released group by group
@@ -594,8 +606,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (n0 + c0 >= args.N || args.dbg_mode >= 2) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
+        float4 bias4, gamma4;
+        load_bias_gamma(c0, bias4, gamma4);
         tmem_ld_wait();
-        process_chunk(r, c0);
+        process_chunk(r, c0, bias4, gamma4);
       }
       tc_fence_before();
       __syncwarp();

@@ -106,10 +106,13 @@ def test_solo_head_and_decode_from_the_reference_levels_reproduce_the_reference_
     """north_star: mask ids bit-exact.  tests/golden/solo_tiny_head.npz holds the VENDORED mmdet SOLOV2Head's own FPN
     levels and its final scores / labels / masks (oracle/tools/make_golden.py).  Replaying head + decode from those levels
     on the fp32-class path (three kind::tf32 tensor-core passes per contraction, fp32 activations) must give the same
-    instance list: the same labels in the same order, scores and masks up to what the tensor core's truncating fp32
-    accumulation leaves (tests/test_gemm_gpu.py: <= 6e-6 of sum |a||w| per contraction; an exact-arithmetic emulation of
-    3xTF32 in the oracle gives scores to 1.5e-6 and 1 differing mask bit of 7.68 M).  The single-pass fp16 head of round 1
-    changes a third of the list on the same input (labels differ, scores off by 2e-3, 4 % of the mask bits)."""
+    instance list: the same labels in the same order, scores to 5e-5 relative, masks bit-equal except razor-margin boundary
+    pixels (|p - 0.5| ~ 1e-6), at most 1e-6 of the bits.  Measured on B200: labels equal, scores 6.4e-6, 3 of 7.68 M mask
+    bits (an exact-arithmetic emulation of 3xTF32 in the oracle: 1.5e-6 and 1 bit; two fp32 implementations that sum in a
+    different order -- cuDNN vs MKL-DNN -- differ the same way).  Getting there needed the external fp32 accumulation of
+    gemm_prepare_tf32x3: with whole-K TMEM chains the tensor core's truncating accumulate left 4.6e-4 on the class logits,
+    swapped two ranks and moved scores by 2e-3.  The single-pass fp16 head of round 1 changes a third of the list on the
+    same input (labels differ, scores off by 2e-3, 4 % of the mask bits)."""
     import os
     eng, sd = tiny
     g = np.load(os.path.join(golden_dir, "solo_tiny_head.npz"))
@@ -137,10 +140,10 @@ def test_solo_head_and_decode_from_the_reference_levels_reproduce_the_reference_
         bad = np.nonzero(res["labels"] != g["labels"][:n])[0]
         print("  first label mismatches (rank, got, ref, score got, score ref):",
               [(int(i), int(res["labels"][i]), int(g["labels"][i]), float(res["scores"][i]), float(g["scores"][i])) for i in bad[:6]])
-    assert e_cls <= 1e-3 and e_k <= 2e-4 and e_mf <= 2e-5, (e_cls, e_k, e_mf)
+    assert e_cls <= 5e-5 and e_k <= 1e-5 and e_mf <= 5e-6, (e_cls, e_k, e_mf)
     assert same_n and lab_eq
-    assert rel.max() <= 1e-3, rel.max()
-    assert diff_bits <= 2e-4 * ref_masks[:n].size, diff_bits
+    assert rel.max() <= 5e-5, rel.max()
+    assert diff_bits <= 1e-6 * ref_masks[:n].size, diff_bits
 
 
 @pytest.mark.gpu
