@@ -37,13 +37,16 @@ def tiny():
     eng.close()
 
 
-def check_instances(res, scores, labels, masks, min_match=0.9):
-    """GPU instances vs oracle instances: greedy match on (label, IoU)."""
+def check_instances(res, scores, labels, masks, min_match=0.9, tag=""):
+    """GPU instances vs oracle instances: greedy match on (label, IoU).  Prints the residual: how many oracle instances were
+    reproduced (same label, IoU >= 0.97, score within 2 %), how many at the same rank, and for every miss its rank / score and
+    the best same-label IoU found -- the misses sit at the tail of the list, where consecutive scores differ by less than the
+    backbone's fp16 rounding moves them (the max_per_img = 100 cut and the 0.05 filter threshold then pick other members)."""
     n_ref = len(scores)
     assert abs(len(res["scores"]) - n_ref) <= max(2, n_ref // 10), (len(res["scores"]), n_ref)
     ref_m = masks.numpy().reshape(n_ref, -1)
     got_m = res["masks"].reshape(len(res["scores"]), -1)
-    used, matched = set(), 0
+    used, matched, same_rank, misses, score_err = set(), 0, 0, [], []
     for i in range(n_ref):
         best, bj = 0.0, -1
         for j in range(len(res["scores"])):
@@ -57,7 +60,16 @@ def check_instances(res, scores, labels, masks, min_match=0.9):
         if bj >= 0 and best >= 0.97 and abs(float(scores[i]) - float(res["scores"][bj])) <= 2e-3 + 2e-2 * float(scores[i]):
             used.add(bj)
             matched += 1
+            same_rank += int(bj == i)
+            score_err.append(abs(float(scores[i]) - float(res["scores"][bj])) / max(float(scores[i]), 1e-6))
+        else:
+            misses.append((i, round(float(scores[i]), 5), int(labels[i]), round(float(best), 3)))
+    gaps = np.diff(-np.asarray(scores, dtype=np.float64)) if n_ref > 1 else np.array([0.0])
+    print(f"{tag} instances: {matched}/{n_ref} reproduced ({same_rank} at the same rank), median score rel err "
+          f"{np.median(score_err) if score_err else float('nan'):.2e}, max {max(score_err) if score_err else float('nan'):.2e}; "
+          f"median gap between consecutive oracle scores {np.median(gaps):.2e}; misses (rank, score, label, best IoU): {misses[:12]}")
     assert matched >= min_match * n_ref, (matched, n_ref)
+    return matched, misses
 
 
 @pytest.mark.gpu
@@ -94,7 +106,7 @@ def test_solo_tiny_stages_and_results(tiny):
     n_cand = int((taps["cls_scores"] > 0.1).sum())
     got_cand = int(eng.read_tap("cand_count", (1,))[0])
     assert abs(got_cand - n_cand) <= max(3, n_cand // 50), (got_cand, n_cand)
-    check_instances(res, scores, labels, masks)
+    check_instances(res, scores, labels, masks, tag="tiny 240x320")
     ref_union = osolo.band_union(scores, labels, masks, 0.5)[..., 0]
     assert (res["union"] != ref_union).mean() < 5e-3
     bbox, mres = eng.inference_detector(img)
@@ -175,7 +187,7 @@ def test_solo_r101_720p_matches_oracle():
         m, l2 = rel(got, f[0].numpy())
         assert m < 1e-2 and l2 < 4e-3, (f"fpn{i}", m, l2)   # 33 bottlenecks of fp16 maps
     eng.close()
-    check_instances(res, scores, labels, masks, min_match=0.8)
+    check_instances(res, scores, labels, masks, min_match=0.8, tag="r101 720p")
 
 
 @pytest.mark.gpu
