@@ -248,10 +248,11 @@ def depth_720p_extras(eng):
             "frames_per_s_device": BATCH / (ms * 1e-3), "ms_per_pass": ms, "frames_per_pass": BATCH}
 
 
-# kernels launched by one RAFT video pass beyond its step count: corr_build = 6 pooling kernels + 8 GEMMs (1 step),
-# flow_encode = 2 directions x 3 kernels (1 step), raft_preprocess = 2 kernels (1 step); reuse_prev / fmap_swap are
-# device-to-device copies, not kernels
-RAFT_EXTRA_KERNELS = 13 + 5 + 1 - 2
+def raft_extra_kernels(pairs):
+    """Kernels launched by one RAFT video pass of `pairs` frame pairs beyond its step count: raft_preprocess = 2 kernels per
+    new frame (1 step), corr_pool = 3 per new frame (1 step), corr_build = 4 GEMMs per direction (1 step), flow_encode = 3
+    per direction (1 step); reuse_prev is device-to-device copies, not a kernel."""
+    return (2 * pairs - 1) + (3 * pairs - 1) + (8 * pairs - 1) + (6 * pairs - 1) - 1
 
 
 def run_b200(args, rank, local_rank, world):
@@ -319,14 +320,14 @@ def run_b200(args, rank, local_rank, world):
     res_ms = 0.0
     for s in range(args.steps):
         res_ms += da.time_resident(H, W, passes, BATCH) * passes         # ms per pass of BATCH frames
-        res_ms += raft.time_resident(H, W, FRAMES_PER_STEP) * FRAMES_PER_STEP   # ms per pair (video pass)
+        res_ms += raft.time_resident(H, W, FRAMES_PER_STEP // raft.pairs_per_pass) * FRAMES_PER_STEP   # ms per pair (video passes)
     res_s = max_over_ranks(res_ms * 1e-3)
     clocks = sampler.stop()
     barrier()
 
     da_prof = da.profile(H, W, BATCH)     # per kernel-group CUDA-event times of one pass of BATCH frames (ms)
     da_work = da.work(H, W, BATCH)
-    rf_prof = raft.profile(H, W)          # ... of one video pass (one frame pair)
+    rf_prof = raft.profile(H, W)          # ... of one video pass, per frame pair
     rf_work = raft.work_detail(H, W)
     if rank == 0:
         peaks = measured_peaks()
@@ -339,14 +340,15 @@ def run_b200(args, rank, local_rank, world):
         step_ms_prof = da_prof["total"] * passes + rf_prof["total"] * FRAMES_PER_STEP
         gemm_tf = tf(gemm_flop, gemm_ms)
         corr_gbs = rf_work["corr_bytes"] / (rf_prof["corr_build"] * 1e-3) / 1e9 if rf_prof["corr_build"] > 0 else 0.0
-        launches_step = da_work["launches"] * passes + (rf_work["launches_video"] + RAFT_EXTRA_KERNELS) * FRAMES_PER_STEP
+        rf_np = rf_work["pairs_per_pass"]
+        launches_step = da_work["launches"] * passes + (rf_work["launches_video"] + raft_extra_kernels(rf_np)) * (FRAMES_PER_STEP // rf_np)
         out = {
             "metric": "frames/sec at 1080p (depth_anything+flow_raft)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * res_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frame": [H, W], "encoder": ENCODER, "raft_iterations": RAFT_ITERS,
                        "raft_scale": RAFT_SCALE, "frames_per_step": FRAMES_PER_STEP, "depth_frames_per_pass": BATCH,
-                       "parallelism": f"frame-sharded x{world}",
+                       "flow_pairs_per_pass": rf_np, "parallelism": f"frame-sharded x{world}",
                        "l2": "working set per step (0.6 GB fp16 ViT-L weights, 3.6 GB correlation pyramids per pair, activations) "
                              "exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": total_frames / e2e_s, "unit": "frames/s",

@@ -139,8 +139,15 @@ int prisma_flow_infer_video(prisma_engine* e, const uint8_t* prev, const uint8_t
 int prisma_flow_infer_stream(prisma_engine* e, const uint8_t* frames, int n, int h, int w, double scale, int iters,
                              int continue_clip, float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd,
                              float* max_bwd, int* pairs_out);
-/* `reps` passes over the frame pair already resident on the device (video pass when a previous call left its features,
- * else the full pass), outputs left on the device: ms per pass by CUDA events on the engine stream (bench.py).          */
+/* Frame pairs per pass of the clip path (prisma_flow_infer_stream / _infer_resident / _work_detail / _profile): 1 or 2
+ * (default 2; PRISMA_RAFT_PAIRS=1 in the environment selects 1).  With 2, one pass takes three consecutive frames and
+ * produces both directions of both pairs: every update-block launch covers twice the rows, so the per-launch fixed cost is
+ * shared by two pairs.  Results per pair are the same.  The pair calls prisma_flow_infer / _infer_video always use 1.   */
+int prisma_flow_set_pairs_per_pass(prisma_engine* e, int pairs);
+int prisma_flow_pairs_per_pass(prisma_engine* e);   /* current setting, < 0 on error */
+/* `reps` passes over the frames already resident on the device (video pass when a previous call left its features,
+ * else the full pass), outputs left on the device: ms per PASS (= pairs_per_pass pairs) by CUDA events on the engine
+ * stream (bench.py).                                                                                                  */
 int prisma_flow_infer_resident(prisma_engine* e, int h, int w, double scale, int iters, int reps, float* ms_per_pass);
 /* intermediate tensors of the last pass (tests): "fmap" [2][P][256], "cnet_out" [2P][256], "coords1_iter0",
  * "h_iter0", "coords1"; returns the number of floats written                                                       */
@@ -148,8 +155,8 @@ long long prisma_flow_read_tap(prisma_engine* e, const char* name, float* out, l
 /* out[0] = algorithmic FLOP of one pass, out[1] = kernel launches per pass, out[2] = hs, out[3] = ws               */
 int prisma_flow_work(prisma_engine* e, int h, int w, double scale, int iters, double* out4);
 /* out[0] / out[1] = algorithmic FLOP of the tcgen05 conv GEMMs of the full / the video pass (encoders, update block, heads;
- * without the correlation build), out[2] / out[3] = FLOP / algorithmic bytes of one correlation-pyramid build (both
- * directions; bytes = fp32 pyramid written once + fp16 features read once, raft/corr.py:13-27), out[4] / out[5] = kernel
+ * without the correlation build), out[2] / out[3] = FLOP / algorithmic bytes of one correlation-pyramid build (all 2 * pairs_per_pass
+ * directions of a pass; bytes = fp32 pyramid written once + fp16 features read once, raft/corr.py:13-27), out[4] / out[5] = kernel
  * steps of the full / video pass, out[6], out[7] = hs, ws                                                              */
 int prisma_flow_work_detail(prisma_engine* e, int h, int w, double scale, int iters, double* out8);
 /* CUDA-event times (ms) of one pass by kernel group, for bench.py's roofline block (video pass when the previous call left

@@ -739,6 +739,7 @@ int prisma_flow_work(prisma_engine* e, int h, int w, double scale, int iters, do
   API_GUARD_BEGIN
   RaftEngine* r = as_raft(e);
   if (!r) return -1;
+  r->use_pairs(1);
   PRISMA_TRY(r->build_plan(h, w, scale, iters));
   int full_steps = 0;
   for (const auto& st : r->steps) full_steps += (st.group & 1) ? 1 : 0;  // steps of the full pass (the video pass has fewer)
@@ -751,6 +752,7 @@ int prisma_flow_work_detail(prisma_engine* e, int h, int w, double scale, int it
   RaftEngine* r = as_raft(e);
   if (!r) return -1;
   PRISMA_CHECK(out8 != nullptr, "null argument");
+  r->use_pairs(r->pairs_per_pass());
   PRISMA_TRY(r->build_plan(h, w, scale, iters));
   int full_steps = 0, video_steps = 0;
   for (const auto& st : r->steps) { full_steps += (st.group & 1) ? 1 : 0; video_steps += (st.group & 2) ? 1 : 0; }
@@ -758,6 +760,18 @@ int prisma_flow_work_detail(prisma_engine* e, int h, int w, double scale, int it
   out8[2] = r->corr_block()->flops_build; out8[3] = r->corr_block()->bytes_build;
   out8[4] = full_steps; out8[5] = video_steps; out8[6] = r->Hs; out8[7] = r->Ws;
   return 0;
+  API_GUARD_END
+}
+int prisma_flow_set_pairs_per_pass(prisma_engine* e, int pairs) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  return r ? r->set_pairs_per_pass(pairs) : -1;
+  API_GUARD_END
+}
+int prisma_flow_pairs_per_pass(prisma_engine* e) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  return r ? r->pairs_per_pass() : -1;
   API_GUARD_END
 }
 int prisma_flow_profile(prisma_engine* e, int h, int w, double scale, int iters, float* out8) {

@@ -67,6 +67,7 @@ int RaftEngine::init(int dev) {
   PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   const char* ng = getenv("PRISMA_NO_GRAPH");
   use_graph = !(ng && ng[0] == '1');
+  if (const char* np = getenv("PRISMA_RAFT_PAIRS")) stream_pairs = (np[0] == '1') ? 1 : 2;
   return 0;
 }
 
@@ -357,10 +358,21 @@ int RaftEngine::build_encoder(const EncW& e, bool inorm, const __half* stem_cols
   return 0;
 }
 
+int RaftEngine::set_pairs_per_pass(int np) {
+  PRISMA_CHECK(np == 1 || np == 2, "pairs per pass must be 1 or 2");
+  stream_pairs = np;
+  return 0;
+}
+
+int RaftEngine::use_pairs(int np) {
+  if (np != npairs) { npairs = np; cache_valid = false; }  // build_plan sees plan_B != 2 * npairs and rebuilds
+  return 0;
+}
+
 int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   PRISMA_CHECK(finalized, "weights not finalized");
   PRISMA_CHECK(iters_ >= 1 && iters_ <= 64, "iterations must be in [1,64]");
-  if (plan_H == H && plan_W == W && plan_scale == scale && iters == iters_) return 0;
+  if (plan_H == H && plan_W == W && plan_scale == scale && iters == iters_ && plan_B == 2 * npairs) return 0;
   PRISMA_CUDA_OK(cudaSetDevice(device));
   PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
   for (void* q : plan_allocs) cudaFree(q);
@@ -378,34 +390,41 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   pads[0] = pad_w / 2; pads[1] = pad_w - pad_w / 2; pads[2] = pad_h / 2; pads[3] = pad_h - pad_h / 2;
   Hp_ = Hs + pad_h; Wp_ = Ws + pad_w;
   H8 = Hp_ / 8; W8 = Wp_ / 8;
-  const int B = 2, P = H8 * W8;
+  // One pass = NP consecutive frame pairs of a clip = NF = NP + 1 frames and B = 2 NP (image1, image2) directions: direction
+  // 2p is the forward flow of pair p (frame p -> p + 1), 2p + 1 the backward flow (flow_raft.py:105-106).  NP = 2 doubles the
+  // rows of every update-block launch (four waves of tiles instead of two), halving the per-pair share of each launch's
+  // fixed cost.
+  const int NP = npairs, NF = NP + 1, B = 2 * NP, P = H8 * W8;
+  int fr1[8], fr2[8];
+  for (int pp = 0; pp < NP; ++pp) { fr1[2 * pp] = pp; fr2[2 * pp] = pp + 1; fr1[2 * pp + 1] = pp + 1; fr2[2 * pp + 1] = pp; }
+  plan_B = B;
 
-  PRISMA_TRY(r_alloc(plan_allocs, &b.img, (size_t)2 * H * W * 3));
-  PRISMA_TRY(r_alloc(plan_allocs, &b.resized, (size_t)2 * Hs * Ws * 3));
-  PRISMA_TRY(r_alloc(plan_allocs, &b.chw, (size_t)2 * 3 * Hp_ * Wp_));
-  PRISMA_TRY(r_alloc(plan_allocs, &b.stem_cols, (size_t)2 * (Hp_ / 2) * (Wp_ / 2) * 192));
-  const size_t dense_max = (size_t)2 * (Hp_ / 2) * (Wp_ / 2) * 64;  // largest conv output of the encoders (floats)
+  PRISMA_TRY(r_alloc(plan_allocs, &b.img, (size_t)NF * H * W * 3));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.resized, (size_t)NF * Hs * Ws * 3));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.chw, (size_t)NF * 3 * Hp_ * Wp_));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.stem_cols, (size_t)NF * (Hp_ / 2) * (Wp_ / 2) * 192));
+  const size_t dense_max = (size_t)NF * (Hp_ / 2) * (Wp_ / 2) * 64;  // largest conv output of the encoders (floats)
   PRISMA_TRY(r_alloc(plan_allocs, &dense_a, dense_max));
   PRISMA_TRY(r_alloc(plan_allocs, &dense_b, dense_max / 2));
-  PRISMA_TRY(r_alloc(plan_allocs, &stats_a, 2 * 256 * 2));
-  PRISMA_TRY(r_alloc(plan_allocs, &stats_b, 2 * 256 * 2));
-  PRISMA_TRY(r_alloc(plan_allocs, &in_part, (size_t)instnorm_partial_floats(2, (Hp_ / 2) * (Wp_ / 2), 128)));
+  PRISMA_TRY(r_alloc(plan_allocs, &stats_a, NF * 256 * 2));
+  PRISMA_TRY(r_alloc(plan_allocs, &stats_b, NF * 256 * 2));
+  PRISMA_TRY(r_alloc(plan_allocs, &in_part, (size_t)instnorm_partial_floats(NF, (Hp_ / 2) * (Wp_ / 2), 128)));
   {  // per-slab (32 rows) column sums of the conv epilogues: the largest conv input is a pad-1 half-resolution map
     const long long ir = (((long long)(Hp_ / 2 + 1) * (Wp_ / 2 + 1) + 31) / 32) * 32;
-    slab_part_floats = (size_t)(round_up((int)(2 * ir), 256) / 32) * 2 * 128;  // CTA-pair tiles cover 256 rows
+    slab_part_floats = (size_t)(round_up((int)(NF * ir), 256) / 32) * 2 * 128;  // CTA-pair tiles cover 256 rows
     PRISMA_TRY(r_alloc(plan_allocs, &slab_part, slab_part_floats));
-    PRISMA_TRY(r_alloc(plan_allocs, &slab_part2, (size_t)2 * INSTNORM_STAGE1_BLOCKS * 128 * 2));
+    PRISMA_TRY(r_alloc(plan_allocs, &slab_part2, (size_t)NF * INSTNORM_STAGE1_BLOCKS * 128 * 2));
   }
   PRISMA_TRY(r_alloc(plan_allocs, &b.coords0, (size_t)B * 2 * P));
   PRISMA_TRY(r_alloc(plan_allocs, &b.coords1, (size_t)B * 2 * P));
-  PRISMA_TRY(r_alloc(plan_allocs, &b.cnet_out, (size_t)B * P * 256));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.cnet_out, (size_t)NF * P * 256));   // per FRAME (slot 0 = the cached previous frame)
   PRISMA_TRY(r_alloc(plan_allocs, &b.flow_up, (size_t)B * Hs * Ws * 2));
   PRISMA_TRY(r_alloc(plan_allocs, &b.rgb, (size_t)B * Hs * Ws * 3));
-  PRISMA_TRY(r_alloc(plan_allocs, &b.mm, 4));
-  PRISMA_TRY(r_alloc(plan_allocs, &b.maxd, 4));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.mm, 8));
+  PRISMA_TRY(r_alloc(plan_allocs, &b.maxd, 8));
 
   corr = new FlowCorr();
-  PRISMA_TRY(corr->init(device, B, H8, W8));
+  PRISMA_TRY(corr->init(device, B, H8, W8, NF, fr1, fr2));
 
   // ---- K11 pre-process of both frames, stem im2col (shared by fnet and cnet)
   {
@@ -416,63 +435,67 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
     int pdc[4] = {pads[0], pads[1], pads[2], pads[3]};
     cur_mask = 1;
     add("raft_preprocess", [=](cudaStream_t s) {
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < NF; ++i)
         PRISMA_TRY(raft_preprocess(img + (size_t)i * H * W * 3, H, W, Hs_, Ws_, fx, pd, rs + (size_t)i * Hs_ * Ws_ * 3,
                                    chw + (size_t)i * 3 * Hpp * Wpp, s));
       return 0;
     });
-    add("stem_im2col", [=](cudaStream_t s) { return raft_im2col_stem(chw, 2, Hpp, Wpp, cols, s); });
-    // video pass: slot 0 (prev) <- slot 1 (the previous call's curr) for the encoder outputs; only `curr` is pre-processed
+    add("stem_im2col", [=](cudaStream_t s) { return raft_im2col_stem(chw, NF, Hpp, Wpp, cols, s); });
+    // video pass: slot 0 (prev) <- slot NP (the last frame of the previous pass) for everything the encoders produced;
+    // only the NP new frames are pre-processed and encoded
     cur_mask = 2;
     {
       FlowCorr* c = corr; float* cn = b.cnet_out; uint8_t* rsz = rs; const size_t rbytes = (size_t)Hs_ * Ws_ * 3;
       const size_t cn_n = (size_t)P * 256 * sizeof(float);
       add("reuse_prev", [=](cudaStream_t s) {
         const size_t n = (size_t)c->rows_pad * c->C * sizeof(__half);
-        PRISMA_CUDA_OK(cudaMemcpyAsync(c->fmap1, c->fmap1 + (size_t)c->rows_pad * c->C, n, cudaMemcpyDeviceToDevice, s));
-        PRISMA_CUDA_OK(cudaMemcpyAsync(cn, reinterpret_cast<const char*>(cn) + cn_n, cn_n, cudaMemcpyDeviceToDevice, s));
-        PRISMA_CUDA_OK(cudaMemcpyAsync(rsz, rsz + rbytes, rbytes, cudaMemcpyDeviceToDevice, s));
+        PRISMA_CUDA_OK(cudaMemcpyAsync(c->feat, c->feat + (size_t)NP * c->rows_pad * c->C, n, cudaMemcpyDeviceToDevice, s));
+        for (int l = 1; l < 4; ++l) {
+          const size_t pn = (size_t)c->lrows_pad[l] * c->C * 2 * sizeof(__half);
+          PRISMA_CUDA_OK(cudaMemcpyAsync(c->pool[l], c->pool[l] + (size_t)NP * c->lrows_pad[l] * c->C * 2, pn, cudaMemcpyDeviceToDevice, s));
+        }
+        PRISMA_CUDA_OK(cudaMemcpyAsync(cn, reinterpret_cast<const char*>(cn) + NP * cn_n, cn_n, cudaMemcpyDeviceToDevice, s));
+        PRISMA_CUDA_OK(cudaMemcpyAsync(rsz, rsz + NP * rbytes, rbytes, cudaMemcpyDeviceToDevice, s));
         return 0;
       });
     }
     add("raft_preprocess", [=](cudaStream_t s) {
-      return raft_preprocess(img + (size_t)H * W * 3, H, W, Hs_, Ws_, fx, pdc, rs + (size_t)Hs_ * Ws_ * 3, chw + (size_t)3 * Hpp * Wpp, s);
+      for (int i = 1; i < NF; ++i)
+        PRISMA_TRY(raft_preprocess(img + (size_t)i * H * W * 3, H, W, Hs_, Ws_, fx, pdc, rs + (size_t)i * Hs_ * Ws_ * 3,
+                                   chw + (size_t)i * 3 * Hpp * Wpp, s));
+      return 0;
     });
     add("stem_im2col", [=](cudaStream_t s) {
-      return raft_im2col_stem(chw + (size_t)3 * Hpp * Wpp, 1, Hpp, Wpp, cols + (size_t)(Hpp / 2) * (Wpp / 2) * 192, s);
+      return raft_im2col_stem(chw + (size_t)3 * Hpp * Wpp, NP, Hpp, Wpp, cols + (size_t)(Hpp / 2) * (Wpp / 2) * 192, s);
     });
     cur_mask = 3;
   }
   // ---- fnet (instance norm) -> feature maps straight into the correlation operand buffers
   RMap f128, c128, f128c, c128c;
-  const __half* cols1 = b.stem_cols + (size_t)(Hp_ / 2) * (Wp_ / 2) * 192;  // im2col rows of frame 1 (`curr`)
+  const __half* cols1 = b.stem_cols + (size_t)(Hp_ / 2) * (Wp_ / 2) * 192;  // im2col rows of frame 1 (the first new frame)
   cur_mask = 1;
-  PRISMA_TRY(build_encoder(w.fnet, true, b.stem_cols, &f128, 2));
+  PRISMA_TRY(build_encoder(w.fnet, true, b.stem_cols, &f128, NF));
   { GemmEpilogue ep; ep.row_map = ROW_PAD2TOK; ep.out_img_rows = corr->rows_pad;
-    ep.out_f16 = corr->fmap1; ep.out_f16_ld = 256;
+    ep.out_f16 = corr->feat; ep.out_f16_ld = 256;
     PRISMA_TRY(add_conv("fnet_out", f128, 0, w.fnet.out, ep, 1)); }
-  cur_mask = 2;  // video pass: encode `curr` alone, into slot 1
-  PRISMA_TRY(build_encoder(w.fnet, true, cols1, &f128c, 1));
+  { FlowCorr* c = corr; add("corr_pool", [=](cudaStream_t s) { return c->pool_frames(0, NF, s); }); }
+  cur_mask = 2;  // video pass: encode the NP new frames alone, into slots 1..NP
+  PRISMA_TRY(build_encoder(w.fnet, true, cols1, &f128c, NP));
   { GemmEpilogue ep; ep.row_map = ROW_PAD2TOK; ep.out_img_rows = corr->rows_pad;
-    ep.out_f16 = corr->fmap1 + (size_t)corr->rows_pad * 256; ep.out_f16_ld = 256;
+    ep.out_f16 = corr->feat + (size_t)corr->rows_pad * 256; ep.out_f16_ld = 256;
     PRISMA_TRY(add_conv("fnet_out", f128c, 0, w.fnet.out, ep, 1)); }
+  { FlowCorr* c = corr; add("corr_pool", [=](cudaStream_t s) { return c->pool_frames(1, NP, s); }); }
   cur_mask = 3;
-  {  // image pair b uses fmap1 = frame b, fmap2 = the other frame (flow_raft.py:105-106)
+  {  // direction b correlates frame fr1[b] against frame fr2[b] (flow_raft.py:105-106): the GEMMs read the per-frame features
     FlowCorr* c = corr;
-    add("fmap_swap", [c](cudaStream_t s) {
-      const size_t n = (size_t)c->rows_pad * c->C * sizeof(__half);
-      PRISMA_CUDA_OK(cudaMemcpyAsync(c->fmap2[0], c->fmap1 + (size_t)c->rows_pad * c->C, n, cudaMemcpyDeviceToDevice, s));
-      PRISMA_CUDA_OK(cudaMemcpyAsync(c->fmap2[0] + (size_t)c->rows_pad * c->C, c->fmap1, n, cudaMemcpyDeviceToDevice, s));
-      return 0;
-    });
-    add("corr_build", [c](cudaStream_t s) { return c->build(s); });
+    add("corr_build", [c](cudaStream_t s) { return c->build_gemms(s); });
     flops += c->flops_build;
   }
   // ---- cnet (batch norm folded) -> tanh / relu split into the GRU operand maps
   cur_mask = 1;
-  PRISMA_TRY(build_encoder(w.cnet, false, b.stem_cols, &c128, 2));
+  PRISMA_TRY(build_encoder(w.cnet, false, b.stem_cols, &c128, NF));
   cur_mask = 2;
-  PRISMA_TRY(build_encoder(w.cnet, false, cols1, &c128c, 1));
+  PRISMA_TRY(build_encoder(w.cnet, false, cols1, &c128c, NP));
   cur_mask = 3;
   RMap hx, rhx, corrf, c1, c2, f1, fh, mk;
   PRISMA_TRY(new_map(&hx, B, H8, W8, 384, 2));
@@ -488,8 +511,10 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   {
     const float* cn = b.cnet_out; float* hm = b.h_master; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
     float* c0 = b.coords0; float* c1p = b.coords1; const long long ir8 = hx.img_rows();
-    add("cnet_split", [=](cudaStream_t s) { return raft_cnet_split(cn, 2, h8, w8, 2, ir8, hm, hxp, rhp, s); });
-    add("coords_init", [=](cudaStream_t s) { return raft_coords_init(c0, c1p, 2, h8, w8, s); });
+    DirFrames df;  // the context features of direction b are those of its image1 frame
+    for (int d = 0; d < 8; ++d) df.f[d] = d < B ? fr1[d] : 0;
+    add("cnet_split", [=](cudaStream_t s) { return raft_cnet_split(cn, B, h8, w8, 2, ir8, df, hm, hxp, rhp, s); });
+    add("coords_init", [=](cudaStream_t s) { return raft_coords_init(c0, c1p, B, h8, w8, s); });
   }
   // ---- update block, `iters` times (raft.py:123-141)
   PRISMA_TRY(new_map(&corrf, B, H8, W8, 384, 2));
@@ -520,13 +545,13 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
     {
       // convf1 7x7 on the flow: im2col with an fp16 hi/lo split of every value (K = 256) + one GEMM, ReLU, -> padded map
       const float* c0 = b.coords0; const float* c1p = b.coords1; __half* cols = f1_cols; const int h8 = H8, w8 = W8;
-      add("convf1_im2col", [=](cudaStream_t s) { return raft_flow_im2col(c0, c1p, 2, h8, w8, cols, s); });
+      add("convf1_im2col", [=](cudaStream_t s) { return raft_flow_im2col(c0, c1p, B, h8, w8, cols, s); });
       GemmEpilogue ep; ep.bias = w.convf1_b; ep.act = 2; ep.out_f16 = f1.p; ep.out_f16_ld = 128;
       ep.row_map = ROW_TOK2PAD; ep.in_w = W8; ep.in_h = H8; ep.out_wp = f1.Wp(); ep.out_img_rows = (int)f1.img_rows(); ep.out_pad = 2; ep.out_lead = 0;
       GemmLaunch g;
       const int zoff[1] = {0};
-      PRISMA_TRY(gemm_prepare(&g, f1_cols, 2LL * H8 * W8, 256, 256, w.convf1_gemm_w, 256, 2 * H8 * W8, 128, 1, zoff, ep, num_sms));
-      { const double f = 2.0 * 2 * H8 * (double)W8 * 98.0 * 128; flops += f; flops_conv += f; flops_conv_video += f; }
+      PRISMA_TRY(gemm_prepare(&g, f1_cols, (long long)B * H8 * W8, 256, 256, w.convf1_gemm_w, 256, B * H8 * W8, 128, 1, zoff, ep, num_sms));
+      { const double f = 2.0 * B * H8 * (double)W8 * 98.0 * 128; flops += f; flops_conv += f; flops_conv_video += f; }
       add("convf1_gemm", [g](cudaStream_t s) { return gemm_run(g, s); });
     }
     { GemmEpilogue ep; ep.act = 2; ep.out_f16 = c2.p + 192; ep.out_f16_ld = 256;      // convf2 3x3 128 -> 64
@@ -537,7 +562,7 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
       PRISMA_TRY(add_conv("motion_conv", c2, 0, w.conv, ep, 1));
       const float* c0 = b.coords0; const float* c1p = b.coords1; __half* hxp = hx.p; __half* rhp = rhx.p; const int h8 = H8, w8 = W8;
       const long long ir8 = hx.img_rows();
-      add("flow_cols", [=](cudaStream_t s) { return raft_flow_cols(c0, c1p, 2, h8, w8, 2, ir8, hxp, rhp, s); });
+      add("flow_cols", [=](cudaStream_t s) { return raft_flow_cols(c0, c1p, B, h8, w8, 2, ir8, hxp, rhp, s); });
     }
     for (int pass = 0; pass < 2; ++pass) {  // SepConvGRU horizontal then vertical (update.py:45-60)
       { GemmEpilogue ep; ep.act = 3; ep.out_f32 = zr_f; ep.out_f32_ld = 256;
@@ -557,7 +582,7 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
       PRISMA_TRY(add_conv("flow_head2", fh, 0, w.fh2u, ep, 1));
       const float* up = fh2_u; const float b0 = w.fh2_b[0], b1 = w.fh2_b[1]; float* c1p = b.coords1;
       const int h8 = H8, w8 = W8; const long long ir8 = fh.img_rows();
-      add("coords_update", [=](cudaStream_t s) { return raft_flow_head2_gather(up, 2, h8, w8, 2, ir8, b0, b1, c1p, s); }); }
+      add("coords_update", [=](cudaStream_t s) { return raft_flow_head2_gather(up, B, h8, w8, 2, ir8, b0, b1, c1p, s); }); }
     if (debug_taps && it == 0) {
       PRISMA_TRY(r_alloc(plan_allocs, &b.h_tap, (size_t)hx.rows() * 128));
       PRISMA_TRY(r_alloc(plan_allocs, &b.coords_tap, (size_t)B * 2 * P));
@@ -579,17 +604,17 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
     const float* m = b.mask; const float* c0 = b.coords0; const float* c1p = b.coords1; float* up = b.flow_up;
     const int h8 = H8, w8 = W8, Hs_ = Hs, Ws_ = Ws, pt = pads[2], pl = pads[0];
     const long long ir8 = hx.img_rows();
-    add("convex_upsample", [=](cudaStream_t s) { return raft_convex_upsample(m, c0, c1p, 2, h8, w8, 2, ir8, Hs_, Ws_, pt, pl, up, s); });
+    add("convex_upsample", [=](cudaStream_t s) { return raft_convex_upsample(m, c0, c1p, B, h8, w8, 2, ir8, Hs_, Ws_, pt, pl, up, s); });
     uint8_t* rgb = b.rgb; uint32_t* mm = b.mm; float* mx = b.maxd; const int sms = num_sms;
     add("flow_encode", [=](cudaStream_t s) {
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < B; ++i)
         PRISMA_TRY(flow_encode(up + (size_t)i * Hs_ * Ws_ * 2, Hs_, Ws_, rgb + (size_t)i * Hs_ * Ws_ * 3, mm + i, mx + i, sms, s));
       return 0;
     });
   }
-  taps["resized"] = {b.resized, 2 * Hs, Ws * 3, 1, 3};
-  taps["fmap"] = {corr->fmap1, 0, 0, 0, 4};
-  taps["cnet_out"] = {b.cnet_out, B * P, 256, 1, 0};
+  taps["resized"] = {b.resized, NF * Hs, Ws * 3, 1, 3};
+  taps["fmap"] = {corr->feat, 0, 0, 0, 4};
+  taps["cnet_out"] = {b.cnet_out, NF * P, 256, 1, 0};
   taps["coords1_iter0"] = {b.coords_tap, B * 2, P, 1, 0};
   taps["h_iter0"] = {b.h_tap, (int)hx.rows(), 128, 1, 0};
   taps["coords1"] = {b.coords1, B * 2, P, 1, 0};
@@ -623,6 +648,7 @@ int RaftEngine::infer(const uint8_t* prev, const uint8_t* curr, int H, int W, do
   PRISMA_CHECK(curr && (prev || reuse_prev) && H > 0 && W > 0, "bad frame pair");
   NvtxRange nvtx_pass("prisma.flow_raft.infer");
   PRISMA_CUDA_OK(cudaSetDevice(device));
+  use_pairs(1);
   PRISMA_TRY(build_plan(H, W, scale, iters_));
   const int which = (reuse_prev && cache_valid) ? 2 : 1;
   PRISMA_CHECK(which == 2 || prev != nullptr, "no cached features for the previous frame: pass it");
@@ -679,7 +705,7 @@ int RaftEngine::ensure_stream_slots(int H, int W) {
       for (cudaEvent_t* e : {&sl.loaded, &sl.consumed, &sl.done, &sl.drained})
         PRISMA_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
-  const size_t in_bytes = (size_t)H * W * 3, out_px = (size_t)Hs * Ws;
+  const size_t in_bytes = (size_t)npairs * H * W * 3, out_px = (size_t)npairs * Hs * Ws;  // per pass: NP frames in, NP pairs out
   if (slot_in_bytes == in_bytes && slot_out_px == out_px) return 0;
   PRISMA_CUDA_OK(cudaDeviceSynchronize());
   for (auto& sl : slot) {
@@ -688,7 +714,7 @@ int RaftEngine::ensure_stream_slots(int H, int W) {
     PRISMA_CUDA_OK(cudaMalloc(&sl.in, in_bytes));
     PRISMA_CUDA_OK(cudaMalloc(&sl.flow, 2 * out_px * 2 * sizeof(float)));
     PRISMA_CUDA_OK(cudaMalloc(&sl.rgb, 2 * out_px * 3));
-    PRISMA_CUDA_OK(cudaMalloc(&sl.mx, 8));
+    PRISMA_CUDA_OK(cudaMalloc(&sl.mx, 8 * sizeof(float)));
   }
   slot_in_bytes = in_bytes; slot_out_px = out_px;
   return 0;
@@ -702,7 +728,8 @@ int RaftEngine::infer_stream(const uint8_t* frames, int n, int H, int W, double 
   PRISMA_CHECK(frames != nullptr && H > 0 && W > 0 && n >= 1, "bad frame chunk");
   NvtxRange nvtx_pass("prisma.flow_raft.infer_stream");
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  const bool same_plan = (plan_H == H && plan_W == W && plan_scale == scale && iters == iters_);
+  use_pairs(stream_pairs);
+  const bool same_plan = (plan_H == H && plan_W == W && plan_scale == scale && iters == iters_ && plan_B == 2 * npairs);
   PRISMA_TRY(build_plan(H, W, scale, iters_));
   PRISMA_TRY(ensure_stream_slots(H, W));
   const bool cont = continue_clip && cache_valid && same_plan;
@@ -712,58 +739,70 @@ int RaftEngine::infer_stream(const uint8_t* frames, int n, int H, int W, double 
     cache_valid = false;  // its features are not computed by any pass, so the next chunk must start a new clip
     return 0;
   }
-  if (mx_host_pairs < (size_t)pairs) {
+  const int NP = npairs, B = 2 * NP;
+  const int passes = (pairs + NP - 1) / NP;
+  if (mx_host_pairs < (size_t)passes * NP) {
     if (mx_host) cudaFreeHost(mx_host);
     mx_host = nullptr; mx_host_pairs = 0;
-    PRISMA_CUDA_OK(cudaMallocHost(&mx_host, (size_t)pairs * 8));
-    mx_host_pairs = pairs;
+    PRISMA_CUDA_OK(cudaMallocHost(&mx_host, (size_t)passes * NP * 8));
+    mx_host_pairs = (size_t)passes * NP;
   }
   const size_t fb = (size_t)H * W * 3, px = (size_t)Hs * Ws;
   const int first_curr = cont ? 0 : 1;  // index of the `curr` frame of pair 0
   cache_valid = false;
   if (!cont) PRISMA_CUDA_OK(cudaMemcpyAsync(b.img, frames, fb, cudaMemcpyHostToDevice, stream));  // `prev` of pair 0
-  auto drain = [&](int j) -> int {
-    StreamSlot& sl = slot[j & 1];
+  // pass g covers pairs [g NP, g NP + NP): its new frames are first_curr + g NP + p.  A last pass with fewer pairs than NP
+  // repeats the final frame (the extra pair is computed and dropped; the cached slot still ends up holding the last frame).
+  auto drain = [&](int g) -> int {
+    StreamSlot& sl = slot[g & 1];
     PRISMA_CUDA_OK(cudaStreamWaitEvent(s_out, sl.done, 0));
-    if (fwd) PRISMA_CUDA_OK(cudaMemcpyAsync(fwd + (size_t)j * px * 2, sl.flow, px * 8, cudaMemcpyDeviceToHost, s_out));
-    if (bwd) PRISMA_CUDA_OK(cudaMemcpyAsync(bwd + (size_t)j * px * 2, sl.flow + px * 2, px * 8, cudaMemcpyDeviceToHost, s_out));
-    if (fwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(fwd_rgb + (size_t)j * px * 3, sl.rgb, px * 3, cudaMemcpyDeviceToHost, s_out));
-    if (bwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(bwd_rgb + (size_t)j * px * 3, sl.rgb + px * 3, px * 3, cudaMemcpyDeviceToHost, s_out));
-    PRISMA_CUDA_OK(cudaMemcpyAsync(mx_host + (size_t)j * 2, sl.mx, 8, cudaMemcpyDeviceToHost, s_out));
+    for (int p = 0; p < NP; ++p) {
+      const int j = g * NP + p;
+      if (j >= pairs) break;
+      if (fwd) PRISMA_CUDA_OK(cudaMemcpyAsync(fwd + (size_t)j * px * 2, sl.flow + (size_t)(2 * p) * px * 2, px * 8, cudaMemcpyDeviceToHost, s_out));
+      if (bwd) PRISMA_CUDA_OK(cudaMemcpyAsync(bwd + (size_t)j * px * 2, sl.flow + (size_t)(2 * p + 1) * px * 2, px * 8, cudaMemcpyDeviceToHost, s_out));
+      if (fwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(fwd_rgb + (size_t)j * px * 3, sl.rgb + (size_t)(2 * p) * px * 3, px * 3, cudaMemcpyDeviceToHost, s_out));
+      if (bwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(bwd_rgb + (size_t)j * px * 3, sl.rgb + (size_t)(2 * p + 1) * px * 3, px * 3, cudaMemcpyDeviceToHost, s_out));
+    }
+    PRISMA_CUDA_OK(cudaMemcpyAsync(mx_host + (size_t)g * B, sl.mx, B * sizeof(float), cudaMemcpyDeviceToHost, s_out));
     PRISMA_CUDA_OK(cudaEventRecord(sl.drained, s_out));
     return 0;
   };
-  for (int j = 0; j < pairs; ++j) {
-    StreamSlot& sl = slot[j & 1];
-    const int which = (j == 0 && !cont) ? 1 : 2;
-    if (j >= 2) PRISMA_CUDA_OK(cudaStreamWaitEvent(s_in, sl.consumed, 0));
-    PRISMA_CUDA_OK(cudaMemcpyAsync(sl.in, frames + (size_t)(first_curr + j) * fb, fb, cudaMemcpyHostToDevice, s_in));
+  for (int g = 0; g < passes; ++g) {
+    StreamSlot& sl = slot[g & 1];
+    const int which = (g == 0 && !cont) ? 1 : 2;
+    if (g >= 2) PRISMA_CUDA_OK(cudaStreamWaitEvent(s_in, sl.consumed, 0));
+    for (int p = 0; p < NP; ++p) {
+      const int fi = std::min(first_curr + g * NP + p, n - 1);
+      PRISMA_CUDA_OK(cudaMemcpyAsync(sl.in + (size_t)p * fb, frames + (size_t)fi * fb, fb, cudaMemcpyHostToDevice, s_in));
+    }
     PRISMA_CUDA_OK(cudaEventRecord(sl.loaded, s_in));
     PRISMA_CUDA_OK(cudaStreamWaitEvent(stream, sl.loaded, 0));
-    PRISMA_CUDA_OK(cudaMemcpyAsync(b.img + fb, sl.in, fb, cudaMemcpyDeviceToDevice, stream));
+    PRISMA_CUDA_OK(cudaMemcpyAsync(b.img + fb, sl.in, NP * fb, cudaMemcpyDeviceToDevice, stream));
     PRISMA_CUDA_OK(cudaEventRecord(sl.consumed, stream));
     if (graph_exec) PRISMA_CUDA_OK(cudaGraphLaunch(which == 1 ? graph_exec : graph_cached, stream));
     else PRISMA_TRY(run_direct(stream, which));
-    if (j >= 2) PRISMA_CUDA_OK(cudaStreamWaitEvent(stream, sl.drained, 0));
-    if (fwd || bwd) PRISMA_CUDA_OK(cudaMemcpyAsync(sl.flow, b.flow_up, 2 * px * 8, cudaMemcpyDeviceToDevice, stream));
-    if (fwd_rgb || bwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(sl.rgb, b.rgb, 2 * px * 3, cudaMemcpyDeviceToDevice, stream));
-    PRISMA_CUDA_OK(cudaMemcpyAsync(sl.mx, b.maxd, 8, cudaMemcpyDeviceToDevice, stream));
+    if (g >= 2) PRISMA_CUDA_OK(cudaStreamWaitEvent(stream, sl.drained, 0));
+    if (fwd || bwd) PRISMA_CUDA_OK(cudaMemcpyAsync(sl.flow, b.flow_up, B * px * 8, cudaMemcpyDeviceToDevice, stream));
+    if (fwd_rgb || bwd_rgb) PRISMA_CUDA_OK(cudaMemcpyAsync(sl.rgb, b.rgb, B * px * 3, cudaMemcpyDeviceToDevice, stream));
+    PRISMA_CUDA_OK(cudaMemcpyAsync(sl.mx, b.maxd, B * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     PRISMA_CUDA_OK(cudaEventRecord(sl.done, stream));
-    if (j >= 1) PRISMA_TRY(drain(j - 1));
+    if (g >= 1) PRISMA_TRY(drain(g - 1));
   }
-  PRISMA_TRY(drain(pairs - 1));
+  PRISMA_TRY(drain(passes - 1));
   PRISMA_CUDA_OK(cudaStreamSynchronize(s_out));
   PRISMA_CUDA_OK(cudaStreamSynchronize(stream));
   for (int j = 0; j < pairs; ++j) {
     if (max_fwd) max_fwd[j] = mx_host[2 * j];
     if (max_bwd) max_bwd[j] = mx_host[2 * j + 1];
   }
-  cache_valid = true;  // slot 1 of the feature buffers holds the last frame of the chunk
+  cache_valid = true;  // slot NP of the feature buffers holds the last frame of the chunk
   return 0;
 }
 
 int RaftEngine::time_resident(int H, int W, double scale, int iters_, int reps, float* ms_per_pass) {
   PRISMA_CUDA_OK(cudaSetDevice(device));
+  use_pairs(stream_pairs);
   PRISMA_TRY(build_plan(H, W, scale, iters_));
   const int which = cache_valid ? 2 : 1;
   auto once = [&]() -> int {
@@ -792,6 +831,7 @@ int RaftEngine::time_resident(int H, int W, double scale, int iters_, int reps, 
 // up-sampling + HSV encode, [7] total.
 int RaftEngine::profile(int H, int W, double scale, int iters_, float* out8) {
   PRISMA_CUDA_OK(cudaSetDevice(device));
+  use_pairs(stream_pairs);
   PRISMA_TRY(build_plan(H, W, scale, iters_));
   const int which = cache_valid ? 2 : 1;
   for (int i = 0; i < 8; ++i) out8[i] = 0.f;

@@ -53,6 +53,12 @@ class RaftEngine {
   double flops = 0, flops_conv = 0, flops_conv_video = 0;  // full pass total; conv GEMMs of the full / video pass
   int profile(int H, int W, double scale, int iters, float* out8);
   bool has_cache() const { return cache_valid; }
+  // Frame pairs per pass of the clip path (infer_stream / time_resident / profile / work_detail): 1 or 2, default 2
+  // (PRISMA_RAFT_PAIRS overrides), see build_plan.  The pair call infer() always plans one pair per pass; switching
+  // between the two paths rebuilds the plan.
+  int set_pairs_per_pass(int np);
+  int pairs_per_pass() const { return stream_pairs; }
+  int use_pairs(int np);  // select the plan variant for the next build_plan
   FlowCorr* corr_block() { return corr; }
   std::vector<Step> steps;
   bool debug_taps = true;
@@ -73,7 +79,7 @@ class RaftEngine {
   cudaStream_t stream = nullptr;
   cudaGraphExec_t graph_exec = nullptr, graph_cached = nullptr;
   int cur_mask = 3;          // steps carry a mask (Step::group): bit 0 = full pass, bit 1 = video pass
-  bool cache_valid = false;  // slot 1 of the feature buffers holds the last call's `curr`
+  bool cache_valid = false;  // slot NP of the feature buffers holds the last frame of the previous pass
   bool use_graph = true, finalized = false;
   std::map<std::string, HostTensor> host;
   std::vector<void*> allocs, plan_allocs;
@@ -83,6 +89,7 @@ class RaftEngine {
   std::map<std::string, Tap> taps;
   float *dense_a = nullptr, *dense_b = nullptr, *stats_a = nullptr, *stats_b = nullptr, *in_part = nullptr;
   float* slab_part = nullptr; double* slab_part2 = nullptr; size_t slab_part_floats = 0;
+  int npairs = 1, stream_pairs = 2, plan_B = 2;
   int plan_H = 0, plan_W = 0, iters = 0, Hp_ = 0, Wp_ = 0, pads[4] = {0, 0, 0, 0};
   double plan_scale = 0.0;
   struct StreamSlot {
@@ -90,7 +97,7 @@ class RaftEngine {
     cudaEvent_t loaded = nullptr, consumed = nullptr, done = nullptr, drained = nullptr;
   } slot[2];
   cudaStream_t s_in = nullptr, s_out = nullptr;
-  float* mx_host = nullptr;  // pinned, 2 floats per pair
+  float* mx_host = nullptr;  // pinned, 2 floats per pair (padded to whole passes)
   size_t mx_host_pairs = 0, slot_in_bytes = 0, slot_out_px = 0;
   int ensure_stream_slots(int H, int W);
 };

@@ -306,9 +306,15 @@ FlowCorr::~FlowCorr() {
   if (stream) cudaStreamDestroy(stream);
 }
 
-int FlowCorr::init(int dev, int batch, int h8, int w8) {
+int FlowCorr::init(int dev, int batch, int h8, int w8, int n_frames, const int* f1_idx, const int* f2_idx) {
   device = dev; B = batch; H8 = h8; W8 = w8; P = h8 * w8;
-  PRISMA_CHECK(batch >= 1 && h8 >= 8 && w8 >= 8, "flowcorr: bad geometry");
+  PRISMA_CHECK(batch >= 1 && batch <= 8 && h8 >= 8 && w8 >= 8, "flowcorr: bad geometry");
+  NF = n_frames > 0 ? n_frames : 2 * batch;
+  for (int b = 0; b < B; ++b) {
+    f1[b] = f1_idx ? f1_idx[b] : b;
+    f2[b] = f2_idx ? f2_idx[b] : B + b;
+    PRISMA_CHECK(f1[b] >= 0 && f1[b] < NF && f2[b] >= 0 && f2[b] < NF, "flowcorr: frame index out of range");
+  }
   PRISMA_CUDA_OK(cudaSetDevice(dev));
   cudaDeviceProp prop;
   PRISMA_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
@@ -316,17 +322,17 @@ int FlowCorr::init(int dev, int batch, int h8, int w8) {
   num_sms = prop.multiProcessorCount;
   PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   rows_pad = round_up(P, 256);
-  PRISMA_TRY(fc_alloc(allocs, &fmap1, (size_t)B * rows_pad * C));
+  PRISMA_TRY(fc_alloc(allocs, &feat, (size_t)NF * rows_pad * C));
   for (int l = 0; l < 4; ++l) {
     lh[l] = H8 >> l; lw[l] = W8 >> l; ln[l] = lh[l] * lw[l];
     lpitch[l] = round_up(ln[l], 4);
-    lrows_pad[l] = round_up(lpitch[l], 256);
-    PRISMA_TRY(fc_alloc(allocs, &fmap2[l], (size_t)B * lrows_pad[l] * C * (l == 0 ? 1 : 2)));
+    lrows_pad[l] = l == 0 ? rows_pad : round_up(lpitch[l], 256);
+    if (l > 0) PRISMA_TRY(fc_alloc(allocs, &pool[l], (size_t)NF * lrows_pad[l] * C * 2));
     PRISMA_TRY(fc_alloc(allocs, &vol[l], (size_t)B * P * lpitch[l]));
   }
   PRISMA_TRY(fc_alloc(allocs, &coords, (size_t)B * 2 * P));
   PRISMA_TRY(fc_alloc(allocs, &lookup_out, (size_t)B * P * 384));
-  // one GEMM per (image, level): vol_l[b] = fmap1[b] . fmap2_l[b]^T / sqrt(C)      (corr.py:53-60)
+  // one GEMM per (direction, level): vol_l[b] = feat[f1[b]] . pooled_l(feat[f2[b]])^T / sqrt(C)      (corr.py:53-60)
   const int off[2] = {0, 0};
   bytes_build = flops_build = 0;
   for (int b = 0; b < B; ++b)
@@ -339,45 +345,49 @@ int FlowCorr::init(int dev, int batch, int h8, int w8) {
       static const bool tma_off = [] { const char* e = getenv("PRISMA_CORR_TMA_STORE"); return e && e[0] == '0'; }();
       GemmLaunch g;
       ep.tma_store = !tma_off && gemm_pick_bn(P, lpitch[l], num_sms) >= 128;
-      const int wk = l == 0 ? 1 : 2;  // coarse levels: fmap1 against [hi | lo] pooled features = two K-slabs
-      PRISMA_TRY(gemm_prepare(&g, fmap1 + (size_t)b * rows_pad * C, P, C, C, fmap2[l] + (size_t)b * lrows_pad[l] * C * wk,
-                              lrows_pad[l], P, lpitch[l], wk, off, ep, num_sms));
+      const int wk = l == 0 ? 1 : 2;  // coarse levels: against [hi | lo] pooled features = two K-slabs
+      const __half* w2 = l == 0 ? feat + (size_t)f2[b] * rows_pad * C : pool[l] + (size_t)f2[b] * lrows_pad[l] * C * 2;
+      PRISMA_TRY(gemm_prepare(&g, feat + (size_t)f1[b] * rows_pad * C, P, C, C, w2, lrows_pad[l], P, lpitch[l], wk, off, ep, num_sms));
       gemms.push_back(g);
       flops_build += 2.0 * P * (double)ln[l] * C;
       bytes_build += 4.0 * P * (double)ln[l];
     }
-  bytes_build += 2.0 * B * P * (double)C * 2.0;  // the two fp16 feature maps, read once
+  bytes_build += 2.0 * B * P * (double)C * 2.0;  // the two fp16 feature maps of every direction, read once
   return 0;
 }
 
-int FlowCorr::set_fmaps(const float* f1, const float* f2) {
+int FlowCorr::set_fmaps(const float* fm1, const float* fm2) {
+  PRISMA_CHECK(NF == 2 * B, "flowcorr: set_fmaps needs the default frame layout");
   PRISMA_CUDA_OK(cudaSetDevice(device));
   std::vector<__half> h((size_t)B * rows_pad * C, __float2half_rn(0.f));
   for (int which = 0; which < 2; ++which) {
-    const float* src = which == 0 ? f1 : f2;
+    const float* src = which == 0 ? fm1 : fm2;
     std::fill(h.begin(), h.end(), __float2half_rn(0.f));
     for (int b = 0; b < B; ++b)
       for (int c = 0; c < C; ++c)
         for (int p = 0; p < P; ++p)
           h[((size_t)b * rows_pad + p) * C + c] = __float2half_rn(src[((size_t)b * C + c) * P + p]);
-    if (which == 0) {
-      PRISMA_CUDA_OK(cudaMemcpy(fmap1, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
-    } else {
-      // level 0 buffer has lrows_pad[0] == rows_pad rows per image
-      PRISMA_CUDA_OK(cudaMemcpy(fmap2[0], h.data(), h.size() * 2, cudaMemcpyHostToDevice));
-    }
+    PRISMA_CUDA_OK(cudaMemcpy(feat + (size_t)which * B * rows_pad * C, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   }
   return 0;
 }
 
-int FlowCorr::build(cudaStream_t s) {
-  for (int b = 0; b < B; ++b)
+int FlowCorr::pool_frames(int first, int count, cudaStream_t s) {
+  for (int f = first; f < first + count; ++f)
     for (int l = 1; l < 4; ++l)
-      PRISMA_CUDA_OK(pdl_launch(k_pool_fmap, dim3(ln[l]), dim3(128), 0, s, fmap2[0] + (size_t)b * lrows_pad[0] * C, H8, W8, C,
-                                        fmap2[l] + (size_t)b * lrows_pad[l] * C * 2, lh[l], lw[l], 1 << l));
-  PRISMA_CUDA_OK(cudaGetLastError());
+      PRISMA_CUDA_OK(pdl_launch(k_pool_fmap, dim3(ln[l]), dim3(128), 0, s, feat + (size_t)f * rows_pad * C, H8, W8, C,
+                                pool[l] + (size_t)f * lrows_pad[l] * C * 2, lh[l], lw[l], 1 << l));
+  return 0;
+}
+
+int FlowCorr::build_gemms(cudaStream_t s) {
   for (auto& g : gemms) PRISMA_TRY(gemm_run(g, s));
   return 0;
+}
+
+int FlowCorr::build(cudaStream_t s) {
+  PRISMA_TRY(pool_frames(0, NF, s));
+  return build_gemms(s);
 }
 
 int FlowCorr::lookup(const float* d_coords, cudaStream_t s) {

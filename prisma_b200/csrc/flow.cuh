@@ -20,7 +20,10 @@ int flow_encode_u16(const float* flow, const uint8_t* mask, int H, int W, uint16
 class FlowCorr {
  public:
   ~FlowCorr();
-  int init(int device, int batch, int h8, int w8);
+  // batch = number of (image1, image2) directions.  Features are stored per FRAME: direction b correlates frame f1_idx[b]
+  // against frame f2_idx[b] (the engine: consecutive frames of a clip, each used by up to four directions; default / tests:
+  // 2 * batch frames, direction b = frame b against frame batch + b, which is what set_fmaps fills).
+  int init(int device, int batch, int h8, int w8, int n_frames = 0, const int* f1_idx = nullptr, const int* f2_idx = nullptr);
   int set_fmaps(const float* fmap1_nchw, const float* fmap2_nchw);  // host fp32 [B][256][h8][w8]
   int build(cudaStream_t s);                                        // K13 + K14
   int lookup(const float* d_coords, cudaStream_t s);                // K15: coords device fp32 [B][2][h8][w8]
@@ -33,8 +36,12 @@ class FlowCorr {
 
   int device = 0, B = 0, H8 = 0, W8 = 0, P = 0, C = 256, num_sms = 148;
   int lh[4], lw[4], ln[4], lpitch[4];  // level sizes, element counts, row pitch (multiple of 4) of the fp32 volumes
-  __half* fmap1 = nullptr;             // [B][P][C]   (rows padded to the next multiple of 256)
-  __half* fmap2[4] = {nullptr, nullptr, nullptr, nullptr};  // per level [B][ln_pad][C]: level l = 2^l x 2^l mean of fmap2
+  int NF = 0;                          // frames held
+  int f1[8] = {0}, f2[8] = {0};        // frame of image1 / image2 per direction
+  __half* feat = nullptr;              // [NF][rows_pad][C] fp16 features (rows padded to the next multiple of 256)
+  __half* pool[4] = {nullptr, nullptr, nullptr, nullptr};  // levels 1..3: [NF][lrows_pad][2 C] = [hi | lo] of the 2^l x 2^l mean
+  int pool_frames(int first, int count, cudaStream_t s);   // K14 operands of frames [first, first + count)
+  int build_gemms(cudaStream_t s);                          // the 4 * B correlation GEMMs
   float* vol[4] = {nullptr, nullptr, nullptr, nullptr};     // per level fp32 [B*P][lpitch]
   float* coords = nullptr;
   __half* lookup_out = nullptr;  // [B*P][384] fp16 (324 used), the A operand of the motion encoder's convc1

@@ -200,8 +200,9 @@ int instnorm_apply(const float* x, const float* stats, int B, int H, int W, int 
 // cnet output split (raft.py:113-116): net = tanh(cnet[:, :128]) -> h (fp32 master + fp16 operand), inp = relu(rest).
 // Destination: the GRU operand maps hx = [h | inp | motion] and rhx = [r*h | inp | motion], 384 channels, pad 2.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, int pad, long long img_rows, float* __restrict__ h_master,
-                             __half* __restrict__ hx, __half* __restrict__ rhx) {
+// cn holds the context features per FRAME; direction b reads those of frame df.f[b] (its image1).
+__global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, int pad, long long img_rows, DirFrames df,
+                             float* __restrict__ h_master, __half* __restrict__ hx, __half* __restrict__ rhx) {
   pdl_prologue();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W*256
   const long long total = (long long)B * H * W * 256;
@@ -213,7 +214,7 @@ __global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, 
   const int y = r / W, x = r - y * W;
   const int Wp = W + pad;  // shared-border layout: zeros only after each row / image
   const size_t prow = (size_t)b * img_rows + (size_t)y * Wp + x;
-  const float v = cn[idx];
+  const float v = cn[((size_t)df.f[b] * H * W + r) * 256 + c];
   if (c < 128) {
     const float t = tanhf(v);
     h_master[prow * 128 + c] = t;
@@ -224,10 +225,10 @@ __global__ void k_cnet_split(const float* __restrict__ cn, int B, int H, int W, 
     rhx[prow * 384 + c] = i;
   }
 }
-int raft_cnet_split(const float* cn, int B, int H, int W, int pad, long long img_rows, float* h_master, __half* hx, __half* rhx,
-                    cudaStream_t s) {
+int raft_cnet_split(const float* cn, int B, int H, int W, int pad, long long img_rows, DirFrames df, float* h_master, __half* hx,
+                    __half* rhx, cudaStream_t s) {
   const long long total = (long long)B * H * W * 256;
-  PRISMA_CUDA_OK(pdl_launch(k_cnet_split, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, cn, B, H, W, pad, img_rows, h_master, hx, rhx));
+  PRISMA_CUDA_OK(pdl_launch(k_cnet_split, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, cn, B, H, W, pad, img_rows, df, h_master, hx, rhx));
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }

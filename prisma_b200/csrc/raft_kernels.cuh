@@ -13,8 +13,9 @@ int instnorm_stats_from_slabs(const float* slab_part, int B, int slabs_per_image
                               cudaStream_t s);
 int instnorm_apply(const float* x, const float* stats, int B, int H, int W, int C, const __half* skip_map,
                    const float* skip_raw, const float* skip_stats, __half* out, int pad, long long img_rows, cudaStream_t s);
-int raft_cnet_split(const float* cn, int B, int H, int W, int pad, long long img_rows, float* h_master, __half* hx, __half* rhx,
-                    cudaStream_t s);
+struct DirFrames { int f[8]; };  // frame whose context features direction b uses
+int raft_cnet_split(const float* cn, int B, int H, int W, int pad, long long img_rows, DirFrames df, float* h_master, __half* hx,
+                    __half* rhx, cudaStream_t s);
 int raft_flow_im2col(const float* c0, const float* c1, int B, int H, int W, __half* out, cudaStream_t s);
 int raft_flow_cols(const float* c0, const float* c1, int B, int H, int W, int pad, long long img_rows, __half* hx, __half* rhx,
                    cudaStream_t s);

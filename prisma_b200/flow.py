@@ -91,11 +91,20 @@ class RaftFlowEngine:
         cut = lambda a: None if a is None else a[:p]
         return dict(pairs=p, fwd=cut(fwd), bwd=cut(bwd), fwd_rgb=cut(frgb), bwd_rgb=cut(brgb), max_fwd=mf[:p], max_bwd=mb[:p])
 
+    @property
+    def pairs_per_pass(self):
+        """Frame pairs one pass of the clip path covers (prisma_flow_set_pairs_per_pass; 2 by default)."""
+        return check(lib().prisma_flow_pairs_per_pass(self._h))
+
+    @pairs_per_pass.setter
+    def pairs_per_pass(self, n):
+        check(lib().prisma_flow_set_pairs_per_pass(self._h, int(n)))
+
     def time_resident(self, h, w, reps):
-        """ms per pass over the frame pair resident on the device (CUDA events inside the C ABI)."""
+        """ms per PAIR of `reps` passes over the frames resident on the device (CUDA events inside the C ABI)."""
         ms = C.c_float()
         check(lib().prisma_flow_infer_resident(self._h, h, w, float(self.scale), self.iterations, reps, C.byref(ms)))
-        return ms.value
+        return ms.value / self.pairs_per_pass
 
     def infer_pair(self, prev, curr, want_rgb=False, reuse_prev=False):
         """prev/curr: HxWx3 u8 RGB -> dict(fwd, bwd [hs,ws,2] f32, max_fwd, max_bwd[, fwd_rgb, bwd_rgb], ms).
@@ -128,15 +137,17 @@ class RaftFlowEngine:
     def work_detail(self, h, w):
         out = (C.c_double * 8)()
         check(lib().prisma_flow_work_detail(self._h, h, w, float(self.scale), self.iterations, out))
-        return dict(conv_flop_full=out[0], conv_flop_video=out[1], corr_flop=out[2], corr_bytes=out[3],
-                    launches_full=int(out[4]), launches_video=int(out[5]), hs=int(out[6]), ws=int(out[7]))
+        np_ = self.pairs_per_pass  # FLOP / bytes per PAIR (both directions), kernel steps per PASS of np_ pairs
+        return dict(conv_flop_full=out[0] / np_, conv_flop_video=out[1] / np_, corr_flop=out[2] / np_, corr_bytes=out[3] / np_,
+                    launches_full=int(out[4]), launches_video=int(out[5]), hs=int(out[6]), ws=int(out[7]), pairs_per_pass=np_)
 
     def profile(self, h, w):
-        """ms per kernel group of one pass (CUDA events, ungraphed): see prisma_flow_profile."""
+        """ms per PAIR by kernel group of one pass (CUDA events, ungraphed): see prisma_flow_profile."""
         out = (C.c_float * 8)()
         check(lib().prisma_flow_profile(self._h, h, w, float(self.scale), self.iterations, out))
         keys = ["pre", "conv_gemm", "corr_build", "corr_lookup", "instnorm", "pointwise", "post", "total"]
-        return dict(zip(keys, [float(v) for v in out]))
+        np_ = self.pairs_per_pass
+        return dict(zip(keys, [float(v) / np_ for v in out]))
 
     def close(self):
         if self._h:

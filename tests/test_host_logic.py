@@ -56,8 +56,13 @@ def test_flo_writer_and_metadata_roundtrip(tmp_path):
     assert json.load(open(folder / "metadata.json")) == back
 
 
-def test_shard_flag_stripping_and_frame_spec():
-    from bands.common.depth_loop import parse_frames, strip_shard_flags
-    argv = ["-i", "clip", "--gpus", "4", "--encoder", "vits", "--device-list", "0,1,2,3", "-o", "x.mp4", "--seeded-weights", "-n"]
-    assert strip_shard_flags(argv) == ["-i", "clip", "--encoder", "vits", "--seeded-weights", "-n"]
-    assert parse_frames("", 100) == (0, 100) and parse_frames("10:40", 100) == (10, 40) and parse_frames("90:200", 100) == (90, 100)
+def test_shard_flag_stripping_and_frame_ranges():
+    """`<band>.py --gpus N` hands its workers the same command line minus the sharding flags; every worker owns a contiguous
+    frame range (flow bands read one halo frame)."""
+    from bands.common.sharded import strip_flags
+    from prisma_b200.shard import frame_range
+    argv = ["-i", "clip", "--gpus", "4", "--encoder", "vits", "--device-list=0,1,2,3", "-o", "x.mp4", "--seeded-weights", "--device", "3", "-n"]
+    assert strip_flags(argv) == ["-i", "clip", "--encoder", "vits", "-o", "x.mp4", "--seeded-weights", "-n"]
+    got = [frame_range(r, 3, 100, 1) for r in range(3)]
+    assert [g[0] for g in got] == [0] + [g[1] for g in got[:-1]] and got[-1][1] == 100   # contiguous cover of [0, 100)
+    assert got[0][2] == 0 and all(g[2] == g[0] - 1 for g in got[1:])                      # halo frame
