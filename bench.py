@@ -320,7 +320,7 @@ def run_b200(args, rank, local_rank, world):
     res_ms = 0.0
     for s in range(args.steps):
         res_ms += da.time_resident(H, W, passes, BATCH) * passes         # ms per pass of BATCH frames
-        res_ms += raft.time_resident(H, W, FRAMES_PER_STEP // raft.pairs_per_pass) * FRAMES_PER_STEP   # ms per pair (video passes)
+        res_ms += raft.time_resident(H, W, FRAMES_PER_STEP // raft.plan_pairs) * FRAMES_PER_STEP   # ms per pair (video passes)
     res_s = max_over_ranks(res_ms * 1e-3)
     clocks = sampler.stop()
     barrier()

@@ -139,12 +139,14 @@ int prisma_flow_infer_video(prisma_engine* e, const uint8_t* prev, const uint8_t
 int prisma_flow_infer_stream(prisma_engine* e, const uint8_t* frames, int n, int h, int w, double scale, int iters,
                              int continue_clip, float* fwd, float* bwd, uint8_t* fwd_rgb, uint8_t* bwd_rgb, float* max_fwd,
                              float* max_bwd, int* pairs_out);
-/* Frame pairs per pass of the clip path (prisma_flow_infer_stream / _infer_resident / _work_detail / _profile): 1 or 2
- * (default 2; PRISMA_RAFT_PAIRS=1 in the environment selects 1).  With 2, one pass takes three consecutive frames and
- * produces both directions of both pairs: every update-block launch covers twice the rows, so the per-launch fixed cost is
- * shared by two pairs.  Results per pair are the same.  The pair calls prisma_flow_infer / _infer_video always use 1.   */
+/* Frame pairs per pass of the clip path (prisma_flow_infer_stream / _infer_resident / _work_detail / _profile): 1..4
+ * (default 4; PRISMA_RAFT_PAIRS in the environment overrides; lowered per frame size until the correlation pyramids of one
+ * pass fit in a third of the device memory -- 4K frames run one pair per pass).  With n, one pass takes n + 1 consecutive frames and
+ * produces both directions of the n pairs: every update-block launch covers n times the rows, so the per-launch fixed
+ * cost is shared by n pairs.  Results per pair are the same.  The pair calls prisma_flow_infer / _infer_video always use 1.   */
 int prisma_flow_set_pairs_per_pass(prisma_engine* e, int pairs);
 int prisma_flow_pairs_per_pass(prisma_engine* e);   /* current setting, < 0 on error */
+int prisma_flow_plan_pairs(prisma_engine* e);       /* pairs per pass of the plan the last call built, < 0 on error */
 /* `reps` passes over the frames already resident on the device (video pass when a previous call left its features,
  * else the full pass), outputs left on the device: ms per PASS (= pairs_per_pass pairs) by CUDA events on the engine
  * stream (bench.py).                                                                                                  */

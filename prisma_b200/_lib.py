@@ -72,6 +72,7 @@ SIGNATURES = {
                                            c_float_p, c_u8_p, c_u8_p, c_float_p, c_float_p, C.POINTER(C.c_int)]),
     "prisma_flow_set_pairs_per_pass": (C.c_int, [C.c_void_p, C.c_int]),
     "prisma_flow_pairs_per_pass": (C.c_int, [C.c_void_p]),
+    "prisma_flow_plan_pairs": (C.c_int, [C.c_void_p]),
     "prisma_flow_infer_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_float_p]),
     "prisma_debug_gemm": (C.c_int, [C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, c_float_p]),

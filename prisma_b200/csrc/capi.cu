@@ -752,7 +752,7 @@ int prisma_flow_work_detail(prisma_engine* e, int h, int w, double scale, int it
   RaftEngine* r = as_raft(e);
   if (!r) return -1;
   PRISMA_CHECK(out8 != nullptr, "null argument");
-  r->use_pairs(r->pairs_per_pass());
+  r->use_pairs(r->clip_pairs(h, w, scale));
   PRISMA_TRY(r->build_plan(h, w, scale, iters));
   int full_steps = 0, video_steps = 0;
   for (const auto& st : r->steps) { full_steps += (st.group & 1) ? 1 : 0; video_steps += (st.group & 2) ? 1 : 0; }
@@ -772,6 +772,12 @@ int prisma_flow_pairs_per_pass(prisma_engine* e) {
   API_GUARD_BEGIN
   RaftEngine* r = as_raft(e);
   return r ? r->pairs_per_pass() : -1;
+  API_GUARD_END
+}
+int prisma_flow_plan_pairs(prisma_engine* e) {
+  API_GUARD_BEGIN
+  RaftEngine* r = as_raft(e);
+  return r ? r->plan_pairs() : -1;
   API_GUARD_END
 }
 int prisma_flow_profile(prisma_engine* e, int h, int w, double scale, int iters, float* out8) {

@@ -64,10 +64,11 @@ int RaftEngine::init(int dev) {
   PRISMA_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
   PRISMA_CHECK(prop.major == 10, "prisma_b200 kernels are sm_100a only; there is no fallback path");
   num_sms = prop.multiProcessorCount;
+  device_mem = prop.totalGlobalMem;
   PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   const char* ng = getenv("PRISMA_NO_GRAPH");
   use_graph = !(ng && ng[0] == '1');
-  if (const char* np = getenv("PRISMA_RAFT_PAIRS")) stream_pairs = (np[0] == '1') ? 1 : 2;
+  if (const char* np = getenv("PRISMA_RAFT_PAIRS")) stream_pairs = std::min(std::max(atoi(np), 1), 4);
   return 0;
 }
 
@@ -359,9 +360,20 @@ int RaftEngine::build_encoder(const EncW& e, bool inorm, const __half* stem_cols
 }
 
 int RaftEngine::set_pairs_per_pass(int np) {
-  PRISMA_CHECK(np == 1 || np == 2, "pairs per pass must be 1 or 2");
+  PRISMA_CHECK(np >= 1 && np <= 4, "pairs per pass must be in [1, 4]");
   stream_pairs = np;
   return 0;
+}
+
+// Pairs per pass the clip path uses for frames of this size: the setting, lowered until the fp32 correlation pyramids of
+// one pass (2 np directions x P^2 x 4 bytes x 4/3) fit in a third of the device memory (4K frames: one pair per pass).
+int RaftEngine::clip_pairs(int H, int W, double scale) const {
+  const int hs = (int)nearbyint((double)H * scale), ws = (int)nearbyint((double)W * scale);
+  const double P = (double)((hs + 7) / 8) * ((ws + 7) / 8);
+  const double per_pair = 2.0 * P * P * 4.0 * (4.0 / 3.0);
+  int np = stream_pairs;
+  while (np > 1 && per_pair * np > (double)device_mem / 3.0) --np;
+  return np;
 }
 
 int RaftEngine::use_pairs(int np) {
@@ -728,7 +740,7 @@ int RaftEngine::infer_stream(const uint8_t* frames, int n, int H, int W, double 
   PRISMA_CHECK(frames != nullptr && H > 0 && W > 0 && n >= 1, "bad frame chunk");
   NvtxRange nvtx_pass("prisma.flow_raft.infer_stream");
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  use_pairs(stream_pairs);
+  use_pairs(clip_pairs(H, W, scale));
   const bool same_plan = (plan_H == H && plan_W == W && plan_scale == scale && iters == iters_ && plan_B == 2 * npairs);
   PRISMA_TRY(build_plan(H, W, scale, iters_));
   PRISMA_TRY(ensure_stream_slots(H, W));
@@ -802,7 +814,7 @@ int RaftEngine::infer_stream(const uint8_t* frames, int n, int H, int W, double 
 
 int RaftEngine::time_resident(int H, int W, double scale, int iters_, int reps, float* ms_per_pass) {
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  use_pairs(stream_pairs);
+  use_pairs(clip_pairs(H, W, scale));
   PRISMA_TRY(build_plan(H, W, scale, iters_));
   const int which = cache_valid ? 2 : 1;
   auto once = [&]() -> int {
@@ -831,7 +843,7 @@ int RaftEngine::time_resident(int H, int W, double scale, int iters_, int reps, 
 // up-sampling + HSV encode, [7] total.
 int RaftEngine::profile(int H, int W, double scale, int iters_, float* out8) {
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  use_pairs(stream_pairs);
+  use_pairs(clip_pairs(H, W, scale));
   PRISMA_TRY(build_plan(H, W, scale, iters_));
   const int which = cache_valid ? 2 : 1;
   for (int i = 0; i < 8; ++i) out8[i] = 0.f;

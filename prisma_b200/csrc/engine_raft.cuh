@@ -53,12 +53,14 @@ class RaftEngine {
   double flops = 0, flops_conv = 0, flops_conv_video = 0;  // full pass total; conv GEMMs of the full / video pass
   int profile(int H, int W, double scale, int iters, float* out8);
   bool has_cache() const { return cache_valid; }
-  // Frame pairs per pass of the clip path (infer_stream / time_resident / profile / work_detail): 1 or 2, default 2
-  // (PRISMA_RAFT_PAIRS overrides), see build_plan.  The pair call infer() always plans one pair per pass; switching
+  // Frame pairs per pass of the clip path (infer_stream / time_resident / profile / work_detail): 1..4, default 4
+  // (PRISMA_RAFT_PAIRS overrides), see build_plan; clip_pairs() lowers it for frames whose pyramids would not fit.  The pair call infer() always plans one pair per pass; switching
   // between the two paths rebuilds the plan.
   int set_pairs_per_pass(int np);
   int pairs_per_pass() const { return stream_pairs; }
   int use_pairs(int np);  // select the plan variant for the next build_plan
+  int clip_pairs(int H, int W, double scale) const;
+  int plan_pairs() const { return plan_B / 2; }  // pairs per pass of the current plan
   FlowCorr* corr_block() { return corr; }
   std::vector<Step> steps;
   bool debug_taps = true;
@@ -89,7 +91,8 @@ class RaftEngine {
   std::map<std::string, Tap> taps;
   float *dense_a = nullptr, *dense_b = nullptr, *stats_a = nullptr, *stats_b = nullptr, *in_part = nullptr;
   float* slab_part = nullptr; double* slab_part2 = nullptr; size_t slab_part_floats = 0;
-  int npairs = 1, stream_pairs = 2, plan_B = 2;
+  int npairs = 1, stream_pairs = 4, plan_B = 2;
+  size_t device_mem = 0;
   int plan_H = 0, plan_W = 0, iters = 0, Hp_ = 0, Wp_ = 0, pads[4] = {0, 0, 0, 0};
   double plan_scale = 0.0;
   struct StreamSlot {

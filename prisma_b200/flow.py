@@ -93,8 +93,13 @@ class RaftFlowEngine:
 
     @property
     def pairs_per_pass(self):
-        """Frame pairs one pass of the clip path covers (prisma_flow_set_pairs_per_pass; 2 by default)."""
+        """Frame pairs one pass of the clip path covers at most (prisma_flow_set_pairs_per_pass; 4 by default)."""
         return check(lib().prisma_flow_pairs_per_pass(self._h))
+
+    @property
+    def plan_pairs(self):
+        """Pairs per pass of the plan the last call built (the setting, lowered for very large frames; 1 after infer_pair)."""
+        return check(lib().prisma_flow_plan_pairs(self._h))
 
     @pairs_per_pass.setter
     def pairs_per_pass(self, n):
@@ -104,7 +109,7 @@ class RaftFlowEngine:
         """ms per PAIR of `reps` passes over the frames resident on the device (CUDA events inside the C ABI)."""
         ms = C.c_float()
         check(lib().prisma_flow_infer_resident(self._h, h, w, float(self.scale), self.iterations, reps, C.byref(ms)))
-        return ms.value / self.pairs_per_pass
+        return ms.value / self.plan_pairs
 
     def infer_pair(self, prev, curr, want_rgb=False, reuse_prev=False):
         """prev/curr: HxWx3 u8 RGB -> dict(fwd, bwd [hs,ws,2] f32, max_fwd, max_bwd[, fwd_rgb, bwd_rgb], ms).
@@ -137,7 +142,7 @@ class RaftFlowEngine:
     def work_detail(self, h, w):
         out = (C.c_double * 8)()
         check(lib().prisma_flow_work_detail(self._h, h, w, float(self.scale), self.iterations, out))
-        np_ = self.pairs_per_pass  # FLOP / bytes per PAIR (both directions), kernel steps per PASS of np_ pairs
+        np_ = self.plan_pairs  # FLOP / bytes per PAIR (both directions), kernel steps per PASS of np_ pairs
         return dict(conv_flop_full=out[0] / np_, conv_flop_video=out[1] / np_, corr_flop=out[2] / np_, corr_bytes=out[3] / np_,
                     launches_full=int(out[4]), launches_video=int(out[5]), hs=int(out[6]), ws=int(out[7]), pairs_per_pass=np_)
 
@@ -146,7 +151,7 @@ class RaftFlowEngine:
         out = (C.c_float * 8)()
         check(lib().prisma_flow_profile(self._h, h, w, float(self.scale), self.iterations, out))
         keys = ["pre", "conv_gemm", "corr_build", "corr_lookup", "instnorm", "pointwise", "post", "total"]
-        np_ = self.pairs_per_pass
+        np_ = self.plan_pairs
         return dict(zip(keys, [float(v) / np_ for v in out]))
 
     def close(self):

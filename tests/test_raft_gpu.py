@@ -111,15 +111,15 @@ def test_raft_1080p_matches_oracle(raft_engine):
     assert abs(out["max_fwd"] - float(np.sqrt((fwd_ref ** 2).sum(-1)).max())) <= 1e-3 * float(np.abs(fwd_ref).max())
 
 
-@pytest.mark.parametrize("pairs_per_pass", [2, 1])
+@pytest.mark.parametrize("pairs_per_pass", [4, 2, 1])
 def test_raft_streamed_clip_equals_pairwise_calls(pairs_per_pass):
     """prisma_flow_infer_stream over a clip (new clip, then a continued chunk; pinned and pageable buffers) == the
     per-pair calls of the band's loop, bit for bit (flows, HSV frames, max displacements) -- with one pair per pass and with
-    two (three frames -> four directions per pass; the 3-pair chunk ends on a half-filled pass)."""
+    two / four (n + 1 frames -> 2 n directions per pass; the chunks end on partly filled passes)."""
     from prisma_b200.depth import pinned_empty
     from prisma_b200.flow import RaftFlowEngine
     eng = RaftFlowEngine(make_raft_weights(0), iterations=3, scale=0.75)
-    assert eng.pairs_per_pass == 2   # the default of the clip path
+    assert eng.pairs_per_pass == 4   # the default of the clip path
     eng.pairs_per_pass = pairs_per_pass
     assert eng.pairs_per_pass == pairs_per_pass
     frames = np.stack([synthetic_frame(240, 320, t) for t in range(6)])
