@@ -137,13 +137,20 @@ int RaftEngine::up_conv(const std::string& name, const std::string& bn, int Cout
 
 int RaftEngine::up_encoder(const std::string& p, bool bn, EncW* e) {
   auto B = [&](const std::string& n) { return bn ? p + n : std::string(); };
-  {  // stem: im2col K = 147 -> 192; weight [64][3][7][7] flattens to k = c*49 + ky*7 + kx, i.e. a "1x1 conv" with Cin 147
+  {  // stem: im2col K = 168 -> 192; weight [64][3][7][7] flattens to k = (c*7 + ky)*8 + kx (kx = 7: zero), i.e. a "1x1 conv"
+     // with Cin 168 -- one 16-byte im2col group is one 7-pixel input row segment (raft_kernels.cu:k_im2col_stem)
     const HostTensor* w = get(p + "conv1.weight");
     if (!w) return -1;
-    HostTensor flat = *w;
+    PRISMA_CHECK(w->data.size() == (size_t)64 * 147, "RAFT conv1 has an unexpected size");
+    HostTensor flat;
+    flat.shape = {64, 168, 1, 1};
+    flat.data.assign((size_t)64 * 168, 0.f);
+    for (int o = 0; o < 64; ++o)
+      for (int cy = 0; cy < 21; ++cy)
+        for (int kx = 0; kx < 7; ++kx) flat.data[(size_t)o * 168 + cy * 8 + kx] = w->data[(size_t)o * 147 + cy * 7 + kx];
     host[p + "conv1_flat.weight"] = flat;
     host[p + "conv1_flat.bias"] = *get(p + "conv1.bias");
-    PRISMA_TRY(up_conv(p + "conv1_flat", B("norm1"), 64, 147, 1, 1, 64, 1.f, &e->stem));
+    PRISMA_TRY(up_conv(p + "conv1_flat", B("norm1"), 64, 168, 1, 1, 64, 1.f, &e->stem));
   }
   const int dims[3] = {64, 96, 128};
   int cin = 64;
@@ -536,6 +543,7 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
   __half* f1_cols = nullptr;
   PRISMA_TRY(r_alloc(plan_allocs, &f1_cols, (size_t)B * H8 * W8 * 256));
   float *zr_f = nullptr, *q_f = nullptr;  // gates in fp32, padded-row layout of the pad-2 maps
+  static const bool fuse_gru = [] { const char* e = getenv("PRISMA_RAFT_FUSE_GRU"); return !(e && e[0] == '0'); }();
   PRISMA_TRY(r_alloc(plan_allocs, &zr_f, (size_t)hx.rows() * 256));
   PRISMA_TRY(r_alloc(plan_allocs, &q_f, (size_t)hx.rows() * 128));
   PRISMA_TRY(new_map(&fh, B, H8, W8, 256, 2));
@@ -577,14 +585,24 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
       add("flow_cols", [=](cudaStream_t s) { return raft_flow_cols(c0, c1p, B, h8, w8, 2, ir8, hxp, rhp, s); });
     }
     for (int pass = 0; pass < 2; ++pass) {  // SepConvGRU horizontal then vertical (update.py:45-60)
-      { GemmEpilogue ep; ep.act = 3; ep.out_f32 = zr_f; ep.out_f32_ld = 256;
-        PRISMA_TRY(add_conv("gru_zr", hx, 0, w.zr[pass], ep, 1)); }
-      { const float* z = zr_f; const float* hm = b.h_master; __half* rhp = rhx.p;
-        add("gru_rh", [=](cudaStream_t s) { return raft_gru_rh(z, hm, rhp, rows, s); }); }
-      { GemmEpilogue ep; ep.act = 4; ep.out_f32 = q_f; ep.out_f32_ld = 128;
-        PRISMA_TRY(add_conv("gru_q", rhx, 0, w.q[pass], ep, 1)); }
-      { const float* z = zr_f; const float* qq = q_f; float* hm = b.h_master; __half* hxp = hx.p;
-        add("gru_update", [=](cudaStream_t s) { return raft_gru_update(z, qq, hm, hxp, rows, s); }); }
+      if (fuse_gru) {
+        // gate arithmetic in the conv epilogues: r * h -> the q conv's operand; h' = (1 - z) h + z q -> fp32 master + operand copy
+        { GemmEpilogue ep; ep.act = 3; ep.out_f32 = zr_f; ep.out_f32_ld = 256;
+          ep.gru = 1; ep.gru_h = b.h_master; ep.gru_rh = rhx.p; ep.gru_rh_ld = 384;
+          PRISMA_TRY(add_conv("gru_zr", hx, 0, w.zr[pass], ep, 1)); }
+        { GemmEpilogue ep; ep.act = 4; ep.out_f32 = b.h_master; ep.out_f32_ld = 128; ep.out_f16 = hx.p; ep.out_f16_ld = 384;
+          ep.gru = 2; ep.gru_h = b.h_master; ep.gru_z = zr_f;
+          PRISMA_TRY(add_conv("gru_q", rhx, 0, w.q[pass], ep, 1)); }
+      } else {
+        { GemmEpilogue ep; ep.act = 3; ep.out_f32 = zr_f; ep.out_f32_ld = 256;
+          PRISMA_TRY(add_conv("gru_zr", hx, 0, w.zr[pass], ep, 1)); }
+        { const float* z = zr_f; const float* hm = b.h_master; __half* rhp = rhx.p;
+          add("gru_rh", [=](cudaStream_t s) { return raft_gru_rh(z, hm, rhp, rows, s); }); }
+        { GemmEpilogue ep; ep.act = 4; ep.out_f32 = q_f; ep.out_f32_ld = 128;
+          PRISMA_TRY(add_conv("gru_q", rhx, 0, w.q[pass], ep, 1)); }
+        { const float* z = zr_f; const float* qq = q_f; float* hm = b.h_master; __half* hxp = hx.p;
+          add("gru_update", [=](cudaStream_t s) { return raft_gru_update(z, qq, hm, hxp, rows, s); }); }
+      }
     }
     { GemmEpilogue ep; ep.act = 2; ep.out_f16 = fh.p; ep.out_f16_ld = 256;            // flow head
       ConvW cw = w.fh1;

@@ -134,8 +134,11 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   static const bool pairs_off = [] { const char* e = getenv("PRISMA_GEMM_PAIRS"); return e && e[0] == '0'; }();
   int bn = force_bn ? force_bn : gemm_pick_bn(M, N, num_sms);
   int cg = 1;
+  static const bool pair128 = [] { const char* e = getenv("PRISMA_GEMM_PAIR128"); return e && e[0] == '1'; }();
   if (bn == 512) { bn = 256; cg = 2; }
+  else if (bn == 384) { bn = 128; cg = 2; }  // force: 256 x 128 CTA-pair tiles
   else if (!force_bn && !pairs_off && !tf32 && bn == 256 && M >= 1024 && N >= 256) cg = 2;
+  else if (!force_bn && !pairs_off && !tf32 && pair128 && bn == 128 && M >= 4096 && N >= 128 && !ep.tma_store) cg = 2;
   PRISMA_CHECK(!(tf32 && cg == 2), "gemm: the tf32 path has no CTA-pair instantiation");
   out->tf32 = tf32;
   out->xacc = false;
@@ -286,7 +289,8 @@ int gemm_run(const GemmLaunch& g, cudaStream_t stream) {
   }
   if (g.cg == 2) {
     if (g.bn == 256) return launch_bn<256, 2>(g, stream);
-    set_last_error("gemm_run: CTA pairs need BLOCK_N 256");
+    if (g.bn == 128) return launch_bn<128, 2>(g, stream);
+    set_last_error("gemm_run: CTA pairs need BLOCK_N 256 or 128");
     return -1;
   }
   switch (g.bn) {

@@ -88,6 +88,16 @@ struct GemmEpilogue {
   const int* m_dev = nullptr;
   // dense fp32 output (row_map LINEAR, scale only) stored by TMA: tcgen05.ld -> swizzled smem box -> cp.async.bulk.tensor
   bool tma_store = false;
+  // ConvGRU gate arithmetic in the epilogue of the gate convs (raft/update.py:54-58), all fp32, indexed by dst row:
+  //  gru == 1 (the z | r conv, N = 256, act sigmoid): columns [0,128) = z -> out_f32 as usual; columns [128,256) = r are not
+  //            stored: r * h (gru_h: fp32 [rows][128]) goes to gru_rh (fp16, pitch gru_rh_ld) -- the q conv's operand;
+  //  gru == 2 (the q conv, N = 128, act tanh): h' = (1 - z) h + z q with z = gru_z (fp32, pitch 256) and h = gru_h; h' then
+  //            takes the normal output path (out_f32 = the fp32 master of h, in place; out_f16 = the conv operand copy).
+  int gru = 0;
+  const float* gru_h = nullptr;
+  const float* gru_z = nullptr;
+  __half* gru_rh = nullptr;
+  int gru_rh_ld = 0;
 };
 
 struct GemmArgs {
@@ -146,6 +156,7 @@ __device__ __forceinline__ void add_h4(float4& v, const uint2& r) {
 // Coalesced phase of the epilogue for one 32-column chunk: this lane owns 4 consecutive columns (col..col+3) of the
 // 8 rows dr[0..7] (8 lanes cover a row's 32 columns, so a warp instruction touches 4 rows x 128 B fp32 / 64 B fp16).
 // All loads of a kind are issued before any is consumed (8 independent requests in flight per lane).
+template <bool GRU>  // GRU: compile the ConvGRU gate paths (fp16-operand instantiations only; keeps the 3xTF32 kernels lean)
 __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&v)[8], const int (&dr)[8], uint32_t okm,
                                                const float4& bias, const float4& gamma, int col) {
 #pragma unroll
@@ -186,6 +197,39 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) { v[i].x *= gamma.x; v[i].y *= gamma.y; v[i].z *= gamma.z; v[i].w *= gamma.w; }
+  if (GRU && ep.gru == 1) {
+    if (col >= 128) {  // warp-uniform: a 32-column chunk lies in one half
+      float4 h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        h[i] = (okm >> i) & 1 ? *reinterpret_cast<const float4*>(ep.gru_h + (size_t)dr[i] * 128 + (col - 128))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((okm >> i) & 1)
+          *reinterpret_cast<uint2*>(ep.gru_rh + (size_t)dr[i] * ep.gru_rh_ld + (col - 128)) =
+              make_uint2(pack_half2(v[i].x * h[i].x, v[i].y * h[i].y), pack_half2(v[i].z * h[i].z, v[i].w * h[i].w));
+      return;
+    }
+  } else if (GRU && ep.gru == 2) {
+    float4 z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      z[i] = (okm >> i) & 1 ? *reinterpret_cast<const float4*>(ep.gru_z + (size_t)dr[i] * 256 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i].x *= z[i].x; v[i].y *= z[i].y; v[i].z *= z[i].z; v[i].w *= z[i].w; }   // z q
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { z[i].x = 1.f - z[i].x; z[i].y = 1.f - z[i].y; z[i].z = 1.f - z[i].z; z[i].w = 1.f - z[i].w; }
+    float4 h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      h[i] = (okm >> i) & 1 ? *reinterpret_cast<const float4*>(ep.gru_h + (size_t)dr[i] * 128 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // (1 - z) * h + z * q, the products rounded separately like the reference's two multiplies
+      v[i].x = __fadd_rn(__fmul_rn(z[i].x, h[i].x), v[i].x); v[i].y = __fadd_rn(__fmul_rn(z[i].y, h[i].y), v[i].y);
+      v[i].z = __fadd_rn(__fmul_rn(z[i].z, h[i].z), v[i].z); v[i].w = __fadd_rn(__fmul_rn(z[i].w, h[i].w), v[i].w);
+    }
+  }
   if (ep.res_f32) {
     float4 t[8];
 #pragma unroll
@@ -527,9 +571,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int rr = 0; rr < 8; ++rr)
             drs[rr] = ib8[rr] + (ty8[rr] * ep.shuf_s + sdy + out_ld) * ep.out_wp + tx8[rr] * ep.shuf_s + sdx + out_ld;
-          epilogue_rows8(ep, v, drs, ncol_ok ? okrows : 0u, bias4, gamma4, col);
+          epilogue_rows8<!TF32 && !XACC && !TMAST>(ep, v, drs, ncol_ok ? okrows : 0u, bias4, gamma4, col);
         } else {
-          epilogue_rows8(ep, v, dr8, ncol_ok ? okrows : 0u, bias4, gamma4, col);
+          epilogue_rows8<!TF32 && !XACC && !TMAST>(ep, v, dr8, ncol_ok ? okrows : 0u, bias4, gamma4, col);
         }
         if (ep.stat_part != nullptr) {
           float4 sm = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -9,30 +9,34 @@ namespace prisma {
 
 // ------------------------------------------------------------------------------------------------
 // stem im2col: conv1 = Conv2d(3, 64, 7, stride 2, padding 3) (extractor.py:133) on the normalised CHW fp32 image
-// -> fp16 [B*Ho*Wo][192], k = c*49 + ky*7 + kx (zero padded 147..191).  Stride 2 is applied here, no wasted rows.
+// -> fp16 [B*Ho*Wo][192], k = (c*7 + ky)*8 + kx (kx = 7 and k >= 168: zero; the engine packs the weights in the same order).
+// Stride 2 is applied here, no wasted rows.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_im2col_stem(const float* __restrict__ x, int B, int H, int W, __half* __restrict__ out) {
   pdl_prologue();
-  // one thread = 8 consecutive k of one output pixel (a 16-byte store); consecutive threads = consecutive k groups, so a
-  // warp writes 512 contiguous bytes and its gathers walk the same few image rows
+  // one thread = one (c, ky) row of one output pixel: 7 consecutive input floats -> a 16-byte store; consecutive threads =
+  // consecutive groups, so a warp writes 512 contiguous bytes and its gathers walk the same few image rows
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * Ho * Wo * 24;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i % 24);
     const long long pix = i / 24;  // b*Ho*Wo + oy*Wo + ox
-    const int b = (int)(pix / ((long long)Ho * Wo));
-    const int r = (int)(pix - (long long)b * Ho * Wo);
-    const int oy = r / Wo, ox = r - oy * Wo;
-    const float* img = x + (size_t)b * 3 * H * W;
-    float v[8];
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (g < 21) {
+      const int b = (int)(pix / ((long long)Ho * Wo));
+      const int r = (int)(pix - (long long)b * Ho * Wo);
+      const int oy = r / Wo, ox = r - oy * Wo;
+      const int c = g / 7, ky = g - c * 7;
+      const int iy = oy * 2 - 3 + ky, ix0 = ox * 2 - 3;
+      if (iy >= 0 && iy < H) {
+        const float* row = x + (((size_t)b * 3 + c) * H + iy) * W;
+        if (ix0 >= 0 && ix0 + 6 < W) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      v[j] = 0.f;
-      if (k < 147) {
-        const int c = k / 49, t = k - c * 49, ky = t / 7, kx = t - ky * 7;
-        const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[j] = img[((size_t)c * H + iy) * W + ix];
+          for (int j = 0; j < 7; ++j) v[j] = __ldg(row + ix0 + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 7; ++j) if (ix0 + j >= 0 && ix0 + j < W) v[j] = __ldg(row + ix0 + j);
+        }
       }
     }
     *reinterpret_cast<uint4*>(out + (size_t)pix * 192 + g * 8) =
@@ -79,14 +83,26 @@ __global__ void k_in_partial(const float* __restrict__ x, int HW, int C, int row
 }
 __global__ void k_in_final(const float* __restrict__ part, int nblk, int C, int HW, float eps, float* __restrict__ stats) {
   pdl_prologue();
-  const int b = blockIdx.x, c = threadIdx.x;
-  if (c >= C) return;
+  // blockDim.x / C groups of C threads add interleaved stripes of the partial blocks in double, then group 0 adds the groups
+  // (fixed order: deterministic)
+  __shared__ double shd[512 * 2];
+  const int b = blockIdx.x;
+  const int groups = blockDim.x / C;
+  const int g = threadIdx.x / C, c = threadIdx.x - g * C;
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < nblk; ++k) {
-    const float* p = part + (((size_t)b * nblk + k) * C + c) * 2;
-    s += p[0];
-    q += p[1];
+  if (g < groups) {
+    for (int k = g; k < nblk; k += groups) {
+      const float* p = part + (((size_t)b * nblk + k) * C + c) * 2;
+      s += p[0];
+      q += p[1];
+    }
+    shd[(g * C + c) * 2] = s;
+    shd[(g * C + c) * 2 + 1] = q;
   }
+  __syncthreads();
+  if (threadIdx.x >= C) return;
+  s = 0.0; q = 0.0;
+  for (int gg = 0; gg < groups; ++gg) { s += shd[(gg * C + c) * 2]; q += shd[(gg * C + c) * 2 + 1]; }
   const double mean = s / HW;
   const double var = fmax(q / HW - mean * mean, 0.0);
   stats[((size_t)b * C + c) * 2] = (float)mean;
@@ -97,7 +113,7 @@ int instnorm_stats(const float* x, int B, int HW, int C, float* part, float* sta
   const int rows_per_block = 512;
   const int nblk = ceil_div(HW, rows_per_block);
   PRISMA_CUDA_OK(pdl_launch(k_in_partial, dim3(dim3(nblk, B)), dim3(threads), threads * 2 * sizeof(float), s, x, HW, C, rows_per_block, part));
-  PRISMA_CUDA_OK(pdl_launch(k_in_final, dim3(B), dim3(128), 0, s, part, nblk, C, HW, 1e-5f, stats));
+  PRISMA_CUDA_OK(pdl_launch(k_in_final, dim3(B), dim3(512), 0, s, part, nblk, C, HW, 1e-5f, stats));
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
 }

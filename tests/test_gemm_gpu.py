@@ -38,6 +38,8 @@ def _gemm(A, W, bias, act, bn):
     (2443, 3072, 1024, 0, 512),  # CTA pairs, ViT-L qkv: ragged M, many tiles per pair
     (9772, 1024, 4096, 1, 512),  # CTA pairs, 4-frame fc2 shape with gelu
     (300, 256, 200, 2, 512),     # CTA pairs: second CTA's rows partly / fully out of range, K tail
+    (37000, 128, 1920, 0, 384),  # CTA pairs with 256 x 128 tiles (the RAFT GRU q conv shape), ragged M
+    (700, 256, 320, 2, 384),     # 256 x 128 pair tiles, two column tiles, K tail
     # auto tile choice with a partial last wave -> mixed-width tail tiles (GemmArgs::tail_split)
     (29316, 1024, 192, 0, 0),    # CTA pairs: 460 pair tiles = 6 waves + 16 -> the 16 cut into 4 x 64-wide tiles
     (26624, 256, 128, 2, 0),     # CTA pairs: 104 pair tiles = 1 wave + 30 -> cut into 2 x 128-wide tiles
