@@ -175,11 +175,19 @@ int SoloEngine::up_conv3(const std::string& name, const std::string& gn, int Cou
 int SoloEngine::finalize() {
   PRISMA_CHECK(!finalized, "finalize called twice");
   PRISMA_CUDA_OK(cudaSetDevice(device));
-  {  // stem 7x7/2: im2col K = 147 (k = c*49 + ky*7 + kx) -> a "1x1 conv" with Cin 147
+  {  // stem 7x7/2: im2col K = 168, k = (c*7 + ky)*8 + kx with kx = 7 zero (the layout raft_im2col_stem writes: one 16-byte group
+     // = one 7-pixel input row segment) -> a "1x1 conv" with Cin 168
     const HostTensor* w = get("backbone.conv1.weight");
     if (!w) return -1;
-    host["backbone.conv1_flat.weight"] = *w;
-    PRISMA_TRY(up_conv("backbone.conv1_flat", "backbone.bn1", "", 64, 147, 1, false, &stem));
+    PRISMA_CHECK(w->data.size() == (size_t)64 * 147, "backbone.conv1 has an unexpected size");
+    HostTensor flat;
+    flat.shape = {64, 168, 1, 1};
+    flat.data.assign((size_t)64 * 168, 0.f);
+    for (int o = 0; o < 64; ++o)
+      for (int cy = 0; cy < 21; ++cy)
+        for (int kx = 0; kx < 7; ++kx) flat.data[(size_t)o * 168 + cy * 8 + kx] = w->data[(size_t)o * 147 + cy * 7 + kx];
+    host["backbone.conv1_flat.weight"] = flat;
+    PRISMA_TRY(up_conv("backbone.conv1_flat", "backbone.bn1", "", 64, 168, 1, false, &stem));
   }
   int inplanes = 64;
   const int planes_of[4] = {64, 128, 256, 512};
