@@ -6,32 +6,97 @@
 //                             [tokens][3*D] qkv matrix -- no head split/transposes ever materialise)
 //   warp 1   : MMA issuer    (S = Q K^T  -> TMEM cols [0,128);  O += P V -> TMEM cols [128,192): A = P read from TMEM
 //                             cols [192,256) (fp16 pairs written there by the softmax warps with tcgen05.st), B = V
-//                             from smem as an MN-major operand.  P never goes through shared memory: the SM's 128 B/clk
-//                             smem port is then only used by TMA fills and the Q/K/V operand reads)
-//   warps 2-9: softmax       (thread = half a query row -- warps w and w+4 share a TMEM lane quarter and take the
-//                             column halves, so 4 warps per scheduler keep the MUFU pipe fed: tcgen05.ld S, online max/sum in fp32, P -> fp16 -> swizzled smem
-//                             as the A operand of the PV MMA).  O accumulates in TMEM across all KV tiles; the
-//                             running-max rescale is lazy: O (and l) are only rescaled -- tcgen05.ld/st of this
-//                             warp's 32 lanes -- when a row's max grew by more than 2^8, so P stays <= 256 in fp16
-//                             and the common path has no per-tile accumulator traffic at all.
+//                             from smem as an MN-major operand.  P never goes through shared memory.)
+//   warps 2-5: softmax       (thread = ONE query row = one TMEM lane: the 128 scores of the tile sit in 128 registers, so
+//                             nothing is exchanged between threads and there is no barrier inside a tile).
+// The exp pipe (MUFU, 16 ex2 / clk / SM) bounds this kernel; a softmax warp is in-order and only two of them share a
+// scheduler, so the tile loop is written for instruction-level parallelism inside one warp:
+//   * row max by four FMNMX3 chains over the 128 registers (no exchange, no barrier); O and l are rescaled lazily, only when a
+//     row's max grew by more than 2^8 since the value they are scaled by (p stays <= 256 in fp16);
+//   * the exps of a 32-key chunk are computed IN PLACE, all 32 FFMA + MUFU.EX2 issued before the first sum / pack consumes
+//     a result, so the warp does not stall on the MUFU latency;
+//   * warps whose 32 query rows all lie beyond the last token (last q tile) take no part, and the columns of the last KV tile
+//     beyond the last key are zero-filled in 32-column chunks without touching the exp pipe.
 #include "attention.cuh"
 
 namespace prisma {
 
 constexpr int ATT_BQ = 128, ATT_BKV = 128, ATT_HD = 64;
-constexpr int ATT_THREADS = 320;  // TMA warp + MMA warp + 8 softmax warps (two per TMEM lane quarter: column halves)
-constexpr int ATT_SOFTMAX_WARP0 = 2;
+constexpr int ATT_THREADS = 192;  // TMA warp + MMA warp + 4 softmax warps (one per TMEM lane quarter)
+constexpr int ATT_SOFTMAX_WARPS = 4;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
-// 7 tiles + barriers = 114,816 B: two CTAs (+1 KB reserved each) fit the 228 KB of an SM; no alignment slack, the
+// Q + 2 x (K, V) + barriers = 82,048 B: two CTAs (+1 KB reserved each) fit the 228 KB of an SM; no alignment slack, the
 // dynamic smem base is declared 1024-aligned (128B-swizzle atoms are 1 KB) and checked at kernel entry.
-// Q + 2 x (K, V) + barriers + row-max exchange; P never touches shared memory (it is the TMEM A operand of the PV MMA)
-constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 + 2) + 128 /*barriers*/ + 1024 /*row-max exchange, two parities*/;
+constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 + 2) + 128 /*barriers*/;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// 32 scores -> 32 probabilities, in place; fp16 pairs to pk[16], their sum to four partial sums.  nvalid < 32: the rest are 0.
+template <bool PARTIAL>
+__device__ __forceinline__ void att_exp_chunk(uint32_t* v, float mscaled, int nvalid, uint32_t* pk, float& s0, float& s1, float& s2,
+                                              float& s3) {
+  const float LOG2E = 1.4426950408889634f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(v[i]), LOG2E, -mscaled));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ex2_approx(__uint_as_float(v[i])));
+  if (PARTIAL) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? v[i] : 0u;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t* e = v + c * 8;
+    s0 += __uint_as_float(e[0]) + __uint_as_float(e[4]); s1 += __uint_as_float(e[1]) + __uint_as_float(e[5]);
+    s2 += __uint_as_float(e[2]) + __uint_as_float(e[6]); s3 += __uint_as_float(e[3]) + __uint_as_float(e[7]);
+    pk[c * 4 + 0] = pack_half2(__uint_as_float(e[0]), __uint_as_float(e[1])); pk[c * 4 + 1] = pack_half2(__uint_as_float(e[2]), __uint_as_float(e[3]));
+    pk[c * 4 + 2] = pack_half2(__uint_as_float(e[4]), __uint_as_float(e[5])); pk[c * 4 + 3] = pack_half2(__uint_as_float(e[6]), __uint_as_float(e[7]));
+  }
+}
+
+// A full tile (128 valid keys): the same arithmetic as four att_exp_chunk<false> calls, software-pipelined across the chunks --
+// the MUFU.EX2 of chunk c + 1 are issued interleaved with the sums / packs of chunk c, so an in-order warp never waits on the
+// exp it has just issued (only two softmax warps share a scheduler: there is nobody else to hide that latency).
+__device__ __forceinline__ void att_exp_tile(uint32_t* v, float mscaled, uint32_t tmem_p_row, float& s0, float& s1, float& s2,
+                                             float& s3) {
+  const float LOG2E = 1.4426950408889634f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(v[i]), LOG2E, -mscaled)));
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t* e = v + c * 32;
+    uint32_t* nx = v + (c + 1) * 32;
+    if (c + 1 < 4) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) nx[i] = __float_as_uint(fmaf(__uint_as_float(nx[i]), LOG2E, -mscaled));
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (c + 1 < 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nx[g * 8 + i] = __float_as_uint(ex2_approx(__uint_as_float(nx[g * 8 + i])));
+      }
+      const uint32_t* q = e + g * 8;
+      s0 += __uint_as_float(q[0]) + __uint_as_float(q[4]); s1 += __uint_as_float(q[1]) + __uint_as_float(q[5]);
+      s2 += __uint_as_float(q[2]) + __uint_as_float(q[6]); s3 += __uint_as_float(q[3]) + __uint_as_float(q[7]);
+      pk[g * 4 + 0] = pack_half2(__uint_as_float(q[0]), __uint_as_float(q[1])); pk[g * 4 + 1] = pack_half2(__uint_as_float(q[2]), __uint_as_float(q[3]));
+      pk[g * 4 + 2] = pack_half2(__uint_as_float(q[4]), __uint_as_float(q[5])); pk[g * 4 + 3] = pack_half2(__uint_as_float(q[6]), __uint_as_float(q[7]));
+    }
+    tmem_st16(tmem_p_row + c * 16, pk);
+  }
+}
+
+// Two CTAs share an SM and start together; their tile loops have the same period, so without help they stay in lockstep --
+// both in the exp phase (contending for MUFU), then both in the load / max / store phases (MUFU idle).  Every second CTA to
+// arrive on an SM in the first wave therefore delays its softmax warps by about half a tile period; equal periods keep the
+// offset, and the CTAs of later waves inherit it from the CTA whose slot they take over.
+__device__ unsigned int g_att_sm_ticket[1024];
+constexpr int ATT_STAGGER_CYCLES = 1100;
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ AttnArgs args) {
@@ -52,7 +117,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* pv_done = bars + 7;
   uint64_t* s_free = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  __half* s_xmax = reinterpret_cast<__half*>(smem + 5 * ATT_TILE_BYTES + 128);  // [2 parities][2 halves][128 rows]
+  uint32_t* sm_ticket = tmem_slot + 1;  // arrival number of this CTA on its SM
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = args.tokens, D = args.D;
@@ -66,10 +131,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 8);
+    // softmax warps whose 32 rows all lie beyond the last token take no part (last q tile of an image)
+    const int n_live = min(ATT_SOFTMAX_WARPS, (args.tokens - blockIdx.x * ATT_BQ + 31) / 32);
+    mbar_init(p_full, n_live);
     mbar_init(pv_done, 1);
-    mbar_init(s_free, 8);
+    mbar_init(s_free, n_live);
     fence_mbar_init();
+    unsigned int smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    *sm_ticket = args.stagger > 0 ? atomicAdd(&g_att_sm_ticket[smid & 1023u], 1u) : 0u;
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -119,7 +189,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           for (int k = 0; k < 4; ++k) umma_f16(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
           umma_commit(s_full);
         }
-        mbar_wait(p_full, j & 1);  // P(j) in smem, any lazy rescale of O done
+        mbar_wait(p_full, j & 1);  // P(j) in TMEM, any rescale of O done
         tc_fence_after();
         const uint32_t vbase = smem_u32(sV + st * ATT_TILE_BYTES);
 #pragma unroll
@@ -131,164 +201,160 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         umma_commit(&kv_empty[st]);
       }
     }
-  } else if (warp >= ATT_SOFTMAX_WARP0) {
-    const int quarter = warp & 3;
-    const int half = (warp - ATT_SOFTMAX_WARP0) >> 2;   // which 64 score columns (= which K-slab of P, which 32 columns of O)
-    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+  } else {
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;    // query row inside the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const bool warp_live = q0 + quarter * 32 < T;  // warp-uniform: at least one of my 32 rows is a real query
     const float LOG2E = 1.4426950408889634f;
-    float m_used = -INFINITY, l_part = 0.f;  // m_used: the max P / O are currently scaled by; l_part: my half's row sum
-    const uint32_t bar_id = 1 + quarter;  // named barrier of the two warps that share this lane quarter
+    float m_used = -INFINITY, l_sum = 0.f;  // m_used: the max P / O are currently scaled by
+    // only the CTAs of the first wave start together; later ones inherit the offset of the CTA whose slot they take over
+    const unsigned int linear_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (args.stagger > 0 && linear_cta < (unsigned)args.first_wave && (*sm_ticket & 1u)) {  // the second CTA of the pair on this SM
+      const long long t0 = clock64();
+      while (clock64() - t0 < args.stagger) { }
+    }
 #ifdef PRISMA_ATTN_PROFILE
-    long long t_wait = 0, t_p1 = 0, t_p2 = 0, t_ld = 0, t_max = 0, t_pvw = 0, t_exp = 0, t_tot = clock64();
+    long long t_wait = 0, t_ld = 0, t_max = 0, t_exp = 0, t_st = 0, t_slow = 0, n_slow = 0, t_tot = clock64();
     const bool prof = args.dbg != nullptr && threadIdx.x == 64 && blockIdx.x == 1 && blockIdx.y == 1;
 #define ATT_CLK(x) long long x = clock64()
 #else
 #define ATT_CLK(x)
 #endif
 
-    for (int j = 0; j < n_kv; ++j) {
-      const int valid = min(64, max(0, T - j * ATT_BKV - half * 64));  // valid columns of my half (0..64)
+    for (int j = 0; warp_live && j < n_kv; ++j) {  // dead warps (rows beyond the last token) are not counted by the barriers
       ATT_CLK(c0_);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       ATT_CLK(c1_);
-      // ---- my half of the S row (64 fp32) into registers with one wait; then the TMEM buffer is free for S(j+1)
-      uint32_t v[64];
-      tmem_ld32(tmem_S + lane_sel + half * 64, v);
-      tmem_ld32(tmem_S + lane_sel + half * 64 + 32, v + 32);
+      const int valid = min(ATT_BKV, T - j * ATT_BKV);  // valid key columns of this tile (1..128)
+      // ---- the whole S row (128 fp32) into registers with one wait; then the TMEM buffer is free for S(j+1)
+      uint32_t v[128];
+      tmem_ld32(tmem_S + lane_sel, v);
+      tmem_ld32(tmem_S + lane_sel + 32, v + 32);
+      tmem_ld32(tmem_S + lane_sel + 64, v + 64);
+      tmem_ld32(tmem_S + lane_sel + 96, v + 96);
       tmem_ld_wait();
-      ATT_CLK(c1a_);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
-      float mx = -INFINITY;
-      if (valid == 64) {  // four FMNMX3 chains
-        float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
-        float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
-        float m2 = fmax3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
-        float m3 = fmax3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+      ATT_CLK(c2_);
+
+      // ---- row max (thread-local), lazy rescale of O and l
+      float mx;
+      if (valid == ATT_BKV) {  // eight FMNMX3 chains of 8 (short dependent chains: the warp is in-order)
+        float m[8];
 #pragma unroll
-        for (int i = 12; i < 60; i += 8) {
-          m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-          m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-          m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
-          m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-        }
-        m0 = fmax3(m0, __uint_as_float(v[60]), __uint_as_float(v[61]));
-        m1 = fmax3(m1, __uint_as_float(v[62]), __uint_as_float(v[63]));
-        mx = fmaxf(fmax3(m0, m1, m2), m3);
+        for (int c = 0; c < 8; ++c) m[c] = fmax3(__uint_as_float(v[c * 16]), __uint_as_float(v[c * 16 + 1]), __uint_as_float(v[c * 16 + 2]));
+#pragma unroll
+        for (int k = 3; k < 15; k += 2)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) m[c] = fmax3(m[c], __uint_as_float(v[c * 16 + k]), __uint_as_float(v[c * 16 + k + 1]));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m[c] = fmaxf(m[c], __uint_as_float(v[c * 16 + 15]));
+        mx = fmaxf(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], fmax3(m[5], m[6], m[7])));
       } else {
+        mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 128; ++i) if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
-      // ---- row max across the two halves: exchanged as fp16 rounded UP (both threads then use the identical value,
-      // which is all the online softmax needs; >= the true max, so p <= 1 up to the lazy-rescale slack)
-      ATT_CLK(c1b_);
-      // Buffers alternate with the tile parity, so one barrier per tile suffices: a buffer is rewritten two tiles later,
-      // after the barrier of the tile in between, which the partner only reaches once it has read this one.
-      __half* xm = s_xmax + (j & 1) * 256;
-      xm[half * 128 + r] = __float2half_ru(fmaxf(mx, -60000.f));
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      mx = fmaxf(__half2float(xm[r]), __half2float(xm[128 + r]));
-      // ---- lazy rescale (identical decision in both warps of the quarter; each owns 32 columns of O)
+      mx = fmaxf(mx, -60000.f);  // a row of -inf scores must not produce inf - inf
+      bool pv_waited = (j == 0);
       if (j == 0) {
         m_used = mx;
       } else {
         const bool need = (mx - m_used) * LOG2E > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
+          ATT_CLK(cs0_);
           const float m_new = need ? mx : m_used;
           const float alpha = ex2_approx((m_used - m_new) * LOG2E);  // 1 for rows that keep their max
           mbar_wait(pv_done, (j - 1) & 1);                            // no PV may be in flight on O
           tc_fence_after();
+          pv_waited = true;
 #pragma unroll 1
-          for (int hh = 0; hh < 2; ++hh) {  // 16 columns at a time: keeps the S row in registers
+          for (int hh = 0; hh < 4; ++hh) {  // 16 columns at a time: the S row stays in registers
             uint32_t o[16];
-            tmem_ld16(tmem_O + lane_sel + half * 32 + hh * 16, o);
+            tmem_ld16(tmem_O + lane_sel + hh * 16, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tmem_O + lane_sel + half * 32 + hh * 16, o);
+            tmem_st16(tmem_O + lane_sel + hh * 16, o);
           }
           tmem_st_wait();
-          l_part *= alpha;
+          l_sum *= alpha;
           m_used = m_new;
+#ifdef PRISMA_ATTN_PROFILE
+          t_slow += clock64() - cs0_; ++n_slow;
+#endif
         }
       }
-      const float mscaled = m_used * LOG2E;
-      ATT_CLK(c2_);
-      // ---- p = exp(s - m_used), partial row sum, P -> fp16 -> swizzled smem (K-slab `half` of the PV A operand)
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      // two chunks of 32 probabilities -> 16 packed fp16 pairs -> 16 TMEM columns each (keeps the live set small)
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t pk[16];
-        if (valid == 64) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float e[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[hh * 32 + c * 8 + i]), LOG2E, -mscaled));
-            sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
-            pk[c * 4 + 0] = pack_half2(e[0], e[1]); pk[c * 4 + 1] = pack_half2(e[2], e[3]);
-            pk[c * 4 + 2] = pack_half2(e[4], e[5]); pk[c * 4 + 3] = pack_half2(e[6], e[7]);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {  // last KV tile only; fully unrolled so v[] stays in registers
-            float e[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float x = ex2_approx(fmaf(__uint_as_float(v[hh * 32 + c * 8 + i]), LOG2E, -mscaled));
-              e[i] = (hh * 32 + c * 8 + i < valid) ? x : 0.f;
-            }
-            sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
-            pk[c * 4 + 0] = pack_half2(e[0], e[1]); pk[c * 4 + 1] = pack_half2(e[2], e[3]);
-            pk[c * 4 + 2] = pack_half2(e[4], e[5]); pk[c * 4 + 3] = pack_half2(e[6], e[7]);
-          }
-        }
-        // P(j-1) must have been consumed by PV(j-1) before the buffer is rewritten (issued a whole softmax ago)
-        if (hh == 0 && j > 0) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }
-        tmem_st16(tmem_P + lane_sel + half * 32 + hh * 16, pk);
-      }
-      l_part += (sum0 + sum1) + (sum2 + sum3);
       ATT_CLK(c2b_);
+      // ---- p = exp(s - m_used) in four chunks of 32 keys -> 16 packed fp16 pairs -> 16 TMEM columns each
+      const float mscaled = m_used * LOG2E;
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      // P(j-1) must have been consumed by PV(j-1) before the buffer is rewritten (issued a whole softmax ago: no wait in practice)
+      if (!pv_waited) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }
+      if (valid == ATT_BKV) {
+        att_exp_tile(v, mscaled, tmem_P + lane_sel, sum0, sum1, sum2, sum3);
+      } else {
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          const int nv = valid - hh * 32;  // valid columns of this chunk (warp-uniform)
+          if (nv >= 32) {
+            uint32_t pk[16];
+            att_exp_chunk<false>(v + hh * 32, mscaled, 32, pk, sum0, sum1, sum2, sum3);
+            tmem_st16(tmem_P + lane_sel + hh * 16, pk);
+          } else if (nv > 0) {
+            uint32_t pk[16];
+            att_exp_chunk<true>(v + hh * 32, mscaled, nv, pk, sum0, sum1, sum2, sum3);
+            tmem_st16(tmem_P + lane_sel + hh * 16, pk);
+          } else {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            tmem_st16(tmem_P + lane_sel + hh * 16, pk);
+          }
+        }
+      }
+      const float tsum = (sum0 + sum1) + (sum2 + sum3);
+      l_sum += tsum;
+      ATT_CLK(c3_);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
 #ifdef PRISMA_ATTN_PROFILE
-      long long c3_ = clock64();
-      t_wait += c1_ - c0_; t_p1 += c2_ - c1_; t_p2 += c3_ - c2_;
-      t_ld += c1a_ - c1_; t_max += c1b_ - c1a_; t_exp += c2b_ - c2_;
+      long long c4_ = clock64();
+      t_wait += c1_ - c0_; t_ld += c2_ - c1_; t_max += c2b_ - c2_; t_exp += c3_ - c2b_; t_st += c4_ - c3_;
 #endif
     }
 #ifdef PRISMA_ATTN_PROFILE
-    if (prof) { args.dbg[0] = t_wait; args.dbg[1] = t_p1; args.dbg[2] = t_p2; args.dbg[3] = clock64() - t_tot; args.dbg[4] = n_kv;
-                args.dbg[5] = t_ld; args.dbg[6] = t_max; args.dbg[7] = t_pvw; args.dbg[8] = t_exp; }
+    if (prof) { args.dbg[0] = t_wait; args.dbg[1] = t_ld; args.dbg[2] = t_exp; args.dbg[3] = clock64() - t_tot; args.dbg[4] = n_kv;
+                args.dbg[5] = t_st; args.dbg[6] = t_slow; args.dbg[7] = n_slow; args.dbg[8] = t_max; }
 #endif
-    // ---- O is complete once the last PV retires; the K stages are then idle and carry the row-sum exchange
-    mbar_wait(pv_done, (n_kv - 1) & 1);
-    tc_fence_after();
-    float* s_l = reinterpret_cast<float*>(sK);  // [2 parities][2 halves][128 rows]; the K stages are idle by now
-    s_l[half * 128 + r] = l_part;
-    uint32_t ov[32];
-    tmem_ld32(tmem_O + lane_sel + half * 32, ov);
-    tmem_ld_wait();
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-    const float inv = 1.0f / (s_l[r] + s_l[128 + r]);
-    // ---- normalise and store my 32 columns: out[row][head*64 + half*32 + d]
-    const int q = q0 + r;
-    if (q < T) {
-      __half* dst = args.out + (size_t)(row_base + q) * args.out_ld + head * ATT_HD + half * 32;
+    if (warp_live) {
+      // ---- O is complete once the last PV retires: normalise and store my row, out[row][head*64 + d]
+      mbar_wait(pv_done, (n_kv - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l_sum;
+      const int q = q0 + r;
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t ov[32];
+        tmem_ld32(tmem_O + lane_sel + hh * 32, ov);
+        tmem_ld_wait();
+        if (q < T) {
+          __half* dst = args.out + (size_t)(row_base + q) * args.out_ld + head * ATT_HD + hh * 32;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 o;
-        o.x = pack_half2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
-        o.y = pack_half2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
-        o.z = pack_half2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
-        o.w = pack_half2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + g * 8) = o;
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_half2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
+            o.y = pack_half2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
+            o.z = pack_half2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
+            o.w = pack_half2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + g * 8) = o;
+          }
+        }
       }
     }
   }
@@ -310,6 +376,16 @@ int attention_prepare(AttnLaunch* out, const __half* qkv, __half* o, int batch, 
   out->args.out = o;
   out->args.out_ld = D;
   out->args.dbg = nullptr;
+  {
+    static const int stagger = [] { const char* e = getenv("PRISMA_ATTN_STAGGER"); return e ? atoi(e) : ATT_STAGGER_CYCLES; }();
+    out->args.stagger = stagger;
+    static const int first_wave = [] {
+      int dev = 0, sms = 148;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      return 2 * sms;  // two resident CTAs per SM
+    }();
+    out->args.first_wave = first_wave;
+  }
   PRISMA_TRY(make_tmap_2d_f16(&out->tm, qkv, (uint64_t)3 * D, (uint64_t)batch * tokens, (uint64_t)3 * D, 64, 128));
   out->grid = dim3(ceil_div(tokens, ATT_BQ), heads, batch);
   out->flops = 4.0 * batch * heads * (double)tokens * tokens * ATT_HD;

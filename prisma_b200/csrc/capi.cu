@@ -392,9 +392,8 @@ int prisma_debug_attention(int device, const float* qkv, float* out, int T, int 
   if (a.args.dbg) {
     long long h[16];
     PRISMA_CUDA_OK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
-    printf("attention cycles (one softmax warp, CTA (1,1)): wait_S %lld  pass1 %lld  pass2 %lld  total %lld  tiles %lld\n"
-           "   pass1: tmem_ld %lld  max %lld  exchange+rescale %lld | pass2: pv_wait %lld  exp %lld  st+arrive %lld\n",
-           h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[1] - h[5] - h[6], h[7], h[8], h[2] - h[7] - h[8]);
+    printf("attention cycles (one softmax warp, CTA (1,1)): wait_S %lld  tmem_ld %lld  max(+rescale) %lld  exp %lld  st+arrive %lld  total %lld  tiles %lld\n"
+           "   lazy rescale of O: %lld cycles in %lld tiles\n", h[0], h[1], h[8], h[2], h[5], h[3], h[4], h[6], h[7]);
   }
   std::vector<__half> ho((size_t)T * D);
   PRISMA_CUDA_OK(cudaMemcpy(ho.data(), dO, ho.size() * 2, cudaMemcpyDeviceToHost));
