@@ -35,6 +35,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// exp2 on the FMA / ALU pipes for a fraction of the elements: Cody-Waite split x = n + f, f in [-0.5, 0.5], 2^f by a degree-3
+// minimax polynomial (max relative error 7.6e-5, well below the 4.9e-4 rounding of the fp16 probability it becomes), 2^n by
+// adding n to the exponent field.  x <= 8 here (lazy-rescale slack).  MEASURED AND LEFT OFF (B200, 2443 tokens, 192 heads):
+// none 643 TFLOP/s, every 4th element 636, every 3rd 619, every 2nd 550 -- with two in-order softmax warps per scheduler the
+// kernel is bound by issue slots and dependency latency, not by the exp pipe's 16 / clk, so nine instructions instead of two
+// per element lose.  -DPRISMA_ATTN_POLY=n builds the variant.
+#ifndef PRISMA_ATTN_POLY
+#define PRISMA_ATTN_POLY 0   // every PRISMA_ATTN_POLY-th element of a chunk takes the polynomial (0: none)
+#endif
+__device__ __forceinline__ float ex2_poly3(float x) {
+  x = fmaxf(x, -125.f);
+  const float r = x + 12582912.f;        // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (r - 12582912.f);
+  float p = fmaf(0.05520550534f, f, 0.2426139712f);
+  p = fmaf(p, f, 0.6932547688f);
+  p = fmaf(p, f, 0.9999276996f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+__device__ __forceinline__ float att_ex2(float x, int i) {
+#if PRISMA_ATTN_POLY > 0
+  if (i % PRISMA_ATTN_POLY == PRISMA_ATTN_POLY - 1) return ex2_poly3(x);
+#endif
+  return ex2_approx(x);
+}
+
 // 32 scores -> 32 probabilities, in place; fp16 pairs to pk[16], their sum to four partial sums.  nvalid < 32: the rest are 0.
 template <bool PARTIAL>
 __device__ __forceinline__ void att_exp_chunk(uint32_t* v, float mscaled, int nvalid, uint32_t* pk, float& s0, float& s1, float& s2,
@@ -65,7 +90,7 @@ __device__ __forceinline__ void att_exp_tile(uint32_t* v, float mscaled, uint32_
                                              float& s3) {
   const float LOG2E = 1.4426950408889634f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(v[i]), LOG2E, -mscaled)));
+  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(att_ex2(fmaf(__uint_as_float(v[i]), LOG2E, -mscaled), i));
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t* e = v + c * 32;
@@ -79,7 +104,7 @@ __device__ __forceinline__ void att_exp_tile(uint32_t* v, float mscaled, uint32_
     for (int g = 0; g < 4; ++g) {
       if (c + 1 < 4) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) nx[g * 8 + i] = __float_as_uint(ex2_approx(__uint_as_float(nx[g * 8 + i])));
+        for (int i = 0; i < 8; ++i) nx[g * 8 + i] = __float_as_uint(att_ex2(__uint_as_float(nx[g * 8 + i]), g * 8 + i));
       }
       const uint32_t* q = e + g * 8;
       s0 += __uint_as_float(q[0]) + __uint_as_float(q[4]); s1 += __uint_as_float(q[1]) + __uint_as_float(q[5]);
@@ -90,13 +115,6 @@ __device__ __forceinline__ void att_exp_tile(uint32_t* v, float mscaled, uint32_
     tmem_st16(tmem_p_row + c * 16, pk);
   }
 }
-
-// Two CTAs share an SM and start together; their tile loops have the same period, so without help they stay in lockstep --
-// both in the exp phase (contending for MUFU), then both in the load / max / store phases (MUFU idle).  Every second CTA to
-// arrive on an SM in the first wave therefore delays its softmax warps by about half a tile period; equal periods keep the
-// offset, and the CTAs of later waves inherit it from the CTA whose slot they take over.
-__device__ unsigned int g_att_sm_ticket[1024];
-constexpr int ATT_STAGGER_CYCLES = 1100;
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ AttnArgs args) {
@@ -117,7 +135,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* pv_done = bars + 7;
   uint64_t* s_free = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  uint32_t* sm_ticket = tmem_slot + 1;  // arrival number of this CTA on its SM
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = args.tokens, D = args.D;
@@ -137,9 +154,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     mbar_init(pv_done, 1);
     mbar_init(s_free, n_live);
     fence_mbar_init();
-    unsigned int smid;
-    asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    *sm_ticket = args.stagger > 0 ? atomicAdd(&g_att_sm_ticket[smid & 1023u], 1u) : 0u;
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -208,12 +222,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const bool warp_live = q0 + quarter * 32 < T;  // warp-uniform: at least one of my 32 rows is a real query
     const float LOG2E = 1.4426950408889634f;
     float m_used = -INFINITY, l_sum = 0.f;  // m_used: the max P / O are currently scaled by
-    // only the CTAs of the first wave start together; later ones inherit the offset of the CTA whose slot they take over
-    const unsigned int linear_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    if (args.stagger > 0 && linear_cta < (unsigned)args.first_wave && (*sm_ticket & 1u)) {  // the second CTA of the pair on this SM
-      const long long t0 = clock64();
-      while (clock64() - t0 < args.stagger) { }
-    }
 #ifdef PRISMA_ATTN_PROFILE
     long long t_wait = 0, t_ld = 0, t_max = 0, t_exp = 0, t_st = 0, t_slow = 0, n_slow = 0, t_tot = clock64();
     const bool prof = args.dbg != nullptr && threadIdx.x == 64 && blockIdx.x == 1 && blockIdx.y == 1;
@@ -376,16 +384,6 @@ int attention_prepare(AttnLaunch* out, const __half* qkv, __half* o, int batch, 
   out->args.out = o;
   out->args.out_ld = D;
   out->args.dbg = nullptr;
-  {
-    static const int stagger = [] { const char* e = getenv("PRISMA_ATTN_STAGGER"); return e ? atoi(e) : ATT_STAGGER_CYCLES; }();
-    out->args.stagger = stagger;
-    static const int first_wave = [] {
-      int dev = 0, sms = 148;
-      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      return 2 * sms;  // two resident CTAs per SM
-    }();
-    out->args.first_wave = first_wave;
-  }
   PRISMA_TRY(make_tmap_2d_f16(&out->tm, qkv, (uint64_t)3 * D, (uint64_t)batch * tokens, (uint64_t)3 * D, 64, 128));
   out->grid = dim3(ceil_div(tokens, ATT_BQ), heads, batch);
   out->flops = 4.0 * batch * heads * (double)tokens * tokens * ATT_HD;

@@ -9,8 +9,6 @@ struct AttnArgs {
   __half* out;
   int out_ld;
   long long* dbg;  // optional cycle counters (debug builds of the harness only)
-  int stagger;     // cycles every second CTA on an SM delays its softmax warps (0 = off), see attention.cu
-  int first_wave;  // number of CTAs that start together (2 per SM)
 };
 struct AttnLaunch {
   CUtensorMap tm;
