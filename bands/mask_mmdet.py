@@ -8,7 +8,8 @@ optional <subpath>/%05d.png with the inverted mask for COLMAP) and the metadata.
 
 --sdf: the clamped signed distance field of the union (snowy.generate_sdf in the reference) is an exact Euclidean
 distance transform on the GPU (prisma_mask_sdf).
-Additions: --weights (the mmdet checkpoint .pth or .npz), --seeded-weights, --device.
+Additions: --weights (the mmdet checkpoint .pth or .npz), --seeded-weights, --device, --gpus / --device-list (frame sharding),
+--lanes (engines per GPU working on consecutive frames at once, prisma_b200/mask.py:SoloV2Lanes).
 """
 import argparse
 import os
@@ -47,8 +48,9 @@ def _load_state_dict(a):
 def init_model():
     """reference :38-41."""
     global model
-    from prisma_b200.mask import SoloV2Engine
-    model = SoloV2Engine(_load_state_dict(args), device=args.device)
+    from prisma_b200.mask import SoloV2Lanes
+    lanes = getattr(args, "lanes", 4) if is_video(getattr(args, "output", "") or "") else 1   # a still image needs one engine
+    model = SoloV2Lanes(_load_state_dict(args), device=args.device, lanes=lanes)
     return model
 
 
@@ -90,16 +92,19 @@ def process_video(a, ctx=None):
     if start > 0:
         reader.seek(start)
     if stop > start:
-        for k, frame in enumerate(reader):
+        def frames():  # this rank's frames, read lazily (the lanes keep a few of them in flight)
+            for k, frame in enumerate(reader):
+                yield frame
+                if start + k + 1 >= stop:
+                    return
+        for k, res in enumerate(model.map(frames(), confidence=a.confidence)):
             f = start + k
-            masks = frame_masks(frame, a.confidence)
+            masks = np.repeat(res["union"][..., None], 3, axis=-1)
             if sub:  # COLMAP wants black-on-white masks (:148-149)
                 write_rgb(os.path.join(sub, "{:05d}.png".format(f)), 255 - masks)
             if a.sdf:
                 masks = encode_sdf(masks)
             streams.write("mask", masks)
-            if f + 1 >= stop:
-                break
     streams.finish()
     if ctx.is_writer() and data is not None:
         data["bands"][BAND] = {"url": os.path.basename(a.output), "ids": CLASSES}
@@ -117,6 +122,7 @@ def build_parser():
     p.add_argument("--weights", type=str, default="", help="mmdet SOLOv2 checkpoint (.pth/.npz)")
     p.add_argument("--seeded-weights", action="store_true", help="seeded random weights (offline testing)")
     p.add_argument("--device", type=int, default=DEVICE)
+    p.add_argument("--lanes", type=int, default=4, help="engines per GPU that take consecutive frames concurrently (video)")
     p.add_argument("--gpus", type=int, default=1, help="shard the frames of a video over this many GPUs (one worker each)")
     p.add_argument("--device-list", type=str, default="", help="GPU ordinals of the workers (default 0..gpus-1)")
     return p

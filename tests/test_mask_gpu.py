@@ -1,6 +1,7 @@
 """mask_mmdet band: SOLOv2 CUDA path vs oracle/solo.py, stage by stage.
 
-The oracle restates the vendored-but-unimportable mmdet sources (mmcv absent: parity unpinned, see oracle/solo.py).
+The oracle restates the vendored mmdet sources and is pinned bit-equal to them (loaded by path with mmcv's primitives
+stubbed, see oracle/solo.py and tests/golden/solo_tiny_head.npz).
 "tiny" is a test-size twin of the same graph (one bottleneck per ResNet stage, test scale (448, 256)); "r101" is the
 real configuration.  Float stages: 1e-3-class tolerances (fp16 operands, fp32 accumulate, fp16 feature maps); the decode
 is integer / boolean work downstream of those floats, so it is compared as sets: same instances (label, score within
@@ -206,3 +207,22 @@ def test_sdf_green_channel_bit_exact():
     assert np.array_equal(sdf_green(m), osolo.sdf_green(m))
     for special in (np.zeros((64, 96), np.uint8), np.full((64, 96), 255, np.uint8)):
         assert np.array_equal(sdf_green(special), osolo.sdf_green(special))
+
+
+def test_solo_lanes_equal_sequential_calls():
+    """SoloV2Lanes.map (three engines taking consecutive frames from worker threads, the band's video loop) returns the same
+    unions / scores / labels, in frame order, as one engine called frame by frame."""
+    from prisma_b200.mask import SoloV2Engine, SoloV2Lanes
+    from prisma_b200.seeded_weights import make_solo_weights
+    from prisma_b200.synthetic import synthetic_frame
+    sd = make_solo_weights("tiny", 0)
+    frames = [synthetic_frame(240, 320, t) for t in range(7)]
+    one = SoloV2Engine(sd, variant="tiny")
+    ref = [one.infer(f, confidence=0.3) for f in frames]
+    one.close()
+    lanes = SoloV2Lanes(sd, variant="tiny", lanes=3)
+    got = list(lanes.map(iter(frames), confidence=0.3))
+    lanes.close()
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a["union"], b["union"]) and np.array_equal(a["scores"], b["scores"]) and np.array_equal(a["labels"], b["labels"])
