@@ -209,6 +209,7 @@ def test_sdf_green_channel_bit_exact():
         assert np.array_equal(sdf_green(special), osolo.sdf_green(special))
 
 
+@pytest.mark.gpu
 def test_solo_lanes_equal_sequential_calls():
     """SoloV2Lanes.map (three engines taking consecutive frames from worker threads, the band's video loop) returns the same
     unions / scores / labels, in frame order, as one engine called frame by frame."""
