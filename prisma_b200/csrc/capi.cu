@@ -256,9 +256,21 @@ int prisma_debug_gemm(int device, const float* A, const float* W, const float* b
     ep.out_f16 = dH;
     ep.out_f16_ld = N;
   }
-  if (act == -4) {  // TMA-store epilogue (dense fp32, scaled): the path of the RAFT correlation volume
+  if (act == -4) {  // TMA-store epilogue (dense fp32, scaled)
     ep.bias = nullptr;
     ep.alpha = 0.0625f;
+    ep.tma_store = true;
+  }
+  if (act == -5) {  // TMA-store epilogue, fp16 destination (scaled): the path of the RAFT correlation volume; N % 8 == 0
+    PRISMA_CHECK(N % 8 == 0, "debug gemm: the fp16 TMA-store path needs N % 8 == 0");
+    dH = sc.alloc<__half>((size_t)M * N);
+    PRISMA_CHECK(dH != nullptr, "cudaMalloc failed");
+    PRISMA_CUDA_OK(cudaMemset(dH, 0xFF, (size_t)M * N * 2));  // NaN pattern: every element must be written
+    ep.bias = nullptr;
+    ep.alpha = 0.0625f;
+    ep.out_f32 = nullptr;
+    ep.out_f16 = dH;
+    ep.out_f16_ld = N;
     ep.tma_store = true;
   }
   if (act == -3) {  // micro-benchmark of the residual-stream epilogue: D += acc in place (fp32 read + write)
@@ -270,6 +282,12 @@ int prisma_debug_gemm(int device, const float* A, const float* W, const float* b
   const int off[1] = {0};
   PRISMA_TRY(gemm_prepare(&g, dA, M, K, Kp, dW, Nw, M, N, 1, off, ep, sms, force_bn));
   PRISMA_TRY(timed(0, iters > 0 ? iters : 1, ms_out, [&]() { return gemm_run(g, 0); }));
+  if (act == -5) {
+    std::vector<__half> hd((size_t)M * N);
+    PRISMA_CUDA_OK(cudaMemcpy(hd.data(), dH, hd.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < hd.size(); ++i) Dout[i] = __half2float(hd[i]);
+    return 0;
+  }
   PRISMA_CUDA_OK(cudaMemcpy(Dout, dD, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
   return 0;
   API_GUARD_END

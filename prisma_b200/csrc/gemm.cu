@@ -76,6 +76,23 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t
   return 0;
 }
 
+// fp16 destination of the TMA-store epilogue: boxes of 32 rows x 64 columns (128-byte rows), 128-byte swizzle
+static int make_tmap_2d_f16_store(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems) {
+  EncodeTiledFn fn = get_encode_fn();
+  PRISMA_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  PRISMA_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  PRISMA_CHECK((pitch_elems * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {64, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PRISMA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp16 store) failed (code " + std::to_string((int)r) + ")");
+  return 0;
+}
+
 // Tile-N choice: minimise waves x per-tile time.  Per-tile costs are MEASURED on B200 (8192^3 sweep, relative units
 // per 64-wide K block): the 128x256 tile runs at 1351 TF/s, 128x128 at 919 TF/s (L2->SM operand traffic per MMA is
 // 1.5x higher), narrower tiles are smem-read bound; plus a per-tile constant for the drain / epilogue hand-off.
@@ -193,6 +210,7 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
       for (int split = 2; split <= 4; split *= 2) {
         const int bw = bn / split;
         if (bw < 32 * cg || rem * split > groups) continue;
+        if (ep.tma_store && ep.out_f16 && bw < 64) continue;  // the fp16 TMA-store epilogue writes 64-column boxes
         if (cost(bw) < best) { best = cost(bw); best_split = split; }
       }
       if (best_split > 1) {
@@ -216,11 +234,12 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   out->tma_store = false;
   out->tmD = out->tmA;
   if (ep.tma_store) {
-    PRISMA_CHECK(ep.out_f32 && !ep.out_f16 && !ep.out_f16_relu && !ep.bias && !ep.gamma && ep.act == 0 && !ep.res_f32 && !ep.res_a &&
-                     !ep.res_b && ep.row_map == ROW_LINEAR && !ep.head_w && !ep.stat_part,
-                 "gemm: the TMA-store epilogue handles a scaled dense fp32 output only");
+    PRISMA_CHECK((ep.out_f32 != nullptr) != (ep.out_f16 != nullptr) && !ep.out_f16_relu && !ep.bias && !ep.gamma && ep.act == 0 &&
+                     !ep.res_f32 && !ep.res_a && !ep.res_b && ep.row_map == ROW_LINEAR && !ep.head_w && !ep.stat_part,
+                 "gemm: the TMA-store epilogue handles one scaled dense output (fp32 or fp16) only");
     PRISMA_CHECK(bn >= 128, "gemm: the TMA-store epilogue is built for BLOCK_N 128 / 256");
-    PRISMA_TRY(make_tmap_2d_f32(&out->tmD, ep.out_f32, (uint64_t)N, (uint64_t)M, (uint64_t)ep.out_f32_ld, 32, 32));
+    if (ep.out_f16) PRISMA_TRY(make_tmap_2d_f16_store(&out->tmD, ep.out_f16, (uint64_t)N, (uint64_t)M, (uint64_t)ep.out_f16_ld));
+    else PRISMA_TRY(make_tmap_2d_f32(&out->tmD, ep.out_f32, (uint64_t)N, (uint64_t)M, (uint64_t)ep.out_f32_ld, 32, 32));
     out->tma_store = true;
   }
   return 0;

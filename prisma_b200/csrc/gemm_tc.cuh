@@ -86,7 +86,7 @@ struct GemmEpilogue {
   // Row count known only on the device (SOLOv2: the number of candidates of this frame): when set, only the first
   // round_up(*m_dev, 128) rows of the output space are computed (the launch is sized for the capacity M).
   const int* m_dev = nullptr;
-  // dense fp32 output (row_map LINEAR, scale only) stored by TMA: tcgen05.ld -> swizzled smem box -> cp.async.bulk.tensor
+  // dense output (row_map LINEAR, scale only; out_f32 or out_f16) stored by TMA: tcgen05.ld -> swizzled smem box -> cp.async.bulk.tensor
   bool tma_store = false;
   // ConvGRU gate arithmetic in the epilogue of the gate convs (raft/update.py:54-58), all fp32, indexed by dst row:
   //  gru == 1 (the z | r conv, N = 256, act sigmoid): columns [0,128) = z -> out_f32 as usual; columns [128,256) = r are not
@@ -645,6 +645,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+      if (TMAST && ep.out_f16 != nullptr) {
+        // fp16 destination: a warp takes 64-column blocks (two TMEM chunks) so that every bulk store still moves a
+        // 32 x 128-byte box, the same staging layout and swizzle as the fp32 path
+#pragma unroll 1
+        for (int cb = chunk_par * 64; cb < bw; cb += 128) {
+          if (n0 + cb >= args.N || args.dbg_mode >= 2) break;  // warp-uniform
+          const uint32_t buf = stg + (st_cnt & 1) * 4096;
+          if (st_cnt >= 2) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int c0 = cb + hf * 32;
+            if (c0 < bw && n0 + c0 < args.N) {  // warp-uniform; a missing right half lies beyond N and is clipped by the store
+              uint32_t r[32];
+              tmem_ld32(taddr + c0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t h0 = pack_half2(__uint_as_float(r[8 * j]) * ep.alpha, __uint_as_float(r[8 * j + 1]) * ep.alpha);
+                const uint32_t h1 = pack_half2(__uint_as_float(r[8 * j + 2]) * ep.alpha, __uint_as_float(r[8 * j + 3]) * ep.alpha);
+                const uint32_t h2 = pack_half2(__uint_as_float(r[8 * j + 4]) * ep.alpha, __uint_as_float(r[8 * j + 5]) * ep.alpha);
+                const uint32_t h3 = pack_half2(__uint_as_float(r[8 * j + 6]) * ep.alpha, __uint_as_float(r[8 * j + 7]) * ep.alpha);
+                sts128(buf + lane * 128 + (((hf * 4 + j) ^ (lane & 7)) << 4), __uint_as_float(h0), __uint_as_float(h1),
+                       __uint_as_float(h2), __uint_as_float(h3));
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmD)),
+                         "r"(buf), "r"(n0 + cb), "r"(m0 + quarter * 32)
+                         : "memory");
+            tma_store_commit();
+          }
+          ++st_cnt;
+        }
+      } else
 #pragma unroll 1
       for (int c0 = chunk_par * 32; c0 < bw; c0 += 64) {
         if (n0 + c0 >= args.N || args.dbg_mode >= 2) break;  // warp-uniform
@@ -674,7 +712,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Host-side prepared launch: tensor maps encoded once, replayed every frame (also inside CUDA graphs).
 struct GemmLaunch {
   CUtensorMap tmA, tmB, tmBt;  // tmBt: W with the narrow box of the tail tiles (== tmB when there is no tail)
-  CUtensorMap tmD;             // fp32 output, 32 x 32 boxes (TMA-store epilogue only)
+  CUtensorMap tmD;             // dense output, 32 x 32 boxes (TMA-store epilogue only)
   bool tma_store = false;
   bool xacc = false;           // external fp32 accumulation (tf32x3 only): see GemmArgs::acc_group
   bool tf32 = false;           // kind::tf32 operands (fp32 containers): the 3xTF32 "fp32-class" path of the mask band

@@ -82,6 +82,26 @@ def test_gemm_tma_store_epilogue(M, N, K, bn):
     assert np.isfinite(got).all()
 
 
+@pytest.mark.parametrize("M,N,K,bn", [
+    (18360, 18360, 256, 0),   # RAFT correlation level 0 at 1080p x 0.75: CTA pairs, ragged M and N (N % 32 = 24)
+    (18360, 4592, 512, 0),    # level 1 (hi/lo pooled features: K = 512), N % 32 = 16
+    (1000, 264, 256, 128),    # level 3 size class, single CTAs, 128-wide tiles
+    (300, 520, 64, 256),      # single CTAs, 256-wide, rows of the last tile out of range
+])
+def test_gemm_tma_store_epilogue_fp16(M, N, K, bn):
+    """The same epilogue with an fp16 destination (32 x 64-byte boxes, 64-byte swizzle): fp32 accumulate, scaled by 1/16,
+    rounded once; every element of [M][N] written (the buffer starts as NaN), boxes clipped at the ragged edges."""
+    rng = np.random.default_rng(M + N + K + 1)
+    A = rng.standard_normal((M, K), dtype=np.float32)
+    W = rng.standard_normal((N, K), dtype=np.float32)
+    got = _gemm(A, W, None, -5, bn)
+    assert np.isfinite(got).all()
+    rows = np.unique(np.concatenate([np.arange(0, min(M, 300)), np.arange(max(0, M - 300), M), rng.integers(0, M, 200)]))
+    ref = (torch.from_numpy(_h(A[rows])) @ torch.from_numpy(_h(W)).T).numpy() * 0.0625
+    err = np.abs(got[rows] - ref).max()
+    assert err <= 6e-4 * max(1.0, np.abs(ref).max()), f"max abs err {err}"   # one fp16 rounding: 2^-11 relative
+
+
 @pytest.mark.parametrize("H,W,Cin,Cout,k,relu", [
     (37, 66, 64, 64, 3, 1),
     (19, 33, 384, 64, 3, 0),
