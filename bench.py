@@ -181,7 +181,7 @@ def corr_build_block(device, peaks):
     l.prisma_engine_destroy(h)
     gbs = work[1] / (ms.value * 1e-3) / 1e9
     tr = (measured_traffic()[1] or {}).get("corr_level0", {})
-    return {"bound": "hbm", "kernel": "gemm_tc_kernel (RAFT all-pairs correlation pyramid: 8 GEMMs per build, K = 256, fp32 output)",
+    return {"bound": "hbm", "kernel": "gemm_tc_kernel (RAFT all-pairs correlation pyramid: 2 GEMMs per direction (level 0; levels 1-3 side by side), K = 256 / 512, fp32 output)",
             "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"], "ms_per_build": ms.value,
             "algorithmic_bytes": work[1], "traffic": tr.get("traffic_bytes_per_launch"), "traffic_detail": tr or None,
             "peak_source": peaks["src"],
@@ -250,9 +250,9 @@ def depth_720p_extras(eng):
 
 def raft_extra_kernels(pairs):
     """Kernels launched by one RAFT video pass of `pairs` frame pairs beyond its step count: raft_preprocess = 2 kernels per
-    new frame (1 step), corr_pool = 3 per new frame (1 step), corr_build = 4 GEMMs per direction (1 step), flow_encode = 3
-    per direction (1 step); reuse_prev is device-to-device copies, not a kernel."""
-    return (2 * pairs - 1) + (3 * pairs - 1) + (8 * pairs - 1) + (6 * pairs - 1) - 1
+    new frame (1 step), corr_pool = 1 for all new frames (1 step), corr_build = 2 GEMMs per direction (level 0; levels 1-3
+    side by side) (1 step), flow_encode = 3 per direction (1 step); reuse_prev is device-to-device copies, not a kernel."""
+    return (2 * pairs - 1) + 0 + (4 * pairs - 1) + (6 * pairs - 1) - 1
 
 
 def run_b200(args, rank, local_rank, world):

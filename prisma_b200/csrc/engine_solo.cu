@@ -49,7 +49,10 @@ int SoloEngine::init(const std::string& vin, int dev) {
   std::string v = vin;
   exact_head = true;  // "<variant>-fast": the single-pass fp16 head of round 1 (not mask-id faithful, ~40 % faster per frame)
   if (v.size() > 5 && v.substr(v.size() - 5) == "-fast") { exact_head = false; v = v.substr(0, v.size() - 5); }
+  if (v.size() > 6 && v.substr(v.size() - 6) == "-exact") { exact_backbone = true; v = v.substr(0, v.size() - 6); }
   if (const char* e = getenv("PRISMA_SOLO_HEAD")) exact_head = std::string(e) != "fast";
+  if (const char* e = getenv("PRISMA_SOLO_BACKBONE")) exact_backbone = std::string(e) == "exact";
+  if (!exact_head) exact_backbone = false;  // the fp32-class backbone feeds the fp32-class head
   variant = v;
   if (v == "r101") { const int l[4] = {3, 4, 23, 3}; std::copy(l, l + 4, layers); scale_long = 1333; scale_short = 800; }
   else if (v == "tiny") { const int l[4] = {1, 1, 1, 1}; std::copy(l, l + 4, layers); scale_long = 448; scale_short = 256; }
@@ -136,26 +139,39 @@ int SoloEngine::up_conv(const std::string& name, const std::string& bn, const st
 // head conv weight [Cout][Cin][k][k] -> fp32 [round_up(Cout,256)][k*k * 3 * cin32], per tap [W_hi | W_hi | W_lo] with
 // W_hi = the weight with its low 13 mantissa bits cleared (a TF32 number), W_lo = W - W_hi: the B operand of
 // gemm_prepare_tf32x3.  GroupNorm affine kept separately, bias fp32.
-int SoloEngine::up_conv3(const std::string& name, const std::string& gn, int Cout, int Cin, int k, bool bias, SoloConvW3* out) {
+// bn (backbone convs): eval BatchNorm folded in fp32 -- weight * gamma / sqrt(var + eps), bias (0 - mean) * that + beta.
+int SoloEngine::up_conv3(const std::string& name, const std::string& gn, int Cout, int Cin, int k, bool bias, SoloConvW3* out,
+                         const std::string& bn) {
   const HostTensor* w = get(name + ".weight");
   if (!w) return -1;
   PRISMA_CHECK((long long)w->data.size() == (long long)Cout * Cin * k * k, "SOLOv2 weight '" + name + "' has an unexpected size");
   const int taps = k * k, c32 = round_up(Cin, 32), K = taps * 3 * c32, rows = round_up(Cout, 256);
   std::vector<float> h((size_t)rows * K, 0.f);
   auto hi_of = [](float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; };
+  std::vector<float> sc(Cout, 1.f), sh(Cout, 0.f);
+  if (!bn.empty()) {
+    const HostTensor *g = get(bn + ".weight"), *be = get(bn + ".bias"), *mu = get(bn + ".running_mean"), *var = get(bn + ".running_var");
+    if (!g || !be || !mu || !var) return -1;
+    for (int n = 0; n < Cout; ++n) {
+      sc[n] = g->data[n] / sqrtf(var->data[n] + 1e-5f);
+      sh[n] = (0.f - mu->data[n]) * sc[n] + be->data[n];
+    }
+  }
   for (int n = 0; n < Cout; ++n)
     for (int t = 0; t < taps; ++t)
       for (int c = 0; c < Cin; ++c) {
-        const float v = w->data[((size_t)n * Cin + c) * taps + t], hi = hi_of(v);
+        const float v = w->data[((size_t)n * Cin + c) * taps + t] * sc[n], hi = hi_of(v);
         float* base = h.data() + (size_t)n * K + (size_t)t * 3 * c32;
         base[c] = hi; base[c32 + c] = hi; base[2 * c32 + c] = v - hi;
       }
   PRISMA_TRY(s_alloc(allocs, &out->w, h.size()));
   PRISMA_CUDA_OK(cudaMemcpy(out->w, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
   std::vector<float> bv(round_up(Cout, 8), 0.f);
+  for (int n = 0; n < Cout; ++n) bv[n] = sh[n];
   if (bias) {
     const HostTensor* b = get(name + ".bias");
     if (!b) return -1;
+    PRISMA_CHECK(bn.empty(), "up_conv3: bias and BatchNorm together are not used by this model");
     for (int n = 0; n < Cout; ++n) bv[n] = b->data[n];
   }
   PRISMA_TRY(s_alloc(allocs, &out->b, bv.size()));
@@ -241,6 +257,27 @@ int SoloEngine::finalize() {
     PRISMA_TRY(up_conv3("mask_head.conv_cls", "", SOLO_NC, 512, 3, true, &conv_cls3));
     PRISMA_TRY(up_conv3("mask_head.conv_kernel", "", 256, 512, 3, true, &conv_kernel3));
   }
+  if (exact_backbone) {  // ResNet + FPN in [hi | hi | lo] fp32, BatchNorm folded in fp32
+    PRISMA_TRY(up_conv3("backbone.conv1_flat", "", 64, 168, 1, false, &stem3, "backbone.bn1"));
+    int inp = 64;
+    for (int li = 0; li < 4; ++li) {
+      blocks3[li].resize(layers[li]);
+      for (int b = 0; b < layers[li]; ++b) {
+        const std::string p = "backbone.layer" + std::to_string(li + 1) + "." + std::to_string(b) + ".";
+        Block3& k = blocks3[li][b];
+        const int pl = planes_of[li];
+        PRISMA_TRY(up_conv3(p + "conv1", "", pl, inp, 1, false, &k.c1, p + "bn1"));
+        PRISMA_TRY(up_conv3(p + "conv2", "", pl, pl, 3, false, &k.c2, p + "bn2"));
+        PRISMA_TRY(up_conv3(p + "conv3", "", pl * 4, pl, 1, false, &k.c3, p + "bn3"));
+        if (b == 0) PRISMA_TRY(up_conv3(p + "downsample.0", "", pl * 4, inp, 1, false, &k.ds, p + "downsample.1"));
+        inp = pl * 4;
+      }
+    }
+    for (int i = 0; i < 4; ++i) {
+      PRISMA_TRY(up_conv3("neck.lateral_convs." + std::to_string(i) + ".conv", "", 256, cins[i], 1, true, &lateral3[i]));
+      PRISMA_TRY(up_conv3("neck.fpn_convs." + std::to_string(i) + ".conv", "", 256, 256, 3, true, &fpnc3[i]));
+    }
+  }
   host.clear();
   finalized = true;
   return 0;
@@ -324,69 +361,168 @@ int SoloEngine::build_plan(int H, int W) {
     push_step([=](cudaStream_t s) { return solo_preprocess(img, H, W, nh_, nw_, hp_, wp_, net, rs, s); });
   }
   cur_tag = "backbone";
-  // ---- ResNet stem: 7x7/2 conv + BN + ReLU (im2col GEMM), 3x3/2 max-pool
-  SMap s1, x;
-  PRISMA_TRY(new_map(&s1, hp / 2, wp / 2, 64));
-  {
-    __half* cols = nullptr;
-    PRISMA_TRY(s_alloc(plan_allocs, &cols, (size_t)(hp / 2) * (wp / 2) * 192));
-    const float* net = d_net; const int hp_ = hp, wp_ = wp;
-    push_step([=](cudaStream_t s) { return raft_im2col_stem(net, 1, hp_, wp_, cols, s); });
-    GemmEpilogue ep; ep.bias = stem.b; ep.act = 2; ep.out_f16 = s1.p; ep.out_f16_ld = 64;
-    ep.row_map = ROW_TOK2PAD; ep.in_w = wp / 2; ep.in_h = hp / 2; ep.out_wp = s1.Wp(); ep.out_img_rows = (int)s1.rows(); ep.out_pad = 1;
-    GemmLaunch g;
-    const int M = (hp / 2) * (wp / 2);
-    PRISMA_TRY(gemm_prepare(&g, cols, M, 192, 192, stem.w, 256, M, 64, 1, zero_off, ep, num_sms));
-    flops += 2.0 * M * 147.0 * 64;
-    push_step([g](cudaStream_t s) { return gemm_run(g, s); });
-  }
-  PRISMA_TRY(new_map(&x, hp / 4, wp / 4, 64));
-  { const SMap a = s1, o = x; push_step([=](cudaStream_t s) { return maxpool3s2_f16(a.p, a.H, a.W, 64, o.p, o.H, o.W, s); }); }
-  // ---- bottlenecks (resnet.py:255-300): 1x1 -> 3x3 (stride) -> 1x1, + identity / downsample, ReLU
-  SMap C[4];
-  for (int li = 0; li < 4; ++li) {
-    for (size_t b = 0; b < blocks[li].size(); ++b) {
-      const Block& k = blocks[li][b];
-      const int ho = x.H / k.stride, wo = x.W / k.stride;
-      SMap a, m2, o, idn = x;
-      PRISMA_TRY(new_map(&a, x.H, x.W, k.c1.cout));
-      PRISMA_TRY(new_map(&m2, ho, wo, k.c2.cout));
-      PRISMA_TRY(new_map(&o, ho, wo, k.c3.cout));
-      { GemmEpilogue ep; ep.bias = k.c1.b; ep.act = 2; ep.out_f16 = a.p; ep.out_f16_ld = a.C;
-        PRISMA_TRY(conv(x, x.C, k.c1, 1, ep, &a, nullptr)); }
-      { GemmEpilogue ep; ep.bias = k.c2.b; ep.act = 2; ep.out_f16 = m2.p; ep.out_f16_ld = m2.C;
-        PRISMA_TRY(conv(a, a.C, k.c2, k.stride, ep, &m2, nullptr)); }
-      if (k.has_ds) {
-        PRISMA_TRY(new_map(&idn, ho, wo, k.ds.cout));
-        GemmEpilogue ep; ep.bias = k.ds.b; ep.out_f16 = idn.p; ep.out_f16_ld = idn.C;
-        PRISMA_TRY(conv(x, x.C, k.ds, k.stride, ep, &idn, nullptr));
+  SMap P[5];
+  float* P_dense[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // exact backbone: FPN levels as dense fp32 [H*W][256]
+  if (exact_backbone) {
+    // ================================================================ fp32-class ResNet + FPN ("-exact" variants)
+    // conv = 3xTF32 GEMM (external fp32 accumulation) from a split map to a dense fp32 [Ho*Wo][Cout] map; bias (folded
+    // BatchNorm), the residual sum (pre_f32) and ReLU in the epilogue; solo_dense_to_split builds the next conv's operand.
+    auto new_xm = [&](XMap* mm, int h, int w, int c) -> int {
+      mm->H = h; mm->W = w; mm->C = c;
+      return s_alloc(plan_allocs, &mm->p, (size_t)mm->rows() * 2 * c);
+    };
+    auto conv_b = [&](const XMap& in, const SoloConvW3& w, int sub, GemmEpilogue ep, float* dst_dense) -> int {
+      PRISMA_CHECK(in.C == w.cin32, "solo(exact backbone): operand channels do not match the packed weights");
+      int off[9], taps_n = w.k * w.k;
+      if (w.k == 3) { for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky - 1) * in.Wp() + (kx - 1); }
+      else off[0] = 0;
+      ep.in_w = in.Wp(); ep.in_h = in.Hp(); ep.img_rows = 0; ep.sub = sub; ep.pad = 1;
+      ep.row_map = ROW_PAD2TOK; ep.out_f32 = dst_dense; ep.out_f32_ld = w.cout; ep.bias = w.b;
+      GemmLaunch g;
+      PRISMA_TRY(gemm_prepare_tf32x3(&g, in.p, in.rows(), in.C, in.C, w.w, round_up(w.cout, 256), (int)in.rows(), w.cout, taps_n, off,
+                                     ep, num_sms));
+      flops += 2.0 * ceil_div(in.H, sub) * (double)ceil_div(in.W, sub) * taps_n * w.cin * w.cout;
+      push_step([g](cudaStream_t s) { return gemm_run(g, s); });
+      return 0;
+    };
+    auto to_split = [&](const float* dense, const XMap& o) {
+      push_step([=](cudaStream_t s) { return solo_dense_to_split(dense, o.H, o.W, o.C, o.p, o.C, s); });
+    };
+    // stem: im2col split -> GEMM (+ folded BN, ReLU) -> dense [H/2 * W/2][64] -> max-pool -> dense + split
+    const int h2 = hp / 2, w2 = wp / 2, h4 = hp / 4, w4 = wp / 4;
+    float *cols = nullptr, *s1d = nullptr, *xd = nullptr;
+    PRISMA_TRY(s_alloc(plan_allocs, &cols, (size_t)h2 * w2 * 384));
+    PRISMA_TRY(s_alloc(plan_allocs, &s1d, (size_t)h2 * w2 * 64));
+    PRISMA_TRY(s_alloc(plan_allocs, &xd, (size_t)h4 * w4 * 64));
+    { const float* net = d_net; const int hp_ = hp, wp_ = wp;
+      push_step([=](cudaStream_t s) { return solo_im2col_stem_split(net, hp_, wp_, cols, s); }); }
+    { GemmEpilogue ep; ep.bias = stem3.b; ep.act = 2; ep.out_f32 = s1d; ep.out_f32_ld = 64;
+      GemmLaunch g;
+      const int M = h2 * w2;
+      PRISMA_TRY(gemm_prepare_tf32x3(&g, cols, M, 192, 192, stem3.w, 256, M, 64, 1, zero_off, ep, num_sms));
+      flops += 2.0 * M * 147.0 * 64;
+      push_step([g](cudaStream_t s) { return gemm_run(g, s); }); }
+    XMap xs;
+    PRISMA_TRY(new_xm(&xs, h4, w4, 64));
+    { const XMap o = xs; push_step([=](cudaStream_t s) { return maxpool3s2_dense(s1d, h2, w2, 64, xd, o.p, o.H, o.W, s); }); }
+    // bottlenecks (resnet.py:255-300)
+    XMap CX[4];
+    for (int li = 0; li < 4; ++li) {
+      for (size_t b = 0; b < blocks3[li].size(); ++b) {
+        const Block3& k = blocks3[li][b];
+        const int stride = blocks[li][b].stride;
+        const int ho = xs.H / stride, wo = xs.W / stride;
+        XMap as, ms, os;
+        float *ad = nullptr, *md = nullptr, *od = nullptr, *idn = xd;
+        PRISMA_TRY(new_xm(&as, xs.H, xs.W, k.c1.cout));
+        PRISMA_TRY(new_xm(&ms, ho, wo, k.c2.cout));
+        PRISMA_TRY(new_xm(&os, ho, wo, k.c3.cout));
+        PRISMA_TRY(s_alloc(plan_allocs, &ad, (size_t)xs.H * xs.W * k.c1.cout));
+        PRISMA_TRY(s_alloc(plan_allocs, &md, (size_t)ho * wo * k.c2.cout));
+        PRISMA_TRY(s_alloc(plan_allocs, &od, (size_t)ho * wo * k.c3.cout));
+        { GemmEpilogue ep; ep.act = 2; PRISMA_TRY(conv_b(xs, k.c1, 1, ep, ad)); }
+        to_split(ad, as);
+        { GemmEpilogue ep; ep.act = 2; PRISMA_TRY(conv_b(as, k.c2, stride, ep, md)); }
+        to_split(md, ms);
+        if (b == 0) {
+          PRISMA_TRY(s_alloc(plan_allocs, &idn, (size_t)ho * wo * k.ds.cout));
+          GemmEpilogue ep; PRISMA_TRY(conv_b(xs, k.ds, stride, ep, idn));
+        }
+        { GemmEpilogue ep; ep.act = 2; ep.pre_f32 = idn; ep.pre_f32_ld = k.c3.cout; PRISMA_TRY(conv_b(ms, k.c3, 1, ep, od)); }
+        to_split(od, os);
+        xs = os; xd = od;
       }
-      { GemmEpilogue ep; ep.bias = k.c3.b; ep.res_a = idn.p; ep.res_a_ld = idn.C; ep.out_f16_relu = o.p; ep.out_f16_relu_ld = o.C;
-        PRISMA_TRY(conv(m2, m2.C, k.c3, 1, ep, &o, nullptr)); }
-      x = o;
+      CX[li] = xs;
     }
-    C[li] = x;
+    cur_tag = "fpn";
+    float* Ld[4];
+    XMap LX[4];
+    for (int i = 0; i < 4; ++i) {
+      PRISMA_TRY(s_alloc(plan_allocs, &Ld[i], (size_t)CX[i].H * CX[i].W * 256));
+      GemmEpilogue ep; PRISMA_TRY(conv_b(CX[i], lateral3[i], 1, ep, Ld[i]));
+    }
+    for (int i = 3; i > 0; --i) {
+      float* f = Ld[i - 1]; const float* c = Ld[i];
+      const int hf = CX[i - 1].H, wf = CX[i - 1].W, hc = CX[i].H, wc = CX[i].W;
+      push_step([=](cudaStream_t s) { return nearest_add_dense(f, hf, wf, c, hc, wc, 256, s); });
+    }
+    for (int i = 0; i < 4; ++i) {
+      PRISMA_TRY(new_xm(&LX[i], CX[i].H, CX[i].W, 256));
+      to_split(Ld[i], LX[i]);
+      P[i].H = CX[i].H; P[i].W = CX[i].W; P[i].C = 256; P[i].p = nullptr;
+      PRISMA_TRY(s_alloc(plan_allocs, &P_dense[i], (size_t)P[i].H * P[i].W * 256));
+      GemmEpilogue ep; PRISMA_TRY(conv_b(LX[i], fpnc3[i], 1, ep, P_dense[i]));
+    }
+    P[4].H = (P[3].H - 1) / 2 + 1; P[4].W = (P[3].W - 1) / 2 + 1; P[4].C = 256; P[4].p = nullptr;
+    PRISMA_TRY(s_alloc(plan_allocs, &P_dense[4], (size_t)P[4].H * P[4].W * 256));
+    { const float* a = P_dense[3]; float* o = P_dense[4]; const int h3 = P[3].H, w3 = P[3].W, h4_ = P[4].H, w4_ = P[4].W;
+      push_step([=](cudaStream_t s) { return subsample2_dense(a, h3, w3, 256, o, h4_, w4_, s); }); }
+    for (int i = 0; i < 5; ++i) taps["fpn" + std::to_string(i)] = {P_dense[i], 0, P[i].H * P[i].W, 256, 0};
+  } else {
+    // ---- ResNet stem: 7x7/2 conv + BN + ReLU (im2col GEMM), 3x3/2 max-pool
+    SMap s1, x;
+    PRISMA_TRY(new_map(&s1, hp / 2, wp / 2, 64));
+    {
+      __half* cols = nullptr;
+      PRISMA_TRY(s_alloc(plan_allocs, &cols, (size_t)(hp / 2) * (wp / 2) * 192));
+      const float* net = d_net; const int hp_ = hp, wp_ = wp;
+      push_step([=](cudaStream_t s) { return raft_im2col_stem(net, 1, hp_, wp_, cols, s); });
+      GemmEpilogue ep; ep.bias = stem.b; ep.act = 2; ep.out_f16 = s1.p; ep.out_f16_ld = 64;
+      ep.row_map = ROW_TOK2PAD; ep.in_w = wp / 2; ep.in_h = hp / 2; ep.out_wp = s1.Wp(); ep.out_img_rows = (int)s1.rows(); ep.out_pad = 1;
+      GemmLaunch g;
+      const int M = (hp / 2) * (wp / 2);
+      PRISMA_TRY(gemm_prepare(&g, cols, M, 192, 192, stem.w, 256, M, 64, 1, zero_off, ep, num_sms));
+      flops += 2.0 * M * 147.0 * 64;
+      push_step([g](cudaStream_t s) { return gemm_run(g, s); });
+    }
+    PRISMA_TRY(new_map(&x, hp / 4, wp / 4, 64));
+    { const SMap a = s1, o = x; push_step([=](cudaStream_t s) { return maxpool3s2_f16(a.p, a.H, a.W, 64, o.p, o.H, o.W, s); }); }
+    // ---- bottlenecks (resnet.py:255-300): 1x1 -> 3x3 (stride) -> 1x1, + identity / downsample, ReLU
+    SMap C[4];
+    for (int li = 0; li < 4; ++li) {
+      for (size_t b = 0; b < blocks[li].size(); ++b) {
+        const Block& k = blocks[li][b];
+        const int ho = x.H / k.stride, wo = x.W / k.stride;
+        SMap a, m2, o, idn = x;
+        PRISMA_TRY(new_map(&a, x.H, x.W, k.c1.cout));
+        PRISMA_TRY(new_map(&m2, ho, wo, k.c2.cout));
+        PRISMA_TRY(new_map(&o, ho, wo, k.c3.cout));
+        { GemmEpilogue ep; ep.bias = k.c1.b; ep.act = 2; ep.out_f16 = a.p; ep.out_f16_ld = a.C;
+          PRISMA_TRY(conv(x, x.C, k.c1, 1, ep, &a, nullptr)); }
+        { GemmEpilogue ep; ep.bias = k.c2.b; ep.act = 2; ep.out_f16 = m2.p; ep.out_f16_ld = m2.C;
+          PRISMA_TRY(conv(a, a.C, k.c2, k.stride, ep, &m2, nullptr)); }
+        if (k.has_ds) {
+          PRISMA_TRY(new_map(&idn, ho, wo, k.ds.cout));
+          GemmEpilogue ep; ep.bias = k.ds.b; ep.out_f16 = idn.p; ep.out_f16_ld = idn.C;
+          PRISMA_TRY(conv(x, x.C, k.ds, k.stride, ep, &idn, nullptr));
+        }
+        { GemmEpilogue ep; ep.bias = k.c3.b; ep.res_a = idn.p; ep.res_a_ld = idn.C; ep.out_f16_relu = o.p; ep.out_f16_relu_ld = o.C;
+          PRISMA_TRY(conv(m2, m2.C, k.c3, 1, ep, &o, nullptr)); }
+        x = o;
+      }
+      C[li] = x;
+    }
+    cur_tag = "fpn";
+    // ---- FPN
+    SMap L[4];
+    for (int i = 0; i < 4; ++i) {
+      PRISMA_TRY(new_map(&L[i], C[i].H, C[i].W, 256));
+      GemmEpilogue ep; ep.bias = lateral[i].b; ep.out_f16 = L[i].p; ep.out_f16_ld = 256;
+      PRISMA_TRY(conv(C[i], C[i].C, lateral[i], 1, ep, &L[i], nullptr));
+    }
+    for (int i = 3; i > 0; --i) {
+      const SMap f = L[i - 1], c = L[i];
+      push_step([=](cudaStream_t s) { return nearest_add_f16(f.p, f.H, f.W, c.p, c.H, c.W, 256, s); });
+    }
+    for (int i = 0; i < 4; ++i) {
+      PRISMA_TRY(new_map(&P[i], L[i].H, L[i].W, 256));
+      GemmEpilogue ep; ep.bias = fpnc[i].b; ep.out_f16 = P[i].p; ep.out_f16_ld = 256;
+      PRISMA_TRY(conv(L[i], 256, fpnc[i], 1, ep, &P[i], nullptr));
+    }
+    PRISMA_TRY(new_map(&P[4], (P[3].H - 1) / 2 + 1, (P[3].W - 1) / 2 + 1, 256));
+    { const SMap a = P[3], o = P[4]; push_step([=](cudaStream_t s) { return subsample2_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, s); }); }
+    for (int i = 0; i < 5; ++i) taps["fpn" + std::to_string(i)] = {P[i].p, 1, P[i].H, P[i].W, 256};
   }
-  cur_tag = "fpn";
-  // ---- FPN
-  SMap L[4], P[5];
-  for (int i = 0; i < 4; ++i) {
-    PRISMA_TRY(new_map(&L[i], C[i].H, C[i].W, 256));
-    GemmEpilogue ep; ep.bias = lateral[i].b; ep.out_f16 = L[i].p; ep.out_f16_ld = 256;
-    PRISMA_TRY(conv(C[i], C[i].C, lateral[i], 1, ep, &L[i], nullptr));
-  }
-  for (int i = 3; i > 0; --i) {
-    const SMap f = L[i - 1], c = L[i];
-    push_step([=](cudaStream_t s) { return nearest_add_f16(f.p, f.H, f.W, c.p, c.H, c.W, 256, s); });
-  }
-  for (int i = 0; i < 4; ++i) {
-    PRISMA_TRY(new_map(&P[i], L[i].H, L[i].W, 256));
-    GemmEpilogue ep; ep.bias = fpnc[i].b; ep.out_f16 = P[i].p; ep.out_f16_ld = 256;
-    PRISMA_TRY(conv(L[i], 256, fpnc[i], 1, ep, &P[i], nullptr));
-  }
-  PRISMA_TRY(new_map(&P[4], (P[3].H - 1) / 2 + 1, (P[3].W - 1) / 2 + 1, 256));
-  { const SMap a = P[3], o = P[4]; push_step([=](cudaStream_t s) { return subsample2_f16(a.p, a.H, a.W, 256, o.p, o.H, o.W, s); }); }
-  for (int i = 0; i < 5; ++i) taps["fpn" + std::to_string(i)] = {P[i].p, 1, P[i].H, P[i].W, 256};
 
   head_step0 = steps.size();
   fh = P[0].H; fw = P[0].W;
@@ -522,8 +658,10 @@ int SoloEngine::build_plan(int H, int W) {
     PRISMA_TRY(s_alloc(plan_allocs, &d_feat_in[i], (size_t)P[i].H * P[i].W * 256));
     feat_h[i] = P[i].H; feat_w[i] = P[i].W;
     const SMap a = P[i]; const XMap o = PX[i]; const float* inj = d_feat_in[i]; const bool* flag = &inject;
+    const float* dense = P_dense[i];  // exact backbone: the level is already fp32
     push_step([=](cudaStream_t s) {
-      return *flag ? solo_dense_to_split(inj, a.H, a.W, 256, o.p, 256, s) : solo_f16map_to_split(a.p, a.H, a.W, 256, o.p, 256, s);
+      if (*flag) return solo_dense_to_split(inj, a.H, a.W, 256, o.p, 256, s);
+      return dense ? solo_dense_to_split(dense, a.H, a.W, 256, o.p, 256, s) : solo_f16map_to_split(a.p, a.H, a.W, 256, o.p, 256, s);
     });
   }
   XMap accx;

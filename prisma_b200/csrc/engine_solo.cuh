@@ -34,6 +34,7 @@ class SoloEngine {
   int infer_from_feats(int H, int W, int img_h, int img_w, float confidence, uint8_t* union_out, int* n_out, float* scores_out,
                        int* labels_out, uint8_t* inst_masks_out);
   bool exact_head = true;   // fp32-class head + decode (3xTF32 contractions, fp32 activations): the default of the band
+  bool exact_backbone = false;  // "<variant>-exact": ResNet + FPN in the same fp32-class arithmetic (3 tensor-core passes per conv)
   long long read_tap(const std::string& name, float* out, long long capacity);
   int net_shape(int H, int W, int* nh, int* nw, int* hp, int* wp) const;
   double flops = 0;
@@ -67,7 +68,11 @@ class SoloEngine {
   std::vector<Block> blocks[4];
   SoloConvW lateral[4], fpnc[4], mf[4][3], mf_pred, kconv[4], cconv[4], conv_cls, conv_kernel;
   SoloConvW3 mf3[4][3], mf_pred3, kconv3[4], cconv3[4], conv_cls3, conv_kernel3;  // the head in [hi | hi | lo] fp32 (exact_head)
-  int up_conv3(const std::string& name, const std::string& gn, int Cout, int Cin, int k, bool bias, SoloConvW3* out);
+  int up_conv3(const std::string& name, const std::string& gn, int Cout, int Cin, int k, bool bias, SoloConvW3* out,
+               const std::string& bn = "");
+  SoloConvW3 stem3, lateral3[4], fpnc3[4];  // exact_backbone
+  struct Block3 { SoloConvW3 c1, c2, c3, ds; };
+  std::vector<Block3> blocks3[4];
   float* d_feat_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // injected FPN levels, dense fp32 NHWC
   int feat_h[5] = {0, 0, 0, 0, 0}, feat_w[5] = {0, 0, 0, 0, 0};
   bool inject = false;

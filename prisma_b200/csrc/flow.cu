@@ -216,20 +216,33 @@ int flow_encode_u16(const float* flow, const uint8_t* mask, int H, int W, uint16
 // ------------------------------------------------------------------------------------------------
 // The pooled features are kept as an fp16 hi/lo pair ([hi(C) | lo(C)] per row, consumed as two K-slabs of the same
 // GEMM) so the coarse levels carry no extra rounding beyond the fp16 feature maps themselves.
-__global__ void k_pool_fmap(const __half* __restrict__ f, int H8, int W8, int C, __half* __restrict__ out, int lh, int lw,
-                            int win) {
+// One launch pools `frames` feature maps to all three coarse levels: grid.x = cells of level 3, then 2, then 1 (the 8 x 8
+// windows, the longest blocks, start first), grid.y = frame.  A thread owns two channels (half2 loads); the sum runs in
+// fp32 in raster order of the window, as before.  Level l lands at row coff[l] of the frame's [n123][2 C] operand.
+__global__ void k_pool_fmap(const __half* __restrict__ feat, size_t frame_stride, int W8, int C, __half* __restrict__ out,
+                            size_t out_frame_stride, PoolGeom g) {
   pdl_prologue();
-  const int cell = blockIdx.x;  // y * lw + x
+  int cell = blockIdx.x, lvl = 3;
+  if (cell >= g.ln[3]) { cell -= g.ln[3]; lvl = 2; if (cell >= g.ln[2]) { cell -= g.ln[2]; lvl = 1; } }
+  const int lw = g.lw[lvl], win = 1 << lvl;
   const int y = cell / lw, x = cell - y * lw;
   const float inv = 1.0f / (float)(win * win);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int dy = 0; dy < win; ++dy)
-      for (int dx = 0; dx < win; ++dx) acc += __half2float(f[((size_t)(y * win + dy) * W8 + x * win + dx) * C + c]);
-    const float m = acc * inv;
-    const __half hi = __float2half_rn(m);
-    out[(size_t)cell * 2 * C + c] = hi;
-    out[(size_t)cell * 2 * C + C + c] = __float2half_rn(m - __half2float(hi));
+  const __half* f = feat + blockIdx.y * frame_stride;
+  __half* o = out + blockIdx.y * out_frame_stride + (size_t)(g.coff[lvl] + cell) * 2 * C;
+  for (int c = 2 * threadIdx.x; c < C; c += 2 * blockDim.x) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int dy = 0; dy < win; ++dy) {
+      const __half* row = f + ((size_t)(y * win + dy) * W8 + x * win) * C + c;
+#pragma unroll 8
+      for (int dx = 0; dx < win; ++dx) {
+        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(row + (size_t)dx * C));
+        a0 += v.x; a1 += v.y;
+      }
+    }
+    const float m0 = a0 * inv, m1 = a1 * inv;
+    const __half h0 = __float2half_rn(m0), h1 = __float2half_rn(m1);
+    *reinterpret_cast<__half2*>(o + c) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(o + C + c) = __halves2half2(__float2half_rn(m0 - __half2float(h0)), __float2half_rn(m1 - __half2float(h1)));
   }
 }
 
@@ -323,12 +336,28 @@ int FlowCorr::init(int dev, int batch, int h8, int w8, int n_frames, const int* 
   PRISMA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   rows_pad = round_up(P, 256);
   PRISMA_TRY(fc_alloc(allocs, &feat, (size_t)NF * rows_pad * C));
+  // Levels 1..3 share one operand buffer and one volume: the pooled features of a frame are the rows [coff[l], coff[l] + ln[l])
+  // of a [n123][2 C] matrix, so ONE GEMM per direction writes the three coarse levels side by side into rows of pitch
+  // pitch123 (level l = columns coff[l]...).  Two launches per direction instead of four: the coarse levels used to run
+  // at 2.8-3.7 TB/s against level 0's 5.1 (short launches, 8-wave ramp each).
+  coff[0] = 0;
   for (int l = 0; l < 4; ++l) {
     lh[l] = H8 >> l; lw[l] = W8 >> l; ln[l] = lh[l] * lw[l];
-    lpitch[l] = round_up(ln[l], 4);
-    lrows_pad[l] = l == 0 ? rows_pad : round_up(lpitch[l], 256);
-    if (l > 0) PRISMA_TRY(fc_alloc(allocs, &pool[l], (size_t)NF * lrows_pad[l] * C * 2));
-    PRISMA_TRY(fc_alloc(allocs, &vol[l], (size_t)B * P * lpitch[l]));
+    if (l >= 1) coff[l] = l == 1 ? 0 : coff[l - 1] + round_up(ln[l - 1], 4);
+  }
+  n123 = coff[3] + ln[3];
+  pitch123 = round_up(n123, 4);
+  rows123_pad = round_up(pitch123, 256);
+  lpitch[0] = round_up(ln[0], 4);
+  lrows_pad[0] = rows_pad;
+  PRISMA_TRY(fc_alloc(allocs, &pool123, (size_t)NF * rows123_pad * C * 2));
+  PRISMA_TRY(fc_alloc(allocs, &vol[0], (size_t)B * P * lpitch[0]));
+  PRISMA_TRY(fc_alloc(allocs, &vol123, (size_t)B * P * pitch123));
+  for (int l = 1; l < 4; ++l) {
+    lpitch[l] = pitch123;
+    lrows_pad[l] = rows123_pad;
+    pool[l] = pool123 + (size_t)coff[l] * C * 2;
+    vol[l] = vol123 + coff[l];
   }
   PRISMA_TRY(fc_alloc(allocs, &coords, (size_t)B * 2 * P));
   PRISMA_TRY(fc_alloc(allocs, &lookup_out, (size_t)B * P * 384));
@@ -336,22 +365,26 @@ int FlowCorr::init(int dev, int batch, int h8, int w8, int n_frames, const int* 
   const int off[2] = {0, 0};
   bytes_build = flops_build = 0;
   for (int b = 0; b < B; ++b)
-    for (int l = 0; l < 4; ++l) {
+    for (int part = 0; part < 2; ++part) {  // part 0: level 0 against the features; part 1: levels 1..3 against [hi | lo] pooled rows
+      const int ncols = part == 0 ? lpitch[0] : pitch123;
       GemmEpilogue ep;
       ep.alpha = 1.0f / sqrtf((float)C);
-      ep.out_f32 = vol[l] + (size_t)b * P * lpitch[l];
-      ep.out_f32_ld = lpitch[l];
+      ep.out_f32 = part == 0 ? vol[0] + (size_t)b * P * lpitch[0] : vol123 + (size_t)b * P * pitch123;
+      ep.out_f32_ld = ncols;
       // the volume is store-bound (131 KB per 128 x 256 tile against 4 K-blocks of MMA): leave through TMA bulk stores
       static const bool tma_off = [] { const char* e = getenv("PRISMA_CORR_TMA_STORE"); return e && e[0] == '0'; }();
       GemmLaunch g;
-      ep.tma_store = !tma_off && gemm_pick_bn(P, lpitch[l], num_sms) >= 128;
-      const int wk = l == 0 ? 1 : 2;  // coarse levels: against [hi | lo] pooled features = two K-slabs
-      const __half* w2 = l == 0 ? feat + (size_t)f2[b] * rows_pad * C : pool[l] + (size_t)f2[b] * lrows_pad[l] * C * 2;
-      PRISMA_TRY(gemm_prepare(&g, feat + (size_t)f1[b] * rows_pad * C, P, C, C, w2, lrows_pad[l], P, lpitch[l], wk, off, ep, num_sms));
+      ep.tma_store = !tma_off && gemm_pick_bn(P, ncols, num_sms) >= 128;
+      const int wk = part == 0 ? 1 : 2;  // coarse levels: against [hi | lo] pooled features = two K-slabs
+      const __half* w2 = part == 0 ? feat + (size_t)f2[b] * rows_pad * C : pool123 + (size_t)f2[b] * rows123_pad * C * 2;
+      PRISMA_TRY(gemm_prepare(&g, feat + (size_t)f1[b] * rows_pad * C, P, C, C, w2, part == 0 ? rows_pad : rows123_pad, P, ncols, wk,
+                              off, ep, num_sms));
       gemms.push_back(g);
-      flops_build += 2.0 * P * (double)ln[l] * C;
-      bytes_build += 4.0 * P * (double)ln[l];
     }
+  for (int l = 0; l < 4; ++l) {
+    flops_build += (double)B * 2.0 * P * (double)ln[l] * C;
+    bytes_build += (double)B * 4.0 * P * (double)ln[l];
+  }
   bytes_build += 2.0 * B * P * (double)C * 2.0;  // the two fp16 feature maps of every direction, read once
   return 0;
 }
@@ -373,10 +406,10 @@ int FlowCorr::set_fmaps(const float* fm1, const float* fm2) {
 }
 
 int FlowCorr::pool_frames(int first, int count, cudaStream_t s) {
-  for (int f = first; f < first + count; ++f)
-    for (int l = 1; l < 4; ++l)
-      PRISMA_CUDA_OK(pdl_launch(k_pool_fmap, dim3(ln[l]), dim3(128), 0, s, feat + (size_t)f * rows_pad * C, H8, W8, C,
-                                pool[l] + (size_t)f * lrows_pad[l] * C * 2, lh[l], lw[l], 1 << l));
+  PoolGeom g;
+  for (int l = 0; l < 4; ++l) { g.lh[l] = lh[l]; g.lw[l] = lw[l]; g.ln[l] = ln[l]; g.coff[l] = coff[l]; }
+  PRISMA_CUDA_OK(pdl_launch(k_pool_fmap, dim3(ln[1] + ln[2] + ln[3], count), dim3(128), 0, s, (const __half*)(feat + (size_t)first * rows_pad * C),
+                            (size_t)rows_pad * C, W8, C, pool123 + (size_t)first * rows123_pad * C * 2, (size_t)rows123_pad * C * 2, g));
   return 0;
 }
 

@@ -17,6 +17,8 @@ int flow_consistency_masks(const float* fwd, const float* bwd, int H, int W, uin
 int flow_encode_u16(const float* flow, const uint8_t* mask, int H, int W, uint16_t* out, int num_sms, cudaStream_t s);
 
 // All-pairs correlation pyramid + lookup for `batch` image pairs at 1/8 resolution (h8 x w8, C = 256 channels).
+struct PoolGeom { int lh[4], lw[4], ln[4], coff[4]; };
+
 class FlowCorr {
  public:
   ~FlowCorr();
@@ -39,10 +41,15 @@ class FlowCorr {
   int NF = 0;                          // frames held
   int f1[8] = {0}, f2[8] = {0};        // frame of image1 / image2 per direction
   __half* feat = nullptr;              // [NF][rows_pad][C] fp16 features (rows padded to the next multiple of 256)
-  __half* pool[4] = {nullptr, nullptr, nullptr, nullptr};  // levels 1..3: [NF][lrows_pad][2 C] = [hi | lo] of the 2^l x 2^l mean
+  // levels 1..3 of a frame: rows [coff[l], coff[l] + ln[l]) of pool123 [NF][rows123_pad][2 C] = [hi | lo] of the 2^l x 2^l mean;
+  // pool[l] / vol[l] point at level l inside the shared buffers (row pitch rows123_pad * 2 C per frame / pitch123 per position)
+  __half* pool123 = nullptr;
+  float* vol123 = nullptr;
+  int coff[4] = {0, 0, 0, 0}, n123 = 0, pitch123 = 0, rows123_pad = 0;
+  __half* pool[4] = {nullptr, nullptr, nullptr, nullptr};
   int pool_frames(int first, int count, cudaStream_t s);   // K14 operands of frames [first, first + count)
-  int build_gemms(cudaStream_t s);                          // the 4 * B correlation GEMMs
-  float* vol[4] = {nullptr, nullptr, nullptr, nullptr};     // per level fp32 [B*P][lpitch]
+  int build_gemms(cudaStream_t s);                          // the 2 * B correlation GEMMs (level 0; levels 1..3)
+  float* vol[4] = {nullptr, nullptr, nullptr, nullptr};     // per level fp32 [B*P][lpitch] (levels 1..3: columns of vol123)
   float* coords = nullptr;
   __half* lookup_out = nullptr;  // [B*P][384] fp16 (324 used), the A operand of the motion encoder's convc1
   int rows_pad = 0, lrows_pad[4];

@@ -113,7 +113,8 @@ struct GemmArgs {
   int acc_group;  // XACC kernels: K blocks accumulated inside one TMEM chain before the partial sum is added to the running
                   // fp32 sums held in the epilogue warps' registers (see gemm_prepare_tf32x3)
   int dbg_mode;  // diagnostics (PRISMA_GEMM_DBG): 1 = prologue + teardown only, 2 = loads + MMAs but the epilogue warps only
-                 // release the accumulators, 3 = loads only (the MMA warp commits without issuing)
+                 // release the accumulators, 3 = loads only (the MMA warp commits without issuing), 4 = taps one row after
+                 // the previous tap skip their A load, 5 = no loads (MMAs on whatever shared memory holds), 6 = 5 + no epilogue
   int raster_n;  // 1: consecutive tiles walk N first (the CTAs of a wave share few A row panels and all of W: A is read
                  // from HBM once when M >> N); 0: M first
   GemmEpilogue ep;
@@ -340,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // diagnostics: nothing but the prologue and the teardown
   } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (lane == 0 && args.dbg_mode != 5 && args.dbg_mode != 6) {  // dbg_mode 5 / 6: no operand loads at all (the MMA warp does not wait)
       int stage = 0; uint32_t phase = 0;
       for (int tile = group; tile < num_items; tile += num_groups) {
         int tm, tn, nsub, bw;
@@ -352,14 +353,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int tap = 0, chunk = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          // diagnostics (dbg_mode 4): taps that shift the previous tap's rows by exactly one row do not load A at all (the
+          // MMAs read stale tiles; results are garbage) -- the upper bound of what a shared row-halo A tile would save
+          const bool skip_a = args.dbg_mode == 4 && tap > 0 && args.tap_off[tap] == args.tap_off[tap - 1] + 1;
           if (CG == 2) {
             // both CTAs' bytes land on the leader's barrier; only the leader arrives (count 1) and posts the total
-            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * stage_bytes);
-            tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], args.tap_acol[tap] + chunk * BKE, m0 + args.tap_off[tap]);
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (stage_bytes - (skip_a ? Cfg::A_BYTES : 0)));
+            if (!skip_a) tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], args.tap_acol[tap] + chunk * BKE, m0 + args.tap_off[tap]);
             tma_load_2d_pair(sB + stage * Cfg::B_BYTES, tb, &full[stage], kb * BKE, n0);
           } else {
-            mbar_arrive_expect_tx(&full[stage], stage_bytes);
-            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], args.tap_acol[tap] + chunk * BKE, m0 + args.tap_off[tap]);
+            mbar_arrive_expect_tx(&full[stage], stage_bytes - (skip_a ? Cfg::A_BYTES : 0));
+            if (!skip_a) tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], args.tap_acol[tap] + chunk * BKE, m0 + args.tap_off[tap]);
             tma_load_2d(sB + stage * Cfg::B_BYTES, tb, &full[stage], kb * BKE, n0);
           }
           if (++chunk == args.kchunks) { chunk = 0; ++tap; }
@@ -409,7 +413,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
+          if (args.dbg_mode != 5 && args.dbg_mode != 6) mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t adesc = make_sdesc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
           const uint64_t bdesc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
@@ -650,7 +654,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // 32 x 128-byte box, the same staging layout and swizzle as the fp32 path
 #pragma unroll 1
         for (int cb = chunk_par * 64; cb < bw; cb += 128) {
-          if (n0 + cb >= args.N || args.dbg_mode >= 2) break;  // warp-uniform
+          if (n0 + cb >= args.N || args.dbg_mode == 2 || args.dbg_mode == 3 || args.dbg_mode == 6) break;  // warp-uniform
           const uint32_t buf = stg + (st_cnt & 1) * 4096;
           if (st_cnt >= 2) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
 #pragma unroll
@@ -685,7 +689,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else
 #pragma unroll 1
       for (int c0 = chunk_par * 32; c0 < bw; c0 += 64) {
-        if (n0 + c0 >= args.N || args.dbg_mode >= 2) break;  // warp-uniform
+        if (n0 + c0 >= args.N || args.dbg_mode == 2 || args.dbg_mode == 3 || args.dbg_mode == 6) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         float4 bias4, gamma4;

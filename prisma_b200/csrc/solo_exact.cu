@@ -223,4 +223,104 @@ int solo_gather_kernels_split(const SoloCand* cand, const int* count, int cap, c
   return 0;
 }
 
+// ================================================================ fp32-class backbone (variant "<name>-exact")
+// The ResNet + FPN in the same arithmetic as the head: every conv is a 3xTF32 GEMM from a split map to a dense fp32
+// [H*W][Cout] output (BatchNorm folded into fp32 weights and bias, ReLU / the residual sum in the epilogue); the kernels
+// below are what sits between those GEMMs.  Reference: models/backbones/resnet.py:361-367,631-646, models/necks/fpn.py:151-204.
+
+// stem im2col of the normalised CHW fp32 image for conv1 = Conv2d(3, 64, 7, stride 2, padding 3): row = [hi(192) | lo(192)],
+// k = (c*7 + ky)*8 + kx (kx = 7 and k >= 168 zero) -- the K order of raft_im2col_stem, in fp32 halves
+__global__ void k_im2col_stem_split(const float* __restrict__ x, int H, int W, float* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)Ho * Wo * 24;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % 24);
+    const long long pix = i / 24;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (g < 21) {
+      const int oy = (int)(pix / Wo), ox = (int)(pix - (long long)oy * Wo);
+      const int c = g / 7, ky = g - c * 7;
+      const int iy = oy * 2 - 3 + ky, ix0 = ox * 2 - 3;
+      if (iy >= 0 && iy < H) {
+        const float* row = x + ((size_t)c * H + iy) * W;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) if (ix0 + j >= 0 && ix0 + j < W) v[j] = __ldg(row + ix0 + j);
+      }
+    }
+    float* o = out + (size_t)pix * 384;
+    store_split4(o, 192, g * 8, make_float4(v[0], v[1], v[2], v[3]));
+    store_split4(o, 192, g * 8 + 4, make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+int solo_im2col_stem_split(const float* x, int H, int W, float* out, cudaStream_t s) {
+  k_im2col_stem_split<<<148 * 8, 256, 0, s>>>(x, H, W, out);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// MaxPool2d(3, stride 2, padding 1) of a dense fp32 NHWC map -> dense fp32 (the identity of the first block) + split map
+__global__ void k_maxpool3s2_dense(const float* __restrict__ in, int H, int W, int C, float* __restrict__ out, float* __restrict__ out_split,
+                                   int Ho, int Wo) {
+  const int cv = C / 4;
+  const long long total = (long long)Ho * Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 4;
+    const int ox = (int)((i / cv) % Wo), oy = (int)(i / ((long long)cv * Wo));
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int y = 2 * oy + dy, x = 2 * ox + dx;
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+        const float4 v = *reinterpret_cast<const float4*>(in + ((size_t)y * W + x) * C + c);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    *reinterpret_cast<float4*>(out + ((size_t)oy * Wo + ox) * C + c) = m;
+    store_split4(out_split + sprow(oy, ox, Wo) * 2 * C, C, c, m);
+  }
+}
+int maxpool3s2_dense(const float* in, int H, int W, int C, float* out, float* out_split, int Ho, int Wo, cudaStream_t s) {
+  k_maxpool3s2_dense<<<148 * 8, 256, 0, s>>>(in, H, W, C, out, out_split, Ho, Wo);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// FPN top-down step on dense fp32 maps: fine += F.interpolate(coarse, size=fine.shape, mode="nearest") (fpn.py:166-177)
+__global__ void k_nearest_add_dense(float* __restrict__ fine, int Hf, int Wf, const float* __restrict__ coarse, int Hc, int Wc, int C,
+                                    float sy, float sx) {
+  const int cv = C / 4;
+  const long long total = (long long)Hf * Wf * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 4;
+    const int x = (int)((i / cv) % Wf), y = (int)(i / ((long long)cv * Wf));
+    const int ys = min((int)floorf(y * sy), Hc - 1), xs = min((int)floorf(x * sx), Wc - 1);
+    float4* a = reinterpret_cast<float4*>(fine + ((size_t)y * Wf + x) * C + c);
+    const float4 b = *reinterpret_cast<const float4*>(coarse + ((size_t)ys * Wc + xs) * C + c);
+    float4 v = *a;
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    *a = v;
+  }
+}
+int nearest_add_dense(float* fine, int Hf, int Wf, const float* coarse, int Hc, int Wc, int C, cudaStream_t s) {
+  k_nearest_add_dense<<<148 * 4, 256, 0, s>>>(fine, Hf, Wf, coarse, Hc, Wc, C, (float)Hc / (float)Hf, (float)Wc / (float)Wf);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// extra FPN level on dense fp32 maps: F.max_pool2d(x, 1, stride=2) = x[::2, ::2] (fpn.py:188)
+__global__ void k_subsample2_dense(const float* __restrict__ in, int W, int C, float* __restrict__ out, int Ho, int Wo) {
+  const int cv = C / 4;
+  const long long total = (long long)Ho * Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 4;
+    const int x = (int)((i / cv) % Wo), y = (int)(i / ((long long)cv * Wo));
+    *reinterpret_cast<float4*>(out + ((size_t)y * Wo + x) * C + c) = *reinterpret_cast<const float4*>(in + ((size_t)(2 * y) * W + 2 * x) * C + c);
+  }
+}
+int subsample2_dense(const float* in, int H, int W, int C, float* out, int Ho, int Wo, cudaStream_t s) {
+  (void)H;
+  k_subsample2_dense<<<64, 256, 0, s>>>(in, W, C, out, Ho, Wo);
+  PRISMA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace prisma

@@ -66,6 +66,11 @@ int groupnorm_relu_grid_split(const float* x, int B, int F, GridSizes S, int C, 
                               float* out_split, cudaStream_t s);
 int resize_bilinear_split(const float* src, int Hs, int Ws, int Csrc, int Csrc_pitch, float* dst, int Hd, int Wd, int Cdst, int coord,
                           int accumulate, cudaStream_t s, int dst_frame_w = 0);
+// fp32-class backbone ("-exact" variants): dense fp32 NHWC maps between the 3xTF32 convs
+int solo_im2col_stem_split(const float* x_chw, int H, int W, float* out, cudaStream_t s);  // -> [H/2 * W/2][hi(192) | lo(192)]
+int maxpool3s2_dense(const float* in, int H, int W, int C, float* out, float* out_split, int Ho, int Wo, cudaStream_t s);
+int nearest_add_dense(float* fine, int Hf, int Wf, const float* coarse, int Hc, int Wc, int C, cudaStream_t s);
+int subsample2_dense(const float* in, int H, int W, int C, float* out, int Ho, int Wo, cudaStream_t s);
 int solo_gather_kernels_split(const SoloCand* cand, const int* count, int cap, const float* const* lvl_kernels,
                               const int* lvl_cell0, int levels, int num_classes, int C, float* out, cudaStream_t s,
                               const int* lvl_S = nullptr, int frame = 0);
