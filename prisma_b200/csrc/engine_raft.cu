@@ -469,8 +469,8 @@ int RaftEngine::build_plan(int H, int W, double scale, int iters_) {
       add("reuse_prev", [=](cudaStream_t s) {
         const size_t n = (size_t)c->rows_pad * c->C * sizeof(__half);
         PRISMA_CUDA_OK(cudaMemcpyAsync(c->feat, c->feat + (size_t)NP * c->rows_pad * c->C, n, cudaMemcpyDeviceToDevice, s));
-        const size_t pn = (size_t)c->rows123_pad * c->C * 2 * sizeof(__half);
-        PRISMA_CUDA_OK(cudaMemcpyAsync(c->pool123, c->pool123 + (size_t)NP * c->rows123_pad * c->C * 2, pn, cudaMemcpyDeviceToDevice, s));
+        const size_t pn = (size_t)c->rows123_pad * c->C * c->pw * sizeof(__half);
+        PRISMA_CUDA_OK(cudaMemcpyAsync(c->pool123, c->pool123 + (size_t)NP * c->rows123_pad * c->C * c->pw, pn, cudaMemcpyDeviceToDevice, s));
         PRISMA_CUDA_OK(cudaMemcpyAsync(cn, reinterpret_cast<const char*>(cn) + NP * cn_n, cn_n, cudaMemcpyDeviceToDevice, s));
         PRISMA_CUDA_OK(cudaMemcpyAsync(rsz, rsz + NP * rbytes, rbytes, cudaMemcpyDeviceToDevice, s));
         return 0;

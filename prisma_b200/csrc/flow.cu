@@ -214,13 +214,15 @@ int flow_encode_u16(const float* flow, const uint8_t* mask, int H, int W, uint16
 // K14 (by linearity): avg_pool2d of the correlation volume over its last two dims == correlation with the
 // average-pooled fmap2.  Pool fmap2 (fp16 [P][C]) into the three coarser levels (floor sizes, corr.py:24-27).
 // ------------------------------------------------------------------------------------------------
-// The pooled features are kept as an fp16 hi/lo pair ([hi(C) | lo(C)] per row, consumed as two K-slabs of the same
-// GEMM) so the coarse levels carry no extra rounding beyond the fp16 feature maps themselves.
+// The pooled features are fp16 like the features themselves (one K-slab).  PRISMA_CORR_POOL_LO=1 keeps them as an fp16
+// hi/lo pair ([hi(C) | lo(C)] per row, two K-slabs of the same GEMM: no rounding of the means at all) -- the round-2 default
+// until the oracle study (fp16 features, means rounded or not, 12 iterations) put the difference at 5e-6 of the largest
+// displacement against a 1e-3 budget, while the second slab made the coarse GEMM operand-bound (K = 512 for 128 KB of output).
 // One launch pools `frames` feature maps to all three coarse levels: grid.x = cells of level 3, then 2, then 1 (the 8 x 8
 // windows, the longest blocks, start first), grid.y = frame.  A thread owns two channels (half2 loads); the sum runs in
 // fp32 in raster order of the window, as before.  Level l lands at row coff[l] of the frame's [n123][2 C] operand.
 __global__ void k_pool_fmap(const __half* __restrict__ feat, size_t frame_stride, int W8, int C, __half* __restrict__ out,
-                            size_t out_frame_stride, PoolGeom g) {
+                            size_t out_frame_stride, PoolGeom g, int with_lo) {
   pdl_prologue();
   int cell = blockIdx.x, lvl = 3;
   if (cell >= g.ln[3]) { cell -= g.ln[3]; lvl = 2; if (cell >= g.ln[2]) { cell -= g.ln[2]; lvl = 1; } }
@@ -228,7 +230,7 @@ __global__ void k_pool_fmap(const __half* __restrict__ feat, size_t frame_stride
   const int y = cell / lw, x = cell - y * lw;
   const float inv = 1.0f / (float)(win * win);
   const __half* f = feat + blockIdx.y * frame_stride;
-  __half* o = out + blockIdx.y * out_frame_stride + (size_t)(g.coff[lvl] + cell) * 2 * C;
+  __half* o = out + blockIdx.y * out_frame_stride + (size_t)(g.coff[lvl] + cell) * (with_lo ? 2 : 1) * C;
   for (int c = 2 * threadIdx.x; c < C; c += 2 * blockDim.x) {
     float a0 = 0.f, a1 = 0.f;
     for (int dy = 0; dy < win; ++dy) {
@@ -242,7 +244,8 @@ __global__ void k_pool_fmap(const __half* __restrict__ feat, size_t frame_stride
     const float m0 = a0 * inv, m1 = a1 * inv;
     const __half h0 = __float2half_rn(m0), h1 = __float2half_rn(m1);
     *reinterpret_cast<__half2*>(o + c) = __halves2half2(h0, h1);
-    *reinterpret_cast<__half2*>(o + C + c) = __halves2half2(__float2half_rn(m0 - __half2float(h0)), __float2half_rn(m1 - __half2float(h1)));
+    if (with_lo)
+      *reinterpret_cast<__half2*>(o + C + c) = __halves2half2(__float2half_rn(m0 - __half2float(h0)), __float2half_rn(m1 - __half2float(h1)));
   }
 }
 
@@ -350,13 +353,15 @@ int FlowCorr::init(int dev, int batch, int h8, int w8, int n_frames, const int* 
   rows123_pad = round_up(pitch123, 256);
   lpitch[0] = round_up(ln[0], 4);
   lrows_pad[0] = rows_pad;
-  PRISMA_TRY(fc_alloc(allocs, &pool123, (size_t)NF * rows123_pad * C * 2));
+  pool_lo = [] { const char* e = getenv("PRISMA_CORR_POOL_LO"); return e && e[0] == '1'; }();
+  pw = pool_lo ? 2 : 1;
+  PRISMA_TRY(fc_alloc(allocs, &pool123, (size_t)NF * rows123_pad * C * pw));
   PRISMA_TRY(fc_alloc(allocs, &vol[0], (size_t)B * P * lpitch[0]));
   PRISMA_TRY(fc_alloc(allocs, &vol123, (size_t)B * P * pitch123));
   for (int l = 1; l < 4; ++l) {
     lpitch[l] = pitch123;
     lrows_pad[l] = rows123_pad;
-    pool[l] = pool123 + (size_t)coff[l] * C * 2;
+    pool[l] = pool123 + (size_t)coff[l] * C * pw;
     vol[l] = vol123 + coff[l];
   }
   PRISMA_TRY(fc_alloc(allocs, &coords, (size_t)B * 2 * P));
@@ -365,7 +370,7 @@ int FlowCorr::init(int dev, int batch, int h8, int w8, int n_frames, const int* 
   const int off[2] = {0, 0};
   bytes_build = flops_build = 0;
   for (int b = 0; b < B; ++b)
-    for (int part = 0; part < 2; ++part) {  // part 0: level 0 against the features; part 1: levels 1..3 against [hi | lo] pooled rows
+    for (int part = 0; part < 2; ++part) {  // part 0: level 0 against the features; part 1: levels 1..3 against the pooled rows
       const int ncols = part == 0 ? lpitch[0] : pitch123;
       GemmEpilogue ep;
       ep.alpha = 1.0f / sqrtf((float)C);
@@ -375,8 +380,8 @@ int FlowCorr::init(int dev, int batch, int h8, int w8, int n_frames, const int* 
       static const bool tma_off = [] { const char* e = getenv("PRISMA_CORR_TMA_STORE"); return e && e[0] == '0'; }();
       GemmLaunch g;
       ep.tma_store = !tma_off && gemm_pick_bn(P, ncols, num_sms) >= 128;
-      const int wk = part == 0 ? 1 : 2;  // coarse levels: against [hi | lo] pooled features = two K-slabs
-      const __half* w2 = part == 0 ? feat + (size_t)f2[b] * rows_pad * C : pool123 + (size_t)f2[b] * rows123_pad * C * 2;
+      const int wk = part == 0 ? 1 : pw;  // PRISMA_CORR_POOL_LO: against [hi | lo] pooled features = two K-slabs
+      const __half* w2 = part == 0 ? feat + (size_t)f2[b] * rows_pad * C : pool123 + (size_t)f2[b] * rows123_pad * C * pw;
       PRISMA_TRY(gemm_prepare(&g, feat + (size_t)f1[b] * rows_pad * C, P, C, C, w2, part == 0 ? rows_pad : rows123_pad, P, ncols, wk,
                               off, ep, num_sms));
       gemms.push_back(g);
@@ -409,7 +414,8 @@ int FlowCorr::pool_frames(int first, int count, cudaStream_t s) {
   PoolGeom g;
   for (int l = 0; l < 4; ++l) { g.lh[l] = lh[l]; g.lw[l] = lw[l]; g.ln[l] = ln[l]; g.coff[l] = coff[l]; }
   PRISMA_CUDA_OK(pdl_launch(k_pool_fmap, dim3(ln[1] + ln[2] + ln[3], count), dim3(128), 0, s, (const __half*)(feat + (size_t)first * rows_pad * C),
-                            (size_t)rows_pad * C, W8, C, pool123 + (size_t)first * rows123_pad * C * 2, (size_t)rows123_pad * C * 2, g));
+                            (size_t)rows_pad * C, W8, C, pool123 + (size_t)first * rows123_pad * C * pw, (size_t)rows123_pad * C * pw, g,
+                            pool_lo ? 1 : 0));
   return 0;
 }
 

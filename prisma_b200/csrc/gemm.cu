@@ -157,11 +157,28 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   else if (!force_bn && !pairs_off && !tf32 && bn == 256 && M >= 1024 && N >= 256) cg = 2;
   else if (!force_bn && !pairs_off && !tf32 && pair128 && bn == 128 && M >= 4096 && N >= 128 && !ep.tma_store) cg = 2;
   PRISMA_CHECK(!(tf32 && cg == 2), "gemm: the tf32 path has no CTA-pair instantiation");
+  // Transposed tiles (GemmCfg SWAP) when one 128-wide tile covers all output columns: an M = 128 instruction costs the tensor
+  // core >= 128 cycles whatever its N, so 128 x 256 (weights x rows) runs at twice the rate of 128 x 128 (rows x weights).
+  // PRISMA_GEMM_SWAP=0 switches it off; force_bn == 640 requests it.
+  static const bool swap_off = [] { const char* e = getenv("PRISMA_GEMM_SWAP"); return e && e[0] == '0'; }();
+  bool swap = false;
+  if (bn == 640) { bn = 128; cg = 1; swap = true; }
+  else if (!force_bn && !swap_off && !tf32 && cg == 1 && bn == 128 && N <= 128 && M >= 4096 && !ep.tma_store && !ep.head_w && !ep.m_dev) swap = true;
+  else {
+    // 64 output columns: the same transposed tile with the upper 64 weight rows zero (they must exist: w_rows >= 128) -- twice
+    // the MMA work of a 128 x 64 tile, but half the instructions, barriers and TMA boxes per output row.  PRISMA_GEMM_SWAP64=1.
+    static const bool swap64 = [] { const char* e = getenv("PRISMA_GEMM_SWAP64"); return e && e[0] == '1'; }();
+    if (swap64 && !force_bn && !swap_off && !tf32 && cg == 1 && bn == 64 && N > 32 && N <= 64 && w_rows >= 128 && M >= 4096 &&
+        !ep.tma_store && !ep.head_w && !ep.m_dev) { bn = 128; swap = true; }
+  }
+  PRISMA_CHECK(!swap || (N <= 128 && !tf32 && !ep.tma_store && !ep.head_w), "gemm: transposed tiles need N <= 128, fp16 operands, the plain epilogue");
+  out->swap = swap;
   out->tf32 = tf32;
   out->xacc = false;
   out->args.acc_group = 1;
   const int bke = tf32 ? 32 : 64;  // elements per 128-byte K block
   PRISMA_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: unsupported BLOCK_N");
+  PRISMA_CHECK(!swap || a_rows >= 1, "gemm: empty operand");
   out->cg = cg;
   PRISMA_CHECK(w_rows >= round_up(N, bn), "gemm: weight rows must be padded to a multiple of BLOCK_N");
   const int kchunks = ceil_div(a_cols, bke);
@@ -188,11 +205,11 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
     PRISMA_TRY(make_tmap_2d_f32(&out->tmA, A, (uint64_t)a_pitch, (uint64_t)a_rows, (uint64_t)a_pitch, 32, GEMM_BM));
     PRISMA_TRY(make_tmap_2d_f32(&out->tmB, W, (uint64_t)taps * kchunks * 32, (uint64_t)w_rows, (uint64_t)taps * kchunks * 32, 32, bn));
   } else {
-    PRISMA_TRY(make_tmap_2d_f16(&out->tmA, A, (uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)a_pitch, 64, GEMM_BM));
+    PRISMA_TRY(make_tmap_2d_f16(&out->tmA, A, (uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)a_pitch, 64, swap ? 256 : GEMM_BM));
     PRISMA_TRY(make_tmap_2d_f16(&out->tmB, W, (uint64_t)taps * kchunks * 64, (uint64_t)w_rows,
                                 (uint64_t)taps * kchunks * 64, 64, bn / cg));
   }
-  const int tiles = ceil_div(M, GEMM_BM * cg) * ceil_div(N, bn);
+  const int tiles = ceil_div(M, swap ? 256 : GEMM_BM * cg) * ceil_div(N, bn);
   const int groups = num_sms / cg;
   out->grid = (tiles < groups ? tiles : groups) * cg;
   // Tail tiles: when the last wave is partial, cut its tiles into narrower ones so that it costs a fraction of a full
@@ -204,7 +221,7 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
     static const bool tail_off = [] { const char* e = getenv("PRISMA_GEMM_TAIL"); return e && e[0] == '0'; }();
     const int full = tiles / groups, rem = tiles % groups;
     auto cost = [](int w) { return w >= 256 ? 134.0 : (w >= 128 ? 100.0 : (w >= 64 ? 68.0 : 51.0)); };
-    if (!tail_off && !force_bn && full >= 1 && rem > 0) {
+    if (!tail_off && !force_bn && !swap && full >= 1 && rem > 0) {
       int best_split = 1;
       double best = cost(bn);
       for (int split = 2; split <= 4; split *= 2) {
@@ -245,12 +262,12 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   return 0;
 }
 
-template <int BN, int CG, bool TMAST = false, bool TF32 = false, bool XACC = false>
+template <int BN, int CG, bool TMAST = false, bool TF32 = false, bool XACC = false, bool SWAP = false>
 static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
   static bool attr_set = false;  // per-process, per-instantiation
-  using Cfg = GemmCfg<BN, CG, TMAST>;
+  using Cfg = GemmCfg<BN, CG, TMAST, SWAP>;
   if (!attr_set) {
-    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, TMAST, TF32, XACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, TMAST, TF32, XACC, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   {
@@ -273,7 +290,7 @@ static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, TMAST, TF32, XACC>, g.tmA, g.tmB, g.tmBt, g.tmD, g.args));
+    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, TMAST, TF32, XACC, SWAP>, g.tmA, g.tmB, g.tmBt, g.tmD, g.args));
   }
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
@@ -299,6 +316,7 @@ int gemm_run(const GemmLaunch& g, cudaStream_t stream) {
     set_last_error("gemm_run: unsupported BLOCK_N (tf32)");
     return -1;
   }
+  if (g.swap) return launch_bn<128, 1, false, false, false, true>(g, stream);
   if (g.tma_store) {
     if (g.cg == 2 && g.bn == 256) return launch_bn<256, 2, true>(g, stream);
     if (g.cg == 1 && g.bn == 256) return launch_bn<256, 1, true>(g, stream);

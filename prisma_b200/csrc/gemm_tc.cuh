@@ -120,13 +120,21 @@ struct GemmArgs {
   GemmEpilogue ep;
 };
 
-template <int BN, int CG = 1, bool TMAST = false>  // CG = CTAs per MMA (cta_group): 2 = a CTA pair computes a 256 x BN tile, each loading half of W
+// SWAP ("swap A/B", BN == 128, CG == 1): the tensor core spends >= 128 cycles on every M = 128 instruction whatever its N
+// (measured, tools/gemm_pace.py: N = 128 tiles reach half the rate of N = 256 ones with no loads and no epilogue), so a
+// GEMM with <= 128 output columns runs transposed: the WEIGHT tile (128 output channels) is the M operand, 256 pixel rows
+// are the N operand of one instruction, the accumulator holds channels in its lanes and pixels in its columns, and the
+// epilogue transposes through its staging buffer (which it does anyway).  Half the instructions, barriers and TMA boxes
+// per FLOP; the operand bytes per FLOP drop by a quarter.
+template <int BN, int CG = 1, bool TMAST = false, bool SWAP = false>  // CG = CTAs per MMA (cta_group): 2 = a CTA pair computes a 256 x BN tile, each loading half of W
 struct GemmCfg {                                   // TMAST: TMA-store epilogue (double-buffered staging, one operand stage fewer)
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int A_ROWS = SWAP ? 256 : GEMM_BM;   // activation rows per tile and CTA
+  static constexpr int ACC_COLS = SWAP ? 256 : BN;      // TMEM columns of one accumulator stage
+  static constexpr int A_BYTES = A_ROWS * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = ((STAGE_BYTES >= 49152) ? 4 : (STAGE_BYTES >= 32768 ? 6 : 7)) - (TMAST ? 1 : 0);
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
   static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 32 * 4 * (TMAST ? 2 : 1);  // epilogue staging: 32x32 fp32 per warp (x2 buffers)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -277,12 +285,14 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   }
 }
 
-template <int BN, int CG, bool TMAST, bool TF32, bool XACC>
+template <int BN, int CG, bool TMAST, bool TF32, bool XACC, bool SWAP = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmD,
                const __grid_constant__ GemmArgs args) {
-  using Cfg = GemmCfg<BN, CG, TMAST>;
+  static_assert(!SWAP || (BN == 128 && CG == 1 && !TMAST && !TF32 && !XACC), "SWAP: 128 output channels x 256 pixel rows, fp16, one CTA");
+  using Cfg = GemmCfg<BN, CG, TMAST, SWAP>;
+  constexpr int ACC = Cfg::ACC_COLS;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BKE = TF32 ? 32 : 64;  // elements per 128-byte K block (fp32 containers for kind::tf32, fp16 otherwise)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -305,7 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // position inside the CTA pair
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
-  constexpr int TILE_M = GEMM_BM * CG;
+  constexpr int TILE_M = SWAP ? 256 : GEMM_BM * CG;
   const int M_run = args.ep.m_dev ? min(args.M, (*args.ep.m_dev + TILE_M - 1) / TILE_M * TILE_M) : args.M;  // see GemmEpilogue::m_dev
   const int tiles_m = (M_run + TILE_M - 1) / TILE_M;
   const int tiles_n = (args.N + BN - 1) / BN;
@@ -374,7 +384,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc_full = TF32 ? make_idesc_tf32(TILE_M, BN) : make_idesc_f16(TILE_M, BN);
+      constexpr uint32_t idesc_full = SWAP ? make_idesc_f16(128, 256) : (TF32 ? make_idesc_tf32(TILE_M, BN) : make_idesc_f16(TILE_M, BN));
       const uint32_t idesc_tail = TF32 ? make_idesc_tf32(TILE_M, bw_tail) : make_idesc_f16(TILE_M, bw_tail);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
@@ -411,12 +421,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tmem_base + as * ACC;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (args.dbg_mode != 5 && args.dbg_mode != 6) mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = make_sdesc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
-          const uint64_t bdesc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+          // SWAP: the weight tile is the M operand, the 256 activation rows the N operand
+          const uint64_t adesc = make_sdesc_sw128(smem_u32(SWAP ? sB + stage * Cfg::B_BYTES : sA + stage * Cfg::A_BYTES));
+          const uint64_t bdesc = make_sdesc_sw128(smem_u32(SWAP ? sA + stage * Cfg::A_BYTES : sB + stage * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             if (args.dbg_mode == 3) break;
@@ -449,55 +460,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       item_tile(tile, &tm, &tn, &nsub, &bw);
       const int m0 = tm * TILE_M + rank * GEMM_BM;
       const int n0 = tn * BN + nsub;
-      const int m = m0 + quarter * 32 + lane;
-      // ---- row mapping of "my" accumulator row (lane == row inside this warp's 32-row slab)
-      int valid = m < args.M;
-      int drow = m;
+      // ---- row mapping of the 32 output rows a chunk covers (lane == row inside the slab): once per tile (the warp's 32
+      // accumulator rows), or -- SWAP, where the accumulator's COLUMNS are the output rows -- once per 32-pixel chunk
+      int m = 0, valid = 0, drow = 0;
       int ty = 0, tx = 0, img_base = 0;  // token coordinates / image base row for ROW_SHUFFLE
       const int out_ld = ep.out_lead < 0 ? ep.out_pad : ep.out_lead;  // leading border of the destination map
-      if (ep.row_map == ROW_PADDED || ep.row_map == ROW_PAD2TOK) {
-        int img = 0, r = m;
-        if (ep.img_rows > 0) { img = m / ep.img_rows; r = m - img * ep.img_rows; }
-        const int y = r / ep.in_w, x = r - y * ep.in_w;
-        const int pd = ep.pad, ld = ep.lead < 0 ? ep.pad : ep.lead;
-        valid = valid && y >= ld && y < ep.in_h - pd && x >= ld && x < ep.in_w - pd;
-        if (ep.row_map == ROW_PAD2TOK) {
-          const int ho = (ep.in_h - pd - ld + ep.sub - 1) / ep.sub, wo = (ep.in_w - pd - ld + ep.sub - 1) / ep.sub;
-          valid = valid && ((y - ld) % ep.sub == 0) && ((x - ld) % ep.sub == 0);
-          drow = img * (ep.out_img_rows > 0 ? ep.out_img_rows : ho * wo) + ((y - ld) / ep.sub) * wo + (x - ld) / ep.sub;
-        } else if (ep.sub > 1 || ep.out_wp > 0) {
-          // destination geometry differs from the source one (stride-2 sub-sampling and / or another border width)
-          valid = valid && ((y - ld) % ep.sub == 0) && ((x - ld) % ep.sub == 0);
-          drow = img * ep.out_img_rows + ((y - ld) / ep.sub + out_ld) * ep.out_wp + (x - ld) / ep.sub + out_ld;
-        }
-      } else if (ep.row_map == ROW_TOKSKIP) {
-        drow = m + m / ep.in_w + 1;
-      } else if (ep.row_map == ROW_TOK2PAD || ep.row_map == ROW_SHUFFLE) {
-        const int per = ep.in_w * ep.in_h;
-        const int img = m / per, r = m - img * per;
-        ty = r / ep.in_w; tx = r - ty * ep.in_w;
-        img_base = img * ep.out_img_rows;
-        drow = img_base + (ty + out_ld) * ep.out_wp + tx + out_ld;
-      }
-      // row mapping of the 8 rows this lane stores in the coalesced phase (constant over the tile's chunks)
       int dr8[8], ty8[8], tx8[8], ib8[8];
       uint32_t okrows = 0;
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        const int row = rr * 4 + rsub;
-        okrows |= (__shfl_sync(0xffffffffu, valid, row) ? 1u : 0u) << rr;
-        dr8[rr] = __shfl_sync(0xffffffffu, drow, row);
-        if (ep.row_map == ROW_SHUFFLE) {
-          ty8[rr] = __shfl_sync(0xffffffffu, ty, row);
-          tx8[rr] = __shfl_sync(0xffffffffu, tx, row);
-          ib8[rr] = __shfl_sync(0xffffffffu, img_base, row);
+      auto map_rows = [&](const int mbase) {
+        m = mbase + lane;
+        valid = m < args.M;
+        drow = m;
+        ty = 0; tx = 0; img_base = 0;
+        if (ep.row_map == ROW_PADDED || ep.row_map == ROW_PAD2TOK) {
+          int img = 0, r = m;
+          if (ep.img_rows > 0) { img = m / ep.img_rows; r = m - img * ep.img_rows; }
+          const int y = r / ep.in_w, x = r - y * ep.in_w;
+          const int pd = ep.pad, ld = ep.lead < 0 ? ep.pad : ep.lead;
+          valid = valid && y >= ld && y < ep.in_h - pd && x >= ld && x < ep.in_w - pd;
+          if (ep.row_map == ROW_PAD2TOK) {
+            const int ho = (ep.in_h - pd - ld + ep.sub - 1) / ep.sub, wo = (ep.in_w - pd - ld + ep.sub - 1) / ep.sub;
+            valid = valid && ((y - ld) % ep.sub == 0) && ((x - ld) % ep.sub == 0);
+            drow = img * (ep.out_img_rows > 0 ? ep.out_img_rows : ho * wo) + ((y - ld) / ep.sub) * wo + (x - ld) / ep.sub;
+          } else if (ep.sub > 1 || ep.out_wp > 0) {
+            // destination geometry differs from the source one (stride-2 sub-sampling and / or another border width)
+            valid = valid && ((y - ld) % ep.sub == 0) && ((x - ld) % ep.sub == 0);
+            drow = img * ep.out_img_rows + ((y - ld) / ep.sub + out_ld) * ep.out_wp + (x - ld) / ep.sub + out_ld;
+          }
+        } else if (ep.row_map == ROW_TOKSKIP) {
+          drow = m + m / ep.in_w + 1;
+        } else if (ep.row_map == ROW_TOK2PAD || ep.row_map == ROW_SHUFFLE) {
+          const int per = ep.in_w * ep.in_h;
+          const int img = m / per, r = m - img * per;
+          ty = r / ep.in_w; tx = r - ty * ep.in_w;
+          img_base = img * ep.out_img_rows;
+          drow = img_base + (ty + out_ld) * ep.out_wp + tx + out_ld;
         }
-      }
+        // row mapping of the 8 rows this lane stores in the coalesced phase
+        okrows = 0;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int row = rr * 4 + rsub;
+          okrows |= (__shfl_sync(0xffffffffu, valid, row) ? 1u : 0u) << rr;
+          dr8[rr] = __shfl_sync(0xffffffffu, drow, row);
+          if (ep.row_map == ROW_SHUFFLE) {
+            ty8[rr] = __shfl_sync(0xffffffffu, ty, row);
+            tx8[rr] = __shfl_sync(0xffffffffu, tx, row);
+            ib8[rr] = __shfl_sync(0xffffffffu, img_base, row);
+          }
+        }
+      };
+      if (!SWAP) map_rows(m0 + quarter * 32);
       // one 32-column chunk of this warp's 32 accumulator rows: r[j] = row `lane`, column c0 + j
       // bias / LayerScale vectors of a chunk: issued BEFORE the TMEM read is waited for, so the global-load latency hides
       // behind it (they used to sit between the shared-memory phases, on the critical path of every chunk)
       auto load_bias_gamma = [&](const int c0, float4& bias4, float4& gamma4) {
-        const int n = n0 + c0 + cg * 4;
+        const int n = SWAP ? n0 + quarter * 32 + cg * 4 : n0 + c0 + cg * 4;
         bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         gamma4 = make_float4(1.f, 1.f, 1.f, 1.f);
         if (n < args.N && ep.bias) bias4 = *reinterpret_cast<const float4*>(ep.bias + n);
@@ -551,13 +569,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           return;
         }
         // ---- phase 1: row-per-lane registers -> swizzled smem (conflict-free 16 B slots)
+        if (SWAP) {
+          // the lane holds output column (channel) `lane` of the 32 output rows (pixels) c0 .. c0 + 31: element (row j, column
+          // lane) goes to the same swizzled slot the row-per-lane layout uses (32 consecutive words per instruction)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts128(stg + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          for (int j = 0; j < 32; ++j)
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + j * 128 + ((((lane >> 2) ^ (j & 7))) << 4) + ((lane & 3) << 2)), "r"(r[j]) : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(stg + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
         __syncwarp();
         // ---- phase 2: 8 lanes x 4 columns cover one row's 32 columns; 4 rows per step -> coalesced global access
-        const int n = n0 + c0 + cg * 4;
+        const int n = SWAP ? n0 + quarter * 32 + cg * 4 : n0 + c0 + cg * 4;
         const bool ncol_ok = n < args.N;
         float4 v[8];
 #pragma unroll
@@ -596,7 +622,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
           }
           if (rsub == 0 && ncol_ok) {
-            const size_t slab = (size_t)(m0 + quarter * 32) >> 5;
+            const size_t slab = (size_t)(SWAP ? m0 + c0 : m0 + quarter * 32) >> 5;
             *reinterpret_cast<float4*>(ep.stat_part + (slab * 2) * args.N + n) = sm;
             *reinterpret_cast<float4*>(ep.stat_part + (slab * 2 + 1) * args.N + n) = sq;
           }
@@ -648,8 +674,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-      if (TMAST && ep.out_f16 != nullptr) {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * ACC;
+      if (SWAP) {
+        // this warp: output columns n0 + quarter * 32 .. + 31 (TMEM lanes), alternate 32-pixel chunks (TMEM columns)
+#pragma unroll 1
+        for (int c0 = chunk_par * 32; c0 < 256; c0 += 64) {
+          if (m0 + c0 >= args.M || n0 + quarter * 32 >= args.N || args.dbg_mode == 2 || args.dbg_mode == 3 || args.dbg_mode == 6) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          map_rows(m0 + c0);
+          float4 bias4, gamma4;
+          load_bias_gamma(c0, bias4, gamma4);
+          tmem_ld_wait();
+          process_chunk(r, c0, bias4, gamma4);
+        }
+      } else if (TMAST && ep.out_f16 != nullptr) {
         // fp16 destination: a warp takes 64-column blocks (two TMEM chunks) so that every bulk store still moves a
         // 32 x 128-byte box, the same staging layout and swizzle as the fp32 path
 #pragma unroll 1
@@ -720,6 +759,7 @@ struct GemmLaunch {
   bool tma_store = false;
   bool xacc = false;           // external fp32 accumulation (tf32x3 only): see GemmArgs::acc_group
   bool tf32 = false;           // kind::tf32 operands (fp32 containers): the 3xTF32 "fp32-class" path of the mask band
+  bool swap = false;           // transposed tiles for N <= 128: 128 output columns x 256 rows per instruction (GemmCfg SWAP)
   GemmArgs args;
   int bn = 128;
   int cg = 1;  // 2 = CTA pairs (cta_group::2), 256 x bn tiles

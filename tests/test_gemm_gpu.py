@@ -45,6 +45,13 @@ def _gemm(A, W, bias, act, bn):
     (26624, 256, 128, 2, 0),     # CTA pairs: 104 pair tiles = 1 wave + 30 -> cut into 2 x 128-wide tiles
     (39008, 128, 384, 1, 0),     # single CTAs, 128-wide: 305 tiles = 2 waves + 9 -> 2 x 64-wide tiles, gelu
     (20000, 64, 128, 0, 0),      # 64-wide: 157 tiles = 1 wave + 9 -> 2 x 32-wide tiles
+    # transposed tiles (GemmCfg SWAP, force 640): 128 output columns x 256 rows per instruction, epilogue transposed
+    (256, 128, 64, 0, 640),      # one tile, one k-block
+    (37000, 128, 1920, 0, 640),  # the RAFT GRU q conv shape: ragged M (the last tile has 136 valid rows), many tiles per CTA
+    (5000, 96, 576, 2, 640),     # N = 96 (RAFT encoder layer 2): the fourth column quarter is beyond N; relu
+    (777, 128, 200, 1, 640),     # K tail, gelu, M not a multiple of 32
+    (151552, 128, 256, 0, 0),    # auto choice picks the transposed tiles (N <= 128, M >= 4096): 8 whole waves
+    (4100, 68, 128, 0, 640),     # N % 32 = 4: one 4-column group of the third quarter valid
 ])
 def test_gemm_matches_fp32_reference(M, N, K, act, bn):
     rng = np.random.default_rng(M * 7 + N * 3 + K)

@@ -173,15 +173,22 @@ def test_solo_test_pipeline_resize_is_byte_equal_to_cv2(tiny, H, W):
     assert np.array_equal(rs, meta["resized_u8"])
 
 
-@pytest.mark.gpu
-def test_solo_r101_720p_matches_oracle():
-    from prisma_b200.mask import SoloV2Engine
+@pytest.fixture(scope="module")
+def r101_oracle():
+    """The CPU oracle on the R-101 config (one 720p frame): shared by the fp16-backbone and the fp32-class-backbone tests."""
     sd = make_solo_weights("r101", 0)
-    eng = SoloV2Engine(sd, variant="r101")
     img = synthetic_frame(720, 1280, 0)
-    res = eng.infer(img, confidence=0.3, want_instances=True)
     taps = {}
     scores, labels, masks = osolo.solo_infer(sd, img, "r101", taps)
+    return sd, img, taps, scores, labels, masks
+
+
+@pytest.mark.gpu
+def test_solo_r101_720p_matches_oracle(r101_oracle):
+    from prisma_b200.mask import SoloV2Engine
+    sd, img, taps, scores, labels, masks = r101_oracle
+    eng = SoloV2Engine(sd, variant="r101")
+    res = eng.infer(img, confidence=0.3, want_instances=True)
     for i in (0, 3):
         f = taps["fpn"][i]
         got = eng.read_tap(f"fpn{i}", (f.shape[2], f.shape[3], 256)).transpose(2, 0, 1)
@@ -189,6 +196,63 @@ def test_solo_r101_720p_matches_oracle():
         assert m < 1e-2 and l2 < 4e-3, (f"fpn{i}", m, l2)   # 33 bottlenecks of fp16 maps
     eng.close()
     check_instances(res, scores, labels, masks, min_match=0.8, tag="r101 720p")
+
+
+def check_instances_exact(res, scores, labels, masks, tag=""):
+    """north_star: mask ids bit-exact.  The fp32-class engine ("-exact": backbone, FPN, head and decode all in 3xTF32 with
+    fp32 accumulation) must reproduce the oracle's instance list itself: same count, same labels in the same order, scores to
+    fp32 summation-order accuracy, and masks that differ in at most a 1e-5 fraction of their bits (two fp32 implementations
+    that add in a different order differ the same way at pixels whose mask logit sits within 1e-6 of the threshold)."""
+    n_ref = len(scores)
+    assert len(res["scores"]) == n_ref, (len(res["scores"]), n_ref)
+    assert np.array_equal(res["labels"], np.asarray(labels, dtype=res["labels"].dtype)), "labels / order differ"
+    serr = np.abs(res["scores"] - np.asarray(scores, np.float32)) / np.maximum(np.asarray(scores, np.float32), 1e-6)
+    ref_m = masks.numpy().reshape(n_ref, -1).astype(bool)
+    got_m = res["masks"].reshape(n_ref, -1)
+    bits = int((ref_m != got_m).sum())
+    print(f"{tag} exact: {n_ref} instances, labels equal in order, score rel err max {serr.max() if n_ref else 0:.2e}, "
+          f"{bits} of {ref_m.size} mask bits differ")
+    assert (serr.max() if n_ref else 0.0) <= 5e-5
+    assert bits <= max(8, int(1e-5 * ref_m.size)), (bits, ref_m.size)
+    return bits
+
+
+@pytest.mark.gpu
+def test_solo_tiny_exact_backbone_reproduces_the_oracle_instances():
+    """End to end (frame -> instances) on the test-size twin with the fp32-class backbone: FPN levels to 1e-5, instances exact."""
+    from prisma_b200.mask import SoloV2Engine
+    sd = make_solo_weights("tiny", 0)
+    eng = SoloV2Engine(sd, variant="tiny-exact")
+    img = synthetic_frame(240, 320, 0)
+    res = eng.infer(img, confidence=0.5, want_instances=True)
+    taps = {}
+    scores, labels, masks = osolo.solo_infer(sd, img, "tiny", taps)
+    for i, f in enumerate(taps["fpn"]):
+        got = eng.read_tap(f"fpn{i}", (f.shape[2], f.shape[3], 256)).transpose(2, 0, 1)
+        m, l2 = rel(got, f[0].numpy())
+        print(f"tiny-exact fpn{i}: max rel {m:.2e} l2 rel {l2:.2e}")
+        assert m < 2e-5 and l2 < 5e-6, (f"fpn{i}", m, l2)
+    eng.close()
+    check_instances_exact(res, scores, labels, masks, tag="tiny-exact 240x320")
+    ref_union = osolo.band_union(scores, labels, masks, 0.5)[..., 0]
+    assert (res["union"] != ref_union).mean() <= 1e-5
+
+
+@pytest.mark.gpu
+def test_solo_r101_exact_backbone_720p_reproduces_the_oracle_instances(r101_oracle):
+    """The real config (ResNet-101, 33 bottlenecks) with the fp32-class backbone: the instance list of the oracle itself."""
+    from prisma_b200.mask import SoloV2Engine
+    sd, img, taps, scores, labels, masks = r101_oracle
+    eng = SoloV2Engine(sd, variant="r101-exact")
+    res = eng.infer(img, confidence=0.3, want_instances=True)
+    for i in (0, 3):
+        f = taps["fpn"][i]
+        got = eng.read_tap(f"fpn{i}", (f.shape[2], f.shape[3], 256)).transpose(2, 0, 1)
+        m, l2 = rel(got, f[0].numpy())
+        print(f"r101-exact fpn{i}: max rel {m:.2e} l2 rel {l2:.2e}  ({res['ms']:.2f} ms per frame)")
+        assert m < 1e-4 and l2 < 5e-5, (f"fpn{i}", m, l2)   # 100 convs deep: the summation-order differences add up
+    eng.close()
+    check_instances_exact(res, scores, labels, masks, tag="r101-exact 720p")
 
 
 @pytest.mark.gpu
