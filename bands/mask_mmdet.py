@@ -50,9 +50,10 @@ def init_model():
     global model
     from prisma_b200.mask import SoloV2Lanes
     lanes = getattr(args, "lanes", 4) if is_video(getattr(args, "output", "") or "") else 1   # a still image needs one engine
-    # precision: "fast" = fp16 backbone + fp16 head; default = fp16 backbone + fp32-class head and decode; "exact" = the whole
-    # network in fp32-class arithmetic (3xTF32, fp32 accumulation): the reference's instance list itself, ~3x the GPU time
-    variant = "r101" + {"fast": "-fast", "exact": "-exact"}.get(getattr(args, "precision", "default"), "")
+    # precision: "exact" (default) = the whole network in fp32-class arithmetic (3xTF32, fp32 accumulation): the reference's
+    # instance list itself (north_star: mask ids bit-exact); "mixed" = fp16 backbone + fp32-class head and decode (half the GPU
+    # time, instances at the 0.05 score filter may differ); "fast" = fp16 everywhere
+    variant = "r101" + {"fast": "-fast", "exact": "-exact"}.get(getattr(args, "precision", "exact"), "")
     model = SoloV2Lanes(_load_state_dict(args), device=args.device, lanes=lanes, variant=variant)
     return model
 
@@ -125,8 +126,8 @@ def build_parser():
     p.add_argument("--weights", type=str, default="", help="mmdet SOLOv2 checkpoint (.pth/.npz)")
     p.add_argument("--seeded-weights", action="store_true", help="seeded random weights (offline testing)")
     p.add_argument("--device", type=int, default=DEVICE)
-    p.add_argument("--precision", choices=("fast", "default", "exact"), default="default",
-                   help="fast: fp16 everywhere; default: fp16 backbone, fp32-class head + decode; exact: fp32-class everywhere")
+    p.add_argument("--precision", choices=("fast", "mixed", "exact"), default="exact",
+                   help="exact: fp32-class everywhere (the reference's instances); mixed: fp16 backbone, fp32-class head + decode; fast: fp16")
     p.add_argument("--lanes", type=int, default=4, help="engines per GPU that take consecutive frames concurrently (video)")
     p.add_argument("--gpus", type=int, default=1, help="shard the frames of a video over this many GPUs (one worker each)")
     p.add_argument("--device-list", type=str, default="", help="GPU ordinals of the workers (default 0..gpus-1)")

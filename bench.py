@@ -219,25 +219,31 @@ def zoe_extras(device):
 
 def mask_extras(device):
     """The mask band (SOLOv2 R-101) on synthetic 1080p frames: host frame in, union mask + instance list out (H2D / D2H
-    inside the wall time; `ms` is the device time of the pass)."""
+    inside the wall time; `ms` is the device time of the pass).  Three arithmetic variants of the same engine: "exact" (the
+    band's default: the whole network in fp32-class 3xTF32, reproduces the oracle's instance list), "mixed" (fp16 backbone,
+    fp32-class head + decode), "fast" (fp16 everywhere)."""
     from prisma_b200.mask import SoloV2Engine
     from prisma_b200.seeded_weights import make_solo_weights
     from prisma_b200.synthetic import synthetic_frame
-    eng = SoloV2Engine(make_solo_weights("r101", 0), device=device)
+    sd = make_solo_weights("r101", 0)
     f = [synthetic_frame(1080, 1920, t) for t in range(2)]
-    for i in range(3):
-        eng.infer(f[i % 2])
-    n, dev_ms = 8, 0.0
-    t0 = time.perf_counter()
-    for i in range(n):
-        dev_ms += eng.infer(f[i % 2])["ms"]
-    e2e_s = time.perf_counter() - t0
-    w = eng.work(1080, 1920)
-    eng.close()
-    return {"workload": "synthetic 1080p frames, mask_mmdet SOLOv2 R-101 (768x1344 net input), one frame per pass",
-            "frames_per_s_device": n / (dev_ms * 1e-3), "frames_per_s_e2e": n / e2e_s, "ms_per_pass_device": dev_ms / n,
-            "algorithmic_gflop_per_pass": w["flop"] / 1e9, "tflops": w["flop"] / (dev_ms / n * 1e-3) / 1e12,
-            "launches_per_pass": w["launches"]}
+    out = {"workload": "synthetic 1080p frames, mask_mmdet SOLOv2 R-101 (768x1344 net input), one frame per pass, one lane"}
+    for name, variant in (("exact", "r101-exact"), ("mixed", "r101"), ("fast", "r101-fast")):
+        eng = SoloV2Engine(sd, device=device, variant=variant)
+        for i in range(3):
+            eng.infer(f[i % 2])
+        n, dev_ms = 8, 0.0
+        t0 = time.perf_counter()
+        for i in range(n):
+            dev_ms += eng.infer(f[i % 2])["ms"]
+        e2e_s = time.perf_counter() - t0
+        w = eng.work(1080, 1920)
+        eng.close()
+        out[name] = {"frames_per_s_device": n / (dev_ms * 1e-3), "frames_per_s_e2e": n / e2e_s, "ms_per_pass_device": dev_ms / n,
+                     "algorithmic_gflop_per_pass": w["flop"] / 1e9, "tflops": w["flop"] / (dev_ms / n * 1e-3) / 1e12,
+                     "launches_per_pass": w["launches"]}
+    out.update({k: out["exact"][k] for k in ("frames_per_s_device", "frames_per_s_e2e", "ms_per_pass_device")})
+    return out
 
 
 def depth_720p_extras(eng):

@@ -273,6 +273,17 @@ int prisma_debug_gemm(int device, const float* A, const float* W, const float* b
     ep.out_f16_ld = N;
     ep.tma_store = true;
   }
+  if (act == -6 || act == -7) {  // TMA-store epilogue, fp16 destination with bias + GELU (-6) / ReLU (-7): the ViT qkv / fc1 path
+    PRISMA_CHECK(N % 8 == 0, "debug gemm: the fp16 TMA-store path needs N % 8 == 0");
+    dH = sc.alloc<__half>((size_t)M * N);
+    PRISMA_CHECK(dH != nullptr, "cudaMalloc failed");
+    PRISMA_CUDA_OK(cudaMemset(dH, 0xFF, (size_t)M * N * 2));
+    ep.act = act == -6 ? 1 : 2;
+    ep.out_f32 = nullptr;
+    ep.out_f16 = dH;
+    ep.out_f16_ld = N;
+    ep.tma_store = true;
+  }
   if (act == -3) {  // micro-benchmark of the residual-stream epilogue: D += acc in place (fp32 read + write)
     ep.res_f32 = dD;
     ep.res_f32_ld = N;
@@ -282,7 +293,7 @@ int prisma_debug_gemm(int device, const float* A, const float* W, const float* b
   const int off[1] = {0};
   PRISMA_TRY(gemm_prepare(&g, dA, M, K, Kp, dW, Nw, M, N, 1, off, ep, sms, force_bn));
   PRISMA_TRY(timed(0, iters > 0 ? iters : 1, ms_out, [&]() { return gemm_run(g, 0); }));
-  if (act == -5) {
+  if (act == -5 || act == -6 || act == -7) {
     std::vector<__half> hd((size_t)M * N);
     PRISMA_CUDA_OK(cudaMemcpy(hd.data(), dH, hd.size() * 2, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < hd.size(); ++i) Dout[i] = __half2float(hd[i]);

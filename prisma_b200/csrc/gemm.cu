@@ -166,8 +166,8 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   else if (!force_bn && !swap_off && !tf32 && cg == 1 && bn == 128 && N <= 128 && M >= 4096 && !ep.tma_store && !ep.head_w && !ep.m_dev) swap = true;
   else {
     // 64 output columns: the same transposed tile with the upper 64 weight rows zero (they must exist: w_rows >= 128) -- twice
-    // the MMA work of a 128 x 64 tile, but half the instructions, barriers and TMA boxes per output row.  PRISMA_GEMM_SWAP64=1.
-    static const bool swap64 = [] { const char* e = getenv("PRISMA_GEMM_SWAP64"); return e && e[0] == '1'; }();
+    // the MMA work of a 128 x 64 tile, but half the instructions, barriers and TMA boxes per output row (RAFT pass 6.73 -> 6.57 ms per pair).  PRISMA_GEMM_SWAP64=0: off.
+    static const bool swap64 = [] { const char* e = getenv("PRISMA_GEMM_SWAP64"); return !(e && e[0] == '0'); }();
     if (swap64 && !force_bn && !swap_off && !tf32 && cg == 1 && bn == 64 && N > 32 && N <= 64 && w_rows >= 128 && M >= 4096 &&
         !ep.tma_store && !ep.head_w && !ep.m_dev) { bn = 128; swap = true; }
   }
@@ -251,9 +251,12 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   out->tma_store = false;
   out->tmD = out->tmA;
   if (ep.tma_store) {
-    PRISMA_CHECK((ep.out_f32 != nullptr) != (ep.out_f16 != nullptr) && !ep.out_f16_relu && !ep.bias && !ep.gamma && ep.act == 0 &&
+    PRISMA_CHECK((ep.out_f32 != nullptr) != (ep.out_f16 != nullptr) && !ep.out_f16_relu && !ep.gamma && !ep.pre_f32 && !ep.gru &&
                      !ep.res_f32 && !ep.res_a && !ep.res_b && ep.row_map == ROW_LINEAR && !ep.head_w && !ep.stat_part,
                  "gemm: the TMA-store epilogue handles one scaled dense output (fp32 or fp16) only");
+    PRISMA_CHECK(ep.out_f16 ? (ep.act >= 0 && ep.act <= 2) : (!ep.bias && ep.act == 0),
+                 "gemm: the TMA-store epilogue applies bias / GELU / ReLU for fp16 destinations only");
+    PRISMA_CHECK(!ep.out_f16 || N % 8 == 0, "gemm: the fp16 TMA-store epilogue needs N % 8 == 0");
     PRISMA_CHECK(bn >= 128, "gemm: the TMA-store epilogue is built for BLOCK_N 128 / 256");
     if (ep.out_f16) PRISMA_TRY(make_tmap_2d_f16_store(&out->tmD, ep.out_f16, (uint64_t)N, (uint64_t)M, (uint64_t)ep.out_f16_ld));
     else PRISMA_TRY(make_tmap_2d_f32(&out->tmD, ep.out_f32, (uint64_t)N, (uint64_t)M, (uint64_t)ep.out_f32_ld, 32, 32));

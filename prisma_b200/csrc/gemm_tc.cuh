@@ -86,7 +86,8 @@ struct GemmEpilogue {
   // Row count known only on the device (SOLOv2: the number of candidates of this frame): when set, only the first
   // round_up(*m_dev, 128) rows of the output space are computed (the launch is sized for the capacity M).
   const int* m_dev = nullptr;
-  // dense output (row_map LINEAR, scale only; out_f32 or out_f16) stored by TMA: tcgen05.ld -> swizzled smem box -> cp.async.bulk.tensor
+  // dense output (row_map LINEAR; out_f32: scale only; out_f16: scale, bias, GELU / ReLU) stored by TMA: tcgen05.ld ->
+  // registers (row per lane) -> swizzled smem box -> cp.async.bulk.tensor
   bool tma_store = false;
   // ConvGRU gate arithmetic in the epilogue of the gate convs (raft/update.py:54-58), all fp32, indexed by dst row:
   //  gru == 1 (the z | r conv, N = 256, act sigmoid): columns [0,128) = z -> out_f32 as usual; columns [128,256) = r are not
@@ -703,12 +704,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint32_t r[32];
               tmem_ld32(taddr + c0, r);
               tmem_ld_wait();
+              const int ncol = n0 + c0;  // column of r[0]; every lane holds the same 32 columns of its own row
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint32_t h0 = pack_half2(__uint_as_float(r[8 * j]) * ep.alpha, __uint_as_float(r[8 * j + 1]) * ep.alpha);
-                const uint32_t h1 = pack_half2(__uint_as_float(r[8 * j + 2]) * ep.alpha, __uint_as_float(r[8 * j + 3]) * ep.alpha);
-                const uint32_t h2 = pack_half2(__uint_as_float(r[8 * j + 4]) * ep.alpha, __uint_as_float(r[8 * j + 5]) * ep.alpha);
-                const uint32_t h3 = pack_half2(__uint_as_float(r[8 * j + 6]) * ep.alpha, __uint_as_float(r[8 * j + 7]) * ep.alpha);
+                // bias (the same addresses in every lane: one broadcast transaction) + GELU / ReLU in the row-per-lane layout
+                float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+                if (ep.bias != nullptr && ncol + 8 * j + 8 <= args.N) {
+                  ba = __ldg(reinterpret_cast<const float4*>(ep.bias + ncol + 8 * j));
+                  bb = __ldg(reinterpret_cast<const float4*>(ep.bias + ncol + 8 * j + 4));
+                }
+                float x[8] = {fmaf(__uint_as_float(r[8 * j]), ep.alpha, ba.x),     fmaf(__uint_as_float(r[8 * j + 1]), ep.alpha, ba.y),
+                              fmaf(__uint_as_float(r[8 * j + 2]), ep.alpha, ba.z), fmaf(__uint_as_float(r[8 * j + 3]), ep.alpha, ba.w),
+                              fmaf(__uint_as_float(r[8 * j + 4]), ep.alpha, bb.x), fmaf(__uint_as_float(r[8 * j + 5]), ep.alpha, bb.y),
+                              fmaf(__uint_as_float(r[8 * j + 6]), ep.alpha, bb.z), fmaf(__uint_as_float(r[8 * j + 7]), ep.alpha, bb.w)};
+                if (ep.act == 1) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) x[q] = gelu_erf(x[q]);
+                } else if (ep.act == 2) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) x[q] = fmaxf(x[q], 0.f);
+                }
+                const uint32_t h0 = pack_half2(x[0], x[1]), h1 = pack_half2(x[2], x[3]), h2 = pack_half2(x[4], x[5]), h3 = pack_half2(x[6], x[7]);
                 sts128(buf + lane * 128 + (((hf * 4 + j) ^ (lane & 7)) << 4), __uint_as_float(h0), __uint_as_float(h1),
                        __uint_as_float(h2), __uint_as_float(h3));
               }

@@ -109,6 +109,27 @@ def test_gemm_tma_store_epilogue_fp16(M, N, K, bn):
     assert err <= 6e-4 * max(1.0, np.abs(ref).max()), f"max abs err {err}"   # one fp16 rounding: 2^-11 relative
 
 
+@pytest.mark.parametrize("M,N,K,act,bn", [
+    (29316, 4096, 1024, -6, 0),   # ViT-L fc1 at 12 frames: CTA pairs, ragged M, tail tiles, bias + GELU
+    (2443, 3072, 1024, -7, 0),    # qkv-like, bias + ReLU
+    (700, 328, 200, -6, 128),     # single CTAs, N % 64 = 8: the last 64-column box is clipped to 8 columns, K tail
+])
+def test_gemm_tma_store_epilogue_fp16_bias_activation(M, N, K, act, bn):
+    """The fp16 TMA-store epilogue of the ViT qkv / fc1 linears: bias and GELU / ReLU applied in the row-per-lane registers,
+    then 32 x 64-column bulk stores; every element of [M][N] written, boxes clipped at the ragged edges."""
+    rng = np.random.default_rng(M + N + K + 2)
+    A = rng.standard_normal((M, K), dtype=np.float32)
+    W = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N, dtype=np.float32)
+    got = _gemm(A, W, bias, act, bn)
+    assert np.isfinite(got).all()
+    rows = np.unique(np.concatenate([np.arange(0, min(M, 300)), np.arange(max(0, M - 300), M), rng.integers(0, M, 200)]))
+    ref = torch.from_numpy(_h(A[rows])) @ torch.from_numpy(_h(W)).T + torch.from_numpy(bias)
+    ref = (torch.nn.functional.gelu(ref) if act == -6 else torch.relu(ref)).numpy()
+    err = np.abs(got[rows] - ref).max()
+    assert err <= 6e-4 * max(1.0, np.abs(ref).max()), f"max abs err {err}"   # one fp16 rounding: 2^-11 relative
+
+
 @pytest.mark.parametrize("H,W,Cin,Cout,k,relu", [
     (37, 66, 64, 64, 3, 1),
     (19, 33, 384, 64, 3, 0),

@@ -30,3 +30,19 @@ if which in ("corr",):
     assert l.prisma_flowcorr_build(h, 2, C.byref(ms)) == 0
     work = (C.c_double * 2)(); l.prisma_flowcorr_work(h, work)
     print("corr build ms", ms.value, "GB/s", work[1] / ms.value / 1e6, "TF", work[0] / ms.value / 1e9)
+if which in ("gemm_tma",):
+    # fc1 of a 12-frame pass through the TMA-store epilogue (bias + GELU in registers, bulk stores): act -6
+    M, N, K = 29316, 4096, 1024
+    A = rng.standard_normal((M, K), dtype=np.float32)
+    W = (rng.standard_normal((N, K), dtype=np.float32) / 32).astype(np.float32)
+    b = np.zeros(N, np.float32); D = np.empty((M, N), np.float32); ms = C.c_float()
+    assert l.prisma_debug_gemm(0, fptr(A), fptr(W), fptr(b), fptr(D), M, N, K, -6, 0, 3, C.byref(ms)) == 0
+    print("gemm fc1 tma-store", M, N, K, "ms", ms.value, "TF", 2.0 * M * N * K / ms.value / 1e9)
+if which in ("gemm_swap",):
+    # the RAFT GRU q-conv size class (N = 128, K = 1920, 8 waves) on the transposed tiles
+    M, N, K = 148 * 8 * 128, 128, 1920
+    A = np.ones((M, K), np.float32); A[::7] = 0.5
+    W = (rng.standard_normal((N, K), dtype=np.float32) / 32).astype(np.float32)
+    b = np.zeros(N, np.float32); D = np.empty((M, N), np.float32); ms = C.c_float()
+    assert l.prisma_debug_gemm(0, fptr(A), fptr(W), fptr(b), fptr(D), M, N, K, -2, 0, 3, C.byref(ms)) == 0
+    print("gemm swap", M, N, K, "ms", ms.value, "TF", 2.0 * M * N * K / ms.value / 1e9)
