@@ -153,7 +153,7 @@ def run_reference(args, rank, world):
 
 def measured_traffic():
     """DRAM bytes per launch of the profiled kernels from the committed ncu --set full captures (profiles/)."""
-    for name in ("r02_traffic.json", "r01_traffic.json"):
+    for name in ("r02c_traffic.json", "r02_traffic.json", "r01_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f)

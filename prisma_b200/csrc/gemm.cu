@@ -265,18 +265,18 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   return 0;
 }
 
-template <int BN, int CG, bool TMAST = false, bool TF32 = false, bool XACC = false, bool SWAP = false>
+template <int BN, int CG, bool TMAST = false, bool TF32 = false, bool XACC = false, bool SWAP = false, int EW = GEMM_EPI_WARPS>
 static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
   static bool attr_set = false;  // per-process, per-instantiation
-  using Cfg = GemmCfg<BN, CG, TMAST, SWAP>;
+  using Cfg = GemmCfg<BN, CG, TMAST, SWAP, EW>;
   if (!attr_set) {
-    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, TMAST, TF32, XACC, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PRISMA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, TMAST, TF32, XACC, SWAP, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -293,7 +293,7 @@ static int launch_bn(const GemmLaunch& g, cudaStream_t stream) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, TMAST, TF32, XACC, SWAP>, g.tmA, g.tmB, g.tmBt, g.tmD, g.args));
+    PRISMA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, TMAST, TF32, XACC, SWAP, EW>, g.tmA, g.tmB, g.tmBt, g.tmD, g.args));
   }
   PRISMA_CUDA_OK(cudaGetLastError());
   return 0;
@@ -318,6 +318,24 @@ int gemm_run(const GemmLaunch& g, cudaStream_t stream) {
     }
     set_last_error("gemm_run: unsupported BLOCK_N (tf32)");
     return -1;
+  }
+  // 16 epilogue warps for the plain fp16 kernels (GemmCfg EW).
+  // Measured (same box, whole bench step): 16 warps everywhere: RAFT convs 4.53 -> 4.34 ms per pair but DA linears 16.7 ->
+  // 17.4 ms per pass and head convs 7.05 -> 7.38 (the 256-wide tiles lose an operand stage and spill 270 bytes per thread at the
+  // 96 registers ptxas then allocates).  Default: 16 for the transposed / narrow tiles, 8 for the 256-wide ones;
+  // PRISMA_GEMM_EW=8 / 16 forces one value everywhere.
+  static const int ew_env = [] { const char* e = getenv("PRISMA_GEMM_EW"); return e ? atoi(e) : 0; }();
+  const int ew = ew_env ? ew_env : ((g.swap || (g.cg == 1 && g.bn <= 128)) ? 16 : 8);
+  if (ew == 16 && !g.tma_store) {
+    if (g.swap) return launch_bn<128, 1, false, false, false, true, 16>(g, stream);
+    if (g.cg == 2 && g.bn == 256) return launch_bn<256, 2, false, false, false, false, 16>(g, stream);
+    if (g.cg == 1) {
+      switch (g.bn) {
+        case 256: return launch_bn<256, 1, false, false, false, false, 16>(g, stream);
+        case 128: return launch_bn<128, 1, false, false, false, false, 16>(g, stream);
+        case 64: return launch_bn<64, 1, false, false, false, false, 16>(g, stream);
+      }
+    }
   }
   if (g.swap) return launch_bn<128, 1, false, false, false, true>(g, stream);
   if (g.tma_store) {

@@ -23,8 +23,9 @@ namespace prisma {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 8;                          // two per TMEM lane quarter
+constexpr int GEMM_EPI_WARPS = 8;                          // two per TMEM lane quarter (EW template parameter: 8 or 16)
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;      // + TMA producer warp + MMA warp
+constexpr int GEMM_SMEM_MAX = 232448;                       // 227 KB of dynamic shared memory per CTA
 constexpr int GEMM_MAX_TAPS = 49;
 
 enum RowMap : int {
@@ -127,17 +128,24 @@ struct GemmArgs {
 // are the N operand of one instruction, the accumulator holds channels in its lanes and pixels in its columns, and the
 // epilogue transposes through its staging buffer (which it does anyway).  Half the instructions, barriers and TMA boxes
 // per FLOP; the operand bytes per FLOP drop by a quarter.
-template <int BN, int CG = 1, bool TMAST = false, bool SWAP = false>  // CG = CTAs per MMA (cta_group): 2 = a CTA pair computes a 256 x BN tile, each loading half of W
+// EW: epilogue warps (EW / 4 per TMEM lane quarter, taking every (EW / 4)-th 32-column chunk).  The epilogue is latency-bound
+// (ncu on fc1: issue slots 25 % busy, long-scoreboard / wait stalls) and paces the kernel, so the fp16 kernels can
+// run 16 of them: half the chunks per warp; the register cap drops to 112 per thread and one operand stage is given up for
+// the staging buffers.
+template <int BN, int CG = 1, bool TMAST = false, bool SWAP = false, int EW = GEMM_EPI_WARPS>  // CG = CTAs per MMA (cta_group): 2 = a CTA pair computes a 256 x BN tile, each loading half of W
 struct GemmCfg {                                   // TMAST: TMA-store epilogue (double-buffered staging, one operand stage fewer)
   static constexpr int A_ROWS = SWAP ? 256 : GEMM_BM;   // activation rows per tile and CTA
   static constexpr int ACC_COLS = SWAP ? 256 : BN;      // TMEM columns of one accumulator stage
   static constexpr int A_BYTES = A_ROWS * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = ((STAGE_BYTES >= 49152) ? 4 : (STAGE_BYTES >= 32768 ? 6 : 7)) - (TMAST ? 1 : 0);
+  static constexpr int STG_BYTES = EW * 32 * 32 * 4 * (TMAST ? 2 : 1);  // epilogue staging: 32x32 fp32 per warp (x2 buffers)
+  static constexpr int FIT = (GEMM_SMEM_MAX - STG_BYTES - 1280) / STAGE_BYTES;  // operand stages that fit beside the staging
+  static constexpr int STAGES = FIT > 7 ? 7 : FIT;
+  static constexpr int THREADS = 64 + 32 * EW;
   static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
-  static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * 32 * 4 * (TMAST ? 2 : 1);  // epilogue staging: 32x32 fp32 per warp (x2 buffers)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(STAGES >= 3, "too few operand stages");
 };
 
 #ifdef __CUDACC__
@@ -286,14 +294,16 @@ __device__ __forceinline__ void epilogue_rows8(const GemmEpilogue& ep, float4 (&
   }
 }
 
-template <int BN, int CG, bool TMAST, bool TF32, bool XACC, bool SWAP = false>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int CG, bool TMAST, bool TF32, bool XACC, bool SWAP = false, int EW = GEMM_EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmD,
                const __grid_constant__ GemmArgs args) {
   static_assert(!SWAP || (BN == 128 && CG == 1 && !TMAST && !TF32 && !XACC), "SWAP: 128 output channels x 256 pixel rows, fp16, one CTA");
-  using Cfg = GemmCfg<BN, CG, TMAST, SWAP>;
+  static_assert(EW == 8 || (EW == 16 && !TMAST && !TF32 && !XACC), "16 epilogue warps: the plain fp16 kernels only");
+  using Cfg = GemmCfg<BN, CG, TMAST, SWAP, EW>;
   constexpr int ACC = Cfg::ACC_COLS;
+  constexpr int CSTEP = 32 * (EW / 4);  // column distance between the chunks one warp takes
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BKE = TF32 ? 32 : 64;  // elements per 128-byte K block (fp32 containers for kind::tf32, fp16 otherwise)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -338,7 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], GEMM_EPI_WARPS * CG); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EW * CG); }
     fence_mbar_init();
   }
   if (warp == 1) { if (CG == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); else tmem_alloc(tmem_slot, Cfg::TMEM_COLS); }
@@ -446,7 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------------ epilogue warps (2..9)
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
-    const int chunk_par = (warp - 2) >> 2;  // the two warps of a quarter take even / odd 32-column chunks
+    const int chunk_par = (warp - 2) >> 2;  // the EW / 4 warps of a quarter take every (EW / 4)-th 32-column chunk
     const GemmEpilogue& ep = args.ep;
     const uint32_t stg = smem_u32(stg_all) + (warp - 2) * (TMAST ? 8192 : 4096);
     uint32_t st_cnt = 0;  // TMAST: chunks stored so far by this warp (staging buffer parity)
@@ -679,7 +689,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (SWAP) {
         // this warp: output columns n0 + quarter * 32 .. + 31 (TMEM lanes), alternate 32-pixel chunks (TMEM columns)
 #pragma unroll 1
-        for (int c0 = chunk_par * 32; c0 < 256; c0 += 64) {
+        for (int c0 = chunk_par * 32; c0 < 256; c0 += CSTEP) {
           if (m0 + c0 >= args.M || n0 + quarter * 32 >= args.N || args.dbg_mode == 2 || args.dbg_mode == 3 || args.dbg_mode == 6) break;  // warp-uniform
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
@@ -743,7 +753,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else
 #pragma unroll 1
-      for (int c0 = chunk_par * 32; c0 < bw; c0 += 64) {
+      for (int c0 = chunk_par * 32; c0 < bw; c0 += CSTEP) {
         if (n0 + c0 >= args.N || args.dbg_mode == 2 || args.dbg_mode == 3 || args.dbg_mode == 6) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
