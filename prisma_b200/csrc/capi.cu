@@ -284,6 +284,12 @@ int prisma_debug_gemm(int device, const float* A, const float* W, const float* b
     ep.out_f16_ld = N;
     ep.tma_store = true;
   }
+  if (act == -8) {  // in-place fp32 residual through the TMA reduce-add epilogue: D (zeros) += acc + bias, once per launch
+    ep.res_f32 = dD;
+    ep.res_f32_ld = N;
+    ep.tma_store = true;
+    PRISMA_CUDA_OK(cudaMemset(dD, 0, (size_t)M * N * 4));
+  }
   if (act == -3) {  // micro-benchmark of the residual-stream epilogue: D += acc in place (fp32 read + write)
     ep.res_f32 = dD;
     ep.res_f32_ld = N;

@@ -142,7 +142,7 @@ int gemm_prepare_tf32x3(GemmLaunch* out, const float* A_split, long long a_rows,
 }
 
 static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, int a_cols, int a_pitch, const void* W,
-                             int w_rows, int M, int N, int taps, const int* tap_off, const int* tap_acol, const GemmEpilogue& ep,
+                             int w_rows, int M, int N, int taps, const int* tap_off, const int* tap_acol, const GemmEpilogue& ep_in,
                              int num_sms, int force_bn, bool tf32) {
   PRISMA_CHECK(taps >= 1 && taps <= GEMM_MAX_TAPS, "gemm: bad tap count");
   PRISMA_CHECK(N % 4 == 0, "gemm: N must be a multiple of 4");
@@ -150,6 +150,10 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   // force_bn == 512 requests the CTA-pair kernel (256 x 256 tiles); otherwise it is chosen for large problems
   static const bool pairs_off = [] { const char* e = getenv("PRISMA_GEMM_PAIRS"); return e && e[0] == '0'; }();
   int bn = force_bn ? force_bn : gemm_pick_bn(M, N, num_sms);
+  // the TMA-store epilogue exists for 128- and 256-wide tiles; a problem the tile choice gives narrower tiles keeps the
+  // register epilogue (same results: the TMA path is an optimisation of the same arithmetic)
+  GemmEpilogue ep = ep_in;
+  if (ep.tma_store && (bn == 32 || bn == 64) && !tf32) ep.tma_store = false;
   int cg = 1;
   static const bool pair128 = [] { const char* e = getenv("PRISMA_GEMM_PAIR128"); return e && e[0] == '1'; }();
   if (bn == 512) { bn = 256; cg = 2; }
@@ -251,11 +255,15 @@ static int gemm_prepare_impl(GemmLaunch* out, const void* A, long long a_rows, i
   out->tma_store = false;
   out->tmD = out->tmA;
   if (ep.tma_store) {
-    PRISMA_CHECK((ep.out_f32 != nullptr) != (ep.out_f16 != nullptr) && !ep.out_f16_relu && !ep.gamma && !ep.pre_f32 && !ep.gru &&
-                     !ep.res_f32 && !ep.res_a && !ep.res_b && ep.row_map == ROW_LINEAR && !ep.head_w && !ep.stat_part,
+    PRISMA_CHECK((ep.out_f32 != nullptr) != (ep.out_f16 != nullptr) && !ep.out_f16_relu && !ep.pre_f32 && !ep.gru &&
+                     !ep.res_a && !ep.res_b && ep.row_map == ROW_LINEAR && !ep.head_w && !ep.stat_part,
                  "gemm: the TMA-store epilogue handles one scaled dense output (fp32 or fp16) only");
-    PRISMA_CHECK(ep.out_f16 ? (ep.act >= 0 && ep.act <= 2) : (!ep.bias && ep.act == 0),
-                 "gemm: the TMA-store epilogue applies bias / GELU / ReLU for fp16 destinations only");
+    PRISMA_CHECK(ep.out_f16 ? (ep.act >= 0 && ep.act <= 2 && !ep.gamma && !ep.res_f32) : ep.act == 0,
+                 "gemm: the TMA-store epilogue applies bias + GELU / ReLU (fp16 destinations) or bias + LayerScale (fp32) only");
+    // an fp32 residual must be the destination itself (x += ...): it becomes a TMA reduce-add
+    PRISMA_CHECK(!ep.res_f32 || (ep.res_f32 == ep.out_f32 && ep.res_f32_ld == ep.out_f32_ld),
+                 "gemm: the TMA-store epilogue adds a residual only in place");
+    out->args.ep.tma_reduce = ep.res_f32 != nullptr;
     PRISMA_CHECK(!ep.out_f16 || N % 8 == 0, "gemm: the fp16 TMA-store epilogue needs N % 8 == 0");
     PRISMA_CHECK(bn >= 128, "gemm: the TMA-store epilogue is built for BLOCK_N 128 / 256");
     if (ep.out_f16) PRISMA_TRY(make_tmap_2d_f16_store(&out->tmD, ep.out_f16, (uint64_t)N, (uint64_t)M, (uint64_t)ep.out_f16_ld));

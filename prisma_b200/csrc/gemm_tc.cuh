@@ -90,6 +90,10 @@ struct GemmEpilogue {
   // dense output (row_map LINEAR; out_f32: scale only; out_f16: scale, bias, GELU / ReLU) stored by TMA: tcgen05.ld ->
   // registers (row per lane) -> swizzled smem box -> cp.async.bulk.tensor
   bool tma_store = false;
+  // set by gemm_prepare when tma_store is asked for an in-place fp32 residual update (res_f32 == out_f32: the ViT proj / fc2
+  // linears, x += gamma (acc + bias)): the staged box leaves through cp.reduce.async.bulk.tensor ... .add.f32 -- the add is
+  // done by the L2 (one round-to-nearest fp32 add per element, as the register path does); the epilogue reads nothing
+  bool tma_reduce = false;
   // ConvGRU gate arithmetic in the epilogue of the gate convs (raft/update.py:54-58), all fp32, indexed by dst row:
   //  gru == 1 (the z | r conv, N = 256, act sigmoid): columns [0,128) = z -> out_f32 as usual; columns [128,256) = r are not
   //            stored: r * h (gru_h: fp32 [rows][128]) goes to gru_rh (fp16, pitch gru_rh_ld) -- the q conv's operand;
@@ -539,17 +543,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // so the store of chunk i reads shared memory while chunk i + 1 is being staged
           const uint32_t buf = stg + (st_cnt & 1) * 4096;
           if (st_cnt >= 2) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
+          if (ep.bias == nullptr && ep.gamma == nullptr) {
+            // scale only (the correlation volume): keep this path minimal -- it is store-bound and every extra instruction
+            // per element showed (0.75 -> 0.86 ms per pair when the bias / LayerScale code ran unconditionally)
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(buf + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]) * ep.alpha, __uint_as_float(r[4 * j + 1]) * ep.alpha,
-                   __uint_as_float(r[4 * j + 2]) * ep.alpha, __uint_as_float(r[4 * j + 3]) * ep.alpha);
+            for (int j = 0; j < 8; ++j)
+              sts128(buf + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]) * ep.alpha, __uint_as_float(r[4 * j + 1]) * ep.alpha,
+                     __uint_as_float(r[4 * j + 2]) * ep.alpha, __uint_as_float(r[4 * j + 3]) * ep.alpha);
+          } else {
+            const int ncol = n0 + c0;  // column of r[0]; bias / LayerScale: the same addresses in every lane (broadcast loads)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (ncol + 4 * j + 4 <= args.N) {
+                if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + ncol + 4 * j));
+                if (ep.gamma != nullptr) g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + ncol + 4 * j));
+              }
+              sts128(buf + lane * 128 + ((j ^ (lane & 7)) << 4), fmaf(__uint_as_float(r[4 * j]), ep.alpha, b4.x) * g4.x,
+                     fmaf(__uint_as_float(r[4 * j + 1]), ep.alpha, b4.y) * g4.y, fmaf(__uint_as_float(r[4 * j + 2]), ep.alpha, b4.z) * g4.z,
+                     fmaf(__uint_as_float(r[4 * j + 3]), ep.alpha, b4.w) * g4.w);
+            }
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(&tmD)),
-                         "r"(buf), "r"(n0 + c0), "r"(m0 + quarter * 32)
-                         : "memory");
+            if (ep.tma_reduce)
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmD)),
+                           "r"(buf), "r"(n0 + c0), "r"(m0 + quarter * 32)
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmD)),
+                           "r"(buf), "r"(n0 + c0), "r"(m0 + quarter * 32)
+                           : "memory");
             tma_store_commit();
           }
           ++st_cnt;

@@ -130,6 +130,26 @@ def test_gemm_tma_store_epilogue_fp16_bias_activation(M, N, K, act, bn):
     assert err <= 6e-4 * max(1.0, np.abs(ref).max()), f"max abs err {err}"   # one fp16 rounding: 2^-11 relative
 
 
+@pytest.mark.parametrize("M,N,K,bn", [
+    (29316, 1024, 4096, 0),   # ViT-L fc2 at 12 frames: CTA pairs, ragged M
+    (2443, 384, 384, 0),      # ViT-S proj: single CTAs, 128-wide tiles
+    (300, 264, 200, 128),     # ragged N (N % 32 = 8), K tail
+])
+def test_gemm_tma_reduce_epilogue_in_place_residual(M, N, K, bn):
+    """x += acc + bias through cp.reduce.async.bulk.tensor .add.f32 (the ViT proj / fc2 epilogue): the debug entry starts from
+    zeros and launches twice (warm-up + 1), so D = 2 (A W^T + bias) exactly in fp32; nothing outside [M][N] is touched."""
+    rng = np.random.default_rng(M + N + K + 3)
+    A = rng.standard_normal((M, K), dtype=np.float32)
+    W = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N, dtype=np.float32)
+    got = _gemm(A, W, bias, -8, bn) * 0.5
+    assert np.isfinite(got).all()
+    rows = np.unique(np.concatenate([np.arange(0, min(M, 300)), np.arange(max(0, M - 300), M), rng.integers(0, M, 200)]))
+    ref = (torch.from_numpy(_h(A[rows])) @ torch.from_numpy(_h(W)).T + torch.from_numpy(bias)).numpy()
+    err = np.abs(got[rows] - ref).max()
+    assert err <= 2e-4 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
+
+
 @pytest.mark.parametrize("H,W,Cin,Cout,k,relu", [
     (37, 66, 64, 64, 3, 1),
     (19, 33, 384, 64, 3, 0),
