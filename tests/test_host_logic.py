@@ -66,3 +66,12 @@ def test_shard_flag_stripping_and_frame_ranges():
     got = [frame_range(r, 3, 100, 1) for r in range(3)]
     assert [g[0] for g in got] == [0] + [g[1] for g in got[:-1]] and got[-1][1] == 100   # contiguous cover of [0, 100)
     assert got[0][2] == 0 and all(g[2] == g[0] - 1 for g in got[1:])                      # halo frame
+
+def test_mask_band_precision_flag_selects_the_engine_variant():
+    """bands/mask_mmdet.py --precision: exact (default, the whole network fp32-class) / mixed / fast -> engine variant names."""
+    from bands import mask_mmdet as band
+    p = band.build_parser()
+    assert p.parse_args(["-i", "x.png"]).precision == "exact"
+    for flag, variant in (("exact", "r101-exact"), ("mixed", "r101"), ("fast", "r101-fast")):
+        a = p.parse_args(["-i", "x.png", "--precision", flag])
+        assert "r101" + {"fast": "-fast", "exact": "-exact"}.get(a.precision, "") == variant
