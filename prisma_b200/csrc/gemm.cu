@@ -333,7 +333,9 @@ int gemm_run(const GemmLaunch& g, cudaStream_t stream) {
   // 96 registers ptxas then allocates).  Default: 16 for the transposed / narrow tiles, 8 for the 256-wide ones;
   // PRISMA_GEMM_EW=8 / 16 forces one value everywhere.
   static const int ew_env = [] { const char* e = getenv("PRISMA_GEMM_EW"); return e ? atoi(e) : 0; }();
-  const int ew = ew_env ? ew_env : ((g.swap || (g.cg == 1 && g.bn <= 128)) ? 16 : 8);
+  static const int ew_narrow = [] { const char* e = getenv("PRISMA_GEMM_EW_NARROW"); return e ? atoi(e) : 16; }();  // 8 / 12 / 16
+  static const int ew_wide = [] { const char* e = getenv("PRISMA_GEMM_EW_WIDE"); return e ? atoi(e) : 8; }();
+  const int ew = ew_env ? ew_env : ((g.swap || (g.cg == 1 && g.bn <= 128)) ? ew_narrow : ew_wide);
   if (ew == 16 && !g.tma_store) {
     if (g.swap) return launch_bn<128, 1, false, false, false, true, 16>(g, stream);
     if (g.cg == 2 && g.bn == 256) return launch_bn<256, 2, false, false, false, false, 16>(g, stream);
@@ -342,6 +344,17 @@ int gemm_run(const GemmLaunch& g, cudaStream_t stream) {
         case 256: return launch_bn<256, 1, false, false, false, false, 16>(g, stream);
         case 128: return launch_bn<128, 1, false, false, false, false, 16>(g, stream);
         case 64: return launch_bn<64, 1, false, false, false, false, 16>(g, stream);
+      }
+    }
+  }
+  if (ew == 12 && !g.tma_store) {
+    if (g.swap) return launch_bn<128, 1, false, false, false, true, 12>(g, stream);
+    if (g.cg == 2 && g.bn == 256) return launch_bn<256, 2, false, false, false, false, 12>(g, stream);
+    if (g.cg == 1) {
+      switch (g.bn) {
+        case 256: return launch_bn<256, 1, false, false, false, false, 12>(g, stream);
+        case 128: return launch_bn<128, 1, false, false, false, false, 12>(g, stream);
+        case 64: return launch_bn<64, 1, false, false, false, false, 12>(g, stream);
       }
     }
   }

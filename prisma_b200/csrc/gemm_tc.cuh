@@ -134,8 +134,9 @@ struct GemmArgs {
 // per FLOP; the operand bytes per FLOP drop by a quarter.
 // EW: epilogue warps (EW / 4 per TMEM lane quarter, taking every (EW / 4)-th 32-column chunk).  The epilogue is latency-bound
 // (ncu on fc1: issue slots 25 % busy, long-scoreboard / wait stalls) and paces the kernel, so the fp16 kernels can
-// run 16 of them: half the chunks per warp; the register cap drops to 112 per thread and one operand stage is given up for
-// the staging buffers.
+// run 16 of them: half the chunks per warp; one operand stage is given up for the staging buffers and the register cap
+// drops: 18 warps put 5 on one scheduler's 16 K registers = 96 per thread (spills 100-280 bytes), 14 warps (EW = 12) keep 128
+// (spills 40-64 bytes).
 template <int BN, int CG = 1, bool TMAST = false, bool SWAP = false, int EW = GEMM_EPI_WARPS>  // CG = CTAs per MMA (cta_group): 2 = a CTA pair computes a 256 x BN tile, each loading half of W
 struct GemmCfg {                                   // TMAST: TMA-store epilogue (double-buffered staging, one operand stage fewer)
   static constexpr int A_ROWS = SWAP ? 256 : GEMM_BM;   // activation rows per tile and CTA
@@ -304,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmD,
                const __grid_constant__ GemmArgs args) {
   static_assert(!SWAP || (BN == 128 && CG == 1 && !TMAST && !TF32 && !XACC), "SWAP: 128 output channels x 256 pixel rows, fp16, one CTA");
-  static_assert(EW == 8 || (EW == 16 && !TMAST && !TF32 && !XACC), "16 epilogue warps: the plain fp16 kernels only");
+  static_assert(EW == 8 || ((EW == 12 || EW == 16) && !TMAST && !TF32 && !XACC), "12 / 16 epilogue warps: the plain fp16 kernels only");
   using Cfg = GemmCfg<BN, CG, TMAST, SWAP, EW>;
   constexpr int ACC = Cfg::ACC_COLS;
   constexpr int CSTEP = 32 * (EW / 4);  // column distance between the chunks one warp takes
