@@ -10,4 +10,4 @@ timeout 900 compute-sanitizer --tool memcheck --error-exitcode 99 --print-limit 
 echo "sanitizer corr rc=$?" >> gpurun_out/r2c40_sanitizer_corr.log
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 99 --print-limit 20 python -m pytest tests/test_mask_gpu.py -m gpu -q -k "tiny_exact" > gpurun_out/r2c40_sanitizer_mask.log 2>&1
 echo "sanitizer mask rc=$?" >> gpurun_out/r2c40_sanitizer_mask.log
-tail -5 gpurun_out/r2c40_sanitizer_gemm.log gpurun_out/r2c40_sanitizer_corr.log gpurun_out/r2c40_sanitizer_mask.log
+for f in gemm corr mask; do tail -5 gpurun_out/r2c40_sanitizer_$f.log; done
