@@ -112,7 +112,7 @@ def cpu_reference_step(n_frames, threads):
     import torch
     from oracle import da as oda
     from oracle import raft as oraft
-    from oracle.weights import make_da_weights, make_raft_weights
+    from prisma_b200.seeded_weights import make_da_weights, make_raft_weights
     torch.set_num_threads(threads)
     sd, rsd = make_da_weights(ENCODER, 0), make_raft_weights(0)
     frames = make_frames(n_frames + 1, H, W, 0)

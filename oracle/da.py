@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .weights import DA_CONFIGS
+from prisma_b200.seeded_weights import DA_CONFIGS
 
 IMAGENET_MEAN = np.array([0.485, 0.456, 0.406])  # depth_anything.py:72
 IMAGENET_STD = np.array([0.229, 0.224, 0.225])

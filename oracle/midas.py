@@ -23,7 +23,7 @@ import torch
 import torch.nn.functional as F
 
 from .da import _conv, _fusion, _ident, _linear, heat_to_rgb
-from .weights import MIDAS_CONFIGS
+from prisma_b200.seeded_weights import MIDAS_CONFIGS
 
 
 def midas_get_size(width, height, target=384, multiple=32):

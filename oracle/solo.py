@@ -21,7 +21,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .weights import SOLO_CONFIGS
+from prisma_b200.seeded_weights import SOLO_CONFIGS
 
 MEAN = np.array([123.675, 116.28, 103.53], np.float32)  # _base_/datasets/coco_instance.py:4-5 (RGB order, to_rgb=True)
 STD = np.array([58.395, 57.12, 57.375], np.float32)

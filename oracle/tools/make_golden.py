@@ -3,7 +3,7 @@
 Runs ONLY in the authoring container (needs /root/reference).  It
   1. imports the reference modules read-only (PYTHONPATH=/root/reference/bands, cwd
      /root/reference because d_anything/dpt.py:147 uses a relative torch.hub path),
-  2. loads oracle.weights' seeded state_dict into them (strict=True -> names/shapes pinned),
+  2. loads prisma_b200.seeded_weights' seeded state_dict into them (strict=True -> names/shapes pinned),
   3. checks every oracle stage against the reference module's output on seeded inputs,
   4. writes small fixtures to tests/golden/*.npz (inputs + reference outputs) that the
      `-m "not gpu"` tests replay against the oracle and the `-m gpu` tests against CUDA.
@@ -24,8 +24,8 @@ import numpy as np
 import torch
 
 from oracle import da as oda
-from oracle.weights import make_da_weights, DA_CONFIGS
-from oracle.frames import synthetic_frame
+from prisma_b200.seeded_weights import make_da_weights, DA_CONFIGS
+from prisma_b200.synthetic import synthetic_frame
 
 GOLD = os.path.join(REPO, "tests", "golden")
 os.makedirs(GOLD, exist_ok=True)
@@ -125,7 +125,7 @@ def golden_raft():
     from common import encode as renc
     from common.flow import InputPadder
     from oracle import raft as oraft
-    from oracle.weights import make_raft_weights
+    from prisma_b200.seeded_weights import make_raft_weights
     sd = make_raft_weights(0)
     m = RAFT(argparse.Namespace(small=False, mixed_precision=False, alternate_corr=False)).eval()
     print("[raft] load_state_dict:", m.load_state_dict(sd, strict=True))
@@ -216,7 +216,7 @@ def golden_zoe(encoder="vits", H=240, W=320):
     from patchfusion.zoedepth.models.base_models.dpt_dinov2.dpt import DPT_DINOv2
     import common.encode as renc
     from oracle import zoe as ozoe
-    from oracle.weights import make_zoe_weights, ZOE_CONFIG
+    from prisma_b200.seeded_weights import make_zoe_weights, ZOE_CONFIG
 
     cfg = get_org_config("zoedepth", "eval", dataset=None)
     for k in ("n_bins", "bin_embedding_dim", "n_attractors", "attractor_alpha", "attractor_gamma", "min_temp", "max_temp"):
@@ -380,7 +380,7 @@ def _load_vendored_solo_head():
 def golden_solo():
     """SOLOv2 head + decode of oracle/solo.py against the vendored reference sources (mmcv primitives stubbed)."""
     from oracle import solo as osolo
-    from oracle.weights import make_solo_weights, SOLO_CONFIGS
+    from prisma_b200.seeded_weights import make_solo_weights, SOLO_CONFIGS
     mod, nms, resnet_mod, fpn_mod = _load_vendored_solo_head()
     c = SOLO_CONFIGS["tiny"]
     cfgd = dict(nms_pre=500, score_thr=0.1, mask_thr=0.5, filter_thr=0.05, kernel="gaussian", sigma=2.0, max_per_img=100)

@@ -6,8 +6,8 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import da as oda
-from oracle.weights import make_da_weights
-from oracle.frames import synthetic_frame
+from prisma_b200.seeded_weights import make_da_weights
+from prisma_b200.synthetic import synthetic_frame
 
 enc = sys.argv[1] if len(sys.argv) > 1 else "vits"
 H, W = (480, 640) if enc == "vits" else (720, 1280)

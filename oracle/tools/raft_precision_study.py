@@ -5,8 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import numpy as np, torch
 import torch.nn.functional as TF
 from oracle import raft as oraft
-from oracle.weights import make_raft_weights
-from oracle.frames import synthetic_frame
+from prisma_b200.seeded_weights import make_raft_weights
+from prisma_b200.synthetic import synthetic_frame
 
 torch.set_grad_enabled(False)
 sd = make_raft_weights(0)

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from PIL import Image
 
 from . import da as oda
-from .weights import DA_CONFIGS, ZOE_CONFIG
+from prisma_b200.seeded_weights import DA_CONFIGS, ZOE_CONFIG
 
 MEAN = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)  # PrepForMidas (base_models/depth_anything.py:183-184)
 STD = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)

@@ -44,7 +44,7 @@ def test_band_cli_matches_reference_flags():
 @pytest.mark.gpu
 def test_process_runs_band_into_prisma_folder(tmp_path):
     import cv2
-    from oracle.frames import synthetic_frame
+    from prisma_b200.synthetic import synthetic_frame
     src = str(tmp_path / "clip.mp4")
     w = cv2.VideoWriter(src, cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
     for t in range(3):
@@ -73,7 +73,7 @@ def test_process_runs_band_into_prisma_folder(tmp_path):
 def test_flow_band_masks_flo_and_u16_png(tmp_path):
     """--mask / --subpath / --subpath_mask outputs of bands/flow_raft.py (reference :60-66, common/flow.py:64-98)."""
     import cv2
-    from oracle.frames import synthetic_frame
+    from prisma_b200.synthetic import synthetic_frame
     folder = tmp_path / "clip"
     folder.mkdir()
     src = str(folder / "rgba.mp4")
@@ -118,7 +118,7 @@ def test_midas_band_cli_matches_reference_flags():
 @pytest.mark.gpu
 def test_midas_band_writes_video_csv_and_frames(tmp_path):
     import cv2
-    from oracle.frames import synthetic_frame
+    from prisma_b200.synthetic import synthetic_frame
     folder = tmp_path / "clip"
     folder.mkdir()
     w = cv2.VideoWriter(str(folder / "rgba.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
@@ -156,7 +156,7 @@ def test_mask_band_cli_matches_reference_flags():
 @pytest.mark.gpu
 def test_mask_band_writes_mask_video_and_colmap_frames(tmp_path):
     import cv2
-    from oracle.frames import synthetic_frame
+    from prisma_b200.synthetic import synthetic_frame
     folder = tmp_path / "clip"
     folder.mkdir()
     w = cv2.VideoWriter(str(folder / "rgba.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
@@ -182,7 +182,7 @@ def test_mask_band_writes_mask_video_and_colmap_frames(tmp_path):
 def test_depth_band_metric_path(tmp_path):
     """--metric outdoor (what the reference's process.py passes by default): ZoeDepth head, no flip in the encode."""
     import cv2
-    from oracle.frames import synthetic_frame
+    from prisma_b200.synthetic import synthetic_frame
     folder = tmp_path / "clip"
     folder.mkdir()
     w = cv2.VideoWriter(str(folder / "rgba.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
@@ -206,7 +206,7 @@ def test_depth_band_metric_path(tmp_path):
 def test_depth_band_sharded_over_two_workers_equals_single(tmp_path):
     """--gpus 2 (both workers on device 0 here): frame-range workers + parent assembly == the single-process run."""
     import cv2
-    from oracle.frames import synthetic_frame
+    from prisma_b200.synthetic import synthetic_frame
     outs = {}
     for tag, extra in (("one", []), ("two", ["--gpus", "2", "--device-list", "0,0"])):
         folder = tmp_path / tag
@@ -233,7 +233,7 @@ def test_depth_band_sharded_over_two_workers_equals_single(tmp_path):
 
 def _clip_folder(folder, n):
     import cv2
-    from oracle.frames import synthetic_frame
+    from prisma_b200.synthetic import synthetic_frame
     folder.mkdir()
     w = cv2.VideoWriter(str(folder / "rgba.mp4"), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 240))
     for t in range(n):

@@ -8,8 +8,8 @@ import pytest
 import torch
 
 from oracle import da as oda
-from oracle.frames import synthetic_frame
-from oracle.weights import make_da_weights
+from prisma_b200.synthetic import synthetic_frame
+from prisma_b200.seeded_weights import make_da_weights
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3

@@ -12,8 +12,8 @@ import pytest
 import torch
 
 from oracle import solo as osolo
-from oracle.frames import synthetic_frame
-from oracle.weights import SOLO_CONFIGS, make_solo_weights
+from prisma_b200.synthetic import synthetic_frame
+from prisma_b200.seeded_weights import SOLO_CONFIGS, make_solo_weights
 
 
 def rel(a, b):

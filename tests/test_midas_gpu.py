@@ -9,8 +9,8 @@ import pytest
 import torch
 
 from oracle import midas as om
-from oracle.frames import synthetic_frame
-from oracle.weights import make_midas_weights
+from prisma_b200.synthetic import synthetic_frame
+from prisma_b200.seeded_weights import make_midas_weights
 
 
 def test_midas_size_arithmetic_and_pos_embed():

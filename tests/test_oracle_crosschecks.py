@@ -11,7 +11,7 @@ import torchvision
 
 from oracle import midas as omidas
 from oracle import solo as osolo
-from oracle.weights import make_midas_weights, make_solo_weights
+from prisma_b200.seeded_weights import make_midas_weights, make_solo_weights
 
 
 def test_solo_backbone_equals_torchvision_resnet():

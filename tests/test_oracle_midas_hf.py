@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import midas as omidas
-from oracle.weights import MIDAS_CONFIGS, make_midas_weights
+from prisma_b200.seeded_weights import MIDAS_CONFIGS, make_midas_weights
 
 transformers = pytest.importorskip("transformers")
 

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from oracle import raft as oraft
-from oracle.frames import synthetic_frame
+from prisma_b200.synthetic import synthetic_frame
 
 
 def test_raft_oracle_stages(golden_dir):

@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from oracle import solo as osolo
-from oracle.weights import SOLO_CONFIGS, make_solo_weights
+from prisma_b200.seeded_weights import SOLO_CONFIGS, make_solo_weights
 
 
 def test_solo_oracle_matches_vendored_mmdet_fixture(golden_dir):

@@ -6,7 +6,7 @@ import numpy as np
 
 from oracle import da as oda
 from oracle import zoe as ozoe
-from oracle.weights import make_zoe_weights
+from prisma_b200.seeded_weights import make_zoe_weights
 
 
 def test_zoe_oracle_matches_reference_fixture(golden_dir):

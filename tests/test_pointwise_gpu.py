@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import da as oda
-from oracle.frames import synthetic_frame
+from prisma_b200.synthetic import synthetic_frame
 from prisma_b200._lib import check, fptr, lib, u8ptr
 
 pytestmark = pytest.mark.gpu

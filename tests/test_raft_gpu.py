@@ -7,8 +7,8 @@ import pytest
 import torch
 
 from oracle import raft as oraft
-from oracle.frames import synthetic_frame
-from oracle.weights import make_raft_weights
+from prisma_b200.synthetic import synthetic_frame
+from prisma_b200.seeded_weights import make_raft_weights
 
 pytestmark = pytest.mark.gpu
 
@@ -169,8 +169,8 @@ def test_video_pass_reuses_features_bit_identically():
     engine instead of being recomputed, equals a fresh full pass over (f1, f2) bit for bit; reuse_prev means "prev is the last
     call's curr" -- after (f1, f2) it makes the engine pair f2 (not the f0 handed in) with the new frame."""
     from prisma_b200.flow import RaftFlowEngine
-    from oracle.frames import synthetic_frame
-    from oracle.weights import make_raft_weights
+    from prisma_b200.synthetic import synthetic_frame
+    from prisma_b200.seeded_weights import make_raft_weights
     eng = RaftFlowEngine(make_raft_weights(0), iterations=4, scale=0.75)
     f = [synthetic_frame(240, 320, t) for t in range(3)]
     fresh = eng.infer_pair(f[1], f[2], want_rgb=True)                       # full pass; the cache now holds f2

@@ -9,8 +9,8 @@ from PIL import Image
 
 from oracle import da as oda
 from oracle import zoe as ozoe
-from oracle.frames import synthetic_frame
-from oracle.weights import make_zoe_weights
+from prisma_b200.synthetic import synthetic_frame
+from prisma_b200.seeded_weights import make_zoe_weights
 
 
 def rel(a, b):

@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oracle import da as oda
-from oracle.weights import make_da_weights
+from prisma_b200.seeded_weights import make_da_weights
 from prisma_b200.synthetic import synthetic_frame
 sd = make_da_weights("vitl", 0); f = synthetic_frame(720, 1280, 0)
 for t in (8, 16, 32, 64, 128):
