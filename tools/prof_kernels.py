@@ -46,3 +46,11 @@ if which in ("gemm_swap",):
     b = np.zeros(N, np.float32); D = np.empty((M, N), np.float32); ms = C.c_float()
     assert l.prisma_debug_gemm(0, fptr(A), fptr(W), fptr(b), fptr(D), M, N, K, -2, 0, 3, C.byref(ms)) == 0
     print("gemm swap", M, N, K, "ms", ms.value, "TF", 2.0 * M * N * K / ms.value / 1e9)
+if which in ("gemm_red",):
+    # fc2 of a 12-frame pass through the TMA reduce-add epilogue (x += acc + bias in place, the add done by the L2): act -8
+    M, N, K = 29316, 1024, 4096
+    A = rng.standard_normal((M, K), dtype=np.float32)
+    W = (rng.standard_normal((N, K), dtype=np.float32) / 64).astype(np.float32)
+    b = np.zeros(N, np.float32); D = np.empty((M, N), np.float32); ms = C.c_float()
+    assert l.prisma_debug_gemm(0, fptr(A), fptr(W), fptr(b), fptr(D), M, N, K, -8, 0, 3, C.byref(ms)) == 0
+    print("gemm fc2 tma reduce-add", M, N, K, "ms", ms.value, "TF", 2.0 * M * N * K / ms.value / 1e9)
